@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the fractal transform + quantization hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One step = one pass of the hot path over one frame per GPU: the fused forward transform +
+quantization (encode) followed by the fused dequantization + inverse transform (decode).
+Workload: BASELINE.json configs[1], a synthetic 4096x4096 8-bit RGB image (one per GPU; frames
+are independent, so N GPUs = N frames, weak scaling, no data-path collective).
+
+Prints ONE JSON line (rank 0).  `value` is device-resident MPix/s, `e2e` the same metric through
+the host-buffer C-ABI entry points (pinned host memory, copies inside the timed region),
+`roofline` the dominant kernel against the measured HBM copy bandwidth, `cpu_baseline` the CPU
+oracle (single thread, like the reference) on the same image.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "MPix/s fractal transform+quant (enc/dec)"
+UNIT = "MPix/s"
+W, H, C = 4096, 4096, 3
+SMALLEST_LAYER_DIVISOR = 4  # q[8] = q[9] = 4: "dividing the smallest layer of fractals" (README.md:12)
+BYTES_PER_SAMPLE = 5        # u8 pixel + i32 coefficient, either direction
+N_SETS = 4                  # rotating buffer sets: 4 x (50 + 201 + 50 MB) = 1.2 GB >> 126 MB of L2
+
+
+def quant_matrix() -> np.ndarray:
+    q = np.ones(32, np.int32)
+    q[8] = q[9] = SMALLEST_LAYER_DIVISOR
+    return q
+
+
+def workload_config(n_gpus: int) -> dict:
+    return {
+        "workload": f"{W}x{H}x{C} u8 synthetic image (BASELINE.json configs[1]); step = fused transform+quant encode "
+                    f"then fused dequant+inverse decode of one frame per GPU",
+        "frames_per_gpu": 1,
+        "global_frames": n_gpus,
+        "depth": 9,
+        "quant": f"q[8]=q[9]={SMALLEST_LAYER_DIVISOR}, other layers 1; decode divides again like quantization.rs:37",
+        "l2": f"inputs rotate over {N_SETS} buffer sets (1.2 GB) so every timed launch reads cold HBM",
+        "parallelism": f"frames sharded over {n_gpus} GPU(s), no collective",
+    }
+
+
+def measured_peak_gbs() -> tuple[float, str]:
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel: str):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+    def __init__(self, index: int):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "50"], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, smax, reasons = [], [], set()
+        for line in self.tmp.read().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(self.NAMES, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        self.tmp.close()
+        os.unlink(self.tmp.name)
+        # samples taken while the GPU was busy: the load phase (pre-heat + warm-up + timed steps)
+        busy = sorted(sm)[len(sm) // 4:] if sm else []
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def synthetic_image(seed: int) -> np.ndarray:
+    return np.random.Generator(np.random.PCG64(seed)).integers(0, 256, size=(H, W, C), dtype=np.uint8)
+
+
+def cpu_pass(O, img, centers, some, q, nthreads, tiles=None, coef_buf=None, out_buf=None) -> float:
+    """One oracle pass (transform+quant, then dividing dequant+inverse) over `tiles`; seconds."""
+    cen = centers if tiles is None else centers[tiles]
+    sm = None if some is None else (some if tiles is None else some[tiles])
+    t0 = time.perf_counter()
+    coef = O.encode_tiles(img, cen, q, nthreads=nthreads, out=coef_buf)
+    O.decode_tiles(cen, coef, sm, q, H, W, nthreads=nthreads, out=out_buf)
+    return time.perf_counter() - t0
+
+
+def run_reference(args, rank: int) -> None:
+    """--impl reference: the reference's CPU path.  The reference is pure Rust and cannot be built
+    here (no cargo/rustc), so this times the C oracle restating it, on all host threads."""
+    if rank != 0:
+        return
+    from frave_b200 import capi
+    from oracle import c_oracle as O
+
+    threads = host_threads()
+    q = quant_matrix()
+    img = synthetic_image(2)
+    plan = capi.Plan(W, H, C, device=-1)  # host-only plan: tile list, no GPU involved
+    centers = plan.centers()
+    n_tiles = len(centers)
+    # calibrate, then bound the per-step sample so that the whole run stays within ~90 s
+    probe = np.arange(min(2048, n_tiles))
+    t_probe = cpu_pass(O, img, centers, None, q, threads, probe)
+    per_tile = t_probe / len(probe)
+    budget = 90.0 / max(1, args.steps + args.warmup)
+    sample = int(max(256, min(n_tiles, budget / per_tile)))
+    tiles = np.linspace(0, n_tiles - 1, sample).astype(np.int64)
+    coef_buf = np.empty((sample, C, 512), np.int32)
+    out_buf = np.zeros((H, W, C), np.uint8)
+    for _ in range(args.warmup):
+        cpu_pass(O, img, centers, None, q, threads, tiles, coef_buf, out_buf)
+    t = 0.0
+    for _ in range(args.steps):
+        t += cpu_pass(O, img, centers, None, q, threads, tiles, coef_buf, out_buf)
+    mpix = sample * 512 * args.steps / t / 1e6
+    desc = f"{sample} of {n_tiles} tiles ({sample * 512 / 1e6:.2f} MPix) of the {W}x{H}x{C} image per step"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": mpix, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "i32", "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": mpix, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+        "e2e": {"value": mpix, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference is Rust and unbuildable here (no cargo); timed the C oracle port of its hot path, "
+                "tiles split over all host threads",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args, rank: int, local_rank: int, world: int) -> None:
+    import torch
+    import torch.distributed as dist
+
+    from frave_b200 import capi
+
+    if capi.device_count() < 1:
+        raise RuntimeError("bench.py needs a CUDA device: libfri_cuda has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    q = quant_matrix()
+    plan = capi.Plan(W, H, C, device=local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # ---- buffers: N_SETS rotating sets, synthetic pixels generated per rank
+    img0 = synthetic_image(2 + rank)
+    px = [torch.from_numpy(img0).to(dev)]
+    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    for _ in range(1, N_SETS):
+        px.append(torch.randint(0, 256, (H, W, C), generator=gen, device=dev, dtype=torch.int32).to(torch.uint8))
+    coefs = [torch.empty(plan.coef_shape, dtype=torch.int32, device=dev) for _ in range(N_SETS)]
+    outs = [torch.empty((H, W, C), dtype=torch.uint8, device=dev) for _ in range(N_SETS)]
+
+    # sanity (untimed): encode -> decode is the identity at q == 1
+    plan.encode_device(px[0].data_ptr(), 1, coefs[0].data_ptr(), None, stream)
+    plan.decode_device(coefs[0].data_ptr(), 1, outs[0].data_ptr(), None, False, stream)
+    torch.cuda.synchronize()
+    if not torch.equal(px[0], outs[0]):
+        raise RuntimeError("sanity check failed: encode -> decode is not lossless at q == 1")
+    for s in range(N_SETS):
+        plan.encode_device(px[s].data_ptr(), 1, coefs[s].data_ptr(), q, stream)
+    torch.cuda.synchronize()
+
+    launches = 0
+
+    def step(i: int, ev=None) -> None:
+        nonlocal launches
+        a, b = i % N_SETS, (i + N_SETS // 2) % N_SETS
+        if ev:
+            ev[0].record()
+        plan.encode_device(px[a].data_ptr(), 1, coefs[a].data_ptr(), q, stream)
+        launches += plan.last_launches
+        if ev:
+            ev[1].record()
+        plan.decode_device(coefs[b].data_ptr(), 1, outs[b].data_ptr(), q, False, stream)
+        launches += plan.last_launches
+        if ev:
+            ev[2].record()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t_end = time.perf_counter() + 1.0  # pre-heat so clocks are sampled under the same load
+    i = 0
+    while time.perf_counter() < t_end:
+        for _ in range(50):
+            step(i)
+            i += 1
+        torch.cuda.synchronize()
+    for k in range(args.warmup):
+        step(k)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+    events = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    start.record()
+    for k in range(args.steps):
+        step(k, events[k])
+    end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if sampler else None
+    elapsed_ms = start.elapsed_time(end)
+    enc_ms = statistics.fmean(e[0].elapsed_time(e[1]) for e in events)
+    dec_ms = statistics.fmean(e[1].elapsed_time(e[2]) for e in events)
+    timed_launches = launches
+
+    # ---- end to end through the host-buffer C ABI: pinned host memory, H2D and D2H in the timed region
+    e2e_steps = max(2, min(args.steps, 8))
+    px_h = capi.PinnedBuffer((1, H, W, C), np.uint8)
+    cf_h = capi.PinnedBuffer((1,) + plan.coef_shape, np.int32)
+    out_h = capi.PinnedBuffer((1, H, W, C), np.uint8)
+    px_h.array[0] = img0
+    plan.encode(px_h.array, q, out=cf_h.array)  # warm-up (allocates the plan's device slots)
+    plan.decode(cf_h.array, q, out=out_h.array)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        plan.encode(px_h.array, q, out=cf_h.array)
+        plan.decode(cf_h.array, q, out=out_h.array)
+    e2e_s = time.perf_counter() - t0
+    h2d = px_h.array.nbytes + cf_h.array.nbytes
+    d2h = cf_h.array.nbytes + out_h.array.nbytes
+
+    if world > 1:
+        t = torch.tensor([elapsed_ms, e2e_s, enc_ms, dec_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms, e2e_s, enc_ms, dec_ms = (float(x) for x in t.tolist())
+        dist.barrier()
+
+    if rank == 0:
+        pix_step = W * H * world  # pixels through encode+decode per step, all GPUs
+        value = pix_step * args.steps / (elapsed_ms * 1e-3) / 1e6
+        e2e_value = pix_step * e2e_steps / e2e_s / 1e6
+        peak, peak_src = measured_peak_gbs()
+        alg_bytes = W * H * C * BYTES_PER_SAMPLE
+
+        def roof(ms: float, kernel: str) -> dict:
+            ach = alg_bytes / (ms * 1e-3) / 1e9
+            return {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": ncu_traffic(kernel), "algorithmic_bytes": alg_bytes, "avg_launch_ms": ms,
+                    "peak_source": peak_src}
+
+        r_enc, r_dec = roof(enc_ms, "fri_encode_kernel<3,u8>"), roof(dec_ms, "fri_decode_kernel<3,u8>")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "i32", "data": "synthetic", "config": workload_config(world),
+            "encode_mpix_s": W * H * world / (enc_ms * 1e-3) / 1e6, "decode_mpix_s": W * H * world / (dec_ms * 1e-3) / 1e6,
+            "roofline": r_enc if enc_ms >= dec_ms else r_dec, "roofline_encode": r_enc, "roofline_decode": r_dec,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "api": "fri_encode_tq + fri_decode_tq (host buffers, pinned)"},
+            "gpu_launches": timed_launches, "clocks": clocks, "launch": plan.launch_info(),
+        }
+        if world == 1:
+            from oracle import c_oracle as O
+            centers = plan.centers()
+            coef_buf = np.empty(plan.coef_shape, np.int32)
+            out_buf = np.zeros((H, W, C), np.uint8)
+            t_cpu, passes = 0.0, 0
+            while t_cpu < 10.0:
+                t_cpu += cpu_pass(O, img0, centers, None, q, 1, None, coef_buf, out_buf)
+                passes += 1
+            line["cpu_baseline"] = {
+                "value": W * H * passes / t_cpu / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
+                "sample": f"{passes} full pass(es) of the same {W}x{H}x{C} image (encode+decode), C oracle, 1 thread "
+                          f"(the reference is single-threaded)"}
+        print(json.dumps(line), flush=True)
+    px_h.free(); cf_h.free(); out_h.free()
+    plan.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("launch N > 1 with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...")
+    run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,245 @@
+"""ctypes binding of libfri_cuda.so — the same C ABI (include/fri_cuda.h) that the `libfri-cuda`
+Rust crate binds.  There is no CPU fallback: if the shared library is missing it is built with
+nvcc, and if that is impossible importing callers get a RuntimeError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+FRI_OK = 0
+FRI_E_INVALID = -1
+FRI_E_CUDA = -2
+FRI_E_NOMEM = -3
+FRI_E_UNSUPPORTED = -4
+FRI_DEQUANT_DIVIDE = 0
+FRI_DEQUANT_MULTIPLY = 1
+FRI_BASE_DEPTH = 9
+
+# every symbol include/fri_cuda.h declares: (name, restype, argtypes)
+_P = C.c_void_p
+_SYMBOLS = [
+    ("fri_version", C.c_char_p, []),
+    ("fri_last_error", C.c_char_p, []),
+    ("fri_device_count", C.c_int, []),
+    ("fri_plan_create", C.c_int, [C.POINTER(_P), C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
+    ("fri_plan_destroy", None, [_P]),
+    ("fri_plan_num_tiles", C.c_uint32, [_P]),
+    ("fri_plan_num_built", C.c_uint32, [_P]),
+    ("fri_plan_num_full_tiles", C.c_uint32, [_P]),
+    ("fri_plan_coefs_per_frame", C.c_uint64, [_P]),
+    ("fri_plan_pixels_covered", C.c_uint64, [_P]),
+    ("fri_plan_launch_info", C.c_int, [_P, _P]),
+    ("fri_plan_centers", C.c_int, [_P, _P]),
+    ("fri_plan_masks", C.c_int, [_P, _P]),
+    ("fri_encode_tq_device", C.c_int, [_P, _P, C.c_uint32, _P, _P, _P]),
+    ("fri_decode_tq_device", C.c_int, [_P, _P, C.c_uint32, _P, C.c_int, _P, _P]),
+    ("fri_encode_tq", C.c_int, [_P, _P, C.c_uint32, _P, _P]),
+    ("fri_decode_tq", C.c_int, [_P, _P, C.c_uint32, _P, C.c_int, _P]),
+    ("fri_host_alloc", C.c_int, [C.POINTER(_P), C.c_size_t]),
+    ("fri_host_free", None, [_P]),
+    ("fri_plan_last_launches", C.c_uint32, [_P]),
+    ("fri_quant_divide", C.c_int32, [C.c_int32, C.c_int32]),
+]
+SYMBOL_NAMES = [s[0] for s in _SYMBOLS]
+
+_lib = None
+
+
+class FriError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"libfri_cuda error {code}: {message}")
+        self.code = code
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def lib() -> C.CDLL:
+    """Loads (building first if necessary) libfri_cuda.so.  Never falls back to a CPU path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_build.LIB_PATH):
+            _build.build()
+        L = C.CDLL(_build.LIB_PATH)
+        for name, res, args in _SYMBOLS:
+            fn = getattr(L, name)  # AttributeError if the library does not export it
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _check(rc: int) -> None:
+    if rc != FRI_OK:
+        raise FriError(rc, lib().fri_last_error().decode("utf-8", "replace"))
+
+
+def version() -> str:
+    return lib().fri_version().decode()
+
+
+def device_count() -> int:
+    return int(lib().fri_device_count())
+
+
+def quant_divide(value: int, q: int) -> int:
+    """value / q with the kernels' multiply-high division routine (host evaluation, for tests)."""
+    return int(lib().fri_quant_divide(int(value), int(q)))
+
+
+def _q_array(q):
+    if q is None:
+        return None, None
+    qa = np.ascontiguousarray(q, dtype=np.int32)
+    if qa.shape != (32,):
+        raise ValueError("the quantization matrix has 32 entries (quantization.rs:3-5)")
+    return qa, qa.ctypes.data
+
+
+class PinnedBuffer:
+    """Page-locked host memory from fri_host_alloc, viewed as a numpy array."""
+
+    def __init__(self, shape, dtype):
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = np.dtype(dtype)
+        nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+        ptr = _P()
+        _check(lib().fri_host_alloc(C.byref(ptr), nbytes))
+        self.ptr = ptr.value
+        buf = (C.c_uint8 * max(nbytes, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=nbytes // self.dtype.itemsize).reshape(self.shape)
+
+    def free(self) -> None:
+        if self.ptr:
+            self.array = None
+            lib().fri_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Plan:
+    """fri_plan: lattice + launch geometry for one (width, height, channels, depth, sample size).
+
+    device >= 0 uploads the tables to that CUDA device; device = -1 makes a host-only plan on
+    which only the metadata queries work (compute calls raise FriError(FRI_E_CUDA)).
+    """
+
+    def __init__(self, width: int, height: int, channels: int, depth: int = FRI_BASE_DEPTH, sample_bytes: int = 1,
+                 device: int = 0):
+        self._h = _P()
+        _check(lib().fri_plan_create(C.byref(self._h), device, width, height, channels, depth, sample_bytes))
+        self.width, self.height, self.channels = int(width), int(height), int(channels)
+        self.depth, self.sample_bytes, self.device = int(depth), int(sample_bytes), int(device)
+        L = lib()
+        self.n_tiles = int(L.fri_plan_num_tiles(self._h))
+        self.n_built = int(L.fri_plan_num_built(self._h))
+        self.n_full = int(L.fri_plan_num_full_tiles(self._h))
+        self.coefs_per_frame = int(L.fri_plan_coefs_per_frame(self._h))
+        self.pixels_covered = int(L.fri_plan_pixels_covered(self._h))
+        self.pixel_dtype = np.uint8 if sample_bytes == 1 else np.uint16
+        self.frame_shape = (self.height, self.width, self.channels)
+        self.coef_shape = (self.n_tiles, self.channels, 1 << self.depth)
+
+    def close(self) -> None:
+        if self._h:
+            lib().fri_plan_destroy(self._h)
+            self._h = _P()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ---- metadata -------------------------------------------------------------------------
+    def centers(self) -> np.ndarray:
+        out = np.empty((self.n_tiles, 2), np.int32)
+        _check(lib().fri_plan_centers(self._h, out.ctypes.data))
+        return out
+
+    def mask_words(self) -> np.ndarray:
+        out = np.empty((self.n_tiles, (1 << self.depth) // 32), np.uint32)
+        _check(lib().fri_plan_masks(self._h, out.ctypes.data))
+        return out
+
+    def masks(self) -> np.ndarray:
+        """bool [n_tiles, 2^depth]: coefficient i of tile t is `Some` in the reference."""
+        w = self.mask_words()
+        bits = np.unpackbits(w.view(np.uint8), axis=1, bitorder="little")
+        return bits.astype(bool)
+
+    def launch_info(self) -> dict:
+        info = (C.c_int32 * 16)()
+        _check(lib().fri_plan_launch_info(self._h, C.addressof(info)))
+        keys = ["group_a", "group_b", "region_w", "region_h", "smem_pitch", "smem_bytes", "n_groups", "n_base_tiles",
+                "threads", "chunks_per_row", "depth", "sub_bits"]
+        return {k: int(info[i]) for i, k in enumerate(keys)}
+
+    @property
+    def last_launches(self) -> int:
+        return int(lib().fri_plan_last_launches(self._h))
+
+    # ---- host-buffer entry points -----------------------------------------------------------
+    def _frames(self, pixels: np.ndarray) -> tuple[np.ndarray, int]:
+        px = np.asarray(pixels)
+        if px.dtype != self.pixel_dtype:
+            raise ValueError(f"pixels must be {np.dtype(self.pixel_dtype).name}")
+        if px.shape == self.frame_shape:
+            px = px[None]
+        if px.ndim != 4 or px.shape[1:] != self.frame_shape:
+            raise ValueError(f"pixels must have shape [F]{self.frame_shape}")
+        return np.ascontiguousarray(px), px.shape[0]
+
+    def encode(self, pixels: np.ndarray, q=None, out: np.ndarray | None = None) -> np.ndarray:
+        """HWC pixels [F, H, W, C] -> quantized coefficients int32 [F, n_tiles, C, 2^depth]."""
+        px, n = self._frames(pixels)
+        if out is None:
+            out = np.empty((n,) + self.coef_shape, np.int32)
+        assert out.dtype == np.int32 and out.flags.c_contiguous and out.size == n * self.coefs_per_frame
+        qa, qp = _q_array(q)
+        _check(lib().fri_encode_tq(self._h, px.ctypes.data, n, qp, out.ctypes.data))
+        return out
+
+    def decode(self, coefs: np.ndarray, q=None, multiply: bool = False, out: np.ndarray | None = None) -> np.ndarray:
+        """Quantized coefficients [F, n_tiles, C, 2^depth] -> HWC pixels [F, H, W, C]."""
+        cf = np.ascontiguousarray(coefs, dtype=np.int32)
+        if cf.shape == self.coef_shape:
+            cf = cf[None]
+        if cf.ndim != 4 or cf.shape[1:] != self.coef_shape:
+            raise ValueError(f"coefs must have shape [F]{self.coef_shape}")
+        n = cf.shape[0]
+        if out is None:
+            out = np.empty((n,) + self.frame_shape, self.pixel_dtype)
+        assert out.dtype == self.pixel_dtype and out.flags.c_contiguous and out.shape[1:] == self.frame_shape
+        qa, qp = _q_array(q)
+        mode = FRI_DEQUANT_MULTIPLY if multiply else FRI_DEQUANT_DIVIDE
+        _check(lib().fri_decode_tq(self._h, cf.ctypes.data, n, qp, mode, out.ctypes.data))
+        return out
+
+    # ---- device-resident entry points (raw device pointers, e.g. torch.Tensor.data_ptr()) -----
+    def encode_device(self, d_pixels: int, n_frames: int, d_coefs: int, q=None, stream: int = 0) -> None:
+        qa, qp = _q_array(q)
+        _check(lib().fri_encode_tq_device(self._h, d_pixels, n_frames, qp, d_coefs, stream))
+
+    def decode_device(self, d_coefs: int, n_frames: int, d_pixels: int, q=None, multiply: bool = False,
+                      stream: int = 0) -> None:
+        qa, qp = _q_array(q)
+        mode = FRI_DEQUANT_MULTIPLY if multiply else FRI_DEQUANT_DIVIDE
+        _check(lib().fri_decode_tq_device(self._h, d_coefs, n_frames, qp, mode, d_pixels, stream))

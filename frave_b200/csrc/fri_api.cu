@@ -1,0 +1,370 @@
+// fri_api.cu — the C ABI of libfri_cuda (see include/fri_cuda.h for the contract).
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/fri_cuda.h"
+#include "fri_kernels.cuh"
+#include "fri_plan.h"
+
+using namespace fri;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char *what)
+{
+    return fail(FRI_E_CUDA, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+#define FRI_CUDA(call)                                              \
+    do {                                                            \
+        cudaError_t e__ = (call);                                   \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call);       \
+    } while (0)
+
+constexpr int kSlots = 3;  // frames in flight in the host-buffer entry points
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    void *d_pixels = nullptr;
+    int32_t *d_coefs = nullptr;
+    int32_t *d_dc = nullptr;
+};
+
+}  // namespace
+
+struct fri_plan {
+    Plan plan;
+    int device = -1;
+    DeviceTables tables;
+    void *d_groups = nullptr, *d_tile_unit = nullptr, *d_ownership = nullptr;
+    Slot slots[kSlots];
+    bool slots_ready = false;
+    int32_t *d_dc_shared = nullptr;  // low-pass scratch for the *_device entry points (depth > 9)
+    size_t d_dc_frames = 0;
+    uint32_t last_launches = 0;
+};
+
+namespace {
+
+std::once_flag g_cfg_once[16];
+cudaError_t g_cfg_err[16];
+
+int enter_device(const fri_plan *p)
+{
+    if (!p) return fail(FRI_E_INVALID, "plan is NULL");
+    if (p->device < 0) return fail(FRI_E_CUDA, "plan was created without a device (device < 0): no CPU fallback exists");
+    FRI_CUDA(cudaSetDevice(p->device));
+    return FRI_OK;
+}
+
+int check_q(const int32_t *q)
+{
+    if (!q) return FRI_OK;
+    for (int l = 0; l < 32; ++l)
+        if (q[l] < 1) return fail(FRI_E_INVALID, "quantization matrix entry %d is %d; entries must be >= 1", l, q[l]);
+    return FRI_OK;
+}
+
+size_t dc_elems_per_frame(const Geometry &g)
+{
+    return g.sub_bits > 0 ? ((size_t)g.n_fractals * g.channels) << g.sub_bits : 0;
+}
+
+int ensure_dc(fri_plan *p, size_t frames)
+{
+    const Geometry &g = p->plan.geo;
+    if (g.sub_bits == 0 || frames <= p->d_dc_frames) return FRI_OK;
+    if (p->d_dc_shared) cudaFree(p->d_dc_shared);
+    p->d_dc_shared = nullptr;
+    p->d_dc_frames = 0;
+    FRI_CUDA(cudaMalloc(&p->d_dc_shared, frames * dc_elems_per_frame(g) * sizeof(int32_t)));
+    p->d_dc_frames = frames;
+    return FRI_OK;
+}
+
+int ensure_slots(fri_plan *p)
+{
+    if (p->slots_ready) return FRI_OK;
+    const Geometry &g = p->plan.geo;
+    for (auto &s : p->slots) {
+        FRI_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        FRI_CUDA(cudaMalloc(&s.d_pixels, (size_t)g.frame_bytes + 16));
+        FRI_CUDA(cudaMalloc(&s.d_coefs, (size_t)g.coefs_per_frame * sizeof(int32_t) + 16));
+        if (g.sub_bits > 0) FRI_CUDA(cudaMalloc(&s.d_dc, dc_elems_per_frame(g) * sizeof(int32_t)));
+    }
+    p->slots_ready = true;
+    return FRI_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *fri_version(void) { return "libfri_cuda 0.1.0 sm_100a"; }
+const char *fri_last_error(void) { return g_last_error.c_str(); }
+
+int fri_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int fri_plan_create(fri_plan **out, int device, uint32_t width, uint32_t height, uint32_t channels, uint32_t depth,
+                    uint32_t sample_bytes)
+{
+    if (!out) return fail(FRI_E_INVALID, "out is NULL");
+    *out = nullptr;
+    fri_plan *p = new (std::nothrow) fri_plan;
+    if (!p) return fail(FRI_E_NOMEM, "out of host memory");
+    std::string err;
+    try {
+        err = build_plan(p->plan, width, height, channels, depth, sample_bytes, 0, 0);
+    } catch (const std::bad_alloc &) {
+        delete p;
+        return fail(FRI_E_NOMEM, "out of host memory while building the lattice");
+    }
+    if (!err.empty()) {
+        delete p;
+        return fail(FRI_E_INVALID, "%s", err.c_str());
+    }
+    p->device = device;
+    if (device >= 0) {
+        int n = fri_device_count();
+        if (device >= n) {
+            delete p;
+            return fail(FRI_E_CUDA, "CUDA device %d requested but %d device(s) visible; there is no CPU fallback", device, n);
+        }
+        const Plan &pl = p->plan;
+        const size_t smem = kernel_smem_bytes(pl.geo);
+        if (smem > 227 * 1024) {
+            delete p;
+            return fail(FRI_E_UNSUPPORTED, "group needs %zu bytes of shared memory", smem);
+        }
+        auto upload = [&](void **dst, const void *src, size_t bytes) -> cudaError_t {
+            if (bytes == 0) return cudaSuccess;
+            cudaError_t e = cudaMalloc(dst, bytes);
+            if (e != cudaSuccess) return e;
+            return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+        };
+        cudaError_t e = cudaSetDevice(device);
+        if (e == cudaSuccess && device < 16) {
+            std::call_once(g_cfg_once[device], [&] { g_cfg_err[device] = configure_kernels(); });
+            e = g_cfg_err[device];
+        } else if (e == cudaSuccess) {
+            e = configure_kernels();
+        }
+        if (e == cudaSuccess) e = upload(&p->d_groups, pl.groups.data(), pl.groups.size() * sizeof(GroupDesc));
+        if (e == cudaSuccess && pl.geo.sub_bits > 0)
+            e = upload(&p->d_tile_unit, pl.tile_unit.data(), pl.tile_unit.size() * sizeof(uint32_t));
+        if (e == cudaSuccess) e = upload(&p->d_ownership, pl.ownership.data(), pl.ownership.size() * sizeof(uint32_t));
+        if (e != cudaSuccess) {
+            fri_plan_destroy(p);
+            return cuda_fail(e, "uploading the plan tables");
+        }
+        p->tables.groups = static_cast<const GroupDesc *>(p->d_groups);
+        p->tables.tile_unit = static_cast<const uint32_t *>(p->d_tile_unit);
+        p->tables.ownership = static_cast<const uint32_t *>(p->d_ownership);
+    }
+    *out = p;
+    return FRI_OK;
+}
+
+void fri_plan_destroy(fri_plan *p)
+{
+    if (!p) return;
+    if (p->device >= 0 && cudaSetDevice(p->device) == cudaSuccess) {
+        for (auto &s : p->slots) {
+            if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
+            if (s.d_pixels) cudaFree(s.d_pixels);
+            if (s.d_coefs) cudaFree(s.d_coefs);
+            if (s.d_dc) cudaFree(s.d_dc);
+        }
+        if (p->d_dc_shared) cudaFree(p->d_dc_shared);
+        if (p->d_groups) cudaFree(p->d_groups);
+        if (p->d_tile_unit) cudaFree(p->d_tile_unit);
+        if (p->d_ownership) cudaFree(p->d_ownership);
+    }
+    delete p;
+}
+
+uint32_t fri_plan_num_tiles(const fri_plan *p) { return p ? (uint32_t)p->plan.geo.n_fractals : 0; }
+uint32_t fri_plan_num_built(const fri_plan *p) { return p ? p->plan.n_built : 0; }
+uint32_t fri_plan_num_full_tiles(const fri_plan *p) { return p ? p->plan.n_full : 0; }
+uint64_t fri_plan_coefs_per_frame(const fri_plan *p) { return p ? (uint64_t)p->plan.geo.coefs_per_frame : 0; }
+uint64_t fri_plan_pixels_covered(const fri_plan *p) { return p ? p->plan.pixels_covered : 0; }
+
+int fri_plan_centers(const fri_plan *p, int32_t *centers)
+{
+    if (!p || !centers) return fail(FRI_E_INVALID, "NULL argument");
+    std::memcpy(centers, p->plan.centers.data(), p->plan.centers.size() * sizeof(int32_t));
+    return FRI_OK;
+}
+
+int fri_plan_masks(const fri_plan *p, uint32_t *masks)
+{
+    if (!p || !masks) return fail(FRI_E_INVALID, "NULL argument");
+    const Geometry &g = p->plan.geo;
+    const size_t words = ((size_t)1 << g.depth) / 32;
+    for (int32_t i = 0; i < g.n_fractals; ++i) {
+        if (p->plan.full[i])
+            std::memset(masks + i * words, 0xff, words * sizeof(uint32_t));
+        else
+            fractal_mask(g.depth, p->plan.centers[2 * i], p->plan.centers[2 * i + 1], g.width, g.height, masks + i * words);
+    }
+    return FRI_OK;
+}
+
+int fri_plan_launch_info(const fri_plan *p, int32_t info[16])
+{
+    if (!p || !info) return fail(FRI_E_INVALID, "NULL argument");
+    const Geometry &g = p->plan.geo;
+    const int32_t v[16] = {g.group_a, g.group_b, g.region_w, g.region_h, g.pitch, (int32_t)kernel_smem_bytes(g),
+                           g.n_groups, g.n_base_tiles, kThreads, g.chunks_per_row, g.depth, g.sub_bits, 0, 0, 0, 0};
+    std::memcpy(info, v, sizeof(v));
+    return FRI_OK;
+}
+
+int fri_encode_tq_device(const fri_plan *cp, const void *d_pixels, uint32_t n_frames, const int32_t *q, int32_t *d_coefs,
+                         void *stream)
+{
+    fri_plan *p = const_cast<fri_plan *>(cp);
+    int rc = enter_device(p);
+    if (rc) return rc;
+    if ((rc = check_q(q))) return rc;
+    if (n_frames == 0) return FRI_OK;
+    if (!d_pixels || !d_coefs) return fail(FRI_E_INVALID, "NULL device buffer");
+    const Geometry &g = p->plan.geo;
+    if ((uintptr_t)d_coefs & 15) return fail(FRI_E_INVALID, "d_coefs must be 16-byte aligned");
+    if ((uintptr_t)d_pixels & (uintptr_t)(g.sample_bytes - 1)) return fail(FRI_E_INVALID, "d_pixels must be aligned to the sample size");
+    if ((rc = ensure_dc(p, n_frames))) return rc;
+    QuantParams qp;
+    make_quant_params(qp, q, 0);
+    p->last_launches = 0;
+    FRI_CUDA(launch_encode(g, p->tables, qp, d_pixels, n_frames, d_coefs, p->d_dc_shared, static_cast<cudaStream_t>(stream),
+                           &p->last_launches));
+    return FRI_OK;
+}
+
+int fri_decode_tq_device(const fri_plan *cp, const int32_t *d_coefs, uint32_t n_frames, const int32_t *q, int dequant_mode,
+                         void *d_pixels, void *stream)
+{
+    fri_plan *p = const_cast<fri_plan *>(cp);
+    int rc = enter_device(p);
+    if (rc) return rc;
+    if ((rc = check_q(q))) return rc;
+    if (dequant_mode != FRI_DEQUANT_DIVIDE && dequant_mode != FRI_DEQUANT_MULTIPLY)
+        return fail(FRI_E_INVALID, "dequant_mode must be FRI_DEQUANT_DIVIDE or FRI_DEQUANT_MULTIPLY");
+    if (n_frames == 0) return FRI_OK;
+    if (!d_pixels || !d_coefs) return fail(FRI_E_INVALID, "NULL device buffer");
+    const Geometry &g = p->plan.geo;
+    if ((uintptr_t)d_coefs & 15) return fail(FRI_E_INVALID, "d_coefs must be 16-byte aligned");
+    if ((uintptr_t)d_pixels & (uintptr_t)(g.sample_bytes - 1)) return fail(FRI_E_INVALID, "d_pixels must be aligned to the sample size");
+    if ((rc = ensure_dc(p, n_frames))) return rc;
+    QuantParams qp;
+    make_quant_params(qp, q, dequant_mode == FRI_DEQUANT_MULTIPLY);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    p->last_launches = 0;
+    // from_wavelet zero-initialises the raster (wavelet_transform.rs:309-317); only needed when
+    // the retained fractals do not cover every pixel.
+    if (p->plan.pixels_covered != (uint64_t)g.width * g.height)
+        FRI_CUDA(cudaMemsetAsync(d_pixels, 0, (size_t)g.frame_bytes * n_frames, st));
+    FRI_CUDA(launch_decode(g, p->tables, qp, d_coefs, n_frames, d_pixels, p->d_dc_shared, st, &p->last_launches));
+    return FRI_OK;
+}
+
+int fri_encode_tq(fri_plan *p, const void *pixels, uint32_t n_frames, const int32_t *q, int32_t *coefs)
+{
+    int rc = enter_device(p);
+    if (rc) return rc;
+    if ((rc = check_q(q))) return rc;
+    if (n_frames == 0) return FRI_OK;
+    if (!pixels || !coefs) return fail(FRI_E_INVALID, "NULL host buffer");
+    if ((rc = ensure_slots(p))) return rc;
+    const Geometry &g = p->plan.geo;
+    QuantParams qp;
+    make_quant_params(qp, q, 0);
+    p->last_launches = 0;
+    const size_t coef_bytes = (size_t)g.coefs_per_frame * sizeof(int32_t);
+    for (uint32_t f = 0; f < n_frames; ++f) {
+        Slot &s = p->slots[f % kSlots];
+        FRI_CUDA(cudaMemcpyAsync(s.d_pixels, static_cast<const uint8_t *>(pixels) + (size_t)f * g.frame_bytes,
+                                 (size_t)g.frame_bytes, cudaMemcpyHostToDevice, s.stream));
+        FRI_CUDA(launch_encode(g, p->tables, qp, s.d_pixels, 1, s.d_coefs, s.d_dc, s.stream, &p->last_launches));
+        FRI_CUDA(cudaMemcpyAsync(coefs + (size_t)f * g.coefs_per_frame, s.d_coefs, coef_bytes, cudaMemcpyDeviceToHost,
+                                 s.stream));
+    }
+    for (auto &s : p->slots) FRI_CUDA(cudaStreamSynchronize(s.stream));
+    return FRI_OK;
+}
+
+int fri_decode_tq(fri_plan *p, const int32_t *coefs, uint32_t n_frames, const int32_t *q, int dequant_mode, void *pixels)
+{
+    int rc = enter_device(p);
+    if (rc) return rc;
+    if ((rc = check_q(q))) return rc;
+    if (dequant_mode != FRI_DEQUANT_DIVIDE && dequant_mode != FRI_DEQUANT_MULTIPLY)
+        return fail(FRI_E_INVALID, "dequant_mode must be FRI_DEQUANT_DIVIDE or FRI_DEQUANT_MULTIPLY");
+    if (n_frames == 0) return FRI_OK;
+    if (!pixels || !coefs) return fail(FRI_E_INVALID, "NULL host buffer");
+    if ((rc = ensure_slots(p))) return rc;
+    const Geometry &g = p->plan.geo;
+    QuantParams qp;
+    make_quant_params(qp, q, dequant_mode == FRI_DEQUANT_MULTIPLY);
+    p->last_launches = 0;
+    const size_t coef_bytes = (size_t)g.coefs_per_frame * sizeof(int32_t);
+    const bool need_zero = p->plan.pixels_covered != (uint64_t)g.width * g.height;
+    for (uint32_t f = 0; f < n_frames; ++f) {
+        Slot &s = p->slots[f % kSlots];
+        FRI_CUDA(cudaMemcpyAsync(s.d_coefs, coefs + (size_t)f * g.coefs_per_frame, coef_bytes, cudaMemcpyHostToDevice,
+                                 s.stream));
+        if (need_zero) FRI_CUDA(cudaMemsetAsync(s.d_pixels, 0, (size_t)g.frame_bytes, s.stream));
+        FRI_CUDA(launch_decode(g, p->tables, qp, s.d_coefs, 1, s.d_pixels, s.d_dc, s.stream, &p->last_launches));
+        FRI_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(pixels) + (size_t)f * g.frame_bytes, s.d_pixels,
+                                 (size_t)g.frame_bytes, cudaMemcpyDeviceToHost, s.stream));
+    }
+    for (auto &s : p->slots) FRI_CUDA(cudaStreamSynchronize(s.stream));
+    return FRI_OK;
+}
+
+int fri_host_alloc(void **out, size_t bytes)
+{
+    if (!out) return fail(FRI_E_INVALID, "out is NULL");
+    *out = nullptr;
+    FRI_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return FRI_OK;
+}
+
+void fri_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+uint32_t fri_plan_last_launches(const fri_plan *p) { return p ? p->last_launches : 0; }
+
+int32_t fri_quant_divide(int32_t value, int32_t q) { return trunc_div(value, make_div(q)); }
+
+}  // extern "C"

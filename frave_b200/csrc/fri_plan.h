@@ -1,0 +1,73 @@
+// fri_plan.h — host-side lattice plan: which tiles exist, in which order, and how the kernels
+// are launched over them.  Pure C++ (no CUDA), so it is unit-testable without a GPU.
+//
+// Restates crates/libfri/src/stages/wavelet_transform.rs:450-484 (fractal_divide BFS),
+// :71-90 (get_nearby_vectors), :415-416 (retain) in lattice coordinates.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "fri_geometry.h"
+
+namespace fri {
+
+constexpr int kMaxGroupTiles = 32;  // tiles per CTA group (bits of GroupDesc::tile_mask)
+
+// One CTA's worth of work: up to A x B lattice-adjacent base tiles whose pixels are staged
+// together through shared memory.
+struct GroupDesc {
+    int32_t x0, y0;      // image coordinates of the staged region's top-left pixel (may be < 0)
+    uint32_t tile_mask;  // bit (j*A + i) set <=> base tile (a0 + i, b0 + j) is present
+    uint32_t tile_base;  // plan index of the group's first present base tile
+};
+static_assert(sizeof(GroupDesc) == 16, "GroupDesc is uploaded verbatim");
+
+// Launch geometry shared by the encode and decode kernels (passed by value to the kernels).
+struct Geometry {
+    int32_t width, height;
+    int32_t channels, sample_bytes;
+    int32_t depth;               // fractal depth (9 = reference)
+    int32_t sub_bits;            // depth - 9: a fractal is 2^sub_bits base tiles
+    int32_t group_a, group_b;    // group shape in base-lattice coordinates
+    int32_t region_w, region_h;  // staged region in pixels
+    int32_t row_bytes;           // region_w * channels * sample_bytes
+    int32_t pitch;               // shared-memory row pitch in bytes (== width*C*sz mod 16)
+    int32_t chunks_per_row;      // upper bound on 16-byte chunks covering one staged row
+    int32_t own_words;           // 32-bit words per row of the ownership bitmap
+    int32_t n_groups;
+    int32_t n_base_tiles;        // base tiles processed per frame (n_fractals << sub_bits)
+    int32_t n_fractals;          // retained fractals per frame (== n_base_tiles at depth 9)
+    int32_t pad_;
+    int64_t row_stride;          // width * channels * sample_bytes
+    int64_t frame_bytes;         // height * row_stride
+    int64_t coefs_per_frame;     // n_fractals * channels * 2^depth
+    int16_t tile_rel_x[kMaxGroupTiles];  // base tile centre relative to the region origin
+    int16_t tile_rel_y[kMaxGroupTiles];
+};
+
+struct Plan {
+    Geometry geo{};
+    uint32_t n_built = 0;         // fractals the reference's BFS constructs (incl. dropped fringe)
+    uint32_t n_full = 0;          // retained fractals with all leaves inside the image
+    uint64_t pixels_covered = 0;  // in-image pixels owned by retained fractals
+    std::vector<int32_t> centers;     // [n_fractals][2] (re, im), plan order
+    std::vector<uint8_t> full;        // [n_fractals]
+    std::vector<GroupDesc> groups;    // [n_groups]
+    std::vector<uint32_t> tile_unit;  // [n_base_tiles] fractal_index << sub_bits | sub_tile (empty at depth 9)
+    std::vector<uint32_t> ownership;  // [region_h][own_words]: bit x set <=> region pixel belongs to the group
+};
+
+// Returns an empty string on success, else an error message.  group_a/group_b == 0 picks the
+// default group shape for the pixel size.
+std::string build_plan(Plan &plan, uint32_t width, uint32_t height, uint32_t channels, uint32_t depth,
+                       uint32_t sample_bytes, int group_a, int group_b);
+
+// 2^depth-bit Some/None mask of the fractal centred at (cx, cy): bit i <=> coefficient i is
+// Some.  out has 2^depth / 32 words.
+void fractal_mask(int depth, int32_t cx, int32_t cy, int32_t width, int32_t height, uint32_t *out);
+
+// Average / worst shared-memory conflict degree of the leaf gather for a pitch (lower is better).
+double gather_conflict_degree(int pitch, int pixel_bytes, int sample_bytes, int *worst);
+
+}  // namespace fri

@@ -1,0 +1,132 @@
+/*
+ * fri_cuda.h — C ABI of libfri_cuda: frave's fractal transform + quantization hot path on
+ * NVIDIA B200 (sm_100a).  This is the boundary a `libfri-cuda` Rust crate binds with
+ * `extern "C"` (see rust/libfri-cuda/ and INTEGRATION.md); plain pointers and sizes only.
+ *
+ * Reference citations are file:line relative to the pagmerek/frave tree
+ * (crates/libfri/src/...).  What each entry point replaces:
+ *
+ *   fri_plan_create        WaveletImage::fractal_divide + Fractal::new + the retain step
+ *                          (stages/wavelet_transform.rs:450-484, :42-69, :415-416) and, on
+ *                          decode, WaveletImage::from_metadata (:392-403) whose only purpose
+ *                          is to rebuild the lattice and the Some/None masks.
+ *   fri_encode_tq*         wavelet_transform::encode (:708-713 -> from_raster :405-416 ->
+ *                          extract_coefficients :179-225) fused with quantization::encode
+ *                          (stages/quantization.rs:7-25).  Call sites: encoder.rs:26-33.
+ *   fri_decode_tq*         quantization::decode (quantization.rs:27-45) fused with
+ *                          wavelet_transform::decode (:715-717 -> from_wavelet :308-322 ->
+ *                          extract_values :358-381, images.rs:103-111).  Call sites:
+ *                          decoder.rs:27-34.
+ *
+ * Data layouts (identical to the reference's):
+ *   pixels        HWC interleaved, index (y*W + x)*C + ch (images.rs:94); u8 (reference) or
+ *                 little-endian u16 (extension, sample_bytes = 2).
+ *   coefficients  int32 [n_tiles][C][2^depth], heap order: [0] = DC (:221), [pos] = residue of
+ *                 tree node pos.  A coefficient the reference holds as `None` is 0 on encode
+ *                 output and ignored on decode input; fri_plan_masks() says which are `Some`.
+ *   tile order    defined by the plan: fri_plan_centers() returns the centre (re = x, im = y)
+ *                 of tile i.  (The reference keeps tiles in a HashMap keyed by centre, so it
+ *                 has no order of its own.)
+ *
+ * All functions return 0 on success or a negative FRI_E_* code; fri_last_error() returns a
+ * thread-local message for the last failure.  There is NO CPU fallback: without a CUDA
+ * device every compute entry point fails with FRI_E_CUDA.
+ */
+#ifndef FRI_CUDA_H
+#define FRI_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FRI_OK 0
+#define FRI_E_INVALID (-1) /* bad argument */
+#define FRI_E_CUDA (-2)    /* CUDA runtime / driver error, or no device */
+#define FRI_E_NOMEM (-3)
+#define FRI_E_UNSUPPORTED (-4)
+
+/* quantization::decode behaviour */
+#define FRI_DEQUANT_DIVIDE 0   /* reference-faithful: divides again (quantization.rs:37) */
+#define FRI_DEQUANT_MULTIPLY 1 /* true dequantizer (not what the reference does) */
+
+#define FRI_BASE_DEPTH 9 /* BASE_FRAC_DEPTH, wavelet_transform.rs:39 */
+
+typedef struct fri_plan fri_plan;
+
+/* Version / build info: "libfri_cuda <ver> sm_100a". */
+const char *fri_version(void);
+const char *fri_last_error(void);
+
+/* Number of visible CUDA devices (0 if none / no driver). */
+int fri_device_count(void);
+
+/*
+ * Builds the lattice for a (width, height, channels) image: the BFS of fractal_divide, the
+ * retain rule, the tile order and the launch geometry.  Pure host work; if device >= 0 the
+ * plan's tables are also uploaded to that device (required by every *_device / host entry
+ * point), if device < 0 the plan is host-only (metadata queries work, compute calls fail).
+ *   depth         9 is the only depth the reference reaches (BASE_FRAC_DEPTH); 10..24 is the
+ *                 deep-tree extension (one fractal = 2^(depth-9) base tiles + coarse levels).
+ *   sample_bytes  1 (reference) or 2 (u16 extension).
+ */
+int fri_plan_create(fri_plan **out, int device, uint32_t width, uint32_t height, uint32_t channels,
+                    uint32_t depth, uint32_t sample_bytes);
+void fri_plan_destroy(fri_plan *plan);
+
+uint32_t fri_plan_num_tiles(const fri_plan *plan);       /* retained tiles (fractals of 2^depth leaves) */
+uint32_t fri_plan_num_built(const fri_plan *plan);       /* tiles fractal_divide builds (incl. fringe) */
+uint32_t fri_plan_num_full_tiles(const fri_plan *plan);  /* tiles with every leaf inside the image */
+uint64_t fri_plan_coefs_per_frame(const fri_plan *plan); /* n_tiles * C * 2^depth */
+uint64_t fri_plan_pixels_covered(const fri_plan *plan);  /* in-image pixels owned by retained tiles */
+
+/* Launch geometry, for reports: info = {group_a, group_b, region_w, region_h, smem_pitch,
+ * smem_bytes_per_cta, n_groups (CTAs per frame), n_base_tiles, threads_per_cta,
+ * chunks_per_row, depth, depth - 9, 0...}. */
+int fri_plan_launch_info(const fri_plan *plan, int32_t info[16]);
+
+/* centres[n_tiles][2] = (re, im) of each retained tile, in plan order. */
+int fri_plan_centers(const fri_plan *plan, int32_t *centers);
+/* masks[n_tiles][2^depth / 32]: bit (i & 31) of word (i >> 5) set <=> coefficient i is `Some`.
+ * Channel-independent (validity is geometric). */
+int fri_plan_masks(const fri_plan *plan, uint32_t *masks);
+
+/*
+ * Device-resident batch entry points (inputs and outputs already in HBM on the plan's
+ * device).  `stream` is a cudaStream_t (NULL = default stream); the call only enqueues.
+ *   pixels  n_frames consecutive HWC frames;  coefs  n_frames consecutive coefficient blocks.
+ *   q       32-entry quantization matrix, host memory, every entry >= 1; q == NULL means
+ *           all ones (get_quantization_matrix, quantization.rs:3-5).
+ */
+int fri_encode_tq_device(const fri_plan *plan, const void *d_pixels, uint32_t n_frames, const int32_t *q,
+                         int32_t *d_coefs, void *stream);
+int fri_decode_tq_device(const fri_plan *plan, const int32_t *d_coefs, uint32_t n_frames, const int32_t *q,
+                         int dequant_mode, void *d_pixels, void *stream);
+
+/*
+ * Host-buffer entry points (what libfri's stage functions call): copy in, run, copy out,
+ * synchronise.  Frames are pipelined over the plan's internal streams; buffers obtained from
+ * fri_host_alloc are pinned and take the fast path, any other host memory is staged through
+ * pinned bounce buffers.
+ */
+int fri_encode_tq(fri_plan *plan, const void *pixels, uint32_t n_frames, const int32_t *q, int32_t *coefs);
+int fri_decode_tq(fri_plan *plan, const int32_t *coefs, uint32_t n_frames, const int32_t *q, int dequant_mode,
+                  void *pixels);
+
+/* Pinned host memory (cudaHostAlloc) for the host-buffer entry points. */
+int fri_host_alloc(void **out, size_t bytes);
+void fri_host_free(void *p);
+
+/* Launch statistics of the last *_device / host call on this plan (kernel launches issued). */
+uint32_t fri_plan_last_launches(const fri_plan *plan);
+
+/* The kernels' truncating division value / q (q >= 1) evaluated on the host: the same
+ * multiply-high + shift routine the device code uses for quantization.rs:19 / :37 (for tests). */
+int32_t fri_quant_divide(int32_t value, int32_t q);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -57,6 +57,12 @@ def lib() -> C.CDLL:
         L.fri_oracle_extract_values.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_uint32,
                                                 C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int]
         L.fri_oracle_extract_values.restype = None
+        L.fri_oracle_encode_tiles.argtypes = [C.POINTER(Raster), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p,
+                                              C.c_void_p, C.c_int]
+        L.fri_oracle_encode_tiles.restype = None
+        L.fri_oracle_decode_tiles.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_uint32,
+                                              C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
+        L.fri_oracle_decode_tiles.restype = None
         L.fri_oracle_image_positions.argtypes = [C.c_int, C.c_int32, C.c_int32, C.c_void_p]
         L.fri_oracle_image_positions.restype = None
         L.fri_oracle_prev_power_two.argtypes = [C.c_size_t]
@@ -144,4 +150,34 @@ def extract_values(centers: np.ndarray, coef: np.ndarray, some: np.ndarray | Non
     out = np.zeros((h, w, c), dtype=dtype)
     L.fri_oracle_extract_values(centers.ctypes.data, coef.ctypes.data, s8.ctypes.data if s8 is not None else None,
                                 n, depth, w, h, c, out.dtype.itemsize, out.ctypes.data, nthreads)
+    return out
+
+
+def encode_tiles(img: np.ndarray, centers: np.ndarray, q, depth: int = 9, nthreads: int = 1,
+                 out: np.ndarray | None = None) -> np.ndarray:
+    """Timed-baseline driver: forward transform + quantization over a tile list (None -> 0)."""
+    L = lib()
+    r, img = _raster(img)
+    centers = np.ascontiguousarray(centers, dtype=np.int32)
+    qa = np.ascontiguousarray(q, dtype=np.int32)
+    n, c = len(centers), img.shape[2]
+    if out is None:
+        out = np.empty((n, c, 1 << depth), np.int32)
+    L.fri_oracle_encode_tiles(C.byref(r), depth, centers.ctypes.data, n, qa.ctypes.data, out.ctypes.data, nthreads)
+    return out
+
+
+def decode_tiles(centers: np.ndarray, coef: np.ndarray, some: np.ndarray | None, q, h: int, w: int, depth: int = 9,
+                 dtype=np.uint8, nthreads: int = 1, out: np.ndarray | None = None) -> np.ndarray:
+    """Timed-baseline driver: dividing dequantization + inverse transform over a tile list."""
+    L = lib()
+    centers = np.ascontiguousarray(centers, dtype=np.int32)
+    coef = np.ascontiguousarray(coef, dtype=np.int32)
+    qa = np.ascontiguousarray(q, dtype=np.int32)
+    n, c, _ = coef.shape
+    s8 = np.ascontiguousarray(some, dtype=np.uint8) if some is not None else None
+    if out is None:
+        out = np.zeros((h, w, c), dtype=dtype)
+    L.fri_oracle_decode_tiles(centers.ctypes.data, coef.ctypes.data, s8.ctypes.data if s8 is not None else None, n,
+                              depth, w, h, c, out.dtype.itemsize, qa.ctypes.data, out.ctypes.data, nthreads)
     return out

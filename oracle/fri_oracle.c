@@ -442,4 +442,54 @@ void fri_oracle_extract_values(const int32_t *centers, const int32_t *coef, cons
     parallel_for(n_tiles, nthreads, xv_body, &x);
 }
 
+/* ---- whole-path drivers used as the timed CPU baseline (bench.py): the reference's
+ * wavelet_transform::encode + quantization::encode (encoder.rs:26-33) and quantization::decode +
+ * wavelet_transform::decode (decoder.rs:27-34) over a given tile list, tiles split over threads. */
+typedef struct {
+    const fri_oracle_raster *img; int depth; const int32_t *centers; int32_t *coef; const int32_t *q;
+} et_ctx;
+static void et_body(size_t t, void *p)
+{
+    et_ctx *c = (et_ctx *)p;
+    const size_t n = (size_t)1 << c->depth, per = (size_t)c->img->channels * n;
+    fri_opt_i32 *tmp = (fri_opt_i32 *)malloc(per * sizeof(fri_opt_i32));
+    fri_oracle_extract_coefficients(c->img, c->depth, c->centers[2 * t], c->centers[2 * t + 1], tmp);
+    for (size_t i = 0; i < per; ++i) {
+        unsigned layer = (unsigned)__builtin_ctzll((unsigned long long)fri_oracle_prev_power_two((i & (n - 1)) + 1));
+        c->coef[t * per + i] = tmp[i].some ? tmp[i].v / c->q[layer] : 0;
+    }
+    free(tmp);
+}
+void fri_oracle_encode_tiles(const fri_oracle_raster *img, int depth, const int32_t *centers, size_t n_tiles,
+                             const int32_t q[32], int32_t *coef, int nthreads)
+{
+    et_ctx c = {img, depth, centers, coef, q};
+    parallel_for(n_tiles, nthreads, et_body, &c);
+}
+
+typedef struct { xv_ctx x; const int32_t *q; int32_t *tmp_all; } dt_ctx;
+static void dt_body(size_t t, void *p)
+{
+    dt_ctx *d = (dt_ctx *)p;
+    const size_t n = (size_t)1 << d->x.depth, per = (size_t)d->x.channels * n;
+    int32_t *tmp = (int32_t *)malloc(per * sizeof(int32_t));
+    for (size_t i = 0; i < per; ++i) {
+        unsigned layer = (unsigned)__builtin_ctzll((unsigned long long)fri_oracle_prev_power_two((i & (n - 1)) + 1));
+        tmp[i] = d->x.coef[t * per + i] / d->q[layer]; /* quantization.rs:37 divides */
+    }
+    xv_ctx one = d->x;
+    one.centers = d->x.centers + 2 * t;
+    one.coef = tmp;
+    one.some = d->x.some ? d->x.some + t * per : NULL;
+    xv_body(0, &one);
+    free(tmp);
+}
+void fri_oracle_decode_tiles(const int32_t *centers, const int32_t *coef, const uint8_t *some, size_t n_tiles,
+                             int depth, uint32_t width, uint32_t height, uint32_t channels, uint32_t sample_bytes,
+                             const int32_t q[32], void *out, int nthreads)
+{
+    dt_ctx d = {{centers, coef, some, depth, width, height, channels, sample_bytes, out}, q, NULL};
+    parallel_for(n_tiles, nthreads, dt_body, &d);
+}
+
 void fri_oracle_free(void *p) { free(p); }

@@ -87,6 +87,14 @@ void fri_oracle_extract_values(const int32_t *centers, const int32_t *coef, cons
                                size_t n_tiles, int depth, uint32_t width, uint32_t height,
                                uint32_t channels, uint32_t sample_bytes, void *out, int nthreads);
 
+/* Timed CPU baseline drivers: transform + quantization (encoder.rs:26-33) and dequantization
+ * (dividing, quantization.rs:37) + inverse transform (decoder.rs:27-34) over a tile list. */
+void fri_oracle_encode_tiles(const fri_oracle_raster *img, int depth, const int32_t *centers, size_t n_tiles,
+                             const int32_t q[32], int32_t *coef, int nthreads);
+void fri_oracle_decode_tiles(const int32_t *centers, const int32_t *coef, const uint8_t *some, size_t n_tiles,
+                             int depth, uint32_t width, uint32_t height, uint32_t channels, uint32_t sample_bytes,
+                             const int32_t q[32], void *out, int nthreads);
+
 void fri_oracle_free(void *p);
 
 #ifdef __cplusplus

@@ -1,0 +1,249 @@
+"""GPU parity suite (-m gpu): libfri_cuda, called through its C ABI, against the CPU oracle on
+the same seeded inputs — bit-exact int32 coefficients and bit-exact reconstructed pixels — plus
+size-independent properties at BASELINE.json's full sizes."""
+import os
+
+import numpy as np
+import pytest
+
+from frave_b200 import capi, stages
+from oracle import c_oracle as O
+from tests.conftest import smallest_layer_q, smooth_image, uniform_image
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+ONES = np.ones(32, np.int32)
+
+
+def oracle_encode(plan, img, q=ONES, nthreads=8):
+    """Oracle coefficients in the plan's tile order; None -> 0 exactly like the GPU output."""
+    coef, some = O.extract_tiles(img, plan.centers(), depth=plan.depth, nthreads=nthreads)
+    return O.quantize(coef, some, q, depth=plan.depth), some
+
+
+def oracle_decode(plan, coefs, some, q=ONES, multiply=False, nthreads=8):
+    dq = O.quantize(coefs, some, q, depth=plan.depth, multiply=multiply)
+    return O.extract_values(plan.centers(), dq, some, plan.height, plan.width, depth=plan.depth,
+                            dtype=plan.pixel_dtype, nthreads=nthreads)
+
+
+def some_of(plan):
+    m = plan.masks()
+    return np.broadcast_to(m[:, None, :], plan.coef_shape).copy()
+
+
+def random_q(seed, hi=64):
+    return np.random.Generator(np.random.PCG64(seed)).integers(1, hi + 1, size=32).astype(np.int32)
+
+
+SHAPES = [(1, 1, 1), (10, 10, 3), (48, 64, 1), (37, 100, 3), (300, 7, 3), (131, 77, 3), (512, 512, 1), (257, 1031, 3),
+          (64, 4096, 1), (33, 65, 1)]
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16], ids=["u8", "u16"])
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_encode_bit_exact(shape, dtype):
+    h, w, c = shape
+    img = uniform_image(h, w, c, seed=h * 7 + w, dtype=dtype)
+    with capi.Plan(w, h, c, sample_bytes=img.itemsize) as plan:
+        for q in (None, smallest_layer_q(5), random_q(h + w), np.full(32, 70000, np.int32)):
+            got = plan.encode(img, q)[0]
+            want, some = oracle_encode(plan, img, ONES if q is None else q)
+            assert np.array_equal(got, want), f"q={None if q is None else q[:10]}"
+            assert not got[~some].any()  # None comes out as 0
+        assert plan.last_launches == 1
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16], ids=["u8", "u16"])
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_decode_bit_exact(shape, dtype):
+    h, w, c = shape
+    rng = np.random.Generator(np.random.PCG64(h * 11 + w))
+    with capi.Plan(w, h, c, sample_bytes=np.dtype(dtype).itemsize) as plan:
+        some = some_of(plan)
+        hi = 300 if dtype == np.uint8 else 70000
+        coefs = rng.integers(-hi, hi + 1, size=plan.coef_shape).astype(np.int32)
+        coefs[:, :, 0] = rng.integers(-50, hi + 50, size=plan.coef_shape[:2])  # DC mostly in range, clamp exercised
+        for q, multiply in ((None, False), (random_q(w, 5), False), (random_q(h, 3), True)):
+            got = plan.decode(coefs, q, multiply=multiply)[0]
+            want = oracle_decode(plan, coefs, some, ONES if q is None else q, multiply)
+            assert np.array_equal(got, want)
+        # coefficients the reference holds as None are ignored, whatever the buffer contains
+        noisy = coefs.copy()
+        noisy[~some] = rng.integers(-2**31, 2**31 - 1, size=int((~some).sum()))
+        assert np.array_equal(plan.decode(noisy)[0], oracle_decode(plan, coefs, some))
+        # wrapping i32 arithmetic (release-mode Rust) on extreme coefficients
+        wild = rng.integers(-2**31, 2**31 - 1, size=plan.coef_shape).astype(np.int32)
+        assert np.array_equal(plan.decode(wild, random_q(3, 4))[0], oracle_decode(plan, wild, some, random_q(3, 4)))
+
+
+@pytest.mark.parametrize("name", ["u8_rgb_70x96_q5", "u8_luma_48x64_q1", "u16_luma_65x33_q3"])
+def test_golden_fixtures(name):
+    fx = np.load(os.path.join(GOLDEN, name + ".npz"))
+    img = fx["pixels"]
+    h, w, c = img.shape
+    with capi.Plan(w, h, c, sample_bytes=img.itemsize) as plan:
+        order = {tuple(x): i for i, x in enumerate(fx["centers"].tolist())}
+        idx = np.array([order[tuple(x)] for x in plan.centers().tolist()])
+        got = plan.encode(img, fx["q"])[0]
+        assert np.array_equal(got, fx["coef"][idx])
+        assert np.array_equal(plan.mask_words().view(np.uint8), fx["some"][idx])
+        assert np.array_equal(plan.decode(got, fx["q"])[0], fx["recon"])
+
+
+@pytest.mark.parametrize("depth", [10, 11, 13, 16])
+@pytest.mark.parametrize("dtype,c", [(np.uint8, 1), (np.uint8, 3), (np.uint16, 1)], ids=["u8x1", "u8x3", "u16x1"])
+def test_deep_tree_extension(depth, dtype, c):
+    h, w = (150, 260) if depth < 16 else (420, 610)
+    img = uniform_image(h, w, c, seed=depth, dtype=dtype)
+    with capi.Plan(w, h, c, depth=depth, sample_bytes=img.itemsize) as plan:
+        q = random_q(depth, 9)
+        got = plan.encode(img, q)[0]
+        want, some = oracle_encode(plan, img, q)
+        assert np.array_equal(got, want)
+        assert plan.last_launches == 2  # base kernel + coarse levels
+        assert np.array_equal(plan.decode(got, q)[0], oracle_decode(plan, got, some, q))
+        lossless = plan.encode(img)[0]
+        rec = plan.decode(lossless)[0]
+        assert np.array_equal(rec, img)
+
+
+def test_batch_equals_per_frame_and_unaligned_frames():
+    # 5 frames of 37x100x3: frame_bytes = 11100 (not a multiple of 16), row stride 300
+    h, w, c, n = 37, 100, 3, 5
+    frames = np.stack([uniform_image(h, w, c, seed=50 + i) for i in range(n)])
+    with capi.Plan(w, h, c) as plan:
+        q = smallest_layer_q(3)
+        batch = plan.encode(frames, q)
+        for i in range(n):
+            assert np.array_equal(batch[i], oracle_encode(plan, frames[i], q)[0])
+        rec = plan.decode(plan.encode(frames))
+        assert np.array_equal(rec, frames)
+
+
+def test_device_entry_points_with_misaligned_pixel_pointer():
+    torch = pytest.importorskip("torch")
+    h, w, c, n = 61, 93, 3, 3
+    frames = np.stack([uniform_image(h, w, c, seed=70 + i) for i in range(n)])
+    with capi.Plan(w, h, c) as plan:
+        dev = torch.device("cuda", 0)
+        for shift in (0, 1, 7):
+            raw = torch.zeros(frames.size + 64, dtype=torch.uint8, device=dev)
+            raw[shift:shift + frames.size] = torch.from_numpy(frames.reshape(-1)).to(dev)
+            d_coefs = torch.empty((n,) + plan.coef_shape, dtype=torch.int32, device=dev)
+            plan.encode_device(raw.data_ptr() + shift, n, d_coefs.data_ptr())
+            torch.cuda.synchronize()
+            got = d_coefs.cpu().numpy()
+            for i in range(n):
+                assert np.array_equal(got[i], oracle_encode(plan, frames[i])[0])
+            out = torch.full((frames.size + 64,), 0xAB, dtype=torch.uint8, device=dev)
+            plan.decode_device(d_coefs.data_ptr(), n, out.data_ptr() + shift)
+            torch.cuda.synchronize()
+            o = out.cpu().numpy()
+            assert np.array_equal(o[shift:shift + frames.size].reshape(frames.shape), frames)
+            assert (o[:shift] == 0xAB).all() and (o[shift + frames.size:] == 0xAB).all()  # no stray writes
+
+
+def test_uncovered_pixels_are_zeroed_like_from_wavelet():
+    # 7x300: the reference's BFS does not reach every pixel (pixels_covered < W*H)
+    h, w, c = 300, 7, 3
+    img = uniform_image(h, w, c, seed=9)
+    with capi.Plan(w, h, c) as plan:
+        assert plan.pixels_covered < w * h
+        coefs = plan.encode(img)
+        want = oracle_decode(plan, coefs[0], some_of(plan))
+        out = np.full((1, h, w, c), 0x5A, np.uint8)
+        plan.decode(coefs, out=out)
+        assert np.array_equal(out[0], want)
+
+
+def test_quantization_sweep_1080p():
+    """BASELINE.json configs[4]: smallest-layer divisor 1..64 on 1920x1080 RGB, coefficient for
+    coefficient against the oracle (container bytes are out of scope: SURVEY.md §8(c))."""
+    h, w, c = 1080, 1920, 3
+    img = smooth_image(h, w, c, seed=5)
+    with capi.Plan(w, h, c) as plan:
+        base, some = O.extract_tiles(img, plan.centers(), nthreads=8)
+        for d in range(1, 65):
+            for both in (True, False):
+                q = smallest_layer_q(d, both)
+                got = plan.encode(img, q)[0]
+                assert np.array_equal(got, O.quantize(base, some, q)), (d, both)
+        q = smallest_layer_q(16)
+        coefs = plan.encode(img, q)
+        assert np.array_equal(plan.decode(coefs, q)[0], oracle_decode(plan, coefs[0], some, q))
+        assert np.array_equal(plan.decode(coefs, q, multiply=True)[0], oracle_decode(plan, coefs[0], some, q, True))
+
+
+def _device_roundtrip(torch, w, h, c, n_frames, dtype, seed, sample_tiles=64):
+    """Full-size check on device-resident data: encode -> decode is the identity at q == 1, the
+    buffers' guard bands stay untouched, and a random sample of tiles matches the oracle."""
+    tdtype = torch.uint8 if dtype == np.uint8 else torch.uint16
+    dev = torch.device("cuda", 0)
+    with capi.Plan(w, h, c, sample_bytes=np.dtype(dtype).itemsize) as plan:
+        gen = torch.Generator(device=dev).manual_seed(seed)
+        hi = 256 if dtype == np.uint8 else 65536
+        px = torch.randint(0, hi, (n_frames, h, w, c), generator=gen, device=dev, dtype=torch.int32).to(tdtype)
+        coefs = torch.empty((n_frames,) + plan.coef_shape, dtype=torch.int32, device=dev)
+        out = torch.empty_like(px)
+        plan.encode_device(px.data_ptr(), n_frames, coefs.data_ptr())
+        plan.decode_device(coefs.data_ptr(), n_frames, out.data_ptr())
+        torch.cuda.synchronize()
+        assert torch.equal(px.view(torch.uint8), out.view(torch.uint8))
+        rng = np.random.Generator(np.random.PCG64(seed))
+        f = int(rng.integers(0, n_frames))
+        tiles = np.sort(rng.choice(plan.n_tiles, size=min(sample_tiles, plan.n_tiles), replace=False))
+        img = px[f].cpu().numpy() if dtype == np.uint8 else px[f].view(torch.int16).cpu().numpy().view(np.uint16)
+        want, _ = O.extract_tiles(img, plan.centers()[tiles], nthreads=8)
+        got = coefs[f][torch.from_numpy(tiles).to(dev)].cpu().numpy()
+        assert np.array_equal(got, want)
+        # the DC of a fully covered tile is bounded by the sample range; checksum of checksums
+        assert int(coefs[:, :, :, 0].min()) >= 0 and int(coefs[:, :, :, 0].max()) < hi
+
+
+def test_full_size_4096_rgb_roundtrip():
+    torch = pytest.importorskip("torch")
+    _device_roundtrip(torch, 4096, 4096, 3, 1, np.uint8, seed=2)
+
+
+def test_full_size_4k_batch_roundtrip():
+    torch = pytest.importorskip("torch")
+    _device_roundtrip(torch, 3840, 2160, 3, 8, np.uint8, seed=3)
+
+
+def test_full_size_16384_u16_roundtrip():
+    torch = pytest.importorskip("torch")
+    _device_roundtrip(torch, 16384, 16384, 1, 1, np.uint16, seed=4)
+
+
+def test_stage_interface_mirrors_reference_pipeline():
+    img = smooth_image(120, 200, 3, seed=1)
+    raster = stages.RasterImage.from_array(img, stages.ColorSpace.RGB)
+    opts = stages.EncoderOpts(quantization_matrix=smallest_layer_q(4))
+    wi = stages.quantization.encode(stages.wavelet_transform.encode(raster, opts))  # encoder.rs:26-33
+    centers, coef, some = O.from_raster(img)
+    want = O.quantize(coef, some, opts.quantization_matrix)
+    order = {tuple(x): i for i, x in enumerate(centers.tolist())}
+    idx = np.array([order[tuple(x)] for x in wi.centers.tolist()])
+    assert np.array_equal(wi.coefficients, want[idx])
+    assert np.array_equal(wi.some, some[idx][:, 0, :])
+    back = stages.wavelet_transform.decode(stages.quantization.decode(wi))  # decoder.rs:27-34
+    ref = O.extract_values(centers, O.quantize(want, some, opts.quantization_matrix), some, 120, 200)
+    assert np.array_equal(back.data, ref)
+    lattice = wi.fractal_lattice()
+    assert set(lattice) == set(order)
+
+
+def test_bad_arguments_on_device():
+    with capi.Plan(32, 32, 1) as plan:
+        img = np.zeros((32, 32, 1), np.uint8)
+        q = ONES.copy()
+        q[4] = 0
+        with pytest.raises(capi.FriError) as e:
+            plan.encode(img, q)
+        assert e.value.code == capi.FRI_E_INVALID
+        with pytest.raises(ValueError):
+            plan.encode(np.zeros((32, 32, 3), np.uint8))
+    with pytest.raises(capi.FriError) as e:
+        capi.Plan(32, 32, 1, device=capi.device_count())
+    assert e.value.code == capi.FRI_E_CUDA

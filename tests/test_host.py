@@ -1,0 +1,182 @@
+"""CPU suite: the C-ABI library loads and exports every declared symbol, the host-side plan
+reproduces the reference's lattice (checked against the oracle), error behaviour without a
+device, and the frame sharding used for N > 1 (gloo, world_size 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from frave_b200 import capi, sharding, stages
+from oracle import c_oracle as O
+from oracle import fri_oracle_np as N
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "fri_cuda.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(fri_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no prototypes found"
+    L = ctypes.CDLL(capi.lib_path()) if os.path.exists(capi.lib_path()) else capi.lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} is declared in include/fri_cuda.h but not exported"
+    assert declared == set(capi.SYMBOL_NAMES)
+    assert "sm_100a" in capi.version()
+
+
+def test_kernels_are_compiled_for_sm_100a():
+    out = subprocess.run(["cuobjdump", "-lelf", capi.lib_path()], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump not available")
+    assert "sm_100a" in out.stdout
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (10, 10, 3), (48, 64, 1), (37, 100, 3), (300, 7, 3), (512, 512, 1),
+                                   (240, 427, 3)])
+def test_plan_matches_reference_lattice(shape):
+    h, w, c = shape
+    with capi.Plan(w, h, c, device=-1) as p:
+        img = np.zeros((h, w, c), np.uint8)
+        centers, _, some = O.from_raster(img)
+        assert p.n_built == len(O.fractal_divide(w, h))
+        assert p.n_tiles == len(centers)
+        pc = p.centers()
+        order = {tuple(x): i for i, x in enumerate(centers.tolist())}
+        assert len(order) == len(pc)
+        idx = np.array([order[tuple(x)] for x in pc.tolist()], dtype=np.int64)
+        assert np.array_equal(p.masks(), some[idx][:, 0, :])
+        off = N.leaf_offsets(9)
+        x, y = pc[:, 0:1] + off[None, :, 0], pc[:, 1:2] + off[None, :, 1]
+        inside = (x >= 0) & (y >= 0) & (x < w) & (y < h)
+        assert p.pixels_covered == int(inside.sum())
+        assert p.n_full == int(inside.all(axis=1).sum())
+        assert p.coefs_per_frame == p.n_tiles * c * 512
+        info = p.launch_info()
+        assert info["smem_bytes"] <= 227 * 1024 and info["n_base_tiles"] == p.n_tiles
+
+
+def test_survey_tile_counts():
+    # built / retained / fully-inside
+    for (w, h), want in {(512, 512): (617, 578, 448), (1920, 1080): (4317, 4221, 3881)}.items():
+        with capi.Plan(w, h, 3, device=-1) as p:
+            assert (p.n_built, p.n_tiles, p.n_full) == want
+            assert p.pixels_covered == w * h
+
+
+def test_deep_plan_is_a_union_of_base_tiles():
+    # depth-D fractal = 2^(D-9) base tiles (wavelet_transform.rs:47-53); check against the oracle's BFS
+    for depth in (10, 12):
+        w, h = 300, 200
+        with capi.Plan(w, h, 1, depth=depth, device=-1) as p:
+            centers, _, some = O.from_raster(np.zeros((h, w, 1), np.uint8), depth=depth)
+            assert p.n_built == len(O.fractal_divide(w, h, depth))
+            assert p.n_tiles == len(centers)
+            pc = p.centers()
+            order = {tuple(x): i for i, x in enumerate(centers.tolist())}
+            idx = np.array([order[tuple(x)] for x in pc.tolist()], dtype=np.int64)
+            assert np.array_equal(p.masks(), some[idx][:, 0, :])
+            assert p.launch_info()["n_base_tiles"] == p.n_tiles << (depth - 9)
+
+
+def test_invalid_arguments_and_no_cpu_fallback():
+    for args in [(0, 5, 1), (5, 0, 1), (5, 5, 2), (5, 5, 4)]:
+        with pytest.raises(capi.FriError) as e:
+            capi.Plan(*args, device=-1)
+        assert e.value.code == capi.FRI_E_INVALID
+    with pytest.raises(capi.FriError):
+        capi.Plan(8, 8, 1, depth=8, device=-1)
+    with pytest.raises(capi.FriError):
+        capi.Plan(8, 8, 1, sample_bytes=3, device=-1)
+    with capi.Plan(16, 16, 1, device=-1) as p:
+        with pytest.raises(capi.FriError) as e:
+            p.encode(np.zeros((16, 16, 1), np.uint8))
+        assert e.value.code == capi.FRI_E_CUDA and "no CPU fallback" in str(e.value)
+        with pytest.raises(capi.FriError):
+            p.decode(np.zeros((1,) + p.coef_shape, np.int32))
+    if capi.device_count() == 0:
+        with pytest.raises(capi.FriError) as e:
+            capi.Plan(16, 16, 1, device=0)
+        assert e.value.code == capi.FRI_E_CUDA
+        with pytest.raises(stages.StageError):
+            stages.wavelet_transform.encode(stages.RasterImage.from_array(np.zeros((16, 16, 3), np.uint8)))
+
+
+def test_kernel_division_routine_is_exact_truncating_division():
+    """quantization.rs:19/:37 is Rust `i32 / i32` (truncation toward zero); the kernels use a
+    multiply-high routine instead of a hardware divide — check it against C semantics."""
+    L = capi.lib()
+    rng = np.random.Generator(np.random.PCG64(0))
+    edge = [0, 1, -1, 2, -2, 254, 255, 256, -255, -256, 65535, -65535, 65536, 2**31 - 1, -(2**31), -(2**31) + 1]
+    qs = list(range(1, 70)) + [127, 128, 255, 256, 257, 641, 1000, 4095, 4096, 32768, 65535, 65536, 65537,
+                                (1 << 20) + 7, 2**31 - 1, 2**30, 715827883]
+    for q in qs:
+        vals = edge + [int(v) for v in rng.integers(-2**31, 2**31 - 1, 300)] + list(range(-600, 600, 7)) + \
+            [k * q + o for k in (-3, -1, 1, 2, 1000) for o in (-1, 0, 1) if -2**31 <= k * q + o < 2**31]
+        for v in vals:
+            want = abs(v) // q * (1 if v >= 0 else -1)
+            assert L.fri_quant_divide(v, q) == want, (v, q)
+
+
+def test_shard_frames_partitions_the_batch():
+    for n in (0, 1, 7, 16, 255, 256):
+        for world in (1, 2, 3, 4, 8):
+            seen = []
+            for r in range(world):
+                sh = sharding.shard_frames(n, r, world)
+                seen += list(sh)
+                for f in sh:
+                    assert sharding.frame_owner(f, n, world) == r
+            assert seen == list(range(n))
+            sizes = [len(sharding.shard_frames(n, r, world)) for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+from frave_b200 import sharding
+from oracle import c_oracle as O
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+rank, world = dist.get_rank(), dist.get_world_size()
+n_frames, h, w, c = 5, 40, 56, 3
+frames = [np.random.Generator(np.random.PCG64(100 + f)).integers(0, 256, (h, w, c), dtype=np.uint8) for f in range(n_frames)]
+mine = sharding.shard_frames(n_frames, rank, world)
+# each rank transforms only its own frames (no data-path collective); a checksum of checksums is
+# all-reduced for the test only, like the timing reduction in bench.py
+local = 0
+for f in mine:
+    _, coef, _ = O.from_raster(frames[f])
+    local += int(coef.astype(np.int64).sum()) * (f + 1)
+t = torch.tensor([local, len(mine)], dtype=torch.int64)
+dist.all_reduce(t)
+want = sum(int(O.from_raster(frames[f])[1].astype(np.int64).sum()) * (f + 1) for f in range(n_frames))
+assert t[0].item() == want and t[1].item() == n_frames, (t, want)
+el = torch.tensor([1.0 + rank])
+dist.all_reduce(el, op=dist.ReduceOp.MAX)
+assert el.item() == 2.0
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_two_rank_sharding_over_gloo(tmp_path):
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                              text=True) for r in range(2)]
+    for r, p in enumerate(procs):
+        out, _ = p.communicate(timeout=240)
+        assert p.returncode == 0, out
+        assert f"rank {r} ok" in out

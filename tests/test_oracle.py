@@ -1,0 +1,123 @@
+"""CPU suite: the oracle (oracle/fri_oracle.c and its numpy twin) against the known-answer
+digests of SURVEY.md §8(c), against each other, against the committed golden fixtures and
+against the algebraic properties the reference guarantees (losslessness at q == 1)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle as O
+from oracle import fri_oracle_np as N
+from tests.conftest import smallest_layer_q, uniform_image
+from tests.golden import make_golden
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+KAT = json.load(open(os.path.join(GOLDEN, "survey_kat.json")))["cases"]
+
+
+def _q(case):
+    q = np.ones(32, np.int32)
+    q[8], q[9] = case["q8"], case["q9"]
+    return q
+
+
+@pytest.mark.parametrize("case", KAT, ids=lambda c: f"{c['w']}x{c['h']}x{c['c']}_q{c['q8']}")
+@pytest.mark.parametrize("impl", ["c", "numpy"])
+def test_survey_known_answers(case, impl):
+    img = N.survey_image(case["w"], case["h"], case["c"])
+    if impl == "c":
+        centers, coef, some = O.from_raster(img)
+        coef = O.quantize(coef, some, _q(case))
+        assert len(O.fractal_divide(case["w"], case["h"])) == case.get("built", len(O.fractal_divide(case["w"], case["h"])))
+    else:
+        centers, coef, some = N.from_raster(img)
+        coef = N.quantize(coef, some, _q(case))
+    digest, n_some, total = N.kat_hash(np.asarray(centers), np.asarray(coef), np.asarray(some))
+    assert digest == case["sha256"]
+    assert total == case["sum"]
+    if "some" in case:
+        assert n_some == case["some"]
+    if "retained" in case:
+        assert len(centers) == case["retained"]
+    if "tile" in case:
+        t = [tuple(x) for x in np.asarray(centers).tolist()].index(tuple(case["tile"]))
+        if "coef_head" in case:
+            assert coef[t, 0, :8].tolist() == case["coef_head"]
+        assert [int(coef[t, 0, i]) for i in (255, 256, 511)] == case["coef_255_256_511"]
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (10, 10, 3), (37, 100, 3), (64, 48, 1), (131, 77, 3), (300, 7, 3)])
+def test_c_oracle_matches_numpy_oracle(shape):
+    h, w, c = shape
+    img = uniform_image(h, w, c, seed=h * 1000 + w)
+    cc, ck, cs = O.from_raster(img)
+    nc, nk, ns = N.from_raster(img)
+    assert np.array_equal(cc, nc) and np.array_equal(ck, nk) and np.array_equal(cs, ns)
+    q = smallest_layer_q(7)
+    q[0], q[3] = 2, 3
+    assert np.array_equal(O.quantize(ck, cs, q), N.quantize(nk, ns, q))
+    assert np.array_equal(O.quantize(ck, cs, q, multiply=True), N.quantize(nk, ns, q, multiply=True))
+    rec_c = O.extract_values(cc, ck, cs, h, w)
+    rec_n = N.inverse_tiles(nc, nk, ns, 9, h, w)
+    assert np.array_equal(rec_c, rec_n)
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16])
+@pytest.mark.parametrize("shape", [(64, 48, 1), (90, 125, 3), (257, 33, 3)])
+def test_lossless_roundtrip_on_cpu(shape, dtype):
+    h, w, c = shape
+    img = uniform_image(h, w, c, seed=5, dtype=dtype)
+    centers, coef, some = O.from_raster(img)
+    rec = O.extract_values(centers, coef, some, h, w, dtype=dtype)
+    covered = np.zeros((h, w), bool)
+    off = N.leaf_offsets(9)
+    for cx, cy in centers.tolist():
+        x, y = cx + off[:, 0], cy + off[:, 1]
+        ok = (x >= 0) & (y >= 0) & (x < w) & (y < h)
+        assert not covered[y[ok], x[ok]].any()  # every pixel owned by exactly one tile
+        covered[y[ok], x[ok]] = True
+    assert np.array_equal(rec[covered], img[covered])
+    assert not rec[~covered].any()  # from_wavelet zero-initialises (wavelet_transform.rs:309-317)
+
+
+def test_quant_layer_formula():
+    # quantization.rs:13: layer = trailing_zeros(prev_power_two(i + 1)) = floor(log2(i + 1))
+    layers = N.quant_layers(9)
+    assert layers[0] == 0 and layers[1] == 1 and layers[2] == 1 and layers[3] == 2
+    assert layers[254] == 7 and layers[255] == 8 and layers[510] == 8 and layers[511] == 9
+    for i in range(512):
+        assert (1 << layers[i]) == O.lib().fri_oracle_prev_power_two(i + 1)
+
+
+def test_truncating_division_semantics():
+    coef = np.array([[[-7, 7, -1, 1, -255, 255, 0, -8] + [0] * 504]], np.int32)
+    some = np.ones_like(coef, bool)
+    q = np.full(32, 4, np.int32)
+    out = O.quantize(coef, some, q)
+    assert out[0, 0, :8].tolist() == [-1, 1, 0, 0, -63, 63, 0, -2]
+    none = some.copy()
+    none[0, 0, 0] = False
+    assert O.quantize(coef, none, q)[0, 0, 0] == -7  # None is skipped
+
+
+@pytest.mark.parametrize("name", sorted(make_golden.CASES))
+def test_golden_fixtures_match_oracle(name):
+    fx = np.load(os.path.join(GOLDEN, name + ".npz"))
+    fresh = make_golden.make(name)
+    for k in fresh:
+        assert np.array_equal(fx[k], fresh[k]), k
+
+
+def test_fringe_and_retained_counts():
+    # 512x512 -> 617 built / 578 retained / 448 full
+    built = O.fractal_divide(512, 512)
+    assert len(built) == 617
+    img = np.zeros((512, 512, 1), np.uint8)
+    centers, _, some = O.from_raster(img)
+    assert len(centers) == 578
+    off = N.leaf_offsets(9)
+    x, y = centers[:, 0:1] + off[None, :, 0], centers[:, 1:2] + off[None, :, 1]
+    inside = (x >= 0) & (y >= 0) & (x < 512) & (y < 512)
+    assert int(inside.all(axis=1).sum()) == 448
+    assert int(inside.sum()) == 512 * 512
