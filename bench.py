@@ -33,6 +33,8 @@ import numpy as np  # noqa: E402
 METRIC = "MPix/s fractal transform+quant (enc/dec)"
 UNIT = "MPix/s"
 W, H, C = 4096, 4096, 3
+FRAMES = 1                  # frames per GPU per step (one batched launch per direction)
+PREHEAT_S = 1.0
 SMALLEST_LAYER_DIVISOR = 4  # q[8] = q[9] = 4: "dividing the smallest layer of fractals" (README.md:12)
 BYTES_PER_SAMPLE = 5        # u8 pixel + i32 coefficient, either direction
 N_SETS = 4                  # rotating buffer sets: 4 x (50 + 201 + 50 MB) = 1.2 GB >> 126 MB of L2
@@ -46,13 +48,14 @@ def quant_matrix() -> np.ndarray:
 
 def workload_config(n_gpus: int) -> dict:
     return {
-        "workload": f"{W}x{H}x{C} u8 synthetic image (BASELINE.json configs[1]); step = fused transform+quant encode "
-                    f"then fused dequant+inverse decode of one frame per GPU",
-        "frames_per_gpu": 1,
-        "global_frames": n_gpus,
+        "workload": f"{W}x{H}x{C} u8 synthetic image{' (BASELINE.json configs[1])' if (W, H, C, FRAMES) == (4096, 4096, 3, 1) else ''}"
+                    f"; step = fused transform+quant encode then fused dequant+inverse decode of {FRAMES} frame(s) per GPU",
+        "frames_per_gpu": FRAMES,
+        "global_frames": n_gpus * FRAMES,
         "depth": 9,
         "quant": f"q[8]=q[9]={SMALLEST_LAYER_DIVISOR}, other layers 1; decode divides again like quantization.rs:37",
-        "l2": f"inputs rotate over {N_SETS} buffer sets (1.2 GB) so every timed launch reads cold HBM",
+        "l2": f"inputs rotate over {N_SETS} buffer sets ({N_SETS * FRAMES * W * H * C * 6 / 1e9:.1f} GB) so every timed "
+              f"launch reads cold HBM",
         "parallelism": f"frames sharded over {n_gpus} GPU(s), no collective",
     }
 
@@ -202,21 +205,23 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
 
     # ---- buffers: N_SETS rotating sets, synthetic pixels generated per rank
     img0 = synthetic_image(2 + rank)
-    px = [torch.from_numpy(img0).to(dev)]
     gen = torch.Generator(device=dev).manual_seed(1000 + rank)
-    for _ in range(1, N_SETS):
-        px.append(torch.randint(0, 256, (H, W, C), generator=gen, device=dev, dtype=torch.int32).to(torch.uint8))
-    coefs = [torch.empty(plan.coef_shape, dtype=torch.int32, device=dev) for _ in range(N_SETS)]
-    outs = [torch.empty((H, W, C), dtype=torch.uint8, device=dev) for _ in range(N_SETS)]
+    px = []
+    for _ in range(N_SETS):
+        t = torch.randint(0, 256, (FRAMES, H, W, C), generator=gen, device=dev, dtype=torch.int32).to(torch.uint8)
+        px.append(t)
+    px[0][0] = torch.from_numpy(img0).to(dev)
+    coefs = [torch.empty((FRAMES,) + plan.coef_shape, dtype=torch.int32, device=dev) for _ in range(N_SETS)]
+    outs = [torch.empty((FRAMES, H, W, C), dtype=torch.uint8, device=dev) for _ in range(N_SETS)]
 
     # sanity (untimed): encode -> decode is the identity at q == 1
-    plan.encode_device(px[0].data_ptr(), 1, coefs[0].data_ptr(), None, stream)
-    plan.decode_device(coefs[0].data_ptr(), 1, outs[0].data_ptr(), None, False, stream)
+    plan.encode_device(px[0].data_ptr(), FRAMES, coefs[0].data_ptr(), None, stream)
+    plan.decode_device(coefs[0].data_ptr(), FRAMES, outs[0].data_ptr(), None, False, stream)
     torch.cuda.synchronize()
     if not torch.equal(px[0], outs[0]):
         raise RuntimeError("sanity check failed: encode -> decode is not lossless at q == 1")
     for s in range(N_SETS):
-        plan.encode_device(px[s].data_ptr(), 1, coefs[s].data_ptr(), q, stream)
+        plan.encode_device(px[s].data_ptr(), FRAMES, coefs[s].data_ptr(), q, stream)
     torch.cuda.synchronize()
 
     launches = 0
@@ -226,20 +231,20 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
         a, b = i % N_SETS, (i + N_SETS // 2) % N_SETS
         if ev:
             ev[0].record()
-        plan.encode_device(px[a].data_ptr(), 1, coefs[a].data_ptr(), q, stream)
+        plan.encode_device(px[a].data_ptr(), FRAMES, coefs[a].data_ptr(), q, stream)
         launches += plan.last_launches
         if ev:
             ev[1].record()
-        plan.decode_device(coefs[b].data_ptr(), 1, outs[b].data_ptr(), q, False, stream)
+        plan.decode_device(coefs[b].data_ptr(), FRAMES, outs[b].data_ptr(), q, False, stream)
         launches += plan.last_launches
         if ev:
             ev[2].record()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    t_end = time.perf_counter() + 1.0  # pre-heat so clocks are sampled under the same load
+    t_end = time.perf_counter() + PREHEAT_S  # pre-heat so clocks are sampled under the same load
     i = 0
     while time.perf_counter() < t_end:
-        for _ in range(50):
+        for _ in range(max(1, 50 // FRAMES)):
             step(i)
             i += 1
         torch.cuda.synchronize()
@@ -291,11 +296,11 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
         dist.barrier()
 
     if rank == 0:
-        pix_step = W * H * world  # pixels through encode+decode per step, all GPUs
+        pix_step = W * H * FRAMES * world  # pixels through encode+decode per step, all GPUs
         value = pix_step * args.steps / (elapsed_ms * 1e-3) / 1e6
-        e2e_value = pix_step * e2e_steps / e2e_s / 1e6
+        e2e_value = W * H * world * e2e_steps / e2e_s / 1e6  # one frame per GPU per e2e step
         peak, peak_src = measured_peak_gbs()
-        alg_bytes = W * H * C * BYTES_PER_SAMPLE
+        alg_bytes = W * H * C * FRAMES * BYTES_PER_SAMPLE
 
         def roof(ms: float, kernel: str) -> dict:
             ach = alg_bytes / (ms * 1e-3) / 1e9
@@ -303,18 +308,18 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
                     "traffic": ncu_traffic(kernel), "algorithmic_bytes": alg_bytes, "avg_launch_ms": ms,
                     "peak_source": peak_src}
 
-        r_enc, r_dec = roof(enc_ms, "fri_encode_kernel<3,u8>"), roof(dec_ms, "fri_decode_kernel<3,u8>")
+        r_enc, r_dec = roof(enc_ms, f"fri_encode_kernel<{C},u8>"), roof(dec_ms, f"fri_decode_kernel<{C},u8>")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "i32", "data": "synthetic", "config": workload_config(world),
-            "encode_mpix_s": W * H * world / (enc_ms * 1e-3) / 1e6, "decode_mpix_s": W * H * world / (dec_ms * 1e-3) / 1e6,
+            "encode_mpix_s": pix_step / (enc_ms * 1e-3) / 1e6, "decode_mpix_s": pix_step / (dec_ms * 1e-3) / 1e6,
             "roofline": r_enc if enc_ms >= dec_ms else r_dec, "roofline_encode": r_enc, "roofline_decode": r_dec,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "fri_encode_tq + fri_decode_tq (host buffers, pinned)"},
             "gpu_launches": timed_launches, "clocks": clocks, "launch": plan.launch_info(),
         }
-        if world == 1:
+        if world == 1 and not args.no_cpu:
             from oracle import c_oracle as O
             centers = plan.centers()
             coef_buf = np.empty(plan.coef_shape, np.int32)
@@ -340,7 +345,15 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--shape", default=None, help="WxHxC override for experiments (default: BASELINE.json configs[1])")
+    ap.add_argument("--frames", type=int, default=1, help="frames per GPU per step (batched launch)")
+    ap.add_argument("--preheat", type=float, default=1.0, help="seconds of untimed load before the warm-up steps")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (experiments only)")
     args = ap.parse_args()
+    global W, H, C, FRAMES, PREHEAT_S
+    if args.shape:
+        W, H, C = (int(v) for v in args.shape.lower().split("x"))
+    FRAMES, PREHEAT_S = args.frames, args.preheat
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

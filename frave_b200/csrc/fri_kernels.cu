@@ -365,6 +365,14 @@ fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
     const int n_tasks = __popc(gd.tile_mask) * C;
     const int lane_off = lane_anchor_bytes(lane, g.pitch, PB);
     const bool any_q = qp.active != 0;
+    // A lattice tile the reference's BFS never built (possible only next to the image border,
+    // e.g. 480x270) still owns its pixels in the ownership bitmap: stage zeros for it, which is
+    // what from_wavelet's zero-initialised raster holds there (wavelet_transform.rs:309-317).
+    if (__popc(gd.tile_mask) != g.group_a * g.group_b) {
+        const int n16 = (g.region_h * g.pitch + 15) >> 4;
+        for (int i = threadIdx.x; i < n16; i += kThreads) reinterpret_cast<int4 *>(region)[i] = make_int4(0, 0, 0, 0);
+        __syncthreads();
+    }
     for (int task = warp; task < n_tasks; task += kWarps) {
         const int e = task / C, ch = task - e * C;
         const int slot = (gd.tile_mask & (gd.tile_mask + 1u)) ? (int)__fns(gd.tile_mask, 0, e + 1) : e;
