@@ -56,7 +56,7 @@ struct fri_plan {
     Plan plan;
     int device = -1;
     DeviceTables tables;
-    void *d_groups = nullptr, *d_tile_unit = nullptr, *d_ownership = nullptr;
+    void *d_groups = nullptr, *d_tile_unit = nullptr, *d_chunk_mask = nullptr, *d_chunk_list = nullptr;
     Slot slots[kSlots];
     bool slots_ready = false;
     int32_t *d_dc_shared = nullptr;  // low-pass scratch for the *_device entry points (depth > 9)
@@ -180,14 +180,16 @@ int fri_plan_create(fri_plan **out, int device, uint32_t width, uint32_t height,
         if (e == cudaSuccess) e = upload(&p->d_groups, pl.groups.data(), pl.groups.size() * sizeof(GroupDesc));
         if (e == cudaSuccess && pl.geo.sub_bits > 0)
             e = upload(&p->d_tile_unit, pl.tile_unit.data(), pl.tile_unit.size() * sizeof(uint32_t));
-        if (e == cudaSuccess) e = upload(&p->d_ownership, pl.ownership.data(), pl.ownership.size() * sizeof(uint32_t));
+        if (e == cudaSuccess) e = upload(&p->d_chunk_mask, pl.chunk_mask.data(), pl.chunk_mask.size() * sizeof(uint16_t));
+        if (e == cudaSuccess) e = upload(&p->d_chunk_list, pl.chunk_list.data(), pl.chunk_list.size() * sizeof(uint32_t));
         if (e != cudaSuccess) {
             fri_plan_destroy(p);
             return cuda_fail(e, "uploading the plan tables");
         }
         p->tables.groups = static_cast<const GroupDesc *>(p->d_groups);
         p->tables.tile_unit = static_cast<const uint32_t *>(p->d_tile_unit);
-        p->tables.ownership = static_cast<const uint32_t *>(p->d_ownership);
+        p->tables.chunk_mask = static_cast<const uint16_t *>(p->d_chunk_mask);
+        p->tables.chunk_list = static_cast<const uint32_t *>(p->d_chunk_list);
     }
     *out = p;
     return FRI_OK;
@@ -206,7 +208,8 @@ void fri_plan_destroy(fri_plan *p)
         if (p->d_dc_shared) cudaFree(p->d_dc_shared);
         if (p->d_groups) cudaFree(p->d_groups);
         if (p->d_tile_unit) cudaFree(p->d_tile_unit);
-        if (p->d_ownership) cudaFree(p->d_ownership);
+        if (p->d_chunk_mask) cudaFree(p->d_chunk_mask);
+        if (p->d_chunk_list) cudaFree(p->d_chunk_list);
     }
     delete p;
 }
@@ -365,6 +368,6 @@ void fri_host_free(void *p)
 
 uint32_t fri_plan_last_launches(const fri_plan *p) { return p ? p->last_launches : 0; }
 
-int32_t fri_quant_divide(int32_t value, int32_t q) { return trunc_div(value, make_div(q)); }
+int32_t fri_quant_divide(int32_t value, int32_t q) { return q <= 1 ? value : trunc_div(value, make_div(q)); }
 
 }  // extern "C"

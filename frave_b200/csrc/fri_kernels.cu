@@ -35,24 +35,28 @@ namespace fri {
 // ------------------------------------------------------------------------------------------
 Div make_div(int32_t q)
 {
-    const uint32_t d = q < 1 ? 1u : (uint32_t)q;
-    uint32_t fl = 0;
-    while ((d >> (fl + 1)) != 0) ++fl;  // floor(log2 d)
-    if ((d & (d - 1)) == 0) return Div{0u, fl};
-    const uint64_t num = (uint64_t)1 << (32 + fl);
-    uint32_t m = (uint32_t)(num / d);
-    const uint32_t rem = (uint32_t)(num - (uint64_t)m * d);
-    const uint32_t e = d - rem;
-    uint32_t more;
-    if (e < (1u << fl)) {
-        more = fl;  // a 32-bit magic is exact
-    } else {         // 33-bit magic: keep the low 32 bits and fix up with the add step
-        m += m;
-        const uint32_t twice = rem + rem;
-        if (twice >= d || twice < rem) m += 1;
-        more = fl | kDivAdd;
-    }
-    return Div{m + 1u, more};
+    // Signed magic number for a divisor d >= 2 (Hacker's Delight, fig. 10-1, positive d only):
+    // the smallest p >= 32 with 2^p > nc * (d - 2^p mod d), nc = 2^31 - 1 - (2^31 mod d).
+    const uint32_t d = q < 2 ? 2u : (uint32_t)q;
+    const uint32_t two31 = 0x80000000u;
+    const uint32_t nc = two31 - 1u - two31 % d;
+    int p = 31;
+    uint32_t q1 = two31 / nc, r1 = two31 - q1 * nc;  // 2^p / nc
+    uint32_t q2 = two31 / d, r2 = two31 - q2 * d;    // 2^p / d
+    uint32_t delta;
+    do {
+        ++p;
+        q1 *= 2; r1 *= 2;
+        if (r1 >= nc) { ++q1; r1 -= nc; }
+        q2 *= 2; r2 *= 2;
+        if (r2 >= d) { ++q2; r2 -= d; }
+        delta = d - r2;
+    } while (q1 < delta || (q1 == delta && r1 == 0));
+    Div dv;
+    dv.magic = (int32_t)(q2 + 1u);
+    dv.addmask = dv.magic < 0 ? -1 : 0;
+    dv.shift = p - 32;
+    return dv;
 }
 
 void make_quant_params(QuantParams &qp, const int32_t *q, int multiply)
@@ -64,7 +68,8 @@ void make_quant_params(QuantParams &qp, const int32_t *q, int multiply)
         const Div dv = make_div(v);
         qp.q[l] = v;
         qp.magic[l] = dv.magic;
-        qp.more[l] = (uint8_t)dv.more;
+        qp.addmask[l] = dv.addmask;
+        qp.shift[l] = dv.shift;
         if (v != 1) qp.active |= 1u << l;
     }
 }
@@ -90,29 +95,53 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ int wsub(int a, int b) { return (int)((unsigned)a - (unsigned)b); }
 __device__ __forceinline__ int wadd(int a, int b) { return (int)((unsigned)a + (unsigned)b); }
 
+// d / 2 with Rust/C truncation toward zero.  Written in PTX so that the compiler keeps it a
+// 32-bit add-sign-bit + arithmetic shift (it otherwise narrows the arithmetic on 8-bit samples
+// to 16 bits and pays for it in masks and sign extensions).
+__device__ __forceinline__ int half_trunc(int d)
+{
+    int h;
+    asm("{\n\t.reg .s32 t;\n\tshr.u32 t, %1, 31;\n\tadd.s32 t, t, %1;\n\tshr.s32 %0, t, 1;\n\t}" : "=r"(h) : "r"(d));
+    return h;
+}
 // forward lifting of one node: d = l - r; s = r + d/2 (truncating)   wavelet_transform.rs:211-218
 __device__ __forceinline__ void lift(int l, int r, int &d, int &s)
 {
     d = wsub(l, r);
-    s = wadd(r, d / 2);
+    s = wadd(r, half_trunc(d));
 }
 // inverse lifting of one node: r = s - d/2; l = d + r                 wavelet_transform.rs:366-367
 __device__ __forceinline__ void unlift(int s, int d, int &l, int &r)
 {
-    r = wsub(s, d / 2);
+    r = wsub(s, half_trunc(d));
     l = wadd(d, r);
-}
-
-// quantization::encode of one coefficient                            quantization.rs:19
-__device__ __forceinline__ int quant1(int d, Div dv) { return trunc_div(d, dv); }
-// quantization::decode of one coefficient                            quantization.rs:37
-__device__ __forceinline__ int dequant1(int d, Div dv, int q, int multiply)
-{
-    return multiply ? (int)((unsigned)d * (unsigned)q) : trunc_div(d, dv);
 }
 
 // floor(log2(pos + 1)): the reference's layer index of heap position pos (quantization.rs:13)
 __device__ __forceinline__ int layer_of(uint32_t pos) { return 31 - __clz((int)(pos + 1u)); }
+
+// quantization::encode (quantization.rs:19) / ::decode (:37) of one coefficient of layer l.
+// The branch is uniform whenever l is.
+__device__ __forceinline__ int quant_layer(const QuantParams &qp, int d, int l)
+{
+    return ((qp.active >> l) & 1u) ? trunc_div(d, qp.div(l)) : d;
+}
+__device__ __forceinline__ int dequant_layer(const QuantParams &qp, int d, int l)
+{
+    if (!((qp.active >> l) & 1u)) return d;
+    return qp.multiply ? (int)((unsigned)d * (unsigned)qp.q[l]) : trunc_div(d, qp.div(l));
+}
+
+template <typename S>
+__device__ __forceinline__ S clamp_sample(int v)  // images.rs:109 (u16: the 16-bit extension)
+{
+    uint32_t r;
+    if (sizeof(S) == 1)
+        asm("cvt.sat.u8.s32 %0, %1;" : "=r"(r) : "r"(v));
+    else
+        asm("cvt.sat.u16.s32 %0, %1;" : "=r"(r) : "r"(v));
+    return (S)r;
+}
 
 __device__ __forceinline__ int lane_anchor_bytes(int lane, int pitch, int pixel_bytes)
 {
@@ -127,18 +156,27 @@ __device__ __forceinline__ int lane_anchor_bytes(int lane, int pitch, int pixel_
     return y * pitch + x * pixel_bytes;
 }
 
-// Per-CTA view of the staged region.
+// Per-CTA view of the staged region.  Shared-memory byte s of the region image corresponds to
+// global byte gbase0 + r * delta + s for a byte of staged row r (delta = row_stride - pitch is a
+// multiple of 16, gbase0 is 16-byte aligned), so 16-byte chunks are aligned on both sides.
 struct RegionView {
-    int64_t a0;   // global address of region pixel (0, 0) of this frame (may lie outside the frame)
-    int phi0;     // a0 & 15: the region keeps the global 16-byte phase in shared memory
+    int64_t gbase0;  // global address of shared-memory offset 0 of row 0
+    int delta;       // row_stride - pitch
+    int phi0;        // shared-memory offset of region pixel (0, 0): its global address & 15
+    int xb0;         // byte offset of region column 0 inside its image row (x0 * pixel bytes)
+    bool interior;   // the whole staged region lies inside the image
 };
 
 template <int PB>
 __device__ __forceinline__ RegionView region_view(const Geometry &g, const GroupDesc &gd, const void *frame_base)
 {
     RegionView v;
-    v.a0 = (int64_t)(uintptr_t)frame_base + (int64_t)gd.y0 * g.row_stride + (int64_t)gd.x0 * PB;
-    v.phi0 = (int)(v.a0 & 15);
+    const int64_t a0 = (int64_t)(uintptr_t)frame_base + (int64_t)gd.y0 * g.row_stride + (int64_t)gd.x0 * PB;
+    v.phi0 = (int)(a0 & 15);
+    v.gbase0 = a0 - v.phi0;
+    v.delta = (int)(g.row_stride - g.pitch);
+    v.xb0 = gd.x0 * PB;
+    v.interior = gd.x0 >= 0 && gd.y0 >= 0 && gd.x0 + g.region_w <= g.width && gd.y0 + g.region_h <= g.height;
     return v;
 }
 
@@ -171,6 +209,28 @@ __device__ __forceinline__ TaskAddr task_addr(const Geometry &g, const uint32_t 
     return a;
 }
 
+// Stores the bytes of one 16-byte chunk selected by mask m (bit j = byte j) to global memory.
+__device__ __forceinline__ void store_chunk_masked(uint8_t *gp, const uint8_t *sp, uint32_t m)
+{
+    const int4 v = *reinterpret_cast<const int4 *>(sp);
+    if (m == 0xffffu) {
+        *reinterpret_cast<int4 *>(gp) = v;
+        return;
+    }
+    const uint32_t w[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t nib = (m >> (4 * k)) & 15u;
+        if (nib == 15u) {
+            *reinterpret_cast<uint32_t *>(gp + 4 * k) = w[k];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if ((nib >> j) & 1u) gp[4 * k + j] = (uint8_t)(w[k] >> (8 * j));
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // encode: pixels -> quantized coefficients
 // ------------------------------------------------------------------------------------------
@@ -178,7 +238,8 @@ template <int C, typename S>
 __global__ void __launch_bounds__(kThreads, 4)
 fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ QuantParams qp,
                   const GroupDesc *__restrict__ groups, const uint32_t *__restrict__ tile_unit,
-                  const uint8_t *__restrict__ pixels, int32_t *__restrict__ coefs, int32_t *__restrict__ dc_out)
+                  const uint32_t *__restrict__ chunk_list, const uint8_t *__restrict__ pixels,
+                  int32_t *__restrict__ coefs, int32_t *__restrict__ dc_out)
 {
     constexpr int SB = (int)sizeof(S);
     constexpr int PB = C * SB;
@@ -191,30 +252,36 @@ fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
     const int frame = blockIdx.y;
     const uint8_t *fbase = pixels + (int64_t)frame * g.frame_bytes;
     const RegionView rv = region_view<PB>(g, gd, fbase);
-
-    // ---- stage the group's pixel footprint: one warp per row, one lane per 16-byte chunk.
-    for (int r = warp; r < g.region_h; r += kWarps) {
-        const int y = gd.y0 + r;
-        const int srow = r * g.pitch + rv.phi0;  // shared-memory offset of region pixel (r, 0)
-        const int sbase = srow & ~15;
-        const int send = srow + g.row_bytes;
-        const bool yin = (unsigned)y < (unsigned)g.height;
-        const int64_t row_lo = (int64_t)(uintptr_t)fbase + (int64_t)y * g.row_stride;  // in-image bytes of row y
-        const int64_t row_hi = row_lo + g.row_stride;
-        const int64_t gbase = rv.a0 + (int64_t)r * g.row_stride - (srow & 15);  // floor16(global row start)
-        for (int c = lane; c < g.chunks_per_row; c += 32) {
-            const int s = sbase + 16 * c;
-            if (s >= send) break;
-            const int64_t ga = gbase + 16 * c;
-            if (yin && ga >= row_lo && ga + 16 <= row_hi) {
-                cp_async_16(region + s, reinterpret_cast<const void *>(ga));
-            } else if (!yin || ga + 16 <= row_lo || ga >= row_hi) {
-                *reinterpret_cast<int4 *>(region + s) = make_int4(0, 0, 0, 0);
-            } else {  // chunk straddles the left or right image edge
-                const uint8_t *gp = reinterpret_cast<const uint8_t *>(ga);
+    // ---- stage the group's pixel footprint: one 16-byte chunk (aligned in global and in shared
+    // memory) per thread and iteration, taken from the plan's list of chunks that hold at least
+    // one pixel of this group's tiles.
+    {
+        const uint32_t *cl = chunk_list + (size_t)rv.phi0 * g.list_cap;
+        const int n_all = g.list_all[rv.phi0];
+        if (rv.interior) {
+            for (int k = threadIdx.x; k < n_all; k += kThreads) {
+                const uint32_t e = __ldg(cl + k);
+                const int r = (int)(e >> 16), s = (int)(e & 0xffffu) << 4;
+                cp_async_16(region + s, reinterpret_cast<const uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s);
+            }
+        } else {
+            const int stride32 = (int)g.row_stride;
+            for (int k = threadIdx.x; k < n_all; k += kThreads) {
+                const uint32_t e = __ldg(cl + k);
+                const int r = (int)(e >> 16), s = (int)(e & 0xffffu) << 4;
+                const int y = gd.y0 + r;
+                const bool yin = (unsigned)y < (unsigned)g.height;
+                const int xb = rv.xb0 + s - (r * g.pitch + rv.phi0);  // byte position of the chunk inside image row y
+                const uint8_t *gp = reinterpret_cast<const uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s;
+                if (yin && xb >= 0 && xb + 16 <= stride32) {
+                    cp_async_16(region + s, gp);
+                } else if (!yin || xb + 16 <= 0 || xb >= stride32) {
+                    *reinterpret_cast<int4 *>(region + s) = make_int4(0, 0, 0, 0);
+                } else {  // chunk straddles the left or right image edge
 #pragma unroll 1
-                for (int j = 0; j < 16; ++j)
-                    region[s + j] = (ga + j >= row_lo && ga + j < row_hi) ? __ldg(gp + j) : (uint8_t)0;
+                    for (int j = 0; j < 16; ++j)
+                        region[s + j] = (xb + j >= 0 && xb + j < stride32) ? __ldg(gp + j) : (uint8_t)0;
+                }
             }
         }
     }
@@ -223,14 +290,15 @@ fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
 
     // ---- one (base tile, channel) task per warp iteration
     const int n_tasks = __popc(gd.tile_mask) * C;
-    const int lane_off = lane_anchor_bytes(lane, g.pitch, PB);
-    const bool any_q = qp.active != 0;
+    const uint8_t *lane_base = region + rv.phi0 + lane_anchor_bytes(lane, g.pitch, PB);
+    const int half = kHalfB.y * g.pitch + kHalfB.x * PB;
+    const int top = g.sub_bits;  // fractal level of a base tile's root
+    const bool sparse_group = (gd.tile_mask & (gd.tile_mask + 1u)) != 0;
     for (int task = warp; task < n_tasks; task += kWarps) {
         const int e = task / C, ch = task - e * C;
-        const int slot = (gd.tile_mask & (gd.tile_mask + 1u)) ? (int)__fns(gd.tile_mask, 0, e + 1) : e;
-        const uint8_t *p0 = region + rv.phi0 + g.tile_rel_y[slot] * g.pitch + g.tile_rel_x[slot] * PB + lane_off + ch * SB;
+        const int slot = sparse_group ? (int)__fns(gd.tile_mask, 0, e + 1) : e;
+        const uint8_t *p0 = lane_base + g.tile_off[slot] + ch * SB;
         const uint8_t *p1 = p0 + g.pitch, *p2 = p1 + g.pitch;
-        const int half = kHalfB.y * g.pitch + kHalfB.x * PB;
 
         // gather: leaf i of a depth-3 subtree sits at sub_leaf(i) from the subtree's first leaf
         int v[8], w[8];
@@ -247,7 +315,6 @@ fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
 
         const TaskAddr ta = task_addr<C>(g, tile_unit, frame, gd.tile_base + e, ch);
         int32_t *out = coefs + ta.block;
-        const int top = g.sub_bits;              // global level of the base tile's root
         const bool lastB = ta.last && lane == 31;  // this lane holds the last node of every level
 
         // levels 8, 7, 6 in registers
@@ -267,20 +334,29 @@ fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
         lift(sa7[0], sa7[1], a6, sA);
         lift(sb7[0], sb7[1], b6, sB);
 
-        if (any_q) {  // quantization.rs:13 — layer = level, except the last node of a level: level + 1
-            const Div m8 = qp.div(top + 8), m7 = qp.div(top + 7), m6 = qp.div(top + 6);
+        // quantization.rs:13 — layer = level, except the last node of a level: level + 1
+        if ((qp.active >> (top + 6)) & 0xfu) {
+            const int r8 = b8[3], r7 = b7[1], r6 = b6;  // unquantized values of the level-last nodes
+            if ((qp.active >> (top + 8)) & 1u) {
+                const Div dv = qp.div(top + 8);
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                a8[m] = quant1(a8[m], m8);
-                b8[m] = quant1(b8[m], (m == 3 && lastB) ? qp.div(top + 9) : m8);
+                for (int m = 0; m < 4; ++m) { a8[m] = trunc_div(a8[m], dv); b8[m] = trunc_div(b8[m], dv); }
             }
+            if ((qp.active >> (top + 7)) & 1u) {
+                const Div dv = qp.div(top + 7);
 #pragma unroll
-            for (int m = 0; m < 2; ++m) {
-                a7[m] = quant1(a7[m], m7);
-                b7[m] = quant1(b7[m], (m == 1 && lastB) ? m8 : m7);
+                for (int m = 0; m < 2; ++m) { a7[m] = trunc_div(a7[m], dv); b7[m] = trunc_div(b7[m], dv); }
             }
-            a6 = quant1(a6, m6);
-            b6 = quant1(b6, lastB ? m7 : m6);
+            if ((qp.active >> (top + 6)) & 1u) {
+                const Div dv = qp.div(top + 6);
+                a6 = trunc_div(a6, dv);
+                b6 = trunc_div(b6, dv);
+            }
+            if (lastB) {
+                b8[3] = quant_layer(qp, r8, top + 9);
+                b7[1] = quant_layer(qp, r7, top + 8);
+                b6 = quant_layer(qp, r6, top + 7);
+            }
         }
         {
             int32_t *o8 = out + ((size_t)ta.node << 8), *o7 = out + ((size_t)ta.node << 7), *o6 = out + ((size_t)ta.node << 6);
@@ -316,9 +392,9 @@ fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
         int2 t2 = *reinterpret_cast<const int2 *>(scratch + 2 * lane);
         __syncwarp();
         if (g.sub_bits == 0) {
-            if (any_q) {
-                t2.x = quant1(t2.x, qp.div(layer_of(2 * lane)));
-                t2.y = quant1(t2.y, qp.div(layer_of(2 * lane + 1)));
+            if (qp.active & 0x7fu) {  // positions 0..63 live in layers 0..6
+                t2.x = quant_layer(qp, t2.x, layer_of(2 * lane));
+                t2.y = quant_layer(qp, t2.y, layer_of(2 * lane + 1));
             }
             __stcs(reinterpret_cast<int2 *>(out) + lane, t2);
         } else {
@@ -332,7 +408,7 @@ fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
                 } else {
                     const int m = 31 - __clz((int)p);
                     const uint32_t pos = (ta.node << m) + p - (1u << m);
-                    out[pos] = any_q ? quant1(vals[k], qp.div(layer_of(pos))) : vals[k];
+                    out[pos] = quant_layer(qp, vals[k], layer_of(pos));
                 }
             }
         }
@@ -346,12 +422,11 @@ template <int C, typename S>
 __global__ void __launch_bounds__(kThreads, 4)
 fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ QuantParams qp,
                   const GroupDesc *__restrict__ groups, const uint32_t *__restrict__ tile_unit,
-                  const uint32_t *__restrict__ ownership, const int32_t *__restrict__ coefs,
-                  const int32_t *__restrict__ dc_in, uint8_t *__restrict__ pixels)
+                  const uint32_t *__restrict__ chunk_list, const uint16_t *__restrict__ chunk_mask,
+                  const int32_t *__restrict__ coefs, const int32_t *__restrict__ dc_in, uint8_t *__restrict__ pixels)
 {
     constexpr int SB = (int)sizeof(S);
     constexpr int PB = C * SB;
-    constexpr int kMaxVal = SB == 1 ? 255 : 65535;
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *region = smem;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -363,10 +438,12 @@ fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
     const RegionView rv = region_view<PB>(g, gd, fbase);
 
     const int n_tasks = __popc(gd.tile_mask) * C;
-    const int lane_off = lane_anchor_bytes(lane, g.pitch, PB);
-    const bool any_q = qp.active != 0;
+    uint8_t *lane_base = region + rv.phi0 + lane_anchor_bytes(lane, g.pitch, PB);
+    const int half = kHalfB.y * g.pitch + kHalfB.x * PB;
+    const int top = g.sub_bits;
+    const bool sparse_group = (gd.tile_mask & (gd.tile_mask + 1u)) != 0;
     // A lattice tile the reference's BFS never built (possible only next to the image border,
-    // e.g. 480x270) still owns its pixels in the ownership bitmap: stage zeros for it, which is
+    // e.g. 480x270) still owns its pixels in the chunk masks: stage zeros for it, which is
     // what from_wavelet's zero-initialised raster holds there (wavelet_transform.rs:309-317).
     if (__popc(gd.tile_mask) != g.group_a * g.group_b) {
         const int n16 = (g.region_h * g.pitch + 15) >> 4;
@@ -375,10 +452,9 @@ fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
     }
     for (int task = warp; task < n_tasks; task += kWarps) {
         const int e = task / C, ch = task - e * C;
-        const int slot = (gd.tile_mask & (gd.tile_mask + 1u)) ? (int)__fns(gd.tile_mask, 0, e + 1) : e;
+        const int slot = sparse_group ? (int)__fns(gd.tile_mask, 0, e + 1) : e;
         const TaskAddr ta = task_addr<C>(g, tile_unit, frame, gd.tile_base + e, ch);
         const int32_t *in = coefs + ta.block;
-        const int top = g.sub_bits;
         const bool lastB = ta.last && lane == 31;
 
         // coefficient loads: all issued before the first use
@@ -392,9 +468,9 @@ fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
         int2 t2;
         if (g.sub_bits == 0) {
             t2 = __ldcs(reinterpret_cast<const int2 *>(in) + lane);
-            if (any_q) {
-                t2.x = dequant1(t2.x, qp.div(layer_of(2 * lane)), qp.q[layer_of(2 * lane)], qp.multiply);
-                t2.y = dequant1(t2.y, qp.div(layer_of(2 * lane + 1)), qp.q[layer_of(2 * lane + 1)], qp.multiply);
+            if (qp.active & 0x7fu) {
+                t2.x = dequant_layer(qp, t2.x, layer_of(2 * lane));
+                t2.y = dequant_layer(qp, t2.y, layer_of(2 * lane + 1));
             }
         } else {
             int vals[2];
@@ -406,8 +482,7 @@ fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
                 } else {
                     const int m = 31 - __clz((int)p);
                     const uint32_t pos = (ta.node << m) + p - (1u << m);
-                    vals[k] = __ldcs(in + pos);
-                    if (any_q) vals[k] = dequant1(vals[k], qp.div(layer_of(pos)), qp.q[layer_of(pos)], qp.multiply);
+                    vals[k] = dequant_layer(qp, __ldcs(in + pos), layer_of(pos));
                 }
             }
             t2 = make_int2(vals[0], vals[1]);
@@ -416,21 +491,32 @@ fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
         *reinterpret_cast<int2 *>(scratch + 2 * lane) = t2;
         __syncwarp();
 
-        if (any_q) {
+        if ((qp.active >> (top + 6)) & 0xfu) {
+            const int r8 = b8.w, r7 = b7.y, r6 = b6;  // raw values of the level-last nodes
             const int mul = qp.multiply;
-            const int l8 = top + 8, l7 = top + 7, l6 = top + 6;
-            const Div d8 = qp.div(l8), d7 = qp.div(l7), d6 = qp.div(l6);
-            const int q8 = qp.q[l8], q7 = qp.q[l7], q6 = qp.q[l6];
-            a8.x = dequant1(a8.x, d8, q8, mul); a8.y = dequant1(a8.y, d8, q8, mul);
-            a8.z = dequant1(a8.z, d8, q8, mul); a8.w = dequant1(a8.w, d8, q8, mul);
-            b8.x = dequant1(b8.x, d8, q8, mul); b8.y = dequant1(b8.y, d8, q8, mul);
-            b8.z = dequant1(b8.z, d8, q8, mul);
-            b8.w = lastB ? dequant1(b8.w, qp.div(l8 + 1), qp.q[l8 + 1], mul) : dequant1(b8.w, d8, q8, mul);
-            a7.x = dequant1(a7.x, d7, q7, mul); a7.y = dequant1(a7.y, d7, q7, mul);
-            b7.x = dequant1(b7.x, d7, q7, mul);
-            b7.y = lastB ? dequant1(b7.y, d8, q8, mul) : dequant1(b7.y, d7, q7, mul);
-            a6 = dequant1(a6, d6, q6, mul);
-            b6 = lastB ? dequant1(b6, d7, q7, mul) : dequant1(b6, d6, q6, mul);
+            if ((qp.active >> (top + 8)) & 1u) {
+                const Div dv = qp.div(top + 8);
+                const int q = qp.q[top + 8];
+#define FRI_DQ(x) x = mul ? (int)((unsigned)(x) * (unsigned)q) : trunc_div(x, dv)
+                FRI_DQ(a8.x); FRI_DQ(a8.y); FRI_DQ(a8.z); FRI_DQ(a8.w);
+                FRI_DQ(b8.x); FRI_DQ(b8.y); FRI_DQ(b8.z); FRI_DQ(b8.w);
+            }
+            if ((qp.active >> (top + 7)) & 1u) {
+                const Div dv = qp.div(top + 7);
+                const int q = qp.q[top + 7];
+                FRI_DQ(a7.x); FRI_DQ(a7.y); FRI_DQ(b7.x); FRI_DQ(b7.y);
+            }
+            if ((qp.active >> (top + 6)) & 1u) {
+                const Div dv = qp.div(top + 6);
+                const int q = qp.q[top + 6];
+                FRI_DQ(a6); FRI_DQ(b6);
+#undef FRI_DQ
+            }
+            if (lastB) {
+                b8.w = dequant_layer(qp, r8, top + 9);
+                b7.y = dequant_layer(qp, r7, top + 8);
+                b6 = dequant_layer(qp, r6, top + 7);
+            }
         }
 
         // levels 0..5: every lane walks its own root-to-subtree path (broadcast reads)
@@ -463,10 +549,9 @@ fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
         unlift(sb8[3], b8.w, w[6], w[7]);
 
         // scatter into the staged region (clamp: images.rs:109)
-        uint8_t *p0 = region + rv.phi0 + g.tile_rel_y[slot] * g.pitch + g.tile_rel_x[slot] * PB + lane_off + ch * SB;
+        uint8_t *p0 = lane_base + g.tile_off[slot] + ch * SB;
         uint8_t *p1 = p0 + g.pitch, *p2 = p1 + g.pitch;
-        const int half = kHalfB.y * g.pitch + kHalfB.x * PB;
-#define FRI_ST(ptr, dx, val) (*reinterpret_cast<S *>((ptr) + (dx) * PB) = (S)min(max((val), 0), kMaxVal))
+#define FRI_ST(ptr, dx, val) (*reinterpret_cast<S *>((ptr) + (dx) * PB) = clamp_sample<S>(val))
         FRI_ST(p0, 0, v[0]);  FRI_ST(p1, 0, v[1]);
         FRI_ST(p1, -1, v[2]); FRI_ST(p2, -1, v[3]);
         FRI_ST(p0, 2, v[4]);  FRI_ST(p1, 2, v[5]);
@@ -479,60 +564,37 @@ fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
     }
     __syncthreads();
 
-    // ---- write-out: one warp per staged row, one lane per 16-byte chunk aligned in global
-    // memory.  Only bytes of pixels that belong to this group's tiles (ownership bitmap) and lie
-    // inside the image (set_pixel's bounds check, images.rs:104) are written.
-    const int vx0 = max(0, -gd.x0), vx1 = min(g.region_w, g.width - gd.x0);  // in-image columns of the region
-    for (int r = warp; r < g.region_h; r += kWarps) {
-        const int y = gd.y0 + r;
-        if ((unsigned)y >= (unsigned)g.height) continue;
-        const int srow = r * g.pitch + rv.phi0;
-        const int sbase = srow & ~15;
-        const int64_t gbase = rv.a0 + (int64_t)r * g.row_stride - (srow & 15);
-        const uint32_t *own = ownership + (size_t)r * g.own_words;
-        for (int c = lane; c < g.chunks_per_row; c += 32) {
-            const int s = sbase + 16 * c;
-            const int b0 = s - srow;  // region byte offset of the chunk's first byte (can be < 0)
-            if (b0 >= g.row_bytes) break;
-            const int lo = max(0, -b0), hi = min(16, g.row_bytes - b0);
-            const int px0 = (b0 + lo) / PB, px1 = (b0 + hi - 1) / PB;
-            const int q0 = max(px0, vx0), q1 = min(px1, vx1 - 1);
-            if (q0 > q1) continue;
-            const int n = q1 - q0 + 1;  // <= 16
-            const uint32_t w0 = __ldg(own + (q0 >> 5));
-            const uint32_t w1 = __ldg(own + min((q0 >> 5) + 1, g.own_words - 1));
-            const uint32_t bits = __funnelshift_r(w0, w1, q0 & 31) & ((1u << n) - 1u);
-            if (bits == 0) continue;
-            uint8_t *gp = reinterpret_cast<uint8_t *>(gbase + 16 * c);
-            const uint8_t *sp = region + s;
-            if (bits == ((1u << n) - 1u) && q0 == px0 && q1 == px1 && lo == 0 && hi == 16) {
-                *reinterpret_cast<int4 *>(gp) = *reinterpret_cast<const int4 *>(sp);
-                continue;
-            }
-            uint32_t bm = 0;  // byte mask of the chunk
-            if (PB == 1) {
-                bm = bits << (q0 - b0);
-            } else {
-#pragma unroll 1
-                for (int p = q0; p <= q1; ++p)
-                    if ((bits >> (p - q0)) & 1u) {
-                        const int bs = p * PB - b0;
-                        const uint32_t pm = (1u << PB) - 1u;
-                        bm |= bs >= 0 ? pm << bs : pm >> (-bs);
-                    }
-                bm &= 0xffffu;
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t nib = (bm >> (4 * k)) & 15u;
-                if (nib == 15u) {
-                    *reinterpret_cast<uint32_t *>(gp + 4 * k) = *reinterpret_cast<const uint32_t *>(sp + 4 * k);
-                } else if (nib) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if ((nib >> j) & 1u) gp[4 * k + j] = sp[4 * k + j];
-                }
-            }
+    // ---- write-out in 16-byte chunks aligned in global memory, one chunk per thread and
+    // iteration from the plan's chunk list.  Only bytes of pixels that belong to this group's
+    // tiles (chunk masks) and lie inside the image (set_pixel's bounds check, images.rs:104) are
+    // written: fully owned chunks as one 128-bit store, the chunks along the group's fractal
+    // outline byte-masked.
+    const uint32_t *cl = chunk_list + (size_t)rv.phi0 * g.list_cap;
+    const uint16_t *cmk = chunk_mask + (size_t)rv.phi0 * g.list_cap;
+    const int n_full = g.list_full[rv.phi0], n_all = g.list_all[rv.phi0];
+    if (rv.interior) {
+        for (int k = threadIdx.x; k < n_full; k += kThreads) {
+            const uint32_t e = __ldg(cl + k);
+            const int r = (int)(e >> 16), s = (int)(e & 0xffffu) << 4;
+            *reinterpret_cast<int4 *>(reinterpret_cast<uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s) =
+                *reinterpret_cast<const int4 *>(region + s);
+        }
+        for (int k = n_full + threadIdx.x; k < n_all; k += kThreads) {
+            const uint32_t e = __ldg(cl + k);
+            const int r = (int)(e >> 16), s = (int)(e & 0xffffu) << 4;
+            store_chunk_masked(reinterpret_cast<uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s, region + s, __ldg(cmk + k));
+        }
+    } else {
+        const int stride32 = (int)g.row_stride;
+        for (int k = threadIdx.x; k < n_all; k += kThreads) {
+            const uint32_t e = __ldg(cl + k);
+            const int r = (int)(e >> 16), s = (int)(e & 0xffffu) << 4;
+            if ((unsigned)(gd.y0 + r) >= (unsigned)g.height) continue;
+            uint32_t m = k < n_full ? 0xffffu : (uint32_t)__ldg(cmk + k);
+            const int xb = rv.xb0 + s - (r * g.pitch + rv.phi0);  // byte position of the chunk inside its image row
+            const int lo = min(max(-xb, 0), 16), hi = min(max(stride32 - xb, 0), 16);
+            m &= ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+            if (m) store_chunk_masked(reinterpret_cast<uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s, region + s, m);
         }
     }
 }
@@ -561,12 +623,12 @@ fri_coarse_forward_kernel(const __grid_constant__ QuantParams qp, int sub_bits, 
             lift(src[2 * j], src[2 * j + 1], d, s);
             dst[j] = s;
             const uint32_t pos = (uint32_t)(cnt + j);
-            out[pos] = quant1(d, qp.div(layer_of(pos)));
+            out[pos] = quant_layer(qp, d, layer_of(pos));
         }
         __syncthreads();
         int32_t *t = src; src = dst; dst = t;
     }
-    if (threadIdx.x == 0) out[0] = quant1(src[0], qp.div(0));  // wavelet_transform.rs:221, layer 0
+    if (threadIdx.x == 0) out[0] = quant_layer(qp, src[0], 0);  // wavelet_transform.rs:221, layer 0
 }
 
 __global__ void __launch_bounds__(kCoarseThreads)
@@ -578,13 +640,13 @@ fri_coarse_inverse_kernel(const __grid_constant__ QuantParams qp, int sub_bits, 
     int32_t *src = cs + n, *dst = cs;  // sizes: level L reads 2^L values, writes 2^(L+1)
     const int32_t *in = coefs + ((int64_t)blockIdx.x << depth);
     int32_t *out = dc + ((int64_t)blockIdx.x << sub_bits);
-    if (threadIdx.x == 0) src[0] = dequant1(in[0], qp.div(0), qp.q[0], qp.multiply);
+    if (threadIdx.x == 0) src[0] = dequant_layer(qp, in[0], 0);
     __syncthreads();
     for (int level = 0; level < sub_bits; ++level) {
         const int cnt = 1 << level;
         for (int j = threadIdx.x; j < cnt; j += kCoarseThreads) {
             const uint32_t pos = (uint32_t)(cnt + j);
-            const int d = dequant1(in[pos], qp.div(layer_of(pos)), qp.q[layer_of(pos)], qp.multiply);
+            const int d = dequant_layer(qp, in[pos], layer_of(pos));
             int l, r;
             unlift(src[j], d, l, r);
             dst[2 * j] = l;
@@ -638,13 +700,13 @@ cudaError_t launch_encode(const Geometry &g, const DeviceTables &t, const QuantP
         int32_t *c = d_coefs + (int64_t)f0 * g.coefs_per_frame;
         int32_t *dc = d_dc ? d_dc + (((int64_t)f0 * g.n_fractals * g.channels) << g.sub_bits) : nullptr;
         if (g.channels == 1 && g.sample_bytes == 1)
-            fri_encode_kernel<1, uint8_t><<<grid, kThreads, smem, stream>>>(g, qp, t.groups, t.tile_unit, p, c, dc);
+            fri_encode_kernel<1, uint8_t><<<grid, kThreads, smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, p, c, dc);
         else if (g.channels == 3 && g.sample_bytes == 1)
-            fri_encode_kernel<3, uint8_t><<<grid, kThreads, smem, stream>>>(g, qp, t.groups, t.tile_unit, p, c, dc);
+            fri_encode_kernel<3, uint8_t><<<grid, kThreads, smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, p, c, dc);
         else if (g.channels == 1 && g.sample_bytes == 2)
-            fri_encode_kernel<1, uint16_t><<<grid, kThreads, smem, stream>>>(g, qp, t.groups, t.tile_unit, p, c, dc);
+            fri_encode_kernel<1, uint16_t><<<grid, kThreads, smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, p, c, dc);
         else
-            fri_encode_kernel<3, uint16_t><<<grid, kThreads, smem, stream>>>(g, qp, t.groups, t.tile_unit, p, c, dc);
+            fri_encode_kernel<3, uint16_t><<<grid, kThreads, smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, p, c, dc);
         if (launches) ++*launches;
     }
     if (g.sub_bits > 0) {
@@ -676,13 +738,13 @@ cudaError_t launch_decode(const Geometry &g, const DeviceTables &t, const QuantP
         const int32_t *c = d_coefs + (int64_t)f0 * g.coefs_per_frame;
         int32_t *dc = d_dc ? d_dc + (((int64_t)f0 * g.n_fractals * g.channels) << g.sub_bits) : nullptr;
         if (g.channels == 1 && g.sample_bytes == 1)
-            fri_decode_kernel<1, uint8_t><<<grid, kThreads, smem, stream>>>(g, qp, t.groups, t.tile_unit, t.ownership, c, dc, p);
+            fri_decode_kernel<1, uint8_t><<<grid, kThreads, smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, t.chunk_mask, c, dc, p);
         else if (g.channels == 3 && g.sample_bytes == 1)
-            fri_decode_kernel<3, uint8_t><<<grid, kThreads, smem, stream>>>(g, qp, t.groups, t.tile_unit, t.ownership, c, dc, p);
+            fri_decode_kernel<3, uint8_t><<<grid, kThreads, smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, t.chunk_mask, c, dc, p);
         else if (g.channels == 1 && g.sample_bytes == 2)
-            fri_decode_kernel<1, uint16_t><<<grid, kThreads, smem, stream>>>(g, qp, t.groups, t.tile_unit, t.ownership, c, dc, p);
+            fri_decode_kernel<1, uint16_t><<<grid, kThreads, smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, t.chunk_mask, c, dc, p);
         else
-            fri_decode_kernel<3, uint16_t><<<grid, kThreads, smem, stream>>>(g, qp, t.groups, t.tile_unit, t.ownership, c, dc, p);
+            fri_decode_kernel<3, uint16_t><<<grid, kThreads, smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, t.chunk_mask, c, dc, p);
         if (launches) ++*launches;
     }
     return cudaGetLastError();

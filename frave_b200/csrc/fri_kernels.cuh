@@ -7,13 +7,14 @@
 namespace fri {
 
 // Truncating division by a run-time constant (Rust `i32 / i32` with a positive divisor,
-// quantization.rs:19 and :37) as a multiply-high + shifts, exact for every i32 numerator.
-// Granlund & Montgomery / libdivide style: magic == 0 -> divisor is a power of two.
+// quantization.rs:19 and :37) as a signed multiply-high, an optional add, a shift and a sign
+// fix-up (Granlund & Montgomery; Hacker's Delight ch. 10).  Exact for every i32 numerator and
+// every divisor >= 2; divisor 1 is never routed here (layers with q == 1 are skipped).
 struct Div {
-    uint32_t magic;
-    uint32_t more;  // bits 0..4: shift; bit 6: the "add" fix-up step is needed
+    int32_t magic;    // signed magic multiplier
+    int32_t addmask;  // -1 if the numerator is added after the multiply-high (magic < 0), else 0
+    int32_t shift;
 };
-constexpr uint32_t kDivAdd = 0x40u;
 
 #if defined(__CUDACC__)
 #define FRI_HDI __host__ __device__ __forceinline__
@@ -21,40 +22,34 @@ constexpr uint32_t kDivAdd = 0x40u;
 #define FRI_HDI inline
 #endif
 
-FRI_HDI uint32_t mulhi_u32(uint32_t a, uint32_t b)
+FRI_HDI int32_t mulhi_s32(int32_t a, int32_t b)
 {
 #if defined(__CUDA_ARCH__)
-    return __umulhi(a, b);
+    return __mulhi(a, b);
 #else
-    return (uint32_t)(((uint64_t)a * b) >> 32);
+    return (int32_t)(((int64_t)a * b) >> 32);
 #endif
 }
 
-FRI_HDI int32_t trunc_div(int32_t d, Div dv)
+FRI_HDI int32_t trunc_div(int32_t n, Div dv)
 {
-    const uint32_t n = d < 0 ? 0u - (uint32_t)d : (uint32_t)d;
-    uint32_t r;
-    if (dv.magic == 0) {
-        r = n >> (dv.more & 31u);
-    } else {
-        uint32_t t = mulhi_u32(n, dv.magic);
-        if (dv.more & kDivAdd) t = ((n - t) >> 1) + t;
-        r = t >> (dv.more & 31u);
-    }
-    return d < 0 ? (int32_t)(0u - r) : (int32_t)r;
+    int32_t t = (int32_t)((uint32_t)mulhi_s32(n, dv.magic) + (uint32_t)(n & dv.addmask));
+    t >>= dv.shift;
+    return t + (int32_t)((uint32_t)n >> 31);
 }
 
 // Quantization matrix prepared on the host (quantization.rs:3-25).
 struct QuantParams {
-    uint32_t magic[32];
-    uint8_t more[32];
+    int32_t magic[32];
+    int32_t addmask[32];
+    int32_t shift[32];
     int32_t q[32];
     uint32_t active;   // bit l set <=> q[l] != 1
     int32_t multiply;  // decode only: 1 = multiply (true dequantizer), 0 = divide (reference)
-    FRI_HDI Div div(int l) const { return Div{magic[l], more[l]}; }
+    FRI_HDI Div div(int l) const { return Div{magic[l], addmask[l], shift[l]}; }
 };
 
-Div make_div(int32_t q);
+Div make_div(int32_t q);  // q >= 2
 void make_quant_params(QuantParams &qp, const int32_t *q, int multiply);
 
 constexpr int kThreads = 256;       // 8 warps per CTA
@@ -66,8 +61,9 @@ size_t kernel_smem_bytes(const Geometry &g);
 // Device-side tables of a plan.
 struct DeviceTables {
     const GroupDesc *groups = nullptr;
-    const uint32_t *tile_unit = nullptr;  // nullptr at depth 9
-    const uint32_t *ownership = nullptr;
+    const uint32_t *tile_unit = nullptr;   // nullptr at depth 9
+    const uint32_t *chunk_list = nullptr;  // [16][list_cap]
+    const uint16_t *chunk_mask = nullptr;  // [16][list_cap]
 };
 
 // One-time per-process kernel attribute setup (max dynamic shared memory).

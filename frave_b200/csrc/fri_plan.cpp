@@ -273,6 +273,45 @@ std::string build_plan(Plan &plan, uint32_t width, uint32_t height, uint32_t cha
             plan.ownership[(size_t)y * g.own_words + (x >> 5)] |= 1u << (x & 31);
         }
 
+    for (int s = 0; s < group_a * group_b; ++s) g.tile_off[s] = g.tile_rel_y[s] * g.pitch + g.tile_rel_x[s] * csz;
+
+    // Chunk lists.  Shared-memory byte r*pitch + phase + b holds region byte (r, b); chunks are
+    // the 16-byte aligned pieces of shared memory (== aligned pieces of global memory).
+    std::vector<std::vector<std::pair<uint32_t, uint16_t>>> lists(16);
+    g.list_cap = 0;
+    for (int phase = 0; phase < 16; ++phase) {
+        std::vector<std::pair<uint32_t, uint16_t>> full, part;
+        for (int r = 0; r < g.region_h; ++r) {
+            const int srow = r * g.pitch + phase, sbase = srow & ~15;
+            for (int c = 0; c < g.chunks_per_row; ++c) {
+                const int b0 = sbase + 16 * c - srow;
+                uint32_t m = 0;
+                for (int j = 0; j < 16; ++j) {
+                    const int b = b0 + j;
+                    if (b < 0 || b >= g.row_bytes) continue;
+                    const int x = b / csz;
+                    if ((plan.ownership[(size_t)r * g.own_words + (x >> 5)] >> (x & 31)) & 1u) m |= 1u << j;
+                }
+                if (m == 0) continue;
+                const uint32_t entry = (uint32_t)r << 16 | (uint32_t)((sbase + 16 * c) >> 4);
+                (m == 0xffffu ? full : part).emplace_back(entry, (uint16_t)m);
+            }
+        }
+        g.list_full[phase] = (int32_t)full.size();
+        g.list_all[phase] = (int32_t)(full.size() + part.size());
+        g.list_cap = std::max(g.list_cap, g.list_all[phase]);
+        lists[phase] = std::move(full);
+        lists[phase].insert(lists[phase].end(), part.begin(), part.end());
+    }
+    if ((size_t)g.region_h * g.pitch > ((size_t)1 << 20) || g.region_h > 0xffff) return "group region too large";
+    plan.chunk_list.assign((size_t)16 * g.list_cap, 0u);
+    plan.chunk_mask.assign((size_t)16 * g.list_cap, 0);
+    for (int phase = 0; phase < 16; ++phase)
+        for (size_t k = 0; k < lists[phase].size(); ++k) {
+            plan.chunk_list[(size_t)phase * g.list_cap + k] = lists[phase][k].first;
+            plan.chunk_mask[(size_t)phase * g.list_cap + k] = lists[phase][k].second;
+        }
+
     plan.centers.clear(); plan.full.clear(); plan.groups.clear(); plan.tile_unit.clear();
     plan.centers.reserve(kept.size() * 2);
     plan.full.reserve(kept.size());

@@ -38,12 +38,15 @@ struct Geometry {
     int32_t n_groups;
     int32_t n_base_tiles;        // base tiles processed per frame (n_fractals << sub_bits)
     int32_t n_fractals;          // retained fractals per frame (== n_base_tiles at depth 9)
-    int32_t pad_;
+    int32_t list_cap;            // entries per phase in the chunk list
     int64_t row_stride;          // width * channels * sample_bytes
     int64_t frame_bytes;         // height * row_stride
     int64_t coefs_per_frame;     // n_fractals * channels * 2^depth
     int16_t tile_rel_x[kMaxGroupTiles];  // base tile centre relative to the region origin
     int16_t tile_rel_y[kMaxGroupTiles];
+    int32_t tile_off[kMaxGroupTiles];    // tile_rel_y * pitch + tile_rel_x * pixel_bytes
+    int32_t list_full[16];               // per phase: fully owned 16-byte chunks (listed first)
+    int32_t list_all[16];                // per phase: all chunks that hold at least one owned byte
 };
 
 struct Plan {
@@ -56,6 +59,12 @@ struct Plan {
     std::vector<GroupDesc> groups;    // [n_groups]
     std::vector<uint32_t> tile_unit;  // [n_base_tiles] fractal_index << sub_bits | sub_tile (empty at depth 9)
     std::vector<uint32_t> ownership;  // [region_h][own_words]: bit x set <=> region pixel belongs to the group
+    // Byte-ownership of the staged region cut into the 16-byte chunks the kernels move, for each
+    // of the 16 possible phases (global address of the region's first byte mod 16):
+    // chunk_list[phase][k] = row << 16 | (shared-memory offset >> 4) of the k-th chunk holding owned
+    // bytes, fully owned chunks first; chunk_mask[phase][k]: bit j <=> byte j of that chunk is owned.
+    std::vector<uint32_t> chunk_list;  // [16][list_cap]
+    std::vector<uint16_t> chunk_mask;  // [16][list_cap]
 };
 
 // Returns an empty string on success, else an error message.  group_a/group_b == 0 picks the
