@@ -37,7 +37,7 @@ FRAMES = 1                  # frames per GPU per step (one batched launch per di
 PREHEAT_S = 1.0
 SMALLEST_LAYER_DIVISOR = 4  # q[8] = q[9] = 4: "dividing the smallest layer of fractals" (README.md:12)
 BYTES_PER_SAMPLE = 5        # u8 pixel + i32 coefficient, either direction
-N_SETS = 4                  # rotating buffer sets: 4 x (50 + 201 + 50 MB) = 1.2 GB >> 126 MB of L2
+N_SETS = int(os.environ.get("FRI_BENCH_SETS", "4"))  # rotating buffer sets: 4 x (50 + 201 + 50 MB) = 1.2 GB >> 126 MB of L2
 
 
 def quant_matrix() -> np.ndarray:

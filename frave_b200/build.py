@@ -40,20 +40,28 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, out: str | None = None, extra: list[str] | None = None) -> str:
+    """Builds the library.  `out`/`extra` build a tuning variant (extra nvcc flags, e.g. -DFRI_...)
+    next to the product library; capi loads it when FRI_CUDA_LIB points at it."""
+    target = out or LIB_PATH
+    if not force and out is None and not is_stale():
         return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS]
+    cmd = [_nvcc(), *NVCC_FLAGS, *(extra or [])]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", LIB_PATH, *[os.path.join(_CSRC, s) for s in SOURCES]]
+    cmd += ["-o", target, *[os.path.join(_CSRC, s) for s in SOURCES]]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     if verbose:
         sys.stderr.write(res.stdout + res.stderr)
-    return LIB_PATH
+    return target
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    args = [a for a in sys.argv[1:] if a not in ("--force", "--verbose")]
+    out = None
+    if args and args[0] == "--variant":  # python -m frave_b200.build --variant <tag> -DFOO=1 ...
+        out = os.path.join(_HERE, f"libfri_cuda_{args[1]}.so")
+        args = args[2:]
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, out=out, extra=args))

@@ -57,16 +57,17 @@ class FriError(RuntimeError):
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    """The product library, or a tuning variant when FRI_CUDA_LIB names one (see build.py)."""
+    return os.environ.get("FRI_CUDA_LIB") or _build.LIB_PATH
 
 
 def lib() -> C.CDLL:
     """Loads (building first if necessary) libfri_cuda.so.  Never falls back to a CPU path."""
     global _lib
     if _lib is None:
-        if not os.path.exists(_build.LIB_PATH):
+        if not os.environ.get("FRI_CUDA_LIB") and not os.path.exists(_build.LIB_PATH):
             _build.build()
-        L = C.CDLL(_build.LIB_PATH)
+        L = C.CDLL(lib_path())
         for name, res, args in _SYMBOLS:
             fn = getattr(L, name)  # AttributeError if the library does not export it
             fn.restype = res

@@ -246,7 +246,7 @@ int fri_plan_launch_info(const fri_plan *p, int32_t info[16])
     if (!p || !info) return fail(FRI_E_INVALID, "NULL argument");
     const Geometry &g = p->plan.geo;
     const int32_t v[16] = {g.group_a, g.group_b, g.region_w, g.region_h, g.pitch, (int32_t)kernel_smem_bytes(g),
-                           g.n_groups, g.n_base_tiles, kThreads, g.chunks_per_row, g.depth, g.sub_bits, 0, 0, 0, 0};
+                           g.n_groups, g.n_base_tiles, cta_threads(g), g.chunks_per_row, g.depth, g.sub_bits, 0, 0, 0, 0};
     std::memcpy(info, v, sizeof(v));
     return FRI_OK;
 }

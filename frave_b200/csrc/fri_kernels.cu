@@ -74,9 +74,15 @@ void make_quant_params(QuantParams &qp, const int32_t *q, int multiply)
     }
 }
 
+int cta_threads(const Geometry &g)
+{
+    const int warps = (g.group_a * g.group_b + g.tiles_per_warp - 1) / g.tiles_per_warp;
+    return 32 * (warps < 1 ? 1 : (warps > kMaxWarps ? kMaxWarps : warps));
+}
+
 size_t kernel_smem_bytes(const Geometry &g)
 {
-    return (((size_t)g.region_h * g.pitch + 15) & ~(size_t)15) + (size_t)kWarps * kScratchInts * sizeof(int32_t);
+    return (((size_t)g.region_h * g.pitch + 15) & ~(size_t)15) + (size_t)(cta_threads(g) / 32) * g.channels * kScratchInts * sizeof(int32_t);
 }
 
 namespace {
@@ -234,8 +240,24 @@ __device__ __forceinline__ void store_chunk_masked(uint8_t *gp, const uint8_t *s
 // ------------------------------------------------------------------------------------------
 // encode: pixels -> quantized coefficients
 // ------------------------------------------------------------------------------------------
+//
+// Per warp iteration: one base tile, all C channels.
+//   phase 1 (per channel): gather 16 leaves per lane, levels 8..6 in registers, quantize, store;
+//                          the 64 level-6 low-pass values go to the warp's scratch.
+//   phase 2 (all channels at once): lane group g = lane / 8 owns channel g; lane j of the group
+//                          folds s6[8j .. 8j+7] through levels 5..3 in registers and levels 2..0
+//                          with three shuffles inside the group.
+#ifndef FRI_DEC_EAGER
+#define FRI_DEC_EAGER 0
+#endif
+#ifndef FRI_ENC_MINB
+#define FRI_ENC_MINB 4
+#endif
+#ifndef FRI_DEC_MINB
+#define FRI_DEC_MINB 4
+#endif
 template <int C, typename S>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, FRI_ENC_MINB)
 fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ QuantParams qp,
                   const GroupDesc *__restrict__ groups, const uint32_t *__restrict__ tile_unit,
                   const uint32_t *__restrict__ chunk_list, const uint8_t *__restrict__ pixels,
@@ -246,12 +268,14 @@ fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *region = smem;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int32_t *scratch = reinterpret_cast<int32_t *>(smem + (((size_t)g.region_h * g.pitch + 15) & ~(size_t)15)) + warp * kScratchInts;
+    int32_t *scratch = reinterpret_cast<int32_t *>(smem + (((size_t)g.region_h * g.pitch + 15) & ~(size_t)15)) + warp * (C * kScratchInts);
+    const int n_warps = blockDim.x >> 5, n_threads = blockDim.x;
 
     const GroupDesc gd = groups[blockIdx.x];
     const int frame = blockIdx.y;
     const uint8_t *fbase = pixels + (int64_t)frame * g.frame_bytes;
     const RegionView rv = region_view<PB>(g, gd, fbase);
+
     // ---- stage the group's pixel footprint: one 16-byte chunk (aligned in global and in shared
     // memory) per thread and iteration, taken from the plan's list of chunks that hold at least
     // one pixel of this group's tiles.
@@ -259,14 +283,14 @@ fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
         const uint32_t *cl = chunk_list + (size_t)rv.phi0 * g.list_cap;
         const int n_all = g.list_all[rv.phi0];
         if (rv.interior) {
-            for (int k = threadIdx.x; k < n_all; k += kThreads) {
+            for (int k = threadIdx.x; k < n_all; k += n_threads) {
                 const uint32_t e = __ldg(cl + k);
                 const int r = (int)(e >> 16), s = (int)(e & 0xffffu) << 4;
                 cp_async_16(region + s, reinterpret_cast<const uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s);
             }
         } else {
             const int stride32 = (int)g.row_stride;
-            for (int k = threadIdx.x; k < n_all; k += kThreads) {
+            for (int k = threadIdx.x; k < n_all; k += n_threads) {
                 const uint32_t e = __ldg(cl + k);
                 const int r = (int)(e >> 16), s = (int)(e & 0xffffu) << 4;
                 const int y = gd.y0 + r;
@@ -288,77 +312,78 @@ fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
     cp_async_wait_all();
     __syncthreads();
 
-    // ---- one (base tile, channel) task per warp iteration
-    const int n_tasks = __popc(gd.tile_mask) * C;
+    const int n_present = __popc(gd.tile_mask);
     const uint8_t *lane_base = region + rv.phi0 + lane_anchor_bytes(lane, g.pitch, PB);
     const int half = kHalfB.y * g.pitch + kHalfB.x * PB;
     const int top = g.sub_bits;  // fractal level of a base tile's root
     const bool sparse_group = (gd.tile_mask & (gd.tile_mask + 1u)) != 0;
-    for (int task = warp; task < n_tasks; task += kWarps) {
-        const int e = task / C, ch = task - e * C;
+    const int grp = min(lane >> 3, C - 1), j8 = lane & 7;  // phase 2 roles
+    const bool grp_live = (lane >> 3) < C;
+    for (int e = warp; e < n_present; e += n_warps) {
         const int slot = sparse_group ? (int)__fns(gd.tile_mask, 0, e + 1) : e;
-        const uint8_t *p0 = lane_base + g.tile_off[slot] + ch * SB;
-        const uint8_t *p1 = p0 + g.pitch, *p2 = p1 + g.pitch;
+        const uint8_t *t0 = lane_base + g.tile_off[slot];
+        const TaskAddr ta = task_addr<C>(g, tile_unit, frame, gd.tile_base + e, 0);
+        const bool lastB = ta.last && lane == 31;  // this lane holds the last node of levels 8..6
 
-        // gather: leaf i of a depth-3 subtree sits at sub_leaf(i) from the subtree's first leaf
-        int v[8], w[8];
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) {
+            const uint8_t *p0 = t0 + ch * SB, *p1 = p0 + g.pitch, *p2 = p1 + g.pitch;
+            // gather: leaf i of a depth-3 subtree sits at sub_leaf(i) from the subtree's first leaf
+            int v[8], w[8];
 #define FRI_LD(ptr, dx) ((int)*reinterpret_cast<const S *>((ptr) + (dx) * PB))
-        v[0] = FRI_LD(p0, 0);  v[1] = FRI_LD(p1, 0);   // (0,0) (0,1)
-        v[2] = FRI_LD(p1, -1); v[3] = FRI_LD(p2, -1);  // (-1,1) (-1,2)
-        v[4] = FRI_LD(p0, 2);  v[5] = FRI_LD(p1, 2);   // (2,0) (2,1)
-        v[6] = FRI_LD(p1, 1);  v[7] = FRI_LD(p2, 1);   // (1,1) (1,2)
-        w[0] = FRI_LD(p0 + half, 0);  w[1] = FRI_LD(p1 + half, 0);
-        w[2] = FRI_LD(p1 + half, -1); w[3] = FRI_LD(p2 + half, -1);
-        w[4] = FRI_LD(p0 + half, 2);  w[5] = FRI_LD(p1 + half, 2);
-        w[6] = FRI_LD(p1 + half, 1);  w[7] = FRI_LD(p2 + half, 1);
+            v[0] = FRI_LD(p0, 0);  v[1] = FRI_LD(p1, 0);   // (0,0) (0,1)
+            v[2] = FRI_LD(p1, -1); v[3] = FRI_LD(p2, -1);  // (-1,1) (-1,2)
+            v[4] = FRI_LD(p0, 2);  v[5] = FRI_LD(p1, 2);   // (2,0) (2,1)
+            v[6] = FRI_LD(p1, 1);  v[7] = FRI_LD(p2, 1);   // (1,1) (1,2)
+            w[0] = FRI_LD(p0 + half, 0);  w[1] = FRI_LD(p1 + half, 0);
+            w[2] = FRI_LD(p1 + half, -1); w[3] = FRI_LD(p2 + half, -1);
+            w[4] = FRI_LD(p0 + half, 2);  w[5] = FRI_LD(p1 + half, 2);
+            w[6] = FRI_LD(p1 + half, 1);  w[7] = FRI_LD(p2 + half, 1);
 #undef FRI_LD
+            // levels 8, 7, 6 in registers
+            int a8[4], b8[4], sa8[4], sb8[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                lift(v[2 * m], v[2 * m + 1], a8[m], sa8[m]);
+                lift(w[2 * m], w[2 * m + 1], b8[m], sb8[m]);
+            }
+            int a7[2], b7[2], sa7[2], sb7[2];
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                lift(sa8[2 * m], sa8[2 * m + 1], a7[m], sa7[m]);
+                lift(sb8[2 * m], sb8[2 * m + 1], b7[m], sb7[m]);
+            }
+            int a6, b6, sA, sB;
+            lift(sa7[0], sa7[1], a6, sA);
+            lift(sb7[0], sb7[1], b6, sB);
+            scratch[ch * kScratchInts + lane] = sA;       // low-pass of node 64 + lane
+            scratch[ch * kScratchInts + 32 + lane] = sB;  // low-pass of node 96 + lane
 
-        const TaskAddr ta = task_addr<C>(g, tile_unit, frame, gd.tile_base + e, ch);
-        int32_t *out = coefs + ta.block;
-        const bool lastB = ta.last && lane == 31;  // this lane holds the last node of every level
-
-        // levels 8, 7, 6 in registers
-        int a8[4], b8[4], sa8[4], sb8[4];
+            // quantization.rs:13 — layer = level, except the last node of a level: level + 1
+            if ((qp.active >> (top + 6)) & 0xfu) {
+                const int r8 = b8[3], r7 = b7[1], r6 = b6;  // unquantized values of the level-last nodes
+                if ((qp.active >> (top + 8)) & 1u) {
+                    const Div dv = qp.div(top + 8);
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            lift(v[2 * m], v[2 * m + 1], a8[m], sa8[m]);
-            lift(w[2 * m], w[2 * m + 1], b8[m], sb8[m]);
-        }
-        int a7[2], b7[2], sa7[2], sb7[2];
+                    for (int m = 0; m < 4; ++m) { a8[m] = trunc_div(a8[m], dv); b8[m] = trunc_div(b8[m], dv); }
+                }
+                if ((qp.active >> (top + 7)) & 1u) {
+                    const Div dv = qp.div(top + 7);
 #pragma unroll
-        for (int m = 0; m < 2; ++m) {
-            lift(sa8[2 * m], sa8[2 * m + 1], a7[m], sa7[m]);
-            lift(sb8[2 * m], sb8[2 * m + 1], b7[m], sb7[m]);
-        }
-        int a6, b6, sA, sB;
-        lift(sa7[0], sa7[1], a6, sA);
-        lift(sb7[0], sb7[1], b6, sB);
-
-        // quantization.rs:13 — layer = level, except the last node of a level: level + 1
-        if ((qp.active >> (top + 6)) & 0xfu) {
-            const int r8 = b8[3], r7 = b7[1], r6 = b6;  // unquantized values of the level-last nodes
-            if ((qp.active >> (top + 8)) & 1u) {
-                const Div dv = qp.div(top + 8);
-#pragma unroll
-                for (int m = 0; m < 4; ++m) { a8[m] = trunc_div(a8[m], dv); b8[m] = trunc_div(b8[m], dv); }
+                    for (int m = 0; m < 2; ++m) { a7[m] = trunc_div(a7[m], dv); b7[m] = trunc_div(b7[m], dv); }
+                }
+                if ((qp.active >> (top + 6)) & 1u) {
+                    const Div dv = qp.div(top + 6);
+                    a6 = trunc_div(a6, dv);
+                    b6 = trunc_div(b6, dv);
+                }
+                if (lastB) {
+                    b8[3] = quant_layer(qp, r8, top + 9);
+                    b7[1] = quant_layer(qp, r7, top + 8);
+                    b6 = quant_layer(qp, r6, top + 7);
+                }
             }
-            if ((qp.active >> (top + 7)) & 1u) {
-                const Div dv = qp.div(top + 7);
-#pragma unroll
-                for (int m = 0; m < 2; ++m) { a7[m] = trunc_div(a7[m], dv); b7[m] = trunc_div(b7[m], dv); }
-            }
-            if ((qp.active >> (top + 6)) & 1u) {
-                const Div dv = qp.div(top + 6);
-                a6 = trunc_div(a6, dv);
-                b6 = trunc_div(b6, dv);
-            }
-            if (lastB) {
-                b8[3] = quant_layer(qp, r8, top + 9);
-                b7[1] = quant_layer(qp, r7, top + 8);
-                b6 = quant_layer(qp, r6, top + 7);
-            }
-        }
-        {
+            int32_t *out = coefs + ta.block + ((int64_t)ch << g.depth);
             int32_t *o8 = out + ((size_t)ta.node << 8), *o7 = out + ((size_t)ta.node << 7), *o6 = out + ((size_t)ta.node << 6);
             __stcs(reinterpret_cast<int4 *>(o8) + lane, make_int4(a8[0], a8[1], a8[2], a8[3]));
             __stcs(reinterpret_cast<int4 *>(o8 + 128) + lane, make_int4(b8[0], b8[1], b8[2], b8[3]));
@@ -367,59 +392,68 @@ fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
             __stcs(o6 + lane, a6);
             __stcs(o6 + 32 + lane, b6);
         }
+        __syncwarp();
 
-        // levels 5..1: lane pairs, one shuffle per chain per level
-#pragma unroll
-        for (int step = 0; step < 5; ++step) {
-            const int m = 5 - step, bit = 1 << step;
-            const int oA = __shfl_xor_sync(0xffffffffu, sA, bit), oB = __shfl_xor_sync(0xffffffffu, sB, bit);
-            int dA, dB;
-            lift(sA, oA, dA, sA);
-            lift(sB, oB, dB, sB);
-            if ((lane & (2 * bit - 1)) == 0) {
-                const int j = lane >> (step + 1);
-                scratch[(1 << m) + j] = dA;
-                scratch[(1 << m) + (1 << (m - 1)) + j] = dB;
-            }
-        }
-        if (lane == 0) {  // level 0 and the low-pass root (wavelet_transform.rs:221)
-            int d0, s0;
-            lift(sA, sB, d0, s0);
-            scratch[1] = d0;
-            scratch[0] = s0;
-        }
-        __syncwarp();
-        int2 t2 = *reinterpret_cast<const int2 *>(scratch + 2 * lane);
-        __syncwarp();
-        if (g.sub_bits == 0) {
-            if (qp.active & 0x7fu) {  // positions 0..63 live in layers 0..6
-                t2.x = quant_layer(qp, t2.x, layer_of(2 * lane));
-                t2.y = quant_layer(qp, t2.y, layer_of(2 * lane + 1));
-            }
-            __stcs(reinterpret_cast<int2 *>(out) + lane, t2);
-        } else {
-            // local heap position p of the base tile -> fractal heap position (node << m) + p - 2^m
-            const int vals[2] = {t2.x, t2.y};
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const uint32_t p = 2 * lane + k;
-                if (p == 0) {
-                    dc_out[ta.dc] = vals[k];
+        // ---- phase 2: levels 5..0 of all channels, 8 lanes per channel
+        {
+            const int32_t *sp = scratch + grp * kScratchInts + 8 * j8;
+            const int4 x0 = *reinterpret_cast<const int4 *>(sp), x1 = *reinterpret_cast<const int4 *>(sp + 4);
+            int d5[4], s5[4], d4[2], s4[2], d3, d2, d1, d0, s3, s2, s1, s0;
+            lift(x0.x, x0.y, d5[0], s5[0]);
+            lift(x0.z, x0.w, d5[1], s5[1]);
+            lift(x1.x, x1.y, d5[2], s5[2]);
+            lift(x1.z, x1.w, d5[3], s5[3]);
+            lift(s5[0], s5[1], d4[0], s4[0]);
+            lift(s5[2], s5[3], d4[1], s4[1]);
+            lift(s4[0], s4[1], d3, s3);
+            lift(s3, __shfl_xor_sync(0xffffffffu, s3, 1), d2, s2);  // meaningful in lanes j8 % 2 == 0
+            lift(s2, __shfl_xor_sync(0xffffffffu, s2, 2), d1, s1);  // j8 % 4 == 0
+            lift(s1, __shfl_xor_sync(0xffffffffu, s1, 4), d0, s0);  // j8 == 0
+            if ((qp.active >> top) & 0x7fu) {
+                // level-L nodes sit in layer top + L, the level's last node in layer top + L + 1
+                const bool lastG = ta.last && j8 == 7;
+                d5[0] = quant_layer(qp, d5[0], top + 5); d5[1] = quant_layer(qp, d5[1], top + 5);
+                d5[2] = quant_layer(qp, d5[2], top + 5); d5[3] = quant_layer(qp, d5[3], top + (lastG ? 6 : 5));
+                d4[0] = quant_layer(qp, d4[0], top + 4); d4[1] = quant_layer(qp, d4[1], top + (lastG ? 5 : 4));
+                d3 = quant_layer(qp, d3, top + (lastG ? 4 : 3));
+                d2 = quant_layer(qp, d2, top + ((ta.last && j8 == 6) ? 3 : 2));
+                d1 = quant_layer(qp, d1, top + ((ta.last && j8 == 4) ? 2 : 1));
+                if (g.sub_bits == 0) {
+                    d0 = quant_layer(qp, d0, 1);  // position 1 is the last node of level 0
+                    s0 = quant_layer(qp, s0, 0);  // position 0: the low-pass root (wavelet_transform.rs:221)
                 } else {
-                    const int m = 31 - __clz((int)p);
-                    const uint32_t pos = (ta.node << m) + p - (1u << m);
-                    out[pos] = quant_layer(qp, vals[k], layer_of(pos));
+                    d0 = quant_layer(qp, d0, top + (ta.last ? 1 : 0));
+                }
+            }
+            if (grp_live) {
+                int32_t *out = coefs + ta.block + ((int64_t)grp << g.depth);
+                const size_t node = ta.node;
+                __stcs(reinterpret_cast<int4 *>(out + (node << 5)) + j8, make_int4(d5[0], d5[1], d5[2], d5[3]));
+                __stcs(reinterpret_cast<int2 *>(out + (node << 4)) + j8, make_int2(d4[0], d4[1]));
+                __stcs(out + (node << 3) + j8, d3);
+                if ((j8 & 1) == 0) __stcs(out + (node << 2) + (j8 >> 1), d2);
+                if ((j8 & 3) == 0) __stcs(out + (node << 1) + (j8 >> 2), d1);
+                if (j8 == 0) {
+                    __stcs(out + node, d0);
+                    if (g.sub_bits == 0) __stcs(out, s0);
+                    else dc_out[ta.dc + ((int64_t)grp << g.sub_bits)] = s0;
                 }
             }
         }
+        __syncwarp();
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // decode: quantized coefficients -> pixels
 // ------------------------------------------------------------------------------------------
+//
+// Mirror image of the encoder: per warp iteration one base tile, all C channels; lane group
+// g = lane / 8 first unfolds levels 0..5 of channel g (lane j ends with the eight level-6
+// low-pass values 8j .. 8j+7) into the warp's scratch, then every lane unfolds its two depth-3
+// subtrees per channel and scatters the 16 leaves into the staged region.
 template <int C, typename S>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, FRI_DEC_MINB)
 fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ QuantParams qp,
                   const GroupDesc *__restrict__ groups, const uint32_t *__restrict__ tile_unit,
                   const uint32_t *__restrict__ chunk_list, const uint16_t *__restrict__ chunk_mask,
@@ -430,137 +464,184 @@ fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *region = smem;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int32_t *scratch = reinterpret_cast<int32_t *>(smem + (((size_t)g.region_h * g.pitch + 15) & ~(size_t)15)) + warp * kScratchInts;
+    int32_t *scratch = reinterpret_cast<int32_t *>(smem + (((size_t)g.region_h * g.pitch + 15) & ~(size_t)15)) + warp * (C * kScratchInts);
+    const int n_warps = blockDim.x >> 5, n_threads = blockDim.x;
 
     const GroupDesc gd = groups[blockIdx.x];
     const int frame = blockIdx.y;
     uint8_t *fbase = pixels + (int64_t)frame * g.frame_bytes;
     const RegionView rv = region_view<PB>(g, gd, fbase);
 
-    const int n_tasks = __popc(gd.tile_mask) * C;
+    const int n_present = __popc(gd.tile_mask);
     uint8_t *lane_base = region + rv.phi0 + lane_anchor_bytes(lane, g.pitch, PB);
     const int half = kHalfB.y * g.pitch + kHalfB.x * PB;
     const int top = g.sub_bits;
     const bool sparse_group = (gd.tile_mask & (gd.tile_mask + 1u)) != 0;
+    const int grp = min(lane >> 3, C - 1), j8 = lane & 7;
+    const bool grp_live = (lane >> 3) < C;
+    // Pull the group's coefficients towards L2 now: at depth 9 the blocks of a group's tiles are
+    // adjacent (plan order is group-major), n_present * C * 2 KB in one run.
+    if (g.sub_bits == 0) {
+        const char *first = reinterpret_cast<const char *>(coefs + ((((int64_t)frame * g.n_fractals + gd.tile_base) * C) << kBaseDepth));
+        const int lines = n_present * C * 16;  // 128-byte lines
+        for (int i = threadIdx.x; i < lines; i += n_threads)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(first + (size_t)i * 128));
+    }
     // A lattice tile the reference's BFS never built (possible only next to the image border,
     // e.g. 480x270) still owns its pixels in the chunk masks: stage zeros for it, which is
     // what from_wavelet's zero-initialised raster holds there (wavelet_transform.rs:309-317).
-    if (__popc(gd.tile_mask) != g.group_a * g.group_b) {
+    if (n_present != g.group_a * g.group_b) {
         const int n16 = (g.region_h * g.pitch + 15) >> 4;
-        for (int i = threadIdx.x; i < n16; i += kThreads) reinterpret_cast<int4 *>(region)[i] = make_int4(0, 0, 0, 0);
+        for (int i = threadIdx.x; i < n16; i += n_threads) reinterpret_cast<int4 *>(region)[i] = make_int4(0, 0, 0, 0);
         __syncthreads();
     }
-    for (int task = warp; task < n_tasks; task += kWarps) {
-        const int e = task / C, ch = task - e * C;
+    for (int e = warp; e < n_present; e += n_warps) {
         const int slot = sparse_group ? (int)__fns(gd.tile_mask, 0, e + 1) : e;
-        const TaskAddr ta = task_addr<C>(g, tile_unit, frame, gd.tile_base + e, ch);
-        const int32_t *in = coefs + ta.block;
+        const TaskAddr ta = task_addr<C>(g, tile_unit, frame, gd.tile_base + e, 0);
         const bool lastB = ta.last && lane == 31;
+        const size_t node = ta.node;
 
-        // coefficient loads: all issued before the first use
-        const int32_t *i8 = in + ((size_t)ta.node << 8), *i7 = in + ((size_t)ta.node << 7), *i6 = in + ((size_t)ta.node << 6);
-        int4 a8 = __ldcs(reinterpret_cast<const int4 *>(i8) + lane);
-        int4 b8 = __ldcs(reinterpret_cast<const int4 *>(i8 + 128) + lane);
-        int2 a7 = __ldcs(reinterpret_cast<const int2 *>(i7) + lane);
-        int2 b7 = __ldcs(reinterpret_cast<const int2 *>(i7 + 64) + lane);
-        int a6 = __ldcs(i6 + lane);
-        int b6 = __ldcs(i6 + 32 + lane);
-        int2 t2;
-        if (g.sub_bits == 0) {
-            t2 = __ldcs(reinterpret_cast<const int2 *>(in) + lane);
-            if (qp.active & 0x7fu) {
-                t2.x = dequant_layer(qp, t2.x, layer_of(2 * lane));
-                t2.y = dequant_layer(qp, t2.y, layer_of(2 * lane + 1));
-            }
-        } else {
-            int vals[2];
+#if FRI_DEC_EAGER
+        // all of the tile's loads in flight before the first use
+        int4 A8[C], B8[C];
+        int2 A7[C], B7[C];
+        int A6[C], B6[C];
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const uint32_t p = 2 * lane + k;
-                if (p == 0) {
-                    vals[k] = dc_in[ta.dc];  // produced (already dequantized) by the coarse kernel
+        for (int ch = 0; ch < C; ++ch) {
+            const int32_t *in = coefs + ta.block + ((int64_t)ch << g.depth);
+            const int32_t *i8 = in + (node << 8), *i7 = in + (node << 7), *i6 = in + (node << 6);
+            A8[ch] = __ldcs(reinterpret_cast<const int4 *>(i8) + lane);
+            B8[ch] = __ldcs(reinterpret_cast<const int4 *>(i8 + 128) + lane);
+            A7[ch] = __ldcs(reinterpret_cast<const int2 *>(i7) + lane);
+            B7[ch] = __ldcs(reinterpret_cast<const int2 *>(i7 + 64) + lane);
+            A6[ch] = __ldcs(i6 + lane);
+            B6[ch] = __ldcs(i6 + 32 + lane);
+        }
+#endif
+        // ---- levels 0..5 of all channels, 8 lanes per channel
+        {
+            const int32_t *in = coefs + ta.block + ((int64_t)grp << g.depth);
+            int4 d5 = __ldcs(reinterpret_cast<const int4 *>(in + (node << 5)) + j8);
+            int2 d4 = __ldcs(reinterpret_cast<const int2 *>(in + (node << 4)) + j8);
+            int d3 = __ldcs(in + (node << 3) + j8);
+            int d2 = __ldcs(in + (node << 2) + (j8 >> 1));
+            int d1 = __ldcs(in + (node << 1) + (j8 >> 2));
+            int d0 = __ldcs(in + node);
+            int s0 = g.sub_bits == 0 ? __ldcs(in) : dc_in[ta.dc + ((int64_t)grp << g.sub_bits)];
+            if ((qp.active >> top) & 0x7fu) {
+                const bool lastG = ta.last && j8 == 7;
+                d5.x = dequant_layer(qp, d5.x, top + 5); d5.y = dequant_layer(qp, d5.y, top + 5);
+                d5.z = dequant_layer(qp, d5.z, top + 5); d5.w = dequant_layer(qp, d5.w, top + (lastG ? 6 : 5));
+                d4.x = dequant_layer(qp, d4.x, top + 4); d4.y = dequant_layer(qp, d4.y, top + (lastG ? 5 : 4));
+                d3 = dequant_layer(qp, d3, top + (lastG ? 4 : 3));
+                d2 = dequant_layer(qp, d2, top + ((ta.last && (j8 >> 1) == 3) ? 3 : 2));
+                d1 = dequant_layer(qp, d1, top + ((ta.last && (j8 >> 2) == 1) ? 2 : 1));
+                if (g.sub_bits == 0) {
+                    d0 = dequant_layer(qp, d0, 1);
+                    s0 = dequant_layer(qp, s0, 0);
                 } else {
-                    const int m = 31 - __clz((int)p);
-                    const uint32_t pos = (ta.node << m) + p - (1u << m);
-                    vals[k] = dequant_layer(qp, __ldcs(in + pos), layer_of(pos));
+                    d0 = dequant_layer(qp, d0, top + (ta.last ? 1 : 0));  // s0 was dequantized by the coarse kernel
                 }
             }
-            t2 = make_int2(vals[0], vals[1]);
-        }
-        __syncwarp();
-        *reinterpret_cast<int2 *>(scratch + 2 * lane) = t2;
-        __syncwarp();
-
-        if ((qp.active >> (top + 6)) & 0xfu) {
-            const int r8 = b8.w, r7 = b7.y, r6 = b6;  // raw values of the level-last nodes
-            const int mul = qp.multiply;
-            if ((qp.active >> (top + 8)) & 1u) {
-                const Div dv = qp.div(top + 8);
-                const int q = qp.q[top + 8];
-#define FRI_DQ(x) x = mul ? (int)((unsigned)(x) * (unsigned)q) : trunc_div(x, dv)
-                FRI_DQ(a8.x); FRI_DQ(a8.y); FRI_DQ(a8.z); FRI_DQ(a8.w);
-                FRI_DQ(b8.x); FRI_DQ(b8.y); FRI_DQ(b8.z); FRI_DQ(b8.w);
-            }
-            if ((qp.active >> (top + 7)) & 1u) {
-                const Div dv = qp.div(top + 7);
-                const int q = qp.q[top + 7];
-                FRI_DQ(a7.x); FRI_DQ(a7.y); FRI_DQ(b7.x); FRI_DQ(b7.y);
-            }
-            if ((qp.active >> (top + 6)) & 1u) {
-                const Div dv = qp.div(top + 6);
-                const int q = qp.q[top + 6];
-                FRI_DQ(a6); FRI_DQ(b6);
-#undef FRI_DQ
-            }
-            if (lastB) {
-                b8.w = dequant_layer(qp, r8, top + 9);
-                b7.y = dequant_layer(qp, r7, top + 8);
-                b6 = dequant_layer(qp, r6, top + 7);
+            int l, r, s;
+            unlift(s0, d0, l, r); s = (j8 & 4) ? r : l;
+            unlift(s, d1, l, r);  s = (j8 & 2) ? r : l;
+            unlift(s, d2, l, r);  s = (j8 & 1) ? r : l;
+            int s4[2], s5[4];
+            int4 x0, x1;
+            unlift(s, d3, s4[0], s4[1]);
+            unlift(s4[0], d4.x, s5[0], s5[1]);
+            unlift(s4[1], d4.y, s5[2], s5[3]);
+            unlift(s5[0], d5.x, x0.x, x0.y);
+            unlift(s5[1], d5.y, x0.z, x0.w);
+            unlift(s5[2], d5.z, x1.x, x1.y);
+            unlift(s5[3], d5.w, x1.z, x1.w);
+            if (grp_live) {
+                int32_t *sp = scratch + grp * kScratchInts + 8 * j8;
+                *reinterpret_cast<int4 *>(sp) = x0;
+                *reinterpret_cast<int4 *>(sp + 4) = x1;
             }
         }
+        __syncwarp();
 
-        // levels 0..5: every lane walks its own root-to-subtree path (broadcast reads)
-        int sA, sB;
-        unlift(scratch[0], scratch[1], sA, sB);  // children 2 (half A) and 3 (half B)
+        uint8_t *t0 = lane_base + g.tile_off[slot];
 #pragma unroll
-        for (int m = 1; m <= 5; ++m) {
-            const int j = lane >> (6 - m);
-            int l, r;
-            unlift(sA, scratch[(1 << m) + j], l, r);
-            sA = ((lane >> (5 - m)) & 1) ? r : l;
-            unlift(sB, scratch[(1 << m) + (1 << (m - 1)) + j], l, r);
-            sB = ((lane >> (5 - m)) & 1) ? r : l;
-        }
-        // levels 6, 7, 8 in registers
-        int sa7[2], sb7[2], sa8[4], sb8[4], v[8], w[8];
-        unlift(sA, a6, sa7[0], sa7[1]);
-        unlift(sB, b6, sb7[0], sb7[1]);
-        unlift(sa7[0], a7.x, sa8[0], sa8[1]);
-        unlift(sa7[1], a7.y, sa8[2], sa8[3]);
-        unlift(sb7[0], b7.x, sb8[0], sb8[1]);
-        unlift(sb7[1], b7.y, sb8[2], sb8[3]);
-        unlift(sa8[0], a8.x, v[0], v[1]);
-        unlift(sa8[1], a8.y, v[2], v[3]);
-        unlift(sa8[2], a8.z, v[4], v[5]);
-        unlift(sa8[3], a8.w, v[6], v[7]);
-        unlift(sb8[0], b8.x, w[0], w[1]);
-        unlift(sb8[1], b8.y, w[2], w[3]);
-        unlift(sb8[2], b8.z, w[4], w[5]);
-        unlift(sb8[3], b8.w, w[6], w[7]);
+        for (int ch = 0; ch < C; ++ch) {
+#if FRI_DEC_EAGER
+            int4 a8 = A8[ch], b8 = B8[ch];
+            int2 a7 = A7[ch], b7 = B7[ch];
+            int a6 = A6[ch], b6 = B6[ch];
+#else
+            const int32_t *in = coefs + ta.block + ((int64_t)ch << g.depth);
+            const int32_t *i8 = in + (node << 8), *i7 = in + (node << 7), *i6 = in + (node << 6);
+            int4 a8 = __ldcs(reinterpret_cast<const int4 *>(i8) + lane);
+            int4 b8 = __ldcs(reinterpret_cast<const int4 *>(i8 + 128) + lane);
+            int2 a7 = __ldcs(reinterpret_cast<const int2 *>(i7) + lane);
+            int2 b7 = __ldcs(reinterpret_cast<const int2 *>(i7 + 64) + lane);
+            int a6 = __ldcs(i6 + lane);
+            int b6 = __ldcs(i6 + 32 + lane);
+#endif
+            const int sA = scratch[ch * kScratchInts + lane], sB = scratch[ch * kScratchInts + 32 + lane];
 
-        // scatter into the staged region (clamp: images.rs:109)
-        uint8_t *p0 = lane_base + g.tile_off[slot] + ch * SB;
-        uint8_t *p1 = p0 + g.pitch, *p2 = p1 + g.pitch;
+            if ((qp.active >> (top + 6)) & 0xfu) {
+                const int r8 = b8.w, r7 = b7.y, r6 = b6;  // raw values of the level-last nodes
+                const int mul = qp.multiply;
+                if ((qp.active >> (top + 8)) & 1u) {
+                    const Div dv = qp.div(top + 8);
+                    const int q = qp.q[top + 8];
+#define FRI_DQ(x) x = mul ? (int)((unsigned)(x) * (unsigned)q) : trunc_div(x, dv)
+                    FRI_DQ(a8.x); FRI_DQ(a8.y); FRI_DQ(a8.z); FRI_DQ(a8.w);
+                    FRI_DQ(b8.x); FRI_DQ(b8.y); FRI_DQ(b8.z); FRI_DQ(b8.w);
+                }
+                if ((qp.active >> (top + 7)) & 1u) {
+                    const Div dv = qp.div(top + 7);
+                    const int q = qp.q[top + 7];
+                    FRI_DQ(a7.x); FRI_DQ(a7.y); FRI_DQ(b7.x); FRI_DQ(b7.y);
+                }
+                if ((qp.active >> (top + 6)) & 1u) {
+                    const Div dv = qp.div(top + 6);
+                    const int q = qp.q[top + 6];
+                    FRI_DQ(a6); FRI_DQ(b6);
+#undef FRI_DQ
+                }
+                if (lastB) {
+                    b8.w = dequant_layer(qp, r8, top + 9);
+                    b7.y = dequant_layer(qp, r7, top + 8);
+                    b6 = dequant_layer(qp, r6, top + 7);
+                }
+            }
+
+            // levels 6, 7, 8 in registers
+            int sa7[2], sb7[2], sa8[4], sb8[4], v[8], w[8];
+            unlift(sA, a6, sa7[0], sa7[1]);
+            unlift(sB, b6, sb7[0], sb7[1]);
+            unlift(sa7[0], a7.x, sa8[0], sa8[1]);
+            unlift(sa7[1], a7.y, sa8[2], sa8[3]);
+            unlift(sb7[0], b7.x, sb8[0], sb8[1]);
+            unlift(sb7[1], b7.y, sb8[2], sb8[3]);
+            unlift(sa8[0], a8.x, v[0], v[1]);
+            unlift(sa8[1], a8.y, v[2], v[3]);
+            unlift(sa8[2], a8.z, v[4], v[5]);
+            unlift(sa8[3], a8.w, v[6], v[7]);
+            unlift(sb8[0], b8.x, w[0], w[1]);
+            unlift(sb8[1], b8.y, w[2], w[3]);
+            unlift(sb8[2], b8.z, w[4], w[5]);
+            unlift(sb8[3], b8.w, w[6], w[7]);
+
+            // scatter into the staged region (clamp: images.rs:109)
+            uint8_t *p0 = t0 + ch * SB, *p1 = p0 + g.pitch, *p2 = p1 + g.pitch;
 #define FRI_ST(ptr, dx, val) (*reinterpret_cast<S *>((ptr) + (dx) * PB) = clamp_sample<S>(val))
-        FRI_ST(p0, 0, v[0]);  FRI_ST(p1, 0, v[1]);
-        FRI_ST(p1, -1, v[2]); FRI_ST(p2, -1, v[3]);
-        FRI_ST(p0, 2, v[4]);  FRI_ST(p1, 2, v[5]);
-        FRI_ST(p1, 1, v[6]);  FRI_ST(p2, 1, v[7]);
-        FRI_ST(p0 + half, 0, w[0]);  FRI_ST(p1 + half, 0, w[1]);
-        FRI_ST(p1 + half, -1, w[2]); FRI_ST(p2 + half, -1, w[3]);
-        FRI_ST(p0 + half, 2, w[4]);  FRI_ST(p1 + half, 2, w[5]);
-        FRI_ST(p1 + half, 1, w[6]);  FRI_ST(p2 + half, 1, w[7]);
+            FRI_ST(p0, 0, v[0]);  FRI_ST(p1, 0, v[1]);
+            FRI_ST(p1, -1, v[2]); FRI_ST(p2, -1, v[3]);
+            FRI_ST(p0, 2, v[4]);  FRI_ST(p1, 2, v[5]);
+            FRI_ST(p1, 1, v[6]);  FRI_ST(p2, 1, v[7]);
+            FRI_ST(p0 + half, 0, w[0]);  FRI_ST(p1 + half, 0, w[1]);
+            FRI_ST(p1 + half, -1, w[2]); FRI_ST(p2 + half, -1, w[3]);
+            FRI_ST(p0 + half, 2, w[4]);  FRI_ST(p1 + half, 2, w[5]);
+            FRI_ST(p1 + half, 1, w[6]);  FRI_ST(p2 + half, 1, w[7]);
 #undef FRI_ST
+        }
+        __syncwarp();
     }
     __syncthreads();
 
@@ -573,20 +654,20 @@ fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
     const uint16_t *cmk = chunk_mask + (size_t)rv.phi0 * g.list_cap;
     const int n_full = g.list_full[rv.phi0], n_all = g.list_all[rv.phi0];
     if (rv.interior) {
-        for (int k = threadIdx.x; k < n_full; k += kThreads) {
+        for (int k = threadIdx.x; k < n_full; k += n_threads) {
             const uint32_t e = __ldg(cl + k);
             const int r = (int)(e >> 16), s = (int)(e & 0xffffu) << 4;
             *reinterpret_cast<int4 *>(reinterpret_cast<uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s) =
                 *reinterpret_cast<const int4 *>(region + s);
         }
-        for (int k = n_full + threadIdx.x; k < n_all; k += kThreads) {
+        for (int k = n_full + threadIdx.x; k < n_all; k += n_threads) {
             const uint32_t e = __ldg(cl + k);
             const int r = (int)(e >> 16), s = (int)(e & 0xffffu) << 4;
             store_chunk_masked(reinterpret_cast<uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s, region + s, __ldg(cmk + k));
         }
     } else {
         const int stride32 = (int)g.row_stride;
-        for (int k = threadIdx.x; k < n_all; k += kThreads) {
+        for (int k = threadIdx.x; k < n_all; k += n_threads) {
             const uint32_t e = __ldg(cl + k);
             const int r = (int)(e >> 16), s = (int)(e & 0xffffu) << 4;
             if ((unsigned)(gd.y0 + r) >= (unsigned)g.height) continue;
@@ -700,13 +781,13 @@ cudaError_t launch_encode(const Geometry &g, const DeviceTables &t, const QuantP
         int32_t *c = d_coefs + (int64_t)f0 * g.coefs_per_frame;
         int32_t *dc = d_dc ? d_dc + (((int64_t)f0 * g.n_fractals * g.channels) << g.sub_bits) : nullptr;
         if (g.channels == 1 && g.sample_bytes == 1)
-            fri_encode_kernel<1, uint8_t><<<grid, kThreads, smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, p, c, dc);
+            fri_encode_kernel<1, uint8_t><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, p, c, dc);
         else if (g.channels == 3 && g.sample_bytes == 1)
-            fri_encode_kernel<3, uint8_t><<<grid, kThreads, smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, p, c, dc);
+            fri_encode_kernel<3, uint8_t><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, p, c, dc);
         else if (g.channels == 1 && g.sample_bytes == 2)
-            fri_encode_kernel<1, uint16_t><<<grid, kThreads, smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, p, c, dc);
+            fri_encode_kernel<1, uint16_t><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, p, c, dc);
         else
-            fri_encode_kernel<3, uint16_t><<<grid, kThreads, smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, p, c, dc);
+            fri_encode_kernel<3, uint16_t><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, p, c, dc);
         if (launches) ++*launches;
     }
     if (g.sub_bits > 0) {
@@ -738,13 +819,13 @@ cudaError_t launch_decode(const Geometry &g, const DeviceTables &t, const QuantP
         const int32_t *c = d_coefs + (int64_t)f0 * g.coefs_per_frame;
         int32_t *dc = d_dc ? d_dc + (((int64_t)f0 * g.n_fractals * g.channels) << g.sub_bits) : nullptr;
         if (g.channels == 1 && g.sample_bytes == 1)
-            fri_decode_kernel<1, uint8_t><<<grid, kThreads, smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, t.chunk_mask, c, dc, p);
+            fri_decode_kernel<1, uint8_t><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, t.chunk_mask, c, dc, p);
         else if (g.channels == 3 && g.sample_bytes == 1)
-            fri_decode_kernel<3, uint8_t><<<grid, kThreads, smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, t.chunk_mask, c, dc, p);
+            fri_decode_kernel<3, uint8_t><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, t.chunk_mask, c, dc, p);
         else if (g.channels == 1 && g.sample_bytes == 2)
-            fri_decode_kernel<1, uint16_t><<<grid, kThreads, smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, t.chunk_mask, c, dc, p);
+            fri_decode_kernel<1, uint16_t><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, t.chunk_mask, c, dc, p);
         else
-            fri_decode_kernel<3, uint16_t><<<grid, kThreads, smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, t.chunk_mask, c, dc, p);
+            fri_decode_kernel<3, uint16_t><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, t.chunk_mask, c, dc, p);
         if (launches) ++*launches;
     }
     return cudaGetLastError();

@@ -52,9 +52,10 @@ struct QuantParams {
 Div make_div(int32_t q);  // q >= 2
 void make_quant_params(QuantParams &qp, const int32_t *q, int multiply);
 
-constexpr int kThreads = 256;       // 8 warps per CTA
-constexpr int kWarps = kThreads / 32;
-constexpr int kScratchInts = 64;    // per-warp exchange buffer for the top 64 coefficients
+constexpr int kThreads = 256;       // upper bound on threads per CTA (launch bounds)
+constexpr int kMaxWarps = kThreads / 32;
+int cta_threads(const Geometry &g);  // threads per CTA for a plan: one warp per two base tiles of a full group
+constexpr int kScratchInts = 64;    // per warp and channel: the 64 level-6 low-pass values of a base tile
 
 size_t kernel_smem_bytes(const Geometry &g);
 

@@ -2,6 +2,8 @@
 #include "fri_plan.h"
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <unordered_set>
@@ -108,6 +110,11 @@ std::string build_plan(Plan &plan, uint32_t width, uint32_t height, uint32_t cha
     if (sample_bytes != 1 && sample_bytes != 2) return "sample_bytes must be 1 or 2";
     if (depth < (uint32_t)kBaseDepth || depth > (uint32_t)kMaxDepth) return "depth must be in [9, 24]";
     const int csz = (int)(channels * sample_bytes);
+    int tiles_per_warp = 2;
+    if (const char *env = std::getenv("FRI_TILES_PER_WARP")) tiles_per_warp = std::max(1, std::atoi(env));
+    if (group_a == 0 || group_b == 0) {
+        if (const char *env = std::getenv("FRI_GROUP")) std::sscanf(env, "%dx%d", &group_a, &group_b);  // tuning knob
+    }
     if (group_a == 0 || group_b == 0) {
         // Default CTA group: enough (tile, channel) tasks per CTA, small enough that four CTAs
         // fit in one SM's shared memory.
@@ -235,6 +242,7 @@ std::string build_plan(Plan &plan, uint32_t width, uint32_t height, uint32_t cha
     g.depth = (int32_t)depth;
     g.sub_bits = sub_bits;
     g.group_a = group_a; g.group_b = group_b;
+    g.tiles_per_warp = tiles_per_warp;
     g.region_w = gxmax - gxmin + kTileCols;
     g.region_h = gymax - gymin + kTileRows;
     g.row_bytes = g.region_w * csz;

@@ -39,6 +39,8 @@ struct Geometry {
     int32_t n_base_tiles;        // base tiles processed per frame (n_fractals << sub_bits)
     int32_t n_fractals;          // retained fractals per frame (== n_base_tiles at depth 9)
     int32_t list_cap;            // entries per phase in the chunk list
+    int32_t tiles_per_warp;      // base tiles each warp of a CTA processes (full group)
+    int32_t pad_;
     int64_t row_stride;          // width * channels * sample_bytes
     int64_t frame_bytes;         // height * row_stride
     int64_t coefs_per_frame;     // n_fractals * channels * 2^depth
