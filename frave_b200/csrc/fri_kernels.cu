@@ -26,7 +26,9 @@
 //     that the small coarse kernel folds through the remaining depth-9 levels.
 #include "fri_kernels.cuh"
 
+#include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 
 namespace fri {
 
@@ -479,8 +481,9 @@ fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
     const bool sparse_group = (gd.tile_mask & (gd.tile_mask + 1u)) != 0;
     const int grp = min(lane >> 3, C - 1), j8 = lane & 7;
     const bool grp_live = (lane >> 3) < C;
-    // Pull the group's coefficients towards L2 now: at depth 9 the blocks of a group's tiles are
-    // adjacent (plan order is group-major), n_present * C * 2 KB in one run.
+    // Pull the group's coefficients towards L2 right away: at depth 9 the blocks of a group's
+    // tiles are adjacent (plan order is group-major), n_present * C * 2 KB in one run, so the
+    // warps' second and later tiles find their coefficients in L2.
     if (g.sub_bits == 0) {
         const char *first = reinterpret_cast<const char *>(coefs + ((((int64_t)frame * g.n_fractals + gd.tile_base) * C) << kBaseDepth));
         const int lines = n_present * C * 16;  // 128-byte lines
