@@ -240,80 +240,71 @@ __device__ __forceinline__ void store_chunk_masked(uint8_t *gp, const uint8_t *s
 }
 
 // ------------------------------------------------------------------------------------------
-// encode: pixels -> quantized coefficients
+// CTA-level building blocks
 // ------------------------------------------------------------------------------------------
-//
-// Per warp iteration: one base tile, all C channels.
-//   phase 1 (per channel): gather 16 leaves per lane, levels 8..6 in registers, quantize, store;
-//                          the 64 level-6 low-pass values go to the warp's scratch.
-//   phase 2 (all channels at once): lane group g = lane / 8 owns channel g; lane j of the group
-//                          folds s6[8j .. 8j+7] through levels 5..3 in registers and levels 2..0
-//                          with three shuffles inside the group.
-#ifndef FRI_DEC_EAGER
-#define FRI_DEC_EAGER 0
-#endif
-#ifndef FRI_ENC_MINB
-#define FRI_ENC_MINB 4
-#endif
-#ifndef FRI_DEC_MINB
-#define FRI_DEC_MINB 4
-#endif
-template <int C, typename S>
-__global__ void __launch_bounds__(kThreads, FRI_ENC_MINB)
-fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ QuantParams qp,
-                  const GroupDesc *__restrict__ groups, const uint32_t *__restrict__ tile_unit,
-                  const uint32_t *__restrict__ chunk_list, const uint8_t *__restrict__ pixels,
-                  int32_t *__restrict__ coefs, int32_t *__restrict__ dc_out)
+
+constexpr int kListUnroll = 4;
+constexpr uint32_t kNoChunk = 0xffffffffu;  // not a valid chunk-list entry (row 65535)
+
+// Enqueues the copy of a group's pixel footprint into `region`: one 16-byte chunk (aligned in
+// global and in shared memory) per thread and iteration, taken from the plan's list of chunks
+// that hold at least one pixel of the group's tiles.  Completion: cp.async.wait_all + barrier.
+__device__ __forceinline__ void stage_group(const Geometry &g, const GroupDesc &gd, const RegionView &rv,
+                                            const uint32_t *__restrict__ chunk_list, uint8_t *region)
 {
-    constexpr int SB = (int)sizeof(S);
-    constexpr int PB = C * SB;
-    extern __shared__ __align__(16) uint8_t smem[];
-    uint8_t *region = smem;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int32_t *scratch = reinterpret_cast<int32_t *>(smem + (((size_t)g.region_h * g.pitch + 15) & ~(size_t)15)) + warp * (C * kScratchInts);
-    const int n_warps = blockDim.x >> 5, n_threads = blockDim.x;
-
-    const GroupDesc gd = groups[blockIdx.x];
-    const int frame = blockIdx.y;
-    const uint8_t *fbase = pixels + (int64_t)frame * g.frame_bytes;
-    const RegionView rv = region_view<PB>(g, gd, fbase);
-
-    // ---- stage the group's pixel footprint: one 16-byte chunk (aligned in global and in shared
-    // memory) per thread and iteration, taken from the plan's list of chunks that hold at least
-    // one pixel of this group's tiles.
-    {
-        const uint32_t *cl = chunk_list + (size_t)rv.phi0 * g.list_cap;
-        const int n_all = g.list_all[rv.phi0];
-        if (rv.interior) {
-            for (int k = threadIdx.x; k < n_all; k += n_threads) {
-                const uint32_t e = __ldg(cl + k);
-                const int r = (int)(e >> 16), s = (int)(e & 0xffffu) << 4;
-                cp_async_16(region + s, reinterpret_cast<const uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s);
-            }
-        } else {
-            const int stride32 = (int)g.row_stride;
-            for (int k = threadIdx.x; k < n_all; k += n_threads) {
-                const uint32_t e = __ldg(cl + k);
-                const int r = (int)(e >> 16), s = (int)(e & 0xffffu) << 4;
-                const int y = gd.y0 + r;
-                const bool yin = (unsigned)y < (unsigned)g.height;
-                const int xb = rv.xb0 + s - (r * g.pitch + rv.phi0);  // byte position of the chunk inside image row y
-                const uint8_t *gp = reinterpret_cast<const uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s;
-                if (yin && xb >= 0 && xb + 16 <= stride32) {
-                    cp_async_16(region + s, gp);
-                } else if (!yin || xb + 16 <= 0 || xb >= stride32) {
-                    *reinterpret_cast<int4 *>(region + s) = make_int4(0, 0, 0, 0);
-                } else {  // chunk straddles the left or right image edge
-#pragma unroll 1
-                    for (int j = 0; j < 16; ++j)
-                        region[s + j] = (xb + j >= 0 && xb + j < stride32) ? __ldg(gp + j) : (uint8_t)0;
+    const int n_threads = blockDim.x;
+    const uint32_t *cl = chunk_list + (size_t)rv.phi0 * g.list_cap;
+    const int n_all = g.list_all[rv.phi0];
+    if (rv.interior) {
+        // list entries are fetched four at a time so that their latencies overlap
+        for (int k0 = threadIdx.x; k0 < n_all; k0 += kListUnroll * n_threads) {
+            uint32_t e[kListUnroll];
+#pragma unroll
+            for (int u = 0; u < kListUnroll; ++u) e[u] = k0 + u * n_threads < n_all ? __ldg(cl + k0 + u * n_threads) : kNoChunk;
+#pragma unroll
+            for (int u = 0; u < kListUnroll; ++u)
+                if (e[u] != kNoChunk) {
+                    const int r = (int)(e[u] >> 16), s = (int)(e[u] & 0xffffu) << 4;
+                    cp_async_16(region + s, reinterpret_cast<const uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s);
                 }
+        }
+    } else {
+        const int stride32 = (int)g.row_stride;
+        for (int k = threadIdx.x; k < n_all; k += n_threads) {
+            const uint32_t e = __ldg(cl + k);
+            const int r = (int)(e >> 16), s = (int)(e & 0xffffu) << 4;
+            const int y = gd.y0 + r;
+            const bool yin = (unsigned)y < (unsigned)g.height;
+            const int xb = rv.xb0 + s - (r * g.pitch + rv.phi0);  // byte position of the chunk inside image row y
+            const uint8_t *gp = reinterpret_cast<const uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s;
+            if (yin && xb >= 0 && xb + 16 <= stride32) {
+                cp_async_16(region + s, gp);
+            } else if (!yin || xb + 16 <= 0 || xb >= stride32) {
+                *reinterpret_cast<int4 *>(region + s) = make_int4(0, 0, 0, 0);
+            } else {  // chunk straddles the left or right image edge
+#pragma unroll 1
+                for (int j = 0; j < 16; ++j)
+                    region[s + j] = (xb + j >= 0 && xb + j < stride32) ? __ldg(gp + j) : (uint8_t)0;
             }
         }
     }
-    cp_async_wait_all();
-    __syncthreads();
+}
 
+// Forward transform + quantization of the tiles of one staged group; warp w takes tiles
+// w, w + n_warps, ...  Per warp iteration: one base tile, all C channels.
+//   phase 1 (per channel): gather 16 leaves per lane, levels 8..6 in registers, quantize, store;
+//                          the 64 level-6 low-pass values go to the warp's scratch.
+//   phase 2 (all channels at once): lane group lane / 8 owns a channel; lane j of the group
+//                          folds s6[8j .. 8j+7] through levels 5..3 in registers and levels 2..0
+//                          with three shuffles inside the group.
+template <int C, typename S>
+__device__ __forceinline__ void encode_tiles(const Geometry &g, const QuantParams &qp, const GroupDesc &gd, const RegionView &rv,
+                                             const uint32_t *__restrict__ tile_unit, int frame, const uint8_t *region,
+                                             int32_t *scratch, int32_t *__restrict__ coefs, int32_t *__restrict__ dc_out)
+{
+    constexpr int SB = (int)sizeof(S);
+    constexpr int PB = C * SB;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     const int n_present = __popc(gd.tile_mask);
     const uint8_t *lane_base = region + rv.phi0 + lane_anchor_bytes(lane, g.pitch, PB);
     const int half = kHalfB.y * g.pitch + kHalfB.x * PB;
@@ -446,34 +437,32 @@ fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// decode: quantized coefficients -> pixels
-// ------------------------------------------------------------------------------------------
-//
-// Mirror image of the encoder: per warp iteration one base tile, all C channels; lane group
-// g = lane / 8 first unfolds levels 0..5 of channel g (lane j ends with the eight level-6
-// low-pass values 8j .. 8j+7) into the warp's scratch, then every lane unfolds its two depth-3
-// subtrees per channel and scatters the 16 leaves into the staged region.
+// Pulls a group's coefficients towards L2: at depth 9 the blocks of a group's tiles are adjacent
+// (plan order is group-major), n_present * C * 2 KB in one run.
+template <int C>
+__device__ __forceinline__ void prefetch_group_coefs(const Geometry &g, const GroupDesc &gd, int frame,
+                                                     const int32_t *__restrict__ coefs)
+{
+    if (g.sub_bits != 0) return;
+    const char *first = reinterpret_cast<const char *>(coefs + ((((int64_t)frame * g.n_fractals + gd.tile_base) * C) << kBaseDepth));
+    const int lines = __popc(gd.tile_mask) * C * 16;  // 128-byte lines
+    for (int i = threadIdx.x; i < lines; i += blockDim.x)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(first + (size_t)i * 128));
+}
+
+// Dequantization + inverse transform of the tiles of one group into the staged region; mirror
+// image of encode_tiles: lane group lane / 8 first unfolds levels 0..5 of its channel (lane j
+// ends with the eight level-6 low-pass values 8j .. 8j+7) into the warp's scratch, then every
+// lane unfolds its two depth-3 subtrees per channel and scatters the 16 clamped leaves.
 template <int C, typename S>
-__global__ void __launch_bounds__(kThreads, FRI_DEC_MINB)
-fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ QuantParams qp,
-                  const GroupDesc *__restrict__ groups, const uint32_t *__restrict__ tile_unit,
-                  const uint32_t *__restrict__ chunk_list, const uint16_t *__restrict__ chunk_mask,
-                  const int32_t *__restrict__ coefs, const int32_t *__restrict__ dc_in, uint8_t *__restrict__ pixels)
+__device__ __forceinline__ void decode_tiles(const Geometry &g, const QuantParams &qp, const GroupDesc &gd, const RegionView &rv,
+                                             const uint32_t *__restrict__ tile_unit, int frame, uint8_t *region,
+                                             int32_t *scratch, const int32_t *__restrict__ coefs,
+                                             const int32_t *__restrict__ dc_in)
 {
     constexpr int SB = (int)sizeof(S);
     constexpr int PB = C * SB;
-    extern __shared__ __align__(16) uint8_t smem[];
-    uint8_t *region = smem;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int32_t *scratch = reinterpret_cast<int32_t *>(smem + (((size_t)g.region_h * g.pitch + 15) & ~(size_t)15)) + warp * (C * kScratchInts);
-    const int n_warps = blockDim.x >> 5, n_threads = blockDim.x;
-
-    const GroupDesc gd = groups[blockIdx.x];
-    const int frame = blockIdx.y;
-    uint8_t *fbase = pixels + (int64_t)frame * g.frame_bytes;
-    const RegionView rv = region_view<PB>(g, gd, fbase);
-
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     const int n_present = __popc(gd.tile_mask);
     uint8_t *lane_base = region + rv.phi0 + lane_anchor_bytes(lane, g.pitch, PB);
     const int half = kHalfB.y * g.pitch + kHalfB.x * PB;
@@ -481,46 +470,30 @@ fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
     const bool sparse_group = (gd.tile_mask & (gd.tile_mask + 1u)) != 0;
     const int grp = min(lane >> 3, C - 1), j8 = lane & 7;
     const bool grp_live = (lane >> 3) < C;
-    // Pull the group's coefficients towards L2 right away: at depth 9 the blocks of a group's
-    // tiles are adjacent (plan order is group-major), n_present * C * 2 KB in one run, so the
-    // warps' second and later tiles find their coefficients in L2.
-    if (g.sub_bits == 0) {
-        const char *first = reinterpret_cast<const char *>(coefs + ((((int64_t)frame * g.n_fractals + gd.tile_base) * C) << kBaseDepth));
-        const int lines = n_present * C * 16;  // 128-byte lines
-        for (int i = threadIdx.x; i < lines; i += n_threads)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(first + (size_t)i * 128));
-    }
-    // A lattice tile the reference's BFS never built (possible only next to the image border,
-    // e.g. 480x270) still owns its pixels in the chunk masks: stage zeros for it, which is
-    // what from_wavelet's zero-initialised raster holds there (wavelet_transform.rs:309-317).
-    if (n_present != g.group_a * g.group_b) {
-        const int n16 = (g.region_h * g.pitch + 15) >> 4;
-        for (int i = threadIdx.x; i < n16; i += n_threads) reinterpret_cast<int4 *>(region)[i] = make_int4(0, 0, 0, 0);
-        __syncthreads();
-    }
     for (int e = warp; e < n_present; e += n_warps) {
         const int slot = sparse_group ? (int)__fns(gd.tile_mask, 0, e + 1) : e;
         const TaskAddr ta = task_addr<C>(g, tile_unit, frame, gd.tile_base + e, 0);
         const bool lastB = ta.last && lane == 31;
         const size_t node = ta.node;
 
-#if FRI_DEC_EAGER
-        // all of the tile's loads in flight before the first use
-        int4 A8[C], B8[C];
-        int2 A7[C], B7[C];
-        int A6[C], B6[C];
-#pragma unroll
-        for (int ch = 0; ch < C; ++ch) {
-            const int32_t *in = coefs + ta.block + ((int64_t)ch << g.depth);
-            const int32_t *i8 = in + (node << 8), *i7 = in + (node << 7), *i6 = in + (node << 6);
-            A8[ch] = __ldcs(reinterpret_cast<const int4 *>(i8) + lane);
-            B8[ch] = __ldcs(reinterpret_cast<const int4 *>(i8 + 128) + lane);
-            A7[ch] = __ldcs(reinterpret_cast<const int2 *>(i7) + lane);
-            B7[ch] = __ldcs(reinterpret_cast<const int2 *>(i7 + 64) + lane);
-            A6[ch] = __ldcs(i6 + lane);
-            B6[ch] = __ldcs(i6 + 32 + lane);
+        // channel 0's coefficient runs are requested before anything is waited for; channel
+        // c + 1's while channel c is unfolded (register double buffer)
+        int4 n_a8, n_b8;
+        int2 n_a7, n_b7;
+        int n_a6, n_b6;
+#define FRI_LOAD_CH(ch)                                                                          \
+        {                                                                                        \
+            const int32_t *in_ = coefs + ta.block + ((int64_t)(ch) << g.depth);                  \
+            const int32_t *i8 = in_ + (node << 8), *i7 = in_ + (node << 7), *i6 = in_ + (node << 6); \
+            n_a8 = __ldcs(reinterpret_cast<const int4 *>(i8) + lane);                            \
+            n_b8 = __ldcs(reinterpret_cast<const int4 *>(i8 + 128) + lane);                      \
+            n_a7 = __ldcs(reinterpret_cast<const int2 *>(i7) + lane);                            \
+            n_b7 = __ldcs(reinterpret_cast<const int2 *>(i7 + 64) + lane);                       \
+            n_a6 = __ldcs(i6 + lane);                                                            \
+            n_b6 = __ldcs(i6 + 32 + lane);                                                       \
         }
-#endif
+        FRI_LOAD_CH(0)
+
         // ---- levels 0..5 of all channels, 8 lanes per channel
         {
             const int32_t *in = coefs + ta.block + ((int64_t)grp << g.depth);
@@ -570,20 +543,10 @@ fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
         uint8_t *t0 = lane_base + g.tile_off[slot];
 #pragma unroll
         for (int ch = 0; ch < C; ++ch) {
-#if FRI_DEC_EAGER
-            int4 a8 = A8[ch], b8 = B8[ch];
-            int2 a7 = A7[ch], b7 = B7[ch];
-            int a6 = A6[ch], b6 = B6[ch];
-#else
-            const int32_t *in = coefs + ta.block + ((int64_t)ch << g.depth);
-            const int32_t *i8 = in + (node << 8), *i7 = in + (node << 7), *i6 = in + (node << 6);
-            int4 a8 = __ldcs(reinterpret_cast<const int4 *>(i8) + lane);
-            int4 b8 = __ldcs(reinterpret_cast<const int4 *>(i8 + 128) + lane);
-            int2 a7 = __ldcs(reinterpret_cast<const int2 *>(i7) + lane);
-            int2 b7 = __ldcs(reinterpret_cast<const int2 *>(i7 + 64) + lane);
-            int a6 = __ldcs(i6 + lane);
-            int b6 = __ldcs(i6 + 32 + lane);
-#endif
+            int4 a8 = n_a8, b8 = n_b8;
+            int2 a7 = n_a7, b7 = n_b7;
+            int a6 = n_a6, b6 = n_b6;
+            if (ch + 1 < C) FRI_LOAD_CH(ch + 1)
             const int sA = scratch[ch * kScratchInts + lane], sB = scratch[ch * kScratchInts + 32 + lane];
 
             if ((qp.active >> (top + 6)) & 0xfu) {
@@ -644,24 +607,45 @@ fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
             FRI_ST(p1 + half, 1, w[6]);  FRI_ST(p2 + half, 1, w[7]);
 #undef FRI_ST
         }
+#undef FRI_LOAD_CH
         __syncwarp();
     }
-    __syncthreads();
+}
 
-    // ---- write-out in 16-byte chunks aligned in global memory, one chunk per thread and
-    // iteration from the plan's chunk list.  Only bytes of pixels that belong to this group's
-    // tiles (chunk masks) and lie inside the image (set_pixel's bounds check, images.rs:104) are
-    // written: fully owned chunks as one 128-bit store, the chunks along the group's fractal
-    // outline byte-masked.
+// Zero-fills a region buffer (a lattice tile the reference's BFS never built — possible only
+// next to the image border, e.g. 480x270 — still owns its pixels in the chunk masks: staging
+// zeros for it reproduces from_wavelet's zero-initialised raster, wavelet_transform.rs:309-317).
+__device__ __forceinline__ void zero_region(const Geometry &g, uint8_t *region)
+{
+    const int n16 = (g.region_h * g.pitch + 15) >> 4;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) reinterpret_cast<int4 *>(region)[i] = make_int4(0, 0, 0, 0);
+}
+
+// Writes a decoded region out in 16-byte chunks aligned in global memory, one chunk per thread
+// and iteration from the plan's chunk list.  Only bytes of pixels that belong to the group's
+// tiles (chunk masks) and lie inside the image (set_pixel's bounds check, images.rs:104) are
+// written: fully owned chunks as one 128-bit store, the chunks along the group's fractal outline
+// byte-masked.
+__device__ __forceinline__ void write_out_group(const Geometry &g, const GroupDesc &gd, const RegionView &rv,
+                                                const uint32_t *__restrict__ chunk_list,
+                                                const uint16_t *__restrict__ chunk_mask, const uint8_t *region)
+{
+    const int n_threads = blockDim.x;
     const uint32_t *cl = chunk_list + (size_t)rv.phi0 * g.list_cap;
     const uint16_t *cmk = chunk_mask + (size_t)rv.phi0 * g.list_cap;
     const int n_full = g.list_full[rv.phi0], n_all = g.list_all[rv.phi0];
     if (rv.interior) {
-        for (int k = threadIdx.x; k < n_full; k += n_threads) {
-            const uint32_t e = __ldg(cl + k);
-            const int r = (int)(e >> 16), s = (int)(e & 0xffffu) << 4;
-            *reinterpret_cast<int4 *>(reinterpret_cast<uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s) =
-                *reinterpret_cast<const int4 *>(region + s);
+        for (int k0 = threadIdx.x; k0 < n_full; k0 += kListUnroll * n_threads) {
+            uint32_t e[kListUnroll];
+#pragma unroll
+            for (int u = 0; u < kListUnroll; ++u) e[u] = k0 + u * n_threads < n_full ? __ldg(cl + k0 + u * n_threads) : kNoChunk;
+#pragma unroll
+            for (int u = 0; u < kListUnroll; ++u)
+                if (e[u] != kNoChunk) {
+                    const int r = (int)(e[u] >> 16), s = (int)(e[u] & 0xffffu) << 4;
+                    *reinterpret_cast<int4 *>(reinterpret_cast<uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s) =
+                        *reinterpret_cast<const int4 *>(region + s);
+                }
         }
         for (int k = n_full + threadIdx.x; k < n_all; k += n_threads) {
             const uint32_t e = __ldg(cl + k);
@@ -681,6 +665,180 @@ fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
             if (m) store_chunk_masked(reinterpret_cast<uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s, region + s, m);
         }
     }
+}
+
+__device__ __forceinline__ size_t region_bytes(const Geometry &g) { return ((size_t)g.region_h * g.pitch + 15) & ~(size_t)15; }
+
+// ------------------------------------------------------------------------------------------
+// one-group-per-CTA kernels (small launches: fewer groups than persistent CTAs)
+// ------------------------------------------------------------------------------------------
+#ifndef FRI_ENC_MINB
+#define FRI_ENC_MINB 4
+#endif
+#ifndef FRI_DEC_MINB
+#define FRI_DEC_MINB 4
+#endif
+template <int C, typename S>
+__global__ void __launch_bounds__(kThreads, FRI_ENC_MINB)
+fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ QuantParams qp,
+                  const GroupDesc *__restrict__ groups, const uint32_t *__restrict__ tile_unit,
+                  const uint32_t *__restrict__ chunk_list, const uint8_t *__restrict__ pixels,
+                  int32_t *__restrict__ coefs, int32_t *__restrict__ dc_out)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t *region = smem;
+    int32_t *scratch = reinterpret_cast<int32_t *>(smem + region_bytes(g)) + (threadIdx.x >> 5) * (C * kScratchInts);
+    const GroupDesc gd = groups[blockIdx.x];
+    const int frame = blockIdx.y;
+    const RegionView rv = region_view<C * (int)sizeof(S)>(g, gd, pixels + (int64_t)frame * g.frame_bytes);
+    stage_group(g, gd, rv, chunk_list, region);
+    cp_async_wait_all();
+    __syncthreads();
+    encode_tiles<C, S>(g, qp, gd, rv, tile_unit, frame, region, scratch, coefs, dc_out);
+}
+
+template <int C, typename S>
+__global__ void __launch_bounds__(kThreads, FRI_DEC_MINB)
+fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ QuantParams qp,
+                  const GroupDesc *__restrict__ groups, const uint32_t *__restrict__ tile_unit,
+                  const uint32_t *__restrict__ chunk_list, const uint16_t *__restrict__ chunk_mask,
+                  const int32_t *__restrict__ coefs, const int32_t *__restrict__ dc_in, uint8_t *__restrict__ pixels)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t *region = smem;
+    int32_t *scratch = reinterpret_cast<int32_t *>(smem + region_bytes(g)) + (threadIdx.x >> 5) * (C * kScratchInts);
+    const GroupDesc gd = groups[blockIdx.x];
+    const int frame = blockIdx.y;
+    const RegionView rv = region_view<C * (int)sizeof(S)>(g, gd, pixels + (int64_t)frame * g.frame_bytes);
+    prefetch_group_coefs<C>(g, gd, frame, coefs);
+    if (__popc(gd.tile_mask) != g.group_a * g.group_b) {
+        zero_region(g, region);
+        __syncthreads();
+    }
+    decode_tiles<C, S>(g, qp, gd, rv, tile_unit, frame, region, scratch, coefs, dc_in);
+    __syncthreads();
+    write_out_group(g, gd, rv, chunk_list, chunk_mask, region);
+}
+
+// ------------------------------------------------------------------------------------------
+// persistent kernels: a fixed grid of CTAs pulls (frame, group) work items from a counter
+// ------------------------------------------------------------------------------------------
+//
+// The staged region is double-buffered.  Encode: the cp.async copies of the next group's pixels
+// are in flight while the warps transform the current group, one CTA barrier per group.  Decode:
+// the next group's coefficients are prefetched towards L2 while the current group is unfolded,
+// and warps that finish their share of a group's write-out start on the next group's tiles
+// (other buffer) without waiting for the rest — again one barrier per group.
+struct WorkCounter {
+    unsigned int next;  // next unclaimed work item
+    unsigned int done;  // CTAs that have run out of work (the last one resets both)
+};
+
+__device__ __forceinline__ void finish_work(WorkCounter *wc)
+{
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&wc->done, 1u) == gridDim.x - 1) {
+            wc->next = 0;
+            wc->done = 0;
+        }
+    }
+}
+
+template <int C, typename S>
+__global__ void __launch_bounds__(kPersistThreads, 2)
+fri_encode_persistent_kernel(const __grid_constant__ Geometry g, const __grid_constant__ QuantParams qp,
+                             const GroupDesc *__restrict__ groups, const uint32_t *__restrict__ tile_unit,
+                             const uint32_t *__restrict__ chunk_list, const uint8_t *__restrict__ pixels,
+                             int32_t *__restrict__ coefs, int32_t *__restrict__ dc_out, unsigned int total,
+                             WorkCounter *wc)
+{
+    constexpr int PB = C * (int)sizeof(S);
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ unsigned int s_work[2];
+    const size_t rb = region_bytes(g);
+    int32_t *scratch = reinterpret_cast<int32_t *>(smem + 2 * rb) + (threadIdx.x >> 5) * (C * kScratchInts);
+
+    if (threadIdx.x == 0) s_work[0] = atomicAdd(&wc->next, 1u);
+    __syncthreads();
+    unsigned int cur = s_work[0];
+    GroupDesc gd{};
+    RegionView rv{};
+    int frame = 0;
+    if (cur < total) {
+        frame = (int)(cur / (unsigned)g.n_groups);
+        gd = groups[cur - (unsigned)frame * (unsigned)g.n_groups];
+        rv = region_view<PB>(g, gd, pixels + (int64_t)frame * g.frame_bytes);
+        stage_group(g, gd, rv, chunk_list, smem);
+    }
+    for (int it = 0; cur < total; ++it) {
+        if (threadIdx.x == 0) s_work[(it + 1) & 1] = atomicAdd(&wc->next, 1u);
+        cp_async_wait_all();  // this thread's copies of the current group have landed
+        __syncthreads();      // ... everybody's; and everybody is done with the other buffer
+        const unsigned int nxt = s_work[(it + 1) & 1];
+        GroupDesc ngd{};
+        RegionView nrv{};
+        int nframe = 0;
+        if (nxt < total) {
+            nframe = (int)(nxt / (unsigned)g.n_groups);
+            ngd = groups[nxt - (unsigned)nframe * (unsigned)g.n_groups];
+            nrv = region_view<PB>(g, ngd, pixels + (int64_t)nframe * g.frame_bytes);
+            stage_group(g, ngd, nrv, chunk_list, smem + ((it + 1) & 1) * rb);
+        }
+        encode_tiles<C, S>(g, qp, gd, rv, tile_unit, frame, smem + (it & 1) * rb, scratch, coefs, dc_out);
+        cur = nxt; gd = ngd; rv = nrv; frame = nframe;
+    }
+    finish_work(wc);
+}
+
+template <int C, typename S>
+__global__ void __launch_bounds__(kPersistThreads, 2)
+fri_decode_persistent_kernel(const __grid_constant__ Geometry g, const __grid_constant__ QuantParams qp,
+                             const GroupDesc *__restrict__ groups, const uint32_t *__restrict__ tile_unit,
+                             const uint32_t *__restrict__ chunk_list, const uint16_t *__restrict__ chunk_mask,
+                             const int32_t *__restrict__ coefs, const int32_t *__restrict__ dc_in,
+                             uint8_t *__restrict__ pixels, unsigned int total, WorkCounter *wc)
+{
+    constexpr int PB = C * (int)sizeof(S);
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ unsigned int s_work[3];
+    const size_t rb = region_bytes(g);
+    int32_t *scratch = reinterpret_cast<int32_t *>(smem + 2 * rb) + (threadIdx.x >> 5) * (C * kScratchInts);
+
+    // work items are claimed two ahead, so that the coefficients of the next group can be
+    // prefetched towards L2 a whole group before they are used
+    if (threadIdx.x == 0) {
+        s_work[0] = atomicAdd(&wc->next, 1u);
+        s_work[1] = atomicAdd(&wc->next, 1u);
+    }
+    __syncthreads();
+    unsigned int cur = s_work[0], nxt = s_work[1];
+    if (cur < total) {
+        const int f = (int)(cur / (unsigned)g.n_groups);
+        prefetch_group_coefs<C>(g, groups[cur - (unsigned)f * (unsigned)g.n_groups], f, coefs);
+    }
+    for (int it = 0; cur < total; ++it) {
+        const int frame = (int)(cur / (unsigned)g.n_groups);
+        const GroupDesc gd = groups[cur - (unsigned)frame * (unsigned)g.n_groups];
+        const RegionView rv = region_view<PB>(g, gd, pixels + (int64_t)frame * g.frame_bytes);
+        uint8_t *region = smem + (it & 1) * rb;
+        if (nxt < total) {
+            const int nf = (int)(nxt / (unsigned)g.n_groups);
+            prefetch_group_coefs<C>(g, groups[nxt - (unsigned)nf * (unsigned)g.n_groups], nf, coefs);
+        }
+        if (threadIdx.x == 0) s_work[(it + 2) % 3] = atomicAdd(&wc->next, 1u);
+        if (__popc(gd.tile_mask) != g.group_a * g.group_b) {  // rare (image border): an extra barrier
+            zero_region(g, region);
+            __syncthreads();
+        }
+        decode_tiles<C, S>(g, qp, gd, rv, tile_unit, frame, region, scratch, coefs, dc_in);
+        __syncthreads();  // the group's pixels are complete; s_work[(it+2)%3] is visible
+        const unsigned int nxt2 = s_work[(it + 2) % 3];
+        write_out_group(g, gd, rv, chunk_list, chunk_mask, region);
+        cur = nxt;
+        nxt = nxt2;
+    }
+    finish_work(wc);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -748,7 +906,7 @@ cudaError_t set_smem(K kernel, size_t bytes)
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
-constexpr size_t kMaxSmem = 227 * 1024;
+constexpr size_t kMaxSmem = 226 * 1024;  // dynamic part; leaves room for the kernels' few static bytes
 
 }  // namespace
 
@@ -756,42 +914,96 @@ cudaError_t configure_kernels()
 {
     cudaError_t e;
 #define FRI_CFG(k) if ((e = set_smem(k, kMaxSmem)) != cudaSuccess) return e
-    FRI_CFG((fri_encode_kernel<1, uint8_t>));
-    FRI_CFG((fri_encode_kernel<3, uint8_t>));
-    FRI_CFG((fri_encode_kernel<1, uint16_t>));
-    FRI_CFG((fri_encode_kernel<3, uint16_t>));
-    FRI_CFG((fri_decode_kernel<1, uint8_t>));
-    FRI_CFG((fri_decode_kernel<3, uint8_t>));
-    FRI_CFG((fri_decode_kernel<1, uint16_t>));
-    FRI_CFG((fri_decode_kernel<3, uint16_t>));
+#define FRI_CFG4(name)              \
+    FRI_CFG((name<1, uint8_t>));    \
+    FRI_CFG((name<3, uint8_t>));    \
+    FRI_CFG((name<1, uint16_t>));   \
+    FRI_CFG((name<3, uint16_t>))
+    FRI_CFG4(fri_encode_kernel);
+    FRI_CFG4(fri_decode_kernel);
+    FRI_CFG4(fri_encode_persistent_kernel);
+    FRI_CFG4(fri_decode_persistent_kernel);
     FRI_CFG(fri_coarse_forward_kernel);
     FRI_CFG(fri_coarse_inverse_kernel);
+#undef FRI_CFG4
 #undef FRI_CFG
     return cudaSuccess;
 }
 
+namespace {
+
+int sm_count()
+{
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+// Persistent launch shape: threads per CTA, dynamic shared memory, grid size; grid == 0 means
+// "use the one-group-per-CTA kernel" (too few groups to fill the persistent CTAs twice over).
+struct PersistShape {
+    int threads;
+    size_t smem;
+    unsigned grid;
+};
+
+PersistShape persist_shape(const Geometry &g, uint64_t total)
+{
+    PersistShape p;
+    const int tiles = g.group_a * g.group_b;
+    p.threads = 32 * std::max(1, std::min(kPersistThreads / 32, tiles));
+    p.smem = 2 * ((((size_t)g.region_h * g.pitch) + 15) & ~(size_t)15) + (size_t)(p.threads / 32) * g.channels * kScratchInts * sizeof(int32_t);
+    const int per_sm = 2;
+    const uint64_t slots = (uint64_t)sm_count() * per_sm;
+    int mode = -1;  // tuning knob: FRI_PERSISTENT=0/1 forces the choice
+    if (const char *env = std::getenv("FRI_PERSISTENT")) mode = std::atoi(env);
+    const bool fits = p.smem * per_sm + 2048 <= kMaxSmem;
+    (void)total;
+    const bool use = mode > 0 && fits;  // opt-in: measured slower than one group per CTA
+    p.grid = use ? (unsigned)std::min<uint64_t>(total, slots) : 0u;
+    return p;
+}
+
+}  // namespace
+
 cudaError_t launch_encode(const Geometry &g, const DeviceTables &t, const QuantParams &qp, const void *d_pixels,
-                          uint32_t n_frames, int32_t *d_coefs, int32_t *d_dc, cudaStream_t stream,
+                          uint32_t n_frames, int32_t *d_coefs, int32_t *d_dc, void *work_counter, cudaStream_t stream,
                           uint32_t *launches)
 {
     if (n_frames == 0 || g.n_groups == 0) return cudaSuccess;
-    const size_t smem = kernel_smem_bytes(g);
     const uint8_t *px = static_cast<const uint8_t *>(d_pixels);
-    for (uint32_t f0 = 0; f0 < n_frames; f0 += 65535u) {  // gridDim.y limit
-        const uint32_t nf = n_frames - f0 < 65535u ? n_frames - f0 : 65535u;
-        const dim3 grid((unsigned)g.n_groups, nf);
-        const uint8_t *p = px + (int64_t)f0 * g.frame_bytes;
-        int32_t *c = d_coefs + (int64_t)f0 * g.coefs_per_frame;
-        int32_t *dc = d_dc ? d_dc + (((int64_t)f0 * g.n_fractals * g.channels) << g.sub_bits) : nullptr;
-        if (g.channels == 1 && g.sample_bytes == 1)
-            fri_encode_kernel<1, uint8_t><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, p, c, dc);
-        else if (g.channels == 3 && g.sample_bytes == 1)
-            fri_encode_kernel<3, uint8_t><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, p, c, dc);
-        else if (g.channels == 1 && g.sample_bytes == 2)
-            fri_encode_kernel<1, uint16_t><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, p, c, dc);
-        else
-            fri_encode_kernel<3, uint16_t><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, p, c, dc);
+    const uint64_t total = (uint64_t)n_frames * g.n_groups;
+    const PersistShape ps = persist_shape(g, total);
+    if (ps.grid != 0 && work_counter != nullptr && total < 0xffff0000ull) {
+        WorkCounter *wc = static_cast<WorkCounter *>(work_counter);
+#define FRI_LAUNCH(CC, SS) fri_encode_persistent_kernel<CC, SS><<<ps.grid, ps.threads, ps.smem, stream>>>( \
+        g, qp, t.groups, t.tile_unit, t.chunk_list, px, d_coefs, d_dc, (unsigned)total, wc)
+        if (g.channels == 1 && g.sample_bytes == 1) FRI_LAUNCH(1, uint8_t);
+        else if (g.channels == 3 && g.sample_bytes == 1) FRI_LAUNCH(3, uint8_t);
+        else if (g.channels == 1 && g.sample_bytes == 2) FRI_LAUNCH(1, uint16_t);
+        else FRI_LAUNCH(3, uint16_t);
+#undef FRI_LAUNCH
         if (launches) ++*launches;
+    } else {
+        const size_t smem = kernel_smem_bytes(g);
+        for (uint32_t f0 = 0; f0 < n_frames; f0 += 65535u) {  // gridDim.y limit
+            const uint32_t nf = n_frames - f0 < 65535u ? n_frames - f0 : 65535u;
+            const dim3 grid((unsigned)g.n_groups, nf);
+            const uint8_t *p = px + (int64_t)f0 * g.frame_bytes;
+            int32_t *c = d_coefs + (int64_t)f0 * g.coefs_per_frame;
+            int32_t *dc = d_dc ? d_dc + (((int64_t)f0 * g.n_fractals * g.channels) << g.sub_bits) : nullptr;
+#define FRI_LAUNCH(CC, SS) fri_encode_kernel<CC, SS><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, p, c, dc)
+            if (g.channels == 1 && g.sample_bytes == 1) FRI_LAUNCH(1, uint8_t);
+            else if (g.channels == 3 && g.sample_bytes == 1) FRI_LAUNCH(3, uint8_t);
+            else if (g.channels == 1 && g.sample_bytes == 2) FRI_LAUNCH(1, uint16_t);
+            else FRI_LAUNCH(3, uint16_t);
+#undef FRI_LAUNCH
+            if (launches) ++*launches;
+        }
     }
     if (g.sub_bits > 0) {
         const unsigned blocks = (unsigned)((int64_t)n_frames * g.n_fractals * g.channels);
@@ -803,11 +1015,10 @@ cudaError_t launch_encode(const Geometry &g, const DeviceTables &t, const QuantP
 }
 
 cudaError_t launch_decode(const Geometry &g, const DeviceTables &t, const QuantParams &qp, const int32_t *d_coefs,
-                          uint32_t n_frames, void *d_pixels, int32_t *d_dc, cudaStream_t stream,
+                          uint32_t n_frames, void *d_pixels, int32_t *d_dc, void *work_counter, cudaStream_t stream,
                           uint32_t *launches)
 {
     if (n_frames == 0 || g.n_groups == 0) return cudaSuccess;
-    const size_t smem = kernel_smem_bytes(g);
     if (g.sub_bits > 0) {
         const unsigned blocks = (unsigned)((int64_t)n_frames * g.n_fractals * g.channels);
         const size_t cs = ((size_t)3 << g.sub_bits) / 2 * sizeof(int32_t) + 16;
@@ -815,21 +1026,34 @@ cudaError_t launch_decode(const Geometry &g, const DeviceTables &t, const QuantP
         if (launches) ++*launches;
     }
     uint8_t *px = static_cast<uint8_t *>(d_pixels);
-    for (uint32_t f0 = 0; f0 < n_frames; f0 += 65535u) {
-        const uint32_t nf = n_frames - f0 < 65535u ? n_frames - f0 : 65535u;
-        const dim3 grid((unsigned)g.n_groups, nf);
-        uint8_t *p = px + (int64_t)f0 * g.frame_bytes;
-        const int32_t *c = d_coefs + (int64_t)f0 * g.coefs_per_frame;
-        int32_t *dc = d_dc ? d_dc + (((int64_t)f0 * g.n_fractals * g.channels) << g.sub_bits) : nullptr;
-        if (g.channels == 1 && g.sample_bytes == 1)
-            fri_decode_kernel<1, uint8_t><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, t.chunk_mask, c, dc, p);
-        else if (g.channels == 3 && g.sample_bytes == 1)
-            fri_decode_kernel<3, uint8_t><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, t.chunk_mask, c, dc, p);
-        else if (g.channels == 1 && g.sample_bytes == 2)
-            fri_decode_kernel<1, uint16_t><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, t.chunk_mask, c, dc, p);
-        else
-            fri_decode_kernel<3, uint16_t><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, t.chunk_mask, c, dc, p);
+    const uint64_t total = (uint64_t)n_frames * g.n_groups;
+    const PersistShape ps = persist_shape(g, total);
+    if (ps.grid != 0 && work_counter != nullptr && total < 0xffff0000ull) {
+        WorkCounter *wc = static_cast<WorkCounter *>(work_counter);
+#define FRI_LAUNCH(CC, SS) fri_decode_persistent_kernel<CC, SS><<<ps.grid, ps.threads, ps.smem, stream>>>( \
+        g, qp, t.groups, t.tile_unit, t.chunk_list, t.chunk_mask, d_coefs, d_dc, px, (unsigned)total, wc)
+        if (g.channels == 1 && g.sample_bytes == 1) FRI_LAUNCH(1, uint8_t);
+        else if (g.channels == 3 && g.sample_bytes == 1) FRI_LAUNCH(3, uint8_t);
+        else if (g.channels == 1 && g.sample_bytes == 2) FRI_LAUNCH(1, uint16_t);
+        else FRI_LAUNCH(3, uint16_t);
+#undef FRI_LAUNCH
         if (launches) ++*launches;
+    } else {
+        const size_t smem = kernel_smem_bytes(g);
+        for (uint32_t f0 = 0; f0 < n_frames; f0 += 65535u) {
+            const uint32_t nf = n_frames - f0 < 65535u ? n_frames - f0 : 65535u;
+            const dim3 grid((unsigned)g.n_groups, nf);
+            uint8_t *p = px + (int64_t)f0 * g.frame_bytes;
+            const int32_t *c = d_coefs + (int64_t)f0 * g.coefs_per_frame;
+            int32_t *dc = d_dc ? d_dc + (((int64_t)f0 * g.n_fractals * g.channels) << g.sub_bits) : nullptr;
+#define FRI_LAUNCH(CC, SS) fri_decode_kernel<CC, SS><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, t.chunk_mask, c, dc, p)
+            if (g.channels == 1 && g.sample_bytes == 1) FRI_LAUNCH(1, uint8_t);
+            else if (g.channels == 3 && g.sample_bytes == 1) FRI_LAUNCH(3, uint8_t);
+            else if (g.channels == 1 && g.sample_bytes == 2) FRI_LAUNCH(1, uint16_t);
+            else FRI_LAUNCH(3, uint16_t);
+#undef FRI_LAUNCH
+            if (launches) ++*launches;
+        }
     }
     return cudaGetLastError();
 }
