@@ -42,7 +42,6 @@ int cuda_fail(cudaError_t e, const char *what)
     } while (0)
 
 constexpr int kSlots = 3;  // frames in flight in the host-buffer entry points
-constexpr uint32_t kCounters = 256;  // work counters handed to persistent launches round robin
 
 struct Slot {
     cudaStream_t stream = nullptr;
@@ -63,16 +62,9 @@ struct fri_plan {
     int32_t *d_dc_shared = nullptr;  // low-pass scratch for the *_device entry points (depth > 9)
     size_t d_dc_frames = 0;
     uint32_t last_launches = 0;
-    void *d_counters = nullptr;  // kCounters x 8 bytes, zeroed; one per launch in flight (round robin)
-    uint32_t counter_seq = 0;
 };
 
 namespace {
-
-void *next_counter(fri_plan *p)
-{
-    return static_cast<char *>(p->d_counters) + 8 * (p->counter_seq++ % kCounters);
-}
 
 std::once_flag g_cfg_once[16];
 cudaError_t g_cfg_err[16];
@@ -189,8 +181,6 @@ int fri_plan_create(fri_plan **out, int device, uint32_t width, uint32_t height,
         if (e == cudaSuccess && pl.geo.sub_bits > 0)
             e = upload(&p->d_tile_unit, pl.tile_unit.data(), pl.tile_unit.size() * sizeof(uint32_t));
         if (e == cudaSuccess) e = upload(&p->d_chunk_mask, pl.chunk_mask.data(), pl.chunk_mask.size() * sizeof(uint16_t));
-        if (e == cudaSuccess) e = cudaMalloc(&p->d_counters, kCounters * 8);
-        if (e == cudaSuccess) e = cudaMemset(p->d_counters, 0, kCounters * 8);
         if (e == cudaSuccess) e = upload(&p->d_chunk_list, pl.chunk_list.data(), pl.chunk_list.size() * sizeof(uint32_t));
         if (e != cudaSuccess) {
             fri_plan_destroy(p);
@@ -220,7 +210,6 @@ void fri_plan_destroy(fri_plan *p)
         if (p->d_tile_unit) cudaFree(p->d_tile_unit);
         if (p->d_chunk_mask) cudaFree(p->d_chunk_mask);
         if (p->d_chunk_list) cudaFree(p->d_chunk_list);
-        if (p->d_counters) cudaFree(p->d_counters);
     }
     delete p;
 }
@@ -278,7 +267,7 @@ int fri_encode_tq_device(const fri_plan *cp, const void *d_pixels, uint32_t n_fr
     QuantParams qp;
     make_quant_params(qp, q, 0);
     p->last_launches = 0;
-    FRI_CUDA(launch_encode(g, p->tables, qp, d_pixels, n_frames, d_coefs, p->d_dc_shared, next_counter(p), static_cast<cudaStream_t>(stream),
+    FRI_CUDA(launch_encode(g, p->tables, qp, d_pixels, n_frames, d_coefs, p->d_dc_shared, static_cast<cudaStream_t>(stream),
                            &p->last_launches));
     return FRI_OK;
 }
@@ -306,7 +295,7 @@ int fri_decode_tq_device(const fri_plan *cp, const int32_t *d_coefs, uint32_t n_
     // the retained fractals do not cover every pixel.
     if (p->plan.pixels_covered != (uint64_t)g.width * g.height)
         FRI_CUDA(cudaMemsetAsync(d_pixels, 0, (size_t)g.frame_bytes * n_frames, st));
-    FRI_CUDA(launch_decode(g, p->tables, qp, d_coefs, n_frames, d_pixels, p->d_dc_shared, next_counter(p), st, &p->last_launches));
+    FRI_CUDA(launch_decode(g, p->tables, qp, d_coefs, n_frames, d_pixels, p->d_dc_shared, st, &p->last_launches));
     return FRI_OK;
 }
 
@@ -327,7 +316,7 @@ int fri_encode_tq(fri_plan *p, const void *pixels, uint32_t n_frames, const int3
         Slot &s = p->slots[f % kSlots];
         FRI_CUDA(cudaMemcpyAsync(s.d_pixels, static_cast<const uint8_t *>(pixels) + (size_t)f * g.frame_bytes,
                                  (size_t)g.frame_bytes, cudaMemcpyHostToDevice, s.stream));
-        FRI_CUDA(launch_encode(g, p->tables, qp, s.d_pixels, 1, s.d_coefs, s.d_dc, next_counter(p), s.stream, &p->last_launches));
+        FRI_CUDA(launch_encode(g, p->tables, qp, s.d_pixels, 1, s.d_coefs, s.d_dc, s.stream, &p->last_launches));
         FRI_CUDA(cudaMemcpyAsync(coefs + (size_t)f * g.coefs_per_frame, s.d_coefs, coef_bytes, cudaMemcpyDeviceToHost,
                                  s.stream));
     }
@@ -356,7 +345,7 @@ int fri_decode_tq(fri_plan *p, const int32_t *coefs, uint32_t n_frames, const in
         FRI_CUDA(cudaMemcpyAsync(s.d_coefs, coefs + (size_t)f * g.coefs_per_frame, coef_bytes, cudaMemcpyHostToDevice,
                                  s.stream));
         if (need_zero) FRI_CUDA(cudaMemsetAsync(s.d_pixels, 0, (size_t)g.frame_bytes, s.stream));
-        FRI_CUDA(launch_decode(g, p->tables, qp, s.d_coefs, 1, s.d_pixels, s.d_dc, next_counter(p), s.stream, &p->last_launches));
+        FRI_CUDA(launch_decode(g, p->tables, qp, s.d_coefs, 1, s.d_pixels, s.d_dc, s.stream, &p->last_launches));
         FRI_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(pixels) + (size_t)f * g.frame_bytes, s.d_pixels,
                                  (size_t)g.frame_bytes, cudaMemcpyDeviceToHost, s.stream));
     }

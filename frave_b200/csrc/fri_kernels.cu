@@ -196,11 +196,13 @@ struct TaskAddr {
     bool last;       // the base tile is the last one of its fractal
 };
 
-template <int C>
+// DEEP == false instantiates the depth-9 (reference) case with sub_bits == 0 folded in at compile
+// time: node == 1, every tile is "last", no tile_unit / low-pass scratch traffic.
+template <int C, bool DEEP>
 __device__ __forceinline__ TaskAddr task_addr(const Geometry &g, const uint32_t *tile_unit, int frame, int tile, int ch)
 {
     TaskAddr a;
-    if (g.sub_bits == 0) {
+    if (!DEEP) {
         a.block = (((int64_t)frame * g.n_fractals + tile) * C + ch) << kBaseDepth;
         a.node = 1;
         a.dc = 0;
@@ -297,7 +299,7 @@ __device__ __forceinline__ void stage_group(const Geometry &g, const GroupDesc &
 //   phase 2 (all channels at once): lane group lane / 8 owns a channel; lane j of the group
 //                          folds s6[8j .. 8j+7] through levels 5..3 in registers and levels 2..0
 //                          with three shuffles inside the group.
-template <int C, typename S>
+template <int C, typename S, bool DEEP>
 __device__ __forceinline__ void encode_tiles(const Geometry &g, const QuantParams &qp, const GroupDesc &gd, const RegionView &rv,
                                              const uint32_t *__restrict__ tile_unit, int frame, const uint8_t *region,
                                              int32_t *scratch, int32_t *__restrict__ coefs, int32_t *__restrict__ dc_out)
@@ -308,14 +310,15 @@ __device__ __forceinline__ void encode_tiles(const Geometry &g, const QuantParam
     const int n_present = __popc(gd.tile_mask);
     const uint8_t *lane_base = region + rv.phi0 + lane_anchor_bytes(lane, g.pitch, PB);
     const int half = kHalfB.y * g.pitch + kHalfB.x * PB;
-    const int top = g.sub_bits;  // fractal level of a base tile's root
+    const int sub_bits = DEEP ? g.sub_bits : 0, depth = DEEP ? g.depth : kBaseDepth;
+    const int top = sub_bits;  // fractal level of a base tile's root
     const bool sparse_group = (gd.tile_mask & (gd.tile_mask + 1u)) != 0;
     const int grp = min(lane >> 3, C - 1), j8 = lane & 7;  // phase 2 roles
     const bool grp_live = (lane >> 3) < C;
     for (int e = warp; e < n_present; e += n_warps) {
         const int slot = sparse_group ? (int)__fns(gd.tile_mask, 0, e + 1) : e;
         const uint8_t *t0 = lane_base + g.tile_off[slot];
-        const TaskAddr ta = task_addr<C>(g, tile_unit, frame, gd.tile_base + e, 0);
+        const TaskAddr ta = task_addr<C, DEEP>(g, tile_unit, frame, gd.tile_base + e, 0);
         const bool lastB = ta.last && lane == 31;  // this lane holds the last node of levels 8..6
 
 #pragma unroll
@@ -376,7 +379,7 @@ __device__ __forceinline__ void encode_tiles(const Geometry &g, const QuantParam
                     b6 = quant_layer(qp, r6, top + 7);
                 }
             }
-            int32_t *out = coefs + ta.block + ((int64_t)ch << g.depth);
+            int32_t *out = coefs + ta.block + ((int64_t)ch << depth);
             int32_t *o8 = out + ((size_t)ta.node << 8), *o7 = out + ((size_t)ta.node << 7), *o6 = out + ((size_t)ta.node << 6);
             __stcs(reinterpret_cast<int4 *>(o8) + lane, make_int4(a8[0], a8[1], a8[2], a8[3]));
             __stcs(reinterpret_cast<int4 *>(o8 + 128) + lane, make_int4(b8[0], b8[1], b8[2], b8[3]));
@@ -411,7 +414,7 @@ __device__ __forceinline__ void encode_tiles(const Geometry &g, const QuantParam
                 d3 = quant_layer(qp, d3, top + (lastG ? 4 : 3));
                 d2 = quant_layer(qp, d2, top + ((ta.last && j8 == 6) ? 3 : 2));
                 d1 = quant_layer(qp, d1, top + ((ta.last && j8 == 4) ? 2 : 1));
-                if (g.sub_bits == 0) {
+                if (sub_bits == 0) {
                     d0 = quant_layer(qp, d0, 1);  // position 1 is the last node of level 0
                     s0 = quant_layer(qp, s0, 0);  // position 0: the low-pass root (wavelet_transform.rs:221)
                 } else {
@@ -419,7 +422,7 @@ __device__ __forceinline__ void encode_tiles(const Geometry &g, const QuantParam
                 }
             }
             if (grp_live) {
-                int32_t *out = coefs + ta.block + ((int64_t)grp << g.depth);
+                int32_t *out = coefs + ta.block + ((int64_t)grp << depth);
                 const size_t node = ta.node;
                 __stcs(reinterpret_cast<int4 *>(out + (node << 5)) + j8, make_int4(d5[0], d5[1], d5[2], d5[3]));
                 __stcs(reinterpret_cast<int2 *>(out + (node << 4)) + j8, make_int2(d4[0], d4[1]));
@@ -428,8 +431,8 @@ __device__ __forceinline__ void encode_tiles(const Geometry &g, const QuantParam
                 if ((j8 & 3) == 0) __stcs(out + (node << 1) + (j8 >> 2), d1);
                 if (j8 == 0) {
                     __stcs(out + node, d0);
-                    if (g.sub_bits == 0) __stcs(out, s0);
-                    else dc_out[ta.dc + ((int64_t)grp << g.sub_bits)] = s0;
+                    if (sub_bits == 0) __stcs(out, s0);
+                    else dc_out[ta.dc + ((int64_t)grp << sub_bits)] = s0;
                 }
             }
         }
@@ -439,11 +442,11 @@ __device__ __forceinline__ void encode_tiles(const Geometry &g, const QuantParam
 
 // Pulls a group's coefficients towards L2: at depth 9 the blocks of a group's tiles are adjacent
 // (plan order is group-major), n_present * C * 2 KB in one run.
-template <int C>
+template <int C, bool DEEP>
 __device__ __forceinline__ void prefetch_group_coefs(const Geometry &g, const GroupDesc &gd, int frame,
                                                      const int32_t *__restrict__ coefs)
 {
-    if (g.sub_bits != 0) return;
+    if (DEEP) return;
     const char *first = reinterpret_cast<const char *>(coefs + ((((int64_t)frame * g.n_fractals + gd.tile_base) * C) << kBaseDepth));
     const int lines = __popc(gd.tile_mask) * C * 16;  // 128-byte lines
     for (int i = threadIdx.x; i < lines; i += blockDim.x)
@@ -454,7 +457,7 @@ __device__ __forceinline__ void prefetch_group_coefs(const Geometry &g, const Gr
 // image of encode_tiles: lane group lane / 8 first unfolds levels 0..5 of its channel (lane j
 // ends with the eight level-6 low-pass values 8j .. 8j+7) into the warp's scratch, then every
 // lane unfolds its two depth-3 subtrees per channel and scatters the 16 clamped leaves.
-template <int C, typename S>
+template <int C, typename S, bool DEEP>
 __device__ __forceinline__ void decode_tiles(const Geometry &g, const QuantParams &qp, const GroupDesc &gd, const RegionView &rv,
                                              const uint32_t *__restrict__ tile_unit, int frame, uint8_t *region,
                                              int32_t *scratch, const int32_t *__restrict__ coefs,
@@ -466,44 +469,27 @@ __device__ __forceinline__ void decode_tiles(const Geometry &g, const QuantParam
     const int n_present = __popc(gd.tile_mask);
     uint8_t *lane_base = region + rv.phi0 + lane_anchor_bytes(lane, g.pitch, PB);
     const int half = kHalfB.y * g.pitch + kHalfB.x * PB;
-    const int top = g.sub_bits;
+    const int sub_bits = DEEP ? g.sub_bits : 0, depth = DEEP ? g.depth : kBaseDepth;
+    const int top = sub_bits;
     const bool sparse_group = (gd.tile_mask & (gd.tile_mask + 1u)) != 0;
     const int grp = min(lane >> 3, C - 1), j8 = lane & 7;
     const bool grp_live = (lane >> 3) < C;
     for (int e = warp; e < n_present; e += n_warps) {
         const int slot = sparse_group ? (int)__fns(gd.tile_mask, 0, e + 1) : e;
-        const TaskAddr ta = task_addr<C>(g, tile_unit, frame, gd.tile_base + e, 0);
+        const TaskAddr ta = task_addr<C, DEEP>(g, tile_unit, frame, gd.tile_base + e, 0);
         const bool lastB = ta.last && lane == 31;
         const size_t node = ta.node;
 
-        // channel 0's coefficient runs are requested before anything is waited for; channel
-        // c + 1's while channel c is unfolded (register double buffer)
-        int4 n_a8, n_b8;
-        int2 n_a7, n_b7;
-        int n_a6, n_b6;
-#define FRI_LOAD_CH(ch)                                                                          \
-        {                                                                                        \
-            const int32_t *in_ = coefs + ta.block + ((int64_t)(ch) << g.depth);                  \
-            const int32_t *i8 = in_ + (node << 8), *i7 = in_ + (node << 7), *i6 = in_ + (node << 6); \
-            n_a8 = __ldcs(reinterpret_cast<const int4 *>(i8) + lane);                            \
-            n_b8 = __ldcs(reinterpret_cast<const int4 *>(i8 + 128) + lane);                      \
-            n_a7 = __ldcs(reinterpret_cast<const int2 *>(i7) + lane);                            \
-            n_b7 = __ldcs(reinterpret_cast<const int2 *>(i7 + 64) + lane);                       \
-            n_a6 = __ldcs(i6 + lane);                                                            \
-            n_b6 = __ldcs(i6 + 32 + lane);                                                       \
-        }
-        FRI_LOAD_CH(0)
-
         // ---- levels 0..5 of all channels, 8 lanes per channel
         {
-            const int32_t *in = coefs + ta.block + ((int64_t)grp << g.depth);
+            const int32_t *in = coefs + ta.block + ((int64_t)grp << depth);
             int4 d5 = __ldcs(reinterpret_cast<const int4 *>(in + (node << 5)) + j8);
             int2 d4 = __ldcs(reinterpret_cast<const int2 *>(in + (node << 4)) + j8);
             int d3 = __ldcs(in + (node << 3) + j8);
             int d2 = __ldcs(in + (node << 2) + (j8 >> 1));
             int d1 = __ldcs(in + (node << 1) + (j8 >> 2));
             int d0 = __ldcs(in + node);
-            int s0 = g.sub_bits == 0 ? __ldcs(in) : dc_in[ta.dc + ((int64_t)grp << g.sub_bits)];
+            int s0 = sub_bits == 0 ? __ldcs(in) : dc_in[ta.dc + ((int64_t)grp << sub_bits)];
             if ((qp.active >> top) & 0x7fu) {
                 const bool lastG = ta.last && j8 == 7;
                 d5.x = dequant_layer(qp, d5.x, top + 5); d5.y = dequant_layer(qp, d5.y, top + 5);
@@ -512,7 +498,7 @@ __device__ __forceinline__ void decode_tiles(const Geometry &g, const QuantParam
                 d3 = dequant_layer(qp, d3, top + (lastG ? 4 : 3));
                 d2 = dequant_layer(qp, d2, top + ((ta.last && (j8 >> 1) == 3) ? 3 : 2));
                 d1 = dequant_layer(qp, d1, top + ((ta.last && (j8 >> 2) == 1) ? 2 : 1));
-                if (g.sub_bits == 0) {
+                if (sub_bits == 0) {
                     d0 = dequant_layer(qp, d0, 1);
                     s0 = dequant_layer(qp, s0, 0);
                 } else {
@@ -543,10 +529,14 @@ __device__ __forceinline__ void decode_tiles(const Geometry &g, const QuantParam
         uint8_t *t0 = lane_base + g.tile_off[slot];
 #pragma unroll
         for (int ch = 0; ch < C; ++ch) {
-            int4 a8 = n_a8, b8 = n_b8;
-            int2 a7 = n_a7, b7 = n_b7;
-            int a6 = n_a6, b6 = n_b6;
-            if (ch + 1 < C) FRI_LOAD_CH(ch + 1)
+            const int32_t *in = coefs + ta.block + ((int64_t)ch << depth);
+            const int32_t *i8 = in + (node << 8), *i7 = in + (node << 7), *i6 = in + (node << 6);
+            int4 a8 = __ldcs(reinterpret_cast<const int4 *>(i8) + lane);
+            int4 b8 = __ldcs(reinterpret_cast<const int4 *>(i8 + 128) + lane);
+            int2 a7 = __ldcs(reinterpret_cast<const int2 *>(i7) + lane);
+            int2 b7 = __ldcs(reinterpret_cast<const int2 *>(i7 + 64) + lane);
+            int a6 = __ldcs(i6 + lane);
+            int b6 = __ldcs(i6 + 32 + lane);
             const int sA = scratch[ch * kScratchInts + lane], sB = scratch[ch * kScratchInts + 32 + lane];
 
             if ((qp.active >> (top + 6)) & 0xfu) {
@@ -607,7 +597,6 @@ __device__ __forceinline__ void decode_tiles(const Geometry &g, const QuantParam
             FRI_ST(p1 + half, 1, w[6]);  FRI_ST(p2 + half, 1, w[7]);
 #undef FRI_ST
         }
-#undef FRI_LOAD_CH
         __syncwarp();
     }
 }
@@ -621,31 +610,55 @@ __device__ __forceinline__ void zero_region(const Geometry &g, uint8_t *region)
     for (int i = threadIdx.x; i < n16; i += blockDim.x) reinterpret_cast<int4 *>(region)[i] = make_int4(0, 0, 0, 0);
 }
 
-// Writes a decoded region out in 16-byte chunks aligned in global memory, one chunk per thread
+// Write-out of a decoded region in 16-byte chunks aligned in global memory, one chunk per thread
 // and iteration from the plan's chunk list.  Only bytes of pixels that belong to the group's
 // tiles (chunk masks) and lie inside the image (set_pixel's bounds check, images.rs:104) are
 // written: fully owned chunks as one 128-bit store, the chunks along the group's fractal outline
-// byte-masked.
+// byte-masked.  The first kWriteAhead list entries of every thread are fetched by
+// write_out_preload() *before* the CTA barrier that completes the region, so their latency hides
+// behind the barrier wait.
+constexpr int kWriteAhead = 8;
+
+struct WriteAhead {
+    uint32_t e[kWriteAhead];
+};
+
+__device__ __forceinline__ WriteAhead write_out_preload(const Geometry &g, const RegionView &rv,
+                                                        const uint32_t *__restrict__ chunk_list)
+{
+    WriteAhead w;
+    const uint32_t *cl = chunk_list + (size_t)rv.phi0 * g.list_cap;
+    const int n_full = g.list_full[rv.phi0];
+#pragma unroll
+    for (int u = 0; u < kWriteAhead; ++u) {
+        const int k = threadIdx.x + u * blockDim.x;
+        w.e[u] = (rv.interior && k < n_full) ? __ldg(cl + k) : kNoChunk;
+    }
+    return w;
+}
+
 __device__ __forceinline__ void write_out_group(const Geometry &g, const GroupDesc &gd, const RegionView &rv,
                                                 const uint32_t *__restrict__ chunk_list,
-                                                const uint16_t *__restrict__ chunk_mask, const uint8_t *region)
+                                                const uint16_t *__restrict__ chunk_mask, const uint8_t *region,
+                                                const WriteAhead &ahead)
 {
     const int n_threads = blockDim.x;
     const uint32_t *cl = chunk_list + (size_t)rv.phi0 * g.list_cap;
     const uint16_t *cmk = chunk_mask + (size_t)rv.phi0 * g.list_cap;
     const int n_full = g.list_full[rv.phi0], n_all = g.list_all[rv.phi0];
     if (rv.interior) {
-        for (int k0 = threadIdx.x; k0 < n_full; k0 += kListUnroll * n_threads) {
-            uint32_t e[kListUnroll];
 #pragma unroll
-            for (int u = 0; u < kListUnroll; ++u) e[u] = k0 + u * n_threads < n_full ? __ldg(cl + k0 + u * n_threads) : kNoChunk;
-#pragma unroll
-            for (int u = 0; u < kListUnroll; ++u)
-                if (e[u] != kNoChunk) {
-                    const int r = (int)(e[u] >> 16), s = (int)(e[u] & 0xffffu) << 4;
-                    *reinterpret_cast<int4 *>(reinterpret_cast<uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s) =
-                        *reinterpret_cast<const int4 *>(region + s);
-                }
+        for (int u = 0; u < kWriteAhead; ++u)
+            if (ahead.e[u] != kNoChunk) {
+                const int r = (int)(ahead.e[u] >> 16), s = (int)(ahead.e[u] & 0xffffu) << 4;
+                *reinterpret_cast<int4 *>(reinterpret_cast<uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s) =
+                    *reinterpret_cast<const int4 *>(region + s);
+            }
+        for (int k = threadIdx.x + kWriteAhead * n_threads; k < n_full; k += n_threads) {
+            const uint32_t e = __ldg(cl + k);
+            const int r = (int)(e >> 16), s = (int)(e & 0xffffu) << 4;
+            *reinterpret_cast<int4 *>(reinterpret_cast<uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s) =
+                *reinterpret_cast<const int4 *>(region + s);
         }
         for (int k = n_full + threadIdx.x; k < n_all; k += n_threads) {
             const uint32_t e = __ldg(cl + k);
@@ -670,7 +683,7 @@ __device__ __forceinline__ void write_out_group(const Geometry &g, const GroupDe
 __device__ __forceinline__ size_t region_bytes(const Geometry &g) { return ((size_t)g.region_h * g.pitch + 15) & ~(size_t)15; }
 
 // ------------------------------------------------------------------------------------------
-// one-group-per-CTA kernels (small launches: fewer groups than persistent CTAs)
+// kernels: one CTA per (group, frame)
 // ------------------------------------------------------------------------------------------
 #ifndef FRI_ENC_MINB
 #define FRI_ENC_MINB 4
@@ -678,7 +691,7 @@ __device__ __forceinline__ size_t region_bytes(const Geometry &g) { return ((siz
 #ifndef FRI_DEC_MINB
 #define FRI_DEC_MINB 4
 #endif
-template <int C, typename S>
+template <int C, typename S, bool DEEP>
 __global__ void __launch_bounds__(kThreads, FRI_ENC_MINB)
 fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ QuantParams qp,
                   const GroupDesc *__restrict__ groups, const uint32_t *__restrict__ tile_unit,
@@ -694,10 +707,10 @@ fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
     stage_group(g, gd, rv, chunk_list, region);
     cp_async_wait_all();
     __syncthreads();
-    encode_tiles<C, S>(g, qp, gd, rv, tile_unit, frame, region, scratch, coefs, dc_out);
+    encode_tiles<C, S, DEEP>(g, qp, gd, rv, tile_unit, frame, region, scratch, coefs, dc_out);
 }
 
-template <int C, typename S>
+template <int C, typename S, bool DEEP>
 __global__ void __launch_bounds__(kThreads, FRI_DEC_MINB)
 fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ QuantParams qp,
                   const GroupDesc *__restrict__ groups, const uint32_t *__restrict__ tile_unit,
@@ -710,135 +723,15 @@ fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
     const GroupDesc gd = groups[blockIdx.x];
     const int frame = blockIdx.y;
     const RegionView rv = region_view<C * (int)sizeof(S)>(g, gd, pixels + (int64_t)frame * g.frame_bytes);
-    prefetch_group_coefs<C>(g, gd, frame, coefs);
+    prefetch_group_coefs<C, DEEP>(g, gd, frame, coefs);
     if (__popc(gd.tile_mask) != g.group_a * g.group_b) {
         zero_region(g, region);
         __syncthreads();
     }
-    decode_tiles<C, S>(g, qp, gd, rv, tile_unit, frame, region, scratch, coefs, dc_in);
+    decode_tiles<C, S, DEEP>(g, qp, gd, rv, tile_unit, frame, region, scratch, coefs, dc_in);
+    const WriteAhead ahead = write_out_preload(g, rv, chunk_list);
     __syncthreads();
-    write_out_group(g, gd, rv, chunk_list, chunk_mask, region);
-}
-
-// ------------------------------------------------------------------------------------------
-// persistent kernels: a fixed grid of CTAs pulls (frame, group) work items from a counter
-// ------------------------------------------------------------------------------------------
-//
-// The staged region is double-buffered.  Encode: the cp.async copies of the next group's pixels
-// are in flight while the warps transform the current group, one CTA barrier per group.  Decode:
-// the next group's coefficients are prefetched towards L2 while the current group is unfolded,
-// and warps that finish their share of a group's write-out start on the next group's tiles
-// (other buffer) without waiting for the rest — again one barrier per group.
-struct WorkCounter {
-    unsigned int next;  // next unclaimed work item
-    unsigned int done;  // CTAs that have run out of work (the last one resets both)
-};
-
-__device__ __forceinline__ void finish_work(WorkCounter *wc)
-{
-    if (threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd(&wc->done, 1u) == gridDim.x - 1) {
-            wc->next = 0;
-            wc->done = 0;
-        }
-    }
-}
-
-template <int C, typename S>
-__global__ void __launch_bounds__(kPersistThreads, 2)
-fri_encode_persistent_kernel(const __grid_constant__ Geometry g, const __grid_constant__ QuantParams qp,
-                             const GroupDesc *__restrict__ groups, const uint32_t *__restrict__ tile_unit,
-                             const uint32_t *__restrict__ chunk_list, const uint8_t *__restrict__ pixels,
-                             int32_t *__restrict__ coefs, int32_t *__restrict__ dc_out, unsigned int total,
-                             WorkCounter *wc)
-{
-    constexpr int PB = C * (int)sizeof(S);
-    extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ unsigned int s_work[2];
-    const size_t rb = region_bytes(g);
-    int32_t *scratch = reinterpret_cast<int32_t *>(smem + 2 * rb) + (threadIdx.x >> 5) * (C * kScratchInts);
-
-    if (threadIdx.x == 0) s_work[0] = atomicAdd(&wc->next, 1u);
-    __syncthreads();
-    unsigned int cur = s_work[0];
-    GroupDesc gd{};
-    RegionView rv{};
-    int frame = 0;
-    if (cur < total) {
-        frame = (int)(cur / (unsigned)g.n_groups);
-        gd = groups[cur - (unsigned)frame * (unsigned)g.n_groups];
-        rv = region_view<PB>(g, gd, pixels + (int64_t)frame * g.frame_bytes);
-        stage_group(g, gd, rv, chunk_list, smem);
-    }
-    for (int it = 0; cur < total; ++it) {
-        if (threadIdx.x == 0) s_work[(it + 1) & 1] = atomicAdd(&wc->next, 1u);
-        cp_async_wait_all();  // this thread's copies of the current group have landed
-        __syncthreads();      // ... everybody's; and everybody is done with the other buffer
-        const unsigned int nxt = s_work[(it + 1) & 1];
-        GroupDesc ngd{};
-        RegionView nrv{};
-        int nframe = 0;
-        if (nxt < total) {
-            nframe = (int)(nxt / (unsigned)g.n_groups);
-            ngd = groups[nxt - (unsigned)nframe * (unsigned)g.n_groups];
-            nrv = region_view<PB>(g, ngd, pixels + (int64_t)nframe * g.frame_bytes);
-            stage_group(g, ngd, nrv, chunk_list, smem + ((it + 1) & 1) * rb);
-        }
-        encode_tiles<C, S>(g, qp, gd, rv, tile_unit, frame, smem + (it & 1) * rb, scratch, coefs, dc_out);
-        cur = nxt; gd = ngd; rv = nrv; frame = nframe;
-    }
-    finish_work(wc);
-}
-
-template <int C, typename S>
-__global__ void __launch_bounds__(kPersistThreads, 2)
-fri_decode_persistent_kernel(const __grid_constant__ Geometry g, const __grid_constant__ QuantParams qp,
-                             const GroupDesc *__restrict__ groups, const uint32_t *__restrict__ tile_unit,
-                             const uint32_t *__restrict__ chunk_list, const uint16_t *__restrict__ chunk_mask,
-                             const int32_t *__restrict__ coefs, const int32_t *__restrict__ dc_in,
-                             uint8_t *__restrict__ pixels, unsigned int total, WorkCounter *wc)
-{
-    constexpr int PB = C * (int)sizeof(S);
-    extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ unsigned int s_work[3];
-    const size_t rb = region_bytes(g);
-    int32_t *scratch = reinterpret_cast<int32_t *>(smem + 2 * rb) + (threadIdx.x >> 5) * (C * kScratchInts);
-
-    // work items are claimed two ahead, so that the coefficients of the next group can be
-    // prefetched towards L2 a whole group before they are used
-    if (threadIdx.x == 0) {
-        s_work[0] = atomicAdd(&wc->next, 1u);
-        s_work[1] = atomicAdd(&wc->next, 1u);
-    }
-    __syncthreads();
-    unsigned int cur = s_work[0], nxt = s_work[1];
-    if (cur < total) {
-        const int f = (int)(cur / (unsigned)g.n_groups);
-        prefetch_group_coefs<C>(g, groups[cur - (unsigned)f * (unsigned)g.n_groups], f, coefs);
-    }
-    for (int it = 0; cur < total; ++it) {
-        const int frame = (int)(cur / (unsigned)g.n_groups);
-        const GroupDesc gd = groups[cur - (unsigned)frame * (unsigned)g.n_groups];
-        const RegionView rv = region_view<PB>(g, gd, pixels + (int64_t)frame * g.frame_bytes);
-        uint8_t *region = smem + (it & 1) * rb;
-        if (nxt < total) {
-            const int nf = (int)(nxt / (unsigned)g.n_groups);
-            prefetch_group_coefs<C>(g, groups[nxt - (unsigned)nf * (unsigned)g.n_groups], nf, coefs);
-        }
-        if (threadIdx.x == 0) s_work[(it + 2) % 3] = atomicAdd(&wc->next, 1u);
-        if (__popc(gd.tile_mask) != g.group_a * g.group_b) {  // rare (image border): an extra barrier
-            zero_region(g, region);
-            __syncthreads();
-        }
-        decode_tiles<C, S>(g, qp, gd, rv, tile_unit, frame, region, scratch, coefs, dc_in);
-        __syncthreads();  // the group's pixels are complete; s_work[(it+2)%3] is visible
-        const unsigned int nxt2 = s_work[(it + 2) % 3];
-        write_out_group(g, gd, rv, chunk_list, chunk_mask, region);
-        cur = nxt;
-        nxt = nxt2;
-    }
-    finish_work(wc);
+    write_out_group(g, gd, rv, chunk_list, chunk_mask, region, ahead);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -914,15 +807,17 @@ cudaError_t configure_kernels()
 {
     cudaError_t e;
 #define FRI_CFG(k) if ((e = set_smem(k, kMaxSmem)) != cudaSuccess) return e
-#define FRI_CFG4(name)              \
-    FRI_CFG((name<1, uint8_t>));    \
-    FRI_CFG((name<3, uint8_t>));    \
-    FRI_CFG((name<1, uint16_t>));   \
-    FRI_CFG((name<3, uint16_t>))
+#define FRI_CFG4(name)                     \
+    FRI_CFG((name<1, uint8_t, false>));    \
+    FRI_CFG((name<3, uint8_t, false>));    \
+    FRI_CFG((name<1, uint16_t, false>));   \
+    FRI_CFG((name<3, uint16_t, false>));   \
+    FRI_CFG((name<1, uint8_t, true>));     \
+    FRI_CFG((name<3, uint8_t, true>));     \
+    FRI_CFG((name<1, uint16_t, true>));    \
+    FRI_CFG((name<3, uint16_t, true>))
     FRI_CFG4(fri_encode_kernel);
     FRI_CFG4(fri_decode_kernel);
-    FRI_CFG4(fri_encode_persistent_kernel);
-    FRI_CFG4(fri_decode_persistent_kernel);
     FRI_CFG(fri_coarse_forward_kernel);
     FRI_CFG(fri_coarse_inverse_kernel);
 #undef FRI_CFG4
@@ -930,80 +825,32 @@ cudaError_t configure_kernels()
     return cudaSuccess;
 }
 
-namespace {
-
-int sm_count()
-{
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-    }
-    return sms;
-}
-
-// Persistent launch shape: threads per CTA, dynamic shared memory, grid size; grid == 0 means
-// "use the one-group-per-CTA kernel" (too few groups to fill the persistent CTAs twice over).
-struct PersistShape {
-    int threads;
-    size_t smem;
-    unsigned grid;
-};
-
-PersistShape persist_shape(const Geometry &g, uint64_t total)
-{
-    PersistShape p;
-    const int tiles = g.group_a * g.group_b;
-    p.threads = 32 * std::max(1, std::min(kPersistThreads / 32, tiles));
-    p.smem = 2 * ((((size_t)g.region_h * g.pitch) + 15) & ~(size_t)15) + (size_t)(p.threads / 32) * g.channels * kScratchInts * sizeof(int32_t);
-    const int per_sm = 2;
-    const uint64_t slots = (uint64_t)sm_count() * per_sm;
-    int mode = -1;  // tuning knob: FRI_PERSISTENT=0/1 forces the choice
-    if (const char *env = std::getenv("FRI_PERSISTENT")) mode = std::atoi(env);
-    const bool fits = p.smem * per_sm + 2048 <= kMaxSmem;
-    (void)total;
-    const bool use = mode > 0 && fits;  // opt-in: measured slower than one group per CTA
-    p.grid = use ? (unsigned)std::min<uint64_t>(total, slots) : 0u;
-    return p;
-}
-
-}  // namespace
-
 cudaError_t launch_encode(const Geometry &g, const DeviceTables &t, const QuantParams &qp, const void *d_pixels,
-                          uint32_t n_frames, int32_t *d_coefs, int32_t *d_dc, void *work_counter, cudaStream_t stream,
+                          uint32_t n_frames, int32_t *d_coefs, int32_t *d_dc, cudaStream_t stream,
                           uint32_t *launches)
 {
     if (n_frames == 0 || g.n_groups == 0) return cudaSuccess;
+    const size_t smem = kernel_smem_bytes(g);
     const uint8_t *px = static_cast<const uint8_t *>(d_pixels);
-    const uint64_t total = (uint64_t)n_frames * g.n_groups;
-    const PersistShape ps = persist_shape(g, total);
-    if (ps.grid != 0 && work_counter != nullptr && total < 0xffff0000ull) {
-        WorkCounter *wc = static_cast<WorkCounter *>(work_counter);
-#define FRI_LAUNCH(CC, SS) fri_encode_persistent_kernel<CC, SS><<<ps.grid, ps.threads, ps.smem, stream>>>( \
-        g, qp, t.groups, t.tile_unit, t.chunk_list, px, d_coefs, d_dc, (unsigned)total, wc)
+    for (uint32_t f0 = 0; f0 < n_frames; f0 += 65535u) {  // gridDim.y limit
+        const uint32_t nf = n_frames - f0 < 65535u ? n_frames - f0 : 65535u;
+        const dim3 grid((unsigned)g.n_groups, nf);
+        const uint8_t *p = px + (int64_t)f0 * g.frame_bytes;
+        int32_t *c = d_coefs + (int64_t)f0 * g.coefs_per_frame;
+        int32_t *dc = d_dc ? d_dc + (((int64_t)f0 * g.n_fractals * g.channels) << g.sub_bits) : nullptr;
+#define FRI_LAUNCH(CC, SS)                                                                                                        \
+        do {                                                                                                                      \
+            if (g.sub_bits == 0)                                                                                                  \
+                fri_encode_kernel<CC, SS, false><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, p, c, dc); \
+            else                                                                                                                  \
+                fri_encode_kernel<CC, SS, true><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, p, c, dc);  \
+        } while (0)
         if (g.channels == 1 && g.sample_bytes == 1) FRI_LAUNCH(1, uint8_t);
         else if (g.channels == 3 && g.sample_bytes == 1) FRI_LAUNCH(3, uint8_t);
         else if (g.channels == 1 && g.sample_bytes == 2) FRI_LAUNCH(1, uint16_t);
         else FRI_LAUNCH(3, uint16_t);
 #undef FRI_LAUNCH
         if (launches) ++*launches;
-    } else {
-        const size_t smem = kernel_smem_bytes(g);
-        for (uint32_t f0 = 0; f0 < n_frames; f0 += 65535u) {  // gridDim.y limit
-            const uint32_t nf = n_frames - f0 < 65535u ? n_frames - f0 : 65535u;
-            const dim3 grid((unsigned)g.n_groups, nf);
-            const uint8_t *p = px + (int64_t)f0 * g.frame_bytes;
-            int32_t *c = d_coefs + (int64_t)f0 * g.coefs_per_frame;
-            int32_t *dc = d_dc ? d_dc + (((int64_t)f0 * g.n_fractals * g.channels) << g.sub_bits) : nullptr;
-#define FRI_LAUNCH(CC, SS) fri_encode_kernel<CC, SS><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, p, c, dc)
-            if (g.channels == 1 && g.sample_bytes == 1) FRI_LAUNCH(1, uint8_t);
-            else if (g.channels == 3 && g.sample_bytes == 1) FRI_LAUNCH(3, uint8_t);
-            else if (g.channels == 1 && g.sample_bytes == 2) FRI_LAUNCH(1, uint16_t);
-            else FRI_LAUNCH(3, uint16_t);
-#undef FRI_LAUNCH
-            if (launches) ++*launches;
-        }
     }
     if (g.sub_bits > 0) {
         const unsigned blocks = (unsigned)((int64_t)n_frames * g.n_fractals * g.channels);
@@ -1015,10 +862,11 @@ cudaError_t launch_encode(const Geometry &g, const DeviceTables &t, const QuantP
 }
 
 cudaError_t launch_decode(const Geometry &g, const DeviceTables &t, const QuantParams &qp, const int32_t *d_coefs,
-                          uint32_t n_frames, void *d_pixels, int32_t *d_dc, void *work_counter, cudaStream_t stream,
+                          uint32_t n_frames, void *d_pixels, int32_t *d_dc, cudaStream_t stream,
                           uint32_t *launches)
 {
     if (n_frames == 0 || g.n_groups == 0) return cudaSuccess;
+    const size_t smem = kernel_smem_bytes(g);
     if (g.sub_bits > 0) {
         const unsigned blocks = (unsigned)((int64_t)n_frames * g.n_fractals * g.channels);
         const size_t cs = ((size_t)3 << g.sub_bits) / 2 * sizeof(int32_t) + 16;
@@ -1026,34 +874,25 @@ cudaError_t launch_decode(const Geometry &g, const DeviceTables &t, const QuantP
         if (launches) ++*launches;
     }
     uint8_t *px = static_cast<uint8_t *>(d_pixels);
-    const uint64_t total = (uint64_t)n_frames * g.n_groups;
-    const PersistShape ps = persist_shape(g, total);
-    if (ps.grid != 0 && work_counter != nullptr && total < 0xffff0000ull) {
-        WorkCounter *wc = static_cast<WorkCounter *>(work_counter);
-#define FRI_LAUNCH(CC, SS) fri_decode_persistent_kernel<CC, SS><<<ps.grid, ps.threads, ps.smem, stream>>>( \
-        g, qp, t.groups, t.tile_unit, t.chunk_list, t.chunk_mask, d_coefs, d_dc, px, (unsigned)total, wc)
+    for (uint32_t f0 = 0; f0 < n_frames; f0 += 65535u) {
+        const uint32_t nf = n_frames - f0 < 65535u ? n_frames - f0 : 65535u;
+        const dim3 grid((unsigned)g.n_groups, nf);
+        uint8_t *p = px + (int64_t)f0 * g.frame_bytes;
+        const int32_t *c = d_coefs + (int64_t)f0 * g.coefs_per_frame;
+        int32_t *dc = d_dc ? d_dc + (((int64_t)f0 * g.n_fractals * g.channels) << g.sub_bits) : nullptr;
+#define FRI_LAUNCH(CC, SS)                                                                                                        \
+        do {                                                                                                                      \
+            if (g.sub_bits == 0)                                                                                                  \
+                fri_decode_kernel<CC, SS, false><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, t.chunk_mask, c, dc, p); \
+            else                                                                                                                  \
+                fri_decode_kernel<CC, SS, true><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, t.chunk_mask, c, dc, p);  \
+        } while (0)
         if (g.channels == 1 && g.sample_bytes == 1) FRI_LAUNCH(1, uint8_t);
         else if (g.channels == 3 && g.sample_bytes == 1) FRI_LAUNCH(3, uint8_t);
         else if (g.channels == 1 && g.sample_bytes == 2) FRI_LAUNCH(1, uint16_t);
         else FRI_LAUNCH(3, uint16_t);
 #undef FRI_LAUNCH
         if (launches) ++*launches;
-    } else {
-        const size_t smem = kernel_smem_bytes(g);
-        for (uint32_t f0 = 0; f0 < n_frames; f0 += 65535u) {
-            const uint32_t nf = n_frames - f0 < 65535u ? n_frames - f0 : 65535u;
-            const dim3 grid((unsigned)g.n_groups, nf);
-            uint8_t *p = px + (int64_t)f0 * g.frame_bytes;
-            const int32_t *c = d_coefs + (int64_t)f0 * g.coefs_per_frame;
-            int32_t *dc = d_dc ? d_dc + (((int64_t)f0 * g.n_fractals * g.channels) << g.sub_bits) : nullptr;
-#define FRI_LAUNCH(CC, SS) fri_decode_kernel<CC, SS><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, t.chunk_mask, c, dc, p)
-            if (g.channels == 1 && g.sample_bytes == 1) FRI_LAUNCH(1, uint8_t);
-            else if (g.channels == 3 && g.sample_bytes == 1) FRI_LAUNCH(3, uint8_t);
-            else if (g.channels == 1 && g.sample_bytes == 2) FRI_LAUNCH(1, uint16_t);
-            else FRI_LAUNCH(3, uint16_t);
-#undef FRI_LAUNCH
-            if (launches) ++*launches;
-        }
     }
     return cudaGetLastError();
 }

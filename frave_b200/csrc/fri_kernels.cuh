@@ -54,7 +54,6 @@ void make_quant_params(QuantParams &qp, const int32_t *q, int multiply);
 
 constexpr int kThreads = 256;       // upper bound on threads per CTA (launch bounds)
 constexpr int kMaxWarps = kThreads / 32;
-constexpr int kPersistThreads = 512;  // persistent kernels: 16 warps per CTA, two CTAs per SM
 int cta_threads(const Geometry &g);  // threads per CTA for a plan: one warp per two base tiles of a full group
 constexpr int kScratchInts = 64;    // per warp and channel: the 64 level-6 low-pass values of a base tile
 
@@ -68,9 +67,6 @@ struct DeviceTables {
     const uint16_t *chunk_mask = nullptr;  // [16][list_cap]
 };
 
-// work_counter: 8 zero-initialised bytes of device memory private to the launch (the persistent
-// kernels hand out (frame, group) work items from it and leave it zeroed again).
-
 // One-time per-process kernel attribute setup (max dynamic shared memory).
 cudaError_t configure_kernels();
 
@@ -78,11 +74,11 @@ cudaError_t configure_kernels();
 //   d_dc: scratch for the base tiles' low-pass roots, [n_frames][n_fractals][C][2^sub_bits]
 //         (depth > 9 only; finished by launch_coarse_forward).
 cudaError_t launch_encode(const Geometry &g, const DeviceTables &t, const QuantParams &qp, const void *d_pixels,
-                          uint32_t n_frames, int32_t *d_coefs, int32_t *d_dc, void *work_counter, cudaStream_t stream,
+                          uint32_t n_frames, int32_t *d_coefs, int32_t *d_dc, cudaStream_t stream,
                           uint32_t *launches);
 // Enqueue the fused dequantization + inverse transform + scatter.
 cudaError_t launch_decode(const Geometry &g, const DeviceTables &t, const QuantParams &qp, const int32_t *d_coefs,
-                          uint32_t n_frames, void *d_pixels, int32_t *d_dc, void *work_counter, cudaStream_t stream,
+                          uint32_t n_frames, void *d_pixels, int32_t *d_dc, cudaStream_t stream,
                           uint32_t *launches);
 
 }  // namespace fri
