@@ -5,8 +5,8 @@ TAG=${1:-run}
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_$TAG.log
 tail -4 gpurun_out/pytest_$TAG.log
-python bench.py --steps 300 --warmup 5 --no-cpu > gpurun_out/bench_$TAG.log 2>&1
-python bench.py --steps 60 --warmup 5 --no-cpu --shape 3840x2160x3 --frames 8 > gpurun_out/bench8_$TAG.log 2>&1
+python bench.py --steps 300 --warmup 5 --no-cpu --no-batched > gpurun_out/bench_$TAG.log 2>&1
+python bench.py --steps 60 --warmup 5 --no-cpu --no-batched --shape 3840x2160x3 --frames 8 > gpurun_out/bench8_$TAG.log 2>&1
 python - <<PY
 import json
 for f in ("gpurun_out/bench_$TAG.log", "gpurun_out/bench8_$TAG.log"):
@@ -17,6 +17,6 @@ for f in ("gpurun_out/bench_$TAG.log", "gpurun_out/bench8_$TAG.log"):
     except Exception as e:
         print(f, "FAILED", e); print(open(f).read()[-2000:])
 PY
-CMD="python bench.py --steps 3 --warmup 3 --preheat 0 --no-cpu"
+CMD="python bench.py --steps 3 --warmup 3 --preheat 0 --no-cpu --no-batched"
 $CMD > gpurun_out/plain_$TAG.log 2>&1 && ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sectors_srcunit_tex_op_read.sum,sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_adu.avg.pct_of_peak_sustained_active --clock-control none -k regex:fri_ -s 6 -c 4 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_$TAG.log 2>&1
 python profiles/ncu_launches.py gpurun_out/launches_$TAG.csv

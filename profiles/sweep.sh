@@ -5,7 +5,7 @@ for cfg in "${@}"; do
   IFS=, read grp tpw <<< "$cfg"
   for mode in "single" "batch"; do
     if [ $mode == single ]; then ARGS="--steps 200"; else ARGS="--steps 40 --shape 3840x2160x3 --frames 8"; fi
-    FRI_GROUP=$grp FRI_TILES_PER_WARP=$tpw python bench.py $ARGS --warmup 5 --no-cpu --preheat 0.3 > gpurun_out/sweep.log 2>&1
+    FRI_GROUP=$grp FRI_TILES_PER_WARP=$tpw python bench.py $ARGS --warmup 5 --no-cpu --no-batched --preheat 0.3 > gpurun_out/sweep.log 2>&1
     python - "$cfg" $mode <<PY
 import json, sys
 try:
