@@ -44,6 +44,8 @@ _SYMBOLS = [
     ("fri_host_free", None, [_P]),
     ("fri_plan_last_launches", C.c_uint32, [_P]),
     ("fri_quant_divide", C.c_int32, [C.c_int32, C.c_int32]),
+    ("fri_quant_divide_small", C.c_int32, [C.c_int32, C.c_int32]),
+    ("fri_quant_divide_magic", C.c_int32, [C.c_int32, C.c_int32]),
 ]
 SYMBOL_NAMES = [s[0] for s in _SYMBOLS]
 
@@ -190,7 +192,7 @@ class Plan:
         info = (C.c_int32 * 16)()
         _check(lib().fri_plan_launch_info(self._h, C.addressof(info)))
         keys = ["group_a", "group_b", "region_w", "region_h", "smem_pitch", "smem_bytes", "n_groups", "n_base_tiles",
-                "threads", "chunks_per_row", "depth", "sub_bits"]
+                "threads", "chunks_per_row", "depth", "sub_bits", "chunks_full", "chunks_owned"]
         return {k: int(info[i]) for i, k in enumerate(keys)}
 
     @property

@@ -118,6 +118,10 @@ int ensure_slots(fri_plan *p)
 
 }  // namespace
 
+#if FRI_TRACE
+namespace fri { cudaError_t debug_trace(unsigned long long *out, size_t n); }
+#endif
+
 extern "C" {
 
 const char *fri_version(void) { return "libfri_cuda 0.1.0 sm_100a"; }
@@ -246,7 +250,8 @@ int fri_plan_launch_info(const fri_plan *p, int32_t info[16])
     if (!p || !info) return fail(FRI_E_INVALID, "NULL argument");
     const Geometry &g = p->plan.geo;
     const int32_t v[16] = {g.group_a, g.group_b, g.region_w, g.region_h, g.pitch, (int32_t)kernel_smem_bytes(g),
-                           g.n_groups, g.n_base_tiles, cta_threads(g), g.chunks_per_row, g.depth, g.sub_bits, 0, 0, 0, 0};
+                           g.n_groups, g.n_base_tiles, cta_threads(g), g.chunks_per_row, g.depth, g.sub_bits,
+                           g.list_full[0], g.list_all[0], 0, 0};
     std::memcpy(info, v, sizeof(v));
     return FRI_OK;
 }
@@ -368,6 +373,29 @@ void fri_host_free(void *p)
 
 uint32_t fri_plan_last_launches(const fri_plan *p) { return p ? p->last_launches : 0; }
 
-int32_t fri_quant_divide(int32_t value, int32_t q) { return q <= 1 ? value : trunc_div(value, make_div(q)); }
+int32_t fri_quant_divide(int32_t value, int32_t q)
+{
+    if (q <= 1) return value;
+    if ((q & (q - 1)) == 0) {  // the kernels' power-of-two path
+        int k = 0;
+        while ((1 << k) < q) ++k;
+        return trunc_div_pow2(value, k);
+    }
+    return trunc_div(value, make_div(q));
+}
+
+/* the multiply-high path for any q >= 2, powers of two included (for tests) */
+int32_t fri_quant_divide_magic(int32_t value, int32_t q) { return q <= 1 ? value : trunc_div(value, make_div(q)); }
+
+int32_t fri_quant_divide_small(int32_t value, int32_t q)
+{
+    SmallDiv sd;
+    if (q <= 1) return value;
+    return make_small_div(q, sd) ? trunc_div_small(value, sd) : trunc_div(value, make_div(q));
+}
+
+#if FRI_TRACE
+int fri_debug_trace(unsigned long long *out, size_t n) { return fri::debug_trace(out, n) == cudaSuccess ? 0 : -2; }
+#endif
 
 }  // extern "C"

@@ -61,9 +61,25 @@ Div make_div(int32_t q)
     return dv;
 }
 
+bool make_small_div(int32_t q, SmallDiv &out)
+{
+    // magic = floor(2^(32+s) / q) + 1 with the smallest s >= 0 that keeps kSmallDivRange * q <=
+    // 2^(32+s) (exactness for |n| <= kSmallDivRange); it stays below 2^31 for every q >= 3.
+    if (q < 3) return false;
+    int s = 0;
+    while (((uint64_t)kSmallDivRange + 1) * (uint64_t)q > ((uint64_t)1 << (32 + s))) ++s;
+    const uint64_t m = (((uint64_t)1 << (32 + s)) / (uint64_t)q) + 1u;
+    if (m >= ((uint64_t)1 << 31)) return false;
+    out.magic = (int32_t)m;
+    out.shift = s;
+    return true;
+}
+
 void make_quant_params(QuantParams &qp, const int32_t *q, int multiply)
 {
     qp.active = 0;
+    qp.small = 0;
+    qp.pow2 = 0;
     qp.multiply = multiply;
     for (int l = 0; l < 32; ++l) {
         const int32_t v = q ? q[l] : 1;
@@ -72,6 +88,15 @@ void make_quant_params(QuantParams &qp, const int32_t *q, int multiply)
         qp.magic[l] = dv.magic;
         qp.addmask[l] = dv.addmask;
         qp.shift[l] = dv.shift;
+        qp.pow2_shift[l] = 0;
+        if (v >= 2 && (v & (v - 1)) == 0) {
+            qp.pow2 |= 1u << l;
+            while ((1 << qp.pow2_shift[l]) < v) ++qp.pow2_shift[l];
+        }
+        SmallDiv sd{0, 0};
+        if (make_small_div(v, sd)) qp.small |= 1u << l;
+        qp.small_magic[l] = sd.magic;
+        qp.small_shift[l] = sd.shift;
         if (v != 1) qp.active |= 1u << l;
     }
 }
@@ -87,6 +112,11 @@ size_t kernel_smem_bytes(const Geometry &g)
     return (((size_t)g.region_h * g.pitch + 15) & ~(size_t)15) + (size_t)(cta_threads(g) / 32) * g.channels * kScratchInts * sizeof(int32_t);
 }
 
+#if FRI_TRACE
+__device__ unsigned long long g_trace[3 * 16384];
+cudaError_t debug_trace(unsigned long long *out, size_t n) { return cudaMemcpyFromSymbol(out, g_trace, n * sizeof(unsigned long long)); }
+#endif
+
 namespace {
 
 // ------------------------------------------------------------------------------------------
@@ -97,6 +127,17 @@ __device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src
     const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(gmem_src) : "memory");
 }
+#if FRI_TRACE
+__device__ __forceinline__ unsigned long long gtime()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define FRI_TRACE_MARK(slot) do { if (threadIdx.x == 0 && blockIdx.x < 16384) g_trace[3 * blockIdx.x + (slot)] = gtime(); } while (0)
+#else
+#define FRI_TRACE_MARK(slot) do { } while (0)
+#endif
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
 // wrapping i32 arithmetic (release-mode Rust semantics)
@@ -129,15 +170,18 @@ __device__ __forceinline__ void unlift(int s, int d, int &l, int &r)
 __device__ __forceinline__ int layer_of(uint32_t pos) { return 31 - __clz((int)(pos + 1u)); }
 
 // quantization::encode (quantization.rs:19) / ::decode (:37) of one coefficient of layer l.
-// The branch is uniform whenever l is.
-__device__ __forceinline__ int quant_layer(const QuantParams &qp, int d, int l)
+// The branches are uniform whenever l is.
+// encoder only (|d| <= 65535): prefers the narrow-range division
+__device__ __forceinline__ int quant_layer_enc(const QuantParams &qp, int d, int l)
 {
-    return ((qp.active >> l) & 1u) ? trunc_div(d, qp.div(l)) : d;
+    if (!((qp.active >> l) & 1u)) return d;
+    return ((qp.small >> l) & 1u) ? trunc_div_small(d, qp.sdiv(l)) : trunc_div(d, qp.div(l));
 }
 __device__ __forceinline__ int dequant_layer(const QuantParams &qp, int d, int l)
 {
     if (!((qp.active >> l) & 1u)) return d;
-    return qp.multiply ? (int)((unsigned)d * (unsigned)qp.q[l]) : trunc_div(d, qp.div(l));
+    if (qp.multiply) return (int)((unsigned)d * (unsigned)qp.q[l]);
+    return ((qp.pow2 >> l) & 1u) ? trunc_div_pow2(d, qp.pow2_shift[l]) : trunc_div(d, qp.div(l));
 }
 
 template <typename S>
@@ -358,25 +402,27 @@ __device__ __forceinline__ void encode_tiles(const Geometry &g, const QuantParam
             // quantization.rs:13 — layer = level, except the last node of a level: level + 1
             if ((qp.active >> (top + 6)) & 0xfu) {
                 const int r8 = b8[3], r7 = b7[1], r6 = b6;  // unquantized values of the level-last nodes
-                if ((qp.active >> (top + 8)) & 1u) {
-                    const Div dv = qp.div(top + 8);
-#pragma unroll
-                    for (int m = 0; m < 4; ++m) { a8[m] = trunc_div(a8[m], dv); b8[m] = trunc_div(b8[m], dv); }
+#define FRI_QLEVEL(L, N, A, B)                                                              \
+                if ((qp.active >> (top + (L))) & 1u) {                                              \
+                    if ((qp.small >> (top + (L))) & 1u) {                                           \
+                        const SmallDiv dv = qp.sdiv(top + (L));                                     \
+                        _Pragma("unroll") for (int m = 0; m < (N); ++m) { A[m] = trunc_div_small(A[m], dv); B[m] = trunc_div_small(B[m], dv); } \
+                    } else {                                                                        \
+                        const Div dv = qp.div(top + (L));                                           \
+                        _Pragma("unroll") for (int m = 0; m < (N); ++m) { A[m] = trunc_div(A[m], dv); B[m] = trunc_div(B[m], dv); } \
+                    }                                                                               \
                 }
-                if ((qp.active >> (top + 7)) & 1u) {
-                    const Div dv = qp.div(top + 7);
-#pragma unroll
-                    for (int m = 0; m < 2; ++m) { a7[m] = trunc_div(a7[m], dv); b7[m] = trunc_div(b7[m], dv); }
-                }
-                if ((qp.active >> (top + 6)) & 1u) {
-                    const Div dv = qp.div(top + 6);
-                    a6 = trunc_div(a6, dv);
-                    b6 = trunc_div(b6, dv);
-                }
+                int a6v[1] = {a6}, b6v[1] = {b6};
+                FRI_QLEVEL(8, 4, a8, b8)
+                FRI_QLEVEL(7, 2, a7, b7)
+                FRI_QLEVEL(6, 1, a6v, b6v)
+#undef FRI_QLEVEL
+                a6 = a6v[0];
+                b6 = b6v[0];
                 if (lastB) {
-                    b8[3] = quant_layer(qp, r8, top + 9);
-                    b7[1] = quant_layer(qp, r7, top + 8);
-                    b6 = quant_layer(qp, r6, top + 7);
+                    b8[3] = quant_layer_enc(qp, r8, top + 9);
+                    b7[1] = quant_layer_enc(qp, r7, top + 8);
+                    b6 = quant_layer_enc(qp, r6, top + 7);
                 }
             }
             int32_t *out = coefs + ta.block + ((int64_t)ch << depth);
@@ -408,17 +454,17 @@ __device__ __forceinline__ void encode_tiles(const Geometry &g, const QuantParam
             if ((qp.active >> top) & 0x7fu) {
                 // level-L nodes sit in layer top + L, the level's last node in layer top + L + 1
                 const bool lastG = ta.last && j8 == 7;
-                d5[0] = quant_layer(qp, d5[0], top + 5); d5[1] = quant_layer(qp, d5[1], top + 5);
-                d5[2] = quant_layer(qp, d5[2], top + 5); d5[3] = quant_layer(qp, d5[3], top + (lastG ? 6 : 5));
-                d4[0] = quant_layer(qp, d4[0], top + 4); d4[1] = quant_layer(qp, d4[1], top + (lastG ? 5 : 4));
-                d3 = quant_layer(qp, d3, top + (lastG ? 4 : 3));
-                d2 = quant_layer(qp, d2, top + ((ta.last && j8 == 6) ? 3 : 2));
-                d1 = quant_layer(qp, d1, top + ((ta.last && j8 == 4) ? 2 : 1));
+                d5[0] = quant_layer_enc(qp, d5[0], top + 5); d5[1] = quant_layer_enc(qp, d5[1], top + 5);
+                d5[2] = quant_layer_enc(qp, d5[2], top + 5); d5[3] = quant_layer_enc(qp, d5[3], top + (lastG ? 6 : 5));
+                d4[0] = quant_layer_enc(qp, d4[0], top + 4); d4[1] = quant_layer_enc(qp, d4[1], top + (lastG ? 5 : 4));
+                d3 = quant_layer_enc(qp, d3, top + (lastG ? 4 : 3));
+                d2 = quant_layer_enc(qp, d2, top + ((ta.last && j8 == 6) ? 3 : 2));
+                d1 = quant_layer_enc(qp, d1, top + ((ta.last && j8 == 4) ? 2 : 1));
                 if (sub_bits == 0) {
-                    d0 = quant_layer(qp, d0, 1);  // position 1 is the last node of level 0
-                    s0 = quant_layer(qp, s0, 0);  // position 0: the low-pass root (wavelet_transform.rs:221)
+                    d0 = quant_layer_enc(qp, d0, 1);  // position 1 is the last node of level 0
+                    s0 = quant_layer_enc(qp, s0, 0);  // position 0: the low-pass root (wavelet_transform.rs:221)
                 } else {
-                    d0 = quant_layer(qp, d0, top + (ta.last ? 1 : 0));
+                    d0 = quant_layer_enc(qp, d0, top + (ta.last ? 1 : 0));
                 }
             }
             if (grp_live) {
@@ -542,24 +588,27 @@ __device__ __forceinline__ void decode_tiles(const Geometry &g, const QuantParam
             if ((qp.active >> (top + 6)) & 0xfu) {
                 const int r8 = b8.w, r7 = b7.y, r6 = b6;  // raw values of the level-last nodes
                 const int mul = qp.multiply;
-                if ((qp.active >> (top + 8)) & 1u) {
-                    const Div dv = qp.div(top + 8);
-                    const int q = qp.q[top + 8];
-#define FRI_DQ(x) x = mul ? (int)((unsigned)(x) * (unsigned)q) : trunc_div(x, dv)
-                    FRI_DQ(a8.x); FRI_DQ(a8.y); FRI_DQ(a8.z); FRI_DQ(a8.w);
-                    FRI_DQ(b8.x); FRI_DQ(b8.y); FRI_DQ(b8.z); FRI_DQ(b8.w);
+#define FRI_DQLEVEL(L, STMTS)                                                               \
+                if ((qp.active >> (top + (L))) & 1u) {                                              \
+                    if (mul) {                                                                      \
+                        const unsigned q = (unsigned)qp.q[top + (L)];                               \
+                        auto f = [q](int x) { return (int)((unsigned)x * q); };                     \
+                        STMTS                                                                       \
+                    } else if ((qp.pow2 >> (top + (L))) & 1u) {                                     \
+                        const int k = qp.pow2_shift[top + (L)];                                     \
+                        auto f = [k](int x) { return trunc_div_pow2(x, k); };                       \
+                        STMTS                                                                       \
+                    } else {                                                                        \
+                        const Div dv = qp.div(top + (L));                                           \
+                        auto f = [dv](int x) { return trunc_div(x, dv); };                          \
+                        STMTS                                                                       \
+                    }                                                                               \
                 }
-                if ((qp.active >> (top + 7)) & 1u) {
-                    const Div dv = qp.div(top + 7);
-                    const int q = qp.q[top + 7];
-                    FRI_DQ(a7.x); FRI_DQ(a7.y); FRI_DQ(b7.x); FRI_DQ(b7.y);
-                }
-                if ((qp.active >> (top + 6)) & 1u) {
-                    const Div dv = qp.div(top + 6);
-                    const int q = qp.q[top + 6];
-                    FRI_DQ(a6); FRI_DQ(b6);
-#undef FRI_DQ
-                }
+                FRI_DQLEVEL(8, a8.x = f(a8.x); a8.y = f(a8.y); a8.z = f(a8.z); a8.w = f(a8.w);
+                               b8.x = f(b8.x); b8.y = f(b8.y); b8.z = f(b8.z); b8.w = f(b8.w);)
+                FRI_DQLEVEL(7, a7.x = f(a7.x); a7.y = f(a7.y); b7.x = f(b7.x); b7.y = f(b7.y);)
+                FRI_DQLEVEL(6, a6 = f(a6); b6 = f(b6);)
+#undef FRI_DQLEVEL
                 if (lastB) {
                     b8.w = dequant_layer(qp, r8, top + 9);
                     b7.y = dequant_layer(qp, r7, top + 8);
@@ -619,12 +668,17 @@ __device__ __forceinline__ void zero_region(const Geometry &g, uint8_t *region)
 // behind the barrier wait.
 constexpr int kWriteAhead = 8;
 
+constexpr int kMixedAhead = 2;
+
 struct WriteAhead {
-    uint32_t e[kWriteAhead];
+    uint32_t e[kWriteAhead];      // fully owned chunks
+    uint32_t me[kMixedAhead];     // partially owned chunks ...
+    uint32_t mm[kMixedAhead];     // ... and their byte masks
 };
 
 __device__ __forceinline__ WriteAhead write_out_preload(const Geometry &g, const RegionView &rv,
-                                                        const uint32_t *__restrict__ chunk_list)
+                                                        const uint32_t *__restrict__ chunk_list,
+                                                        const uint16_t *__restrict__ chunk_mask)
 {
     WriteAhead w;
     const uint32_t *cl = chunk_list + (size_t)rv.phi0 * g.list_cap;
@@ -633,6 +687,15 @@ __device__ __forceinline__ WriteAhead write_out_preload(const Geometry &g, const
     for (int u = 0; u < kWriteAhead; ++u) {
         const int k = threadIdx.x + u * blockDim.x;
         w.e[u] = (rv.interior && k < n_full) ? __ldg(cl + k) : kNoChunk;
+    }
+    const uint16_t *cmk = chunk_mask + (size_t)rv.phi0 * g.list_cap;
+    const int n_all = g.list_all[rv.phi0];
+#pragma unroll
+    for (int u = 0; u < kMixedAhead; ++u) {
+        const int k = n_full + threadIdx.x + u * blockDim.x;
+        const bool on = rv.interior && k < n_all;
+        w.me[u] = on ? __ldg(cl + k) : kNoChunk;
+        w.mm[u] = on ? (uint32_t)__ldg(cmk + k) : 0u;
     }
     return w;
 }
@@ -660,7 +723,13 @@ __device__ __forceinline__ void write_out_group(const Geometry &g, const GroupDe
             *reinterpret_cast<int4 *>(reinterpret_cast<uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s) =
                 *reinterpret_cast<const int4 *>(region + s);
         }
-        for (int k = n_full + threadIdx.x; k < n_all; k += n_threads) {
+#pragma unroll
+        for (int u = 0; u < kMixedAhead; ++u)
+            if (ahead.me[u] != kNoChunk) {
+                const int r = (int)(ahead.me[u] >> 16), s = (int)(ahead.me[u] & 0xffffu) << 4;
+                store_chunk_masked(reinterpret_cast<uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s, region + s, ahead.mm[u]);
+            }
+        for (int k = n_full + threadIdx.x + kMixedAhead * n_threads; k < n_all; k += n_threads) {
             const uint32_t e = __ldg(cl + k);
             const int r = (int)(e >> 16), s = (int)(e & 0xffffu) << 4;
             store_chunk_masked(reinterpret_cast<uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s, region + s, __ldg(cmk + k));
@@ -685,6 +754,9 @@ __device__ __forceinline__ size_t region_bytes(const Geometry &g) { return ((siz
 // ------------------------------------------------------------------------------------------
 // kernels: one CTA per (group, frame)
 // ------------------------------------------------------------------------------------------
+#ifndef FRI_TRACE
+#define FRI_TRACE 0
+#endif
 #ifndef FRI_ENC_MINB
 #define FRI_ENC_MINB 4
 #endif
@@ -704,10 +776,16 @@ fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
     const GroupDesc gd = groups[blockIdx.x];
     const int frame = blockIdx.y;
     const RegionView rv = region_view<C * (int)sizeof(S)>(g, gd, pixels + (int64_t)frame * g.frame_bytes);
+    FRI_TRACE_MARK(0);
     stage_group(g, gd, rv, chunk_list, region);
     cp_async_wait_all();
     __syncthreads();
+    FRI_TRACE_MARK(1);
     encode_tiles<C, S, DEEP>(g, qp, gd, rv, tile_unit, frame, region, scratch, coefs, dc_out);
+#if FRI_TRACE
+    __syncthreads();
+#endif
+    FRI_TRACE_MARK(2);
 }
 
 template <int C, typename S, bool DEEP>
@@ -723,15 +801,21 @@ fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
     const GroupDesc gd = groups[blockIdx.x];
     const int frame = blockIdx.y;
     const RegionView rv = region_view<C * (int)sizeof(S)>(g, gd, pixels + (int64_t)frame * g.frame_bytes);
+    FRI_TRACE_MARK(0);
     prefetch_group_coefs<C, DEEP>(g, gd, frame, coefs);
     if (__popc(gd.tile_mask) != g.group_a * g.group_b) {
         zero_region(g, region);
         __syncthreads();
     }
     decode_tiles<C, S, DEEP>(g, qp, gd, rv, tile_unit, frame, region, scratch, coefs, dc_in);
-    const WriteAhead ahead = write_out_preload(g, rv, chunk_list);
+    const WriteAhead ahead = write_out_preload(g, rv, chunk_list, chunk_mask);
     __syncthreads();
+    FRI_TRACE_MARK(1);
     write_out_group(g, gd, rv, chunk_list, chunk_mask, region, ahead);
+#if FRI_TRACE
+    __syncthreads();
+#endif
+    FRI_TRACE_MARK(2);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -758,12 +842,12 @@ fri_coarse_forward_kernel(const __grid_constant__ QuantParams qp, int sub_bits, 
             lift(src[2 * j], src[2 * j + 1], d, s);
             dst[j] = s;
             const uint32_t pos = (uint32_t)(cnt + j);
-            out[pos] = quant_layer(qp, d, layer_of(pos));
+            out[pos] = quant_layer_enc(qp, d, layer_of(pos));
         }
         __syncthreads();
         int32_t *t = src; src = dst; dst = t;
     }
-    if (threadIdx.x == 0) out[0] = quant_layer(qp, src[0], 0);  // wavelet_transform.rs:221, layer 0
+    if (threadIdx.x == 0) out[0] = quant_layer_enc(qp, src[0], 0);  // wavelet_transform.rs:221, layer 0
 }
 
 __global__ void __launch_bounds__(kCoarseThreads)

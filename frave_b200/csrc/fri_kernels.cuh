@@ -38,18 +38,46 @@ FRI_HDI int32_t trunc_div(int32_t n, Div dv)
     return t + (int32_t)((uint32_t)n >> 31);
 }
 
+// Power-of-two divisor 2^k (k >= 1): add 2^k - 1 to negative numerators, then shift.
+FRI_HDI int32_t trunc_div_pow2(int32_t n, int k)
+{
+    return (int32_t)((uint32_t)n + ((uint32_t)(n >> 31) >> (32 - k))) >> k;
+}
+
+// Narrow-range variant for the encoder, whose numerators are residues / low-pass values of 8- or
+// 16-bit samples (|n| <= 65535): a positive magic below 2^31 always exists for q >= 3, so the
+// "add" step disappears: t = mulhi(n, magic) >> shift; t += sign bit of n.
+struct SmallDiv {
+    int32_t magic;
+    int32_t shift;
+};
+constexpr int32_t kSmallDivRange = 65535;
+
+FRI_HDI int32_t trunc_div_small(int32_t n, SmallDiv dv)
+{
+    const int32_t t = mulhi_s32(n, dv.magic) >> dv.shift;
+    return t + (int32_t)((uint32_t)n >> 31);
+}
+
 // Quantization matrix prepared on the host (quantization.rs:3-25).
 struct QuantParams {
     int32_t magic[32];
     int32_t addmask[32];
     int32_t shift[32];
     int32_t q[32];
+    int32_t small_magic[32];  // encoder: narrow-range magic (valid where bit l of `small` is set)
+    int32_t small_shift[32];
+    int32_t pow2_shift[32];   // log2(q[l]) where bit l of `pow2` is set
     uint32_t active;   // bit l set <=> q[l] != 1
+    uint32_t small;    // bit l set <=> the narrow-range division is available for layer l
+    uint32_t pow2;     // bit l set <=> q[l] = 2^pow2_shift[l], pow2_shift[l] >= 1
     int32_t multiply;  // decode only: 1 = multiply (true dequantizer), 0 = divide (reference)
     FRI_HDI Div div(int l) const { return Div{magic[l], addmask[l], shift[l]}; }
+    FRI_HDI SmallDiv sdiv(int l) const { return SmallDiv{small_magic[l], small_shift[l]}; }
 };
 
-Div make_div(int32_t q);  // q >= 2
+Div make_div(int32_t q);                         // q >= 2
+bool make_small_div(int32_t q, SmallDiv &out);   // false if q < 3
 void make_quant_params(QuantParams &qp, const int32_t *q, int multiply);
 
 constexpr int kThreads = 256;       // upper bound on threads per CTA (launch bounds)

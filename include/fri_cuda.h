@@ -84,7 +84,8 @@ uint64_t fri_plan_pixels_covered(const fri_plan *plan);  /* in-image pixels owne
 
 /* Launch geometry, for reports: info = {group_a, group_b, region_w, region_h, smem_pitch,
  * smem_bytes_per_cta, n_groups (CTAs per frame), n_base_tiles, threads_per_cta,
- * chunks_per_row, depth, depth - 9, 0...}. */
+ * chunks_per_row, depth, depth - 9, fully owned 16-byte chunks per group, chunks with any owned
+ * byte per group (both at phase 0), 0...}. */
 int fri_plan_launch_info(const fri_plan *plan, int32_t info[16]);
 
 /* centres[n_tiles][2] = (re, im) of each retained tile, in plan order. */
@@ -125,6 +126,9 @@ uint32_t fri_plan_last_launches(const fri_plan *plan);
 /* The kernels' truncating division value / q (q >= 1) evaluated on the host: the same
  * multiply-high + shift routine the device code uses for quantization.rs:19 / :37 (for tests). */
 int32_t fri_quant_divide(int32_t value, int32_t q);
+int32_t fri_quant_divide_magic(int32_t value, int32_t q); /* multiply-high path even for powers of two */
+/* The encoder's narrow-range variant (exact for |value| <= 65535, all an 8/16-bit image can produce). */
+int32_t fri_quant_divide_small(int32_t value, int32_t q);
 
 #ifdef __cplusplus
 }

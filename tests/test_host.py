@@ -120,6 +120,23 @@ def test_kernel_division_routine_is_exact_truncating_division():
         for v in vals:
             want = abs(v) // q * (1 if v >= 0 else -1)
             assert L.fri_quant_divide(v, q) == want, (v, q)
+            assert L.fri_quant_divide_magic(v, q) == want, (v, q)
+
+
+def test_encoder_narrow_range_division_is_exact_on_its_whole_domain():
+    """The encoder divides residues of 8/16-bit samples (|n| <= 65535) with a cheaper magic: check
+    every numerator of that range against C semantics for a spread of divisors."""
+    L = capi.lib()
+    fn = np.vectorize(lambda v, q: L.fri_quant_divide_small(int(v), int(q)), otypes=[np.int64])
+    n = np.concatenate([np.arange(-65535, 65536, 1)])
+    for q in [2, 3, 4, 5, 7, 8, 64, 255, 256, 1000, 65535, 65536, 65537, 131072, 2**31 - 1]:
+        sub = n if q in (3, 4, 7) else n[::17]
+        want = np.sign(sub) * (np.abs(sub) // q)
+        assert np.array_equal(fn(sub, q), want), q
+    rng = np.random.Generator(np.random.PCG64(3))
+    for q in rng.integers(2, 70000, 40).tolist():
+        sub = rng.integers(-65535, 65536, 4000)
+        assert np.array_equal(fn(sub, q), np.sign(sub) * (np.abs(sub) // q)), q
 
 
 def test_shard_frames_partitions_the_batch():
