@@ -56,7 +56,7 @@ struct fri_plan {
     Plan plan;
     int device = -1;
     DeviceTables tables;
-    void *d_groups = nullptr, *d_tile_unit = nullptr, *d_chunk_mask = nullptr, *d_chunk_list = nullptr;
+    void *d_groups = nullptr, *d_tile_unit = nullptr, *d_chunk_mask = nullptr, *d_chunk_list = nullptr, *d_stage_list = nullptr;
     Slot slots[kSlots];
     bool slots_ready = false;
     int32_t *d_dc_shared = nullptr;  // low-pass scratch for the *_device entry points (depth > 9)
@@ -185,6 +185,7 @@ int fri_plan_create(fri_plan **out, int device, uint32_t width, uint32_t height,
         if (e == cudaSuccess && pl.geo.sub_bits > 0)
             e = upload(&p->d_tile_unit, pl.tile_unit.data(), pl.tile_unit.size() * sizeof(uint32_t));
         if (e == cudaSuccess) e = upload(&p->d_chunk_mask, pl.chunk_mask.data(), pl.chunk_mask.size() * sizeof(uint16_t));
+        if (e == cudaSuccess) e = upload(&p->d_stage_list, pl.stage_list.data(), pl.stage_list.size() * sizeof(uint32_t));
         if (e == cudaSuccess) e = upload(&p->d_chunk_list, pl.chunk_list.data(), pl.chunk_list.size() * sizeof(uint32_t));
         if (e != cudaSuccess) {
             fri_plan_destroy(p);
@@ -194,6 +195,7 @@ int fri_plan_create(fri_plan **out, int device, uint32_t width, uint32_t height,
         p->tables.tile_unit = static_cast<const uint32_t *>(p->d_tile_unit);
         p->tables.chunk_mask = static_cast<const uint16_t *>(p->d_chunk_mask);
         p->tables.chunk_list = static_cast<const uint32_t *>(p->d_chunk_list);
+        p->tables.stage_list = static_cast<const uint32_t *>(p->d_stage_list);
     }
     *out = p;
     return FRI_OK;
@@ -214,6 +216,7 @@ void fri_plan_destroy(fri_plan *p)
         if (p->d_tile_unit) cudaFree(p->d_tile_unit);
         if (p->d_chunk_mask) cudaFree(p->d_chunk_mask);
         if (p->d_chunk_list) cudaFree(p->d_chunk_list);
+        if (p->d_stage_list) cudaFree(p->d_stage_list);
     }
     delete p;
 }

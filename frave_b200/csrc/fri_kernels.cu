@@ -139,6 +139,8 @@ __device__ __forceinline__ unsigned long long gtime()
 #define FRI_TRACE_MARK(slot) do { } while (0)
 #endif
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
 
 // wrapping i32 arithmetic (release-mode Rust semantics)
 __device__ __forceinline__ int wsub(int a, int b) { return (int)((unsigned)a - (unsigned)b); }
@@ -296,11 +298,11 @@ constexpr uint32_t kNoChunk = 0xffffffffu;  // not a valid chunk-list entry (row
 // global and in shared memory) per thread and iteration, taken from the plan's list of chunks
 // that hold at least one pixel of the group's tiles.  Completion: cp.async.wait_all + barrier.
 __device__ __forceinline__ void stage_group(const Geometry &g, const GroupDesc &gd, const RegionView &rv,
-                                            const uint32_t *__restrict__ chunk_list, uint8_t *region)
+                                            const uint32_t *__restrict__ stage_list, uint8_t *region, int k_lo, int k_hi)
 {
     const int n_threads = blockDim.x;
-    const uint32_t *cl = chunk_list + (size_t)rv.phi0 * g.list_cap;
-    const int n_all = g.list_all[rv.phi0];
+    const uint32_t *cl = stage_list + (size_t)rv.phi0 * g.list_cap + k_lo;
+    const int n_all = k_hi - k_lo;
     if (rv.interior) {
         // list entries are fetched four at a time so that their latencies overlap
         for (int k0 = threadIdx.x; k0 < n_all; k0 += kListUnroll * n_threads) {
@@ -346,7 +348,8 @@ __device__ __forceinline__ void stage_group(const Geometry &g, const GroupDesc &
 template <int C, typename S, bool DEEP>
 __device__ __forceinline__ void encode_tiles(const Geometry &g, const QuantParams &qp, const GroupDesc &gd, const RegionView &rv,
                                              const uint32_t *__restrict__ tile_unit, int frame, const uint8_t *region,
-                                             int32_t *scratch, int32_t *__restrict__ coefs, int32_t *__restrict__ dc_out)
+                                             int32_t *scratch, int32_t *__restrict__ coefs, int32_t *__restrict__ dc_out,
+                                             bool two_stage)
 {
     constexpr int SB = (int)sizeof(S);
     constexpr int PB = C * SB;
@@ -360,6 +363,10 @@ __device__ __forceinline__ void encode_tiles(const Geometry &g, const QuantParam
     const int grp = min(lane >> 3, C - 1), j8 = lane & 7;  // phase 2 roles
     const bool grp_live = (lane >> 3) < C;
     for (int e = warp; e < n_present; e += n_warps) {
+        if (two_stage && e == warp + n_warps) {  // second round: the rest of the footprint must have landed
+            cp_async_wait_all();
+            __syncthreads();
+        }
         const int slot = sparse_group ? (int)__fns(gd.tile_mask, 0, e + 1) : e;
         const uint8_t *t0 = lane_base + g.tile_off[slot];
         const TaskAddr ta = task_addr<C, DEEP>(g, tile_unit, frame, gd.tile_base + e, 0);
@@ -767,7 +774,7 @@ template <int C, typename S, bool DEEP>
 __global__ void __launch_bounds__(kThreads, FRI_ENC_MINB)
 fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ QuantParams qp,
                   const GroupDesc *__restrict__ groups, const uint32_t *__restrict__ tile_unit,
-                  const uint32_t *__restrict__ chunk_list, const uint8_t *__restrict__ pixels,
+                  const uint32_t *__restrict__ stage_list, const uint8_t *__restrict__ pixels,
                   int32_t *__restrict__ coefs, int32_t *__restrict__ dc_out)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -777,11 +784,24 @@ fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
     const int frame = blockIdx.y;
     const RegionView rv = region_view<C * (int)sizeof(S)>(g, gd, pixels + (int64_t)frame * g.frame_bytes);
     FRI_TRACE_MARK(0);
-    stage_group(g, gd, rv, chunk_list, region);
-    cp_async_wait_all();
+    // Two-stage copy: the chunks needed by every warp's first tile are committed first, so that
+    // the first round of tiles runs while the rest of the footprint is still in flight.
+    const int n_warps = blockDim.x >> 5;
+    const int n_first = g.stage_first[rv.phi0], n_all = g.list_all[rv.phi0];
+    // (full groups only: every warp then has a tile in both rounds and reaches the barrier between them)
+    const bool two_stage = __popc(gd.tile_mask) == g.group_a * g.group_b && g.group_a * g.group_b == 2 * n_warps;
+    stage_group(g, gd, rv, stage_list, region, 0, two_stage ? n_first : n_all);
+    cp_async_commit();
+    if (two_stage) {
+        stage_group(g, gd, rv, stage_list, region, n_first, n_all);
+        cp_async_commit();
+        cp_async_wait_but_one();
+    } else {
+        cp_async_wait_all();
+    }
     __syncthreads();
     FRI_TRACE_MARK(1);
-    encode_tiles<C, S, DEEP>(g, qp, gd, rv, tile_unit, frame, region, scratch, coefs, dc_out);
+    encode_tiles<C, S, DEEP>(g, qp, gd, rv, tile_unit, frame, region, scratch, coefs, dc_out, two_stage);
 #if FRI_TRACE
     __syncthreads();
 #endif
@@ -925,9 +945,9 @@ cudaError_t launch_encode(const Geometry &g, const DeviceTables &t, const QuantP
 #define FRI_LAUNCH(CC, SS)                                                                                                        \
         do {                                                                                                                      \
             if (g.sub_bits == 0)                                                                                                  \
-                fri_encode_kernel<CC, SS, false><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, p, c, dc); \
+                fri_encode_kernel<CC, SS, false><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.stage_list, p, c, dc); \
             else                                                                                                                  \
-                fri_encode_kernel<CC, SS, true><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, p, c, dc);  \
+                fri_encode_kernel<CC, SS, true><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.stage_list, p, c, dc);  \
         } while (0)
         if (g.channels == 1 && g.sample_bytes == 1) FRI_LAUNCH(1, uint8_t);
         else if (g.channels == 3 && g.sample_bytes == 1) FRI_LAUNCH(3, uint8_t);

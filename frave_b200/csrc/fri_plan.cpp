@@ -283,26 +283,41 @@ std::string build_plan(Plan &plan, uint32_t width, uint32_t height, uint32_t cha
 
     for (int s = 0; s < group_a * group_b; ++s) g.tile_off[s] = g.tile_rel_y[s] * g.pitch + g.tile_rel_x[s] * csz;
 
+    // Pixels of the tile slots every warp processes first (slot = warp index in a full group).
+    const int first_slots = std::min(group_a * group_b, std::max(1, (group_a * group_b + tiles_per_warp - 1) / tiles_per_warp));
+    std::vector<uint32_t> own_first((size_t)g.region_h * g.own_words, 0u);
+    for (int s = 0; s < first_slots; ++s)
+        for (unsigned k = 0; k < (unsigned)kTileLeaves; ++k) {
+            Vec2 o = digit_sum(k, 0, kBaseDepth);
+            int x = g.tile_rel_x[s] + o.x, y = g.tile_rel_y[s] + o.y;
+            own_first[(size_t)y * g.own_words + (x >> 5)] |= 1u << (x & 31);
+        }
+
     // Chunk lists.  Shared-memory byte r*pitch + phase + b holds region byte (r, b); chunks are
     // the 16-byte aligned pieces of shared memory (== aligned pieces of global memory).
     std::vector<std::vector<std::pair<uint32_t, uint16_t>>> lists(16);
+    std::vector<std::vector<uint32_t>> stage(16);
     g.list_cap = 0;
     for (int phase = 0; phase < 16; ++phase) {
         std::vector<std::pair<uint32_t, uint16_t>> full, part;
+        std::vector<uint32_t> st_first, st_rest;
         for (int r = 0; r < g.region_h; ++r) {
             const int srow = r * g.pitch + phase, sbase = srow & ~15;
             for (int c = 0; c < g.chunks_per_row; ++c) {
                 const int b0 = sbase + 16 * c - srow;
                 uint32_t m = 0;
+                bool first = false;
                 for (int j = 0; j < 16; ++j) {
                     const int b = b0 + j;
                     if (b < 0 || b >= g.row_bytes) continue;
                     const int x = b / csz;
                     if ((plan.ownership[(size_t)r * g.own_words + (x >> 5)] >> (x & 31)) & 1u) m |= 1u << j;
+                    first |= (own_first[(size_t)r * g.own_words + (x >> 5)] >> (x & 31)) & 1u;
                 }
                 if (m == 0) continue;
                 const uint32_t entry = (uint32_t)r << 16 | (uint32_t)((sbase + 16 * c) >> 4);
                 (m == 0xffffu ? full : part).emplace_back(entry, (uint16_t)m);
+                (first ? st_first : st_rest).push_back(entry);
             }
         }
         g.list_full[phase] = (int32_t)full.size();
@@ -310,14 +325,19 @@ std::string build_plan(Plan &plan, uint32_t width, uint32_t height, uint32_t cha
         g.list_cap = std::max(g.list_cap, g.list_all[phase]);
         lists[phase] = std::move(full);
         lists[phase].insert(lists[phase].end(), part.begin(), part.end());
+        g.stage_first[phase] = (int32_t)st_first.size();
+        stage[phase] = std::move(st_first);
+        stage[phase].insert(stage[phase].end(), st_rest.begin(), st_rest.end());
     }
     if ((size_t)g.region_h * g.pitch > ((size_t)1 << 20) || g.region_h > 0xffff) return "group region too large";
     plan.chunk_list.assign((size_t)16 * g.list_cap, 0u);
     plan.chunk_mask.assign((size_t)16 * g.list_cap, 0);
+    plan.stage_list.assign((size_t)16 * g.list_cap, 0u);
     for (int phase = 0; phase < 16; ++phase)
         for (size_t k = 0; k < lists[phase].size(); ++k) {
             plan.chunk_list[(size_t)phase * g.list_cap + k] = lists[phase][k].first;
             plan.chunk_mask[(size_t)phase * g.list_cap + k] = lists[phase][k].second;
+            plan.stage_list[(size_t)phase * g.list_cap + k] = stage[phase][k];
         }
 
     plan.centers.clear(); plan.full.clear(); plan.groups.clear(); plan.tile_unit.clear();

@@ -49,6 +49,7 @@ struct Geometry {
     int32_t tile_off[kMaxGroupTiles];    // tile_rel_y * pitch + tile_rel_x * pixel_bytes
     int32_t list_full[16];               // per phase: fully owned 16-byte chunks (listed first)
     int32_t list_all[16];                // per phase: all chunks that hold at least one owned byte
+    int32_t stage_first[16];             // per phase: leading stage_list entries needed by the first tile of every warp
 };
 
 struct Plan {
@@ -67,6 +68,9 @@ struct Plan {
     // bytes, fully owned chunks first; chunk_mask[phase][k]: bit j <=> byte j of that chunk is owned.
     std::vector<uint32_t> chunk_list;  // [16][list_cap]
     std::vector<uint16_t> chunk_mask;  // [16][list_cap]
+    // the same chunks in the order the encoder stages them: first those that hold a pixel of tile
+    // slots 0 .. warps-1 (every warp's first tile), then the rest
+    std::vector<uint32_t> stage_list;  // [16][list_cap]
 };
 
 // Returns an empty string on success, else an error message.  group_a/group_b == 0 picks the
