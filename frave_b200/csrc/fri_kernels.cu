@@ -142,6 +142,37 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
 
+// Plan tables (group descriptors, chunk lists) are a few hundred KB that every CTA of every launch
+// reads first, and the loads that depend on them cannot start before they arrive.  They are
+// fetched with an L2 evict_last policy so that the ~250 MB of streaming traffic per launch does
+// not push them out of the 126 MB L2 between launches.
+__device__ __forceinline__ uint64_t table_policy()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint32_t ld_table(const uint32_t *p, uint64_t pol)
+{
+    uint32_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_table(const uint16_t *p, uint64_t pol)
+{
+    uint16_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ GroupDesc ld_group(const GroupDesc *p, uint64_t pol)
+{
+    GroupDesc g;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(g.x0), "=r"(g.y0), "=r"(g.tile_mask), "=r"(g.tile_base)
+                 : "l"(p), "l"(pol));
+    return g;
+}
+
 // wrapping i32 arithmetic (release-mode Rust semantics)
 __device__ __forceinline__ int wsub(int a, int b) { return (int)((unsigned)a - (unsigned)b); }
 __device__ __forceinline__ int wadd(int a, int b) { return (int)((unsigned)a + (unsigned)b); }
@@ -298,7 +329,8 @@ constexpr uint32_t kNoChunk = 0xffffffffu;  // not a valid chunk-list entry (row
 // global and in shared memory) per thread and iteration, taken from the plan's list of chunks
 // that hold at least one pixel of the group's tiles.  Completion: cp.async.wait_all + barrier.
 __device__ __forceinline__ void stage_group(const Geometry &g, const GroupDesc &gd, const RegionView &rv,
-                                            const uint32_t *__restrict__ stage_list, uint8_t *region, int k_lo, int k_hi)
+                                            const uint32_t *__restrict__ stage_list, uint8_t *region, int k_lo, int k_hi,
+                                            uint64_t pol)
 {
     const int n_threads = blockDim.x;
     const uint32_t *cl = stage_list + (size_t)rv.phi0 * g.list_cap + k_lo;
@@ -308,7 +340,7 @@ __device__ __forceinline__ void stage_group(const Geometry &g, const GroupDesc &
         for (int k0 = threadIdx.x; k0 < n_all; k0 += kListUnroll * n_threads) {
             uint32_t e[kListUnroll];
 #pragma unroll
-            for (int u = 0; u < kListUnroll; ++u) e[u] = k0 + u * n_threads < n_all ? __ldg(cl + k0 + u * n_threads) : kNoChunk;
+            for (int u = 0; u < kListUnroll; ++u) e[u] = k0 + u * n_threads < n_all ? ld_table(cl + k0 + u * n_threads, pol) : kNoChunk;
 #pragma unroll
             for (int u = 0; u < kListUnroll; ++u)
                 if (e[u] != kNoChunk) {
@@ -319,7 +351,7 @@ __device__ __forceinline__ void stage_group(const Geometry &g, const GroupDesc &
     } else {
         const int stride32 = (int)g.row_stride;
         for (int k = threadIdx.x; k < n_all; k += n_threads) {
-            const uint32_t e = __ldg(cl + k);
+            const uint32_t e = ld_table(cl + k, pol);
             const int r = (int)(e >> 16), s = (int)(e & 0xffffu) << 4;
             const int y = gd.y0 + r;
             const bool yin = (unsigned)y < (unsigned)g.height;
@@ -685,7 +717,7 @@ struct WriteAhead {
 
 __device__ __forceinline__ WriteAhead write_out_preload(const Geometry &g, const RegionView &rv,
                                                         const uint32_t *__restrict__ chunk_list,
-                                                        const uint16_t *__restrict__ chunk_mask)
+                                                        const uint16_t *__restrict__ chunk_mask, uint64_t pol)
 {
     WriteAhead w;
     const uint32_t *cl = chunk_list + (size_t)rv.phi0 * g.list_cap;
@@ -693,7 +725,7 @@ __device__ __forceinline__ WriteAhead write_out_preload(const Geometry &g, const
 #pragma unroll
     for (int u = 0; u < kWriteAhead; ++u) {
         const int k = threadIdx.x + u * blockDim.x;
-        w.e[u] = (rv.interior && k < n_full) ? __ldg(cl + k) : kNoChunk;
+        w.e[u] = (rv.interior && k < n_full) ? ld_table(cl + k, pol) : kNoChunk;
     }
     const uint16_t *cmk = chunk_mask + (size_t)rv.phi0 * g.list_cap;
     const int n_all = g.list_all[rv.phi0];
@@ -701,8 +733,8 @@ __device__ __forceinline__ WriteAhead write_out_preload(const Geometry &g, const
     for (int u = 0; u < kMixedAhead; ++u) {
         const int k = n_full + threadIdx.x + u * blockDim.x;
         const bool on = rv.interior && k < n_all;
-        w.me[u] = on ? __ldg(cl + k) : kNoChunk;
-        w.mm[u] = on ? (uint32_t)__ldg(cmk + k) : 0u;
+        w.me[u] = on ? ld_table(cl + k, pol) : kNoChunk;
+        w.mm[u] = on ? ld_table(cmk + k, pol) : 0u;
     }
     return w;
 }
@@ -710,7 +742,7 @@ __device__ __forceinline__ WriteAhead write_out_preload(const Geometry &g, const
 __device__ __forceinline__ void write_out_group(const Geometry &g, const GroupDesc &gd, const RegionView &rv,
                                                 const uint32_t *__restrict__ chunk_list,
                                                 const uint16_t *__restrict__ chunk_mask, const uint8_t *region,
-                                                const WriteAhead &ahead)
+                                                const WriteAhead &ahead, uint64_t pol)
 {
     const int n_threads = blockDim.x;
     const uint32_t *cl = chunk_list + (size_t)rv.phi0 * g.list_cap;
@@ -725,7 +757,7 @@ __device__ __forceinline__ void write_out_group(const Geometry &g, const GroupDe
                     *reinterpret_cast<const int4 *>(region + s);
             }
         for (int k = threadIdx.x + kWriteAhead * n_threads; k < n_full; k += n_threads) {
-            const uint32_t e = __ldg(cl + k);
+            const uint32_t e = ld_table(cl + k, pol);
             const int r = (int)(e >> 16), s = (int)(e & 0xffffu) << 4;
             *reinterpret_cast<int4 *>(reinterpret_cast<uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s) =
                 *reinterpret_cast<const int4 *>(region + s);
@@ -737,17 +769,17 @@ __device__ __forceinline__ void write_out_group(const Geometry &g, const GroupDe
                 store_chunk_masked(reinterpret_cast<uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s, region + s, ahead.mm[u]);
             }
         for (int k = n_full + threadIdx.x + kMixedAhead * n_threads; k < n_all; k += n_threads) {
-            const uint32_t e = __ldg(cl + k);
+            const uint32_t e = ld_table(cl + k, pol);
             const int r = (int)(e >> 16), s = (int)(e & 0xffffu) << 4;
-            store_chunk_masked(reinterpret_cast<uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s, region + s, __ldg(cmk + k));
+            store_chunk_masked(reinterpret_cast<uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s, region + s, ld_table(cmk + k, pol));
         }
     } else {
         const int stride32 = (int)g.row_stride;
         for (int k = threadIdx.x; k < n_all; k += n_threads) {
-            const uint32_t e = __ldg(cl + k);
+            const uint32_t e = ld_table(cl + k, pol);
             const int r = (int)(e >> 16), s = (int)(e & 0xffffu) << 4;
             if ((unsigned)(gd.y0 + r) >= (unsigned)g.height) continue;
-            uint32_t m = k < n_full ? 0xffffu : (uint32_t)__ldg(cmk + k);
+            uint32_t m = k < n_full ? 0xffffu : ld_table(cmk + k, pol);
             const int xb = rv.xb0 + s - (r * g.pitch + rv.phi0);  // byte position of the chunk inside its image row
             const int lo = min(max(-xb, 0), 16), hi = min(max(stride32 - xb, 0), 16);
             m &= ((1u << hi) - 1u) & ~((1u << lo) - 1u);
@@ -775,12 +807,13 @@ __global__ void __launch_bounds__(kThreads, FRI_ENC_MINB)
 fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ QuantParams qp,
                   const GroupDesc *__restrict__ groups, const uint32_t *__restrict__ tile_unit,
                   const uint32_t *__restrict__ stage_list, const uint8_t *__restrict__ pixels,
-                  int32_t *__restrict__ coefs, int32_t *__restrict__ dc_out)
+                  int32_t *__restrict__ coefs, int32_t *__restrict__ dc_out, int lookahead)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *region = smem;
     int32_t *scratch = reinterpret_cast<int32_t *>(smem + region_bytes(g)) + (threadIdx.x >> 5) * (C * kScratchInts);
-    const GroupDesc gd = groups[blockIdx.x];
+    const uint64_t pol = table_policy();
+    const GroupDesc gd = ld_group(groups + blockIdx.x, pol);
     const int frame = blockIdx.y;
     const RegionView rv = region_view<C * (int)sizeof(S)>(g, gd, pixels + (int64_t)frame * g.frame_bytes);
     FRI_TRACE_MARK(0);
@@ -790,14 +823,34 @@ fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
     const int n_first = g.stage_first[rv.phi0], n_all = g.list_all[rv.phi0];
     // (full groups only: every warp then has a tile in both rounds and reaches the barrier between them)
     const bool two_stage = __popc(gd.tile_mask) == g.group_a * g.group_b && g.group_a * g.group_b == 2 * n_warps;
-    stage_group(g, gd, rv, stage_list, region, 0, two_stage ? n_first : n_all);
+    stage_group(g, gd, rv, stage_list, region, 0, two_stage ? n_first : n_all, pol);
     cp_async_commit();
     if (two_stage) {
-        stage_group(g, gd, rv, stage_list, region, n_first, n_all);
+        stage_group(g, gd, rv, stage_list, region, n_first, n_all, pol);
         cp_async_commit();
         cp_async_wait_but_one();
     } else {
         cp_async_wait_all();
+    }
+    // Look-ahead: while this group's copies are in flight, pull the pixel rows of the group that
+    // will run in this CTA slot one residency later towards L2, one 128-byte line per thread and
+    // iteration, so that its copies are served by L2 instead of waiting in the DRAM queues.
+    if (lookahead > 0) {
+        const int64_t target = (int64_t)frame * g.n_groups + blockIdx.x + lookahead;
+        if (target < (int64_t)gridDim.y * g.n_groups) {
+            const int tf = (int)(target / g.n_groups);
+            const GroupDesc tg = ld_group(groups + (target - (int64_t)tf * g.n_groups), pol);
+            const int lines_per_row = (g.row_bytes + 127) / 128 + 1;
+            const int y_lo = max(tg.y0, 0), y_hi = min(tg.y0 + g.region_h, g.height);
+            const int64_t xb = min(max((int64_t)tg.x0 * (C * (int)sizeof(S)), (int64_t)0), g.row_stride - 1);
+            const char *base = reinterpret_cast<const char *>(pixels) + (int64_t)tf * g.frame_bytes + xb;
+            const int total = (y_hi - y_lo) * lines_per_row;
+            for (int i = threadIdx.x; i < total; i += blockDim.x) {
+                const int r = i / lines_per_row, c = i - r * lines_per_row;
+                if (xb + (int64_t)c * 128 < g.row_stride)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (int64_t)(y_lo + r) * g.row_stride + (int64_t)c * 128));
+            }
+        }
     }
     __syncthreads();
     FRI_TRACE_MARK(1);
@@ -818,7 +871,8 @@ fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *region = smem;
     int32_t *scratch = reinterpret_cast<int32_t *>(smem + region_bytes(g)) + (threadIdx.x >> 5) * (C * kScratchInts);
-    const GroupDesc gd = groups[blockIdx.x];
+    const uint64_t pol = table_policy();
+    const GroupDesc gd = ld_group(groups + blockIdx.x, pol);
     const int frame = blockIdx.y;
     const RegionView rv = region_view<C * (int)sizeof(S)>(g, gd, pixels + (int64_t)frame * g.frame_bytes);
     FRI_TRACE_MARK(0);
@@ -828,10 +882,10 @@ fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
         __syncthreads();
     }
     decode_tiles<C, S, DEEP>(g, qp, gd, rv, tile_unit, frame, region, scratch, coefs, dc_in);
-    const WriteAhead ahead = write_out_preload(g, rv, chunk_list, chunk_mask);
+    const WriteAhead ahead = write_out_preload(g, rv, chunk_list, chunk_mask, pol);
     __syncthreads();
     FRI_TRACE_MARK(1);
-    write_out_group(g, gd, rv, chunk_list, chunk_mask, region, ahead);
+    write_out_group(g, gd, rv, chunk_list, chunk_mask, region, ahead, pol);
 #if FRI_TRACE
     __syncthreads();
 #endif
@@ -929,12 +983,34 @@ cudaError_t configure_kernels()
     return cudaSuccess;
 }
 
+namespace {
+
+// CTAs of the main kernels resident on the device at once.
+int resident_ctas(const Geometry &g)
+{
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    const int threads = cta_threads(g);
+    const size_t smem = kernel_smem_bytes(g) + 1024;
+    int per_sm = (int)std::min<size_t>((size_t)(228 * 1024) / smem, (size_t)(65536 / (64 * threads)));
+    per_sm = std::max(1, std::min(per_sm, 2048 / threads));
+    return sms * per_sm;
+}
+
+}  // namespace
+
 cudaError_t launch_encode(const Geometry &g, const DeviceTables &t, const QuantParams &qp, const void *d_pixels,
                           uint32_t n_frames, int32_t *d_coefs, int32_t *d_dc, cudaStream_t stream,
                           uint32_t *launches)
 {
     if (n_frames == 0 || g.n_groups == 0) return cudaSuccess;
     const size_t smem = kernel_smem_bytes(g);
+    int lookahead = resident_ctas(g);  // prefetch distance: the group that will reuse this CTA's slot
+    if (const char *env = std::getenv("FRI_LOOKAHEAD")) lookahead = std::atoi(env);  // tuning knob
     const uint8_t *px = static_cast<const uint8_t *>(d_pixels);
     for (uint32_t f0 = 0; f0 < n_frames; f0 += 65535u) {  // gridDim.y limit
         const uint32_t nf = n_frames - f0 < 65535u ? n_frames - f0 : 65535u;
@@ -945,9 +1021,9 @@ cudaError_t launch_encode(const Geometry &g, const DeviceTables &t, const QuantP
 #define FRI_LAUNCH(CC, SS)                                                                                                        \
         do {                                                                                                                      \
             if (g.sub_bits == 0)                                                                                                  \
-                fri_encode_kernel<CC, SS, false><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.stage_list, p, c, dc); \
+                fri_encode_kernel<CC, SS, false><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.stage_list, p, c, dc, lookahead); \
             else                                                                                                                  \
-                fri_encode_kernel<CC, SS, true><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.stage_list, p, c, dc);  \
+                fri_encode_kernel<CC, SS, true><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.stage_list, p, c, dc, lookahead);  \
         } while (0)
         if (g.channels == 1 && g.sample_bytes == 1) FRI_LAUNCH(1, uint8_t);
         else if (g.channels == 3 && g.sample_bytes == 1) FRI_LAUNCH(3, uint8_t);
