@@ -119,7 +119,7 @@ int ensure_slots(fri_plan *p)
 }  // namespace
 
 #if FRI_TRACE
-namespace fri { cudaError_t debug_trace(unsigned long long *out, size_t n); }
+namespace fri { cudaError_t debug_trace(unsigned long long *out, size_t n); cudaError_t debug_trace2(unsigned long long *out, size_t n); }
 #endif
 
 extern "C" {
@@ -399,6 +399,7 @@ int32_t fri_quant_divide_small(int32_t value, int32_t q)
 
 #if FRI_TRACE
 int fri_debug_trace(unsigned long long *out, size_t n) { return fri::debug_trace(out, n) == cudaSuccess ? 0 : -2; }
+int fri_debug_trace2(unsigned long long *out, size_t n) { return fri::debug_trace2(out, n) == cudaSuccess ? 0 : -2; }
 #endif
 
 }  // extern "C"

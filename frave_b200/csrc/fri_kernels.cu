@@ -114,7 +114,9 @@ size_t kernel_smem_bytes(const Geometry &g)
 
 #if FRI_TRACE
 __device__ unsigned long long g_trace[3 * 16384];
+__device__ unsigned long long g_trace2[4 * 16384];
 cudaError_t debug_trace(unsigned long long *out, size_t n) { return cudaMemcpyFromSymbol(out, g_trace, n * sizeof(unsigned long long)); }
+cudaError_t debug_trace2(unsigned long long *out, size_t n) { return cudaMemcpyFromSymbol(out, g_trace2, n * sizeof(unsigned long long)); }
 #endif
 
 namespace {
@@ -756,6 +758,9 @@ __device__ __forceinline__ void write_out_group(const Geometry &g, const GroupDe
                 *reinterpret_cast<int4 *>(reinterpret_cast<uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s) =
                     *reinterpret_cast<const int4 *>(region + s);
             }
+#if FRI_TRACE
+        if ((threadIdx.x == 0 || threadIdx.x == 255) && blockIdx.x < 16384) g_trace2[4 * blockIdx.x + (threadIdx.x == 0 ? 0 : 1)] = gtime();
+#endif
         for (int k = threadIdx.x + kWriteAhead * n_threads; k < n_full; k += n_threads) {
             const uint32_t e = ld_table(cl + k, pol);
             const int r = (int)(e >> 16), s = (int)(e & 0xffffu) << 4;
@@ -773,6 +778,9 @@ __device__ __forceinline__ void write_out_group(const Geometry &g, const GroupDe
             const int r = (int)(e >> 16), s = (int)(e & 0xffffu) << 4;
             store_chunk_masked(reinterpret_cast<uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s, region + s, ld_table(cmk + k, pol));
         }
+#if FRI_TRACE
+        if ((threadIdx.x == 0 || threadIdx.x == 255) && blockIdx.x < 16384) g_trace2[4 * blockIdx.x + (threadIdx.x == 0 ? 2 : 3)] = gtime();
+#endif
     } else {
         const int stride32 = (int)g.row_stride;
         for (int k = threadIdx.x; k < n_all; k += n_threads) {

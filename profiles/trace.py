@@ -39,6 +39,14 @@ def trace(label, fn):
     print("  t(us)   starts  ends  resident")
     for i in range(len(hs)):
         print(f"  {edges[i]:5.0f}  {hs[i]:6d} {he[i]:6d} {act[i]:6d}")
+    if "decode" in label:
+        t2 = np.zeros(4 * n, np.uint64)
+        L.fri_debug_trace2.argtypes = [C.c_void_p, C.c_size_t]
+        assert L.fri_debug_trace2(t2.ctypes.data, t2.size) == 0
+        t2 = (t2.reshape(n, 4).astype(np.int64) - t0) / 1e3
+        ok = t2[:, 0] > 0
+        print(f"  write-out, interior CTAs: barrier -> full chunks issued  thread0 {np.mean((t2[:,0]-t[:,1])[ok]):.2f} us, thread255 {np.mean((t2[:,1]-t[:,1])[ok]):.2f} us; "
+              f"-> mixed done thread0 {np.mean((t2[:,2]-t[:,1])[ok]):.2f}, thread255 {np.mean((t2[:,3]-t[:,1])[ok]):.2f}; -> CTA end {np.mean((t[:,2]-t[:,1])[ok]):.2f}")
     first = np.argsort(t[:, 0])[:592]
     print(f"  first wave: phase1 {np.mean(t[first,1]-t[first,0]):.2f} us, phase2 {np.mean(t[first,2]-t[first,1]):.2f} us; later: phase1 {np.mean(np.delete(t[:,1]-t[:,0], first)):.2f} phase2 {np.mean(np.delete(t[:,2]-t[:,1], first)):.2f}")
 
