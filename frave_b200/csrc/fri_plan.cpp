@@ -54,10 +54,17 @@ void fractal_mask(int depth, int32_t cx, int32_t cy, int32_t width, int32_t heig
     // root's low-pass value (:221), Some under the same condition as the root's residue.
     const size_t n = (size_t)1 << depth;
     std::vector<uint8_t> some(2 * n);
-    for (size_t k = 0; k < n; ++k) {
-        Vec2 o = digit_sum((unsigned)k, 0, depth);
-        int x = cx + o.x, y = cy + o.y;
-        some[n + k] = x >= 0 && y >= 0 && x < width && y < height;
+    {
+        // leaf k sits at centre + sum_j bit_j(k) * LITERALS[j]: build the offsets by doubling
+        std::vector<Vec2> off(n);
+        off[0] = Vec2{0, 0};
+        for (int j = 0; j < depth; ++j)
+            for (size_t k = 0; k < ((size_t)1 << j); ++k)
+                off[k + ((size_t)1 << j)] = Vec2{off[k].x + kLiterals[j].x, off[k].y + kLiterals[j].y};
+        for (size_t k = 0; k < n; ++k) {
+            const int x = cx + off[k].x, y = cy + off[k].y;
+            some[n + k] = x >= 0 && y >= 0 && x < width && y < height;
+        }
     }
     for (size_t pos = n - 1; pos >= 1; --pos) some[pos] = some[2 * pos] | some[2 * pos + 1];
     std::memset(out, 0, sizeof(uint32_t) * (n / 32));
