@@ -40,6 +40,10 @@ _SYMBOLS = [
     ("fri_decode_tq_device", C.c_int, [_P, _P, C.c_uint32, _P, C.c_int, _P, _P]),
     ("fri_encode_tq", C.c_int, [_P, _P, C.c_uint32, _P, _P]),
     ("fri_decode_tq", C.c_int, [_P, _P, C.c_uint32, _P, C.c_int, _P]),
+    ("fri_plan_emission_count", C.c_uint64, [_P]),
+    ("fri_plan_emission_order", C.c_int, [_P, _P]),
+    ("fri_emit_device", C.c_int, [_P, _P, C.c_uint32, _P, _P]),
+    ("fri_encode_tq_emit", C.c_int, [_P, _P, C.c_uint32, _P, _P]),
     ("fri_host_alloc", C.c_int, [C.POINTER(_P), C.c_size_t]),
     ("fri_host_free", None, [_P]),
     ("fri_plan_last_launches", C.c_uint32, [_P]),
@@ -234,6 +238,36 @@ class Plan:
         qa, qp = _q_array(q)
         mode = FRI_DEQUANT_MULTIPLY if multiply else FRI_DEQUANT_DIVIDE
         _check(lib().fri_decode_tq(self._h, cf.ctypes.data, n, qp, mode, out.ctypes.data))
+        return out
+
+    # ---- emission order (depth 9) -----------------------------------------------------------------
+    def emission_order(self) -> np.ndarray:
+        """uint32 [n_tiles * 512]: tile_index * 512 + coefficient_index in the order the reference's
+        entropy coder consumes one channel (None slots included).  Raises FriError(FRI_E_UNSUPPORTED)
+        where the reference's own scan asserts."""
+        out = np.empty(self.n_tiles << self.depth, np.uint32)
+        _check(lib().fri_plan_emission_order(self._h, out.ctypes.data))
+        return out
+
+    def emission_count(self) -> int:
+        n = int(lib().fri_plan_emission_count(self._h))
+        if n == 0 and self.n_tiles:
+            _check(lib().fri_plan_emission_order(self._h, np.empty(self.n_tiles << self.depth, np.uint32).ctypes.data))
+        return n
+
+    def emit_device(self, d_coefs: int, n_frames: int, d_out: int, stream: int = 0) -> None:
+        _check(lib().fri_emit_device(self._h, d_coefs, n_frames, d_out, stream))
+
+    def encode_emit(self, pixels: np.ndarray, q=None, out: np.ndarray | None = None) -> np.ndarray:
+        """HWC pixels [F, H, W, C] -> int32 [F, C, emission_count()]: the quantized Some coefficients
+        of every channel in emission order."""
+        px, n = self._frames(pixels)
+        cnt = self.emission_count()
+        if out is None:
+            out = np.empty((n, self.channels, cnt), np.int32)
+        assert out.dtype == np.int32 and out.flags.c_contiguous and out.shape == (n, self.channels, cnt)
+        qa, qp = _q_array(q)
+        _check(lib().fri_encode_tq_emit(self._h, px.ctypes.data, n, qp, out.ctypes.data))
         return out
 
     # ---- device-resident entry points (raw device pointers, e.g. torch.Tensor.data_ptr()) -----

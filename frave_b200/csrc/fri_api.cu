@@ -3,6 +3,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -62,6 +63,14 @@ struct fri_plan {
     int32_t *d_dc_shared = nullptr;  // low-pass scratch for the *_device entry points (depth > 9)
     size_t d_dc_frames = 0;
     uint32_t last_launches = 0;
+    // emission order (computed on first use)
+    int emit_state = 0;  // 0 = not computed, 1 = ready, -1 = failed (emit_error)
+    std::string emit_error;
+    std::vector<uint32_t> emit_order;  // [n_tiles * 512], None slots included
+    std::vector<uint32_t> emit_src;    // Some slots only
+    void *d_emit_src = nullptr;
+    int32_t *d_emit_tmp = nullptr;      // device staging for fri_encode_tq_emit
+    size_t d_emit_tmp_frames = 0;
 };
 
 namespace {
@@ -216,6 +225,8 @@ void fri_plan_destroy(fri_plan *p)
         if (p->d_tile_unit) cudaFree(p->d_tile_unit);
         if (p->d_chunk_mask) cudaFree(p->d_chunk_mask);
         if (p->d_chunk_list) cudaFree(p->d_chunk_list);
+        if (p->d_emit_src) cudaFree(p->d_emit_src);
+        if (p->d_emit_tmp) cudaFree(p->d_emit_tmp);
         if (p->d_stage_list) cudaFree(p->d_stage_list);
     }
     delete p;
@@ -356,6 +367,120 @@ int fri_decode_tq(fri_plan *p, const int32_t *coefs, uint32_t n_frames, const in
         FRI_CUDA(launch_decode(g, p->tables, qp, s.d_coefs, 1, s.d_pixels, s.d_dc, s.stream, &p->last_launches));
         FRI_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(pixels) + (size_t)f * g.frame_bytes, s.d_pixels,
                                  (size_t)g.frame_bytes, cudaMemcpyDeviceToHost, s.stream));
+    }
+    for (auto &s : p->slots) FRI_CUDA(cudaStreamSynchronize(s.stream));
+    return FRI_OK;
+}
+
+/* ---- emission order ------------------------------------------------ */
+static int ensure_emission(fri_plan *p)
+{
+    if (!p) return fail(FRI_E_INVALID, "plan is NULL");
+    if (p->emit_state == 0) {
+        std::string err;
+        try {
+            err = build_emission_order(p->plan, p->emit_order);
+        } catch (const std::bad_alloc &) {
+            err = "out of host memory";
+        }
+        if (!err.empty()) {
+            p->emit_state = -1;
+            p->emit_error = err;
+        } else {
+            // drop the slots the reference skips (`if let Some(value)`, entropy_coding.rs:287,298,314)
+            const Geometry &g = p->plan.geo;
+            std::vector<uint32_t> mask(kTileLeaves / 32);
+            std::vector<uint8_t> some((size_t)g.n_fractals * kTileLeaves);
+            for (int32_t t = 0; t < g.n_fractals; ++t) {
+                if (p->plan.full[t]) {
+                    std::fill(some.begin() + (size_t)t * kTileLeaves, some.begin() + (size_t)(t + 1) * kTileLeaves, 1);
+                    continue;
+                }
+                fractal_mask(g.depth, p->plan.centers[2 * t], p->plan.centers[2 * t + 1], g.width, g.height, mask.data());
+                for (int i = 0; i < kTileLeaves; ++i) some[(size_t)t * kTileLeaves + i] = (mask[i >> 5] >> (i & 31)) & 1u;
+            }
+            p->emit_src.clear();
+            p->emit_src.reserve(p->emit_order.size());
+            for (uint32_t v : p->emit_order)
+                if (some[v]) p->emit_src.push_back(v);
+            p->emit_state = 1;
+        }
+    }
+    if (p->emit_state < 0) return fail(FRI_E_UNSUPPORTED, "%s", p->emit_error.c_str());
+    return FRI_OK;
+}
+
+static int ensure_emission_device(fri_plan *p)
+{
+    int rc = ensure_emission(p);
+    if (rc) return rc;
+    if (!p->d_emit_src && !p->emit_src.empty()) {
+        FRI_CUDA(cudaMalloc(&p->d_emit_src, p->emit_src.size() * sizeof(uint32_t)));
+        FRI_CUDA(cudaMemcpy(p->d_emit_src, p->emit_src.data(), p->emit_src.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+    return FRI_OK;
+}
+
+uint64_t fri_plan_emission_count(fri_plan *p)
+{
+    if (ensure_emission(p)) return 0;
+    return (uint64_t)p->emit_src.size();
+}
+
+int fri_plan_emission_order(fri_plan *p, uint32_t *order)
+{
+    if (!order) return fail(FRI_E_INVALID, "NULL argument");
+    int rc = ensure_emission(p);
+    if (rc) return rc;
+    std::memcpy(order, p->emit_order.data(), p->emit_order.size() * sizeof(uint32_t));
+    return FRI_OK;
+}
+
+int fri_emit_device(fri_plan *p, const int32_t *d_coefs, uint32_t n_frames, int32_t *d_out, void *stream)
+{
+    int rc = enter_device(p);
+    if (rc) return rc;
+    if ((rc = ensure_emission_device(p))) return rc;
+    if (n_frames == 0) return FRI_OK;
+    if (!d_coefs || !d_out) return fail(FRI_E_INVALID, "NULL device buffer");
+    p->last_launches = 0;
+    FRI_CUDA(launch_emit(p->plan.geo, static_cast<const uint32_t *>(p->d_emit_src), p->emit_src.size(), d_coefs, n_frames, d_out,
+                         static_cast<cudaStream_t>(stream), &p->last_launches));
+    return FRI_OK;
+}
+
+int fri_encode_tq_emit(fri_plan *p, const void *pixels, uint32_t n_frames, const int32_t *q, int32_t *out)
+{
+    int rc = enter_device(p);
+    if (rc) return rc;
+    if ((rc = check_q(q))) return rc;
+    if ((rc = ensure_emission_device(p))) return rc;
+    if (n_frames == 0) return FRI_OK;
+    if (!pixels || !out) return fail(FRI_E_INVALID, "NULL host buffer");
+    if ((rc = ensure_slots(p))) return rc;
+    const Geometry &g = p->plan.geo;
+    const size_t count = p->emit_src.size();
+    if (p->d_emit_tmp_frames < (size_t)kSlots) {
+        if (p->d_emit_tmp) cudaFree(p->d_emit_tmp);
+        p->d_emit_tmp = nullptr;
+        p->d_emit_tmp_frames = 0;
+        FRI_CUDA(cudaMalloc(&p->d_emit_tmp, (size_t)kSlots * g.channels * count * sizeof(int32_t) + 16));
+        p->d_emit_tmp_frames = kSlots;
+    }
+    QuantParams qp;
+    make_quant_params(qp, q, 0);
+    p->last_launches = 0;
+    const size_t per_frame = (size_t)g.channels * count;
+    for (uint32_t f = 0; f < n_frames; ++f) {
+        Slot &s = p->slots[f % kSlots];
+        int32_t *d_emit = p->d_emit_tmp + (size_t)(f % kSlots) * per_frame;
+        FRI_CUDA(cudaMemcpyAsync(s.d_pixels, static_cast<const uint8_t *>(pixels) + (size_t)f * g.frame_bytes,
+                                 (size_t)g.frame_bytes, cudaMemcpyHostToDevice, s.stream));
+        FRI_CUDA(launch_encode(g, p->tables, qp, s.d_pixels, 1, s.d_coefs, s.d_dc, s.stream, &p->last_launches));
+        FRI_CUDA(launch_emit(g, static_cast<const uint32_t *>(p->d_emit_src), count, s.d_coefs, 1, d_emit, s.stream,
+                             &p->last_launches));
+        FRI_CUDA(cudaMemcpyAsync(out + (size_t)f * per_frame, d_emit, per_frame * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                 s.stream));
     }
     for (auto &s : p->slots) FRI_CUDA(cudaStreamSynchronize(s.stream));
     return FRI_OK;

@@ -959,6 +959,23 @@ fri_coarse_inverse_kernel(const __grid_constant__ QuantParams qp, int sub_bits, 
     for (int i = threadIdx.x; i < n; i += kCoarseThreads) out[i] = src[i];
 }
 
+// ------------------------------------------------------------------------------------------
+// emission order: gather the quantized coefficients of every channel
+// into the order the reference's entropy coder consumes them, `None` slots dropped
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+fri_emit_kernel(const uint32_t *__restrict__ src, unsigned long long count, int channels, int n_tiles,
+                const int32_t *__restrict__ coefs, int32_t *__restrict__ out)
+{
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int ch = blockIdx.y, frame = blockIdx.z;
+    const uint32_t s = __ldg(src + i);
+    const size_t tile = s >> kBaseDepth, pos = s & (kTileLeaves - 1);
+    const int32_t v = __ldg(coefs + ((((size_t)frame * n_tiles + tile) * channels + ch) << kBaseDepth) + pos);
+    __stcs(out + ((size_t)frame * channels + ch) * count + i, v);
+}
+
 template <typename K>
 cudaError_t set_smem(K kernel, size_t bytes)
 {
@@ -1080,6 +1097,21 @@ cudaError_t launch_decode(const Geometry &g, const DeviceTables &t, const QuantP
         else if (g.channels == 1 && g.sample_bytes == 2) FRI_LAUNCH(1, uint16_t);
         else FRI_LAUNCH(3, uint16_t);
 #undef FRI_LAUNCH
+        if (launches) ++*launches;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_emit(const Geometry &g, const uint32_t *d_src, uint64_t count, const int32_t *d_coefs, uint32_t n_frames,
+                        int32_t *d_out, cudaStream_t stream, uint32_t *launches)
+{
+    if (count == 0 || n_frames == 0) return cudaSuccess;
+    for (uint32_t f0 = 0; f0 < n_frames; f0 += 65535u) {  // gridDim.z limit
+        const uint32_t nf = n_frames - f0 < 65535u ? n_frames - f0 : 65535u;
+        const dim3 grid((unsigned)((count + 255) / 256), (unsigned)g.channels, nf);
+        fri_emit_kernel<<<grid, 256, 0, stream>>>(d_src, count, g.channels, g.n_fractals,
+                                                  d_coefs + (int64_t)f0 * g.coefs_per_frame,
+                                                  d_out + (size_t)f0 * g.channels * count);
         if (launches) ++*launches;
     }
     return cudaGetLastError();

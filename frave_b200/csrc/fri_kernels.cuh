@@ -110,4 +110,8 @@ cudaError_t launch_decode(const Geometry &g, const DeviceTables &t, const QuantP
                           uint32_t n_frames, void *d_pixels, int32_t *d_dc, cudaStream_t stream,
                           uint32_t *launches);
 
+// Gathers coefficients into emission order: out[frame][ch][i] = coefs[frame][src[i] >> 9][ch][src[i] & 511].
+cudaError_t launch_emit(const Geometry &g, const uint32_t *d_src, uint64_t count, const int32_t *d_coefs, uint32_t n_frames,
+                        int32_t *d_out, cudaStream_t stream, uint32_t *launches);
+
 }  // namespace fri

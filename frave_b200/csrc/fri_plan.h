@@ -78,6 +78,13 @@ struct Plan {
 std::string build_plan(Plan &plan, uint32_t width, uint32_t height, uint32_t channels, uint32_t depth,
                        uint32_t sample_bytes, int group_a, int group_b);
 
+// Order in which the reference's entropy coder consumes the coefficients of one channel
+// (entropy_coding.rs:283-329 over sort_lattice, wavelet_transform.rs:505-705), depth 9 only:
+// order[i] = tile_index * 512 + coefficient_index, n_tiles * 512 entries (None slots included):
+// all DCs, all roots, then levels 1..8, each in scan order.  Returns an error message if the
+// reference's own scan would fail its assertion (:701) for this image size.
+std::string build_emission_order(const Plan &plan, std::vector<uint32_t> &order);
+
 // 2^depth-bit Some/None mask of the fractal centred at (cx, cy): bit i <=> coefficient i is
 // Some.  out has 2^depth / 32 words.
 void fractal_mask(int depth, int32_t cx, int32_t cy, int32_t width, int32_t height, uint32_t *out);

@@ -116,6 +116,25 @@ int fri_encode_tq(fri_plan *plan, const void *pixels, uint32_t n_frames, const i
 int fri_decode_tq(fri_plan *plan, const int32_t *coefs, uint32_t n_frames, const int32_t *q, int dequant_mode,
                   void *pixels);
 
+/*
+ * Emission order (depth 9 only) — the order in which the reference's entropy coder consumes the
+ * coefficients of one channel: entropy_coding.rs:283-329 walking sort_lattice
+ * (wavelet_transform.rs:505-705): every DC, every root residue, then levels 1..8 in scan order.
+ *   fri_plan_emission_order  order[n_tiles * 512]: entry i = tile_index * 512 + coefficient_index
+ *                            (tile_index in plan order), `None` slots included.
+ *   fri_plan_emission_count  number of `Some` slots = length of one channel's emitted stream.
+ *   fri_emit_device          d_out[n_frames][C][count] <- coefficients in emission order with the
+ *                            `None` slots dropped (what the three scans push, :287 / :298 / :314).
+ *   fri_encode_tq_emit       host pixels -> host emitted streams: transform + quantization +
+ *                            emission gather on the device, one D2H copy per frame.
+ * All of them fail with FRI_E_UNSUPPORTED (and say so in fri_last_error) for the image sizes on
+ * which the reference's own scan fails its assertion at wavelet_transform.rs:701, e.g. 257x300.
+ */
+uint64_t fri_plan_emission_count(fri_plan *plan);
+int fri_plan_emission_order(fri_plan *plan, uint32_t *order);
+int fri_emit_device(fri_plan *plan, const int32_t *d_coefs, uint32_t n_frames, int32_t *d_out, void *stream);
+int fri_encode_tq_emit(fri_plan *plan, const void *pixels, uint32_t n_frames, const int32_t *q, int32_t *out);
+
 /* Pinned host memory (cudaHostAlloc) for the host-buffer entry points. */
 int fri_host_alloc(void **out, size_t bytes);
 void fri_host_free(void *p);

@@ -49,3 +49,29 @@ run(16384, 16384, 1, 9, 2, reps=5)
 for d in (16, 20, 24):
     run(16384, 16384, 1, d, 2, reps=3)
 run(3840, 2160, 3, 9, 1, frames=32, reps=5)
+
+
+def run_emit(w, h, c, frames=1, reps=10):
+    """next-1: emission-order gather on device-resident coefficients."""
+    plan = capi.Plan(w, h, c)
+    cnt = plan.emission_count()
+    co = torch.randint(-255, 256, (frames,) + plan.coef_shape, device=dev, dtype=torch.int32)
+    out = torch.empty((frames, c, cnt), dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(2):
+        plan.emit_device(co.data_ptr(), frames, out.data_ptr(), st)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        plan.emit_device(co.data_ptr(), frames, out.data_ptr(), st)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    print(json.dumps({"emit": f"{w}x{h}x{c}", "frames": frames, "count_per_channel": cnt, "us": round(ms * 1e3, 1),
+                      "GBps_alg(8B per coefficient)": round(8 * cnt * c * frames / ms / 1e6), "MPix_s": round(w * h * frames / ms / 1e3)}))
+    plan.close()
+
+
+run_emit(4096, 4096, 3)
+run_emit(3840, 2160, 3, frames=8)

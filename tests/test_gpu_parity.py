@@ -216,6 +216,36 @@ def test_full_size_16384_u16_roundtrip():
     _device_roundtrip(torch, 16384, 16384, 1, 1, np.uint16, seed=4)
 
 
+@pytest.mark.parametrize("shape", [(48, 64, 1), (131, 77, 3), (270, 480, 3), (512, 512, 1)], ids=lambda s: "x".join(map(str, s)))
+def test_emitted_streams_follow_the_reference_scan_order(shape):
+    """fri_encode_tq_emit / fri_emit_device: quantized Some coefficients of every channel in the
+    order entropy_coding.rs:283-329 pushes them, against the oracle (coefficients from
+    oracle/fri_oracle.c, order from oracle/fri_order_np.py)."""
+    from oracle import fri_order_np as R
+    torch = pytest.importorskip("torch")
+    h, w, c = shape
+    frames = np.stack([uniform_image(h, w, c, seed=90 + i) for i in range(2)])
+    q = smallest_layer_q(3)
+    with capi.Plan(w, h, c) as plan:
+        order = R.emission_order(plan.centers(), w, h)
+        src = order[:, 0] * 512 + order[:, 1]
+        some = plan.masks().reshape(-1)
+        src = src[some[src]]
+        assert len(src) == plan.emission_count()
+        got = plan.encode_emit(frames, q)
+        assert plan.last_launches == 2 * 2  # per frame: transform + quant kernel, emission gather
+        for f in range(2):
+            want, _ = oracle_encode(plan, frames[f], q)
+            for ch in range(c):
+                assert np.array_equal(got[f, ch], want[:, ch, :].reshape(-1)[src])
+        dev = torch.device("cuda", 0)
+        d_coefs = torch.from_numpy(plan.encode(frames, q)).to(dev)
+        d_out = torch.empty((2, c, plan.emission_count()), dtype=torch.int32, device=dev)
+        plan.emit_device(d_coefs.data_ptr(), 2, d_out.data_ptr())
+        torch.cuda.synchronize()
+        assert np.array_equal(d_out.cpu().numpy(), got)
+
+
 def test_stage_interface_mirrors_reference_pipeline():
     img = smooth_image(120, 200, 3, seed=1)
     raster = stages.RasterImage.from_array(img, stages.ColorSpace.RGB)

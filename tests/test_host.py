@@ -83,6 +83,45 @@ def test_deep_plan_is_a_union_of_base_tiles():
             assert p.launch_info()["n_base_tiles"] == p.n_tiles << (depth - 9)
 
 
+@pytest.mark.parametrize("shape", [(10, 10), (64, 48), (100, 37), (131, 77), (480, 270), (300, 400)])
+def test_emission_order_matches_the_dict_based_restatement(shape):
+    """the plan's arithmetic scan against oracle/fri_order_np.py (a literal
+    restatement of sort_lattice / scan_level with hash maps) — same order, same Some count."""
+    from oracle import fri_order_np as R
+    w, h = shape
+    with capi.Plan(w, h, 3, device=-1) as p:
+        centers = p.centers()
+        want = R.emission_order(centers, w, h)
+        got = p.emission_order()
+        assert np.array_equal(got, want[:, 0] * 512 + want[:, 1])
+        assert sorted(got.tolist()) == list(range(p.n_tiles * 512))  # every (tile, coefficient) exactly once
+        assert p.emission_count() == int(p.masks().sum())
+        # entropy_coding.rs:283-329: first every DC, then every root residue, both in level-0 order
+        n = p.n_tiles
+        assert (got[:n] % 512 == 0).all() and (got[n:2 * n] % 512 == 1).all()
+        assert np.array_equal(got[:n] // 512, got[n:2 * n] // 512)
+        for level in range(1, 9):
+            blk = got[n << level:n << (level + 1)] % 512
+            assert blk.min() == 1 << level and blk.max() == (2 << level) - 1
+
+
+def test_emission_order_mirrors_the_reference_assertion():
+    """For some sizes the reference's scan misses a node and its assert_eq! at
+    wavelet_transform.rs:701 would panic; both restatements must agree on that too."""
+    from oracle import fri_order_np as R
+    w, h = 257, 300
+    with capi.Plan(w, h, 3, device=-1) as p:
+        with pytest.raises(AssertionError):
+            R.emission_order(p.centers(), w, h)
+        with pytest.raises(capi.FriError) as e:
+            p.emission_order()
+        assert e.value.code == capi.FRI_E_UNSUPPORTED and "701" in str(e.value)
+    with capi.Plan(300, 200, 1, depth=10, device=-1) as p:
+        with pytest.raises(capi.FriError) as e:
+            p.emission_order()
+        assert e.value.code == capi.FRI_E_UNSUPPORTED
+
+
 def test_invalid_arguments_and_no_cpu_fallback():
     for args in [(0, 5, 1), (5, 0, 1), (5, 5, 2), (5, 5, 4)]:
         with pytest.raises(capi.FriError) as e:
