@@ -42,13 +42,26 @@ int cuda_fail(cudaError_t e, const char *what)
         if (e__ != cudaSuccess) return cuda_fail(e__, #call);       \
     } while (0)
 
-constexpr int kSlots = 3;  // frames in flight in the host-buffer entry points
+constexpr int kSlots = 2;      // frames resident on the device in the host-buffer entry points
+constexpr int kMaxBands = 8;   // a frame is streamed through the device in up to this many bands of groups
 
+// Device buffers of one frame in flight.
 struct Slot {
-    cudaStream_t stream = nullptr;
     void *d_pixels = nullptr;
     int32_t *d_coefs = nullptr;
     int32_t *d_dc = nullptr;
+    cudaEvent_t compute_done = nullptr;  // last kernel of the frame that used the slot
+    cudaEvent_t out_done = nullptr;      // last device-to-host copy of that frame
+    bool used = false;
+};
+
+// The host-buffer entry points run a three-stage pipeline: copies in, kernels, copies out, each on
+// its own in-order stream and chained by events, so host-to-device and device-to-host traffic
+// overlap (PCIe is full duplex) — across the bands of one frame and across frames.
+struct Pipeline {
+    cudaStream_t in = nullptr, compute = nullptr, out = nullptr;
+    cudaEvent_t in_ready[kMaxBands] = {};
+    cudaEvent_t band_done[kMaxBands] = {};
 };
 
 }  // namespace
@@ -59,6 +72,7 @@ struct fri_plan {
     DeviceTables tables;
     void *d_groups = nullptr, *d_tile_unit = nullptr, *d_chunk_mask = nullptr, *d_chunk_list = nullptr, *d_stage_list = nullptr;
     Slot slots[kSlots];
+    Pipeline pipe;
     bool slots_ready = false;
     int32_t *d_dc_shared = nullptr;  // low-pass scratch for the *_device entry points (depth > 9)
     size_t d_dc_frames = 0;
@@ -115,14 +129,60 @@ int ensure_slots(fri_plan *p)
 {
     if (p->slots_ready) return FRI_OK;
     const Geometry &g = p->plan.geo;
+    Pipeline &pl = p->pipe;
+    FRI_CUDA(cudaStreamCreateWithFlags(&pl.in, cudaStreamNonBlocking));
+    FRI_CUDA(cudaStreamCreateWithFlags(&pl.compute, cudaStreamNonBlocking));
+    FRI_CUDA(cudaStreamCreateWithFlags(&pl.out, cudaStreamNonBlocking));
+    for (int k = 0; k < kMaxBands; ++k) {
+        FRI_CUDA(cudaEventCreateWithFlags(&pl.in_ready[k], cudaEventDisableTiming));
+        FRI_CUDA(cudaEventCreateWithFlags(&pl.band_done[k], cudaEventDisableTiming));
+    }
     for (auto &s : p->slots) {
-        FRI_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         FRI_CUDA(cudaMalloc(&s.d_pixels, (size_t)g.frame_bytes + 16));
         FRI_CUDA(cudaMalloc(&s.d_coefs, (size_t)g.coefs_per_frame * sizeof(int32_t) + 16));
         if (g.sub_bits > 0) FRI_CUDA(cudaMalloc(&s.d_dc, dc_elems_per_frame(g) * sizeof(int32_t)));
+        FRI_CUDA(cudaEventCreateWithFlags(&s.compute_done, cudaEventDisableTiming));
+        FRI_CUDA(cudaEventCreateWithFlags(&s.out_done, cudaEventDisableTiming));
     }
     p->slots_ready = true;
     return FRI_OK;
+}
+
+// Splits the plan's groups (ordered top to bottom) into bands of consecutive groups.
+struct Band {
+    int g0, g1;        // groups [g0, g1)
+    size_t t0, t1;     // base tiles [t0, t1) == fractals at depth 9
+    int row_hi;        // encode: pixel rows [0, row_hi) must be on the device before the band runs
+    int final_rows;    // decode: pixel rows [0, final_rows) are complete once the band has run
+};
+
+int make_bands(const fri_plan *p, Band bands[kMaxBands])
+{
+    const Plan &pl = p->plan;
+    const Geometry &g = pl.geo;
+    int n = g.sub_bits > 0 ? 1 : std::max(1, std::min(kMaxBands, g.n_groups / 256));
+    if (const char *env = std::getenv("FRI_BANDS")) n = std::max(1, std::min(kMaxBands, std::atoi(env)));  // tuning knob
+    n = std::min(n, std::max(1, g.n_groups));
+    for (int k = 0; k < n; ++k) {
+        Band &b = bands[k];
+        b.g0 = (int)((int64_t)g.n_groups * k / n);
+        b.g1 = (int)((int64_t)g.n_groups * (k + 1) / n);
+        b.t0 = pl.groups[b.g0].tile_base;
+        b.t1 = b.g1 < g.n_groups ? pl.groups[b.g1].tile_base : (size_t)g.n_base_tiles;
+        int hi = 0;
+        for (int i = b.g0; i < b.g1; ++i) hi = std::max(hi, pl.groups[i].y0 + g.region_h);
+        b.row_hi = k == n - 1 ? g.height : std::max(0, std::min(g.height, hi));
+    }
+    for (int k = 0; k < n; ++k) {
+        int lo = g.height;  // first row any later band still writes
+        for (int i = bands[k].g1; i < g.n_groups; ++i) lo = std::min(lo, pl.groups[i].y0);
+        bands[k].final_rows = k == n - 1 ? g.height : std::max(0, std::min(g.height, lo));
+    }
+    for (int k = 1; k < n; ++k) {  // monotone: a band never un-finishes rows / needs fewer rows
+        bands[k].row_hi = std::max(bands[k].row_hi, bands[k - 1].row_hi);
+        bands[k].final_rows = std::max(bands[k].final_rows, bands[k - 1].final_rows);
+    }
+    return n;
 }
 
 }  // namespace
@@ -214,11 +274,19 @@ void fri_plan_destroy(fri_plan *p)
 {
     if (!p) return;
     if (p->device >= 0 && cudaSetDevice(p->device) == cudaSuccess) {
+        Pipeline &pl = p->pipe;
+        for (cudaStream_t st : {pl.in, pl.compute, pl.out})
+            if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+        for (int k = 0; k < kMaxBands; ++k) {
+            if (pl.in_ready[k]) cudaEventDestroy(pl.in_ready[k]);
+            if (pl.band_done[k]) cudaEventDestroy(pl.band_done[k]);
+        }
         for (auto &s : p->slots) {
-            if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
             if (s.d_pixels) cudaFree(s.d_pixels);
             if (s.d_coefs) cudaFree(s.d_coefs);
             if (s.d_dc) cudaFree(s.d_dc);
+            if (s.compute_done) cudaEventDestroy(s.compute_done);
+            if (s.out_done) cudaEventDestroy(s.out_done);
         }
         if (p->d_dc_shared) cudaFree(p->d_dc_shared);
         if (p->d_groups) cudaFree(p->d_groups);
@@ -327,19 +395,49 @@ int fri_encode_tq(fri_plan *p, const void *pixels, uint32_t n_frames, const int3
     if (!pixels || !coefs) return fail(FRI_E_INVALID, "NULL host buffer");
     if ((rc = ensure_slots(p))) return rc;
     const Geometry &g = p->plan.geo;
+    Pipeline &pl = p->pipe;
     QuantParams qp;
     make_quant_params(qp, q, 0);
     p->last_launches = 0;
-    const size_t coef_bytes = (size_t)g.coefs_per_frame * sizeof(int32_t);
+    Band bands[kMaxBands];
+    const int n_bands = make_bands(p, bands);
+    const size_t block = (size_t)g.channels << g.depth;  // coefficients per fractal
     for (uint32_t f = 0; f < n_frames; ++f) {
         Slot &s = p->slots[f % kSlots];
-        FRI_CUDA(cudaMemcpyAsync(s.d_pixels, static_cast<const uint8_t *>(pixels) + (size_t)f * g.frame_bytes,
-                                 (size_t)g.frame_bytes, cudaMemcpyHostToDevice, s.stream));
-        FRI_CUDA(launch_encode(g, p->tables, qp, s.d_pixels, 1, s.d_coefs, s.d_dc, s.stream, &p->last_launches));
-        FRI_CUDA(cudaMemcpyAsync(coefs + (size_t)f * g.coefs_per_frame, s.d_coefs, coef_bytes, cudaMemcpyDeviceToHost,
-                                 s.stream));
+        const uint8_t *src = static_cast<const uint8_t *>(pixels) + (size_t)f * g.frame_bytes;
+        int32_t *dst = coefs + (size_t)f * g.coefs_per_frame;
+        if (s.used) {  // the frame that had this slot: its kernels have read the pixels, its copies the coefficients
+            FRI_CUDA(cudaStreamWaitEvent(pl.in, s.compute_done, 0));
+            FRI_CUDA(cudaStreamWaitEvent(pl.compute, s.out_done, 0));
+        }
+        int rows_up = 0;
+        for (int k = 0; k < n_bands; ++k) {
+            const Band &b = bands[k];
+            if (b.row_hi > rows_up) {
+                FRI_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(s.d_pixels) + (size_t)rows_up * g.row_stride,
+                                         src + (size_t)rows_up * g.row_stride, (size_t)(b.row_hi - rows_up) * g.row_stride,
+                                         cudaMemcpyHostToDevice, pl.in));
+                rows_up = b.row_hi;
+            }
+            FRI_CUDA(cudaEventRecord(pl.in_ready[k], pl.in));
+            FRI_CUDA(cudaStreamWaitEvent(pl.compute, pl.in_ready[k], 0));
+            FRI_CUDA(launch_encode(g, p->tables, qp, s.d_pixels, 1, s.d_coefs, s.d_dc, pl.compute, &p->last_launches, b.g0, b.g1));
+            FRI_CUDA(cudaEventRecord(pl.band_done[k], pl.compute));
+            FRI_CUDA(cudaStreamWaitEvent(pl.out, pl.band_done[k], 0));
+            if (g.sub_bits == 0) {
+                FRI_CUDA(cudaMemcpyAsync(dst + b.t0 * block, s.d_coefs + b.t0 * block, (b.t1 - b.t0) * block * sizeof(int32_t),
+                                         cudaMemcpyDeviceToHost, pl.out));
+            } else {  // deep trees: one band, the coarse kernel has touched every fractal's top levels
+                FRI_CUDA(cudaMemcpyAsync(dst, s.d_coefs, (size_t)g.coefs_per_frame * sizeof(int32_t), cudaMemcpyDeviceToHost, pl.out));
+            }
+        }
+        FRI_CUDA(cudaEventRecord(s.compute_done, pl.compute));
+        FRI_CUDA(cudaEventRecord(s.out_done, pl.out));
+        s.used = true;
     }
-    for (auto &s : p->slots) FRI_CUDA(cudaStreamSynchronize(s.stream));
+    FRI_CUDA(cudaStreamSynchronize(pl.out));
+    FRI_CUDA(cudaStreamSynchronize(pl.compute));
+    FRI_CUDA(cudaStreamSynchronize(pl.in));
     return FRI_OK;
 }
 
@@ -354,21 +452,51 @@ int fri_decode_tq(fri_plan *p, const int32_t *coefs, uint32_t n_frames, const in
     if (!pixels || !coefs) return fail(FRI_E_INVALID, "NULL host buffer");
     if ((rc = ensure_slots(p))) return rc;
     const Geometry &g = p->plan.geo;
+    Pipeline &pl = p->pipe;
     QuantParams qp;
     make_quant_params(qp, q, dequant_mode == FRI_DEQUANT_MULTIPLY);
     p->last_launches = 0;
-    const size_t coef_bytes = (size_t)g.coefs_per_frame * sizeof(int32_t);
+    Band bands[kMaxBands];
+    const int n_bands = make_bands(p, bands);
+    const size_t block = (size_t)g.channels << g.depth;
     const bool need_zero = p->plan.pixels_covered != (uint64_t)g.width * g.height;
     for (uint32_t f = 0; f < n_frames; ++f) {
         Slot &s = p->slots[f % kSlots];
-        FRI_CUDA(cudaMemcpyAsync(s.d_coefs, coefs + (size_t)f * g.coefs_per_frame, coef_bytes, cudaMemcpyHostToDevice,
-                                 s.stream));
-        if (need_zero) FRI_CUDA(cudaMemsetAsync(s.d_pixels, 0, (size_t)g.frame_bytes, s.stream));
-        FRI_CUDA(launch_decode(g, p->tables, qp, s.d_coefs, 1, s.d_pixels, s.d_dc, s.stream, &p->last_launches));
-        FRI_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(pixels) + (size_t)f * g.frame_bytes, s.d_pixels,
-                                 (size_t)g.frame_bytes, cudaMemcpyDeviceToHost, s.stream));
+        const int32_t *src = coefs + (size_t)f * g.coefs_per_frame;
+        uint8_t *dst = static_cast<uint8_t *>(pixels) + (size_t)f * g.frame_bytes;
+        if (s.used) {  // previous user of the slot: kernels have read the coefficients, copies the pixels
+            FRI_CUDA(cudaStreamWaitEvent(pl.in, s.compute_done, 0));
+            FRI_CUDA(cudaStreamWaitEvent(pl.compute, s.out_done, 0));
+        }
+        if (need_zero) FRI_CUDA(cudaMemsetAsync(s.d_pixels, 0, (size_t)g.frame_bytes, pl.compute));
+        int rows_out = 0;
+        for (int k = 0; k < n_bands; ++k) {
+            const Band &b = bands[k];
+            if (g.sub_bits == 0) {
+                FRI_CUDA(cudaMemcpyAsync(s.d_coefs + b.t0 * block, src + b.t0 * block, (b.t1 - b.t0) * block * sizeof(int32_t),
+                                         cudaMemcpyHostToDevice, pl.in));
+            } else {
+                FRI_CUDA(cudaMemcpyAsync(s.d_coefs, src, (size_t)g.coefs_per_frame * sizeof(int32_t), cudaMemcpyHostToDevice, pl.in));
+            }
+            FRI_CUDA(cudaEventRecord(pl.in_ready[k], pl.in));
+            FRI_CUDA(cudaStreamWaitEvent(pl.compute, pl.in_ready[k], 0));
+            FRI_CUDA(launch_decode(g, p->tables, qp, s.d_coefs, 1, s.d_pixels, s.d_dc, pl.compute, &p->last_launches, b.g0, b.g1));
+            FRI_CUDA(cudaEventRecord(pl.band_done[k], pl.compute));
+            FRI_CUDA(cudaStreamWaitEvent(pl.out, pl.band_done[k], 0));
+            if (b.final_rows > rows_out) {  // rows no later band writes
+                FRI_CUDA(cudaMemcpyAsync(dst + (size_t)rows_out * g.row_stride,
+                                         static_cast<uint8_t *>(s.d_pixels) + (size_t)rows_out * g.row_stride,
+                                         (size_t)(b.final_rows - rows_out) * g.row_stride, cudaMemcpyDeviceToHost, pl.out));
+                rows_out = b.final_rows;
+            }
+        }
+        FRI_CUDA(cudaEventRecord(s.compute_done, pl.compute));
+        FRI_CUDA(cudaEventRecord(s.out_done, pl.out));
+        s.used = true;
     }
-    for (auto &s : p->slots) FRI_CUDA(cudaStreamSynchronize(s.stream));
+    FRI_CUDA(cudaStreamSynchronize(pl.out));
+    FRI_CUDA(cudaStreamSynchronize(pl.compute));
+    FRI_CUDA(cudaStreamSynchronize(pl.in));
     return FRI_OK;
 }
 
@@ -471,18 +599,32 @@ int fri_encode_tq_emit(fri_plan *p, const void *pixels, uint32_t n_frames, const
     make_quant_params(qp, q, 0);
     p->last_launches = 0;
     const size_t per_frame = (size_t)g.channels * count;
+    Pipeline &pl = p->pipe;
     for (uint32_t f = 0; f < n_frames; ++f) {
         Slot &s = p->slots[f % kSlots];
         int32_t *d_emit = p->d_emit_tmp + (size_t)(f % kSlots) * per_frame;
+        if (s.used) {
+            FRI_CUDA(cudaStreamWaitEvent(pl.in, s.compute_done, 0));
+            FRI_CUDA(cudaStreamWaitEvent(pl.compute, s.out_done, 0));
+        }
         FRI_CUDA(cudaMemcpyAsync(s.d_pixels, static_cast<const uint8_t *>(pixels) + (size_t)f * g.frame_bytes,
-                                 (size_t)g.frame_bytes, cudaMemcpyHostToDevice, s.stream));
-        FRI_CUDA(launch_encode(g, p->tables, qp, s.d_pixels, 1, s.d_coefs, s.d_dc, s.stream, &p->last_launches));
-        FRI_CUDA(launch_emit(g, static_cast<const uint32_t *>(p->d_emit_src), count, s.d_coefs, 1, d_emit, s.stream,
+                                 (size_t)g.frame_bytes, cudaMemcpyHostToDevice, pl.in));
+        FRI_CUDA(cudaEventRecord(pl.in_ready[0], pl.in));
+        FRI_CUDA(cudaStreamWaitEvent(pl.compute, pl.in_ready[0], 0));
+        FRI_CUDA(launch_encode(g, p->tables, qp, s.d_pixels, 1, s.d_coefs, s.d_dc, pl.compute, &p->last_launches));
+        FRI_CUDA(launch_emit(g, static_cast<const uint32_t *>(p->d_emit_src), count, s.d_coefs, 1, d_emit, pl.compute,
                              &p->last_launches));
+        FRI_CUDA(cudaEventRecord(pl.band_done[0], pl.compute));
+        FRI_CUDA(cudaEventRecord(s.compute_done, pl.compute));
+        FRI_CUDA(cudaStreamWaitEvent(pl.out, pl.band_done[0], 0));
         FRI_CUDA(cudaMemcpyAsync(out + (size_t)f * per_frame, d_emit, per_frame * sizeof(int32_t), cudaMemcpyDeviceToHost,
-                                 s.stream));
+                                 pl.out));
+        FRI_CUDA(cudaEventRecord(s.out_done, pl.out));
+        s.used = true;
     }
-    for (auto &s : p->slots) FRI_CUDA(cudaStreamSynchronize(s.stream));
+    FRI_CUDA(cudaStreamSynchronize(pl.out));
+    FRI_CUDA(cudaStreamSynchronize(pl.compute));
+    FRI_CUDA(cudaStreamSynchronize(pl.in));
     return FRI_OK;
 }
 

@@ -815,13 +815,13 @@ __global__ void __launch_bounds__(kThreads, FRI_ENC_MINB)
 fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ QuantParams qp,
                   const GroupDesc *__restrict__ groups, const uint32_t *__restrict__ tile_unit,
                   const uint32_t *__restrict__ stage_list, const uint8_t *__restrict__ pixels,
-                  int32_t *__restrict__ coefs, int32_t *__restrict__ dc_out, int lookahead)
+                  int32_t *__restrict__ coefs, int32_t *__restrict__ dc_out, int lookahead, int group_offset)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *region = smem;
     int32_t *scratch = reinterpret_cast<int32_t *>(smem + region_bytes(g)) + (threadIdx.x >> 5) * (C * kScratchInts);
     const uint64_t pol = table_policy();
-    const GroupDesc gd = ld_group(groups + blockIdx.x, pol);
+    const GroupDesc gd = ld_group(groups + group_offset + blockIdx.x, pol);  // the grid covers groups [group_offset, + gridDim.x)
     const int frame = blockIdx.y;
     const RegionView rv = region_view<C * (int)sizeof(S)>(g, gd, pixels + (int64_t)frame * g.frame_bytes);
     FRI_TRACE_MARK(0);
@@ -844,10 +844,10 @@ fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
     // will run in this CTA slot one residency later towards L2, one 128-byte line per thread and
     // iteration, so that its copies are served by L2 instead of waiting in the DRAM queues.
     if (lookahead > 0) {
-        const int64_t target = (int64_t)frame * g.n_groups + blockIdx.x + lookahead;
-        if (target < (int64_t)gridDim.y * g.n_groups) {
-            const int tf = (int)(target / g.n_groups);
-            const GroupDesc tg = ld_group(groups + (target - (int64_t)tf * g.n_groups), pol);
+        const int64_t target = (int64_t)frame * gridDim.x + blockIdx.x + lookahead;  // linear CTA index in this launch
+        if (target < (int64_t)gridDim.y * gridDim.x) {
+            const int tf = (int)(target / gridDim.x);
+            const GroupDesc tg = ld_group(groups + group_offset + (target - (int64_t)tf * gridDim.x), pol);
             const int lines_per_row = (g.row_bytes + 127) / 128 + 1;
             const int y_lo = max(tg.y0, 0), y_hi = min(tg.y0 + g.region_h, g.height);
             const int64_t xb = min(max((int64_t)tg.x0 * (C * (int)sizeof(S)), (int64_t)0), g.row_stride - 1);
@@ -874,13 +874,14 @@ __global__ void __launch_bounds__(kThreads, FRI_DEC_MINB)
 fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ QuantParams qp,
                   const GroupDesc *__restrict__ groups, const uint32_t *__restrict__ tile_unit,
                   const uint32_t *__restrict__ chunk_list, const uint16_t *__restrict__ chunk_mask,
-                  const int32_t *__restrict__ coefs, const int32_t *__restrict__ dc_in, uint8_t *__restrict__ pixels)
+                  const int32_t *__restrict__ coefs, const int32_t *__restrict__ dc_in, uint8_t *__restrict__ pixels,
+                  int group_offset)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *region = smem;
     int32_t *scratch = reinterpret_cast<int32_t *>(smem + region_bytes(g)) + (threadIdx.x >> 5) * (C * kScratchInts);
     const uint64_t pol = table_policy();
-    const GroupDesc gd = ld_group(groups + blockIdx.x, pol);
+    const GroupDesc gd = ld_group(groups + group_offset + blockIdx.x, pol);
     const int frame = blockIdx.y;
     const RegionView rv = region_view<C * (int)sizeof(S)>(g, gd, pixels + (int64_t)frame * g.frame_bytes);
     FRI_TRACE_MARK(0);
@@ -1030,25 +1031,29 @@ int resident_ctas(const Geometry &g)
 
 cudaError_t launch_encode(const Geometry &g, const DeviceTables &t, const QuantParams &qp, const void *d_pixels,
                           uint32_t n_frames, int32_t *d_coefs, int32_t *d_dc, cudaStream_t stream,
-                          uint32_t *launches)
+                          uint32_t *launches, int group_begin, int group_end)
 {
-    if (n_frames == 0 || g.n_groups == 0) return cudaSuccess;
+    if (group_end < 0) group_end = g.n_groups;
+    const int n_groups = group_end - group_begin;
+    const bool whole = group_begin == 0 && group_end == g.n_groups;
+    if (n_frames == 0 || n_groups <= 0) return cudaSuccess;
     const size_t smem = kernel_smem_bytes(g);
     int lookahead = resident_ctas(g);  // prefetch distance: the group that will reuse this CTA's slot
     if (const char *env = std::getenv("FRI_LOOKAHEAD")) lookahead = std::atoi(env);  // tuning knob
+    if (!whole) lookahead = 0;  // banded host pipeline: rows of later groups may not be on the device yet
     const uint8_t *px = static_cast<const uint8_t *>(d_pixels);
     for (uint32_t f0 = 0; f0 < n_frames; f0 += 65535u) {  // gridDim.y limit
         const uint32_t nf = n_frames - f0 < 65535u ? n_frames - f0 : 65535u;
-        const dim3 grid((unsigned)g.n_groups, nf);
+        const dim3 grid((unsigned)n_groups, nf);
         const uint8_t *p = px + (int64_t)f0 * g.frame_bytes;
         int32_t *c = d_coefs + (int64_t)f0 * g.coefs_per_frame;
         int32_t *dc = d_dc ? d_dc + (((int64_t)f0 * g.n_fractals * g.channels) << g.sub_bits) : nullptr;
 #define FRI_LAUNCH(CC, SS)                                                                                                        \
         do {                                                                                                                      \
             if (g.sub_bits == 0)                                                                                                  \
-                fri_encode_kernel<CC, SS, false><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.stage_list, p, c, dc, lookahead); \
+                fri_encode_kernel<CC, SS, false><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.stage_list, p, c, dc, lookahead, group_begin); \
             else                                                                                                                  \
-                fri_encode_kernel<CC, SS, true><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.stage_list, p, c, dc, lookahead);  \
+                fri_encode_kernel<CC, SS, true><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.stage_list, p, c, dc, lookahead, group_begin);  \
         } while (0)
         if (g.channels == 1 && g.sample_bytes == 1) FRI_LAUNCH(1, uint8_t);
         else if (g.channels == 3 && g.sample_bytes == 1) FRI_LAUNCH(3, uint8_t);
@@ -1057,7 +1062,7 @@ cudaError_t launch_encode(const Geometry &g, const DeviceTables &t, const QuantP
 #undef FRI_LAUNCH
         if (launches) ++*launches;
     }
-    if (g.sub_bits > 0) {
+    if (g.sub_bits > 0 && group_end == g.n_groups) {  // after the last band
         const unsigned blocks = (unsigned)((int64_t)n_frames * g.n_fractals * g.channels);
         const size_t cs = ((size_t)3 << g.sub_bits) / 2 * sizeof(int32_t) + 16;
         fri_coarse_forward_kernel<<<blocks, kCoarseThreads, cs, stream>>>(qp, g.sub_bits, g.depth, d_dc, d_coefs);
@@ -1068,11 +1073,13 @@ cudaError_t launch_encode(const Geometry &g, const DeviceTables &t, const QuantP
 
 cudaError_t launch_decode(const Geometry &g, const DeviceTables &t, const QuantParams &qp, const int32_t *d_coefs,
                           uint32_t n_frames, void *d_pixels, int32_t *d_dc, cudaStream_t stream,
-                          uint32_t *launches)
+                          uint32_t *launches, int group_begin, int group_end)
 {
-    if (n_frames == 0 || g.n_groups == 0) return cudaSuccess;
+    if (group_end < 0) group_end = g.n_groups;
+    const int n_groups = group_end - group_begin;
+    if (n_frames == 0 || n_groups <= 0) return cudaSuccess;
     const size_t smem = kernel_smem_bytes(g);
-    if (g.sub_bits > 0) {
+    if (g.sub_bits > 0 && group_begin == 0) {  // before the first band
         const unsigned blocks = (unsigned)((int64_t)n_frames * g.n_fractals * g.channels);
         const size_t cs = ((size_t)3 << g.sub_bits) / 2 * sizeof(int32_t) + 16;
         fri_coarse_inverse_kernel<<<blocks, kCoarseThreads, cs, stream>>>(qp, g.sub_bits, g.depth, d_coefs, d_dc);
@@ -1081,16 +1088,16 @@ cudaError_t launch_decode(const Geometry &g, const DeviceTables &t, const QuantP
     uint8_t *px = static_cast<uint8_t *>(d_pixels);
     for (uint32_t f0 = 0; f0 < n_frames; f0 += 65535u) {
         const uint32_t nf = n_frames - f0 < 65535u ? n_frames - f0 : 65535u;
-        const dim3 grid((unsigned)g.n_groups, nf);
+        const dim3 grid((unsigned)n_groups, nf);
         uint8_t *p = px + (int64_t)f0 * g.frame_bytes;
         const int32_t *c = d_coefs + (int64_t)f0 * g.coefs_per_frame;
         int32_t *dc = d_dc ? d_dc + (((int64_t)f0 * g.n_fractals * g.channels) << g.sub_bits) : nullptr;
 #define FRI_LAUNCH(CC, SS)                                                                                                        \
         do {                                                                                                                      \
             if (g.sub_bits == 0)                                                                                                  \
-                fri_decode_kernel<CC, SS, false><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, t.chunk_mask, c, dc, p); \
+                fri_decode_kernel<CC, SS, false><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, t.chunk_mask, c, dc, p, group_begin); \
             else                                                                                                                  \
-                fri_decode_kernel<CC, SS, true><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, t.chunk_mask, c, dc, p);  \
+                fri_decode_kernel<CC, SS, true><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, t.chunk_mask, c, dc, p, group_begin);  \
         } while (0)
         if (g.channels == 1 && g.sample_bytes == 1) FRI_LAUNCH(1, uint8_t);
         else if (g.channels == 3 && g.sample_bytes == 1) FRI_LAUNCH(3, uint8_t);

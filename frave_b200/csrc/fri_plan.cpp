@@ -218,8 +218,16 @@ std::string build_plan(Plan &plan, uint32_t width, uint32_t height, uint32_t cha
     auto group_key = [&](const BaseTile &t) {
         return std::pair<int, int>(floor_div(t.b - bmin, group_b), floor_div(t.a - amin, group_a));
     };
+    // Groups are ordered top to bottom (by the y, then x, of their first lattice cell), tiles inside a
+    // group by (b, a).  A contiguous range of groups then needs a compact range of pixel rows, which
+    // is what lets the host entry points stream a frame through the device in bands.
+    auto group_origin = [&](const BaseTile &t) {
+        const auto gk = group_key(t);
+        const int a0 = amin + gk.second * group_a, b0 = bmin + gk.first * group_b;
+        return std::pair<int, int>(a0 * l9.y + b0 * l10.y, a0 * l9.x + b0 * l10.x);
+    };
     std::sort(tiles.begin(), tiles.end(), [&](const BaseTile &l, const BaseTile &r) {
-        auto gl = group_key(l), gr = group_key(r);
+        auto gl = group_origin(l), gr = group_origin(r);
         if (gl != gr) return gl < gr;
         if (l.b != r.b) return l.b < r.b;
         return l.a < r.a;

@@ -121,6 +121,27 @@ def test_batch_equals_per_frame_and_unaligned_frames():
         assert np.array_equal(rec, frames)
 
 
+@pytest.mark.parametrize("bands", [1, 3, 8])
+@pytest.mark.parametrize("shape", [(270, 480, 3), (700, 900, 3), (513, 1000, 1)], ids=lambda s: "x".join(map(str, s)))
+def test_banded_host_pipeline(monkeypatch, shape, bands):
+    """The host-buffer entry points stream a frame through the device in bands of groups (copies in,
+    kernels, copies out on three event-chained streams); any band count and several frames in
+    flight must give the same bytes."""
+    monkeypatch.setenv("FRI_BANDS", str(bands))
+    h, w, c = shape
+    frames = np.stack([uniform_image(h, w, c, seed=200 + i) for i in range(5)])
+    q = smallest_layer_q(6)
+    with capi.Plan(w, h, c) as plan:
+        some = some_of(plan)
+        coefs = plan.encode(frames, q)
+        rec = plan.decode(coefs, q)
+        for i in range(5):
+            want, _ = oracle_encode(plan, frames[i], q)
+            assert np.array_equal(coefs[i], want)
+            assert np.array_equal(rec[i], oracle_decode(plan, want, some, q))
+        assert np.array_equal(plan.decode(plan.encode(frames)), frames) or plan.pixels_covered < w * h
+
+
 def test_device_entry_points_with_misaligned_pixel_pointer():
     torch = pytest.importorskip("torch")
     h, w, c, n = 61, 93, 3, 3
