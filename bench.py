@@ -394,8 +394,11 @@ def main() -> None:
     ap.add_argument("--preheat", type=float, default=1.0, help="seconds of untimed load before the warm-up steps")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (experiments only)")
     ap.add_argument("--no-batched", action="store_true", help="skip the batched steady-state leg (experiments only)")
+    ap.add_argument("--divisor", type=int, default=None, help="smallest-layer divisor override (experiments only; default 4)")
     args = ap.parse_args()
-    global W, H, C, FRAMES, PREHEAT_S
+    global W, H, C, FRAMES, PREHEAT_S, SMALLEST_LAYER_DIVISOR
+    if args.divisor is not None:
+        SMALLEST_LAYER_DIVISOR = args.divisor
     if args.shape:
         W, H, C = (int(v) for v in args.shape.lower().split("x"))
     FRAMES, PREHEAT_S = args.frames, args.preheat

@@ -80,6 +80,7 @@ void make_quant_params(QuantParams &qp, const int32_t *q, int multiply)
     qp.active = 0;
     qp.small = 0;
     qp.pow2 = 0;
+    qp.fix = 0;
     qp.multiply = multiply;
     for (int l = 0; l < 32; ++l) {
         const int32_t v = q ? q[l] : 1;
@@ -98,6 +99,7 @@ void make_quant_params(QuantParams &qp, const int32_t *q, int multiply)
         qp.small_magic[l] = sd.magic;
         qp.small_shift[l] = sd.shift;
         if (v != 1) qp.active |= 1u << l;
+        if (l < 31 && (q ? q[l + 1] : 1) != v) qp.fix |= 1u << l;
     }
 }
 
@@ -219,15 +221,17 @@ __device__ __forceinline__ int dequant_layer(const QuantParams &qp, int d, int l
     return ((qp.pow2 >> l) & 1u) ? trunc_div_pow2(d, qp.pow2_shift[l]) : trunc_div(d, qp.div(l));
 }
 
+// clamp (images.rs:109) + store of one sample to shared memory: max(min(v, 255), 0) is one DPX
+// instruction (VIMNMX.RELU) and the byte store takes the low bits of the 32-bit register, where
+// cvt.sat.u8.s32 costs a conversion plus a re-masking LOP3 per sample.
 template <typename S>
-__device__ __forceinline__ S clamp_sample(int v)  // images.rs:109 (u16: the 16-bit extension)
+__device__ __forceinline__ void store_clamped(uint32_t saddr, int v)
 {
-    uint32_t r;
+    const int c = __vimin_s32_relu(v, sizeof(S) == 1 ? 255 : 65535);
     if (sizeof(S) == 1)
-        asm("cvt.sat.u8.s32 %0, %1;" : "=r"(r) : "r"(v));
+        asm volatile("st.shared.u8 [%0], %1;" ::"r"(saddr), "r"(c));
     else
-        asm("cvt.sat.u16.s32 %0, %1;" : "=r"(r) : "r"(v));
-    return (S)r;
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(saddr), "r"(c));
 }
 
 __device__ __forceinline__ int lane_anchor_bytes(int lane, int pitch, int pixel_bytes)
@@ -460,10 +464,10 @@ __device__ __forceinline__ void encode_tiles(const Geometry &g, const QuantParam
 #undef FRI_QLEVEL
                 a6 = a6v[0];
                 b6 = b6v[0];
-                if (lastB) {
-                    b8[3] = quant_layer_enc(qp, r8, top + 9);
-                    b7[1] = quant_layer_enc(qp, r7, top + 8);
-                    b6 = quant_layer_enc(qp, r6, top + 7);
+                if (lastB && ((qp.fix >> (top + 6)) & 7u)) {  // only where the next layer's divisor differs
+                    if ((qp.fix >> (top + 8)) & 1u) b8[3] = quant_layer_enc(qp, r8, top + 9);
+                    if ((qp.fix >> (top + 7)) & 1u) b7[1] = quant_layer_enc(qp, r7, top + 8);
+                    if ((qp.fix >> (top + 6)) & 1u) b6 = quant_layer_enc(qp, r6, top + 7);
                 }
             }
             int32_t *out = coefs + ta.block + ((int64_t)ch << depth);
@@ -536,8 +540,28 @@ __device__ __forceinline__ void prefetch_group_coefs(const Geometry &g, const Gr
     if (DEEP) return;
     const char *first = reinterpret_cast<const char *>(coefs + ((((int64_t)frame * g.n_fractals + gd.tile_base) * C) << kBaseDepth));
     const int lines = __popc(gd.tile_mask) * C * 16;  // 128-byte lines
+#pragma unroll 1
     for (int i = threadIdx.x; i < lines; i += blockDim.x)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(first + (size_t)i * 128));
+}
+
+// The coefficients of levels 6..8 a lane consumes for one (tile, channel): 2 x 128, 2 x 64, 2 x 32 bits.
+struct LaneCoefs {
+    int4 a8, b8;
+    int2 a7, b7;
+    int a6, b6;
+};
+__device__ __forceinline__ LaneCoefs load_lane_coefs(const int32_t *__restrict__ in, size_t node, int lane)
+{
+    const int32_t *i8 = in + (node << 8), *i7 = in + (node << 7), *i6 = in + (node << 6);
+    LaneCoefs c;
+    c.a8 = __ldcs(reinterpret_cast<const int4 *>(i8) + lane);
+    c.b8 = __ldcs(reinterpret_cast<const int4 *>(i8 + 128) + lane);
+    c.a7 = __ldcs(reinterpret_cast<const int2 *>(i7) + lane);
+    c.b7 = __ldcs(reinterpret_cast<const int2 *>(i7 + 64) + lane);
+    c.a6 = __ldcs(i6 + lane);
+    c.b6 = __ldcs(i6 + 32 + lane);
+    return c;
 }
 
 // Dequantization + inverse transform of the tiles of one group into the staged region; mirror
@@ -554,7 +578,7 @@ __device__ __forceinline__ void decode_tiles(const Geometry &g, const QuantParam
     constexpr int PB = C * SB;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     const int n_present = __popc(gd.tile_mask);
-    uint8_t *lane_base = region + rv.phi0 + lane_anchor_bytes(lane, g.pitch, PB);
+    const uint32_t lane_base = (uint32_t)__cvta_generic_to_shared(region) + rv.phi0 + lane_anchor_bytes(lane, g.pitch, PB);
     const int half = kHalfB.y * g.pitch + kHalfB.x * PB;
     const int sub_bits = DEEP ? g.sub_bits : 0, depth = DEEP ? g.depth : kBaseDepth;
     const int top = sub_bits;
@@ -566,6 +590,10 @@ __device__ __forceinline__ void decode_tiles(const Geometry &g, const QuantParam
         const TaskAddr ta = task_addr<C, DEEP>(g, tile_unit, frame, gd.tile_base + e, 0);
         const bool lastB = ta.last && lane == 31;
         const size_t node = ta.node;
+
+        // The first channel's register-level coefficients are requested before the top levels are
+        // unfolded, so that one round trip to L2/HBM covers both.
+        LaneCoefs cur = load_lane_coefs(coefs + ta.block, node, lane);
 
         // ---- levels 0..5 of all channels, 8 lanes per channel
         {
@@ -613,17 +641,13 @@ __device__ __forceinline__ void decode_tiles(const Geometry &g, const QuantParam
         }
         __syncwarp();
 
-        uint8_t *t0 = lane_base + g.tile_off[slot];
+        const uint32_t t0 = lane_base + g.tile_off[slot];
 #pragma unroll
         for (int ch = 0; ch < C; ++ch) {
-            const int32_t *in = coefs + ta.block + ((int64_t)ch << depth);
-            const int32_t *i8 = in + (node << 8), *i7 = in + (node << 7), *i6 = in + (node << 6);
-            int4 a8 = __ldcs(reinterpret_cast<const int4 *>(i8) + lane);
-            int4 b8 = __ldcs(reinterpret_cast<const int4 *>(i8 + 128) + lane);
-            int2 a7 = __ldcs(reinterpret_cast<const int2 *>(i7) + lane);
-            int2 b7 = __ldcs(reinterpret_cast<const int2 *>(i7 + 64) + lane);
-            int a6 = __ldcs(i6 + lane);
-            int b6 = __ldcs(i6 + 32 + lane);
+            int4 a8 = cur.a8, b8 = cur.b8;
+            int2 a7 = cur.a7, b7 = cur.b7;
+            int a6 = cur.a6, b6 = cur.b6;
+            if (ch + 1 < C) cur = load_lane_coefs(coefs + ta.block + ((int64_t)(ch + 1) << depth), node, lane);
             const int sA = scratch[ch * kScratchInts + lane], sB = scratch[ch * kScratchInts + 32 + lane];
 
             if ((qp.active >> (top + 6)) & 0xfu) {
@@ -650,10 +674,10 @@ __device__ __forceinline__ void decode_tiles(const Geometry &g, const QuantParam
                 FRI_DQLEVEL(7, a7.x = f(a7.x); a7.y = f(a7.y); b7.x = f(b7.x); b7.y = f(b7.y);)
                 FRI_DQLEVEL(6, a6 = f(a6); b6 = f(b6);)
 #undef FRI_DQLEVEL
-                if (lastB) {
-                    b8.w = dequant_layer(qp, r8, top + 9);
-                    b7.y = dequant_layer(qp, r7, top + 8);
-                    b6 = dequant_layer(qp, r6, top + 7);
+                if (lastB && ((qp.fix >> (top + 6)) & 7u)) {  // only where the next layer's divisor differs
+                    if ((qp.fix >> (top + 8)) & 1u) b8.w = dequant_layer(qp, r8, top + 9);
+                    if ((qp.fix >> (top + 7)) & 1u) b7.y = dequant_layer(qp, r7, top + 8);
+                    if ((qp.fix >> (top + 6)) & 1u) b6 = dequant_layer(qp, r6, top + 7);
                 }
             }
 
@@ -675,8 +699,8 @@ __device__ __forceinline__ void decode_tiles(const Geometry &g, const QuantParam
             unlift(sb8[3], b8.w, w[6], w[7]);
 
             // scatter into the staged region (clamp: images.rs:109)
-            uint8_t *p0 = t0 + ch * SB, *p1 = p0 + g.pitch, *p2 = p1 + g.pitch;
-#define FRI_ST(ptr, dx, val) (*reinterpret_cast<S *>((ptr) + (dx) * PB) = clamp_sample<S>(val))
+            const uint32_t p0 = t0 + ch * SB, p1 = p0 + g.pitch, p2 = p1 + g.pitch;
+#define FRI_ST(ptr, dx, val) store_clamped<S>((ptr) + (dx) * PB, (val))
             FRI_ST(p0, 0, v[0]);  FRI_ST(p1, 0, v[1]);
             FRI_ST(p1, -1, v[2]); FRI_ST(p2, -1, v[3]);
             FRI_ST(p0, 2, v[4]);  FRI_ST(p1, 2, v[5]);

@@ -71,6 +71,8 @@ struct QuantParams {
     uint32_t active;   // bit l set <=> q[l] != 1
     uint32_t small;    // bit l set <=> the narrow-range division is available for layer l
     uint32_t pow2;     // bit l set <=> q[l] = 2^pow2_shift[l], pow2_shift[l] >= 1
+    uint32_t fix;      // bit l set <=> q[l + 1] != q[l]: the last node of tree level l (which the reference
+                       // bins into layer l + 1, quantization.rs:13) needs its own divisor
     int32_t multiply;  // decode only: 1 = multiply (true dequantizer), 0 = divide (reference)
     FRI_HDI Div div(int l) const { return Div{magic[l], addmask[l], shift[l]}; }
     FRI_HDI SmallDiv sdiv(int l) const { return SmallDiv{small_magic[l], small_shift[l]}; }
@@ -80,7 +82,10 @@ Div make_div(int32_t q);                         // q >= 2
 bool make_small_div(int32_t q, SmallDiv &out);   // false if q < 3
 void make_quant_params(QuantParams &qp, const int32_t *q, int multiply);
 
-constexpr int kThreads = 256;       // upper bound on threads per CTA (launch bounds)
+#ifndef FRI_MAX_THREADS
+#define FRI_MAX_THREADS 256
+#endif
+constexpr int kThreads = FRI_MAX_THREADS;  // upper bound on threads per CTA (launch bounds)
 constexpr int kMaxWarps = kThreads / 32;
 int cta_threads(const Geometry &g);  // threads per CTA for a plan: one warp per two base tiles of a full group
 constexpr int kScratchInts = 64;    // per warp and channel: the 64 level-6 low-pass values of a base tile
