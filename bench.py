@@ -9,7 +9,8 @@ Workload: BASELINE.json configs[1], a synthetic 4096x4096 8-bit RGB image (one p
 are independent, so N GPUs = N frames, weak scaling, no data-path collective).
 
 Prints ONE JSON line (rank 0).  `value` is device-resident MPix/s, `e2e` the same metric through
-the host-buffer C-ABI entry points (pinned host memory, copies inside the timed region),
+the host-buffer C-ABI entry points (pinned host memory, copies inside the timed region; four driving
+patterns are timed, the headline one is named in `e2e.api`),
 `roofline` the dominant kernel against the measured HBM copy bandwidth, `cpu_baseline` the CPU
 oracle (single thread, like the reference) on the same image.
 """
@@ -300,29 +301,79 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
         del bpx, bco, bout
         bplan.close()
 
-    # ---- end to end through the host-buffer C ABI: pinned host memory, H2D and D2H in the timed region
-    e2e_steps = max(2, min(args.steps, 8))
+    # ---- end to end through the host-buffer C ABI: pinned host memory, H2D and D2H in the timed region.
+    # Four ways to drive the same two stage calls; every step moves one frame through encode and one
+    # through decode, each with its own host->device and device->host copies:
+    #   serial  = one host thread calls encode, then decode (the reference's single-threaded shape);
+    #   duplex  = an encoder thread and a decoder thread, one plan handle each (the ABI is re-entrant
+    #             across handles), so one call's device->host copy overlaps the other's host->device
+    #             copy on the full-duplex PCIe link;
+    #   i32/i16 = coefficient type on the host side of the copy (fri_*_tq / fri_*_tq16).
+    import threading
+
+    e2e_steps = max(4, min(args.steps, 12))
     px_h = capi.PinnedBuffer((1, H, W, C), np.uint8)
-    cf_h = capi.PinnedBuffer((1,) + plan.coef_shape, np.int32)
     out_h = capi.PinnedBuffer((1, H, W, C), np.uint8)
     px_h.array[0] = img0
-    plan.encode(px_h.array, q, out=cf_h.array)  # warm-up (allocates the plan's device slots)
-    plan.decode(cf_h.array, q, out=out_h.array)
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        plan.encode(px_h.array, q, out=cf_h.array)
-        plan.decode(cf_h.array, q, out=out_h.array)
-    e2e_s = time.perf_counter() - t0
-    h2d = px_h.array.nbytes + cf_h.array.nbytes
-    d2h = cf_h.array.nbytes + out_h.array.nbytes
+    dplan = capi.Plan(W, H, C, device=local_rank)  # the decoder thread's handle
+    e2e = {}
+    h2d = d2h = 0
+    for cdt, tag in ((np.int32, "i32"), (np.int16, "i16")):
+        cf_enc = capi.PinnedBuffer((1,) + plan.coef_shape, cdt)
+        cf_dec = capi.PinnedBuffer((1,) + plan.coef_shape, cdt)
+        plan.encode(px_h.array, q, out=cf_enc.array)  # warm-up (allocates the plans' device slots)
+        cf_dec.array[...] = cf_enc.array
+        dplan.decode(cf_dec.array, q, out=out_h.array)
+        plan.decode(cf_dec.array, q, out=out_h.array)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            plan.encode(px_h.array, q, out=cf_enc.array)
+            plan.decode(cf_enc.array, q, out=out_h.array)
+        e2e["serial_" + tag] = time.perf_counter() - t0
+
+        errors = []
+
+        def enc_loop():
+            try:
+                for _ in range(e2e_steps):
+                    plan.encode(px_h.array, q, out=cf_enc.array)
+            except Exception as exc:  # surfaced after the join
+                errors.append(exc)
+
+        def dec_loop():
+            try:
+                for _ in range(e2e_steps):
+                    dplan.decode(cf_dec.array, q, out=out_h.array)
+            except Exception as exc:
+                errors.append(exc)
+
+        if world > 1:
+            dist.barrier()
+        th = [threading.Thread(target=enc_loop), threading.Thread(target=dec_loop)]
+        t0 = time.perf_counter()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        e2e["duplex_" + tag] = time.perf_counter() - t0
+        if errors:
+            raise errors[0]
+        h2d = px_h.array.nbytes + cf_dec.array.nbytes
+        d2h = cf_enc.array.nbytes + out_h.array.nbytes
+        cf_enc.free(); cf_dec.free()
+    dplan.close()
+    e2e_keys = sorted(e2e)
+    e2e_s = e2e["duplex_i16"]
 
     if world > 1:
         vals = [elapsed_ms, e2e_s, enc_ms, dec_ms] + ([batched[3], batched[4]] if batched else [0.0, 0.0])
+        vals += [e2e[k] for k in e2e_keys]
         t = torch.tensor(vals, dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms, e2e_s, enc_ms, dec_ms, b0, b1 = (float(x) for x in t.tolist())
+        elapsed_ms, e2e_s, enc_ms, dec_ms, b0, b1 = (float(x) for x in t.tolist()[:6])
+        e2e = dict(zip(e2e_keys, (float(x) for x in t.tolist()[6:])))
         if batched:
             batched = batched[:3] + (b0, b1)
         dist.barrier()
@@ -348,7 +399,13 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
             "encode_mpix_s": pix_step / (enc_ms * 1e-3) / 1e6, "decode_mpix_s": pix_step / (dec_ms * 1e-3) / 1e6,
             "roofline": r_enc if enc_ms >= dec_ms else r_dec, "roofline_encode": r_enc, "roofline_decode": r_dec,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "fri_encode_tq + fri_decode_tq (host buffers, pinned)"},
+                    "steps": e2e_steps,
+                    "api": "fri_encode_tq16 + fri_decode_tq16 (pinned host buffers, int16 coefficients on the host side), "
+                           "encoder thread and decoder thread with one plan handle each",
+                    "variants_mpix_s": {k: W * H * world * e2e_steps / v / 1e6 for k, v in e2e.items()},
+                    "variants": "serial = one thread, encode then decode; duplex = encoder and decoder threads; "
+                                "i32 = fri_*_tq (4 B coefficients over PCIe: 255 MB each way per step), "
+                                "i16 = fri_*_tq16 (151 MB each way)"},
             "gpu_launches": timed_launches, "clocks": clocks, "launch": plan.launch_info(),
         }
         if batched:
@@ -377,7 +434,7 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
                 "sample": f"{passes} full pass(es) of the same {W}x{H}x{C} image (encode+decode), C oracle, 1 thread "
                           f"(the reference is single-threaded)"}
         print(json.dumps(line), flush=True)
-    px_h.free(); cf_h.free(); out_h.free()
+    px_h.free(); out_h.free()
     plan.close()
     if world > 1:
         dist.destroy_process_group()

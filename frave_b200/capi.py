@@ -40,6 +40,8 @@ _SYMBOLS = [
     ("fri_decode_tq_device", C.c_int, [_P, _P, C.c_uint32, _P, C.c_int, _P, _P]),
     ("fri_encode_tq", C.c_int, [_P, _P, C.c_uint32, _P, _P]),
     ("fri_decode_tq", C.c_int, [_P, _P, C.c_uint32, _P, C.c_int, _P]),
+    ("fri_encode_tq16", C.c_int, [_P, _P, C.c_uint32, _P, _P]),
+    ("fri_decode_tq16", C.c_int, [_P, _P, C.c_uint32, _P, C.c_int, _P]),
     ("fri_plan_emission_count", C.c_uint64, [_P]),
     ("fri_plan_emission_order", C.c_int, [_P, _P]),
     ("fri_emit_device", C.c_int, [_P, _P, C.c_uint32, _P, _P]),
@@ -214,19 +216,23 @@ class Plan:
             raise ValueError(f"pixels must have shape [F]{self.frame_shape}")
         return np.ascontiguousarray(px), px.shape[0]
 
-    def encode(self, pixels: np.ndarray, q=None, out: np.ndarray | None = None) -> np.ndarray:
-        """HWC pixels [F, H, W, C] -> quantized coefficients int32 [F, n_tiles, C, 2^depth]."""
+    def encode(self, pixels: np.ndarray, q=None, out: np.ndarray | None = None, dtype=np.int32) -> np.ndarray:
+        """HWC pixels [F, H, W, C] -> quantized coefficients [F, n_tiles, C, 2^depth]: int32, or int16
+        through the 16-bit transport (fri_encode_tq16; `out.dtype` decides when `out` is given)."""
         px, n = self._frames(pixels)
         if out is None:
-            out = np.empty((n,) + self.coef_shape, np.int32)
-        assert out.dtype == np.int32 and out.flags.c_contiguous and out.size == n * self.coefs_per_frame
+            out = np.empty((n,) + self.coef_shape, dtype)
+        assert out.dtype in (np.int32, np.int16) and out.flags.c_contiguous and out.size == n * self.coefs_per_frame
         qa, qp = _q_array(q)
-        _check(lib().fri_encode_tq(self._h, px.ctypes.data, n, qp, out.ctypes.data))
+        fn = lib().fri_encode_tq16 if out.dtype == np.int16 else lib().fri_encode_tq
+        _check(fn(self._h, px.ctypes.data, n, qp, out.ctypes.data))
         return out
 
     def decode(self, coefs: np.ndarray, q=None, multiply: bool = False, out: np.ndarray | None = None) -> np.ndarray:
-        """Quantized coefficients [F, n_tiles, C, 2^depth] -> HWC pixels [F, H, W, C]."""
-        cf = np.ascontiguousarray(coefs, dtype=np.int32)
+        """Quantized coefficients [F, n_tiles, C, 2^depth] -> HWC pixels [F, H, W, C].  int16 input
+        takes the 16-bit transport (fri_decode_tq16), anything else is passed as int32."""
+        half = np.asarray(coefs).dtype == np.int16
+        cf = np.ascontiguousarray(coefs, dtype=np.int16 if half else np.int32)
         if cf.shape == self.coef_shape:
             cf = cf[None]
         if cf.ndim != 4 or cf.shape[1:] != self.coef_shape:
@@ -237,7 +243,8 @@ class Plan:
         assert out.dtype == self.pixel_dtype and out.flags.c_contiguous and out.shape[1:] == self.frame_shape
         qa, qp = _q_array(q)
         mode = FRI_DEQUANT_MULTIPLY if multiply else FRI_DEQUANT_DIVIDE
-        _check(lib().fri_decode_tq(self._h, cf.ctypes.data, n, qp, mode, out.ctypes.data))
+        fn = lib().fri_decode_tq16 if half else lib().fri_decode_tq
+        _check(fn(self._h, cf.ctypes.data, n, qp, mode, out.ctypes.data))
         return out
 
     # ---- emission order (depth 9) -----------------------------------------------------------------

@@ -49,6 +49,7 @@ constexpr int kMaxBands = 8;   // a frame is streamed through the device in up t
 struct Slot {
     void *d_pixels = nullptr;
     int32_t *d_coefs = nullptr;
+    int16_t *d_coefs16 = nullptr;  // 16-bit transport staging (fri_*_tq16), allocated on first use
     int32_t *d_dc = nullptr;
     cudaEvent_t compute_done = nullptr;  // last kernel of the frame that used the slot
     cudaEvent_t out_done = nullptr;      // last device-to-host copy of that frame
@@ -145,6 +146,18 @@ int ensure_slots(fri_plan *p)
         FRI_CUDA(cudaEventCreateWithFlags(&s.out_done, cudaEventDisableTiming));
     }
     p->slots_ready = true;
+    return FRI_OK;
+}
+
+int ensure_slots16(fri_plan *p)
+{
+    int rc = ensure_slots(p);
+    if (rc) return rc;
+    const Geometry &g = p->plan.geo;
+    if (g.sample_bytes != 1)
+        return fail(FRI_E_UNSUPPORTED, "16-bit coefficient transport needs 8-bit samples (residues of 16-bit samples need 18 bits)");
+    for (auto &s : p->slots)
+        if (!s.d_coefs16) FRI_CUDA(cudaMalloc(&s.d_coefs16, (size_t)g.coefs_per_frame * sizeof(int16_t) + 16));
     return FRI_OK;
 }
 
@@ -284,6 +297,7 @@ void fri_plan_destroy(fri_plan *p)
         for (auto &s : p->slots) {
             if (s.d_pixels) cudaFree(s.d_pixels);
             if (s.d_coefs) cudaFree(s.d_coefs);
+            if (s.d_coefs16) cudaFree(s.d_coefs16);
             if (s.d_dc) cudaFree(s.d_dc);
             if (s.compute_done) cudaEventDestroy(s.compute_done);
             if (s.out_done) cudaEventDestroy(s.out_done);
@@ -386,14 +400,14 @@ int fri_decode_tq_device(const fri_plan *cp, const int32_t *d_coefs, uint32_t n_
     return FRI_OK;
 }
 
-int fri_encode_tq(fri_plan *p, const void *pixels, uint32_t n_frames, const int32_t *q, int32_t *coefs)
+static int encode_host(fri_plan *p, const void *pixels, uint32_t n_frames, const int32_t *q, void *coefs, bool half)
 {
     int rc = enter_device(p);
     if (rc) return rc;
     if ((rc = check_q(q))) return rc;
     if (n_frames == 0) return FRI_OK;
     if (!pixels || !coefs) return fail(FRI_E_INVALID, "NULL host buffer");
-    if ((rc = ensure_slots(p))) return rc;
+    if ((rc = half ? ensure_slots16(p) : ensure_slots(p))) return rc;
     const Geometry &g = p->plan.geo;
     Pipeline &pl = p->pipe;
     QuantParams qp;
@@ -405,7 +419,8 @@ int fri_encode_tq(fri_plan *p, const void *pixels, uint32_t n_frames, const int3
     for (uint32_t f = 0; f < n_frames; ++f) {
         Slot &s = p->slots[f % kSlots];
         const uint8_t *src = static_cast<const uint8_t *>(pixels) + (size_t)f * g.frame_bytes;
-        int32_t *dst = coefs + (size_t)f * g.coefs_per_frame;
+        const size_t esz = half ? sizeof(int16_t) : sizeof(int32_t);  // bytes per coefficient on the host side
+        uint8_t *dst = static_cast<uint8_t *>(coefs) + (size_t)f * g.coefs_per_frame * esz;
         if (s.used) {  // the frame that had this slot: its kernels have read the pixels, its copies the coefficients
             FRI_CUDA(cudaStreamWaitEvent(pl.in, s.compute_done, 0));
             FRI_CUDA(cudaStreamWaitEvent(pl.compute, s.out_done, 0));
@@ -422,14 +437,14 @@ int fri_encode_tq(fri_plan *p, const void *pixels, uint32_t n_frames, const int3
             FRI_CUDA(cudaEventRecord(pl.in_ready[k], pl.in));
             FRI_CUDA(cudaStreamWaitEvent(pl.compute, pl.in_ready[k], 0));
             FRI_CUDA(launch_encode(g, p->tables, qp, s.d_pixels, 1, s.d_coefs, s.d_dc, pl.compute, &p->last_launches, b.g0, b.g1));
+            // the band's coefficient range (deep trees: one band, the coarse kernel has touched every fractal's top levels)
+            const size_t c0 = g.sub_bits == 0 ? b.t0 * block : 0;
+            const size_t cn = g.sub_bits == 0 ? (b.t1 - b.t0) * block : (size_t)g.coefs_per_frame;
+            if (half) FRI_CUDA(launch_pack16(s.d_coefs + c0, s.d_coefs16 + c0, cn, pl.compute, &p->last_launches));
             FRI_CUDA(cudaEventRecord(pl.band_done[k], pl.compute));
             FRI_CUDA(cudaStreamWaitEvent(pl.out, pl.band_done[k], 0));
-            if (g.sub_bits == 0) {
-                FRI_CUDA(cudaMemcpyAsync(dst + b.t0 * block, s.d_coefs + b.t0 * block, (b.t1 - b.t0) * block * sizeof(int32_t),
-                                         cudaMemcpyDeviceToHost, pl.out));
-            } else {  // deep trees: one band, the coarse kernel has touched every fractal's top levels
-                FRI_CUDA(cudaMemcpyAsync(dst, s.d_coefs, (size_t)g.coefs_per_frame * sizeof(int32_t), cudaMemcpyDeviceToHost, pl.out));
-            }
+            const void *d_src = half ? static_cast<const void *>(s.d_coefs16 + c0) : static_cast<const void *>(s.d_coefs + c0);
+            FRI_CUDA(cudaMemcpyAsync(dst + c0 * esz, d_src, cn * esz, cudaMemcpyDeviceToHost, pl.out));
         }
         FRI_CUDA(cudaEventRecord(s.compute_done, pl.compute));
         FRI_CUDA(cudaEventRecord(s.out_done, pl.out));
@@ -441,7 +456,18 @@ int fri_encode_tq(fri_plan *p, const void *pixels, uint32_t n_frames, const int3
     return FRI_OK;
 }
 
-int fri_decode_tq(fri_plan *p, const int32_t *coefs, uint32_t n_frames, const int32_t *q, int dequant_mode, void *pixels)
+int fri_encode_tq(fri_plan *p, const void *pixels, uint32_t n_frames, const int32_t *q, int32_t *coefs)
+{
+    return encode_host(p, pixels, n_frames, q, coefs, false);
+}
+
+int fri_encode_tq16(fri_plan *p, const void *pixels, uint32_t n_frames, const int32_t *q, int16_t *coefs)
+{
+    return encode_host(p, pixels, n_frames, q, coefs, true);
+}
+
+static int decode_host(fri_plan *p, const void *coefs, uint32_t n_frames, const int32_t *q, int dequant_mode, void *pixels,
+                       bool half)
 {
     int rc = enter_device(p);
     if (rc) return rc;
@@ -450,7 +476,7 @@ int fri_decode_tq(fri_plan *p, const int32_t *coefs, uint32_t n_frames, const in
         return fail(FRI_E_INVALID, "dequant_mode must be FRI_DEQUANT_DIVIDE or FRI_DEQUANT_MULTIPLY");
     if (n_frames == 0) return FRI_OK;
     if (!pixels || !coefs) return fail(FRI_E_INVALID, "NULL host buffer");
-    if ((rc = ensure_slots(p))) return rc;
+    if ((rc = half ? ensure_slots16(p) : ensure_slots(p))) return rc;
     const Geometry &g = p->plan.geo;
     Pipeline &pl = p->pipe;
     QuantParams qp;
@@ -462,7 +488,8 @@ int fri_decode_tq(fri_plan *p, const int32_t *coefs, uint32_t n_frames, const in
     const bool need_zero = p->plan.pixels_covered != (uint64_t)g.width * g.height;
     for (uint32_t f = 0; f < n_frames; ++f) {
         Slot &s = p->slots[f % kSlots];
-        const int32_t *src = coefs + (size_t)f * g.coefs_per_frame;
+        const size_t esz = half ? sizeof(int16_t) : sizeof(int32_t);
+        const uint8_t *src = static_cast<const uint8_t *>(coefs) + (size_t)f * g.coefs_per_frame * esz;
         uint8_t *dst = static_cast<uint8_t *>(pixels) + (size_t)f * g.frame_bytes;
         if (s.used) {  // previous user of the slot: kernels have read the coefficients, copies the pixels
             FRI_CUDA(cudaStreamWaitEvent(pl.in, s.compute_done, 0));
@@ -472,14 +499,13 @@ int fri_decode_tq(fri_plan *p, const int32_t *coefs, uint32_t n_frames, const in
         int rows_out = 0;
         for (int k = 0; k < n_bands; ++k) {
             const Band &b = bands[k];
-            if (g.sub_bits == 0) {
-                FRI_CUDA(cudaMemcpyAsync(s.d_coefs + b.t0 * block, src + b.t0 * block, (b.t1 - b.t0) * block * sizeof(int32_t),
-                                         cudaMemcpyHostToDevice, pl.in));
-            } else {
-                FRI_CUDA(cudaMemcpyAsync(s.d_coefs, src, (size_t)g.coefs_per_frame * sizeof(int32_t), cudaMemcpyHostToDevice, pl.in));
-            }
+            const size_t c0 = g.sub_bits == 0 ? b.t0 * block : 0;
+            const size_t cn = g.sub_bits == 0 ? (b.t1 - b.t0) * block : (size_t)g.coefs_per_frame;
+            void *d_dst = half ? static_cast<void *>(s.d_coefs16 + c0) : static_cast<void *>(s.d_coefs + c0);
+            FRI_CUDA(cudaMemcpyAsync(d_dst, src + c0 * esz, cn * esz, cudaMemcpyHostToDevice, pl.in));
             FRI_CUDA(cudaEventRecord(pl.in_ready[k], pl.in));
             FRI_CUDA(cudaStreamWaitEvent(pl.compute, pl.in_ready[k], 0));
+            if (half) FRI_CUDA(launch_unpack16(s.d_coefs16 + c0, s.d_coefs + c0, cn, pl.compute, &p->last_launches));
             FRI_CUDA(launch_decode(g, p->tables, qp, s.d_coefs, 1, s.d_pixels, s.d_dc, pl.compute, &p->last_launches, b.g0, b.g1));
             FRI_CUDA(cudaEventRecord(pl.band_done[k], pl.compute));
             FRI_CUDA(cudaStreamWaitEvent(pl.out, pl.band_done[k], 0));
@@ -498,6 +524,16 @@ int fri_decode_tq(fri_plan *p, const int32_t *coefs, uint32_t n_frames, const in
     FRI_CUDA(cudaStreamSynchronize(pl.compute));
     FRI_CUDA(cudaStreamSynchronize(pl.in));
     return FRI_OK;
+}
+
+int fri_decode_tq(fri_plan *p, const int32_t *coefs, uint32_t n_frames, const int32_t *q, int dequant_mode, void *pixels)
+{
+    return decode_host(p, coefs, n_frames, q, dequant_mode, pixels, false);
+}
+
+int fri_decode_tq16(fri_plan *p, const int16_t *coefs, uint32_t n_frames, const int32_t *q, int dequant_mode, void *pixels)
+{
+    return decode_host(p, coefs, n_frames, q, dequant_mode, pixels, true);
 }
 
 /* ---- emission order ------------------------------------------------ */

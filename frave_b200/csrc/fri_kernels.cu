@@ -1001,6 +1001,39 @@ fri_emit_kernel(const uint32_t *__restrict__ src, unsigned long long count, int 
     __stcs(out + ((size_t)frame * channels + ch) * count + i, v);
 }
 
+// ------------------------------------------------------------------------------------------
+// 16-bit transport (host-buffer entry points fri_*_tq16): every coefficient an 8-bit image can
+// produce fits an i16 (|d| <= 255, 0 <= s <= 255), so the copies over PCIe carry half the bytes.
+// Pure streaming repack of the device-resident i32 array; eight coefficients per thread and
+// iteration, saturating so that an out-of-range value can never wrap silently.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_sat16(int lo, int hi)
+{
+    uint32_t r;
+    asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(r) : "r"(hi), "r"(lo));  // {sat(hi), sat(lo)}
+    return r;
+}
+
+__global__ void __launch_bounds__(256)
+fri_pack16_kernel(const int4 *__restrict__ src, int4 *__restrict__ dst, size_t n8)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        const int4 a = __ldcs(src + 2 * i), b = __ldcs(src + 2 * i + 1);
+        __stcs(dst + i, make_int4((int)pack_sat16(a.x, a.y), (int)pack_sat16(a.z, a.w), (int)pack_sat16(b.x, b.y),
+                                  (int)pack_sat16(b.z, b.w)));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+fri_unpack16_kernel(const int4 *__restrict__ src, int4 *__restrict__ dst, size_t n8)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        const int4 v = __ldcs(src + i);
+        __stcs(dst + 2 * i, make_int4((int)(short)v.x, v.x >> 16, (int)(short)v.y, v.y >> 16));
+        __stcs(dst + 2 * i + 1, make_int4((int)(short)v.z, v.z >> 16, (int)(short)v.w, v.w >> 16));
+    }
+}
+
 template <typename K>
 cudaError_t set_smem(K kernel, size_t bytes)
 {
@@ -1130,6 +1163,26 @@ cudaError_t launch_decode(const Geometry &g, const DeviceTables &t, const QuantP
 #undef FRI_LAUNCH
         if (launches) ++*launches;
     }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack16(const int32_t *d_src, int16_t *d_dst, size_t count, cudaStream_t stream, uint32_t *launches)
+{
+    if (count == 0) return cudaSuccess;
+    const size_t n8 = count / 8;  // coefficient blocks are multiples of 512
+    const unsigned blocks = (unsigned)std::min<size_t>((n8 + 255) / 256, (size_t)148 * 16);
+    fri_pack16_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const int4 *>(d_src), reinterpret_cast<int4 *>(d_dst), n8);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unpack16(const int16_t *d_src, int32_t *d_dst, size_t count, cudaStream_t stream, uint32_t *launches)
+{
+    if (count == 0) return cudaSuccess;
+    const size_t n8 = count / 8;
+    const unsigned blocks = (unsigned)std::min<size_t>((n8 + 255) / 256, (size_t)148 * 16);
+    fri_unpack16_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const int4 *>(d_src), reinterpret_cast<int4 *>(d_dst), n8);
+    if (launches) ++*launches;
     return cudaGetLastError();
 }
 

@@ -120,4 +120,9 @@ cudaError_t launch_decode(const Geometry &g, const DeviceTables &t, const QuantP
 cudaError_t launch_emit(const Geometry &g, const uint32_t *d_src, uint64_t count, const int32_t *d_coefs, uint32_t n_frames,
                         int32_t *d_out, cudaStream_t stream, uint32_t *launches);
 
+// 16-bit transport of the host-buffer entry points: saturating i32 -> i16 repack and its inverse
+// (count is a multiple of 8; both pointers 16-byte aligned).
+cudaError_t launch_pack16(const int32_t *d_src, int16_t *d_dst, size_t count, cudaStream_t stream, uint32_t *launches);
+cudaError_t launch_unpack16(const int16_t *d_src, int32_t *d_dst, size_t count, cudaStream_t stream, uint32_t *launches);
+
 }  // namespace fri

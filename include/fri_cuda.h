@@ -117,6 +117,20 @@ int fri_decode_tq(fri_plan *plan, const int32_t *coefs, uint32_t n_frames, const
                   void *pixels);
 
 /*
+ * 16-bit transport of the same two stage calls (8-bit samples only): the host side of the copy is
+ * int16 [n_frames][n_tiles][C][2^depth], same order.  Every coefficient the forward transform of
+ * an 8-bit image can produce fits (|residue| <= 255, 0 <= low-pass <= 255; wavelet_transform.rs:
+ * 211-218), and so does every coefficient a decodable container can hold (1024-symbol alphabet,
+ * entropy_coding.rs:25), so the Rust glue can widen to the reference's Vec<Option<i32>> while it
+ * applies the mask — and the PCIe copies, which bound these calls, carry half the bytes.  The
+ * device computes in i32 exactly as above; encode saturates on the (impossible) overflow instead
+ * of wrapping.  FRI_E_UNSUPPORTED for sample_bytes = 2 (residues need 18 bits).
+ */
+int fri_encode_tq16(fri_plan *plan, const void *pixels, uint32_t n_frames, const int32_t *q, int16_t *coefs);
+int fri_decode_tq16(fri_plan *plan, const int16_t *coefs, uint32_t n_frames, const int32_t *q, int dequant_mode,
+                    void *pixels);
+
+/*
  * Emission order (depth 9 only) — the order in which the reference's entropy coder consumes the
  * coefficients of one channel: entropy_coding.rs:283-329 walking sort_lattice
  * (wavelet_transform.rs:505-705): every DC, every root residue, then levels 1..8 in scan order.

@@ -142,6 +142,41 @@ def test_banded_host_pipeline(monkeypatch, shape, bands):
         assert np.array_equal(plan.decode(plan.encode(frames)), frames) or plan.pixels_covered < w * h
 
 
+@pytest.mark.parametrize("bands", [1, 4])
+@pytest.mark.parametrize("shape", [(270, 480, 3), (513, 1000, 1), (1080, 1920, 3)], ids=lambda s: "x".join(map(str, s)))
+def test_16bit_transport_equals_32bit(monkeypatch, shape, bands):
+    """fri_encode_tq16 / fri_decode_tq16: same coefficients and pixels as the i32 entry points (and
+    the oracle), the host side of the copies being int16."""
+    monkeypatch.setenv("FRI_BANDS", str(bands))
+    h, w, c = shape
+    frames = np.stack([uniform_image(h, w, c, seed=900 + i) for i in range(3)])
+    with capi.Plan(w, h, c) as plan:
+        some = some_of(plan)
+        for q in (None, smallest_layer_q(3), random_q(h, hi=9)):
+            c16 = plan.encode(frames, q, dtype=np.int16)
+            assert c16.dtype == np.int16
+            for i in range(3):
+                want, _ = oracle_encode(plan, frames[i], ONES if q is None else q)
+                assert np.array_equal(c16[i], want)
+            rec = plan.decode(c16, q)
+            for i in range(3):
+                assert np.array_equal(rec[i], oracle_decode(plan, c16[i].astype(np.int32), some, ONES if q is None else q))
+        # arbitrary i16 input (not produced by an encoder), both dequantizers
+        rng = np.random.Generator(np.random.PCG64(h))
+        anyc = rng.integers(-32768, 32768, size=(1,) + plan.coef_shape, dtype=np.int16)
+        q = random_q(w, hi=5)
+        for mul in (False, True):
+            assert np.array_equal(plan.decode(anyc, q, multiply=mul)[0],
+                                  oracle_decode(plan, anyc[0].astype(np.int32), some, q, multiply=mul))
+
+
+def test_16bit_transport_rejects_16bit_samples():
+    with capi.Plan(64, 48, 1, sample_bytes=2) as plan:
+        with pytest.raises(capi.FriError) as e:
+            plan.encode(np.zeros((48, 64, 1), np.uint16), dtype=np.int16)
+        assert e.value.code == capi.FRI_E_UNSUPPORTED
+
+
 def test_device_entry_points_with_misaligned_pixel_pointer():
     torch = pytest.importorskip("torch")
     h, w, c, n = 61, 93, 3, 3
