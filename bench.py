@@ -319,6 +319,9 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
     e2e = {}
     h2d = d2h = 0
     for cdt, tag in ((np.int32, "i32"), (np.int16, "i16")):
+        if args.no_e2e:
+            e2e.update({"serial_" + tag: float("inf"), "duplex_" + tag: float("inf")})
+            continue
         cf_enc = capi.PinnedBuffer((1,) + plan.coef_shape, cdt)
         cf_dec = capi.PinnedBuffer((1,) + plan.coef_shape, cdt)
         plan.encode(px_h.array, q, out=cf_enc.array)  # warm-up (allocates the plans' device slots)
@@ -451,6 +454,7 @@ def main() -> None:
     ap.add_argument("--preheat", type=float, default=1.0, help="seconds of untimed load before the warm-up steps")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (experiments only)")
     ap.add_argument("--no-batched", action="store_true", help="skip the batched steady-state leg (experiments only)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (experiments only)")
     ap.add_argument("--divisor", type=int, default=None, help="smallest-layer divisor override (experiments only; default 4)")
     args = ap.parse_args()
     global W, H, C, FRAMES, PREHEAT_S, SMALLEST_LAYER_DIVISOR

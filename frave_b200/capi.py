@@ -46,6 +46,8 @@ _SYMBOLS = [
     ("fri_plan_emission_order", C.c_int, [_P, _P]),
     ("fri_emit_device", C.c_int, [_P, _P, C.c_uint32, _P, _P]),
     ("fri_encode_tq_emit", C.c_int, [_P, _P, C.c_uint32, _P, _P]),
+    ("fri_emit_device16", C.c_int, [_P, _P, C.c_uint32, _P, _P]),
+    ("fri_encode_tq_emit16", C.c_int, [_P, _P, C.c_uint32, _P, _P]),
     ("fri_host_alloc", C.c_int, [C.POINTER(_P), C.c_size_t]),
     ("fri_host_free", None, [_P]),
     ("fri_plan_last_launches", C.c_uint32, [_P]),
@@ -262,19 +264,22 @@ class Plan:
             _check(lib().fri_plan_emission_order(self._h, np.empty(self.n_tiles << self.depth, np.uint32).ctypes.data))
         return n
 
-    def emit_device(self, d_coefs: int, n_frames: int, d_out: int, stream: int = 0) -> None:
-        _check(lib().fri_emit_device(self._h, d_coefs, n_frames, d_out, stream))
+    def emit_device(self, d_coefs: int, n_frames: int, d_out: int, stream: int = 0, half: bool = False) -> None:
+        """d_out: int32 (or, with half=True, int16) [n_frames, C, emission_count()] on the device."""
+        fn = lib().fri_emit_device16 if half else lib().fri_emit_device
+        _check(fn(self._h, d_coefs, n_frames, d_out, stream))
 
-    def encode_emit(self, pixels: np.ndarray, q=None, out: np.ndarray | None = None) -> np.ndarray:
-        """HWC pixels [F, H, W, C] -> int32 [F, C, emission_count()]: the quantized Some coefficients
-        of every channel in emission order."""
+    def encode_emit(self, pixels: np.ndarray, q=None, out: np.ndarray | None = None, dtype=np.int32) -> np.ndarray:
+        """HWC pixels [F, H, W, C] -> [F, C, emission_count()]: the quantized Some coefficients of every
+        channel in emission order, int32 or int16 (`out.dtype` decides when `out` is given)."""
         px, n = self._frames(pixels)
         cnt = self.emission_count()
         if out is None:
-            out = np.empty((n, self.channels, cnt), np.int32)
-        assert out.dtype == np.int32 and out.flags.c_contiguous and out.shape == (n, self.channels, cnt)
+            out = np.empty((n, self.channels, cnt), dtype)
+        assert out.dtype in (np.int32, np.int16) and out.flags.c_contiguous and out.shape == (n, self.channels, cnt)
         qa, qp = _q_array(q)
-        _check(lib().fri_encode_tq_emit(self._h, px.ctypes.data, n, qp, out.ctypes.data))
+        fn = lib().fri_encode_tq_emit16 if out.dtype == np.int16 else lib().fri_encode_tq_emit
+        _check(fn(self._h, px.ctypes.data, n, qp, out.ctypes.data))
         return out
 
     # ---- device-resident entry points (raw device pointers, e.g. torch.Tensor.data_ptr()) -----

@@ -83,9 +83,10 @@ struct fri_plan {
     std::string emit_error;
     std::vector<uint32_t> emit_order;  // [n_tiles * 512], None slots included
     std::vector<uint32_t> emit_src;    // Some slots only
-    void *d_emit_src = nullptr;
-    int32_t *d_emit_tmp = nullptr;      // device staging for fri_encode_tq_emit
-    size_t d_emit_tmp_frames = 0;
+    void *d_emit_goff = nullptr, *d_emit_dst = nullptr, *d_emit_loc = nullptr;  // the Some slots partitioned by group
+    EmitTables emit_tables;
+    void *d_emit_tmp = nullptr;         // device staging for fri_encode_tq_emit*
+    size_t d_emit_tmp_bytes = 0;
 };
 
 namespace {
@@ -307,7 +308,9 @@ void fri_plan_destroy(fri_plan *p)
         if (p->d_tile_unit) cudaFree(p->d_tile_unit);
         if (p->d_chunk_mask) cudaFree(p->d_chunk_mask);
         if (p->d_chunk_list) cudaFree(p->d_chunk_list);
-        if (p->d_emit_src) cudaFree(p->d_emit_src);
+        if (p->d_emit_goff) cudaFree(p->d_emit_goff);
+        if (p->d_emit_dst) cudaFree(p->d_emit_dst);
+        if (p->d_emit_loc) cudaFree(p->d_emit_loc);
         if (p->d_emit_tmp) cudaFree(p->d_emit_tmp);
         if (p->d_stage_list) cudaFree(p->d_stage_list);
     }
@@ -578,10 +581,42 @@ static int ensure_emission_device(fri_plan *p)
 {
     int rc = ensure_emission(p);
     if (rc) return rc;
-    if (!p->d_emit_src && !p->emit_src.empty()) {
-        FRI_CUDA(cudaMalloc(&p->d_emit_src, p->emit_src.size() * sizeof(uint32_t)));
-        FRI_CUDA(cudaMemcpy(p->d_emit_src, p->emit_src.data(), p->emit_src.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (p->d_emit_goff || p->emit_src.empty()) return FRI_OK;
+    // Partition the Some slots by the group that owns their tile (a group's tiles are consecutive in
+    // plan order), keeping increasing emission index inside every group.
+    const Plan &pl = p->plan;
+    const Geometry &g = pl.geo;
+    const size_t count = p->emit_src.size();
+    std::vector<uint32_t> goff((size_t)g.n_groups + 1, 0), dst(count);
+    std::vector<uint16_t> loc(count);
+    try {
+        std::vector<uint32_t> group_of((size_t)g.n_fractals);
+        for (int32_t gi = 0; gi < g.n_groups; ++gi) {
+            const uint32_t t0 = pl.groups[gi].tile_base, n = (uint32_t)__builtin_popcount(pl.groups[gi].tile_mask);
+            for (uint32_t t = t0; t < t0 + n; ++t) group_of[t] = (uint32_t)gi;
+        }
+        for (uint32_t v : p->emit_src) ++goff[group_of[v >> kBaseDepth] + 1];
+        for (int32_t gi = 0; gi < g.n_groups; ++gi) goff[gi + 1] += goff[gi];
+        std::vector<uint32_t> fill(goff.begin(), goff.end() - 1);
+        for (size_t i = 0; i < count; ++i) {
+            const uint32_t v = p->emit_src[i], tile = v >> kBaseDepth, gi = group_of[tile];
+            const uint32_t k = fill[gi]++;
+            dst[k] = (uint32_t)i;
+            loc[k] = (uint16_t)(((tile - pl.groups[gi].tile_base) << kBaseDepth) | (v & (kTileLeaves - 1)));
+        }
+    } catch (const std::bad_alloc &) {
+        return fail(FRI_E_NOMEM, "out of host memory while building the emission tables");
     }
+    auto upload = [&](void **d, const void *h, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc(d, bytes);
+        return e != cudaSuccess ? e : cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice);
+    };
+    FRI_CUDA(upload(&p->d_emit_goff, goff.data(), goff.size() * sizeof(uint32_t)));
+    FRI_CUDA(upload(&p->d_emit_dst, dst.data(), count * sizeof(uint32_t)));
+    FRI_CUDA(upload(&p->d_emit_loc, loc.data(), count * sizeof(uint16_t)));
+    p->emit_tables.goff = static_cast<const uint32_t *>(p->d_emit_goff);
+    p->emit_tables.dst = static_cast<const uint32_t *>(p->d_emit_dst);
+    p->emit_tables.loc = static_cast<const uint16_t *>(p->d_emit_loc);
     return FRI_OK;
 }
 
@@ -600,20 +635,33 @@ int fri_plan_emission_order(fri_plan *p, uint32_t *order)
     return FRI_OK;
 }
 
-int fri_emit_device(fri_plan *p, const int32_t *d_coefs, uint32_t n_frames, int32_t *d_out, void *stream)
+static int emit_device(fri_plan *p, const int32_t *d_coefs, uint32_t n_frames, void *d_out, bool half, void *stream)
 {
     int rc = enter_device(p);
     if (rc) return rc;
     if ((rc = ensure_emission_device(p))) return rc;
     if (n_frames == 0) return FRI_OK;
     if (!d_coefs || !d_out) return fail(FRI_E_INVALID, "NULL device buffer");
+    if ((uintptr_t)d_coefs & 15) return fail(FRI_E_INVALID, "d_coefs must be 16-byte aligned");
+    if (half && p->plan.geo.sample_bytes != 1)
+        return fail(FRI_E_UNSUPPORTED, "16-bit emission needs 8-bit samples (residues of 16-bit samples need 18 bits)");
     p->last_launches = 0;
-    FRI_CUDA(launch_emit(p->plan.geo, static_cast<const uint32_t *>(p->d_emit_src), p->emit_src.size(), d_coefs, n_frames, d_out,
+    FRI_CUDA(launch_emit(p->plan.geo, p->tables, p->emit_tables, p->emit_src.size(), d_coefs, n_frames, d_out, half,
                          static_cast<cudaStream_t>(stream), &p->last_launches));
     return FRI_OK;
 }
 
-int fri_encode_tq_emit(fri_plan *p, const void *pixels, uint32_t n_frames, const int32_t *q, int32_t *out)
+int fri_emit_device(fri_plan *p, const int32_t *d_coefs, uint32_t n_frames, int32_t *d_out, void *stream)
+{
+    return emit_device(p, d_coefs, n_frames, d_out, false, stream);
+}
+
+int fri_emit_device16(fri_plan *p, const int32_t *d_coefs, uint32_t n_frames, int16_t *d_out, void *stream)
+{
+    return emit_device(p, d_coefs, n_frames, d_out, true, stream);
+}
+
+static int encode_emit_host(fri_plan *p, const void *pixels, uint32_t n_frames, const int32_t *q, void *out, bool half)
 {
     int rc = enter_device(p);
     if (rc) return rc;
@@ -623,22 +671,26 @@ int fri_encode_tq_emit(fri_plan *p, const void *pixels, uint32_t n_frames, const
     if (!pixels || !out) return fail(FRI_E_INVALID, "NULL host buffer");
     if ((rc = ensure_slots(p))) return rc;
     const Geometry &g = p->plan.geo;
+    if (half && g.sample_bytes != 1)
+        return fail(FRI_E_UNSUPPORTED, "16-bit emission needs 8-bit samples (residues of 16-bit samples need 18 bits)");
     const size_t count = p->emit_src.size();
-    if (p->d_emit_tmp_frames < (size_t)kSlots) {
+    const size_t esz = half ? sizeof(int16_t) : sizeof(int32_t);
+    const size_t per_frame = (size_t)g.channels * count * esz;        // bytes
+    const size_t per_slot = (per_frame + 255) & ~(size_t)255;
+    if (p->d_emit_tmp_bytes < (size_t)kSlots * per_slot) {
         if (p->d_emit_tmp) cudaFree(p->d_emit_tmp);
         p->d_emit_tmp = nullptr;
-        p->d_emit_tmp_frames = 0;
-        FRI_CUDA(cudaMalloc(&p->d_emit_tmp, (size_t)kSlots * g.channels * count * sizeof(int32_t) + 16));
-        p->d_emit_tmp_frames = kSlots;
+        p->d_emit_tmp_bytes = 0;
+        FRI_CUDA(cudaMalloc(&p->d_emit_tmp, (size_t)kSlots * per_slot));
+        p->d_emit_tmp_bytes = (size_t)kSlots * per_slot;
     }
     QuantParams qp;
     make_quant_params(qp, q, 0);
     p->last_launches = 0;
-    const size_t per_frame = (size_t)g.channels * count;
     Pipeline &pl = p->pipe;
     for (uint32_t f = 0; f < n_frames; ++f) {
         Slot &s = p->slots[f % kSlots];
-        int32_t *d_emit = p->d_emit_tmp + (size_t)(f % kSlots) * per_frame;
+        uint8_t *d_emit = static_cast<uint8_t *>(p->d_emit_tmp) + (size_t)(f % kSlots) * per_slot;
         if (s.used) {
             FRI_CUDA(cudaStreamWaitEvent(pl.in, s.compute_done, 0));
             FRI_CUDA(cudaStreamWaitEvent(pl.compute, s.out_done, 0));
@@ -648,12 +700,11 @@ int fri_encode_tq_emit(fri_plan *p, const void *pixels, uint32_t n_frames, const
         FRI_CUDA(cudaEventRecord(pl.in_ready[0], pl.in));
         FRI_CUDA(cudaStreamWaitEvent(pl.compute, pl.in_ready[0], 0));
         FRI_CUDA(launch_encode(g, p->tables, qp, s.d_pixels, 1, s.d_coefs, s.d_dc, pl.compute, &p->last_launches));
-        FRI_CUDA(launch_emit(g, static_cast<const uint32_t *>(p->d_emit_src), count, s.d_coefs, 1, d_emit, pl.compute,
-                             &p->last_launches));
+        FRI_CUDA(launch_emit(g, p->tables, p->emit_tables, count, s.d_coefs, 1, d_emit, half, pl.compute, &p->last_launches));
         FRI_CUDA(cudaEventRecord(pl.band_done[0], pl.compute));
         FRI_CUDA(cudaEventRecord(s.compute_done, pl.compute));
         FRI_CUDA(cudaStreamWaitEvent(pl.out, pl.band_done[0], 0));
-        FRI_CUDA(cudaMemcpyAsync(out + (size_t)f * per_frame, d_emit, per_frame * sizeof(int32_t), cudaMemcpyDeviceToHost,
+        FRI_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(out) + (size_t)f * per_frame, d_emit, per_frame, cudaMemcpyDeviceToHost,
                                  pl.out));
         FRI_CUDA(cudaEventRecord(s.out_done, pl.out));
         s.used = true;
@@ -662,6 +713,16 @@ int fri_encode_tq_emit(fri_plan *p, const void *pixels, uint32_t n_frames, const
     FRI_CUDA(cudaStreamSynchronize(pl.compute));
     FRI_CUDA(cudaStreamSynchronize(pl.in));
     return FRI_OK;
+}
+
+int fri_encode_tq_emit(fri_plan *p, const void *pixels, uint32_t n_frames, const int32_t *q, int32_t *out)
+{
+    return encode_emit_host(p, pixels, n_frames, q, out, false);
+}
+
+int fri_encode_tq_emit16(fri_plan *p, const void *pixels, uint32_t n_frames, const int32_t *q, int16_t *out)
+{
+    return encode_emit_host(p, pixels, n_frames, q, out, true);
 }
 
 int fri_host_alloc(void **out, size_t bytes)

@@ -986,19 +986,37 @@ fri_coarse_inverse_kernel(const __grid_constant__ QuantParams qp, int sub_bits, 
 
 // ------------------------------------------------------------------------------------------
 // emission order: gather the quantized coefficients of every channel
-// into the order the reference's entropy coder consumes them, `None` slots dropped
+// into the order the reference's entropy coder consumes them, `None` slots dropped.
+//
+// Consecutive emitted coefficients come from different tiles (the scan walks one tree level across
+// the whole image), so a flat gather reads one 32-byte sector per 4-byte coefficient.  Instead one
+// CTA takes a group of lattice-adjacent tiles (the same groups the transform kernels use): the
+// group's 2 KB coefficient blocks are read coalesced into shared memory, and its emission slots —
+// which the plan lists per group in increasing emission index, so that the nodes a scan row picks
+// up inside the group are adjacent — are written as runs.
 // ------------------------------------------------------------------------------------------
+template <typename T>
 __global__ void __launch_bounds__(256)
-fri_emit_kernel(const uint32_t *__restrict__ src, unsigned long long count, int channels, int n_tiles,
-                const int32_t *__restrict__ coefs, int32_t *__restrict__ out)
+fri_emit_kernel(const GroupDesc *__restrict__ groups, const uint32_t *__restrict__ goff, const uint32_t *__restrict__ dst,
+                const uint16_t *__restrict__ loc, unsigned long long count, int channels, int n_tiles,
+                const int32_t *__restrict__ coefs, T *__restrict__ out)
 {
-    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    const int ch = blockIdx.y, frame = blockIdx.z;
-    const uint32_t s = __ldg(src + i);
-    const size_t tile = s >> kBaseDepth, pos = s & (kTileLeaves - 1);
-    const int32_t v = __ldg(coefs + ((((size_t)frame * n_tiles + tile) * channels + ch) << kBaseDepth) + pos);
-    __stcs(out + ((size_t)frame * channels + ch) * count + i, v);
+    extern __shared__ __align__(16) int32_t es[];
+    const GroupDesc gd = groups[blockIdx.x];
+    const int n_present = __popc(gd.tile_mask), frame = blockIdx.y;
+    const uint32_t k0 = goff[blockIdx.x], k1 = goff[blockIdx.x + 1];
+    for (int ch = 0; ch < channels; ++ch) {
+        // tile t of the group, channel ch: 512 coefficients at ((frame * n_tiles + tile_base + t) * C + ch) << 9
+        for (int idx = threadIdx.x; idx < n_present * (kTileLeaves / 4); idx += blockDim.x) {
+            const int t = idx >> 7, v = idx & 127;
+            const int4 *src = reinterpret_cast<const int4 *>(coefs + ((((size_t)frame * n_tiles + gd.tile_base + t) * channels + ch) << kBaseDepth));
+            reinterpret_cast<int4 *>(es)[idx] = __ldcs(src + v);
+        }
+        __syncthreads();
+        T *o = out + ((size_t)frame * channels + ch) * count;
+        for (uint32_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) o[__ldg(dst + k)] = (T)es[__ldg(loc + k)];
+        __syncthreads();
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1061,6 +1079,8 @@ cudaError_t configure_kernels()
     FRI_CFG4(fri_decode_kernel);
     FRI_CFG(fri_coarse_forward_kernel);
     FRI_CFG(fri_coarse_inverse_kernel);
+    FRI_CFG(fri_emit_kernel<int32_t>);
+    FRI_CFG(fri_emit_kernel<int16_t>);
 #undef FRI_CFG4
 #undef FRI_CFG
     return cudaSuccess;
@@ -1186,16 +1206,23 @@ cudaError_t launch_unpack16(const int16_t *d_src, int32_t *d_dst, size_t count, 
     return cudaGetLastError();
 }
 
-cudaError_t launch_emit(const Geometry &g, const uint32_t *d_src, uint64_t count, const int32_t *d_coefs, uint32_t n_frames,
-                        int32_t *d_out, cudaStream_t stream, uint32_t *launches)
+cudaError_t launch_emit(const Geometry &g, const DeviceTables &t, const EmitTables &et, uint64_t count, const int32_t *d_coefs,
+                        uint32_t n_frames, void *d_out, bool half, cudaStream_t stream, uint32_t *launches)
 {
     if (count == 0 || n_frames == 0) return cudaSuccess;
-    for (uint32_t f0 = 0; f0 < n_frames; f0 += 65535u) {  // gridDim.z limit
+    const size_t smem = (size_t)g.group_a * g.group_b * kTileLeaves * sizeof(int32_t);
+    const size_t esz = half ? sizeof(int16_t) : sizeof(int32_t);
+    for (uint32_t f0 = 0; f0 < n_frames; f0 += 65535u) {  // gridDim.y limit
         const uint32_t nf = n_frames - f0 < 65535u ? n_frames - f0 : 65535u;
-        const dim3 grid((unsigned)((count + 255) / 256), (unsigned)g.channels, nf);
-        fri_emit_kernel<<<grid, 256, 0, stream>>>(d_src, count, g.channels, g.n_fractals,
-                                                  d_coefs + (int64_t)f0 * g.coefs_per_frame,
-                                                  d_out + (size_t)f0 * g.channels * count);
+        const dim3 grid((unsigned)g.n_groups, nf);
+        const int32_t *c = d_coefs + (int64_t)f0 * g.coefs_per_frame;
+        uint8_t *o = static_cast<uint8_t *>(d_out) + (size_t)f0 * g.channels * count * esz;
+        if (half)
+            fri_emit_kernel<int16_t><<<grid, 256, smem, stream>>>(t.groups, et.goff, et.dst, et.loc, count, g.channels,
+                                                                  g.n_fractals, c, reinterpret_cast<int16_t *>(o));
+        else
+            fri_emit_kernel<int32_t><<<grid, 256, smem, stream>>>(t.groups, et.goff, et.dst, et.loc, count, g.channels,
+                                                                  g.n_fractals, c, reinterpret_cast<int32_t *>(o));
         if (launches) ++*launches;
     }
     return cudaGetLastError();

@@ -116,9 +116,18 @@ cudaError_t launch_decode(const Geometry &g, const DeviceTables &t, const QuantP
                           uint32_t n_frames, void *d_pixels, int32_t *d_dc, cudaStream_t stream,
                           uint32_t *launches, int group_begin = 0, int group_end = -1);
 
-// Gathers coefficients into emission order: out[frame][ch][i] = coefs[frame][src[i] >> 9][ch][src[i] & 511].
-cudaError_t launch_emit(const Geometry &g, const uint32_t *d_src, uint64_t count, const int32_t *d_coefs, uint32_t n_frames,
-                        int32_t *d_out, cudaStream_t stream, uint32_t *launches);
+// Emission tables of a plan (device side): the `Some` coefficient slots partitioned by group, each
+// group's slots in increasing emission index.
+struct EmitTables {
+    const uint32_t *goff = nullptr;  // [n_groups + 1] offsets into dst / loc
+    const uint32_t *dst = nullptr;   // [count] emission index of the slot (position in one channel's stream)
+    const uint16_t *loc = nullptr;   // [count] (tile - group's first tile) * 512 + coefficient index
+};
+
+// Gathers coefficients into emission order: out[frame][ch][dst[k]] = coefficient loc[k] of the group, for every
+// group; out is int32 or (half) int16, [n_frames][C][count].
+cudaError_t launch_emit(const Geometry &g, const DeviceTables &t, const EmitTables &et, uint64_t count, const int32_t *d_coefs,
+                        uint32_t n_frames, void *d_out, bool half, cudaStream_t stream, uint32_t *launches);
 
 // 16-bit transport of the host-buffer entry points: saturating i32 -> i16 repack and its inverse
 // (count is a multiple of 8; both pointers 16-byte aligned).

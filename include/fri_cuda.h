@@ -141,6 +141,8 @@ int fri_decode_tq16(fri_plan *plan, const int16_t *coefs, uint32_t n_frames, con
  *                            `None` slots dropped (what the three scans push, :287 / :298 / :314).
  *   fri_encode_tq_emit       host pixels -> host emitted streams: transform + quantization +
  *                            emission gather on the device, one D2H copy per frame.
+ *   fri_emit_device16 /      the same with int16 output streams (8-bit samples only, like
+ *   fri_encode_tq_emit16     fri_encode_tq16): half the bytes over PCIe; saturating.
  * All of them fail with FRI_E_UNSUPPORTED (and say so in fri_last_error) for the image sizes on
  * which the reference's own scan fails its assertion at wavelet_transform.rs:701, e.g. 257x300.
  */
@@ -148,6 +150,8 @@ uint64_t fri_plan_emission_count(fri_plan *plan);
 int fri_plan_emission_order(fri_plan *plan, uint32_t *order);
 int fri_emit_device(fri_plan *plan, const int32_t *d_coefs, uint32_t n_frames, int32_t *d_out, void *stream);
 int fri_encode_tq_emit(fri_plan *plan, const void *pixels, uint32_t n_frames, const int32_t *q, int32_t *out);
+int fri_emit_device16(fri_plan *plan, const int32_t *d_coefs, uint32_t n_frames, int16_t *d_out, void *stream);
+int fri_encode_tq_emit16(fri_plan *plan, const void *pixels, uint32_t n_frames, const int32_t *q, int16_t *out);
 
 /* Pinned host memory (cudaHostAlloc) for the host-buffer entry points. */
 int fri_host_alloc(void **out, size_t bytes);

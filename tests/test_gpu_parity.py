@@ -300,6 +300,34 @@ def test_emitted_streams_follow_the_reference_scan_order(shape):
         plan.emit_device(d_coefs.data_ptr(), 2, d_out.data_ptr())
         torch.cuda.synchronize()
         assert np.array_equal(d_out.cpu().numpy(), got)
+        # int16 streams (fri_encode_tq_emit16 / fri_emit_device16)
+        got16 = plan.encode_emit(frames, q, dtype=np.int16)
+        assert got16.dtype == np.int16 and np.array_equal(got16, got)
+        d_out16 = torch.empty((2, c, plan.emission_count()), dtype=torch.int16, device=dev)
+        plan.emit_device(d_coefs.data_ptr(), 2, d_out16.data_ptr(), half=True)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_out16.cpu().numpy(), got)
+
+
+def test_emission_gather_full_size():
+    """The group-staged gather at BASELINE.json's full size against torch indexing with the plan's own
+    order (the order itself is checked against the dict-based restatement on small shapes)."""
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda", 0)
+    w, h, c = 4096, 4096, 3
+    with capi.Plan(w, h, c) as plan:
+        order = torch.from_numpy(plan.emission_order().astype(np.int64))
+        some = torch.from_numpy(plan.masks().reshape(-1))
+        src = order[some[order]].to(dev)
+        cnt = plan.emission_count()
+        assert len(src) == cnt
+        gen = torch.Generator(device=dev).manual_seed(7)
+        coefs = torch.randint(-255, 256, plan.coef_shape, generator=gen, device=dev, dtype=torch.int32)
+        out = torch.empty((1, c, cnt), dtype=torch.int32, device=dev)
+        plan.emit_device(coefs.data_ptr(), 1, out.data_ptr())
+        torch.cuda.synchronize()
+        for ch in range(c):
+            assert torch.equal(out[0, ch], coefs[:, ch, :].reshape(-1)[src])
 
 
 def test_stage_interface_mirrors_reference_pipeline():
