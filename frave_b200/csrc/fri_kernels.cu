@@ -733,7 +733,11 @@ __device__ __forceinline__ void zero_region(const Geometry &g, uint8_t *region)
 // behind the barrier wait.
 constexpr int kWriteAhead = 8;
 
-constexpr int kMixedAhead = 2;
+// Partially owned chunks are written one 32-bit word per thread and iteration (four neighbouring
+// lanes share a chunk): a word is skipped, stored whole, or — only the word the group's outline
+// passes through — stored bytewise.  One chunk per thread would make every warp walk through all
+// four words' byte paths.
+constexpr int kMixedAhead = 2;  // word-loop iterations whose table entries are fetched before the barrier
 
 struct WriteAhead {
     uint32_t e[kWriteAhead];      // fully owned chunks
@@ -757,12 +761,30 @@ __device__ __forceinline__ WriteAhead write_out_preload(const Geometry &g, const
     const int n_all = g.list_all[rv.phi0];
 #pragma unroll
     for (int u = 0; u < kMixedAhead; ++u) {
-        const int k = n_full + threadIdx.x + u * blockDim.x;
+        const int k = n_full + ((threadIdx.x + u * blockDim.x) >> 2);
         const bool on = rv.interior && k < n_all;
         w.me[u] = on ? ld_table(cl + k, pol) : kNoChunk;
         w.mm[u] = on ? ld_table(cmk + k, pol) : 0u;
     }
     return w;
+}
+
+// Word `w` (0..3) of the partially owned chunk `e` with byte mask `m`.
+__device__ __forceinline__ void store_word_masked(const RegionView &rv, const uint8_t *region, uint32_t e, uint32_t m, int w)
+{
+    const uint32_t nib = (m >> (4 * w)) & 15u;
+    if (nib == 0) return;
+    const int r = (int)(e >> 16), s = ((int)(e & 0xffffu) << 4) + 4 * w;
+    uint8_t *gp = reinterpret_cast<uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s;
+    const uint32_t v = *reinterpret_cast<const uint32_t *>(region + s);
+    if (nib == 15u) {
+        *reinterpret_cast<uint32_t *>(gp) = v;
+    } else {
+        if (nib & 1u) gp[0] = (uint8_t)v;
+        if (nib & 2u) gp[1] = (uint8_t)(v >> 8);
+        if (nib & 4u) gp[2] = (uint8_t)(v >> 16);
+        if (nib & 8u) gp[3] = (uint8_t)(v >> 24);
+    }
 }
 
 __device__ __forceinline__ void write_out_group(const Geometry &g, const GroupDesc &gd, const RegionView &rv,
@@ -785,28 +807,26 @@ __device__ __forceinline__ void write_out_group(const Geometry &g, const GroupDe
 #if FRI_TRACE
         if ((threadIdx.x == 0 || threadIdx.x == 255) && blockIdx.x < 16384) g_trace2[4 * blockIdx.x + (threadIdx.x == 0 ? 0 : 1)] = gtime();
 #endif
+#pragma unroll 1
         for (int k = threadIdx.x + kWriteAhead * n_threads; k < n_full; k += n_threads) {
             const uint32_t e = ld_table(cl + k, pol);
             const int r = (int)(e >> 16), s = (int)(e & 0xffffu) << 4;
             *reinterpret_cast<int4 *>(reinterpret_cast<uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s) =
                 *reinterpret_cast<const int4 *>(region + s);
         }
+        const int w = threadIdx.x & 3;
 #pragma unroll
         for (int u = 0; u < kMixedAhead; ++u)
-            if (ahead.me[u] != kNoChunk) {
-                const int r = (int)(ahead.me[u] >> 16), s = (int)(ahead.me[u] & 0xffffu) << 4;
-                store_chunk_masked(reinterpret_cast<uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s, region + s, ahead.mm[u]);
-            }
-        for (int k = n_full + threadIdx.x + kMixedAhead * n_threads; k < n_all; k += n_threads) {
-            const uint32_t e = ld_table(cl + k, pol);
-            const int r = (int)(e >> 16), s = (int)(e & 0xffffu) << 4;
-            store_chunk_masked(reinterpret_cast<uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s, region + s, ld_table(cmk + k, pol));
-        }
+            if (ahead.me[u] != kNoChunk) store_word_masked(rv, region, ahead.me[u], ahead.mm[u], w);
+#pragma unroll 1
+        for (int k = n_full + ((threadIdx.x + kMixedAhead * n_threads) >> 2); k < n_all; k += n_threads >> 2)
+            store_word_masked(rv, region, ld_table(cl + k, pol), ld_table(cmk + k, pol), w);
 #if FRI_TRACE
         if ((threadIdx.x == 0 || threadIdx.x == 255) && blockIdx.x < 16384) g_trace2[4 * blockIdx.x + (threadIdx.x == 0 ? 2 : 3)] = gtime();
 #endif
     } else {
         const int stride32 = (int)g.row_stride;
+#pragma unroll 1
         for (int k = threadIdx.x; k < n_all; k += n_threads) {
             const uint32_t e = ld_table(cl + k, pol);
             const int r = (int)(e >> 16), s = (int)(e & 0xffffu) << 4;
