@@ -545,6 +545,9 @@ __device__ __forceinline__ void prefetch_group_coefs(const Geometry &g, const Gr
         asm volatile("prefetch.global.L2 [%0];" ::"l"(first + (size_t)i * 128));
 }
 
+#ifndef FRI_DEC_NEXT_TILE
+#define FRI_DEC_NEXT_TILE 1
+#endif
 // The coefficients of levels 6..8 a lane consumes for one (tile, channel): 2 x 128, 2 x 64, 2 x 32 bits.
 struct LaneCoefs {
     int4 a8, b8;
@@ -585,15 +588,21 @@ __device__ __forceinline__ void decode_tiles(const Geometry &g, const QuantParam
     const bool sparse_group = (gd.tile_mask & (gd.tile_mask + 1u)) != 0;
     const int grp = min(lane >> 3, C - 1), j8 = lane & 7;
     const bool grp_live = (lane >> 3) < C;
+    // The first channel's register-level coefficients of a tile are requested ahead of time: for the
+    // warp's first tile before the top levels are unfolded (one round trip to L2/HBM covers both),
+    // for every later tile while the previous tile's last channel is being unfolded.
+    TaskAddr ta{};
+    LaneCoefs cur{};
+    if (warp < n_present) {
+        ta = task_addr<C, DEEP>(g, tile_unit, frame, gd.tile_base + warp, 0);
+        cur = load_lane_coefs(coefs + ta.block, ta.node, lane);
+    }
     for (int e = warp; e < n_present; e += n_warps) {
         const int slot = sparse_group ? (int)__fns(gd.tile_mask, 0, e + 1) : e;
-        const TaskAddr ta = task_addr<C, DEEP>(g, tile_unit, frame, gd.tile_base + e, 0);
+        const bool has_next = e + n_warps < n_present;
+        const TaskAddr tn = has_next ? task_addr<C, DEEP>(g, tile_unit, frame, gd.tile_base + e + n_warps, 0) : ta;
         const bool lastB = ta.last && lane == 31;
         const size_t node = ta.node;
-
-        // The first channel's register-level coefficients are requested before the top levels are
-        // unfolded, so that one round trip to L2/HBM covers both.
-        LaneCoefs cur = load_lane_coefs(coefs + ta.block, node, lane);
 
         // ---- levels 0..5 of all channels, 8 lanes per channel
         {
@@ -648,6 +657,9 @@ __device__ __forceinline__ void decode_tiles(const Geometry &g, const QuantParam
             int2 a7 = cur.a7, b7 = cur.b7;
             int a6 = cur.a6, b6 = cur.b6;
             if (ch + 1 < C) cur = load_lane_coefs(coefs + ta.block + ((int64_t)(ch + 1) << depth), node, lane);
+#if FRI_DEC_NEXT_TILE
+            else if (has_next) cur = load_lane_coefs(coefs + tn.block, tn.node, lane);
+#endif
             const int sA = scratch[ch * kScratchInts + lane], sB = scratch[ch * kScratchInts + 32 + lane];
 
             if ((qp.active >> (top + 6)) & 0xfu) {
@@ -712,6 +724,10 @@ __device__ __forceinline__ void decode_tiles(const Geometry &g, const QuantParam
 #undef FRI_ST
         }
         __syncwarp();
+        ta = tn;
+#if !FRI_DEC_NEXT_TILE
+        if (has_next) cur = load_lane_coefs(coefs + ta.block, ta.node, lane);
+#endif
     }
 }
 
@@ -737,7 +753,10 @@ constexpr int kWriteAhead = 8;
 // lanes share a chunk): a word is skipped, stored whole, or — only the word the group's outline
 // passes through — stored bytewise.  One chunk per thread would make every warp walk through all
 // four words' byte paths.
-constexpr int kMixedAhead = 2;  // word-loop iterations whose table entries are fetched before the barrier
+#ifndef FRI_MIXED_AHEAD
+#define FRI_MIXED_AHEAD 5
+#endif
+constexpr int kMixedAhead = FRI_MIXED_AHEAD;  // word-loop iterations whose table entries are fetched before the barrier
 
 struct WriteAhead {
     uint32_t e[kWriteAhead];      // fully owned chunks
