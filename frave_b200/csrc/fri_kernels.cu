@@ -567,6 +567,29 @@ __device__ __forceinline__ LaneCoefs load_lane_coefs(const int32_t *__restrict__
     return c;
 }
 
+// The top 64 coefficients of one channel as lane j8 of the channel's lane group consumes them.
+struct TopCoefs {
+    int4 d5;
+    int2 d4;
+    int d3, d2, d1, d0, s0;
+};
+template <bool DEEP>
+__device__ __forceinline__ TopCoefs load_top_coefs(const int32_t *__restrict__ coefs, const int32_t *__restrict__ dc_in,
+                                                   const TaskAddr &ta, int grp, int j8, int depth, int sub_bits)
+{
+    const int32_t *in = coefs + ta.block + ((int64_t)grp << depth);
+    const size_t node = ta.node;
+    TopCoefs t;
+    t.d5 = __ldcs(reinterpret_cast<const int4 *>(in + (node << 5)) + j8);
+    t.d4 = __ldcs(reinterpret_cast<const int2 *>(in + (node << 4)) + j8);
+    t.d3 = __ldcs(in + (node << 3) + j8);
+    t.d2 = __ldcs(in + (node << 2) + (j8 >> 1));
+    t.d1 = __ldcs(in + (node << 1) + (j8 >> 2));
+    t.d0 = __ldcs(in + node);
+    t.s0 = (!DEEP || sub_bits == 0) ? __ldcs(in) : dc_in[ta.dc + ((int64_t)grp << sub_bits)];
+    return t;
+}
+
 // Dequantization + inverse transform of the tiles of one group into the staged region; mirror
 // image of encode_tiles: lane group lane / 8 first unfolds levels 0..5 of its channel (lane j
 // ends with the eight level-6 low-pass values 8j .. 8j+7) into the warp's scratch, then every
@@ -606,14 +629,10 @@ __device__ __forceinline__ void decode_tiles(const Geometry &g, const QuantParam
 
         // ---- levels 0..5 of all channels, 8 lanes per channel
         {
-            const int32_t *in = coefs + ta.block + ((int64_t)grp << depth);
-            int4 d5 = __ldcs(reinterpret_cast<const int4 *>(in + (node << 5)) + j8);
-            int2 d4 = __ldcs(reinterpret_cast<const int2 *>(in + (node << 4)) + j8);
-            int d3 = __ldcs(in + (node << 3) + j8);
-            int d2 = __ldcs(in + (node << 2) + (j8 >> 1));
-            int d1 = __ldcs(in + (node << 1) + (j8 >> 2));
-            int d0 = __ldcs(in + node);
-            int s0 = sub_bits == 0 ? __ldcs(in) : dc_in[ta.dc + ((int64_t)grp << sub_bits)];
+            const TopCoefs tc = load_top_coefs<DEEP>(coefs, dc_in, ta, grp, j8, depth, sub_bits);
+            int4 d5 = tc.d5;
+            int2 d4 = tc.d4;
+            int d3 = tc.d3, d2 = tc.d2, d1 = tc.d1, d0 = tc.d0, s0 = tc.s0;
             if ((qp.active >> top) & 0x7fu) {
                 const bool lastG = ta.last && j8 == 7;
                 d5.x = dequant_layer(qp, d5.x, top + 5); d5.y = dequant_layer(qp, d5.y, top + 5);
