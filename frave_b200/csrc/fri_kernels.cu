@@ -123,6 +123,24 @@ cudaError_t debug_trace2(unsigned long long *out, size_t n) { return cudaMemcpyF
 
 namespace {
 
+// Compile-time quantization classes of the register levels (6..8) of a depth-9 tile, so that the two
+// configurations that matter do not walk the generic per-level mode tests for every channel:
+//   kQuantNone      layers 6..9 all have divisor 1 — the reference's matrix (quantization.rs:3-5);
+//   kQuantSmallest  only layers 8 and 9 are active, with one divisor — "dividing the smallest layer
+//                   of fractals" (README.md:12; BASELINE.json's divisor sweep);
+//   kQuantGeneric   anything else (and every deep-tree launch).
+// Layers 0..5 are handled by the run-time tests in every class (once per tile, not per channel).
+constexpr int kQuantGeneric = 0, kQuantNone = 1, kQuantSmallest = 2;
+
+int quant_class(const QuantParams &qp, const Geometry &g)
+{
+    if (g.sub_bits != 0) return kQuantGeneric;
+    const uint32_t hi = (qp.active >> 6) & 0xfu;
+    if (hi == 0) return kQuantNone;
+    if (hi == 0xcu && qp.q[8] == qp.q[9]) return kQuantSmallest;
+    return kQuantGeneric;
+}
+
 // ------------------------------------------------------------------------------------------
 // device helpers
 // ------------------------------------------------------------------------------------------
@@ -383,7 +401,7 @@ __device__ __forceinline__ void stage_group(const Geometry &g, const GroupDesc &
 //   phase 2 (all channels at once): lane group lane / 8 owns a channel; lane j of the group
 //                          folds s6[8j .. 8j+7] through levels 5..3 in registers and levels 2..0
 //                          with three shuffles inside the group.
-template <int C, typename S, bool DEEP>
+template <int C, typename S, bool DEEP, int QS>
 __device__ __forceinline__ void encode_tiles(const Geometry &g, const QuantParams &qp, const GroupDesc &gd, const RegionView &rv,
                                              const uint32_t *__restrict__ tile_unit, int frame, const uint8_t *region,
                                              int32_t *scratch, int32_t *__restrict__ coefs, int32_t *__restrict__ dc_out,
@@ -445,7 +463,23 @@ __device__ __forceinline__ void encode_tiles(const Geometry &g, const QuantParam
             scratch[ch * kScratchInts + 32 + lane] = sB;  // low-pass of node 96 + lane
 
             // quantization.rs:13 — layer = level, except the last node of a level: level + 1
-            if ((qp.active >> (top + 6)) & 0xfu) {
+            if (QS == kQuantSmallest) {
+                // only layers 8 and 9 are active and share one divisor: every level-8 node (the last one
+                // sits in layer 9) and the last node of level 7 (layer 8)
+                int r7 = b7[1];
+                if (qp.small & 0x100u) {
+                    const SmallDiv dv = qp.sdiv(8);
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) { a8[m] = trunc_div_small(a8[m], dv); b8[m] = trunc_div_small(b8[m], dv); }
+                    r7 = trunc_div_small(r7, dv);
+                } else {
+                    const Div dv = qp.div(8);
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) { a8[m] = trunc_div(a8[m], dv); b8[m] = trunc_div(b8[m], dv); }
+                    r7 = trunc_div(r7, dv);
+                }
+                if (lane == 31) b7[1] = r7;
+            } else if (QS == kQuantGeneric && ((qp.active >> (top + 6)) & 0xfu)) {
                 const int r8 = b8[3], r7 = b7[1], r6 = b6;  // unquantized values of the level-last nodes
 #define FRI_QLEVEL(L, N, A, B)                                                              \
                 if ((qp.active >> (top + (L))) & 1u) {                                              \
@@ -594,7 +628,7 @@ __device__ __forceinline__ TopCoefs load_top_coefs(const int32_t *__restrict__ c
 // image of encode_tiles: lane group lane / 8 first unfolds levels 0..5 of its channel (lane j
 // ends with the eight level-6 low-pass values 8j .. 8j+7) into the warp's scratch, then every
 // lane unfolds its two depth-3 subtrees per channel and scatters the 16 clamped leaves.
-template <int C, typename S, bool DEEP>
+template <int C, typename S, bool DEEP, int QS>
 __device__ __forceinline__ void decode_tiles(const Geometry &g, const QuantParams &qp, const GroupDesc &gd, const RegionView &rv,
                                              const uint32_t *__restrict__ tile_unit, int frame, uint8_t *region,
                                              int32_t *scratch, const int32_t *__restrict__ coefs,
@@ -681,7 +715,28 @@ __device__ __forceinline__ void decode_tiles(const Geometry &g, const QuantParam
 #endif
             const int sA = scratch[ch * kScratchInts + lane], sB = scratch[ch * kScratchInts + 32 + lane];
 
-            if ((qp.active >> (top + 6)) & 0xfu) {
+            if (QS == kQuantSmallest) {
+                // only layers 8 and 9 are active and share one divisor (see encode_tiles)
+                int r7 = b7.y;
+#define FRI_DQ8                                                                        \
+                a8.x = f(a8.x); a8.y = f(a8.y); a8.z = f(a8.z); a8.w = f(a8.w);             \
+                b8.x = f(b8.x); b8.y = f(b8.y); b8.z = f(b8.z); b8.w = f(b8.w); r7 = f(r7);
+                if (qp.multiply) {
+                    const unsigned q = (unsigned)qp.q[8];
+                    auto f = [q](int x) { return (int)((unsigned)x * q); };
+                    FRI_DQ8
+                } else if (qp.pow2 & 0x100u) {
+                    const int k = qp.pow2_shift[8];
+                    auto f = [k](int x) { return trunc_div_pow2(x, k); };
+                    FRI_DQ8
+                } else {
+                    const Div dv = qp.div(8);
+                    auto f = [dv](int x) { return trunc_div(x, dv); };
+                    FRI_DQ8
+                }
+#undef FRI_DQ8
+                if (lane == 31) b7.y = r7;
+            } else if (QS == kQuantGeneric && ((qp.active >> (top + 6)) & 0xfu)) {
                 const int r8 = b8.w, r7 = b7.y, r6 = b6;  // raw values of the level-last nodes
                 const int mul = qp.multiply;
 #define FRI_DQLEVEL(L, STMTS)                                                               \
@@ -892,7 +947,7 @@ __device__ __forceinline__ size_t region_bytes(const Geometry &g) { return ((siz
 #ifndef FRI_DEC_MINB
 #define FRI_DEC_MINB 4
 #endif
-template <int C, typename S, bool DEEP>
+template <int C, typename S, bool DEEP, int QS>
 __global__ void __launch_bounds__(kThreads, FRI_ENC_MINB)
 fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ QuantParams qp,
                   const GroupDesc *__restrict__ groups, const uint32_t *__restrict__ tile_unit,
@@ -944,14 +999,14 @@ fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
     }
     __syncthreads();
     FRI_TRACE_MARK(1);
-    encode_tiles<C, S, DEEP>(g, qp, gd, rv, tile_unit, frame, region, scratch, coefs, dc_out, two_stage);
+    encode_tiles<C, S, DEEP, QS>(g, qp, gd, rv, tile_unit, frame, region, scratch, coefs, dc_out, two_stage);
 #if FRI_TRACE
     __syncthreads();
 #endif
     FRI_TRACE_MARK(2);
 }
 
-template <int C, typename S, bool DEEP>
+template <int C, typename S, bool DEEP, int QS>
 __global__ void __launch_bounds__(kThreads, FRI_DEC_MINB)
 fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ QuantParams qp,
                   const GroupDesc *__restrict__ groups, const uint32_t *__restrict__ tile_unit,
@@ -972,7 +1027,7 @@ fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
         zero_region(g, region);
         __syncthreads();
     }
-    decode_tiles<C, S, DEEP>(g, qp, gd, rv, tile_unit, frame, region, scratch, coefs, dc_in);
+    decode_tiles<C, S, DEEP, QS>(g, qp, gd, rv, tile_unit, frame, region, scratch, coefs, dc_in);
     const WriteAhead ahead = write_out_preload(g, rv, chunk_list, chunk_mask, pol);
     __syncthreads();
     FRI_TRACE_MARK(1);
@@ -1124,15 +1179,23 @@ cudaError_t configure_kernels()
 {
     cudaError_t e;
 #define FRI_CFG(k) if ((e = set_smem(k, kMaxSmem)) != cudaSuccess) return e
-#define FRI_CFG4(name)                     \
-    FRI_CFG((name<1, uint8_t, false>));    \
-    FRI_CFG((name<3, uint8_t, false>));    \
-    FRI_CFG((name<1, uint16_t, false>));   \
-    FRI_CFG((name<3, uint16_t, false>));   \
-    FRI_CFG((name<1, uint8_t, true>));     \
-    FRI_CFG((name<3, uint8_t, true>));     \
-    FRI_CFG((name<1, uint16_t, true>));    \
-    FRI_CFG((name<3, uint16_t, true>))
+#define FRI_CFG4(name)                                      \
+    FRI_CFG((name<1, uint8_t, false, kQuantGeneric>));      \
+    FRI_CFG((name<3, uint8_t, false, kQuantGeneric>));      \
+    FRI_CFG((name<1, uint16_t, false, kQuantGeneric>));     \
+    FRI_CFG((name<3, uint16_t, false, kQuantGeneric>));     \
+    FRI_CFG((name<1, uint8_t, false, kQuantNone>));         \
+    FRI_CFG((name<3, uint8_t, false, kQuantNone>));         \
+    FRI_CFG((name<1, uint16_t, false, kQuantNone>));        \
+    FRI_CFG((name<3, uint16_t, false, kQuantNone>));        \
+    FRI_CFG((name<1, uint8_t, false, kQuantSmallest>));     \
+    FRI_CFG((name<3, uint8_t, false, kQuantSmallest>));     \
+    FRI_CFG((name<1, uint16_t, false, kQuantSmallest>));    \
+    FRI_CFG((name<3, uint16_t, false, kQuantSmallest>));    \
+    FRI_CFG((name<1, uint8_t, true, kQuantGeneric>));       \
+    FRI_CFG((name<3, uint8_t, true, kQuantGeneric>));       \
+    FRI_CFG((name<1, uint16_t, true, kQuantGeneric>));      \
+    FRI_CFG((name<3, uint16_t, true, kQuantGeneric>))
     FRI_CFG4(fri_encode_kernel);
     FRI_CFG4(fri_decode_kernel);
     FRI_CFG(fri_coarse_forward_kernel);
@@ -1173,6 +1236,7 @@ cudaError_t launch_encode(const Geometry &g, const DeviceTables &t, const QuantP
     const bool whole = group_begin == 0 && group_end == g.n_groups;
     if (n_frames == 0 || n_groups <= 0) return cudaSuccess;
     const size_t smem = kernel_smem_bytes(g);
+    const int qclass = quant_class(qp, g);
     int lookahead = resident_ctas(g);  // prefetch distance: the group that will reuse this CTA's slot
     if (const char *env = std::getenv("FRI_LOOKAHEAD")) lookahead = std::atoi(env);  // tuning knob
     if (!whole) lookahead = 0;  // banded host pipeline: rows of later groups may not be on the device yet
@@ -1183,18 +1247,21 @@ cudaError_t launch_encode(const Geometry &g, const DeviceTables &t, const QuantP
         const uint8_t *p = px + (int64_t)f0 * g.frame_bytes;
         int32_t *c = d_coefs + (int64_t)f0 * g.coefs_per_frame;
         int32_t *dc = d_dc ? d_dc + (((int64_t)f0 * g.n_fractals * g.channels) << g.sub_bits) : nullptr;
-#define FRI_LAUNCH(CC, SS)                                                                                                        \
-        do {                                                                                                                      \
-            if (g.sub_bits == 0)                                                                                                  \
-                fri_encode_kernel<CC, SS, false><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.stage_list, p, c, dc, lookahead, group_begin); \
-            else                                                                                                                  \
-                fri_encode_kernel<CC, SS, true><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.stage_list, p, c, dc, lookahead, group_begin);  \
+#define FRI_LAUNCH_Q(CC, SS, DD, QQ) \
+    fri_encode_kernel<CC, SS, DD, QQ><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.stage_list, p, c, dc, lookahead, group_begin)
+#define FRI_LAUNCH(CC, SS)                                                          \
+        do {                                                                        \
+            if (g.sub_bits != 0) FRI_LAUNCH_Q(CC, SS, true, kQuantGeneric);         \
+            else if (qclass == kQuantNone) FRI_LAUNCH_Q(CC, SS, false, kQuantNone); \
+            else if (qclass == kQuantSmallest) FRI_LAUNCH_Q(CC, SS, false, kQuantSmallest); \
+            else FRI_LAUNCH_Q(CC, SS, false, kQuantGeneric);                        \
         } while (0)
         if (g.channels == 1 && g.sample_bytes == 1) FRI_LAUNCH(1, uint8_t);
         else if (g.channels == 3 && g.sample_bytes == 1) FRI_LAUNCH(3, uint8_t);
         else if (g.channels == 1 && g.sample_bytes == 2) FRI_LAUNCH(1, uint16_t);
         else FRI_LAUNCH(3, uint16_t);
 #undef FRI_LAUNCH
+#undef FRI_LAUNCH_Q
         if (launches) ++*launches;
     }
     if (g.sub_bits > 0 && group_end == g.n_groups) {  // after the last band
@@ -1214,6 +1281,7 @@ cudaError_t launch_decode(const Geometry &g, const DeviceTables &t, const QuantP
     const int n_groups = group_end - group_begin;
     if (n_frames == 0 || n_groups <= 0) return cudaSuccess;
     const size_t smem = kernel_smem_bytes(g);
+    const int qclass = quant_class(qp, g);
     if (g.sub_bits > 0 && group_begin == 0) {  // before the first band
         const unsigned blocks = (unsigned)((int64_t)n_frames * g.n_fractals * g.channels);
         const size_t cs = ((size_t)3 << g.sub_bits) / 2 * sizeof(int32_t) + 16;
@@ -1227,18 +1295,21 @@ cudaError_t launch_decode(const Geometry &g, const DeviceTables &t, const QuantP
         uint8_t *p = px + (int64_t)f0 * g.frame_bytes;
         const int32_t *c = d_coefs + (int64_t)f0 * g.coefs_per_frame;
         int32_t *dc = d_dc ? d_dc + (((int64_t)f0 * g.n_fractals * g.channels) << g.sub_bits) : nullptr;
-#define FRI_LAUNCH(CC, SS)                                                                                                        \
-        do {                                                                                                                      \
-            if (g.sub_bits == 0)                                                                                                  \
-                fri_decode_kernel<CC, SS, false><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, t.chunk_mask, c, dc, p, group_begin); \
-            else                                                                                                                  \
-                fri_decode_kernel<CC, SS, true><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, t.chunk_mask, c, dc, p, group_begin);  \
+#define FRI_LAUNCH_Q(CC, SS, DD, QQ) \
+    fri_decode_kernel<CC, SS, DD, QQ><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, t.chunk_mask, c, dc, p, group_begin)
+#define FRI_LAUNCH(CC, SS)                                                          \
+        do {                                                                        \
+            if (g.sub_bits != 0) FRI_LAUNCH_Q(CC, SS, true, kQuantGeneric);         \
+            else if (qclass == kQuantNone) FRI_LAUNCH_Q(CC, SS, false, kQuantNone); \
+            else if (qclass == kQuantSmallest) FRI_LAUNCH_Q(CC, SS, false, kQuantSmallest); \
+            else FRI_LAUNCH_Q(CC, SS, false, kQuantGeneric);                        \
         } while (0)
         if (g.channels == 1 && g.sample_bytes == 1) FRI_LAUNCH(1, uint8_t);
         else if (g.channels == 3 && g.sample_bytes == 1) FRI_LAUNCH(3, uint8_t);
         else if (g.channels == 1 && g.sample_bytes == 2) FRI_LAUNCH(1, uint16_t);
         else FRI_LAUNCH(3, uint16_t);
 #undef FRI_LAUNCH
+#undef FRI_LAUNCH_Q
         if (launches) ++*launches;
     }
     return cudaGetLastError();
