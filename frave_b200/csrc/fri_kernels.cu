@@ -274,6 +274,12 @@ struct RegionView {
     int phi0;        // shared-memory offset of region pixel (0, 0): its global address & 15
     int xb0;         // byte offset of region column 0 inside its image row (x0 * pixel bytes)
     bool interior;   // the whole staged region lies inside the image
+    // Global address of shared-memory byte s of staged row r.  The offset fits 32 bits (a region spans
+    // at most region_h rows), so the per-chunk address is one 32-bit multiply-add and one wide add.
+    __device__ __forceinline__ uint8_t *gaddr(int r, int s) const
+    {
+        return reinterpret_cast<uint8_t *>(gbase0) + (ptrdiff_t)(r * delta + s);
+    }
 };
 
 template <int PB>
@@ -369,7 +375,7 @@ __device__ __forceinline__ void stage_group(const Geometry &g, const GroupDesc &
             for (int u = 0; u < kListUnroll; ++u)
                 if (e[u] != kNoChunk) {
                     const int r = (int)(e[u] >> 16), s = (int)(e[u] & 0xffffu) << 4;
-                    cp_async_16(region + s, reinterpret_cast<const uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s);
+                    cp_async_16(region + s, rv.gaddr(r, s));
                 }
         }
     } else {
@@ -380,7 +386,7 @@ __device__ __forceinline__ void stage_group(const Geometry &g, const GroupDesc &
             const int y = gd.y0 + r;
             const bool yin = (unsigned)y < (unsigned)g.height;
             const int xb = rv.xb0 + s - (r * g.pitch + rv.phi0);  // byte position of the chunk inside image row y
-            const uint8_t *gp = reinterpret_cast<const uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s;
+            const uint8_t *gp = rv.gaddr(r, s);
             if (yin && xb >= 0 && xb + 16 <= stride32) {
                 cp_async_16(region + s, gp);
             } else if (!yin || xb + 16 <= 0 || xb >= stride32) {
@@ -821,7 +827,7 @@ __device__ __forceinline__ void zero_region(const Geometry &g, uint8_t *region)
 // byte-masked.  The first kWriteAhead list entries of every thread are fetched by
 // write_out_preload() *before* the CTA barrier that completes the region, so their latency hides
 // behind the barrier wait.
-constexpr int kWriteAhead = 8;
+constexpr int kWriteAhead = 6;
 
 // Partially owned chunks are written one 32-bit word per thread and iteration (four neighbouring
 // lanes share a chunk): a word is skipped, stored whole, or — only the word the group's outline
@@ -845,10 +851,12 @@ __device__ __forceinline__ WriteAhead write_out_preload(const Geometry &g, const
     WriteAhead w;
     const uint32_t *cl = chunk_list + (size_t)rv.phi0 * g.list_cap;
     const int n_full = g.list_full[rv.phi0];
+    // Slots past the end of the list repeat its last chunk (a redundant store of the same bytes)
+    // instead of being skipped: the unrolled stores then need no per-chunk test and branch.
 #pragma unroll
     for (int u = 0; u < kWriteAhead; ++u) {
-        const int k = threadIdx.x + u * blockDim.x;
-        w.e[u] = (rv.interior && k < n_full) ? ld_table(cl + k, pol) : kNoChunk;
+        const int k = min((int)(threadIdx.x + u * blockDim.x), n_full - 1);
+        w.e[u] = (rv.interior && n_full > 0) ? ld_table(cl + k, pol) : kNoChunk;
     }
     const uint16_t *cmk = chunk_mask + (size_t)rv.phi0 * g.list_cap;
     const int n_all = g.list_all[rv.phi0];
@@ -868,7 +876,7 @@ __device__ __forceinline__ void store_word_masked(const RegionView &rv, const ui
     const uint32_t nib = (m >> (4 * w)) & 15u;
     if (nib == 0) return;
     const int r = (int)(e >> 16), s = ((int)(e & 0xffffu) << 4) + 4 * w;
-    uint8_t *gp = reinterpret_cast<uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s;
+    uint8_t *gp = rv.gaddr(r, s);
     const uint32_t v = *reinterpret_cast<const uint32_t *>(region + s);
     if (nib == 15u) {
         *reinterpret_cast<uint32_t *>(gp) = v;
@@ -890,13 +898,13 @@ __device__ __forceinline__ void write_out_group(const Geometry &g, const GroupDe
     const uint16_t *cmk = chunk_mask + (size_t)rv.phi0 * g.list_cap;
     const int n_full = g.list_full[rv.phi0], n_all = g.list_all[rv.phi0];
     if (rv.interior) {
+        if (n_full > 0) {
 #pragma unroll
-        for (int u = 0; u < kWriteAhead; ++u)
-            if (ahead.e[u] != kNoChunk) {
+            for (int u = 0; u < kWriteAhead; ++u) {
                 const int r = (int)(ahead.e[u] >> 16), s = (int)(ahead.e[u] & 0xffffu) << 4;
-                *reinterpret_cast<int4 *>(reinterpret_cast<uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s) =
-                    *reinterpret_cast<const int4 *>(region + s);
+                *reinterpret_cast<int4 *>(rv.gaddr(r, s)) = *reinterpret_cast<const int4 *>(region + s);
             }
+        }
 #if FRI_TRACE
         if ((threadIdx.x == 0 || threadIdx.x == 255) && blockIdx.x < 16384) g_trace2[4 * blockIdx.x + (threadIdx.x == 0 ? 0 : 1)] = gtime();
 #endif
@@ -904,7 +912,7 @@ __device__ __forceinline__ void write_out_group(const Geometry &g, const GroupDe
         for (int k = threadIdx.x + kWriteAhead * n_threads; k < n_full; k += n_threads) {
             const uint32_t e = ld_table(cl + k, pol);
             const int r = (int)(e >> 16), s = (int)(e & 0xffffu) << 4;
-            *reinterpret_cast<int4 *>(reinterpret_cast<uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s) =
+            *reinterpret_cast<int4 *>(rv.gaddr(r, s)) =
                 *reinterpret_cast<const int4 *>(region + s);
         }
         const int w = threadIdx.x & 3;
@@ -928,7 +936,7 @@ __device__ __forceinline__ void write_out_group(const Geometry &g, const GroupDe
             const int xb = rv.xb0 + s - (r * g.pitch + rv.phi0);  // byte position of the chunk inside its image row
             const int lo = min(max(-xb, 0), 16), hi = min(max(stride32 - xb, 0), 16);
             m &= ((1u << hi) - 1u) & ~((1u << lo) - 1u);
-            if (m) store_chunk_masked(reinterpret_cast<uint8_t *>(rv.gbase0 + (int64_t)r * rv.delta) + s, region + s, m);
+            if (m) store_chunk_masked(rv.gaddr(r, s), region + s, m);
         }
     }
 }
