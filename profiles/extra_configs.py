@@ -33,7 +33,7 @@ def run(w, h, c, depth, sb, frames=1, reps=10, q=None):
     # coefficient traffic counts the blocks actually moved (deep trees include out-of-image base tiles)
     moved = plan.coefs_per_frame * frames * 4 + samples * sb
     print(json.dumps({"shape": f"{w}x{h}x{c}", "depth": depth, "sample_bytes": sb, "frames": frames, "tiles": plan.n_tiles,
-                      "lossless": ok, "enc_us": round(te * 1e3, 1), "dec_us": round(td * 1e3, 1),
+                      "lossless": ok, "every_pixel_covered": plan.pixels_covered == w * h, "enc_us": round(te * 1e3, 1), "dec_us": round(td * 1e3, 1),
                       "enc_GBps_alg": round(samples * bps / te / 1e6), "dec_GBps_alg": round(samples * bps / td / 1e6),
                       "enc_GBps_moved": round(moved / te / 1e6), "dec_GBps_moved": round(moved / td / 1e6),
                       "enc_MPix_s": round(w * h * frames / te / 1e3), "dec_MPix_s": round(w * h * frames / td / 1e3),

@@ -22,6 +22,10 @@ extern "C" {
     fn fri_encode_tq(plan: *mut FriPlan, pixels: *const c_void, n_frames: u32, q: *const i32, coefs: *mut i32) -> c_int;
     fn fri_decode_tq(plan: *mut FriPlan, coefs: *const i32, n_frames: u32, q: *const i32, dequant_mode: c_int,
                      pixels: *mut c_void) -> c_int;
+    // 16-bit transport of the same two calls (8-bit samples): half the bytes over PCIe
+    fn fri_encode_tq16(plan: *mut FriPlan, pixels: *const c_void, n_frames: u32, q: *const i32, coefs: *mut i16) -> c_int;
+    fn fri_decode_tq16(plan: *mut FriPlan, coefs: *const i16, n_frames: u32, q: *const i32, dequant_mode: c_int,
+                       pixels: *mut c_void) -> c_int;
 }
 
 fn check(rc: c_int) -> Result<(), String> {
@@ -67,7 +71,23 @@ impl Plan {
     pub fn decode_tq(&mut self, coefs: &[i32], q: &[i32; 32], pixels: &mut [u8]) -> Result<(), String> {
         check(unsafe { fri_decode_tq(self.0, coefs.as_ptr(), 1, q.as_ptr(), FRI_DEQUANT_DIVIDE, pixels.as_mut_ptr() as *mut c_void) })
     }
+    /// encode_tq with int16 coefficients on the host side (every coefficient of an 8-bit image fits:
+    /// |residue| <= 255, wavelet_transform.rs:211-218); widen while applying the mask.
+    pub fn encode_tq16(&mut self, pixels: &[u8], q: &[i32; 32]) -> Result<Vec<i16>, String> {
+        let mut coefs = vec![0i16; self.coefs_per_frame()];
+        check(unsafe { fri_encode_tq16(self.0, pixels.as_ptr() as *const c_void, 1, q.as_ptr(), coefs.as_mut_ptr()) })?;
+        Ok(coefs)
+    }
+    /// decode_tq from int16 coefficients (a decodable container never holds more: 1024-symbol
+    /// alphabet, entropy_coding.rs:25).
+    pub fn decode_tq16(&mut self, coefs: &[i16], q: &[i32; 32], pixels: &mut [u8]) -> Result<(), String> {
+        check(unsafe { fri_decode_tq16(self.0, coefs.as_ptr(), 1, q.as_ptr(), FRI_DEQUANT_DIVIDE, pixels.as_mut_ptr() as *mut c_void) })
+    }
 }
+
+// One handle per host thread: the library keeps no global state besides the thread-local error
+// string, so an encoder thread and a decoder thread can each own a Plan and run concurrently.
+unsafe impl Send for Plan {}
 
 impl Drop for Plan {
     fn drop(&mut self) { unsafe { fri_plan_destroy(self.0) } }
