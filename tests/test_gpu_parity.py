@@ -170,6 +170,73 @@ def test_16bit_transport_equals_32bit(monkeypatch, shape, bands):
                                   oracle_decode(plan, anyc[0].astype(np.int32), some, q, multiply=mul))
 
 
+def test_encoder_and_decoder_threads_with_one_handle_each():
+    """The ABI is re-entrant across handles: an encoder thread and a decoder thread,
+    one plan each on the same device, run concurrently (this is how bench.py's e2e drives the
+    library) and both keep producing the oracle's bytes."""
+    import threading
+
+    h, w, c = 540, 960, 3
+    frames = [uniform_image(h, w, c, seed=700 + i) for i in range(4)]
+    q = smallest_layer_q(4)
+    with capi.Plan(w, h, c) as eplan, capi.Plan(w, h, c) as dplan:
+        some = some_of(eplan)
+        want = [oracle_encode(eplan, f, q)[0] for f in frames]
+        want_px = [oracle_decode(dplan, wc, some, q) for wc in want]
+        errors = []
+
+        def enc():
+            try:
+                for it in range(12):
+                    i = it % 4
+                    dt = np.int16 if it & 1 else np.int32
+                    assert np.array_equal(eplan.encode(frames[i], q, dtype=dt)[0], want[i]), f"encode {it}"
+            except Exception as exc:  # noqa: BLE001
+                errors.append(exc)
+
+        def dec():
+            try:
+                for it in range(12):
+                    i = (it + 1) % 4
+                    cf = want[i].astype(np.int16) if it & 1 else want[i]
+                    assert np.array_equal(dplan.decode(cf, q)[0], want_px[i]), f"decode {it}"
+            except Exception as exc:  # noqa: BLE001
+                errors.append(exc)
+
+        th = [threading.Thread(target=enc), threading.Thread(target=dec)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        assert not errors, errors
+
+
+def test_more_frames_than_one_grid_dimension():
+    """n_frames above the 65535 gridDim.y limit is split over several launches."""
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda", 0)
+    h, w, c, n = 5, 7, 1, 65535 + 9
+    with capi.Plan(w, h, c) as plan:
+        gen = torch.Generator(device=dev).manual_seed(11)
+        px = torch.randint(0, 256, (n, h, w, c), generator=gen, device=dev, dtype=torch.int32).to(torch.uint8)
+        coefs = torch.empty((n,) + plan.coef_shape, dtype=torch.int32, device=dev)
+        out = torch.empty_like(px)
+        q = smallest_layer_q(3)
+        plan.encode_device(px.data_ptr(), n, coefs.data_ptr(), q)
+        assert plan.last_launches == 2
+        plan.decode_device(coefs.data_ptr(), n, out.data_ptr(), q)
+        torch.cuda.synchronize()
+        some = some_of(plan)
+        for f in (0, 65534, 65535, n - 1):
+            want, _ = oracle_encode(plan, px[f].cpu().numpy(), q)
+            assert np.array_equal(coefs[f].cpu().numpy(), want)
+            assert np.array_equal(out[f].cpu().numpy(), oracle_decode(plan, want, some, q))
+        plan.encode_device(px.data_ptr(), n, coefs.data_ptr())
+        plan.decode_device(coefs.data_ptr(), n, out.data_ptr())
+        torch.cuda.synchronize()
+        assert torch.equal(px, out) or plan.pixels_covered < w * h
+
+
 def test_16bit_transport_rejects_16bit_samples():
     with capi.Plan(64, 48, 1, sample_bytes=2) as plan:
         with pytest.raises(capi.FriError) as e:
