@@ -354,6 +354,8 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
 
         if world > 1:
             dist.barrier()
+        plan.set_bands(1)   # concurrent callers: the other thread's call supplies the overlap (fri_plan_set_bands)
+        dplan.set_bands(1)
         th = [threading.Thread(target=enc_loop), threading.Thread(target=dec_loop)]
         t0 = time.perf_counter()
         for t in th:
@@ -363,6 +365,8 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
         e2e["duplex_" + tag] = time.perf_counter() - t0
         if errors:
             raise errors[0]
+        plan.set_bands(0)
+        dplan.set_bands(0)
         h2d = px_h.array.nbytes + cf_dec.array.nbytes
         d2h = cf_enc.array.nbytes + out_h.array.nbytes
         cf_enc.free(); cf_dec.free()
@@ -404,7 +408,7 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps,
                     "api": "fri_encode_tq16 + fri_decode_tq16 (pinned host buffers, int16 coefficients on the host side), "
-                           "encoder thread and decoder thread with one plan handle each",
+                           "encoder thread and decoder thread with one plan handle each, one band per frame (fri_plan_set_bands(1))",
                     "variants_mpix_s": {k: W * H * world * e2e_steps / v / 1e6 for k, v in e2e.items()},
                     "variants": "serial = one thread, encode then decode; duplex = encoder and decoder threads; "
                                 "i32 = fri_*_tq (4 B coefficients over PCIe: 255 MB each way per step), "

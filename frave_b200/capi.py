@@ -51,6 +51,7 @@ _SYMBOLS = [
     ("fri_host_alloc", C.c_int, [C.POINTER(_P), C.c_size_t]),
     ("fri_host_free", None, [_P]),
     ("fri_plan_last_launches", C.c_uint32, [_P]),
+    ("fri_plan_set_bands", C.c_int, [_P, C.c_int]),
     ("fri_quant_divide", C.c_int32, [C.c_int32, C.c_int32]),
     ("fri_quant_divide_small", C.c_int32, [C.c_int32, C.c_int32]),
     ("fri_quant_divide_magic", C.c_int32, [C.c_int32, C.c_int32]),
@@ -202,6 +203,10 @@ class Plan:
         keys = ["group_a", "group_b", "region_w", "region_h", "smem_pitch", "smem_bytes", "n_groups", "n_base_tiles",
                 "threads", "chunks_per_row", "depth", "sub_bits", "chunks_full", "chunks_owned"]
         return {k: int(info[i]) for i, k in enumerate(keys)}
+
+    def set_bands(self, bands: int) -> None:
+        """Bands per frame of the host-buffer entry points (0 = automatic; 1 for concurrent callers)."""
+        _check(lib().fri_plan_set_bands(self._h, int(bands)))
 
     @property
     def last_launches(self) -> int:

@@ -78,6 +78,7 @@ struct fri_plan {
     int32_t *d_dc_shared = nullptr;  // low-pass scratch for the *_device entry points (depth > 9)
     size_t d_dc_frames = 0;
     uint32_t last_launches = 0;
+    int bands = 0;  // fri_plan_set_bands: 0 = automatic
     // emission order (computed on first use)
     int emit_state = 0;  // 0 = not computed, 1 = ready, -1 = failed (emit_error)
     std::string emit_error;
@@ -176,6 +177,7 @@ int make_bands(const fri_plan *p, Band bands[kMaxBands])
     const Geometry &g = pl.geo;
     int n = g.sub_bits > 0 ? 1 : std::max(1, std::min(kMaxBands, g.n_groups / 256));
     if (const char *env = std::getenv("FRI_BANDS")) n = std::max(1, std::min(kMaxBands, std::atoi(env)));  // tuning knob
+    if (p->bands > 0 && g.sub_bits == 0) n = std::min(kMaxBands, p->bands);
     n = std::min(n, std::max(1, g.n_groups));
     for (int k = 0; k < n; ++k) {
         Band &b = bands[k];
@@ -739,6 +741,14 @@ void fri_host_free(void *p)
 }
 
 uint32_t fri_plan_last_launches(const fri_plan *p) { return p ? p->last_launches : 0; }
+
+int fri_plan_set_bands(fri_plan *p, int bands)
+{
+    if (!p) return fail(FRI_E_INVALID, "plan is NULL");
+    if (bands < 0 || bands > kMaxBands) return fail(FRI_E_INVALID, "bands must be in [0, %d] (0 = automatic)", kMaxBands);
+    p->bands = bands;
+    return FRI_OK;
+}
 
 int32_t fri_quant_divide(int32_t value, int32_t q)
 {

@@ -22,6 +22,7 @@ extern "C" {
     fn fri_encode_tq(plan: *mut FriPlan, pixels: *const c_void, n_frames: u32, q: *const i32, coefs: *mut i32) -> c_int;
     fn fri_decode_tq(plan: *mut FriPlan, coefs: *const i32, n_frames: u32, q: *const i32, dequant_mode: c_int,
                      pixels: *mut c_void) -> c_int;
+    fn fri_plan_set_bands(plan: *mut FriPlan, bands: c_int) -> c_int;
     // 16-bit transport of the same two calls (8-bit samples): half the bytes over PCIe
     fn fri_encode_tq16(plan: *mut FriPlan, pixels: *const c_void, n_frames: u32, q: *const i32, coefs: *mut i16) -> c_int;
     fn fri_decode_tq16(plan: *mut FriPlan, coefs: *const i16, n_frames: u32, q: *const i32, dequant_mode: c_int,
@@ -71,6 +72,9 @@ impl Plan {
     pub fn decode_tq(&mut self, coefs: &[i32], q: &[i32; 32], pixels: &mut [u8]) -> Result<(), String> {
         check(unsafe { fri_decode_tq(self.0, coefs.as_ptr(), 1, q.as_ptr(), FRI_DEQUANT_DIVIDE, pixels.as_mut_ptr() as *mut c_void) })
     }
+    /// Bands per frame of the host-buffer calls: 0 = automatic (single caller), 1 when an encoder and a
+    /// decoder thread drive one handle each.
+    pub fn set_bands(&mut self, bands: i32) -> Result<(), String> { check(unsafe { fri_plan_set_bands(self.0, bands) }) }
     /// encode_tq with int16 coefficients on the host side (every coefficient of an 8-bit image fits:
     /// |residue| <= 255, wavelet_transform.rs:211-218); widen while applying the mask.
     pub fn encode_tq16(&mut self, pixels: &[u8], q: &[i32; 32]) -> Result<Vec<i16>, String> {

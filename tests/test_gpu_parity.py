@@ -183,6 +183,8 @@ def test_encoder_and_decoder_threads_with_one_handle_each():
         some = some_of(eplan)
         want = [oracle_encode(eplan, f, q)[0] for f in frames]
         want_px = [oracle_decode(dplan, wc, some, q) for wc in want]
+        eplan.set_bands(1)
+        dplan.set_bands(3)
         errors = []
 
         def enc():

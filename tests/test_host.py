@@ -137,6 +137,14 @@ def test_invalid_arguments_and_no_cpu_fallback():
         assert e.value.code == capi.FRI_E_CUDA and "no CPU fallback" in str(e.value)
         with pytest.raises(capi.FriError):
             p.decode(np.zeros((1,) + p.coef_shape, np.int32))
+        with pytest.raises(capi.FriError) as e:
+            p.encode(np.zeros((16, 16, 1), np.uint8), dtype=np.int16)  # the 16-bit transport has no fallback either
+        assert e.value.code == capi.FRI_E_CUDA
+        p.set_bands(1)
+        p.set_bands(0)
+        with pytest.raises(capi.FriError) as e:
+            p.set_bands(9)
+        assert e.value.code == capi.FRI_E_INVALID
     if capi.device_count() == 0:
         with pytest.raises(capi.FriError) as e:
             capi.Plan(16, 16, 1, device=0)
