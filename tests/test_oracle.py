@@ -81,6 +81,32 @@ def test_lossless_roundtrip_on_cpu(shape, dtype):
     assert not rec[~covered].any()  # from_wavelet zero-initialises (wavelet_transform.rs:309-317)
 
 
+@pytest.mark.parametrize("impl", ["c", "numpy"])
+def test_hand_derived_depth2_example(impl):
+    """A four-leaf fractal worked out by hand from the reference source (the functions are generic in
+    depth): wavelet_transform.rs:47-53 puts heap node 2p at its parent's position and 2p+1 at
+    parent + LITERALS[depth - level - 1], so for depth 2 and centre (1, 0) the leaves sit at
+    (1,0) (1,1) (0,1) (0,2); :211-218 gives d = l - r, s = r + d / 2 with Rust's truncating division.
+
+        leaves 5 2 | 7 10 -> node 2: d = 3, s = 2 + 1 = 3; node 3: d = -3, s = 10 + (-3 / 2 = -1) = 9
+        root: d = 3 - 9 = -6, s = 9 + (-3) = 6              -> coefficients [6, -6, 3, -3]
+
+    With the image cut to two rows, leaf (0,2) is None and counts as 0 (try_apply, :14-26):
+        node 3: d = 7 - 0 = 7, s = 0 + 7 / 2 = 3; root: d = 3 - 3 = 0, s = 3 -> [3, 0, 3, 7]
+    and the inverse (:366-367) returns 5 2 | 7 and never writes the missing pixel."""
+    img = np.zeros((4, 3, 1), np.uint8)
+    img[0, 1], img[1, 1], img[1, 0], img[2, 0] = 5, 2, 7, 10
+    cen = np.array([[1, 0]], np.int32)
+    fwd = (lambda im: O.extract_tiles(im, cen, depth=2)) if impl == "c" else (lambda im: N.forward_tiles(im, cen, 2))
+    coef, some = fwd(img)
+    assert coef[0, 0].tolist() == [6, -6, 3, -3] and some.all()
+    coef, some = fwd(img[:2])
+    assert coef[0, 0].tolist() == [3, 0, 3, 7]
+    rec = (O.extract_values(cen, coef, some, 2, 3, depth=2) if impl == "c"
+           else N.inverse_tiles(cen, coef, some, 2, 2, 3))
+    assert rec[:, :, 0].tolist() == [[0, 5, 0], [7, 2, 0]]
+
+
 def test_quant_layer_formula():
     # quantization.rs:13: layer = trailing_zeros(prev_power_two(i + 1)) = floor(log2(i + 1))
     layers = N.quant_layers(9)
