@@ -48,6 +48,10 @@ _SYMBOLS = [
     ("fri_encode_tq_emit", C.c_int, [_P, _P, C.c_uint32, _P, _P]),
     ("fri_emit_device16", C.c_int, [_P, _P, C.c_uint32, _P, _P]),
     ("fri_encode_tq_emit16", C.c_int, [_P, _P, C.c_uint32, _P, _P]),
+    ("fri_unemit_device", C.c_int, [_P, _P, C.c_uint32, _P, _P]),
+    ("fri_unemit_device16", C.c_int, [_P, _P, C.c_uint32, _P, _P]),
+    ("fri_decode_tq_emit", C.c_int, [_P, _P, C.c_uint32, _P, C.c_int, _P]),
+    ("fri_decode_tq_emit16", C.c_int, [_P, _P, C.c_uint32, _P, C.c_int, _P]),
     ("fri_host_alloc", C.c_int, [C.POINTER(_P), C.c_size_t]),
     ("fri_host_free", None, [_P]),
     ("fri_plan_last_launches", C.c_uint32, [_P]),
@@ -285,6 +289,31 @@ class Plan:
         qa, qp = _q_array(q)
         fn = lib().fri_encode_tq_emit16 if out.dtype == np.int16 else lib().fri_encode_tq_emit
         _check(fn(self._h, px.ctypes.data, n, qp, out.ctypes.data))
+        return out
+
+    def unemit_device(self, d_streams: int, n_frames: int, d_coefs: int, stream: int = 0, half: bool = False) -> None:
+        """Emitted streams int32 (half: int16) [n_frames, C, emission_count()] -> dense coefficient blocks."""
+        fn = lib().fri_unemit_device16 if half else lib().fri_unemit_device
+        _check(fn(self._h, d_streams, n_frames, d_coefs, stream))
+
+    def decode_emit(self, streams: np.ndarray, q=None, multiply: bool = False, out: np.ndarray | None = None) -> np.ndarray:
+        """Emitted streams [F, C, emission_count()] (int32 or int16) -> HWC pixels [F, H, W, C]."""
+        st = np.asarray(streams)
+        half = st.dtype == np.int16
+        st = np.ascontiguousarray(st, dtype=np.int16 if half else np.int32)
+        cnt = self.emission_count()
+        if st.shape == (self.channels, cnt):
+            st = st[None]
+        if st.ndim != 3 or st.shape[1:] != (self.channels, cnt):
+            raise ValueError(f"streams must have shape [F, {self.channels}, {cnt}]")
+        n = st.shape[0]
+        if out is None:
+            out = np.empty((n,) + self.frame_shape, self.pixel_dtype)
+        assert out.dtype == self.pixel_dtype and out.flags.c_contiguous and out.shape == (n,) + self.frame_shape
+        qa, qp = _q_array(q)
+        mode = FRI_DEQUANT_MULTIPLY if multiply else FRI_DEQUANT_DIVIDE
+        fn = lib().fri_decode_tq_emit16 if half else lib().fri_decode_tq_emit
+        _check(fn(self._h, st.ctypes.data, n, qp, mode, out.ctypes.data))
         return out
 
     # ---- device-resident entry points (raw device pointers, e.g. torch.Tensor.data_ptr()) -----

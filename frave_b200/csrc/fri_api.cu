@@ -727,6 +727,97 @@ int fri_encode_tq_emit16(fri_plan *p, const void *pixels, uint32_t n_frames, con
     return encode_emit_host(p, pixels, n_frames, q, out, true);
 }
 
+static int unemit_device(fri_plan *p, const void *d_streams, bool half, uint32_t n_frames, int32_t *d_coefs, void *stream)
+{
+    int rc = enter_device(p);
+    if (rc) return rc;
+    if ((rc = ensure_emission_device(p))) return rc;
+    if (n_frames == 0) return FRI_OK;
+    if (!d_coefs || !d_streams) return fail(FRI_E_INVALID, "NULL device buffer");
+    if ((uintptr_t)d_coefs & 15) return fail(FRI_E_INVALID, "d_coefs must be 16-byte aligned");
+    p->last_launches = 0;
+    FRI_CUDA(launch_unemit(p->plan.geo, p->tables, p->emit_tables, p->emit_src.size(), d_streams, half, n_frames, d_coefs,
+                           static_cast<cudaStream_t>(stream), &p->last_launches));
+    return FRI_OK;
+}
+
+int fri_unemit_device(fri_plan *p, const int32_t *d_streams, uint32_t n_frames, int32_t *d_coefs, void *stream)
+{
+    return unemit_device(p, d_streams, false, n_frames, d_coefs, stream);
+}
+
+int fri_unemit_device16(fri_plan *p, const int16_t *d_streams, uint32_t n_frames, int32_t *d_coefs, void *stream)
+{
+    return unemit_device(p, d_streams, true, n_frames, d_coefs, stream);
+}
+
+static int decode_emit_host(fri_plan *p, const void *streams, bool half, uint32_t n_frames, const int32_t *q, int dequant_mode,
+                            void *pixels)
+{
+    int rc = enter_device(p);
+    if (rc) return rc;
+    if ((rc = check_q(q))) return rc;
+    if (dequant_mode != FRI_DEQUANT_DIVIDE && dequant_mode != FRI_DEQUANT_MULTIPLY)
+        return fail(FRI_E_INVALID, "dequant_mode must be FRI_DEQUANT_DIVIDE or FRI_DEQUANT_MULTIPLY");
+    if ((rc = ensure_emission_device(p))) return rc;
+    if (n_frames == 0) return FRI_OK;
+    if (!pixels || !streams) return fail(FRI_E_INVALID, "NULL host buffer");
+    if ((rc = ensure_slots(p))) return rc;
+    const Geometry &g = p->plan.geo;
+    const size_t count = p->emit_src.size();
+    const size_t esz = half ? sizeof(int16_t) : sizeof(int32_t);
+    const size_t per_frame = (size_t)g.channels * count * esz;  // bytes
+    const size_t per_slot = (per_frame + 255) & ~(size_t)255;
+    if (p->d_emit_tmp_bytes < (size_t)kSlots * per_slot) {
+        if (p->d_emit_tmp) cudaFree(p->d_emit_tmp);
+        p->d_emit_tmp = nullptr;
+        p->d_emit_tmp_bytes = 0;
+        FRI_CUDA(cudaMalloc(&p->d_emit_tmp, (size_t)kSlots * per_slot));
+        p->d_emit_tmp_bytes = (size_t)kSlots * per_slot;
+    }
+    QuantParams qp;
+    make_quant_params(qp, q, dequant_mode == FRI_DEQUANT_MULTIPLY);
+    p->last_launches = 0;
+    const bool need_zero = p->plan.pixels_covered != (uint64_t)g.width * g.height;
+    Pipeline &pl = p->pipe;
+    for (uint32_t f = 0; f < n_frames; ++f) {
+        Slot &s = p->slots[f % kSlots];
+        uint8_t *d_emit = static_cast<uint8_t *>(p->d_emit_tmp) + (size_t)(f % kSlots) * per_slot;
+        if (s.used) {
+            FRI_CUDA(cudaStreamWaitEvent(pl.in, s.compute_done, 0));
+            FRI_CUDA(cudaStreamWaitEvent(pl.compute, s.out_done, 0));
+        }
+        FRI_CUDA(cudaMemcpyAsync(d_emit, static_cast<const uint8_t *>(streams) + (size_t)f * per_frame, per_frame,
+                                 cudaMemcpyHostToDevice, pl.in));
+        FRI_CUDA(cudaEventRecord(pl.in_ready[0], pl.in));
+        FRI_CUDA(cudaStreamWaitEvent(pl.compute, pl.in_ready[0], 0));
+        if (need_zero) FRI_CUDA(cudaMemsetAsync(s.d_pixels, 0, (size_t)g.frame_bytes, pl.compute));
+        FRI_CUDA(launch_unemit(g, p->tables, p->emit_tables, count, d_emit, half, 1, s.d_coefs, pl.compute, &p->last_launches));
+        FRI_CUDA(launch_decode(g, p->tables, qp, s.d_coefs, 1, s.d_pixels, s.d_dc, pl.compute, &p->last_launches));
+        FRI_CUDA(cudaEventRecord(pl.band_done[0], pl.compute));
+        FRI_CUDA(cudaEventRecord(s.compute_done, pl.compute));
+        FRI_CUDA(cudaStreamWaitEvent(pl.out, pl.band_done[0], 0));
+        FRI_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(pixels) + (size_t)f * g.frame_bytes, s.d_pixels, (size_t)g.frame_bytes,
+                                 cudaMemcpyDeviceToHost, pl.out));
+        FRI_CUDA(cudaEventRecord(s.out_done, pl.out));
+        s.used = true;
+    }
+    FRI_CUDA(cudaStreamSynchronize(pl.out));
+    FRI_CUDA(cudaStreamSynchronize(pl.compute));
+    FRI_CUDA(cudaStreamSynchronize(pl.in));
+    return FRI_OK;
+}
+
+int fri_decode_tq_emit(fri_plan *p, const int32_t *streams, uint32_t n_frames, const int32_t *q, int dequant_mode, void *pixels)
+{
+    return decode_emit_host(p, streams, false, n_frames, q, dequant_mode, pixels);
+}
+
+int fri_decode_tq_emit16(fri_plan *p, const int16_t *streams, uint32_t n_frames, const int32_t *q, int dequant_mode, void *pixels)
+{
+    return decode_emit_host(p, streams, true, n_frames, q, dequant_mode, pixels);
+}
+
 int fri_host_alloc(void **out, size_t bytes)
 {
     if (!out) return fail(FRI_E_INVALID, "out is NULL");

@@ -1140,6 +1140,38 @@ fri_emit_kernel(const GroupDesc *__restrict__ groups, const uint32_t *__restrict
     }
 }
 
+// The inverse gather (decoder side): emitted streams -> dense coefficient blocks, `None` slots 0.
+// Same grouping: the group's emission slots are read as runs, placed in shared memory, and the 2 KB
+// blocks are written coalesced.
+template <typename T>
+__global__ void __launch_bounds__(256)
+fri_unemit_kernel(const GroupDesc *__restrict__ groups, const uint32_t *__restrict__ goff, const uint32_t *__restrict__ dst,
+                  const uint16_t *__restrict__ loc, unsigned long long count, int channels, int n_tiles,
+                  const T *__restrict__ in, int32_t *__restrict__ coefs)
+{
+    extern __shared__ __align__(16) int32_t es[];
+    const GroupDesc gd = groups[blockIdx.x];
+    const int n_present = __popc(gd.tile_mask), frame = blockIdx.y;
+    const uint32_t k0 = goff[blockIdx.x], k1 = goff[blockIdx.x + 1];
+    const bool all_some = k1 - k0 == (uint32_t)n_present * kTileLeaves;  // no None slot in this group
+    for (int ch = 0; ch < channels; ++ch) {
+        if (!all_some) {
+            for (int idx = threadIdx.x; idx < n_present * (kTileLeaves / 4); idx += blockDim.x)
+                reinterpret_cast<int4 *>(es)[idx] = make_int4(0, 0, 0, 0);
+            __syncthreads();
+        }
+        const T *src = in + ((size_t)frame * channels + ch) * count;
+        for (uint32_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) es[__ldg(loc + k)] = (int32_t)__ldcs(src + __ldg(dst + k));
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < n_present * (kTileLeaves / 4); idx += blockDim.x) {
+            const int t = idx >> 7, v = idx & 127;
+            int4 *out = reinterpret_cast<int4 *>(coefs + ((((size_t)frame * n_tiles + gd.tile_base + t) * channels + ch) << kBaseDepth));
+            __stcs(out + v, reinterpret_cast<const int4 *>(es)[idx]);
+        }
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // 16-bit transport (host-buffer entry points fri_*_tq16): every coefficient an 8-bit image can
 // produce fits an i16 (|d| <= 255, 0 <= s <= 255), so the copies over PCIe carry half the bytes.
@@ -1210,6 +1242,8 @@ cudaError_t configure_kernels()
     FRI_CFG(fri_coarse_inverse_kernel);
     FRI_CFG(fri_emit_kernel<int32_t>);
     FRI_CFG(fri_emit_kernel<int16_t>);
+    FRI_CFG(fri_unemit_kernel<int32_t>);
+    FRI_CFG(fri_unemit_kernel<int16_t>);
 #undef FRI_CFG4
 #undef FRI_CFG
     return cudaSuccess;
@@ -1318,6 +1352,28 @@ cudaError_t launch_decode(const Geometry &g, const DeviceTables &t, const QuantP
         else FRI_LAUNCH(3, uint16_t);
 #undef FRI_LAUNCH
 #undef FRI_LAUNCH_Q
+        if (launches) ++*launches;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unemit(const Geometry &g, const DeviceTables &t, const EmitTables &et, uint64_t count, const void *d_in,
+                          bool half, uint32_t n_frames, int32_t *d_coefs, cudaStream_t stream, uint32_t *launches)
+{
+    if (n_frames == 0 || g.n_groups == 0) return cudaSuccess;
+    const size_t smem = (size_t)g.group_a * g.group_b * kTileLeaves * sizeof(int32_t);
+    const size_t esz = half ? sizeof(int16_t) : sizeof(int32_t);
+    for (uint32_t f0 = 0; f0 < n_frames; f0 += 65535u) {  // gridDim.y limit
+        const uint32_t nf = n_frames - f0 < 65535u ? n_frames - f0 : 65535u;
+        const dim3 grid((unsigned)g.n_groups, nf);
+        int32_t *c = d_coefs + (int64_t)f0 * g.coefs_per_frame;
+        const uint8_t *in = static_cast<const uint8_t *>(d_in) + (size_t)f0 * g.channels * count * esz;
+        if (half)
+            fri_unemit_kernel<int16_t><<<grid, 256, smem, stream>>>(t.groups, et.goff, et.dst, et.loc, count, g.channels,
+                                                                    g.n_fractals, reinterpret_cast<const int16_t *>(in), c);
+        else
+            fri_unemit_kernel<int32_t><<<grid, 256, smem, stream>>>(t.groups, et.goff, et.dst, et.loc, count, g.channels,
+                                                                    g.n_fractals, reinterpret_cast<const int32_t *>(in), c);
         if (launches) ++*launches;
     }
     return cudaGetLastError();

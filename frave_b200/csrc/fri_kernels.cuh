@@ -129,6 +129,10 @@ struct EmitTables {
 cudaError_t launch_emit(const Geometry &g, const DeviceTables &t, const EmitTables &et, uint64_t count, const int32_t *d_coefs,
                         uint32_t n_frames, void *d_out, bool half, cudaStream_t stream, uint32_t *launches);
 
+// The inverse: coefs[frame][tile][ch][i] <- emitted streams (int32 or, half, int16), `None` slots 0.
+cudaError_t launch_unemit(const Geometry &g, const DeviceTables &t, const EmitTables &et, uint64_t count, const void *d_in,
+                          bool half, uint32_t n_frames, int32_t *d_coefs, cudaStream_t stream, uint32_t *launches);
+
 // 16-bit transport of the host-buffer entry points: saturating i32 -> i16 repack and its inverse
 // (count is a multiple of 8; both pointers 16-byte aligned).
 cudaError_t launch_pack16(const int32_t *d_src, int16_t *d_dst, size_t count, cudaStream_t stream, uint32_t *launches);

@@ -154,6 +154,20 @@ int fri_emit_device16(fri_plan *plan, const int32_t *d_coefs, uint32_t n_frames,
 int fri_encode_tq_emit16(fri_plan *plan, const void *pixels, uint32_t n_frames, const int32_t *q, int16_t *out);
 
 /*
+ * The decoder side of the same order: the entropy decoder produces every channel's coefficients in
+ * emission order (entropy_coding.rs:205-264 walks the same sorted lattice); fri_unemit_device*
+ * places them back into the dense [n_tiles][C][512] blocks (`None` slots 0, where the reference's
+ * from_metadata lattice, wavelet_transform.rs:392-403, holds no value), fri_decode_tq_emit* does
+ * that and dequantization + inverse transform in one call: host streams -> host pixels.
+ */
+int fri_unemit_device(fri_plan *plan, const int32_t *d_streams, uint32_t n_frames, int32_t *d_coefs, void *stream);
+int fri_unemit_device16(fri_plan *plan, const int16_t *d_streams, uint32_t n_frames, int32_t *d_coefs, void *stream);
+int fri_decode_tq_emit(fri_plan *plan, const int32_t *streams, uint32_t n_frames, const int32_t *q, int dequant_mode,
+                       void *pixels);
+int fri_decode_tq_emit16(fri_plan *plan, const int16_t *streams, uint32_t n_frames, const int32_t *q, int dequant_mode,
+                         void *pixels);
+
+/*
  * How the host-buffer entry points stream one frame through the device: in `bands` consecutive
  * bands of tile groups (1..8), each with its own copy in, kernels and copy out on three
  * event-chained streams, so that a single call overlaps its own host->device and device->host

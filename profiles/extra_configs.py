@@ -71,9 +71,15 @@ def run_emit(w, h, c, frames=1, reps=10, half=False):
     b.record()
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / reps
+    a.record()
+    for _ in range(reps):
+        plan.unemit_device(out.data_ptr(), frames, co.data_ptr(), st, half)
+    b.record()
+    torch.cuda.synchronize()
+    ms_un = a.elapsed_time(b) / reps
     bpc = 6 if half else 8
     print(json.dumps({"emit": f"{w}x{h}x{c}", "out": "i16" if half else "i32", "frames": frames, "count_per_channel": cnt,
-                      "us": round(ms * 1e3, 1), f"GBps_alg({bpc}B per coefficient)": round(bpc * cnt * c * frames / ms / 1e6),
+                      "us": round(ms * 1e3, 1), "unemit_us": round(ms_un * 1e3, 1), f"GBps_alg({bpc}B per coefficient)": round(bpc * cnt * c * frames / ms / 1e6),
                       "MPix_s": round(w * h * frames / ms / 1e3)}))
     plan.close()
 

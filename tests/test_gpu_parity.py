@@ -378,6 +378,48 @@ def test_emitted_streams_follow_the_reference_scan_order(shape):
         assert np.array_equal(d_out16.cpu().numpy(), got)
 
 
+@pytest.mark.parametrize("shape", [(48, 64, 1), (131, 77, 3), (270, 480, 3)], ids=lambda s: "x".join(map(str, s)))
+def test_decoder_side_of_the_emission_order(shape):
+    """fri_unemit_device* / fri_decode_tq_emit*: streams in emission order -> dense blocks (None slots 0)
+    -> pixels; the mirror of the emitter, against the i32 block path and the oracle."""
+    torch = pytest.importorskip("torch")
+    h, w, c = shape
+    frames = np.stack([uniform_image(h, w, c, seed=40 + i) for i in range(3)])
+    q = smallest_layer_q(5)
+    with capi.Plan(w, h, c) as plan:
+        some = some_of(plan)
+        coefs = plan.encode(frames, q)
+        streams = plan.encode_emit(frames, q)
+        want_px = np.stack([oracle_decode(plan, coefs[i], some, q) for i in range(3)])
+        assert np.array_equal(plan.decode_emit(streams, q), want_px)
+        assert plan.last_launches == 2 * 3  # per frame: un-emit, dequant + inverse transform
+        assert np.array_equal(plan.decode_emit(streams.astype(np.int16), q), want_px)
+        dev = torch.device("cuda", 0)
+        d_streams = torch.from_numpy(streams).to(dev)
+        d_coefs = torch.full((3,) + plan.coef_shape, 12345, dtype=torch.int32, device=dev)  # None slots must be zeroed
+        plan.unemit_device(d_streams.data_ptr(), 3, d_coefs.data_ptr())
+        torch.cuda.synchronize()
+        assert np.array_equal(d_coefs.cpu().numpy(), coefs)  # encode leaves None slots at 0
+        d16 = d_streams.to(torch.int16)
+        d_coefs.fill_(-7)
+        plan.unemit_device(d16.data_ptr(), 3, d_coefs.data_ptr(), half=True)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_coefs.cpu().numpy(), coefs)
+        # arbitrary stream content (not an encoder's), multiply dequantizer
+        rng = np.random.Generator(np.random.PCG64(h))
+        anys = rng.integers(-2000, 2001, size=streams.shape, dtype=np.int32)
+        dense = np.zeros((3,) + plan.coef_shape, np.int32)
+        order = plan.emission_order().astype(np.int64)
+        src = order[plan.masks().reshape(-1)[order]]
+        for f in range(3):
+            for ch in range(c):
+                blk = dense[f, :, ch, :].reshape(-1).copy()
+                blk[src] = anys[f, ch]
+                dense[f, :, ch, :] = blk.reshape(plan.n_tiles, 512)
+        for f in range(3):
+            assert np.array_equal(plan.decode_emit(anys[f], q, multiply=True)[0], oracle_decode(plan, dense[f], some, q, multiply=True))
+
+
 def test_emission_gather_full_size():
     """The group-staged gather at BASELINE.json's full size against torch indexing with the plan's own
     order (the order itself is checked against the dict-based restatement on small shapes)."""
@@ -397,6 +439,11 @@ def test_emission_gather_full_size():
         torch.cuda.synchronize()
         for ch in range(c):
             assert torch.equal(out[0, ch], coefs[:, ch, :].reshape(-1)[src])
+        back = torch.full_like(coefs, 99)
+        plan.unemit_device(out.data_ptr(), 1, back.data_ptr())
+        torch.cuda.synchronize()
+        keep = some.reshape(plan.n_tiles, 1, 512).to(dev)
+        assert torch.equal(back, torch.where(keep, coefs, torch.zeros_like(coefs)))
 
 
 def test_stage_interface_mirrors_reference_pipeline():
