@@ -273,6 +273,28 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
     dec_ms = statistics.fmean(e[1].elapsed_time(e[2]) for e in events)
     timed_launches = launches
 
+    # ---- the same step on int16 coefficient arrays (fri_*_tq_device16): 3 B per sample instead of 5,
+    # reported as its own variant with its own byte count; the headline stays int32
+    c16 = [torch.empty((FRAMES,) + plan.coef_shape, dtype=torch.int16, device=dev) for _ in range(N_SETS)]
+    for s_ in range(N_SETS):
+        plan.encode_device(px[s_].data_ptr(), FRAMES, c16[s_].data_ptr(), q, stream, half=True)
+    v_steps = min(args.steps, 100)
+    vev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(v_steps)]
+    for k in range(-3, v_steps):
+        a, b = k % N_SETS, (k + N_SETS // 2) % N_SETS
+        if k >= 0:
+            vev[k][0].record()
+        plan.encode_device(px[a].data_ptr(), FRAMES, c16[a].data_ptr(), q, stream, half=True)
+        if k >= 0:
+            vev[k][1].record()
+        plan.decode_device(c16[b].data_ptr(), FRAMES, outs[b].data_ptr(), q, False, stream, half=True)
+        if k >= 0:
+            vev[k][2].record()
+    torch.cuda.synchronize()
+    v_enc = statistics.fmean(e[0].elapsed_time(e[1]) for e in vev)
+    v_dec = statistics.fmean(e[1].elapsed_time(e[2]) for e in vev)
+    del c16
+
     # ---- steady state: BASELINE.json configs[2] per-GPU share at 8 GPUs (32 batched 4K frames in one
     # launch per direction).  Reported beside the headline because a single 4096^2 frame is a ~50 us
     # launch whose ramp-up and last partial wave cost 15-25 %.
@@ -376,11 +398,12 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
 
     if world > 1:
         vals = [elapsed_ms, e2e_s, enc_ms, dec_ms] + ([batched[3], batched[4]] if batched else [0.0, 0.0])
-        vals += [e2e[k] for k in e2e_keys]
+        vals += [e2e[k] for k in e2e_keys] + [v_enc, v_dec]
         t = torch.tensor(vals, dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms, e2e_s, enc_ms, dec_ms, b0, b1 = (float(x) for x in t.tolist()[:6])
-        e2e = dict(zip(e2e_keys, (float(x) for x in t.tolist()[6:])))
+        e2e = dict(zip(e2e_keys, (float(x) for x in t.tolist()[6:6 + len(e2e_keys)])))
+        v_enc, v_dec = (float(x) for x in t.tolist()[-2:])
         if batched:
             batched = batched[:3] + (b0, b1)
         dist.barrier()
@@ -415,6 +438,14 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
                                 "i16 = fri_*_tq16 (151 MB each way)"},
             "gpu_launches": timed_launches, "clocks": clocks, "launch": plan.launch_info(),
         }
+        b16 = W * H * C * FRAMES * 3  # u8 pixel + i16 coefficient
+        line["int16_arrays"] = {
+            "note": "same step through fri_encode_tq_device16 / fri_decode_tq_device16 (int16 coefficient arrays, "
+                    "3 B per sample); a separate variant, not the headline",
+            "value": pix_step / ((v_enc + v_dec) * 1e-3) / 1e6, "unit": UNIT,
+            "encode": {"achieved": b16 / (v_enc * 1e-3) / 1e9, "frac": b16 / (v_enc * 1e-3) / 1e9 / peak, "avg_launch_ms": v_enc},
+            "decode": {"achieved": b16 / (v_dec * 1e-3) / 1e9, "frac": b16 / (v_dec * 1e-3) / 1e9 / peak, "avg_launch_ms": v_dec},
+            "algorithmic_bytes": b16, "unit_bw": "GB/s"}
         if batched:
             bw, bh, bf, b_enc, b_dec = batched
             bbytes = bw * bh * C * bf * BYTES_PER_SAMPLE

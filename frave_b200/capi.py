@@ -38,6 +38,8 @@ _SYMBOLS = [
     ("fri_plan_masks", C.c_int, [_P, _P]),
     ("fri_encode_tq_device", C.c_int, [_P, _P, C.c_uint32, _P, _P, _P]),
     ("fri_decode_tq_device", C.c_int, [_P, _P, C.c_uint32, _P, C.c_int, _P, _P]),
+    ("fri_encode_tq_device16", C.c_int, [_P, _P, C.c_uint32, _P, _P, _P]),
+    ("fri_decode_tq_device16", C.c_int, [_P, _P, C.c_uint32, _P, C.c_int, _P, _P]),
     ("fri_encode_tq", C.c_int, [_P, _P, C.c_uint32, _P, _P]),
     ("fri_decode_tq", C.c_int, [_P, _P, C.c_uint32, _P, C.c_int, _P]),
     ("fri_encode_tq16", C.c_int, [_P, _P, C.c_uint32, _P, _P]),
@@ -317,12 +319,15 @@ class Plan:
         return out
 
     # ---- device-resident entry points (raw device pointers, e.g. torch.Tensor.data_ptr()) -----
-    def encode_device(self, d_pixels: int, n_frames: int, d_coefs: int, q=None, stream: int = 0) -> None:
+    def encode_device(self, d_pixels: int, n_frames: int, d_coefs: int, q=None, stream: int = 0, half: bool = False) -> None:
+        """d_coefs: int32 (or, with half=True, int16) [n_frames, n_tiles, C, 2^depth] on the device."""
         qa, qp = _q_array(q)
-        _check(lib().fri_encode_tq_device(self._h, d_pixels, n_frames, qp, d_coefs, stream))
+        fn = lib().fri_encode_tq_device16 if half else lib().fri_encode_tq_device
+        _check(fn(self._h, d_pixels, n_frames, qp, d_coefs, stream))
 
     def decode_device(self, d_coefs: int, n_frames: int, d_pixels: int, q=None, multiply: bool = False,
-                      stream: int = 0) -> None:
+                      stream: int = 0, half: bool = False) -> None:
         qa, qp = _q_array(q)
         mode = FRI_DEQUANT_MULTIPLY if multiply else FRI_DEQUANT_DIVIDE
-        _check(lib().fri_decode_tq_device(self._h, d_coefs, n_frames, qp, mode, d_pixels, stream))
+        fn = lib().fri_decode_tq_device16 if half else lib().fri_decode_tq_device
+        _check(fn(self._h, d_coefs, n_frames, qp, mode, d_pixels, stream))

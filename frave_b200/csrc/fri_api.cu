@@ -357,7 +357,7 @@ int fri_plan_launch_info(const fri_plan *p, int32_t info[16])
     return FRI_OK;
 }
 
-int fri_encode_tq_device(const fri_plan *cp, const void *d_pixels, uint32_t n_frames, const int32_t *q, int32_t *d_coefs,
+static int encode_device(const fri_plan *cp, const void *d_pixels, uint32_t n_frames, const int32_t *q, void *d_coefs, bool half,
                          void *stream)
 {
     fri_plan *p = const_cast<fri_plan *>(cp);
@@ -367,18 +367,20 @@ int fri_encode_tq_device(const fri_plan *cp, const void *d_pixels, uint32_t n_fr
     if (n_frames == 0) return FRI_OK;
     if (!d_pixels || !d_coefs) return fail(FRI_E_INVALID, "NULL device buffer");
     const Geometry &g = p->plan.geo;
+    if (half && (g.sample_bytes != 1 || g.sub_bits != 0))
+        return fail(FRI_E_UNSUPPORTED, "int16 coefficient arrays need 8-bit samples and depth 9");
     if ((uintptr_t)d_coefs & 15) return fail(FRI_E_INVALID, "d_coefs must be 16-byte aligned");
     if ((uintptr_t)d_pixels & (uintptr_t)(g.sample_bytes - 1)) return fail(FRI_E_INVALID, "d_pixels must be aligned to the sample size");
     if ((rc = ensure_dc(p, n_frames))) return rc;
     QuantParams qp;
     make_quant_params(qp, q, 0);
     p->last_launches = 0;
-    FRI_CUDA(launch_encode(g, p->tables, qp, d_pixels, n_frames, d_coefs, p->d_dc_shared, static_cast<cudaStream_t>(stream),
+    FRI_CUDA(launch_encode(g, p->tables, qp, d_pixels, n_frames, d_coefs, half, p->d_dc_shared, static_cast<cudaStream_t>(stream),
                            &p->last_launches));
     return FRI_OK;
 }
 
-int fri_decode_tq_device(const fri_plan *cp, const int32_t *d_coefs, uint32_t n_frames, const int32_t *q, int dequant_mode,
+static int decode_device(const fri_plan *cp, const void *d_coefs, bool half, uint32_t n_frames, const int32_t *q, int dequant_mode,
                          void *d_pixels, void *stream)
 {
     fri_plan *p = const_cast<fri_plan *>(cp);
@@ -390,6 +392,8 @@ int fri_decode_tq_device(const fri_plan *cp, const int32_t *d_coefs, uint32_t n_
     if (n_frames == 0) return FRI_OK;
     if (!d_pixels || !d_coefs) return fail(FRI_E_INVALID, "NULL device buffer");
     const Geometry &g = p->plan.geo;
+    if (half && (g.sample_bytes != 1 || g.sub_bits != 0))
+        return fail(FRI_E_UNSUPPORTED, "int16 coefficient arrays need 8-bit samples and depth 9");
     if ((uintptr_t)d_coefs & 15) return fail(FRI_E_INVALID, "d_coefs must be 16-byte aligned");
     if ((uintptr_t)d_pixels & (uintptr_t)(g.sample_bytes - 1)) return fail(FRI_E_INVALID, "d_pixels must be aligned to the sample size");
     if ((rc = ensure_dc(p, n_frames))) return rc;
@@ -401,8 +405,32 @@ int fri_decode_tq_device(const fri_plan *cp, const int32_t *d_coefs, uint32_t n_
     // the retained fractals do not cover every pixel.
     if (p->plan.pixels_covered != (uint64_t)g.width * g.height)
         FRI_CUDA(cudaMemsetAsync(d_pixels, 0, (size_t)g.frame_bytes * n_frames, st));
-    FRI_CUDA(launch_decode(g, p->tables, qp, d_coefs, n_frames, d_pixels, p->d_dc_shared, st, &p->last_launches));
+    FRI_CUDA(launch_decode(g, p->tables, qp, d_coefs, half, n_frames, d_pixels, p->d_dc_shared, st, &p->last_launches));
     return FRI_OK;
+}
+
+int fri_encode_tq_device(const fri_plan *p, const void *d_pixels, uint32_t n_frames, const int32_t *q, int32_t *d_coefs,
+                         void *stream)
+{
+    return encode_device(p, d_pixels, n_frames, q, d_coefs, false, stream);
+}
+
+int fri_encode_tq_device16(const fri_plan *p, const void *d_pixels, uint32_t n_frames, const int32_t *q, int16_t *d_coefs,
+                           void *stream)
+{
+    return encode_device(p, d_pixels, n_frames, q, d_coefs, true, stream);
+}
+
+int fri_decode_tq_device(const fri_plan *p, const int32_t *d_coefs, uint32_t n_frames, const int32_t *q, int dequant_mode,
+                         void *d_pixels, void *stream)
+{
+    return decode_device(p, d_coefs, false, n_frames, q, dequant_mode, d_pixels, stream);
+}
+
+int fri_decode_tq_device16(const fri_plan *p, const int16_t *d_coefs, uint32_t n_frames, const int32_t *q, int dequant_mode,
+                           void *d_pixels, void *stream)
+{
+    return decode_device(p, d_coefs, true, n_frames, q, dequant_mode, d_pixels, stream);
 }
 
 static int encode_host(fri_plan *p, const void *pixels, uint32_t n_frames, const int32_t *q, void *coefs, bool half)
@@ -441,11 +469,15 @@ static int encode_host(fri_plan *p, const void *pixels, uint32_t n_frames, const
             }
             FRI_CUDA(cudaEventRecord(pl.in_ready[k], pl.in));
             FRI_CUDA(cudaStreamWaitEvent(pl.compute, pl.in_ready[k], 0));
-            FRI_CUDA(launch_encode(g, p->tables, qp, s.d_pixels, 1, s.d_coefs, s.d_dc, pl.compute, &p->last_launches, b.g0, b.g1));
+            // 16-bit transport: at depth 9 the kernel writes int16 itself; deep trees (coarse levels work on
+            // int32) are repacked on the device
+            const bool native16 = half && g.sub_bits == 0;
+            void *d_out = native16 ? static_cast<void *>(s.d_coefs16) : static_cast<void *>(s.d_coefs);
+            FRI_CUDA(launch_encode(g, p->tables, qp, s.d_pixels, 1, d_out, native16, s.d_dc, pl.compute, &p->last_launches, b.g0, b.g1));
             // the band's coefficient range (deep trees: one band, the coarse kernel has touched every fractal's top levels)
             const size_t c0 = g.sub_bits == 0 ? b.t0 * block : 0;
             const size_t cn = g.sub_bits == 0 ? (b.t1 - b.t0) * block : (size_t)g.coefs_per_frame;
-            if (half) FRI_CUDA(launch_pack16(s.d_coefs + c0, s.d_coefs16 + c0, cn, pl.compute, &p->last_launches));
+            if (half && !native16) FRI_CUDA(launch_pack16(s.d_coefs + c0, s.d_coefs16 + c0, cn, pl.compute, &p->last_launches));
             FRI_CUDA(cudaEventRecord(pl.band_done[k], pl.compute));
             FRI_CUDA(cudaStreamWaitEvent(pl.out, pl.band_done[k], 0));
             const void *d_src = half ? static_cast<const void *>(s.d_coefs16 + c0) : static_cast<const void *>(s.d_coefs + c0);
@@ -510,8 +542,10 @@ static int decode_host(fri_plan *p, const void *coefs, uint32_t n_frames, const 
             FRI_CUDA(cudaMemcpyAsync(d_dst, src + c0 * esz, cn * esz, cudaMemcpyHostToDevice, pl.in));
             FRI_CUDA(cudaEventRecord(pl.in_ready[k], pl.in));
             FRI_CUDA(cudaStreamWaitEvent(pl.compute, pl.in_ready[k], 0));
-            if (half) FRI_CUDA(launch_unpack16(s.d_coefs16 + c0, s.d_coefs + c0, cn, pl.compute, &p->last_launches));
-            FRI_CUDA(launch_decode(g, p->tables, qp, s.d_coefs, 1, s.d_pixels, s.d_dc, pl.compute, &p->last_launches, b.g0, b.g1));
+            const bool native16 = half && g.sub_bits == 0;  // the kernel reads int16 itself at depth 9
+            if (half && !native16) FRI_CUDA(launch_unpack16(s.d_coefs16 + c0, s.d_coefs + c0, cn, pl.compute, &p->last_launches));
+            const void *d_in = native16 ? static_cast<const void *>(s.d_coefs16) : static_cast<const void *>(s.d_coefs);
+            FRI_CUDA(launch_decode(g, p->tables, qp, d_in, native16, 1, s.d_pixels, s.d_dc, pl.compute, &p->last_launches, b.g0, b.g1));
             FRI_CUDA(cudaEventRecord(pl.band_done[k], pl.compute));
             FRI_CUDA(cudaStreamWaitEvent(pl.out, pl.band_done[k], 0));
             if (b.final_rows > rows_out) {  // rows no later band writes
@@ -701,7 +735,7 @@ static int encode_emit_host(fri_plan *p, const void *pixels, uint32_t n_frames, 
                                  (size_t)g.frame_bytes, cudaMemcpyHostToDevice, pl.in));
         FRI_CUDA(cudaEventRecord(pl.in_ready[0], pl.in));
         FRI_CUDA(cudaStreamWaitEvent(pl.compute, pl.in_ready[0], 0));
-        FRI_CUDA(launch_encode(g, p->tables, qp, s.d_pixels, 1, s.d_coefs, s.d_dc, pl.compute, &p->last_launches));
+        FRI_CUDA(launch_encode(g, p->tables, qp, s.d_pixels, 1, s.d_coefs, false, s.d_dc, pl.compute, &p->last_launches));
         FRI_CUDA(launch_emit(g, p->tables, p->emit_tables, count, s.d_coefs, 1, d_emit, half, pl.compute, &p->last_launches));
         FRI_CUDA(cudaEventRecord(pl.band_done[0], pl.compute));
         FRI_CUDA(cudaEventRecord(s.compute_done, pl.compute));
@@ -793,7 +827,7 @@ static int decode_emit_host(fri_plan *p, const void *streams, bool half, uint32_
         FRI_CUDA(cudaStreamWaitEvent(pl.compute, pl.in_ready[0], 0));
         if (need_zero) FRI_CUDA(cudaMemsetAsync(s.d_pixels, 0, (size_t)g.frame_bytes, pl.compute));
         FRI_CUDA(launch_unemit(g, p->tables, p->emit_tables, count, d_emit, half, 1, s.d_coefs, pl.compute, &p->last_launches));
-        FRI_CUDA(launch_decode(g, p->tables, qp, s.d_coefs, 1, s.d_pixels, s.d_dc, pl.compute, &p->last_launches));
+        FRI_CUDA(launch_decode(g, p->tables, qp, s.d_coefs, false, 1, s.d_pixels, s.d_dc, pl.compute, &p->last_launches));
         FRI_CUDA(cudaEventRecord(pl.band_done[0], pl.compute));
         FRI_CUDA(cudaEventRecord(s.compute_done, pl.compute));
         FRI_CUDA(cudaStreamWaitEvent(pl.out, pl.band_done[0], 0));

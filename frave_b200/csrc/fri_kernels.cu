@@ -348,6 +348,39 @@ __device__ __forceinline__ void store_chunk_masked(uint8_t *gp, const uint8_t *s
     }
 }
 
+// Coefficient stores / loads of 4, 2 or 1 consecutive values (streaming), for the two coefficient
+// types a device array can have: int32 (the reference's i32) and int16 (every coefficient of an
+// 8-bit image fits; 3 B per sample instead of 5 — reported as its own variant).
+__device__ __forceinline__ uint32_t pack16(int lo, int hi)
+{
+    uint32_t r;
+    asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(r) : "r"(hi), "r"(lo));  // {sat(hi), sat(lo)}
+    return r;
+}
+__device__ __forceinline__ void st_c4(int32_t *p, int4 v) { __stcs(reinterpret_cast<int4 *>(p), v); }
+__device__ __forceinline__ void st_c2(int32_t *p, int2 v) { __stcs(reinterpret_cast<int2 *>(p), v); }
+__device__ __forceinline__ void st_c1(int32_t *p, int v) { __stcs(p, v); }
+__device__ __forceinline__ void st_c4(int16_t *p, int4 v)
+{
+    __stcs(reinterpret_cast<int2 *>(p), make_int2((int)pack16(v.x, v.y), (int)pack16(v.z, v.w)));
+}
+__device__ __forceinline__ void st_c2(int16_t *p, int2 v) { __stcs(reinterpret_cast<int *>(p), (int)pack16(v.x, v.y)); }
+__device__ __forceinline__ void st_c1(int16_t *p, int v) { __stcs(p, (short)pack16(v, 0)); }
+__device__ __forceinline__ int4 ld_c4(const int32_t *p) { return __ldcs(reinterpret_cast<const int4 *>(p)); }
+__device__ __forceinline__ int2 ld_c2(const int32_t *p) { return __ldcs(reinterpret_cast<const int2 *>(p)); }
+__device__ __forceinline__ int ld_c1(const int32_t *p) { return __ldcs(p); }
+__device__ __forceinline__ int4 ld_c4(const int16_t *p)
+{
+    const int2 r = __ldcs(reinterpret_cast<const int2 *>(p));
+    return make_int4((int)(short)r.x, r.x >> 16, (int)(short)r.y, r.y >> 16);
+}
+__device__ __forceinline__ int2 ld_c2(const int16_t *p)
+{
+    const int r = __ldcs(reinterpret_cast<const int *>(p));
+    return make_int2((int)(short)r, r >> 16);
+}
+__device__ __forceinline__ int ld_c1(const int16_t *p) { return (int)__ldcs(p); }
+
 // ------------------------------------------------------------------------------------------
 // CTA-level building blocks
 // ------------------------------------------------------------------------------------------
@@ -407,10 +440,10 @@ __device__ __forceinline__ void stage_group(const Geometry &g, const GroupDesc &
 //   phase 2 (all channels at once): lane group lane / 8 owns a channel; lane j of the group
 //                          folds s6[8j .. 8j+7] through levels 5..3 in registers and levels 2..0
 //                          with three shuffles inside the group.
-template <int C, typename S, bool DEEP, int QS>
+template <int C, typename S, bool DEEP, int QS, typename CT>
 __device__ __forceinline__ void encode_tiles(const Geometry &g, const QuantParams &qp, const GroupDesc &gd, const RegionView &rv,
                                              const uint32_t *__restrict__ tile_unit, int frame, const uint8_t *region,
-                                             int32_t *scratch, int32_t *__restrict__ coefs, int32_t *__restrict__ dc_out,
+                                             int32_t *scratch, CT *__restrict__ coefs, int32_t *__restrict__ dc_out,
                                              bool two_stage)
 {
     constexpr int SB = (int)sizeof(S);
@@ -510,14 +543,14 @@ __device__ __forceinline__ void encode_tiles(const Geometry &g, const QuantParam
                     if ((qp.fix >> (top + 6)) & 1u) b6 = quant_layer_enc(qp, r6, top + 7);
                 }
             }
-            int32_t *out = coefs + ta.block + ((int64_t)ch << depth);
-            int32_t *o8 = out + ((size_t)ta.node << 8), *o7 = out + ((size_t)ta.node << 7), *o6 = out + ((size_t)ta.node << 6);
-            __stcs(reinterpret_cast<int4 *>(o8) + lane, make_int4(a8[0], a8[1], a8[2], a8[3]));
-            __stcs(reinterpret_cast<int4 *>(o8 + 128) + lane, make_int4(b8[0], b8[1], b8[2], b8[3]));
-            __stcs(reinterpret_cast<int2 *>(o7) + lane, make_int2(a7[0], a7[1]));
-            __stcs(reinterpret_cast<int2 *>(o7 + 64) + lane, make_int2(b7[0], b7[1]));
-            __stcs(o6 + lane, a6);
-            __stcs(o6 + 32 + lane, b6);
+            CT *out = coefs + ta.block + ((int64_t)ch << depth);
+            CT *o8 = out + ((size_t)ta.node << 8), *o7 = out + ((size_t)ta.node << 7), *o6 = out + ((size_t)ta.node << 6);
+            st_c4(o8 + 4 * lane, make_int4(a8[0], a8[1], a8[2], a8[3]));
+            st_c4(o8 + 128 + 4 * lane, make_int4(b8[0], b8[1], b8[2], b8[3]));
+            st_c2(o7 + 2 * lane, make_int2(a7[0], a7[1]));
+            st_c2(o7 + 64 + 2 * lane, make_int2(b7[0], b7[1]));
+            st_c1(o6 + lane, a6);
+            st_c1(o6 + 32 + lane, b6);
         }
         __syncwarp();
 
@@ -553,16 +586,16 @@ __device__ __forceinline__ void encode_tiles(const Geometry &g, const QuantParam
                 }
             }
             if (grp_live) {
-                int32_t *out = coefs + ta.block + ((int64_t)grp << depth);
+                CT *out = coefs + ta.block + ((int64_t)grp << depth);
                 const size_t node = ta.node;
-                __stcs(reinterpret_cast<int4 *>(out + (node << 5)) + j8, make_int4(d5[0], d5[1], d5[2], d5[3]));
-                __stcs(reinterpret_cast<int2 *>(out + (node << 4)) + j8, make_int2(d4[0], d4[1]));
-                __stcs(out + (node << 3) + j8, d3);
-                if ((j8 & 1) == 0) __stcs(out + (node << 2) + (j8 >> 1), d2);
-                if ((j8 & 3) == 0) __stcs(out + (node << 1) + (j8 >> 2), d1);
+                st_c4(out + (node << 5) + 4 * j8, make_int4(d5[0], d5[1], d5[2], d5[3]));
+                st_c2(out + (node << 4) + 2 * j8, make_int2(d4[0], d4[1]));
+                st_c1(out + (node << 3) + j8, d3);
+                if ((j8 & 1) == 0) st_c1(out + (node << 2) + (j8 >> 1), d2);
+                if ((j8 & 3) == 0) st_c1(out + (node << 1) + (j8 >> 2), d1);
                 if (j8 == 0) {
-                    __stcs(out + node, d0);
-                    if (sub_bits == 0) __stcs(out, s0);
+                    st_c1(out + node, d0);
+                    if (sub_bits == 0) st_c1(out, s0);
                     else dc_out[ta.dc + ((int64_t)grp << sub_bits)] = s0;
                 }
             }
@@ -573,13 +606,13 @@ __device__ __forceinline__ void encode_tiles(const Geometry &g, const QuantParam
 
 // Pulls a group's coefficients towards L2: at depth 9 the blocks of a group's tiles are adjacent
 // (plan order is group-major), n_present * C * 2 KB in one run.
-template <int C, bool DEEP>
+template <int C, bool DEEP, typename CT>
 __device__ __forceinline__ void prefetch_group_coefs(const Geometry &g, const GroupDesc &gd, int frame,
-                                                     const int32_t *__restrict__ coefs)
+                                                     const CT *__restrict__ coefs)
 {
     if (DEEP) return;
     const char *first = reinterpret_cast<const char *>(coefs + ((((int64_t)frame * g.n_fractals + gd.tile_base) * C) << kBaseDepth));
-    const int lines = __popc(gd.tile_mask) * C * 16;  // 128-byte lines
+    const int lines = __popc(gd.tile_mask) * C * (4 * (int)sizeof(CT));  // 128-byte lines: 512 coefficients per (tile, channel)
 #pragma unroll 1
     for (int i = threadIdx.x; i < lines; i += blockDim.x)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(first + (size_t)i * 128));
@@ -594,16 +627,17 @@ struct LaneCoefs {
     int2 a7, b7;
     int a6, b6;
 };
-__device__ __forceinline__ LaneCoefs load_lane_coefs(const int32_t *__restrict__ in, size_t node, int lane)
+template <typename CT>
+__device__ __forceinline__ LaneCoefs load_lane_coefs(const CT *__restrict__ in, size_t node, int lane)
 {
-    const int32_t *i8 = in + (node << 8), *i7 = in + (node << 7), *i6 = in + (node << 6);
+    const CT *i8 = in + (node << 8), *i7 = in + (node << 7), *i6 = in + (node << 6);
     LaneCoefs c;
-    c.a8 = __ldcs(reinterpret_cast<const int4 *>(i8) + lane);
-    c.b8 = __ldcs(reinterpret_cast<const int4 *>(i8 + 128) + lane);
-    c.a7 = __ldcs(reinterpret_cast<const int2 *>(i7) + lane);
-    c.b7 = __ldcs(reinterpret_cast<const int2 *>(i7 + 64) + lane);
-    c.a6 = __ldcs(i6 + lane);
-    c.b6 = __ldcs(i6 + 32 + lane);
+    c.a8 = ld_c4(i8 + 4 * lane);
+    c.b8 = ld_c4(i8 + 128 + 4 * lane);
+    c.a7 = ld_c2(i7 + 2 * lane);
+    c.b7 = ld_c2(i7 + 64 + 2 * lane);
+    c.a6 = ld_c1(i6 + lane);
+    c.b6 = ld_c1(i6 + 32 + lane);
     return c;
 }
 
@@ -613,20 +647,20 @@ struct TopCoefs {
     int2 d4;
     int d3, d2, d1, d0, s0;
 };
-template <bool DEEP>
-__device__ __forceinline__ TopCoefs load_top_coefs(const int32_t *__restrict__ coefs, const int32_t *__restrict__ dc_in,
+template <bool DEEP, typename CT>
+__device__ __forceinline__ TopCoefs load_top_coefs(const CT *__restrict__ coefs, const int32_t *__restrict__ dc_in,
                                                    const TaskAddr &ta, int grp, int j8, int depth, int sub_bits)
 {
-    const int32_t *in = coefs + ta.block + ((int64_t)grp << depth);
+    const CT *in = coefs + ta.block + ((int64_t)grp << depth);
     const size_t node = ta.node;
     TopCoefs t;
-    t.d5 = __ldcs(reinterpret_cast<const int4 *>(in + (node << 5)) + j8);
-    t.d4 = __ldcs(reinterpret_cast<const int2 *>(in + (node << 4)) + j8);
-    t.d3 = __ldcs(in + (node << 3) + j8);
-    t.d2 = __ldcs(in + (node << 2) + (j8 >> 1));
-    t.d1 = __ldcs(in + (node << 1) + (j8 >> 2));
-    t.d0 = __ldcs(in + node);
-    t.s0 = (!DEEP || sub_bits == 0) ? __ldcs(in) : dc_in[ta.dc + ((int64_t)grp << sub_bits)];
+    t.d5 = ld_c4(in + (node << 5) + 4 * j8);
+    t.d4 = ld_c2(in + (node << 4) + 2 * j8);
+    t.d3 = ld_c1(in + (node << 3) + j8);
+    t.d2 = ld_c1(in + (node << 2) + (j8 >> 1));
+    t.d1 = ld_c1(in + (node << 1) + (j8 >> 2));
+    t.d0 = ld_c1(in + node);
+    t.s0 = (!DEEP || sub_bits == 0) ? ld_c1(in) : dc_in[ta.dc + ((int64_t)grp << sub_bits)];
     return t;
 }
 
@@ -634,10 +668,10 @@ __device__ __forceinline__ TopCoefs load_top_coefs(const int32_t *__restrict__ c
 // image of encode_tiles: lane group lane / 8 first unfolds levels 0..5 of its channel (lane j
 // ends with the eight level-6 low-pass values 8j .. 8j+7) into the warp's scratch, then every
 // lane unfolds its two depth-3 subtrees per channel and scatters the 16 clamped leaves.
-template <int C, typename S, bool DEEP, int QS>
+template <int C, typename S, bool DEEP, int QS, typename CT>
 __device__ __forceinline__ void decode_tiles(const Geometry &g, const QuantParams &qp, const GroupDesc &gd, const RegionView &rv,
                                              const uint32_t *__restrict__ tile_unit, int frame, uint8_t *region,
-                                             int32_t *scratch, const int32_t *__restrict__ coefs,
+                                             int32_t *scratch, const CT *__restrict__ coefs,
                                              const int32_t *__restrict__ dc_in)
 {
     constexpr int SB = (int)sizeof(S);
@@ -669,7 +703,7 @@ __device__ __forceinline__ void decode_tiles(const Geometry &g, const QuantParam
 
         // ---- levels 0..5 of all channels, 8 lanes per channel
         {
-            const TopCoefs tc = load_top_coefs<DEEP>(coefs, dc_in, ta, grp, j8, depth, sub_bits);
+            const TopCoefs tc = load_top_coefs<DEEP, CT>(coefs, dc_in, ta, grp, j8, depth, sub_bits);
             int4 d5 = tc.d5;
             int2 d4 = tc.d4;
             int d3 = tc.d3, d2 = tc.d2, d1 = tc.d1, d0 = tc.d0, s0 = tc.s0;
@@ -955,12 +989,12 @@ __device__ __forceinline__ size_t region_bytes(const Geometry &g) { return ((siz
 #ifndef FRI_DEC_MINB
 #define FRI_DEC_MINB 4
 #endif
-template <int C, typename S, bool DEEP, int QS>
+template <int C, typename S, bool DEEP, int QS, typename CT>
 __global__ void __launch_bounds__(kThreads, FRI_ENC_MINB)
 fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ QuantParams qp,
                   const GroupDesc *__restrict__ groups, const uint32_t *__restrict__ tile_unit,
                   const uint32_t *__restrict__ stage_list, const uint8_t *__restrict__ pixels,
-                  int32_t *__restrict__ coefs, int32_t *__restrict__ dc_out, int lookahead, int group_offset)
+                  CT *__restrict__ coefs, int32_t *__restrict__ dc_out, int lookahead, int group_offset)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *region = smem;
@@ -1007,19 +1041,19 @@ fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
     }
     __syncthreads();
     FRI_TRACE_MARK(1);
-    encode_tiles<C, S, DEEP, QS>(g, qp, gd, rv, tile_unit, frame, region, scratch, coefs, dc_out, two_stage);
+    encode_tiles<C, S, DEEP, QS, CT>(g, qp, gd, rv, tile_unit, frame, region, scratch, coefs, dc_out, two_stage);
 #if FRI_TRACE
     __syncthreads();
 #endif
     FRI_TRACE_MARK(2);
 }
 
-template <int C, typename S, bool DEEP, int QS>
+template <int C, typename S, bool DEEP, int QS, typename CT>
 __global__ void __launch_bounds__(kThreads, FRI_DEC_MINB)
 fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ QuantParams qp,
                   const GroupDesc *__restrict__ groups, const uint32_t *__restrict__ tile_unit,
                   const uint32_t *__restrict__ chunk_list, const uint16_t *__restrict__ chunk_mask,
-                  const int32_t *__restrict__ coefs, const int32_t *__restrict__ dc_in, uint8_t *__restrict__ pixels,
+                  const CT *__restrict__ coefs, const int32_t *__restrict__ dc_in, uint8_t *__restrict__ pixels,
                   int group_offset)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -1030,12 +1064,12 @@ fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
     const int frame = blockIdx.y;
     const RegionView rv = region_view<C * (int)sizeof(S)>(g, gd, pixels + (int64_t)frame * g.frame_bytes);
     FRI_TRACE_MARK(0);
-    prefetch_group_coefs<C, DEEP>(g, gd, frame, coefs);
+    prefetch_group_coefs<C, DEEP, CT>(g, gd, frame, coefs);
     if (__popc(gd.tile_mask) != g.group_a * g.group_b) {
         zero_region(g, region);
         __syncthreads();
     }
-    decode_tiles<C, S, DEEP, QS>(g, qp, gd, rv, tile_unit, frame, region, scratch, coefs, dc_in);
+    decode_tiles<C, S, DEEP, QS, CT>(g, qp, gd, rv, tile_unit, frame, region, scratch, coefs, dc_in);
     const WriteAhead ahead = write_out_preload(g, rv, chunk_list, chunk_mask, pol);
     __syncthreads();
     FRI_TRACE_MARK(1);
@@ -1219,23 +1253,29 @@ cudaError_t configure_kernels()
 {
     cudaError_t e;
 #define FRI_CFG(k) if ((e = set_smem(k, kMaxSmem)) != cudaSuccess) return e
-#define FRI_CFG4(name)                                      \
-    FRI_CFG((name<1, uint8_t, false, kQuantGeneric>));      \
-    FRI_CFG((name<3, uint8_t, false, kQuantGeneric>));      \
-    FRI_CFG((name<1, uint16_t, false, kQuantGeneric>));     \
-    FRI_CFG((name<3, uint16_t, false, kQuantGeneric>));     \
-    FRI_CFG((name<1, uint8_t, false, kQuantNone>));         \
-    FRI_CFG((name<3, uint8_t, false, kQuantNone>));         \
-    FRI_CFG((name<1, uint16_t, false, kQuantNone>));        \
-    FRI_CFG((name<3, uint16_t, false, kQuantNone>));        \
-    FRI_CFG((name<1, uint8_t, false, kQuantSmallest>));     \
-    FRI_CFG((name<3, uint8_t, false, kQuantSmallest>));     \
-    FRI_CFG((name<1, uint16_t, false, kQuantSmallest>));    \
-    FRI_CFG((name<3, uint16_t, false, kQuantSmallest>));    \
-    FRI_CFG((name<1, uint8_t, true, kQuantGeneric>));       \
-    FRI_CFG((name<3, uint8_t, true, kQuantGeneric>));       \
-    FRI_CFG((name<1, uint16_t, true, kQuantGeneric>));      \
-    FRI_CFG((name<3, uint16_t, true, kQuantGeneric>))
+#define FRI_CFG4(name)                                               \
+    FRI_CFG((name<1, uint8_t, false, kQuantGeneric, int32_t>));      \
+    FRI_CFG((name<3, uint8_t, false, kQuantGeneric, int32_t>));      \
+    FRI_CFG((name<1, uint16_t, false, kQuantGeneric, int32_t>));     \
+    FRI_CFG((name<3, uint16_t, false, kQuantGeneric, int32_t>));     \
+    FRI_CFG((name<1, uint8_t, false, kQuantNone, int32_t>));         \
+    FRI_CFG((name<3, uint8_t, false, kQuantNone, int32_t>));         \
+    FRI_CFG((name<1, uint16_t, false, kQuantNone, int32_t>));        \
+    FRI_CFG((name<3, uint16_t, false, kQuantNone, int32_t>));        \
+    FRI_CFG((name<1, uint8_t, false, kQuantSmallest, int32_t>));     \
+    FRI_CFG((name<3, uint8_t, false, kQuantSmallest, int32_t>));     \
+    FRI_CFG((name<1, uint16_t, false, kQuantSmallest, int32_t>));    \
+    FRI_CFG((name<3, uint16_t, false, kQuantSmallest, int32_t>));    \
+    FRI_CFG((name<1, uint8_t, true, kQuantGeneric, int32_t>));       \
+    FRI_CFG((name<3, uint8_t, true, kQuantGeneric, int32_t>));       \
+    FRI_CFG((name<1, uint16_t, true, kQuantGeneric, int32_t>));      \
+    FRI_CFG((name<3, uint16_t, true, kQuantGeneric, int32_t>));      \
+    FRI_CFG((name<1, uint8_t, false, kQuantGeneric, int16_t>));      \
+    FRI_CFG((name<3, uint8_t, false, kQuantGeneric, int16_t>));      \
+    FRI_CFG((name<1, uint8_t, false, kQuantNone, int16_t>));         \
+    FRI_CFG((name<3, uint8_t, false, kQuantNone, int16_t>));         \
+    FRI_CFG((name<1, uint8_t, false, kQuantSmallest, int16_t>));     \
+    FRI_CFG((name<3, uint8_t, false, kQuantSmallest, int16_t>))
     FRI_CFG4(fri_encode_kernel);
     FRI_CFG4(fri_decode_kernel);
     FRI_CFG(fri_coarse_forward_kernel);
@@ -1270,9 +1310,12 @@ int resident_ctas(const Geometry &g)
 }  // namespace
 
 cudaError_t launch_encode(const Geometry &g, const DeviceTables &t, const QuantParams &qp, const void *d_pixels,
-                          uint32_t n_frames, int32_t *d_coefs, int32_t *d_dc, cudaStream_t stream,
+                          uint32_t n_frames, void *d_coefs_any, bool half, int32_t *d_dc, cudaStream_t stream,
                           uint32_t *launches, int group_begin, int group_end)
 {
+    if (half && (g.sub_bits != 0 || g.sample_bytes != 1)) return cudaErrorInvalidValue;  // int16 arrays: depth 9, 8-bit samples
+    int32_t *d_coefs = static_cast<int32_t *>(d_coefs_any);
+    int16_t *d_coefs16 = static_cast<int16_t *>(d_coefs_any);
     if (group_end < 0) group_end = g.n_groups;
     const int n_groups = group_end - group_begin;
     const bool whole = group_begin == 0 && group_end == g.n_groups;
@@ -1288,20 +1331,28 @@ cudaError_t launch_encode(const Geometry &g, const DeviceTables &t, const QuantP
         const dim3 grid((unsigned)n_groups, nf);
         const uint8_t *p = px + (int64_t)f0 * g.frame_bytes;
         int32_t *c = d_coefs + (int64_t)f0 * g.coefs_per_frame;
+        int16_t *c16 = d_coefs16 + (int64_t)f0 * g.coefs_per_frame;
         int32_t *dc = d_dc ? d_dc + (((int64_t)f0 * g.n_fractals * g.channels) << g.sub_bits) : nullptr;
-#define FRI_LAUNCH_Q(CC, SS, DD, QQ) \
-    fri_encode_kernel<CC, SS, DD, QQ><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.stage_list, p, c, dc, lookahead, group_begin)
-#define FRI_LAUNCH(CC, SS)                                                          \
-        do {                                                                        \
-            if (g.sub_bits != 0) FRI_LAUNCH_Q(CC, SS, true, kQuantGeneric);         \
-            else if (qclass == kQuantNone) FRI_LAUNCH_Q(CC, SS, false, kQuantNone); \
-            else if (qclass == kQuantSmallest) FRI_LAUNCH_Q(CC, SS, false, kQuantSmallest); \
-            else FRI_LAUNCH_Q(CC, SS, false, kQuantGeneric);                        \
+#define FRI_LAUNCH_Q(CC, SS, DD, QQ, TT, PTR) \
+    fri_encode_kernel<CC, SS, DD, QQ, TT><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.stage_list, p, PTR, dc, lookahead, group_begin)
+#define FRI_LAUNCH(CC, SS, TT, PTR)                                                           \
+        do {                                                                                  \
+            if (qclass == kQuantNone) FRI_LAUNCH_Q(CC, SS, false, kQuantNone, TT, PTR);       \
+            else if (qclass == kQuantSmallest) FRI_LAUNCH_Q(CC, SS, false, kQuantSmallest, TT, PTR); \
+            else FRI_LAUNCH_Q(CC, SS, false, kQuantGeneric, TT, PTR);                         \
         } while (0)
-        if (g.channels == 1 && g.sample_bytes == 1) FRI_LAUNCH(1, uint8_t);
-        else if (g.channels == 3 && g.sample_bytes == 1) FRI_LAUNCH(3, uint8_t);
-        else if (g.channels == 1 && g.sample_bytes == 2) FRI_LAUNCH(1, uint16_t);
-        else FRI_LAUNCH(3, uint16_t);
+        if (half) {
+            if (g.channels == 1) FRI_LAUNCH(1, uint8_t, int16_t, c16);
+            else FRI_LAUNCH(3, uint8_t, int16_t, c16);
+        } else if (g.sub_bits != 0) {
+            if (g.channels == 1 && g.sample_bytes == 1) FRI_LAUNCH_Q(1, uint8_t, true, kQuantGeneric, int32_t, c);
+            else if (g.channels == 3 && g.sample_bytes == 1) FRI_LAUNCH_Q(3, uint8_t, true, kQuantGeneric, int32_t, c);
+            else if (g.channels == 1 && g.sample_bytes == 2) FRI_LAUNCH_Q(1, uint16_t, true, kQuantGeneric, int32_t, c);
+            else FRI_LAUNCH_Q(3, uint16_t, true, kQuantGeneric, int32_t, c);
+        } else if (g.channels == 1 && g.sample_bytes == 1) FRI_LAUNCH(1, uint8_t, int32_t, c);
+        else if (g.channels == 3 && g.sample_bytes == 1) FRI_LAUNCH(3, uint8_t, int32_t, c);
+        else if (g.channels == 1 && g.sample_bytes == 2) FRI_LAUNCH(1, uint16_t, int32_t, c);
+        else FRI_LAUNCH(3, uint16_t, int32_t, c);
 #undef FRI_LAUNCH
 #undef FRI_LAUNCH_Q
         if (launches) ++*launches;
@@ -1315,10 +1366,13 @@ cudaError_t launch_encode(const Geometry &g, const DeviceTables &t, const QuantP
     return cudaGetLastError();
 }
 
-cudaError_t launch_decode(const Geometry &g, const DeviceTables &t, const QuantParams &qp, const int32_t *d_coefs,
+cudaError_t launch_decode(const Geometry &g, const DeviceTables &t, const QuantParams &qp, const void *d_coefs_any, bool half,
                           uint32_t n_frames, void *d_pixels, int32_t *d_dc, cudaStream_t stream,
                           uint32_t *launches, int group_begin, int group_end)
 {
+    if (half && (g.sub_bits != 0 || g.sample_bytes != 1)) return cudaErrorInvalidValue;
+    const int32_t *d_coefs = static_cast<const int32_t *>(d_coefs_any);
+    const int16_t *d_coefs16 = static_cast<const int16_t *>(d_coefs_any);
     if (group_end < 0) group_end = g.n_groups;
     const int n_groups = group_end - group_begin;
     if (n_frames == 0 || n_groups <= 0) return cudaSuccess;
@@ -1336,20 +1390,28 @@ cudaError_t launch_decode(const Geometry &g, const DeviceTables &t, const QuantP
         const dim3 grid((unsigned)n_groups, nf);
         uint8_t *p = px + (int64_t)f0 * g.frame_bytes;
         const int32_t *c = d_coefs + (int64_t)f0 * g.coefs_per_frame;
+        const int16_t *c16 = d_coefs16 + (int64_t)f0 * g.coefs_per_frame;
         int32_t *dc = d_dc ? d_dc + (((int64_t)f0 * g.n_fractals * g.channels) << g.sub_bits) : nullptr;
-#define FRI_LAUNCH_Q(CC, SS, DD, QQ) \
-    fri_decode_kernel<CC, SS, DD, QQ><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, t.chunk_mask, c, dc, p, group_begin)
-#define FRI_LAUNCH(CC, SS)                                                          \
-        do {                                                                        \
-            if (g.sub_bits != 0) FRI_LAUNCH_Q(CC, SS, true, kQuantGeneric);         \
-            else if (qclass == kQuantNone) FRI_LAUNCH_Q(CC, SS, false, kQuantNone); \
-            else if (qclass == kQuantSmallest) FRI_LAUNCH_Q(CC, SS, false, kQuantSmallest); \
-            else FRI_LAUNCH_Q(CC, SS, false, kQuantGeneric);                        \
+#define FRI_LAUNCH_Q(CC, SS, DD, QQ, TT, PTR) \
+    fri_decode_kernel<CC, SS, DD, QQ, TT><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, t.chunk_mask, PTR, dc, p, group_begin)
+#define FRI_LAUNCH(CC, SS, TT, PTR)                                                           \
+        do {                                                                                  \
+            if (qclass == kQuantNone) FRI_LAUNCH_Q(CC, SS, false, kQuantNone, TT, PTR);       \
+            else if (qclass == kQuantSmallest) FRI_LAUNCH_Q(CC, SS, false, kQuantSmallest, TT, PTR); \
+            else FRI_LAUNCH_Q(CC, SS, false, kQuantGeneric, TT, PTR);                         \
         } while (0)
-        if (g.channels == 1 && g.sample_bytes == 1) FRI_LAUNCH(1, uint8_t);
-        else if (g.channels == 3 && g.sample_bytes == 1) FRI_LAUNCH(3, uint8_t);
-        else if (g.channels == 1 && g.sample_bytes == 2) FRI_LAUNCH(1, uint16_t);
-        else FRI_LAUNCH(3, uint16_t);
+        if (half) {
+            if (g.channels == 1) FRI_LAUNCH(1, uint8_t, int16_t, c16);
+            else FRI_LAUNCH(3, uint8_t, int16_t, c16);
+        } else if (g.sub_bits != 0) {
+            if (g.channels == 1 && g.sample_bytes == 1) FRI_LAUNCH_Q(1, uint8_t, true, kQuantGeneric, int32_t, c);
+            else if (g.channels == 3 && g.sample_bytes == 1) FRI_LAUNCH_Q(3, uint8_t, true, kQuantGeneric, int32_t, c);
+            else if (g.channels == 1 && g.sample_bytes == 2) FRI_LAUNCH_Q(1, uint16_t, true, kQuantGeneric, int32_t, c);
+            else FRI_LAUNCH_Q(3, uint16_t, true, kQuantGeneric, int32_t, c);
+        } else if (g.channels == 1 && g.sample_bytes == 1) FRI_LAUNCH(1, uint8_t, int32_t, c);
+        else if (g.channels == 3 && g.sample_bytes == 1) FRI_LAUNCH(3, uint8_t, int32_t, c);
+        else if (g.channels == 1 && g.sample_bytes == 2) FRI_LAUNCH(1, uint16_t, int32_t, c);
+        else FRI_LAUNCH(3, uint16_t, int32_t, c);
 #undef FRI_LAUNCH
 #undef FRI_LAUNCH_Q
         if (launches) ++*launches;

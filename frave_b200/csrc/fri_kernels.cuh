@@ -106,13 +106,14 @@ cudaError_t configure_kernels();
 
 // Enqueue the fused forward transform + quantization for n_frames frames.  [group_begin, group_end)
 // restricts the launch to a band of consecutive groups of every frame (default: all groups).
+//   d_coefs / half: int32 coefficient array, or (half; depth 9 and 8-bit samples only) int16.
 //   d_dc: scratch for the base tiles' low-pass roots, [n_frames][n_fractals][C][2^sub_bits]
-//         (depth > 9 only; finished by launch_coarse_forward).
+//         (depth > 9 only; finished by the coarse kernel).
 cudaError_t launch_encode(const Geometry &g, const DeviceTables &t, const QuantParams &qp, const void *d_pixels,
-                          uint32_t n_frames, int32_t *d_coefs, int32_t *d_dc, cudaStream_t stream,
+                          uint32_t n_frames, void *d_coefs, bool half, int32_t *d_dc, cudaStream_t stream,
                           uint32_t *launches, int group_begin = 0, int group_end = -1);
 // Enqueue the fused dequantization + inverse transform + scatter.
-cudaError_t launch_decode(const Geometry &g, const DeviceTables &t, const QuantParams &qp, const int32_t *d_coefs,
+cudaError_t launch_decode(const Geometry &g, const DeviceTables &t, const QuantParams &qp, const void *d_coefs, bool half,
                           uint32_t n_frames, void *d_pixels, int32_t *d_dc, cudaStream_t stream,
                           uint32_t *launches, int group_begin = 0, int group_end = -1);
 

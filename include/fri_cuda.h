@@ -107,6 +107,18 @@ int fri_decode_tq_device(const fri_plan *plan, const int32_t *d_coefs, uint32_t 
                          int dequant_mode, void *d_pixels, void *stream);
 
 /*
+ * The same two calls on int16 coefficient arrays (depth 9 and 8-bit samples only, else
+ * FRI_E_UNSUPPORTED): every coefficient of an 8-bit image fits (see fri_encode_tq16 below), the
+ * arithmetic is the same int32 arithmetic, the array is half the size — 3 bytes of HBM traffic
+ * per sample instead of 5, reported as its own variant.  Encode saturates on the
+ * (impossible) overflow; decode accepts any int16 content.
+ */
+int fri_encode_tq_device16(const fri_plan *plan, const void *d_pixels, uint32_t n_frames, const int32_t *q,
+                           int16_t *d_coefs, void *stream);
+int fri_decode_tq_device16(const fri_plan *plan, const int16_t *d_coefs, uint32_t n_frames, const int32_t *q,
+                           int dequant_mode, void *d_pixels, void *stream);
+
+/*
  * Host-buffer entry points (what libfri's stage functions call): copy in, run, copy out,
  * synchronise.  Frames are pipelined over the plan's internal streams; buffers obtained from
  * fri_host_alloc are pinned and take the fast path, any other host memory is staged through
@@ -123,8 +135,9 @@ int fri_decode_tq(fri_plan *plan, const int32_t *coefs, uint32_t n_frames, const
  * 211-218), and so does every coefficient a decodable container can hold (1024-symbol alphabet,
  * entropy_coding.rs:25), so the Rust glue can widen to the reference's Vec<Option<i32>> while it
  * applies the mask — and the PCIe copies, which bound these calls, carry half the bytes.  The
- * device computes in i32 exactly as above; encode saturates on the (impossible) overflow instead
- * of wrapping.  FRI_E_UNSUPPORTED for sample_bytes = 2 (residues need 18 bits).
+ * device computes in i32 exactly as above (at depth 9 the kernels read / write the int16 array
+ * themselves, deep trees are repacked on the device); encode saturates on the (impossible) overflow
+ * instead of wrapping.  FRI_E_UNSUPPORTED for sample_bytes = 2 (residues need 18 bits).
  */
 int fri_encode_tq16(fri_plan *plan, const void *pixels, uint32_t n_frames, const int32_t *q, int16_t *coefs);
 int fri_decode_tq16(fri_plan *plan, const int16_t *coefs, uint32_t n_frames, const int32_t *q, int dequant_mode,

@@ -8,31 +8,31 @@ from frave_b200 import capi
 dev = torch.device("cuda", 0)
 
 
-def run(w, h, c, depth, sb, frames=1, reps=10, q=None):
+def run(w, h, c, depth, sb, frames=1, reps=10, q=None, half=False):
     plan = capi.Plan(w, h, c, depth=depth, sample_bytes=sb)
     tdt = torch.uint8 if sb == 1 else torch.int16
     px = torch.randint(0, 256 if sb == 1 else 32767, (frames, h, w, c), device=dev, dtype=torch.int32).to(tdt)
-    co = torch.empty((frames,) + plan.coef_shape, dtype=torch.int32, device=dev)
+    co = torch.empty((frames,) + plan.coef_shape, dtype=torch.int16 if half else torch.int32, device=dev)
     out = torch.empty_like(px)
     st = torch.cuda.current_stream().cuda_stream
     for _ in range(2):
-        plan.encode_device(px.data_ptr(), frames, co.data_ptr(), q, st)
-        plan.decode_device(co.data_ptr(), frames, out.data_ptr(), q, False, st)
+        plan.encode_device(px.data_ptr(), frames, co.data_ptr(), q, st, half)
+        plan.decode_device(co.data_ptr(), frames, out.data_ptr(), q, False, st, half)
     torch.cuda.synchronize()
     ok = torch.equal(px, out) if q is None else None
     e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     te = td = 0.0
     for _ in range(reps):
-        e[0].record(); plan.encode_device(px.data_ptr(), frames, co.data_ptr(), q, st)
-        e[1].record(); plan.decode_device(co.data_ptr(), frames, out.data_ptr(), q, False, st)
+        e[0].record(); plan.encode_device(px.data_ptr(), frames, co.data_ptr(), q, st, half)
+        e[1].record(); plan.decode_device(co.data_ptr(), frames, out.data_ptr(), q, False, st, half)
         e[2].record(); torch.cuda.synchronize()
         te += e[0].elapsed_time(e[1]); td += e[1].elapsed_time(e[2])
     te /= reps; td /= reps
     samples = w * h * c * frames
-    bps = sb + 4
+    bps = sb + (2 if half else 4)
     # coefficient traffic counts the blocks actually moved (deep trees include out-of-image base tiles)
-    moved = plan.coefs_per_frame * frames * 4 + samples * sb
-    print(json.dumps({"shape": f"{w}x{h}x{c}", "depth": depth, "sample_bytes": sb, "frames": frames, "tiles": plan.n_tiles,
+    moved = plan.coefs_per_frame * frames * (2 if half else 4) + samples * sb
+    print(json.dumps({"shape": f"{w}x{h}x{c}", "coefs": "i16" if half else "i32", "depth": depth, "sample_bytes": sb, "frames": frames, "tiles": plan.n_tiles,
                       "lossless": ok, "every_pixel_covered": plan.pixels_covered == w * h, "enc_us": round(te * 1e3, 1), "dec_us": round(td * 1e3, 1),
                       "enc_GBps_alg": round(samples * bps / te / 1e6), "dec_GBps_alg": round(samples * bps / td / 1e6),
                       "enc_GBps_moved": round(moved / te / 1e6), "dec_GBps_moved": round(moved / td / 1e6),
@@ -52,6 +52,8 @@ run(16384, 16384, 1, 9, 2, reps=5)
 for d in (16, 20, 24):
     run(16384, 16384, 1, d, 2, reps=3)
 run(3840, 2160, 3, 9, 1, frames=32, reps=5)
+run(3840, 2160, 3, 9, 1, frames=32, reps=5, half=True)
+run(4096, 4096, 3, 9, 1, reps=20, half=True)
 
 
 def run_emit(w, h, c, frames=1, reps=10, half=False):

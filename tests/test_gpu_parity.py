@@ -239,6 +239,48 @@ def test_more_frames_than_one_grid_dimension():
         assert torch.equal(px, out) or plan.pixels_covered < w * h
 
 
+@pytest.mark.parametrize("shape", [(37, 100, 3), (257, 1031, 3), (512, 512, 1), (1080, 1920, 3)], ids=lambda s: "x".join(map(str, s)))
+def test_int16_device_arrays(shape):
+    """fri_encode_tq_device16 / fri_decode_tq_device16: the kernels on int16 coefficient arrays (3 B per
+    sample) against the int32 kernels and the oracle, every quantization class, both dequantizers."""
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda", 0)
+    h, w, c = shape
+    frames = np.stack([uniform_image(h, w, c, seed=300 + i) for i in range(2)])
+    with capi.Plan(w, h, c) as plan:
+        some = some_of(plan)
+        px = torch.from_numpy(frames).to(dev)
+        c16 = torch.empty((2,) + plan.coef_shape, dtype=torch.int16, device=dev)
+        out = torch.empty_like(px)
+        for q in (None, smallest_layer_q(4), smallest_layer_q(7), random_q(h, hi=12)):
+            qq = ONES if q is None else q
+            c16.fill_(-3)
+            plan.encode_device(px.data_ptr(), 2, c16.data_ptr(), q, half=True)
+            assert plan.last_launches == 1
+            torch.cuda.synchronize()
+            got = c16.cpu().numpy()
+            for f in range(2):
+                want, _ = oracle_encode(plan, frames[f], qq)
+                assert np.array_equal(got[f], want)
+            plan.decode_device(c16.data_ptr(), 2, out.data_ptr(), q, half=True)
+            torch.cuda.synchronize()
+            for f in range(2):
+                assert np.array_equal(out[f].cpu().numpy(), oracle_decode(plan, got[f].astype(np.int32), some, qq))
+        rng = np.random.Generator(np.random.PCG64(w))
+        anyc = rng.integers(-32768, 32768, size=(2,) + plan.coef_shape, dtype=np.int16)
+        c16.copy_(torch.from_numpy(anyc))
+        q = random_q(h + 1, hi=6)
+        for mul in (False, True):
+            plan.decode_device(c16.data_ptr(), 2, out.data_ptr(), q, multiply=mul, half=True)
+            torch.cuda.synchronize()
+            for f in range(2):
+                assert np.array_equal(out[f].cpu().numpy(), oracle_decode(plan, anyc[f].astype(np.int32), some, q, multiply=mul))
+    with capi.Plan(64, 48, 1, depth=12) as deep:  # int16 arrays: depth 9 only
+        with pytest.raises(capi.FriError) as e:
+            deep.encode_device(px.data_ptr(), 1, c16.data_ptr(), half=True)
+        assert e.value.code == capi.FRI_E_UNSUPPORTED
+
+
 def test_16bit_transport_rejects_16bit_samples():
     with capi.Plan(64, 48, 1, sample_bytes=2) as plan:
         with pytest.raises(capi.FriError) as e:
