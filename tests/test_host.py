@@ -29,6 +29,26 @@ def test_library_exports_every_declared_symbol():
     assert "sm_100a" in capi.version()
 
 
+def test_header_is_valid_c_and_links(tmp_path):
+    """include/fri_cuda.h compiles as plain C99 and a C program linked against the library resolves every
+    prototype (tests/c_abi_check.c also exercises the host-only paths)."""
+    src = os.path.join(ROOT, "tests", "c_abi_check.c")
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "fri_cuda.h")).read(), flags=re.S)
+    declared = set(re.findall(r"\b(fri_[a-z0-9_]+)\s*\(", header))
+    used = set(re.findall(r"\(fn\)(fri_[a-z0-9_]+)", open(src).read()))
+    assert used == declared, declared ^ used
+    capi.lib()
+    libdir, libname = os.path.split(capi.lib_path())
+    exe = str(tmp_path / "c_abi_check")
+    cmd = ["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
+           "-L", libdir, "-l:" + libname, "-Wl,-rpath," + libdir]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    run = subprocess.run([exe], capture_output=True, text=True)
+    assert run.returncode == 0, (run.returncode, run.stdout, run.stderr)
+    assert "c abi ok" in run.stdout
+
+
 def test_kernels_are_compiled_for_sm_100a():
     out = subprocess.run(["cuobjdump", "-lelf", capi.lib_path()], capture_output=True, text=True)
     if out.returncode != 0:
