@@ -281,6 +281,51 @@ def test_int16_device_arrays(shape):
         assert e.value.code == capi.FRI_E_UNSUPPORTED
 
 
+def test_int16_and_emission_kernels_stay_inside_their_buffers():
+    """Guard bands around every output of the int16 / emission kernels stay untouched (the pool has no
+    compute-sanitizer): outputs are carved out of larger sentinel-filled allocations."""
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda", 0)
+    h, w, c, n = 131, 517, 3, 3
+    G = 4096  # guard elements on each side (keeps 16-byte alignment for every element size)
+
+    def guarded(numel, dtype, fill):
+        buf = torch.full((numel + 2 * G,), fill, dtype=dtype, device=dev)
+        return buf, buf[G:G + numel]
+
+    def intact(buf, fill):
+        return bool((buf[:G] == fill).all()) and bool((buf[-G:] == fill).all())
+
+    with capi.Plan(w, h, c) as plan:
+        px = torch.from_numpy(np.stack([uniform_image(h, w, c, seed=60 + i) for i in range(n)])).to(dev)
+        ncoef = n * plan.coefs_per_frame
+        cnt = plan.emission_count()
+        q = smallest_layer_q(3)
+        b16, c16 = guarded(ncoef, torch.int16, 0x5A5A)
+        plan.encode_device(px.data_ptr(), n, c16.data_ptr(), q, half=True)
+        bpx, opx = guarded(px.numel(), torch.uint8, 0xA5)
+        plan.decode_device(c16.data_ptr(), n, opx.data_ptr(), q, half=True)
+        b32, c32 = guarded(ncoef, torch.int32, 0x5A5A5A5A)
+        plan.encode_device(px.data_ptr(), n, c32.data_ptr(), q)
+        be, e32 = guarded(n * c * cnt, torch.int32, 0x11111111)
+        plan.emit_device(c32.data_ptr(), n, e32.data_ptr())
+        be16, e16 = guarded(n * c * cnt, torch.int16, 0x1111)
+        plan.emit_device(c32.data_ptr(), n, e16.data_ptr(), half=True)
+        bu, u32 = guarded(ncoef, torch.int32, 0x22222222)
+        plan.unemit_device(e32.data_ptr(), n, u32.data_ptr())
+        bu2, u32b = guarded(ncoef, torch.int32, 0x22222222)
+        plan.unemit_device(e16.data_ptr(), n, u32b.data_ptr(), half=True)
+        torch.cuda.synchronize()
+        assert intact(b16, 0x5A5A) and intact(bpx, 0xA5) and intact(b32, 0x5A5A5A5A)
+        assert intact(be, 0x11111111) and intact(be16, 0x1111) and intact(bu, 0x22222222) and intact(bu2, 0x22222222)
+        assert torch.equal(c16.to(torch.int32), c32) and torch.equal(e16.to(torch.int32), e32)
+        assert torch.equal(u32, c32) and torch.equal(u32b, c32)
+        want = torch.empty_like(px)
+        plan.decode_device(c32.data_ptr(), n, want.data_ptr(), q)
+        torch.cuda.synchronize()
+        assert torch.equal(opx.view(n, h, w, c), want)
+
+
 def test_16bit_transport_rejects_16bit_samples():
     with capi.Plan(64, 48, 1, sample_bytes=2) as plan:
         with pytest.raises(capi.FriError) as e:
