@@ -433,6 +433,61 @@ __device__ __forceinline__ void stage_group(const Geometry &g, const GroupDesc &
     }
 }
 
+// ---- bulk-copy (TMA, cp.async.bulk) staging of an interior group: one copy per staged row, issued by
+// one thread each and completed on an mbarrier, instead of ~1700 16-byte cp.async driven by the chunk
+// list.  Two barriers: rows holding pixels of every warp's first tile / the rest.
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "FRI_MBAR_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra FRI_MBAR_DONE;\n\t"
+        "bra FRI_MBAR_WAIT;\n"
+        "FRI_MBAR_DONE:\n\t}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+
+// Thread k < region_h issues the copy of staged row row_order[k] (the 16-byte-aligned cover of its owned
+// span) and arrives on bars[0] (first-round rows) or bars[1].
+__device__ __forceinline__ void stage_rows_bulk(const Geometry &g, const RegionView &rv, uint8_t *region, uint64_t *bars,
+                                                bool two_stage)
+{
+    const int k = threadIdx.x;
+    if (k >= g.region_h) return;
+    uint64_t *bar = bars + ((two_stage && k >= g.n_rows_first) ? 1 : 0);
+    const int r = g.row_order[k];
+    if (g.row_hi[r] == 0) {
+        mbar_arrive(bar);
+        return;
+    }
+    const int srow = r * g.pitch + rv.phi0;
+    const int s0 = (srow + g.row_lo[r]) & ~15, s1 = (srow + g.row_hi[r] + 15) & ~15;
+    mbar_arrive_expect(bar, (uint32_t)(s1 - s0));
+    bulk_g2s(region + s0, rv.gaddr(r, s0), (uint32_t)(s1 - s0), bar);
+}
+
 // Forward transform + quantization of the tiles of one staged group; warp w takes tiles
 // w, w + n_warps, ...  Per warp iteration: one base tile, all C channels.
 //   phase 1 (per channel): gather 16 leaves per lane, levels 8..6 in registers, quantize, store;
@@ -444,7 +499,7 @@ template <int C, typename S, bool DEEP, int QS, typename CT>
 __device__ __forceinline__ void encode_tiles(const Geometry &g, const QuantParams &qp, const GroupDesc &gd, const RegionView &rv,
                                              const uint32_t *__restrict__ tile_unit, int frame, const uint8_t *region,
                                              int32_t *scratch, CT *__restrict__ coefs, int32_t *__restrict__ dc_out,
-                                             bool two_stage)
+                                             bool two_stage, uint64_t *bars)
 {
     constexpr int SB = (int)sizeof(S);
     constexpr int PB = C * SB;
@@ -459,8 +514,12 @@ __device__ __forceinline__ void encode_tiles(const Geometry &g, const QuantParam
     const bool grp_live = (lane >> 3) < C;
     for (int e = warp; e < n_present; e += n_warps) {
         if (two_stage && e == warp + n_warps) {  // second round: the rest of the footprint must have landed
-            cp_async_wait_all();
-            __syncthreads();
+            if (bars) {
+                mbar_wait(bars + 1, 0);
+            } else {
+                cp_async_wait_all();
+                __syncthreads();
+            }
         }
         const int slot = sparse_group ? (int)__fns(gd.tile_mask, 0, e + 1) : e;
         const uint8_t *t0 = lane_base + g.tile_off[slot];
@@ -994,7 +1053,7 @@ __global__ void __launch_bounds__(kThreads, FRI_ENC_MINB)
 fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ QuantParams qp,
                   const GroupDesc *__restrict__ groups, const uint32_t *__restrict__ tile_unit,
                   const uint32_t *__restrict__ stage_list, const uint8_t *__restrict__ pixels,
-                  CT *__restrict__ coefs, int32_t *__restrict__ dc_out, int lookahead, int group_offset)
+                  CT *__restrict__ coefs, int32_t *__restrict__ dc_out, int lookahead, int group_offset, int bulk_staging)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *region = smem;
@@ -1010,14 +1069,28 @@ fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
     const int n_first = g.stage_first[rv.phi0], n_all = g.list_all[rv.phi0];
     // (full groups only: every warp then has a tile in both rounds and reaches the barrier between them)
     const bool two_stage = __popc(gd.tile_mask) == g.group_a * g.group_b && g.group_a * g.group_b == 2 * n_warps;
-    stage_group(g, gd, rv, stage_list, region, 0, two_stage ? n_first : n_all, pol);
-    cp_async_commit();
-    if (two_stage) {
-        stage_group(g, gd, rv, stage_list, region, n_first, n_all, pol);
-        cp_async_commit();
-        cp_async_wait_but_one();
+    // Interior groups are staged with one bulk copy (TMA) per row; groups that touch the image border
+    // keep the chunk-list path, which clips and zero-fills.
+    __shared__ __align__(8) uint64_t bars[2];
+    const bool bulk = bulk_staging && rv.interior && g.n_rows_first > 0 && g.region_h <= (int)blockDim.x;
+    if (bulk) {
+        if (threadIdx.x == 0) {
+            mbar_init(&bars[0], two_stage ? g.n_rows_first : g.region_h);
+            mbar_init(&bars[1], max(1, g.region_h - g.n_rows_first));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        stage_rows_bulk(g, rv, region, bars, two_stage);
     } else {
-        cp_async_wait_all();
+        stage_group(g, gd, rv, stage_list, region, 0, two_stage ? n_first : n_all, pol);
+        cp_async_commit();
+        if (two_stage) {
+            stage_group(g, gd, rv, stage_list, region, n_first, n_all, pol);
+            cp_async_commit();
+            cp_async_wait_but_one();
+        } else {
+            cp_async_wait_all();
+        }
     }
     // Look-ahead: while this group's copies are in flight, pull the pixel rows of the group that
     // will run in this CTA slot one residency later towards L2, one 128-byte line per thread and
@@ -1039,9 +1112,11 @@ fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
             }
         }
     }
-    __syncthreads();
+    if (bulk) mbar_wait(&bars[0], 0);
+    else __syncthreads();
     FRI_TRACE_MARK(1);
-    encode_tiles<C, S, DEEP, QS, CT>(g, qp, gd, rv, tile_unit, frame, region, scratch, coefs, dc_out, two_stage);
+    encode_tiles<C, S, DEEP, QS, CT>(g, qp, gd, rv, tile_unit, frame, region, scratch, coefs, dc_out, two_stage,
+                                     bulk ? bars : nullptr);
 #if FRI_TRACE
     __syncthreads();
 #endif
@@ -1291,6 +1366,9 @@ cudaError_t configure_kernels()
 
 namespace {
 
+// Launches of at least this many waves of CTAs stage interior groups with bulk copies (see launch_encode).
+constexpr int kBulkStagingWaves = 6;
+
 // CTAs of the main kernels resident on the device at once.
 int resident_ctas(const Geometry &g)
 {
@@ -1325,6 +1403,9 @@ cudaError_t launch_encode(const Geometry &g, const DeviceTables &t, const QuantP
     int lookahead = resident_ctas(g);  // prefetch distance: the group that will reuse this CTA's slot
     if (const char *env = std::getenv("FRI_LOOKAHEAD")) lookahead = std::atoi(env);  // tuning knob
     if (!whole) lookahead = 0;  // banded host pipeline: rows of later groups may not be on the device yet
+    // Bulk-copy (TMA) staging of interior groups: tuning knob FRI_STAGE_BULK = 0 / 1, default by launch size
+    int bulk_staging = (int64_t)n_frames * n_groups >= (int64_t)kBulkStagingWaves * resident_ctas(g);
+    if (const char *env = std::getenv("FRI_STAGE_BULK")) bulk_staging = std::atoi(env) != 0;
     const uint8_t *px = static_cast<const uint8_t *>(d_pixels);
     for (uint32_t f0 = 0; f0 < n_frames; f0 += 65535u) {  // gridDim.y limit
         const uint32_t nf = n_frames - f0 < 65535u ? n_frames - f0 : 65535u;
@@ -1334,7 +1415,7 @@ cudaError_t launch_encode(const Geometry &g, const DeviceTables &t, const QuantP
         int16_t *c16 = d_coefs16 + (int64_t)f0 * g.coefs_per_frame;
         int32_t *dc = d_dc ? d_dc + (((int64_t)f0 * g.n_fractals * g.channels) << g.sub_bits) : nullptr;
 #define FRI_LAUNCH_Q(CC, SS, DD, QQ, TT, PTR) \
-    fri_encode_kernel<CC, SS, DD, QQ, TT><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.stage_list, p, PTR, dc, lookahead, group_begin)
+    fri_encode_kernel<CC, SS, DD, QQ, TT><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.stage_list, p, PTR, dc, lookahead, group_begin, bulk_staging)
 #define FRI_LAUNCH(CC, SS, TT, PTR)                                                           \
         do {                                                                                  \
             if (qclass == kQuantNone) FRI_LAUNCH_Q(CC, SS, false, kQuantNone, TT, PTR);       \

@@ -308,6 +308,30 @@ std::string build_plan(Plan &plan, uint32_t width, uint32_t height, uint32_t cha
             own_first[(size_t)y * g.own_words + (x >> 5)] |= 1u << (x & 31);
         }
 
+    // Row spans for the encoder's bulk-copy staging of interior groups.
+    g.n_rows_first = 0;
+    if (g.region_h <= kMaxRegionRows && g.row_bytes < 65536) {
+        std::vector<int> first_rows, rest_rows;
+        for (int r = 0; r < g.region_h; ++r) {
+            int lo = -1, hi = -1;
+            bool in_first = false;
+            for (int x = 0; x < g.region_w; ++x) {
+                if ((plan.ownership[(size_t)r * g.own_words + (x >> 5)] >> (x & 31)) & 1u) {
+                    if (lo < 0) lo = x;
+                    hi = x;
+                }
+                in_first |= (own_first[(size_t)r * g.own_words + (x >> 5)] >> (x & 31)) & 1u;
+            }
+            g.row_lo[r] = (uint16_t)(lo < 0 ? 0 : lo * csz);
+            g.row_hi[r] = (uint16_t)(lo < 0 ? 0 : (hi + 1) * csz);
+            (in_first ? first_rows : rest_rows).push_back(r);
+        }
+        g.n_rows_first = (int32_t)first_rows.size();
+        int k = 0;
+        for (int r : first_rows) g.row_order[k++] = (uint8_t)r;
+        for (int r : rest_rows) g.row_order[k++] = (uint8_t)r;
+    }
+
     // Chunk lists.  Shared-memory byte r*pitch + phase + b holds region byte (r, b); chunks are
     // the 16-byte aligned pieces of shared memory (== aligned pieces of global memory).
     std::vector<std::vector<std::pair<uint32_t, uint16_t>>> lists(16);

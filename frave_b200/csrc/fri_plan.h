@@ -12,6 +12,7 @@
 
 namespace fri {
 
+constexpr int kMaxRegionRows = 128;  // staged rows covered by the row-span tables
 constexpr int kMaxGroupTiles = 32;  // tiles per CTA group (bits of GroupDesc::tile_mask)
 
 // One CTA's worth of work: up to A x B lattice-adjacent base tiles whose pixels are staged
@@ -50,6 +51,13 @@ struct Geometry {
     int32_t list_full[16];               // per phase: fully owned 16-byte chunks (listed first)
     int32_t list_all[16];                // per phase: all chunks that hold at least one owned byte
     int32_t stage_first[16];             // per phase: leading stage_list entries needed by the first tile of every warp
+    // Row spans of a full group's footprint, for the encoder's bulk-copy staging of interior groups (one
+    // cp.async.bulk per staged row): owned bytes of region row r lie in [row_lo[r], row_hi[r]) (holes
+    // inside a span belong to neighbouring groups and are fetched along); row_order lists the rows that
+    // hold pixels of every warp's first tile first (n_rows_first of them).  n_rows_first == 0: not available.
+    int32_t n_rows_first;
+    uint16_t row_lo[kMaxRegionRows], row_hi[kMaxRegionRows];
+    uint8_t row_order[kMaxRegionRows];
 };
 
 struct Plan {

@@ -54,6 +54,27 @@ def test_encode_bit_exact(shape, dtype):
         assert plan.last_launches == 1
 
 
+@pytest.mark.parametrize("bulk", ["0", "1"])
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16], ids=["u8", "u16"])
+@pytest.mark.parametrize("shape", [(131, 77, 3), (512, 512, 1), (257, 1031, 3), (700, 900, 3), (1080, 1920, 3)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_encoder_staging_paths_are_bit_exact(monkeypatch, shape, dtype, bulk):
+    """The encoder stages interior groups either with 16-byte cp.async driven by the chunk list or with one
+    bulk copy (TMA) per row, chosen by launch size; FRI_STAGE_BULK forces either on every shape."""
+    monkeypatch.setenv("FRI_STAGE_BULK", bulk)
+    h, w, c = shape
+    frames = np.stack([uniform_image(h, w, c, seed=h + i, dtype=dtype) for i in range(2)])
+    with capi.Plan(w, h, c, sample_bytes=frames.itemsize) as plan:
+        for q in (None, smallest_layer_q(6), random_q(w, hi=20)):
+            got = plan.encode(frames, q)
+            for f in range(2):
+                want, _ = oracle_encode(plan, frames[f], ONES if q is None else q)
+                assert np.array_equal(got[f], want)
+        if frames.itemsize == 1:
+            got16 = plan.encode(frames, smallest_layer_q(6), dtype=np.int16)
+            assert np.array_equal(got16[1], oracle_encode(plan, frames[1], smallest_layer_q(6))[0])
+
+
 @pytest.mark.parametrize("dtype", [np.uint8, np.uint16], ids=["u8", "u16"])
 @pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
 def test_decode_bit_exact(shape, dtype):
