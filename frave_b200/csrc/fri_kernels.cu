@@ -1074,13 +1074,18 @@ fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
     __shared__ __align__(8) uint64_t bars[2];
     const bool bulk = bulk_staging && rv.interior && g.n_rows_first > 0 && g.region_h <= (int)blockDim.x;
     if (bulk) {
-        if (threadIdx.x == 0) {
-            mbar_init(&bars[0], two_stage ? g.n_rows_first : g.region_h);
-            mbar_init(&bars[1], max(1, g.region_h - g.n_rows_first));
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // only the warps that issue copies (thread r copies row r) wait for the barrier initialisation; the
+        // others go straight on to the look-ahead and meet them at the CTA barrier before the wait
+        const int issuing = (g.region_h + 31) & ~31;
+        if ((int)threadIdx.x < issuing) {
+            if (threadIdx.x == 0) {
+                mbar_init(&bars[0], two_stage ? g.n_rows_first : g.region_h);
+                mbar_init(&bars[1], max(1, g.region_h - g.n_rows_first));
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            asm volatile("bar.sync 1, %0;" ::"r"(issuing) : "memory");
+            stage_rows_bulk(g, rv, region, bars, two_stage);
         }
-        __syncthreads();
-        stage_rows_bulk(g, rv, region, bars, two_stage);
     } else {
         stage_group(g, gd, rv, stage_list, region, 0, two_stage ? n_first : n_all, pol);
         cp_async_commit();
@@ -1112,8 +1117,8 @@ fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
             }
         }
     }
+    __syncthreads();
     if (bulk) mbar_wait(&bars[0], 0);
-    else __syncthreads();
     FRI_TRACE_MARK(1);
     encode_tiles<C, S, DEEP, QS, CT>(g, qp, gd, rv, tile_unit, frame, region, scratch, coefs, dc_out, two_stage,
                                      bulk ? bars : nullptr);
@@ -1366,9 +1371,6 @@ cudaError_t configure_kernels()
 
 namespace {
 
-// Launches of at least this many waves of CTAs stage interior groups with bulk copies (see launch_encode).
-constexpr int kBulkStagingWaves = 6;
-
 // CTAs of the main kernels resident on the device at once.
 int resident_ctas(const Geometry &g)
 {
@@ -1403,9 +1405,9 @@ cudaError_t launch_encode(const Geometry &g, const DeviceTables &t, const QuantP
     int lookahead = resident_ctas(g);  // prefetch distance: the group that will reuse this CTA's slot
     if (const char *env = std::getenv("FRI_LOOKAHEAD")) lookahead = std::atoi(env);  // tuning knob
     if (!whole) lookahead = 0;  // banded host pipeline: rows of later groups may not be on the device yet
-    // Bulk-copy (TMA) staging of interior groups: tuning knob FRI_STAGE_BULK = 0 / 1, default by launch size
-    int bulk_staging = (int64_t)n_frames * n_groups >= (int64_t)kBulkStagingWaves * resident_ctas(g);
-    if (const char *env = std::getenv("FRI_STAGE_BULK")) bulk_staging = std::atoi(env) != 0;
+    // Bulk-copy (TMA) staging of interior groups; FRI_STAGE_BULK=0 falls back to the chunk-list cp.async path
+    int bulk_staging = 1;
+    if (const char *env = std::getenv("FRI_STAGE_BULK")) bulk_staging = std::atoi(env) != 0;  // tuning knob
     const uint8_t *px = static_cast<const uint8_t *>(d_pixels);
     for (uint32_t f0 = 0; f0 < n_frames; f0 += 65535u) {  // gridDim.y limit
         const uint32_t nf = n_frames - f0 < 65535u ? n_frames - f0 : 65535u;
