@@ -342,7 +342,7 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
     h2d = d2h = 0
     for cdt, tag in ((np.int32, "i32"), (np.int16, "i16")):
         if args.no_e2e:
-            e2e.update({"serial_" + tag: float("inf"), "duplex_" + tag: float("inf")})
+            e2e.update({"serial_" + tag: float("inf"), "duplex_" + tag: float("inf"), "async_" + tag: float("inf")})
             continue
         cf_enc = capi.PinnedBuffer((1,) + plan.coef_shape, cdt)
         cf_dec = capi.PinnedBuffer((1,) + plan.coef_shape, cdt)
@@ -387,6 +387,20 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
         e2e["duplex_" + tag] = time.perf_counter() - t0
         if errors:
             raise errors[0]
+        # the same overlap from ONE host thread: asynchronous mode, both handles enqueued, then both synced
+        plan.set_async(True)
+        dplan.set_async(True)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            plan.encode(px_h.array, q, out=cf_enc.array)
+            dplan.decode(cf_dec.array, q, out=out_h.array)
+            plan.sync()
+            dplan.sync()
+        e2e["async_" + tag] = time.perf_counter() - t0
+        plan.set_async(False)
+        dplan.set_async(False)
         plan.set_bands(0)
         dplan.set_bands(0)
         h2d = px_h.array.nbytes + cf_dec.array.nbytes
@@ -434,6 +448,7 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
                            "encoder thread and decoder thread with one plan handle each, one band per frame (fri_plan_set_bands(1))",
                     "variants_mpix_s": {k: W * H * world * e2e_steps / v / 1e6 for k, v in e2e.items()},
                     "variants": "serial = one thread, encode then decode; duplex = encoder and decoder threads; "
+                                "async = one thread, both handles in asynchronous mode (fri_plan_set_async / fri_plan_sync); "
                                 "i32 = fri_*_tq (4 B coefficients over PCIe: 255 MB each way per step), "
                                 "i16 = fri_*_tq16 (151 MB each way)"},
             "gpu_launches": timed_launches, "clocks": clocks, "launch": plan.launch_info(),

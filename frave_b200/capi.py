@@ -58,6 +58,8 @@ _SYMBOLS = [
     ("fri_host_free", None, [_P]),
     ("fri_plan_last_launches", C.c_uint32, [_P]),
     ("fri_plan_set_bands", C.c_int, [_P, C.c_int]),
+    ("fri_plan_set_async", C.c_int, [_P, C.c_int]),
+    ("fri_plan_sync", C.c_int, [_P]),
     ("fri_quant_divide", C.c_int32, [C.c_int32, C.c_int32]),
     ("fri_quant_divide_small", C.c_int32, [C.c_int32, C.c_int32]),
     ("fri_quant_divide_magic", C.c_int32, [C.c_int32, C.c_int32]),
@@ -213,6 +215,13 @@ class Plan:
     def set_bands(self, bands: int) -> None:
         """Bands per frame of the host-buffer entry points (0 = automatic; 1 for concurrent callers)."""
         _check(lib().fri_plan_set_bands(self._h, int(bands)))
+
+    def set_async(self, on: bool) -> None:
+        """Host-buffer calls return after enqueueing (pinned buffers only); sync() waits for them."""
+        _check(lib().fri_plan_set_async(self._h, 1 if on else 0))
+
+    def sync(self) -> None:
+        _check(lib().fri_plan_sync(self._h))
 
     @property
     def last_launches(self) -> int:

@@ -79,6 +79,7 @@ struct fri_plan {
     size_t d_dc_frames = 0;
     uint32_t last_launches = 0;
     int bands = 0;  // fri_plan_set_bands: 0 = automatic
+    bool async_mode = false;  // fri_plan_set_async
     // emission order (computed on first use)
     int emit_state = 0;  // 0 = not computed, 1 = ready, -1 = failed (emit_error)
     std::string emit_error;
@@ -148,6 +149,18 @@ int ensure_slots(fri_plan *p)
         FRI_CUDA(cudaEventCreateWithFlags(&s.out_done, cudaEventDisableTiming));
     }
     p->slots_ready = true;
+    return FRI_OK;
+}
+
+// End of a host-buffer entry point: wait for the plan's three streams, unless the plan is in
+// asynchronous mode (fri_plan_set_async), where the caller does that with fri_plan_sync.
+int finish_host_call(fri_plan *p)
+{
+    if (p->async_mode) return FRI_OK;
+    Pipeline &pl = p->pipe;
+    FRI_CUDA(cudaStreamSynchronize(pl.out));
+    FRI_CUDA(cudaStreamSynchronize(pl.compute));
+    FRI_CUDA(cudaStreamSynchronize(pl.in));
     return FRI_OK;
 }
 
@@ -487,10 +500,7 @@ static int encode_host(fri_plan *p, const void *pixels, uint32_t n_frames, const
         FRI_CUDA(cudaEventRecord(s.out_done, pl.out));
         s.used = true;
     }
-    FRI_CUDA(cudaStreamSynchronize(pl.out));
-    FRI_CUDA(cudaStreamSynchronize(pl.compute));
-    FRI_CUDA(cudaStreamSynchronize(pl.in));
-    return FRI_OK;
+    return finish_host_call(p);
 }
 
 int fri_encode_tq(fri_plan *p, const void *pixels, uint32_t n_frames, const int32_t *q, int32_t *coefs)
@@ -559,10 +569,7 @@ static int decode_host(fri_plan *p, const void *coefs, uint32_t n_frames, const 
         FRI_CUDA(cudaEventRecord(s.out_done, pl.out));
         s.used = true;
     }
-    FRI_CUDA(cudaStreamSynchronize(pl.out));
-    FRI_CUDA(cudaStreamSynchronize(pl.compute));
-    FRI_CUDA(cudaStreamSynchronize(pl.in));
-    return FRI_OK;
+    return finish_host_call(p);
 }
 
 int fri_decode_tq(fri_plan *p, const int32_t *coefs, uint32_t n_frames, const int32_t *q, int dequant_mode, void *pixels)
@@ -745,10 +752,7 @@ static int encode_emit_host(fri_plan *p, const void *pixels, uint32_t n_frames, 
         FRI_CUDA(cudaEventRecord(s.out_done, pl.out));
         s.used = true;
     }
-    FRI_CUDA(cudaStreamSynchronize(pl.out));
-    FRI_CUDA(cudaStreamSynchronize(pl.compute));
-    FRI_CUDA(cudaStreamSynchronize(pl.in));
-    return FRI_OK;
+    return finish_host_call(p);
 }
 
 int fri_encode_tq_emit(fri_plan *p, const void *pixels, uint32_t n_frames, const int32_t *q, int32_t *out)
@@ -836,10 +840,7 @@ static int decode_emit_host(fri_plan *p, const void *streams, bool half, uint32_
         FRI_CUDA(cudaEventRecord(s.out_done, pl.out));
         s.used = true;
     }
-    FRI_CUDA(cudaStreamSynchronize(pl.out));
-    FRI_CUDA(cudaStreamSynchronize(pl.compute));
-    FRI_CUDA(cudaStreamSynchronize(pl.in));
-    return FRI_OK;
+    return finish_host_call(p);
 }
 
 int fri_decode_tq_emit(fri_plan *p, const int32_t *streams, uint32_t n_frames, const int32_t *q, int dequant_mode, void *pixels)
@@ -866,6 +867,25 @@ void fri_host_free(void *p)
 }
 
 uint32_t fri_plan_last_launches(const fri_plan *p) { return p ? p->last_launches : 0; }
+
+int fri_plan_set_async(fri_plan *p, int on)
+{
+    if (!p) return fail(FRI_E_INVALID, "plan is NULL");
+    p->async_mode = on != 0;
+    return FRI_OK;
+}
+
+int fri_plan_sync(fri_plan *p)
+{
+    int rc = enter_device(p);
+    if (rc) return rc;
+    if (!p->slots_ready) return FRI_OK;  // nothing was ever enqueued
+    Pipeline &pl = p->pipe;
+    FRI_CUDA(cudaStreamSynchronize(pl.out));
+    FRI_CUDA(cudaStreamSynchronize(pl.compute));
+    FRI_CUDA(cudaStreamSynchronize(pl.in));
+    return FRI_OK;
+}
 
 int fri_plan_set_bands(fri_plan *p, int bands)
 {

@@ -191,6 +191,18 @@ int fri_decode_tq_emit16(fri_plan *plan, const int16_t *streams, uint32_t n_fram
  */
 int fri_plan_set_bands(fri_plan *plan, int bands);
 
+/*
+ * Asynchronous mode of the host-buffer entry points ("async variants enqueue on
+ * the handle's stream and expose sync()"): with fri_plan_set_async(plan, 1) the fri_encode_tq* /
+ * fri_decode_tq* / *_emit* calls return once their copies and kernels are enqueued on the plan's
+ * streams, and fri_plan_sync(plan) waits for them.  The host buffers must be pinned (fri_host_alloc)
+ * and stay untouched until the sync.  One host thread can this way keep an encoder handle and a
+ * decoder handle busy at once — the same full-duplex overlap two threads get.  Errors of the
+ * enqueued work surface at the sync (or at the next call).
+ */
+int fri_plan_set_async(fri_plan *plan, int on);
+int fri_plan_sync(fri_plan *plan);
+
 /* Pinned host memory (cudaHostAlloc) for the host-buffer entry points. */
 int fri_host_alloc(void **out, size_t bytes);
 void fri_host_free(void *p);

@@ -23,6 +23,8 @@ extern "C" {
     fn fri_decode_tq(plan: *mut FriPlan, coefs: *const i32, n_frames: u32, q: *const i32, dequant_mode: c_int,
                      pixels: *mut c_void) -> c_int;
     fn fri_plan_set_bands(plan: *mut FriPlan, bands: c_int) -> c_int;
+    fn fri_plan_set_async(plan: *mut FriPlan, on: c_int) -> c_int;
+    fn fri_plan_sync(plan: *mut FriPlan) -> c_int;
     // 16-bit transport of the same two calls (8-bit samples): half the bytes over PCIe
     fn fri_encode_tq16(plan: *mut FriPlan, pixels: *const c_void, n_frames: u32, q: *const i32, coefs: *mut i16) -> c_int;
     fn fri_decode_tq16(plan: *mut FriPlan, coefs: *const i16, n_frames: u32, q: *const i32, dequant_mode: c_int,
@@ -75,6 +77,10 @@ impl Plan {
     /// Bands per frame of the host-buffer calls: 0 = automatic (single caller), 1 when an encoder and a
     /// decoder thread drive one handle each.
     pub fn set_bands(&mut self, bands: i32) -> Result<(), String> { check(unsafe { fri_plan_set_bands(self.0, bands) }) }
+    /// Asynchronous mode: encode_tq* / decode_tq* return once enqueued (the slices passed must then be
+    /// pinned memory from fri_host_alloc and must outlive the next `sync`).
+    pub fn set_async(&mut self, on: bool) -> Result<(), String> { check(unsafe { fri_plan_set_async(self.0, on as c_int) }) }
+    pub fn sync(&mut self) -> Result<(), String> { check(unsafe { fri_plan_sync(self.0) }) }
     /// encode_tq with int16 coefficients on the host side (every coefficient of an 8-bit image fits:
     /// |residue| <= 255, wavelet_transform.rs:211-218); widen while applying the mask.
     pub fn encode_tq16(&mut self, pixels: &[u8], q: &[i32; 32]) -> Result<Vec<i16>, String> {

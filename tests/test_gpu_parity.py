@@ -234,6 +234,37 @@ def test_encoder_and_decoder_threads_with_one_handle_each():
         assert not errors, errors
 
 
+def test_asynchronous_mode_of_the_host_entry_points():
+    """fri_plan_set_async / fri_plan_sync: calls return after enqueueing on pinned buffers; one thread
+    drives an encoder and a decoder handle at once and gets the oracle's bytes after the sync."""
+    h, w, c = 540, 960, 3
+    q = smallest_layer_q(4)
+    with capi.Plan(w, h, c) as eplan, capi.Plan(w, h, c) as dplan:
+        some = some_of(eplan)
+        px = capi.PinnedBuffer((1, h, w, c), np.uint8)
+        cf = capi.PinnedBuffer((1,) + eplan.coef_shape, np.int16)
+        cf_in = capi.PinnedBuffer((1,) + eplan.coef_shape, np.int16)
+        out = capi.PinnedBuffer((1, h, w, c), np.uint8)
+        eplan.set_async(True)
+        dplan.set_async(True)
+        eplan.sync()  # nothing enqueued yet: a no-op
+        for it in range(4):
+            img = uniform_image(h, w, c, seed=800 + it)
+            other = oracle_encode(eplan, uniform_image(h, w, c, seed=900 + it), q)[0]
+            px.array[0] = img
+            cf_in.array[0] = other
+            eplan.encode(px.array, q, out=cf.array)
+            dplan.decode(cf_in.array, q, out=out.array)
+            eplan.sync()
+            dplan.sync()
+            assert np.array_equal(cf.array[0], oracle_encode(eplan, img, q)[0])
+            assert np.array_equal(out.array[0], oracle_decode(dplan, other, some, q))
+        eplan.set_async(False)
+        assert np.array_equal(eplan.encode(px.array, q)[0], cf.array[0])  # back to synchronous calls
+        for b in (px, cf, cf_in, out):
+            b.free()
+
+
 def test_more_frames_than_one_grid_dimension():
     """n_frames above the 65535 gridDim.y limit is split over several launches."""
     torch = pytest.importorskip("torch")
