@@ -234,6 +234,53 @@ def test_encoder_and_decoder_threads_with_one_handle_each():
         assert not errors, errors
 
 
+@pytest.mark.parametrize("seed", [20261018, 7, 424242])
+def test_random_shapes_fuzz(seed):
+    """Seeded fuzz over image shapes, channel counts, sample sizes, frame counts and quantization matrices
+    (all three quantization classes): encode and decode bit for bit against the oracle, the 16-bit
+    transport and — where the reference's scan exists — the emitted streams against the block path."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    checked_emit = 0
+    for case in range(36):
+        h = int(rng.integers(1, 420)) if case % 3 else int(rng.integers(1, 40))
+        w = int(rng.integers(1, 640)) if case % 4 else int(rng.integers(1, 40))
+        c = int(rng.choice([1, 3]))
+        dtype = np.uint16 if case % 5 == 4 else np.uint8
+        n = int(rng.integers(1, 4))
+        frames = np.stack([uniform_image(h, w, c, seed=seed % 1000 + 5000 + 10 * case + i, dtype=dtype) for i in range(n)])
+        kind = case % 3
+        q = None if kind == 0 else smallest_layer_q(int(rng.integers(2, 65))) if kind == 1 else random_q(case, hi=int(rng.integers(2, 300)))
+        qq = ONES if q is None else q
+        tag = f"case {case}: {h}x{w}x{c} {np.dtype(dtype).name} n={n} kind={kind}"
+        with capi.Plan(w, h, c, sample_bytes=frames.itemsize) as plan:
+            some = some_of(plan)
+            got = plan.encode(frames, q)
+            rec = plan.decode(got, q, multiply=bool(case & 1))
+            for f in range(n):
+                want, _ = oracle_encode(plan, frames[f], qq)
+                assert np.array_equal(got[f], want), tag
+                assert np.array_equal(rec[f], oracle_decode(plan, want, some, qq, multiply=bool(case & 1))), tag
+            if dtype == np.uint8:
+                g16 = plan.encode(frames, q, dtype=np.int16)
+                assert np.array_equal(g16, got), tag
+                assert np.array_equal(plan.decode(g16, q, multiply=bool(case & 1)), rec), tag
+                try:
+                    cnt = plan.emission_count()
+                except capi.FriError as e:  # sizes on which the reference's own scan asserts
+                    assert e.code == capi.FRI_E_UNSUPPORTED, tag
+                    continue
+                order = plan.emission_order().astype(np.int64)
+                src = order[plan.masks().reshape(-1)[order]]
+                assert len(src) == cnt, tag
+                streams = plan.encode_emit(frames, q)
+                for f in range(n):
+                    for ch in range(c):
+                        assert np.array_equal(streams[f, ch], got[f][:, ch, :].reshape(-1)[src]), tag
+                assert np.array_equal(plan.decode_emit(streams.astype(np.int16), q, multiply=bool(case & 1)), rec), tag
+                checked_emit += 1
+    assert checked_emit >= 10
+
+
 def test_asynchronous_mode_of_the_host_entry_points():
     """fri_plan_set_async / fri_plan_sync: calls return after enqueueing on pinned buffers; one thread
     drives an encoder and a decoder handle at once and gets the oracle's bytes after the sync."""
