@@ -1275,7 +1275,19 @@ fri_unemit_kernel(const GroupDesc *__restrict__ groups, const uint32_t *__restri
             __syncthreads();
         }
         const T *src = in + ((size_t)frame * channels + ch) * count;
-        for (uint32_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) es[__ldg(loc + k)] = (int32_t)__ldcs(src + __ldg(dst + k));
+        uint32_t k = k0 + threadIdx.x;
+        for (; k + 3 * blockDim.x < k1; k += 4 * blockDim.x) {  // four independent gathers in flight per thread
+            uint32_t l[4];
+            int32_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                l[u] = __ldg(loc + k + u * blockDim.x);
+                v[u] = (int32_t)__ldcs(src + __ldg(dst + k + u * blockDim.x));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) es[l[u]] = v[u];
+        }
+        for (; k < k1; k += blockDim.x) es[__ldg(loc + k)] = (int32_t)__ldcs(src + __ldg(dst + k));
         __syncthreads();
         for (int idx = threadIdx.x; idx < n_present * (kTileLeaves / 4); idx += blockDim.x) {
             const int t = idx >> 7, v = idx & 127;
