@@ -885,7 +885,7 @@ __device__ __forceinline__ void decode_tiles(const Geometry &g, const QuantParam
 
             // scatter into the staged region (clamp: images.rs:109)
             const uint32_t p0 = t0 + ch * SB, p1 = p0 + g.pitch, p2 = p1 + g.pitch;
-#define FRI_ST(ptr, dx, val) store_clamped<S>((ptr) + (dx) * PB, (val))
+#define FRI_ST(ptr, dx, val) store_clamped<S>((uint32_t)((int)(ptr) + (dx) * PB), (val))
             FRI_ST(p0, 0, v[0]);  FRI_ST(p1, 0, v[1]);
             FRI_ST(p1, -1, v[2]); FRI_ST(p2, -1, v[3]);
             FRI_ST(p0, 2, v[4]);  FRI_ST(p1, 2, v[5]);
