@@ -71,6 +71,7 @@ struct fri_plan {
     Plan plan;
     int device = -1;
     DeviceTables tables;
+    void *d_groups_launch = nullptr;
     void *d_groups = nullptr, *d_tile_unit = nullptr, *d_chunk_mask = nullptr, *d_chunk_list = nullptr, *d_stage_list = nullptr;
     Slot slots[kSlots];
     Pipeline pipe;
@@ -280,6 +281,21 @@ int fri_plan_create(fri_plan **out, int device, uint32_t width, uint32_t height,
             e = configure_kernels();
         }
         if (e == cudaSuccess) e = upload(&p->d_groups, pl.groups.data(), pl.groups.size() * sizeof(GroupDesc));
+        // Launch order of whole-frame launches: groups whose staged region crosses the image border take the
+        // clipping paths (slower staging and write-out) and, in plan order, the bottom border row would be
+        // the last CTAs of the launch — they go first instead (FRI_ORDER=0 keeps plan order).
+        int order = 1;
+        if (const char *env = std::getenv("FRI_ORDER")) order = std::atoi(env);  // tuning knob
+        if (e == cudaSuccess && order != 0) {
+            std::vector<GroupDesc> lo(pl.groups);
+            const Geometry &gg = pl.geo;
+            auto border = [&](const GroupDesc &d) {
+                return !(d.x0 >= 0 && d.y0 >= 0 && d.x0 + gg.region_w <= gg.width && d.y0 + gg.region_h <= gg.height);
+            };
+            if (order == 1) std::stable_partition(lo.begin(), lo.end(), border);
+            else std::stable_partition(lo.begin(), lo.end(), [&](const GroupDesc &d) { return !border(d); });
+            e = upload(&p->d_groups_launch, lo.data(), lo.size() * sizeof(GroupDesc));
+        }
         if (e == cudaSuccess && pl.geo.sub_bits > 0)
             e = upload(&p->d_tile_unit, pl.tile_unit.data(), pl.tile_unit.size() * sizeof(uint32_t));
         if (e == cudaSuccess) e = upload(&p->d_chunk_mask, pl.chunk_mask.data(), pl.chunk_mask.size() * sizeof(uint16_t));
@@ -290,6 +306,7 @@ int fri_plan_create(fri_plan **out, int device, uint32_t width, uint32_t height,
             return cuda_fail(e, "uploading the plan tables");
         }
         p->tables.groups = static_cast<const GroupDesc *>(p->d_groups);
+        p->tables.groups_launch = static_cast<const GroupDesc *>(p->d_groups_launch);
         p->tables.tile_unit = static_cast<const uint32_t *>(p->d_tile_unit);
         p->tables.chunk_mask = static_cast<const uint16_t *>(p->d_chunk_mask);
         p->tables.chunk_list = static_cast<const uint32_t *>(p->d_chunk_list);
@@ -320,6 +337,7 @@ void fri_plan_destroy(fri_plan *p)
         }
         if (p->d_dc_shared) cudaFree(p->d_dc_shared);
         if (p->d_groups) cudaFree(p->d_groups);
+        if (p->d_groups_launch) cudaFree(p->d_groups_launch);
         if (p->d_tile_unit) cudaFree(p->d_tile_unit);
         if (p->d_chunk_mask) cudaFree(p->d_chunk_mask);
         if (p->d_chunk_list) cudaFree(p->d_chunk_list);

@@ -1420,6 +1420,7 @@ cudaError_t launch_encode(const Geometry &g, const DeviceTables &t, const QuantP
     // Bulk-copy (TMA) staging of interior groups; FRI_STAGE_BULK=0 falls back to the chunk-list cp.async path
     int bulk_staging = 1;
     if (const char *env = std::getenv("FRI_STAGE_BULK")) bulk_staging = std::atoi(env) != 0;  // tuning knob
+    const GroupDesc *gtab = whole && t.groups_launch ? t.groups_launch : t.groups;  // launch order (whole frames only)
     const uint8_t *px = static_cast<const uint8_t *>(d_pixels);
     for (uint32_t f0 = 0; f0 < n_frames; f0 += 65535u) {  // gridDim.y limit
         const uint32_t nf = n_frames - f0 < 65535u ? n_frames - f0 : 65535u;
@@ -1429,7 +1430,7 @@ cudaError_t launch_encode(const Geometry &g, const DeviceTables &t, const QuantP
         int16_t *c16 = d_coefs16 + (int64_t)f0 * g.coefs_per_frame;
         int32_t *dc = d_dc ? d_dc + (((int64_t)f0 * g.n_fractals * g.channels) << g.sub_bits) : nullptr;
 #define FRI_LAUNCH_Q(CC, SS, DD, QQ, TT, PTR) \
-    fri_encode_kernel<CC, SS, DD, QQ, TT><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.stage_list, p, PTR, dc, lookahead, group_begin, bulk_staging)
+    fri_encode_kernel<CC, SS, DD, QQ, TT><<<grid, cta_threads(g), smem, stream>>>(g, qp, gtab, t.tile_unit, t.stage_list, p, PTR, dc, lookahead, group_begin, bulk_staging)
 #define FRI_LAUNCH(CC, SS, TT, PTR)                                                           \
         do {                                                                                  \
             if (qclass == kQuantNone) FRI_LAUNCH_Q(CC, SS, false, kQuantNone, TT, PTR);       \
@@ -1479,6 +1480,7 @@ cudaError_t launch_decode(const Geometry &g, const DeviceTables &t, const QuantP
         fri_coarse_inverse_kernel<<<blocks, kCoarseThreads, cs, stream>>>(qp, g.sub_bits, g.depth, d_coefs, d_dc);
         if (launches) ++*launches;
     }
+    const GroupDesc *gtab = (group_begin == 0 && group_end == g.n_groups && t.groups_launch) ? t.groups_launch : t.groups;
     uint8_t *px = static_cast<uint8_t *>(d_pixels);
     for (uint32_t f0 = 0; f0 < n_frames; f0 += 65535u) {
         const uint32_t nf = n_frames - f0 < 65535u ? n_frames - f0 : 65535u;
@@ -1488,7 +1490,7 @@ cudaError_t launch_decode(const Geometry &g, const DeviceTables &t, const QuantP
         const int16_t *c16 = d_coefs16 + (int64_t)f0 * g.coefs_per_frame;
         int32_t *dc = d_dc ? d_dc + (((int64_t)f0 * g.n_fractals * g.channels) << g.sub_bits) : nullptr;
 #define FRI_LAUNCH_Q(CC, SS, DD, QQ, TT, PTR) \
-    fri_decode_kernel<CC, SS, DD, QQ, TT><<<grid, cta_threads(g), smem, stream>>>(g, qp, t.groups, t.tile_unit, t.chunk_list, t.chunk_mask, PTR, dc, p, group_begin)
+    fri_decode_kernel<CC, SS, DD, QQ, TT><<<grid, cta_threads(g), smem, stream>>>(g, qp, gtab, t.tile_unit, t.chunk_list, t.chunk_mask, PTR, dc, p, group_begin)
 #define FRI_LAUNCH(CC, SS, TT, PTR)                                                           \
         do {                                                                                  \
             if (qclass == kQuantNone) FRI_LAUNCH_Q(CC, SS, false, kQuantNone, TT, PTR);       \

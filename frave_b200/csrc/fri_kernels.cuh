@@ -94,7 +94,8 @@ size_t kernel_smem_bytes(const Geometry &g);
 
 // Device-side tables of a plan.
 struct DeviceTables {
-    const GroupDesc *groups = nullptr;
+    const GroupDesc *groups = nullptr;         // plan order (top to bottom): banded launches, emission kernels
+    const GroupDesc *groups_launch = nullptr;  // whole-frame launch order (nullptr = plan order)
     const uint32_t *tile_unit = nullptr;   // nullptr at depth 9
     const uint32_t *chunk_list = nullptr;  // [16][list_cap]
     const uint16_t *chunk_mask = nullptr;  // [16][list_cap]
