@@ -9,7 +9,7 @@ python bench.py --impl reference --steps 3 --warmup 3 > gpurun_out/bench_ref_$T.
 python bench.py --steps 60 --warmup 5 --no-cpu --no-batched --shape 3840x2160x3 --frames 8 > gpurun_out/bench8_$T.json 2>> gpurun_out/bench_$T.err
 python profiles/pcie.py > gpurun_out/pcie_$T.txt 2>&1
 python profiles/extra_configs.py > gpurun_out/other_$T.jsonl 2>&1
-python profiles/trace.py > gpurun_out/timeline_$T.txt 2>&1
+python -m frave_b200.build --variant trace -DFRI_TRACE=1 > /dev/null 2>&1; python profiles/trace.py > gpurun_out/timeline_$T.txt 2>&1
 CMD="python bench.py --steps 3 --warmup 3 --preheat 0 --no-cpu --no-batched --no-e2e"
 $CMD > gpurun_out/plain_$T.log 2>&1 && ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sectors_srcunit_tex_op_read.sum --clock-control none -k regex:fri_ -c 40 --csv --log-file gpurun_out/launches_$T.csv $CMD > gpurun_out/ncu_$T.log 2>&1
 for K in encode decode; do
