@@ -181,3 +181,12 @@ def decode_tiles(centers: np.ndarray, coef: np.ndarray, some: np.ndarray | None,
     L.fri_oracle_decode_tiles(centers.ctypes.data, coef.ctypes.data, s8.ctypes.data if s8 is not None else None, n,
                               depth, w, h, c, out.dtype.itemsize, qa.ctypes.data, out.ctypes.data, nthreads)
     return out
+
+
+def fractal_new_cost(centers: np.ndarray, channels: int, depth: int = 9) -> int:
+    """Cost model (not a restatement): the containers Fractal::new builds per tile — see fri_oracle.c."""
+    L = lib()
+    L.fri_oracle_fractal_new_cost.restype = C.c_uint64
+    L.fri_oracle_fractal_new_cost.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_uint32]
+    centers = np.ascontiguousarray(centers, dtype=np.int32)
+    return int(L.fri_oracle_fractal_new_cost(depth, centers.ctypes.data, len(centers), channels))

@@ -492,4 +492,83 @@ void fri_oracle_decode_tiles(const int32_t *centers, const int32_t *coef, const 
     parallel_for(n_tiles, nthreads, dt_body, &d);
 }
 
+/* ------------------------------------------------------------------------------------------
+ * "Reference-shaped" cost estimate — NOT a restatement, a cost model.
+ * The reference spends most of its transform time not in the lifting arithmetic but in the
+ * containers Fractal::new builds for every tile (wavelet_transform.rs:42-69): image_positions
+ * (Vec of 2^(depth+1) Complex<i32>), one HashMap<Complex<i32>, usize> per tree level with 2^level
+ * inserts (std HashMap = hashbrown with SipHash-1-3 and doubling growth from empty), the
+ * coefficient and value Vecs.  This function performs the same allocations, hashes and inserts for
+ * every tile of a list so that bench.py can report "arithmetic + containers" beside the
+ * arithmetic-only figure.  It returns a checksum so the work cannot be optimised away.
+ * ------------------------------------------------------------------------------------------ */
+#define ROTL64(x, b) (uint64_t)(((x) << (b)) | ((x) >> (64 - (b))))
+#define SIPROUND(v0, v1, v2, v3) \
+    do { v0 += v1; v1 = ROTL64(v1, 13); v1 ^= v0; v0 = ROTL64(v0, 32); v2 += v3; v3 = ROTL64(v3, 16); v3 ^= v2; \
+         v0 += v3; v3 = ROTL64(v3, 21); v3 ^= v0; v2 += v1; v1 = ROTL64(v1, 17); v1 ^= v2; v2 = ROTL64(v2, 32); } while (0)
+
+static uint64_t siphash13_u64(uint64_t m, uint64_t k0, uint64_t k1)
+{
+    uint64_t v0 = k0 ^ 0x736f6d6570736575ULL, v1 = k1 ^ 0x646f72616e646f6dULL;
+    uint64_t v2 = k0 ^ 0x6c7967656e657261ULL, v3 = k1 ^ 0x7465646279746573ULL;
+    v3 ^= m; SIPROUND(v0, v1, v2, v3); v0 ^= m;            /* one 8-byte block, 1 compression round */
+    const uint64_t b = (uint64_t)8 << 56;                   /* length byte */
+    v3 ^= b; SIPROUND(v0, v1, v2, v3); v0 ^= b;
+    v2 ^= 0xff; SIPROUND(v0, v1, v2, v3); SIPROUND(v0, v1, v2, v3); SIPROUND(v0, v1, v2, v3);  /* 3 finalisation rounds */
+    return v0 ^ v1 ^ v2 ^ v3;
+}
+
+typedef struct { uint64_t *keys; size_t *vals; uint8_t *used; size_t cap, len; } pos_map;
+
+static void pm_insert_raw(pos_map *m, uint64_t key, size_t val)
+{
+    size_t i = (size_t)siphash13_u64(key, 0x0706050403020100ULL, 0x0f0e0d0c0b0a0908ULL) & (m->cap - 1);
+    while (m->used[i]) {
+        if (m->keys[i] == key) { m->vals[i] = val; return; }
+        i = (i + 1) & (m->cap - 1);
+    }
+    m->used[i] = 1; m->keys[i] = key; m->vals[i] = val; ++m->len;
+}
+
+static void pm_insert(pos_map *m, uint64_t key, size_t val)
+{
+    if (m->cap == 0 || (m->len + 1) * 8 > m->cap * 7) {  /* hashbrown: grow at 7/8 load, double, re-insert */
+        pos_map n;
+        n.cap = m->cap ? m->cap * 2 : 4;
+        n.len = 0;
+        n.keys = (uint64_t *)malloc(n.cap * sizeof(uint64_t));
+        n.vals = (size_t *)malloc(n.cap * sizeof(size_t));
+        n.used = (uint8_t *)calloc(n.cap, 1);
+        for (size_t i = 0; i < m->cap; ++i)
+            if (m->used[i]) pm_insert_raw(&n, m->keys[i], m->vals[i]);
+        free(m->keys); free(m->vals); free(m->used);
+        *m = n;
+    }
+    pm_insert_raw(m, key, val);
+}
+
+uint64_t fri_oracle_fractal_new_cost(int depth, const int32_t *centers, size_t n_tiles, uint32_t channels)
+{
+    uint64_t sum = 0;
+    const size_t nodes = (size_t)1 << (depth + 1), leaves = (size_t)1 << depth;
+    for (size_t t = 0; t < n_tiles; ++t) {
+        int32_t *pos = (int32_t *)malloc(nodes * 2 * sizeof(int32_t));  /* image_positions */
+        fri_oracle_image_positions(depth, centers[2 * t], centers[2 * t + 1], pos);
+        pos_map *maps = (pos_map *)calloc((size_t)depth, sizeof(pos_map));  /* position_map[level] */
+        for (int level = 0; level < depth; ++level)
+            for (size_t p = (size_t)1 << level; p < ((size_t)2 << level); ++p)
+                pm_insert(&maps[level], (uint64_t)ks_key(pos[2 * p], pos[2 * p + 1]), p);
+        /* coefficients: [channels] Vec<Option<i32>> (8 B each), values: Vec<Option<i32>> per channel */
+        fri_opt_i32 *coef = (fri_opt_i32 *)calloc((size_t)channels * leaves, sizeof(fri_opt_i32));
+        fri_opt_i32 *vals = (fri_opt_i32 *)calloc((size_t)channels * nodes, sizeof(fri_opt_i32));
+        for (int level = 0; level < depth; ++level) {
+            sum += maps[level].len + maps[level].vals[maps[level].cap / 2];
+            free(maps[level].keys); free(maps[level].vals); free(maps[level].used);
+        }
+        sum += (uint64_t)coef[leaves - 1].v + (uint64_t)vals[nodes - 1].v + (uint64_t)(uint32_t)pos[2 * nodes - 1];
+        free(maps); free(coef); free(vals); free(pos);
+    }
+    return sum;
+}
+
 void fri_oracle_free(void *p) { free(p); }

@@ -95,6 +95,10 @@ void fri_oracle_decode_tiles(const int32_t *centers, const int32_t *coef, const 
                              int depth, uint32_t width, uint32_t height, uint32_t channels, uint32_t sample_bytes,
                              const int32_t q[32], void *out, int nthreads);
 
+/* Cost model, not a restatement: the allocations, SipHash-1-3 hashes and
+ * HashMap inserts Fractal::new performs per tile (wavelet_transform.rs:42-69).  Returns a checksum. */
+uint64_t fri_oracle_fractal_new_cost(int depth, const int32_t *centers, size_t n_tiles, uint32_t channels);
+
 void fri_oracle_free(void *p);
 
 #ifdef __cplusplus

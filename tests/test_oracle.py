@@ -107,6 +107,14 @@ def test_hand_derived_depth2_example(impl):
     assert rec[:, :, 0].tolist() == [[0, 5, 0], [7, 2, 0]]
 
 
+def test_reference_shaped_cost_model_runs():
+    """fri_oracle_fractal_new_cost is a cost model for bench.py, not a restatement:
+    it must be deterministic and touch every tile."""
+    cen = np.array([[5, 7], [100, -3], [0, 0]], np.int32)
+    a = O.fractal_new_cost(cen, 3)
+    assert a == O.fractal_new_cost(cen, 3) and a != O.fractal_new_cost(cen[:2], 3)
+
+
 def test_quant_layer_formula():
     # quantization.rs:13: layer = trailing_zeros(prev_power_two(i + 1)) = floor(log2(i + 1))
     layers = N.quant_layers(9)
