@@ -562,7 +562,7 @@ uint64_t fri_oracle_fractal_new_cost(int depth, const int32_t *centers, size_t n
         fri_opt_i32 *coef = (fri_opt_i32 *)calloc((size_t)channels * leaves, sizeof(fri_opt_i32));
         fri_opt_i32 *vals = (fri_opt_i32 *)calloc((size_t)channels * nodes, sizeof(fri_opt_i32));
         for (int level = 0; level < depth; ++level) {
-            sum += maps[level].len + maps[level].vals[maps[level].cap / 2];
+            sum += maps[level].len + (maps[level].used[maps[level].cap / 2] ? maps[level].vals[maps[level].cap / 2] : 0);
             free(maps[level].keys); free(maps[level].vals); free(maps[level].used);
         }
         sum += (uint64_t)coef[leaves - 1].v + (uint64_t)vals[nodes - 1].v + (uint64_t)(uint32_t)pos[2 * nodes - 1];
