@@ -1134,7 +1134,7 @@ fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
                   const GroupDesc *__restrict__ groups, const uint32_t *__restrict__ tile_unit,
                   const uint32_t *__restrict__ chunk_list, const uint16_t *__restrict__ chunk_mask,
                   const CT *__restrict__ coefs, const int32_t *__restrict__ dc_in, uint8_t *__restrict__ pixels,
-                  int group_offset)
+                  int group_offset, int no_prefetch_ctas)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *region = smem;
@@ -1144,7 +1144,7 @@ fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
     const int frame = blockIdx.y;
     const RegionView rv = region_view<C * (int)sizeof(S)>(g, gd, pixels + (int64_t)frame * g.frame_bytes);
     FRI_TRACE_MARK(0);
-    prefetch_group_coefs<C, DEEP, CT>(g, gd, frame, coefs);
+    if ((int64_t)blockIdx.y * gridDim.x + blockIdx.x >= no_prefetch_ctas) prefetch_group_coefs<C, DEEP, CT>(g, gd, frame, coefs);
     if (__popc(gd.tile_mask) != g.group_a * g.group_b) {
         zero_region(g, region);
         __syncthreads();
@@ -1481,6 +1481,11 @@ cudaError_t launch_decode(const Geometry &g, const DeviceTables &t, const QuantP
         if (launches) ++*launches;
     }
     const GroupDesc *gtab = (group_begin == 0 && group_end == g.n_groups && t.groups_launch) ? t.groups_launch : t.groups;
+    // The CTAs of the first wave start together and their demand loads alone keep HBM busy; an L2 prefetch of
+    // the whole run on top of that only delays everybody's first tiles (+2-4 % without it on a single frame).
+    // Every later CTA starts alone and prefetches its run.  Tuning knob: FRI_DEC_NO_PREFETCH_CTAS.
+    int no_prefetch_ctas = resident_ctas(g);
+    if (const char *env = std::getenv("FRI_DEC_NO_PREFETCH_CTAS")) no_prefetch_ctas = std::atoi(env);
     uint8_t *px = static_cast<uint8_t *>(d_pixels);
     for (uint32_t f0 = 0; f0 < n_frames; f0 += 65535u) {
         const uint32_t nf = n_frames - f0 < 65535u ? n_frames - f0 : 65535u;
@@ -1490,7 +1495,7 @@ cudaError_t launch_decode(const Geometry &g, const DeviceTables &t, const QuantP
         const int16_t *c16 = d_coefs16 + (int64_t)f0 * g.coefs_per_frame;
         int32_t *dc = d_dc ? d_dc + (((int64_t)f0 * g.n_fractals * g.channels) << g.sub_bits) : nullptr;
 #define FRI_LAUNCH_Q(CC, SS, DD, QQ, TT, PTR) \
-    fri_decode_kernel<CC, SS, DD, QQ, TT><<<grid, cta_threads(g), smem, stream>>>(g, qp, gtab, t.tile_unit, t.chunk_list, t.chunk_mask, PTR, dc, p, group_begin)
+    fri_decode_kernel<CC, SS, DD, QQ, TT><<<grid, cta_threads(g), smem, stream>>>(g, qp, gtab, t.tile_unit, t.chunk_list, t.chunk_mask, PTR, dc, p, group_begin, no_prefetch_ctas)
 #define FRI_LAUNCH(CC, SS, TT, PTR)                                                           \
         do {                                                                                  \
             if (qclass == kQuantNone) FRI_LAUNCH_Q(CC, SS, false, kQuantNone, TT, PTR);       \
