@@ -1053,7 +1053,8 @@ __global__ void __launch_bounds__(kThreads, FRI_ENC_MINB)
 fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ QuantParams qp,
                   const GroupDesc *__restrict__ groups, const uint32_t *__restrict__ tile_unit,
                   const uint32_t *__restrict__ stage_list, const uint8_t *__restrict__ pixels,
-                  CT *__restrict__ coefs, int32_t *__restrict__ dc_out, int lookahead, int group_offset, int bulk_staging)
+                  CT *__restrict__ coefs, int32_t *__restrict__ dc_out, int lookahead, int group_offset, int bulk_staging,
+                  int late_lookahead_ctas)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *region = smem;
@@ -1097,28 +1098,34 @@ fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
             cp_async_wait_all();
         }
     }
+    auto look_ahead = [&]() {
     // Look-ahead: while this group's copies are in flight, pull the pixel rows of the group that
-    // will run in this CTA slot one residency later towards L2, one 128-byte line per thread and
-    // iteration, so that its copies are served by L2 instead of waiting in the DRAM queues.
-    if (lookahead > 0) {
-        const int64_t target = (int64_t)frame * gridDim.x + blockIdx.x + lookahead;  // linear CTA index in this launch
-        if (target < (int64_t)gridDim.y * gridDim.x) {
-            const int tf = (int)(target / gridDim.x);
-            const GroupDesc tg = ld_group(groups + group_offset + (target - (int64_t)tf * gridDim.x), pol);
-            const int lines_per_row = (g.row_bytes + 127) / 128 + 1;
-            const int y_lo = max(tg.y0, 0), y_hi = min(tg.y0 + g.region_h, g.height);
-            const int64_t xb = min(max((int64_t)tg.x0 * (C * (int)sizeof(S)), (int64_t)0), g.row_stride - 1);
-            const char *base = reinterpret_cast<const char *>(pixels) + (int64_t)tf * g.frame_bytes + xb;
-            const int total = (y_hi - y_lo) * lines_per_row;
-            for (int i = threadIdx.x; i < total; i += blockDim.x) {
-                const int r = i / lines_per_row, c = i - r * lines_per_row;
-                if (xb + (int64_t)c * 128 < g.row_stride)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (int64_t)(y_lo + r) * g.row_stride + (int64_t)c * 128));
+        // will run in this CTA slot one residency later towards L2, one 128-byte line per thread and
+        // iteration, so that its copies are served by L2 instead of waiting in the DRAM queues.
+        if (lookahead > 0) {
+            const int64_t target = (int64_t)frame * gridDim.x + blockIdx.x + lookahead;  // linear CTA index in this launch
+            if (target < (int64_t)gridDim.y * gridDim.x) {
+                const int tf = (int)(target / gridDim.x);
+                const GroupDesc tg = ld_group(groups + group_offset + (target - (int64_t)tf * gridDim.x), pol);
+                const int lines_per_row = (g.row_bytes + 127) / 128 + 1;
+                const int y_lo = max(tg.y0, 0), y_hi = min(tg.y0 + g.region_h, g.height);
+                const int64_t xb = min(max((int64_t)tg.x0 * (C * (int)sizeof(S)), (int64_t)0), g.row_stride - 1);
+                const char *base = reinterpret_cast<const char *>(pixels) + (int64_t)tf * g.frame_bytes + xb;
+                const int total = (y_hi - y_lo) * lines_per_row;
+                for (int i = threadIdx.x; i < total; i += blockDim.x) {
+                    const int r = i / lines_per_row, c = i - r * lines_per_row;
+                    if (xb + (int64_t)c * 128 < g.row_stride)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (int64_t)(y_lo + r) * g.row_stride + (int64_t)c * 128));
+                }
             }
         }
-    }
+    };
+    // first-wave CTAs (all start together, all waiting on HBM) look ahead only once their own pixels are in
+    const bool late_look = late_lookahead_ctas > 0 && (int64_t)frame * gridDim.x + blockIdx.x < late_lookahead_ctas;
+    if (!late_look) look_ahead();
     __syncthreads();
     if (bulk) mbar_wait(&bars[0], 0);
+    if (late_look) look_ahead();
     FRI_TRACE_MARK(1);
     encode_tiles<C, S, DEEP, QS, CT>(g, qp, gd, rv, tile_unit, frame, region, scratch, coefs, dc_out, two_stage,
                                      bulk ? bars : nullptr);
@@ -1418,6 +1425,10 @@ cudaError_t launch_encode(const Geometry &g, const DeviceTables &t, const QuantP
     if (const char *env = std::getenv("FRI_LOOKAHEAD")) lookahead = std::atoi(env);  // tuning knob
     if (!whole) lookahead = 0;  // banded host pipeline: rows of later groups may not be on the device yet
     // Bulk-copy (TMA) staging of interior groups; FRI_STAGE_BULK=0 falls back to the chunk-list cp.async path
+    // The CTAs of the first wave (they start together and all wait on HBM) issue their look-ahead only after
+    // their own pixels have landed: +2.8 % on a single frame.  Tuning knob: FRI_ENC_LATE_LOOKAHEAD_CTAS.
+    int late_look_ctas = resident_ctas(g);
+    if (const char *env = std::getenv("FRI_ENC_LATE_LOOKAHEAD_CTAS")) late_look_ctas = std::atoi(env);
     int bulk_staging = 1;
     if (const char *env = std::getenv("FRI_STAGE_BULK")) bulk_staging = std::atoi(env) != 0;  // tuning knob
     const GroupDesc *gtab = whole && t.groups_launch ? t.groups_launch : t.groups;  // launch order (whole frames only)
@@ -1430,7 +1441,7 @@ cudaError_t launch_encode(const Geometry &g, const DeviceTables &t, const QuantP
         int16_t *c16 = d_coefs16 + (int64_t)f0 * g.coefs_per_frame;
         int32_t *dc = d_dc ? d_dc + (((int64_t)f0 * g.n_fractals * g.channels) << g.sub_bits) : nullptr;
 #define FRI_LAUNCH_Q(CC, SS, DD, QQ, TT, PTR) \
-    fri_encode_kernel<CC, SS, DD, QQ, TT><<<grid, cta_threads(g), smem, stream>>>(g, qp, gtab, t.tile_unit, t.stage_list, p, PTR, dc, lookahead, group_begin, bulk_staging)
+    fri_encode_kernel<CC, SS, DD, QQ, TT><<<grid, cta_threads(g), smem, stream>>>(g, qp, gtab, t.tile_unit, t.stage_list, p, PTR, dc, lookahead, group_begin, bulk_staging, late_look_ctas)
 #define FRI_LAUNCH(CC, SS, TT, PTR)                                                           \
         do {                                                                                  \
             if (qclass == kQuantNone) FRI_LAUNCH_Q(CC, SS, false, kQuantNone, TT, PTR);       \
