@@ -1205,7 +1205,11 @@ fri_coarse_inverse_kernel(const __grid_constant__ QuantParams qp, int sub_bits, 
 {
     extern __shared__ __align__(16) int32_t cs[];
     const int n = 1 << sub_bits;
-    int32_t *src = cs + n, *dst = cs;  // sizes: level L reads 2^L values, writes 2^(L+1)
+    // Level L reads 2^L values and writes 2^(L+1).  Two buffers, X = cs[0, n) and Y = cs[n, n + n/2): the
+    // last level (sub_bits - 1) writes n values and must land in X, the one before n/2 values in Y, and so
+    // on alternating — so level 0 writes into X when sub_bits is odd, into Y when it is even.
+    int32_t *dst = (sub_bits & 1) ? cs : cs + n;
+    int32_t *src = (sub_bits & 1) ? cs + n : cs;
     const int32_t *in = coefs + ((int64_t)blockIdx.x << depth);
     int32_t *out = dc + ((int64_t)blockIdx.x << sub_bits);
     if (threadIdx.x == 0) src[0] = dequant_layer(qp, in[0], 0);
