@@ -29,6 +29,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdlib>
+#include <utility>
 
 namespace fri {
 
@@ -111,7 +112,7 @@ int cta_threads(const Geometry &g)
 
 size_t kernel_smem_bytes(const Geometry &g)
 {
-    return (((size_t)g.region_h * g.pitch + 15) & ~(size_t)15) + (size_t)(cta_threads(g) / 32) * g.channels * kScratchInts * sizeof(int32_t);
+    return (((size_t)g.region_h * g.pitch + 15) & ~(size_t)15) + (size_t)(cta_threads(g) / 32) * scratch_units(g.channels) * kScratchInts * sizeof(int32_t);
 }
 
 #if FRI_TRACE
@@ -194,6 +195,14 @@ __device__ __forceinline__ GroupDesc ld_group(const GroupDesc *p, uint64_t pol)
                  : "l"(p), "l"(pol));
     return g;
 }
+
+// Programmatic dependent launch: every CTA lets the next kernel of the stream start launching as soon as
+// all CTAs of this one have started (its CTAs take the slots this kernel's last wave leaves empty and run
+// their prologue there), and waits for the previous kernel to complete — memory flushed — before it touches
+// frame data.  Plan tables are constant and may be read before the wait.  Without the launch attribute both
+// instructions are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // wrapping i32 arithmetic (release-mode Rust semantics)
 __device__ __forceinline__ int wsub(int a, int b) { return (int)((unsigned)a - (unsigned)b); }
@@ -488,13 +497,156 @@ __device__ __forceinline__ void stage_rows_bulk(const Geometry &g, const RegionV
     bulk_g2s(region + s0, rv.gaddr(r, s0), (uint32_t)(s1 - s0), bar);
 }
 
+// ---- forward transform + quantization, building blocks
+//
+// Register levels of one (base tile, channel): gather 16 leaves per lane (two depth-3 subtrees), levels
+// 8, 7, 6 in registers, quantize, store; the two level-6 low-pass values go to `sc` (64 ints: node 64 + l).
+template <typename S, int PB, bool DEEP, int QS, typename CT>
+__device__ __forceinline__ void enc_register_levels(const Geometry &g, const QuantParams &qp, const uint8_t *p0, int half,
+                                                    int lane, bool lastB, int top, int32_t *sc, CT *__restrict__ out,
+                                                    size_t node)
+{
+    const uint8_t *p1 = p0 + g.pitch, *p2 = p1 + g.pitch;
+    // gather: leaf i of a depth-3 subtree sits at sub_leaf(i) from the subtree's first leaf
+    int v[8], w[8];
+#define FRI_LD(ptr, dx) ((int)*reinterpret_cast<const S *>((ptr) + (dx) * PB))
+    v[0] = FRI_LD(p0, 0);  v[1] = FRI_LD(p1, 0);   // (0,0) (0,1)
+    v[2] = FRI_LD(p1, -1); v[3] = FRI_LD(p2, -1);  // (-1,1) (-1,2)
+    v[4] = FRI_LD(p0, 2);  v[5] = FRI_LD(p1, 2);   // (2,0) (2,1)
+    v[6] = FRI_LD(p1, 1);  v[7] = FRI_LD(p2, 1);   // (1,1) (1,2)
+    w[0] = FRI_LD(p0 + half, 0);  w[1] = FRI_LD(p1 + half, 0);
+    w[2] = FRI_LD(p1 + half, -1); w[3] = FRI_LD(p2 + half, -1);
+    w[4] = FRI_LD(p0 + half, 2);  w[5] = FRI_LD(p1 + half, 2);
+    w[6] = FRI_LD(p1 + half, 1);  w[7] = FRI_LD(p2 + half, 1);
+#undef FRI_LD
+    // levels 8, 7, 6 in registers
+    int a8[4], b8[4], sa8[4], sb8[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        lift(v[2 * m], v[2 * m + 1], a8[m], sa8[m]);
+        lift(w[2 * m], w[2 * m + 1], b8[m], sb8[m]);
+    }
+    int a7[2], b7[2], sa7[2], sb7[2];
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        lift(sa8[2 * m], sa8[2 * m + 1], a7[m], sa7[m]);
+        lift(sb8[2 * m], sb8[2 * m + 1], b7[m], sb7[m]);
+    }
+    int a6, b6, sA, sB;
+    lift(sa7[0], sa7[1], a6, sA);
+    lift(sb7[0], sb7[1], b6, sB);
+    sc[lane] = sA;       // low-pass of node 64 + lane
+    sc[32 + lane] = sB;  // low-pass of node 96 + lane
+
+    // quantization.rs:13 — layer = level, except the last node of a level: level + 1
+    if (QS == kQuantSmallest) {
+        // only layers 8 and 9 are active and share one divisor: every level-8 node (the last one
+        // sits in layer 9) and the last node of level 7 (layer 8)
+        int r7 = b7[1];
+        if (qp.small & 0x100u) {
+            const SmallDiv dv = qp.sdiv(8);
+#pragma unroll
+            for (int m = 0; m < 4; ++m) { a8[m] = trunc_div_small(a8[m], dv); b8[m] = trunc_div_small(b8[m], dv); }
+            r7 = trunc_div_small(r7, dv);
+        } else {
+            const Div dv = qp.div(8);
+#pragma unroll
+            for (int m = 0; m < 4; ++m) { a8[m] = trunc_div(a8[m], dv); b8[m] = trunc_div(b8[m], dv); }
+            r7 = trunc_div(r7, dv);
+        }
+        if (lane == 31) b7[1] = r7;
+    } else if (QS == kQuantGeneric && ((qp.active >> (top + 6)) & 0xfu)) {
+        const int r8 = b8[3], r7 = b7[1], r6 = b6;  // unquantized values of the level-last nodes
+#define FRI_QLEVEL(L, N, A, B)                                                              \
+        if ((qp.active >> (top + (L))) & 1u) {                                              \
+            if ((qp.small >> (top + (L))) & 1u) {                                           \
+                const SmallDiv dv = qp.sdiv(top + (L));                                     \
+                _Pragma("unroll") for (int m = 0; m < (N); ++m) { A[m] = trunc_div_small(A[m], dv); B[m] = trunc_div_small(B[m], dv); } \
+            } else {                                                                        \
+                const Div dv = qp.div(top + (L));                                           \
+                _Pragma("unroll") for (int m = 0; m < (N); ++m) { A[m] = trunc_div(A[m], dv); B[m] = trunc_div(B[m], dv); } \
+            }                                                                               \
+        }
+        int a6v[1] = {a6}, b6v[1] = {b6};
+        FRI_QLEVEL(8, 4, a8, b8)
+        FRI_QLEVEL(7, 2, a7, b7)
+        FRI_QLEVEL(6, 1, a6v, b6v)
+#undef FRI_QLEVEL
+        a6 = a6v[0];
+        b6 = b6v[0];
+        if (lastB && ((qp.fix >> (top + 6)) & 7u)) {  // only where the next layer's divisor differs
+            if ((qp.fix >> (top + 8)) & 1u) b8[3] = quant_layer_enc(qp, r8, top + 9);
+            if ((qp.fix >> (top + 7)) & 1u) b7[1] = quant_layer_enc(qp, r7, top + 8);
+            if ((qp.fix >> (top + 6)) & 1u) b6 = quant_layer_enc(qp, r6, top + 7);
+        }
+    }
+    CT *o8 = out + (node << 8), *o7 = out + (node << 7), *o6 = out + (node << 6);
+    st_c4(o8 + 4 * lane, make_int4(a8[0], a8[1], a8[2], a8[3]));
+    st_c4(o8 + 128 + 4 * lane, make_int4(b8[0], b8[1], b8[2], b8[3]));
+    st_c2(o7 + 2 * lane, make_int2(a7[0], a7[1]));
+    st_c2(o7 + 64 + 2 * lane, make_int2(b7[0], b7[1]));
+    st_c1(o6 + lane, a6);
+    st_c1(o6 + 32 + lane, b6);
+}
+
+// Levels 5..0 of one (base tile, channel) by the 8 lanes of a lane group: lane j8 folds the level-6 values
+// sp[0 .. 7] (= s6[8 j8 .. 8 j8 + 7]) through levels 5..3 in registers and levels 2..0 with three
+// shuffles inside the group (every lane of the warp must call this), quantizes and — if `live` — stores.
+template <bool DEEP, typename CT>
+__device__ __forceinline__ void enc_top_levels(const QuantParams &qp, const int32_t *sp, const TaskAddr &ta, int j8, int top,
+                                               int sub_bits, bool live, CT *__restrict__ out, int32_t *__restrict__ dc_slot)
+{
+    const int4 x0 = *reinterpret_cast<const int4 *>(sp), x1 = *reinterpret_cast<const int4 *>(sp + 4);
+    int d5[4], s5[4], d4[2], s4[2], d3, d2, d1, d0, s3, s2, s1, s0;
+    lift(x0.x, x0.y, d5[0], s5[0]);
+    lift(x0.z, x0.w, d5[1], s5[1]);
+    lift(x1.x, x1.y, d5[2], s5[2]);
+    lift(x1.z, x1.w, d5[3], s5[3]);
+    lift(s5[0], s5[1], d4[0], s4[0]);
+    lift(s5[2], s5[3], d4[1], s4[1]);
+    lift(s4[0], s4[1], d3, s3);
+    lift(s3, __shfl_xor_sync(0xffffffffu, s3, 1), d2, s2);  // meaningful in lanes j8 % 2 == 0
+    lift(s2, __shfl_xor_sync(0xffffffffu, s2, 2), d1, s1);  // j8 % 4 == 0
+    lift(s1, __shfl_xor_sync(0xffffffffu, s1, 4), d0, s0);  // j8 == 0
+    if ((qp.active >> top) & 0x7fu) {
+        // level-L nodes sit in layer top + L, the level's last node in layer top + L + 1
+        const bool lastG = ta.last && j8 == 7;
+        d5[0] = quant_layer_enc(qp, d5[0], top + 5); d5[1] = quant_layer_enc(qp, d5[1], top + 5);
+        d5[2] = quant_layer_enc(qp, d5[2], top + 5); d5[3] = quant_layer_enc(qp, d5[3], top + (lastG ? 6 : 5));
+        d4[0] = quant_layer_enc(qp, d4[0], top + 4); d4[1] = quant_layer_enc(qp, d4[1], top + (lastG ? 5 : 4));
+        d3 = quant_layer_enc(qp, d3, top + (lastG ? 4 : 3));
+        d2 = quant_layer_enc(qp, d2, top + ((ta.last && j8 == 6) ? 3 : 2));
+        d1 = quant_layer_enc(qp, d1, top + ((ta.last && j8 == 4) ? 2 : 1));
+        if (sub_bits == 0) {
+            d0 = quant_layer_enc(qp, d0, 1);  // position 1 is the last node of level 0
+            s0 = quant_layer_enc(qp, s0, 0);  // position 0: the low-pass root (wavelet_transform.rs:221)
+        } else {
+            d0 = quant_layer_enc(qp, d0, top + (ta.last ? 1 : 0));
+        }
+    }
+    if (live) {
+        const size_t node = ta.node;
+        st_c4(out + (node << 5) + 4 * j8, make_int4(d5[0], d5[1], d5[2], d5[3]));
+        st_c2(out + (node << 4) + 2 * j8, make_int2(d4[0], d4[1]));
+        st_c1(out + (node << 3) + j8, d3);
+        if ((j8 & 1) == 0) st_c1(out + (node << 2) + (j8 >> 1), d2);
+        if ((j8 & 3) == 0) st_c1(out + (node << 1) + (j8 >> 2), d1);
+        if (j8 == 0) {
+            st_c1(out + node, d0);
+            if (sub_bits == 0) st_c1(out, s0);
+            else *dc_slot = s0;
+        }
+    }
+}
+
 // Forward transform + quantization of the tiles of one staged group; warp w takes tiles
-// w, w + n_warps, ...  Per warp iteration: one base tile, all C channels.
-//   phase 1 (per channel): gather 16 leaves per lane, levels 8..6 in registers, quantize, store;
-//                          the 64 level-6 low-pass values go to the warp's scratch.
-//   phase 2 (all channels at once): lane group lane / 8 owns a channel; lane j of the group
-//                          folds s6[8j .. 8j+7] through levels 5..3 in registers and levels 2..0
-//                          with three shuffles inside the group.
+// w, w + n_warps, ...
+//   C == 3, per warp iteration one base tile, all channels:
+//     phase 1 (per channel): enc_register_levels; phase 2 (all channels at once): lane group lane / 8 owns a
+//     channel (enc_top_levels), 24 of 32 lanes busy;
+//   C == 1, per warp iteration a batch of up to four base tiles: phase 1 tile after tile, then ONE phase 2
+//     in which lane group lane / 8 owns a tile — all 32 lanes busy instead of 8 (the top levels are a
+//     quarter of a 1-channel tile's instructions).
 template <int C, typename S, bool DEEP, int QS, typename CT>
 __device__ __forceinline__ void encode_tiles(const Geometry &g, const QuantParams &qp, const GroupDesc &gd, const RegionView &rv,
                                              const uint32_t *__restrict__ tile_unit, int frame, const uint8_t *region,
@@ -510,155 +662,53 @@ __device__ __forceinline__ void encode_tiles(const Geometry &g, const QuantParam
     const int sub_bits = DEEP ? g.sub_bits : 0, depth = DEEP ? g.depth : kBaseDepth;
     const int top = sub_bits;  // fractal level of a base tile's root
     const bool sparse_group = (gd.tile_mask & (gd.tile_mask + 1u)) != 0;
-    const int grp = min(lane >> 3, C - 1), j8 = lane & 7;  // phase 2 roles
+    const int grp = min(lane >> 3, scratch_units(C) - 1), j8 = lane & 7;  // phase 2 roles
+    auto second_round_wait = [&]() {  // the rest of the footprint must have landed
+        if (bars) {
+            mbar_wait(bars + 1, 0);
+        } else {
+            cp_async_wait_all();
+            __syncthreads();
+        }
+    };
+    if (C == 1) {
+        for (int e0 = warp; e0 < n_present; e0 += kTileBatch * n_warps) {
+#pragma unroll
+            for (int k = 0; k < kTileBatch; ++k) {
+                const int e = e0 + k * n_warps;
+                if (e >= n_present) break;
+                if (two_stage && e == warp + n_warps) second_round_wait();
+                const int slot = sparse_group ? (int)__fns(gd.tile_mask, 0, e + 1) : e;
+                const TaskAddr ta = task_addr<C, DEEP>(g, tile_unit, frame, gd.tile_base + e, 0);
+                enc_register_levels<S, PB, DEEP, QS, CT>(g, qp, lane_base + g.tile_off[slot], half, lane, ta.last && lane == 31, top,
+                                                         scratch + k * kScratchInts, coefs + ta.block, ta.node);
+            }
+            __syncwarp();
+            const int eg = e0 + grp * n_warps;
+            const bool live = eg < n_present;
+            const TaskAddr ta = task_addr<C, DEEP>(g, tile_unit, frame, gd.tile_base + (live ? eg : e0), 0);
+            enc_top_levels<DEEP, CT>(qp, scratch + grp * kScratchInts + 8 * j8, ta, j8, top, sub_bits, live, coefs + ta.block,
+                                     DEEP ? dc_out + ta.dc : nullptr);
+            __syncwarp();
+        }
+        return;
+    }
     const bool grp_live = (lane >> 3) < C;
     for (int e = warp; e < n_present; e += n_warps) {
-        if (two_stage && e == warp + n_warps) {  // second round: the rest of the footprint must have landed
-            if (bars) {
-                mbar_wait(bars + 1, 0);
-            } else {
-                cp_async_wait_all();
-                __syncthreads();
-            }
-        }
+        if (two_stage && e == warp + n_warps) second_round_wait();
         const int slot = sparse_group ? (int)__fns(gd.tile_mask, 0, e + 1) : e;
         const uint8_t *t0 = lane_base + g.tile_off[slot];
         const TaskAddr ta = task_addr<C, DEEP>(g, tile_unit, frame, gd.tile_base + e, 0);
         const bool lastB = ta.last && lane == 31;  // this lane holds the last node of levels 8..6
-
 #pragma unroll
-        for (int ch = 0; ch < C; ++ch) {
-            const uint8_t *p0 = t0 + ch * SB, *p1 = p0 + g.pitch, *p2 = p1 + g.pitch;
-            // gather: leaf i of a depth-3 subtree sits at sub_leaf(i) from the subtree's first leaf
-            int v[8], w[8];
-#define FRI_LD(ptr, dx) ((int)*reinterpret_cast<const S *>((ptr) + (dx) * PB))
-            v[0] = FRI_LD(p0, 0);  v[1] = FRI_LD(p1, 0);   // (0,0) (0,1)
-            v[2] = FRI_LD(p1, -1); v[3] = FRI_LD(p2, -1);  // (-1,1) (-1,2)
-            v[4] = FRI_LD(p0, 2);  v[5] = FRI_LD(p1, 2);   // (2,0) (2,1)
-            v[6] = FRI_LD(p1, 1);  v[7] = FRI_LD(p2, 1);   // (1,1) (1,2)
-            w[0] = FRI_LD(p0 + half, 0);  w[1] = FRI_LD(p1 + half, 0);
-            w[2] = FRI_LD(p1 + half, -1); w[3] = FRI_LD(p2 + half, -1);
-            w[4] = FRI_LD(p0 + half, 2);  w[5] = FRI_LD(p1 + half, 2);
-            w[6] = FRI_LD(p1 + half, 1);  w[7] = FRI_LD(p2 + half, 1);
-#undef FRI_LD
-            // levels 8, 7, 6 in registers
-            int a8[4], b8[4], sa8[4], sb8[4];
-#pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                lift(v[2 * m], v[2 * m + 1], a8[m], sa8[m]);
-                lift(w[2 * m], w[2 * m + 1], b8[m], sb8[m]);
-            }
-            int a7[2], b7[2], sa7[2], sb7[2];
-#pragma unroll
-            for (int m = 0; m < 2; ++m) {
-                lift(sa8[2 * m], sa8[2 * m + 1], a7[m], sa7[m]);
-                lift(sb8[2 * m], sb8[2 * m + 1], b7[m], sb7[m]);
-            }
-            int a6, b6, sA, sB;
-            lift(sa7[0], sa7[1], a6, sA);
-            lift(sb7[0], sb7[1], b6, sB);
-            scratch[ch * kScratchInts + lane] = sA;       // low-pass of node 64 + lane
-            scratch[ch * kScratchInts + 32 + lane] = sB;  // low-pass of node 96 + lane
-
-            // quantization.rs:13 — layer = level, except the last node of a level: level + 1
-            if (QS == kQuantSmallest) {
-                // only layers 8 and 9 are active and share one divisor: every level-8 node (the last one
-                // sits in layer 9) and the last node of level 7 (layer 8)
-                int r7 = b7[1];
-                if (qp.small & 0x100u) {
-                    const SmallDiv dv = qp.sdiv(8);
-#pragma unroll
-                    for (int m = 0; m < 4; ++m) { a8[m] = trunc_div_small(a8[m], dv); b8[m] = trunc_div_small(b8[m], dv); }
-                    r7 = trunc_div_small(r7, dv);
-                } else {
-                    const Div dv = qp.div(8);
-#pragma unroll
-                    for (int m = 0; m < 4; ++m) { a8[m] = trunc_div(a8[m], dv); b8[m] = trunc_div(b8[m], dv); }
-                    r7 = trunc_div(r7, dv);
-                }
-                if (lane == 31) b7[1] = r7;
-            } else if (QS == kQuantGeneric && ((qp.active >> (top + 6)) & 0xfu)) {
-                const int r8 = b8[3], r7 = b7[1], r6 = b6;  // unquantized values of the level-last nodes
-#define FRI_QLEVEL(L, N, A, B)                                                              \
-                if ((qp.active >> (top + (L))) & 1u) {                                              \
-                    if ((qp.small >> (top + (L))) & 1u) {                                           \
-                        const SmallDiv dv = qp.sdiv(top + (L));                                     \
-                        _Pragma("unroll") for (int m = 0; m < (N); ++m) { A[m] = trunc_div_small(A[m], dv); B[m] = trunc_div_small(B[m], dv); } \
-                    } else {                                                                        \
-                        const Div dv = qp.div(top + (L));                                           \
-                        _Pragma("unroll") for (int m = 0; m < (N); ++m) { A[m] = trunc_div(A[m], dv); B[m] = trunc_div(B[m], dv); } \
-                    }                                                                               \
-                }
-                int a6v[1] = {a6}, b6v[1] = {b6};
-                FRI_QLEVEL(8, 4, a8, b8)
-                FRI_QLEVEL(7, 2, a7, b7)
-                FRI_QLEVEL(6, 1, a6v, b6v)
-#undef FRI_QLEVEL
-                a6 = a6v[0];
-                b6 = b6v[0];
-                if (lastB && ((qp.fix >> (top + 6)) & 7u)) {  // only where the next layer's divisor differs
-                    if ((qp.fix >> (top + 8)) & 1u) b8[3] = quant_layer_enc(qp, r8, top + 9);
-                    if ((qp.fix >> (top + 7)) & 1u) b7[1] = quant_layer_enc(qp, r7, top + 8);
-                    if ((qp.fix >> (top + 6)) & 1u) b6 = quant_layer_enc(qp, r6, top + 7);
-                }
-            }
-            CT *out = coefs + ta.block + ((int64_t)ch << depth);
-            CT *o8 = out + ((size_t)ta.node << 8), *o7 = out + ((size_t)ta.node << 7), *o6 = out + ((size_t)ta.node << 6);
-            st_c4(o8 + 4 * lane, make_int4(a8[0], a8[1], a8[2], a8[3]));
-            st_c4(o8 + 128 + 4 * lane, make_int4(b8[0], b8[1], b8[2], b8[3]));
-            st_c2(o7 + 2 * lane, make_int2(a7[0], a7[1]));
-            st_c2(o7 + 64 + 2 * lane, make_int2(b7[0], b7[1]));
-            st_c1(o6 + lane, a6);
-            st_c1(o6 + 32 + lane, b6);
-        }
+        for (int ch = 0; ch < C; ++ch)
+            enc_register_levels<S, PB, DEEP, QS, CT>(g, qp, t0 + ch * SB, half, lane, lastB, top, scratch + ch * kScratchInts,
+                                                     coefs + ta.block + ((int64_t)ch << depth), ta.node);
         __syncwarp();
-
         // ---- phase 2: levels 5..0 of all channels, 8 lanes per channel
-        {
-            const int32_t *sp = scratch + grp * kScratchInts + 8 * j8;
-            const int4 x0 = *reinterpret_cast<const int4 *>(sp), x1 = *reinterpret_cast<const int4 *>(sp + 4);
-            int d5[4], s5[4], d4[2], s4[2], d3, d2, d1, d0, s3, s2, s1, s0;
-            lift(x0.x, x0.y, d5[0], s5[0]);
-            lift(x0.z, x0.w, d5[1], s5[1]);
-            lift(x1.x, x1.y, d5[2], s5[2]);
-            lift(x1.z, x1.w, d5[3], s5[3]);
-            lift(s5[0], s5[1], d4[0], s4[0]);
-            lift(s5[2], s5[3], d4[1], s4[1]);
-            lift(s4[0], s4[1], d3, s3);
-            lift(s3, __shfl_xor_sync(0xffffffffu, s3, 1), d2, s2);  // meaningful in lanes j8 % 2 == 0
-            lift(s2, __shfl_xor_sync(0xffffffffu, s2, 2), d1, s1);  // j8 % 4 == 0
-            lift(s1, __shfl_xor_sync(0xffffffffu, s1, 4), d0, s0);  // j8 == 0
-            if ((qp.active >> top) & 0x7fu) {
-                // level-L nodes sit in layer top + L, the level's last node in layer top + L + 1
-                const bool lastG = ta.last && j8 == 7;
-                d5[0] = quant_layer_enc(qp, d5[0], top + 5); d5[1] = quant_layer_enc(qp, d5[1], top + 5);
-                d5[2] = quant_layer_enc(qp, d5[2], top + 5); d5[3] = quant_layer_enc(qp, d5[3], top + (lastG ? 6 : 5));
-                d4[0] = quant_layer_enc(qp, d4[0], top + 4); d4[1] = quant_layer_enc(qp, d4[1], top + (lastG ? 5 : 4));
-                d3 = quant_layer_enc(qp, d3, top + (lastG ? 4 : 3));
-                d2 = quant_layer_enc(qp, d2, top + ((ta.last && j8 == 6) ? 3 : 2));
-                d1 = quant_layer_enc(qp, d1, top + ((ta.last && j8 == 4) ? 2 : 1));
-                if (sub_bits == 0) {
-                    d0 = quant_layer_enc(qp, d0, 1);  // position 1 is the last node of level 0
-                    s0 = quant_layer_enc(qp, s0, 0);  // position 0: the low-pass root (wavelet_transform.rs:221)
-                } else {
-                    d0 = quant_layer_enc(qp, d0, top + (ta.last ? 1 : 0));
-                }
-            }
-            if (grp_live) {
-                CT *out = coefs + ta.block + ((int64_t)grp << depth);
-                const size_t node = ta.node;
-                st_c4(out + (node << 5) + 4 * j8, make_int4(d5[0], d5[1], d5[2], d5[3]));
-                st_c2(out + (node << 4) + 2 * j8, make_int2(d4[0], d4[1]));
-                st_c1(out + (node << 3) + j8, d3);
-                if ((j8 & 1) == 0) st_c1(out + (node << 2) + (j8 >> 1), d2);
-                if ((j8 & 3) == 0) st_c1(out + (node << 1) + (j8 >> 2), d1);
-                if (j8 == 0) {
-                    st_c1(out + node, d0);
-                    if (sub_bits == 0) st_c1(out, s0);
-                    else dc_out[ta.dc + ((int64_t)grp << sub_bits)] = s0;
-                }
-            }
-        }
+        enc_top_levels<DEEP, CT>(qp, scratch + grp * kScratchInts + 8 * j8, ta, j8, top, sub_bits, grp_live,
+                                 coefs + ta.block + ((int64_t)grp << depth),
+                                 DEEP ? dc_out + ta.dc + ((int64_t)grp << sub_bits) : nullptr);
         __syncwarp();
     }
 }
@@ -677,8 +727,8 @@ __device__ __forceinline__ void prefetch_group_coefs(const Geometry &g, const Gr
         asm volatile("prefetch.global.L2 [%0];" ::"l"(first + (size_t)i * 128));
 }
 
-#ifndef FRI_DEC_NEXT_TILE
-#define FRI_DEC_NEXT_TILE 1
+#ifndef FRI_WHATIF_NOWAIT
+#define FRI_WHATIF_NOWAIT 0
 #endif
 // The coefficients of levels 6..8 a lane consumes for one (tile, channel): 2 x 128, 2 x 64, 2 x 32 bits.
 struct LaneCoefs {
@@ -723,10 +773,150 @@ __device__ __forceinline__ TopCoefs load_top_coefs(const CT *__restrict__ coefs,
     return t;
 }
 
-// Dequantization + inverse transform of the tiles of one group into the staged region; mirror
-// image of encode_tiles: lane group lane / 8 first unfolds levels 0..5 of its channel (lane j
-// ends with the eight level-6 low-pass values 8j .. 8j+7) into the warp's scratch, then every
-// lane unfolds its two depth-3 subtrees per channel and scatters the 16 clamped leaves.
+// ---- dequantization + inverse transform, building blocks
+//
+// Levels 0..5 of one (base tile, channel) by the 8 lanes of a lane group: each lane walks its own
+// root-to-subtree path and ends with the eight level-6 low-pass values 8 j8 .. 8 j8 + 7, stored to sp[0..7].
+template <bool DEEP>
+__device__ __forceinline__ void dec_top_levels(const QuantParams &qp, const TopCoefs &tc, const TaskAddr &ta, int j8, int top,
+                                               int sub_bits, bool live, int32_t *sp)
+{
+    int4 d5 = tc.d5;
+    int2 d4 = tc.d4;
+    int d3 = tc.d3, d2 = tc.d2, d1 = tc.d1, d0 = tc.d0, s0 = tc.s0;
+    if ((qp.active >> top) & 0x7fu) {
+        const bool lastG = ta.last && j8 == 7;
+        d5.x = dequant_layer(qp, d5.x, top + 5); d5.y = dequant_layer(qp, d5.y, top + 5);
+        d5.z = dequant_layer(qp, d5.z, top + 5); d5.w = dequant_layer(qp, d5.w, top + (lastG ? 6 : 5));
+        d4.x = dequant_layer(qp, d4.x, top + 4); d4.y = dequant_layer(qp, d4.y, top + (lastG ? 5 : 4));
+        d3 = dequant_layer(qp, d3, top + (lastG ? 4 : 3));
+        d2 = dequant_layer(qp, d2, top + ((ta.last && (j8 >> 1) == 3) ? 3 : 2));
+        d1 = dequant_layer(qp, d1, top + ((ta.last && (j8 >> 2) == 1) ? 2 : 1));
+        if (sub_bits == 0) {
+            d0 = dequant_layer(qp, d0, 1);
+            s0 = dequant_layer(qp, s0, 0);
+        } else {
+            d0 = dequant_layer(qp, d0, top + (ta.last ? 1 : 0));  // s0 was dequantized by the coarse kernel
+        }
+    }
+    int l, r, s;
+    unlift(s0, d0, l, r); s = (j8 & 4) ? r : l;
+    unlift(s, d1, l, r);  s = (j8 & 2) ? r : l;
+    unlift(s, d2, l, r);  s = (j8 & 1) ? r : l;
+    int s4[2], s5[4];
+    int4 x0, x1;
+    unlift(s, d3, s4[0], s4[1]);
+    unlift(s4[0], d4.x, s5[0], s5[1]);
+    unlift(s4[1], d4.y, s5[2], s5[3]);
+    unlift(s5[0], d5.x, x0.x, x0.y);
+    unlift(s5[1], d5.y, x0.z, x0.w);
+    unlift(s5[2], d5.z, x1.x, x1.y);
+    unlift(s5[3], d5.w, x1.z, x1.w);
+    if (live) {
+        *reinterpret_cast<int4 *>(sp) = x0;
+        *reinterpret_cast<int4 *>(sp + 4) = x1;
+    }
+}
+
+// Register levels of one (base tile, channel): dequantize the lane's 2 x 128 + 2 x 64 + 2 x 32 bit
+// coefficient runs, unfold levels 6..8 of its two depth-3 subtrees from the level-6 low-pass values sA, sB
+// and scatter the 16 clamped leaves into the staged region (p0: shared-memory address of the lane's first
+// leaf of this channel).
+template <typename S, int PB, bool DEEP, int QS>
+__device__ __forceinline__ void dec_register_levels(const Geometry &g, const QuantParams &qp, const LaneCoefs &c, int sA, int sB,
+                                                    int lane, bool lastB, int top, uint32_t p0, int half)
+{
+    int4 a8 = c.a8, b8 = c.b8;
+    int2 a7 = c.a7, b7 = c.b7;
+    int a6 = c.a6, b6 = c.b6;
+    if (QS == kQuantSmallest) {
+        // only layers 8 and 9 are active and share one divisor (see enc_register_levels)
+        int r7 = b7.y;
+#define FRI_DQ8                                                                \
+        a8.x = f(a8.x); a8.y = f(a8.y); a8.z = f(a8.z); a8.w = f(a8.w);             \
+        b8.x = f(b8.x); b8.y = f(b8.y); b8.z = f(b8.z); b8.w = f(b8.w); r7 = f(r7);
+        if (qp.multiply) {
+            const unsigned q = (unsigned)qp.q[8];
+            auto f = [q](int x) { return (int)((unsigned)x * q); };
+            FRI_DQ8
+        } else if (qp.pow2 & 0x100u) {
+            const int k = qp.pow2_shift[8];
+            auto f = [k](int x) { return trunc_div_pow2(x, k); };
+            FRI_DQ8
+        } else {
+            const Div dv = qp.div(8);
+            auto f = [dv](int x) { return trunc_div(x, dv); };
+            FRI_DQ8
+        }
+#undef FRI_DQ8
+        if (lane == 31) b7.y = r7;
+    } else if (QS == kQuantGeneric && ((qp.active >> (top + 6)) & 0xfu)) {
+        const int r8 = b8.w, r7 = b7.y, r6 = b6;  // raw values of the level-last nodes
+        const int mul = qp.multiply;
+#define FRI_DQLEVEL(L, STMTS)                                                       \
+        if ((qp.active >> (top + (L))) & 1u) {                                              \
+            if (mul) {                                                                      \
+                const unsigned q = (unsigned)qp.q[top + (L)];                               \
+                auto f = [q](int x) { return (int)((unsigned)x * q); };                     \
+                STMTS                                                                       \
+            } else if ((qp.pow2 >> (top + (L))) & 1u) {                                     \
+                const int k = qp.pow2_shift[top + (L)];                                     \
+                auto f = [k](int x) { return trunc_div_pow2(x, k); };                       \
+                STMTS                                                                       \
+            } else {                                                                        \
+                const Div dv = qp.div(top + (L));                                           \
+                auto f = [dv](int x) { return trunc_div(x, dv); };                          \
+                STMTS                                                                       \
+            }                                                                               \
+        }
+        FRI_DQLEVEL(8, a8.x = f(a8.x); a8.y = f(a8.y); a8.z = f(a8.z); a8.w = f(a8.w);
+                       b8.x = f(b8.x); b8.y = f(b8.y); b8.z = f(b8.z); b8.w = f(b8.w);)
+        FRI_DQLEVEL(7, a7.x = f(a7.x); a7.y = f(a7.y); b7.x = f(b7.x); b7.y = f(b7.y);)
+        FRI_DQLEVEL(6, a6 = f(a6); b6 = f(b6);)
+#undef FRI_DQLEVEL
+        if (lastB && ((qp.fix >> (top + 6)) & 7u)) {  // only where the next layer's divisor differs
+            if ((qp.fix >> (top + 8)) & 1u) b8.w = dequant_layer(qp, r8, top + 9);
+            if ((qp.fix >> (top + 7)) & 1u) b7.y = dequant_layer(qp, r7, top + 8);
+            if ((qp.fix >> (top + 6)) & 1u) b6 = dequant_layer(qp, r6, top + 7);
+        }
+    }
+
+    // levels 6, 7, 8 in registers
+    int sa7[2], sb7[2], sa8[4], sb8[4], v[8], w[8];
+    unlift(sA, a6, sa7[0], sa7[1]);
+    unlift(sB, b6, sb7[0], sb7[1]);
+    unlift(sa7[0], a7.x, sa8[0], sa8[1]);
+    unlift(sa7[1], a7.y, sa8[2], sa8[3]);
+    unlift(sb7[0], b7.x, sb8[0], sb8[1]);
+    unlift(sb7[1], b7.y, sb8[2], sb8[3]);
+    unlift(sa8[0], a8.x, v[0], v[1]);
+    unlift(sa8[1], a8.y, v[2], v[3]);
+    unlift(sa8[2], a8.z, v[4], v[5]);
+    unlift(sa8[3], a8.w, v[6], v[7]);
+    unlift(sb8[0], b8.x, w[0], w[1]);
+    unlift(sb8[1], b8.y, w[2], w[3]);
+    unlift(sb8[2], b8.z, w[4], w[5]);
+    unlift(sb8[3], b8.w, w[6], w[7]);
+
+    // scatter into the staged region (clamp: images.rs:109)
+    const uint32_t p1 = p0 + g.pitch, p2 = p1 + g.pitch;
+#define FRI_ST(ptr, dx, val) store_clamped<S>((uint32_t)((int)(ptr) + (dx) * PB), (val))
+    FRI_ST(p0, 0, v[0]);  FRI_ST(p1, 0, v[1]);
+    FRI_ST(p1, -1, v[2]); FRI_ST(p2, -1, v[3]);
+    FRI_ST(p0, 2, v[4]);  FRI_ST(p1, 2, v[5]);
+    FRI_ST(p1, 1, v[6]);  FRI_ST(p2, 1, v[7]);
+    FRI_ST(p0 + half, 0, w[0]);  FRI_ST(p1 + half, 0, w[1]);
+    FRI_ST(p1 + half, -1, w[2]); FRI_ST(p2 + half, -1, w[3]);
+    FRI_ST(p0 + half, 2, w[4]);  FRI_ST(p1 + half, 2, w[5]);
+    FRI_ST(p1 + half, 1, w[6]);  FRI_ST(p2 + half, 1, w[7]);
+#undef FRI_ST
+}
+
+// Dequantization + inverse transform of the tiles of one group into the staged region; mirror image of
+// encode_tiles: lane group lane / 8 first unfolds levels 0..5 of its channel (C == 3) or of its tile of a
+// batch of up to four (C == 1) into the warp's scratch, then every lane unfolds its two depth-3 subtrees per
+// (tile, channel) and scatters the 16 clamped leaves.  The register-level coefficient loads are
+// software-pipelined one (tile, channel) ahead.
 template <int C, typename S, bool DEEP, int QS, typename CT>
 __device__ __forceinline__ void decode_tiles(const Geometry &g, const QuantParams &qp, const GroupDesc &gd, const RegionView &rv,
                                              const uint32_t *__restrict__ tile_unit, int frame, uint8_t *region,
@@ -742,8 +932,7 @@ __device__ __forceinline__ void decode_tiles(const Geometry &g, const QuantParam
     const int sub_bits = DEEP ? g.sub_bits : 0, depth = DEEP ? g.depth : kBaseDepth;
     const int top = sub_bits;
     const bool sparse_group = (gd.tile_mask & (gd.tile_mask + 1u)) != 0;
-    const int grp = min(lane >> 3, C - 1), j8 = lane & 7;
-    const bool grp_live = (lane >> 3) < C;
+    const int grp = min(lane >> 3, scratch_units(C) - 1), j8 = lane & 7;
     // The first channel's register-level coefficients of a tile are requested ahead of time: for the
     // warp's first tile before the top levels are unfolded (one round trip to L2/HBM covers both),
     // for every later tile while the previous tile's last channel is being unfolded.
@@ -753,6 +942,35 @@ __device__ __forceinline__ void decode_tiles(const Geometry &g, const QuantParam
         ta = task_addr<C, DEEP>(g, tile_unit, frame, gd.tile_base + warp, 0);
         cur = load_lane_coefs(coefs + ta.block, ta.node, lane);
     }
+    if (C == 1) {
+        for (int e0 = warp; e0 < n_present; e0 += kTileBatch * n_warps) {
+            {   // ---- levels 0..5 of up to four tiles, 8 lanes per tile
+                const int eg = e0 + grp * n_warps;
+                const bool live = eg < n_present;
+                const TaskAddr tg = task_addr<C, DEEP>(g, tile_unit, frame, gd.tile_base + (live ? eg : e0), 0);
+                const TopCoefs tc = load_top_coefs<DEEP, CT>(coefs, dc_in, tg, 0, j8, depth, sub_bits);
+                dec_top_levels<DEEP>(qp, tc, tg, j8, top, sub_bits, live, scratch + grp * kScratchInts + 8 * j8);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < kTileBatch; ++k) {
+                const int e = e0 + k * n_warps;
+                if (e >= n_present) break;
+                const int slot = sparse_group ? (int)__fns(gd.tile_mask, 0, e + 1) : e;
+                const bool has_next = e + n_warps < n_present;
+                const TaskAddr tn = has_next ? task_addr<C, DEEP>(g, tile_unit, frame, gd.tile_base + e + n_warps, 0) : ta;
+                const LaneCoefs c = cur;
+                if (has_next) cur = load_lane_coefs(coefs + tn.block, tn.node, lane);
+                const int sA = scratch[k * kScratchInts + lane], sB = scratch[k * kScratchInts + 32 + lane];
+                dec_register_levels<S, PB, DEEP, QS>(g, qp, c, sA, sB, lane, ta.last && lane == 31, top,
+                                                     lane_base + g.tile_off[slot], half);
+                ta = tn;
+            }
+            __syncwarp();
+        }
+        return;
+    }
+    const bool grp_live = (lane >> 3) < C;
     for (int e = warp; e < n_present; e += n_warps) {
         const int slot = sparse_group ? (int)__fns(gd.tile_mask, 0, e + 1) : e;
         const bool has_next = e + n_warps < n_present;
@@ -763,144 +981,21 @@ __device__ __forceinline__ void decode_tiles(const Geometry &g, const QuantParam
         // ---- levels 0..5 of all channels, 8 lanes per channel
         {
             const TopCoefs tc = load_top_coefs<DEEP, CT>(coefs, dc_in, ta, grp, j8, depth, sub_bits);
-            int4 d5 = tc.d5;
-            int2 d4 = tc.d4;
-            int d3 = tc.d3, d2 = tc.d2, d1 = tc.d1, d0 = tc.d0, s0 = tc.s0;
-            if ((qp.active >> top) & 0x7fu) {
-                const bool lastG = ta.last && j8 == 7;
-                d5.x = dequant_layer(qp, d5.x, top + 5); d5.y = dequant_layer(qp, d5.y, top + 5);
-                d5.z = dequant_layer(qp, d5.z, top + 5); d5.w = dequant_layer(qp, d5.w, top + (lastG ? 6 : 5));
-                d4.x = dequant_layer(qp, d4.x, top + 4); d4.y = dequant_layer(qp, d4.y, top + (lastG ? 5 : 4));
-                d3 = dequant_layer(qp, d3, top + (lastG ? 4 : 3));
-                d2 = dequant_layer(qp, d2, top + ((ta.last && (j8 >> 1) == 3) ? 3 : 2));
-                d1 = dequant_layer(qp, d1, top + ((ta.last && (j8 >> 2) == 1) ? 2 : 1));
-                if (sub_bits == 0) {
-                    d0 = dequant_layer(qp, d0, 1);
-                    s0 = dequant_layer(qp, s0, 0);
-                } else {
-                    d0 = dequant_layer(qp, d0, top + (ta.last ? 1 : 0));  // s0 was dequantized by the coarse kernel
-                }
-            }
-            int l, r, s;
-            unlift(s0, d0, l, r); s = (j8 & 4) ? r : l;
-            unlift(s, d1, l, r);  s = (j8 & 2) ? r : l;
-            unlift(s, d2, l, r);  s = (j8 & 1) ? r : l;
-            int s4[2], s5[4];
-            int4 x0, x1;
-            unlift(s, d3, s4[0], s4[1]);
-            unlift(s4[0], d4.x, s5[0], s5[1]);
-            unlift(s4[1], d4.y, s5[2], s5[3]);
-            unlift(s5[0], d5.x, x0.x, x0.y);
-            unlift(s5[1], d5.y, x0.z, x0.w);
-            unlift(s5[2], d5.z, x1.x, x1.y);
-            unlift(s5[3], d5.w, x1.z, x1.w);
-            if (grp_live) {
-                int32_t *sp = scratch + grp * kScratchInts + 8 * j8;
-                *reinterpret_cast<int4 *>(sp) = x0;
-                *reinterpret_cast<int4 *>(sp + 4) = x1;
-            }
+            dec_top_levels<DEEP>(qp, tc, ta, j8, top, sub_bits, grp_live, scratch + grp * kScratchInts + 8 * j8);
         }
         __syncwarp();
 
         const uint32_t t0 = lane_base + g.tile_off[slot];
 #pragma unroll
         for (int ch = 0; ch < C; ++ch) {
-            int4 a8 = cur.a8, b8 = cur.b8;
-            int2 a7 = cur.a7, b7 = cur.b7;
-            int a6 = cur.a6, b6 = cur.b6;
+            const LaneCoefs c = cur;
             if (ch + 1 < C) cur = load_lane_coefs(coefs + ta.block + ((int64_t)(ch + 1) << depth), node, lane);
-#if FRI_DEC_NEXT_TILE
             else if (has_next) cur = load_lane_coefs(coefs + tn.block, tn.node, lane);
-#endif
             const int sA = scratch[ch * kScratchInts + lane], sB = scratch[ch * kScratchInts + 32 + lane];
-
-            if (QS == kQuantSmallest) {
-                // only layers 8 and 9 are active and share one divisor (see encode_tiles)
-                int r7 = b7.y;
-#define FRI_DQ8                                                                        \
-                a8.x = f(a8.x); a8.y = f(a8.y); a8.z = f(a8.z); a8.w = f(a8.w);             \
-                b8.x = f(b8.x); b8.y = f(b8.y); b8.z = f(b8.z); b8.w = f(b8.w); r7 = f(r7);
-                if (qp.multiply) {
-                    const unsigned q = (unsigned)qp.q[8];
-                    auto f = [q](int x) { return (int)((unsigned)x * q); };
-                    FRI_DQ8
-                } else if (qp.pow2 & 0x100u) {
-                    const int k = qp.pow2_shift[8];
-                    auto f = [k](int x) { return trunc_div_pow2(x, k); };
-                    FRI_DQ8
-                } else {
-                    const Div dv = qp.div(8);
-                    auto f = [dv](int x) { return trunc_div(x, dv); };
-                    FRI_DQ8
-                }
-#undef FRI_DQ8
-                if (lane == 31) b7.y = r7;
-            } else if (QS == kQuantGeneric && ((qp.active >> (top + 6)) & 0xfu)) {
-                const int r8 = b8.w, r7 = b7.y, r6 = b6;  // raw values of the level-last nodes
-                const int mul = qp.multiply;
-#define FRI_DQLEVEL(L, STMTS)                                                               \
-                if ((qp.active >> (top + (L))) & 1u) {                                              \
-                    if (mul) {                                                                      \
-                        const unsigned q = (unsigned)qp.q[top + (L)];                               \
-                        auto f = [q](int x) { return (int)((unsigned)x * q); };                     \
-                        STMTS                                                                       \
-                    } else if ((qp.pow2 >> (top + (L))) & 1u) {                                     \
-                        const int k = qp.pow2_shift[top + (L)];                                     \
-                        auto f = [k](int x) { return trunc_div_pow2(x, k); };                       \
-                        STMTS                                                                       \
-                    } else {                                                                        \
-                        const Div dv = qp.div(top + (L));                                           \
-                        auto f = [dv](int x) { return trunc_div(x, dv); };                          \
-                        STMTS                                                                       \
-                    }                                                                               \
-                }
-                FRI_DQLEVEL(8, a8.x = f(a8.x); a8.y = f(a8.y); a8.z = f(a8.z); a8.w = f(a8.w);
-                               b8.x = f(b8.x); b8.y = f(b8.y); b8.z = f(b8.z); b8.w = f(b8.w);)
-                FRI_DQLEVEL(7, a7.x = f(a7.x); a7.y = f(a7.y); b7.x = f(b7.x); b7.y = f(b7.y);)
-                FRI_DQLEVEL(6, a6 = f(a6); b6 = f(b6);)
-#undef FRI_DQLEVEL
-                if (lastB && ((qp.fix >> (top + 6)) & 7u)) {  // only where the next layer's divisor differs
-                    if ((qp.fix >> (top + 8)) & 1u) b8.w = dequant_layer(qp, r8, top + 9);
-                    if ((qp.fix >> (top + 7)) & 1u) b7.y = dequant_layer(qp, r7, top + 8);
-                    if ((qp.fix >> (top + 6)) & 1u) b6 = dequant_layer(qp, r6, top + 7);
-                }
-            }
-
-            // levels 6, 7, 8 in registers
-            int sa7[2], sb7[2], sa8[4], sb8[4], v[8], w[8];
-            unlift(sA, a6, sa7[0], sa7[1]);
-            unlift(sB, b6, sb7[0], sb7[1]);
-            unlift(sa7[0], a7.x, sa8[0], sa8[1]);
-            unlift(sa7[1], a7.y, sa8[2], sa8[3]);
-            unlift(sb7[0], b7.x, sb8[0], sb8[1]);
-            unlift(sb7[1], b7.y, sb8[2], sb8[3]);
-            unlift(sa8[0], a8.x, v[0], v[1]);
-            unlift(sa8[1], a8.y, v[2], v[3]);
-            unlift(sa8[2], a8.z, v[4], v[5]);
-            unlift(sa8[3], a8.w, v[6], v[7]);
-            unlift(sb8[0], b8.x, w[0], w[1]);
-            unlift(sb8[1], b8.y, w[2], w[3]);
-            unlift(sb8[2], b8.z, w[4], w[5]);
-            unlift(sb8[3], b8.w, w[6], w[7]);
-
-            // scatter into the staged region (clamp: images.rs:109)
-            const uint32_t p0 = t0 + ch * SB, p1 = p0 + g.pitch, p2 = p1 + g.pitch;
-#define FRI_ST(ptr, dx, val) store_clamped<S>((uint32_t)((int)(ptr) + (dx) * PB), (val))
-            FRI_ST(p0, 0, v[0]);  FRI_ST(p1, 0, v[1]);
-            FRI_ST(p1, -1, v[2]); FRI_ST(p2, -1, v[3]);
-            FRI_ST(p0, 2, v[4]);  FRI_ST(p1, 2, v[5]);
-            FRI_ST(p1, 1, v[6]);  FRI_ST(p2, 1, v[7]);
-            FRI_ST(p0 + half, 0, w[0]);  FRI_ST(p1 + half, 0, w[1]);
-            FRI_ST(p1 + half, -1, w[2]); FRI_ST(p2 + half, -1, w[3]);
-            FRI_ST(p0 + half, 2, w[4]);  FRI_ST(p1 + half, 2, w[5]);
-            FRI_ST(p1 + half, 1, w[6]);  FRI_ST(p2 + half, 1, w[7]);
-#undef FRI_ST
+            dec_register_levels<S, PB, DEEP, QS>(g, qp, c, sA, sB, lane, lastB, top, t0 + ch * SB, half);
         }
         __syncwarp();
         ta = tn;
-#if !FRI_DEC_NEXT_TILE
-        if (has_next) cur = load_lane_coefs(coefs + ta.block, ta.node, lane);
-#endif
     }
 }
 
@@ -944,12 +1039,15 @@ __device__ __forceinline__ WriteAhead write_out_preload(const Geometry &g, const
     WriteAhead w;
     const uint32_t *cl = chunk_list + (size_t)rv.phi0 * g.list_cap;
     const int n_full = g.list_full[rv.phi0];
-    // Slots past the end of the list repeat its last chunk (a redundant store of the same bytes)
-    // instead of being skipped: the unrolled stores then need no per-chunk test and branch.
+    // Slots past the end of the list inside the last used round repeat its last chunk (a redundant store of
+    // the same bytes) instead of being skipped: the unrolled stores then need no per-chunk test and branch.
+    // Whole rounds past the end (a 1-byte-per-pixel group has 883 full chunks for 6 x 256 slots) are skipped
+    // by a CTA-uniform test — they would all hit the same 16 bytes.
+    const int rounds = (n_full + (int)blockDim.x - 1) / (int)blockDim.x;
 #pragma unroll
     for (int u = 0; u < kWriteAhead; ++u) {
         const int k = min((int)(threadIdx.x + u * blockDim.x), n_full - 1);
-        w.e[u] = (rv.interior && n_full > 0) ? ld_table(cl + k, pol) : kNoChunk;
+        w.e[u] = (rv.interior && u < rounds) ? ld_table(cl + k, pol) : kNoChunk;
     }
     const uint16_t *cmk = chunk_mask + (size_t)rv.phi0 * g.list_cap;
     const int n_all = g.list_all[rv.phi0];
@@ -991,9 +1089,10 @@ __device__ __forceinline__ void write_out_group(const Geometry &g, const GroupDe
     const uint16_t *cmk = chunk_mask + (size_t)rv.phi0 * g.list_cap;
     const int n_full = g.list_full[rv.phi0], n_all = g.list_all[rv.phi0];
     if (rv.interior) {
-        if (n_full > 0) {
+        const int rounds = (n_full + n_threads - 1) / n_threads;
 #pragma unroll
-            for (int u = 0; u < kWriteAhead; ++u) {
+        for (int u = 0; u < kWriteAhead; ++u) {
+            if (u < rounds) {  // CTA-uniform
                 const int r = (int)(ahead.e[u] >> 16), s = (int)(ahead.e[u] & 0xffffu) << 4;
                 *reinterpret_cast<int4 *>(rv.gaddr(r, s)) = *reinterpret_cast<const int4 *>(region + s);
             }
@@ -1058,9 +1157,10 @@ fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
 {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *region = smem;
-    int32_t *scratch = reinterpret_cast<int32_t *>(smem + region_bytes(g)) + (threadIdx.x >> 5) * (C * kScratchInts);
+    int32_t *scratch = reinterpret_cast<int32_t *>(smem + region_bytes(g)) + (threadIdx.x >> 5) * (scratch_units(C) * kScratchInts);
     const uint64_t pol = table_policy();
     const GroupDesc gd = ld_group(groups + group_offset + blockIdx.x, pol);  // the grid covers groups [group_offset, + gridDim.x)
+    pdl_launch_dependents();
     const int frame = blockIdx.y;
     const RegionView rv = region_view<C * (int)sizeof(S)>(g, gd, pixels + (int64_t)frame * g.frame_bytes);
     FRI_TRACE_MARK(0);
@@ -1074,16 +1174,19 @@ fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
     // keep the chunk-list path, which clips and zero-fills.
     __shared__ __align__(8) uint64_t bars[2];
     const bool bulk = bulk_staging && rv.interior && g.n_rows_first > 0 && g.region_h <= (int)blockDim.x;
+    if (bulk && threadIdx.x == 0) {
+        mbar_init(&bars[0], two_stage ? g.n_rows_first : g.region_h);
+        mbar_init(&bars[1], max(1, g.region_h - g.n_rows_first));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+#if !FRI_WHATIF_NOWAIT
+    pdl_wait();  // the previous kernel of the stream may have written these pixels (or still read the coefficients)
+#endif
     if (bulk) {
         // only the warps that issue copies (thread r copies row r) wait for the barrier initialisation; the
         // others go straight on to the look-ahead and meet them at the CTA barrier before the wait
         const int issuing = (g.region_h + 31) & ~31;
         if ((int)threadIdx.x < issuing) {
-            if (threadIdx.x == 0) {
-                mbar_init(&bars[0], two_stage ? g.n_rows_first : g.region_h);
-                mbar_init(&bars[1], max(1, g.region_h - g.n_rows_first));
-                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            }
             asm volatile("bar.sync 1, %0;" ::"r"(issuing) : "memory");
             stage_rows_bulk(g, rv, region, bars, two_stage);
         }
@@ -1145,17 +1248,20 @@ fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
 {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *region = smem;
-    int32_t *scratch = reinterpret_cast<int32_t *>(smem + region_bytes(g)) + (threadIdx.x >> 5) * (C * kScratchInts);
+    int32_t *scratch = reinterpret_cast<int32_t *>(smem + region_bytes(g)) + (threadIdx.x >> 5) * (scratch_units(C) * kScratchInts);
     const uint64_t pol = table_policy();
     const GroupDesc gd = ld_group(groups + group_offset + blockIdx.x, pol);
+    pdl_launch_dependents();
     const int frame = blockIdx.y;
     const RegionView rv = region_view<C * (int)sizeof(S)>(g, gd, pixels + (int64_t)frame * g.frame_bytes);
     FRI_TRACE_MARK(0);
+    const bool sparse = __popc(gd.tile_mask) != g.group_a * g.group_b;
+    if (sparse) zero_region(g, region);
+#if !FRI_WHATIF_NOWAIT
+    pdl_wait();  // the previous kernel of the stream may have produced these coefficients (or still read the pixels)
+#endif
     if ((int64_t)blockIdx.y * gridDim.x + blockIdx.x >= no_prefetch_ctas) prefetch_group_coefs<C, DEEP, CT>(g, gd, frame, coefs);
-    if (__popc(gd.tile_mask) != g.group_a * g.group_b) {
-        zero_region(g, region);
-        __syncthreads();
-    }
+    if (sparse) __syncthreads();
     decode_tiles<C, S, DEEP, QS, CT>(g, qp, gd, rv, tile_unit, frame, region, scratch, coefs, dc_in);
     const WriteAhead ahead = write_out_preload(g, rv, chunk_list, chunk_mask, pol);
     __syncthreads();
@@ -1342,6 +1448,27 @@ fri_unpack16_kernel(const int4 *__restrict__ src, int4 *__restrict__ dst, size_t
     }
 }
 
+// Launch with the programmatic-stream-serialization attribute (see pdl_wait): FRI_PDL=0 turns it off.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, int threads, size_t smem, cudaStream_t stream, Args &&...args)
+{
+    static const bool enabled = [] {
+        const char *env = std::getenv("FRI_PDL");
+        return !env || std::atoi(env) != 0;
+    }();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = enabled ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 template <typename K>
 cudaError_t set_smem(K kernel, size_t bytes)
 {
@@ -1444,8 +1571,9 @@ cudaError_t launch_encode(const Geometry &g, const DeviceTables &t, const QuantP
         int32_t *c = d_coefs + (int64_t)f0 * g.coefs_per_frame;
         int16_t *c16 = d_coefs16 + (int64_t)f0 * g.coefs_per_frame;
         int32_t *dc = d_dc ? d_dc + (((int64_t)f0 * g.n_fractals * g.channels) << g.sub_bits) : nullptr;
+        cudaError_t launch_err = cudaSuccess;
 #define FRI_LAUNCH_Q(CC, SS, DD, QQ, TT, PTR) \
-    fri_encode_kernel<CC, SS, DD, QQ, TT><<<grid, cta_threads(g), smem, stream>>>(g, qp, gtab, t.tile_unit, t.stage_list, p, PTR, dc, lookahead, group_begin, bulk_staging, late_look_ctas)
+    launch_err = launch_pdl(fri_encode_kernel<CC, SS, DD, QQ, TT>, grid, cta_threads(g), smem, stream, g, qp, gtab, t.tile_unit, t.stage_list, p, PTR, dc, lookahead, group_begin, bulk_staging, late_look_ctas)
 #define FRI_LAUNCH(CC, SS, TT, PTR)                                                           \
         do {                                                                                  \
             if (qclass == kQuantNone) FRI_LAUNCH_Q(CC, SS, false, kQuantNone, TT, PTR);       \
@@ -1466,6 +1594,7 @@ cudaError_t launch_encode(const Geometry &g, const DeviceTables &t, const QuantP
         else FRI_LAUNCH(3, uint16_t, int32_t, c);
 #undef FRI_LAUNCH
 #undef FRI_LAUNCH_Q
+        if (launch_err != cudaSuccess) return launch_err;
         if (launches) ++*launches;
     }
     if (g.sub_bits > 0 && group_end == g.n_groups) {  // after the last band
@@ -1509,8 +1638,9 @@ cudaError_t launch_decode(const Geometry &g, const DeviceTables &t, const QuantP
         const int32_t *c = d_coefs + (int64_t)f0 * g.coefs_per_frame;
         const int16_t *c16 = d_coefs16 + (int64_t)f0 * g.coefs_per_frame;
         int32_t *dc = d_dc ? d_dc + (((int64_t)f0 * g.n_fractals * g.channels) << g.sub_bits) : nullptr;
+        cudaError_t launch_err = cudaSuccess;
 #define FRI_LAUNCH_Q(CC, SS, DD, QQ, TT, PTR) \
-    fri_decode_kernel<CC, SS, DD, QQ, TT><<<grid, cta_threads(g), smem, stream>>>(g, qp, gtab, t.tile_unit, t.chunk_list, t.chunk_mask, PTR, dc, p, group_begin, no_prefetch_ctas)
+    launch_err = launch_pdl(fri_decode_kernel<CC, SS, DD, QQ, TT>, grid, cta_threads(g), smem, stream, g, qp, gtab, t.tile_unit, t.chunk_list, t.chunk_mask, PTR, dc, p, group_begin, no_prefetch_ctas)
 #define FRI_LAUNCH(CC, SS, TT, PTR)                                                           \
         do {                                                                                  \
             if (qclass == kQuantNone) FRI_LAUNCH_Q(CC, SS, false, kQuantNone, TT, PTR);       \
@@ -1531,6 +1661,7 @@ cudaError_t launch_decode(const Geometry &g, const DeviceTables &t, const QuantP
         else FRI_LAUNCH(3, uint16_t, int32_t, c);
 #undef FRI_LAUNCH
 #undef FRI_LAUNCH_Q
+        if (launch_err != cudaSuccess) return launch_err;
         if (launches) ++*launches;
     }
     return cudaGetLastError();

@@ -88,7 +88,11 @@ void make_quant_params(QuantParams &qp, const int32_t *q, int multiply);
 constexpr int kThreads = FRI_MAX_THREADS;  // upper bound on threads per CTA (launch bounds)
 constexpr int kMaxWarps = kThreads / 32;
 int cta_threads(const Geometry &g);  // threads per CTA for a plan: one warp per two base tiles of a full group
-constexpr int kScratchInts = 64;    // per warp and channel: the 64 level-6 low-pass values of a base tile
+constexpr int kScratchInts = 64;    // per warp and scratch unit: the 64 level-6 low-pass values of a (base tile, channel)
+// Scratch units per warp: one per channel, or — 1-channel images — one per tile of the batch of kTileBatch
+// tiles whose top levels are folded together (encode_tiles / decode_tiles in fri_kernels.cu).
+constexpr int kTileBatch = 4;
+FRI_HDI constexpr int scratch_units(int channels) { return channels == 1 ? kTileBatch : channels; }
 
 size_t kernel_smem_bytes(const Geometry &g);
 

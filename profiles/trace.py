@@ -8,7 +8,7 @@ from frave_b200 import capi
 L = C.CDLL(os.environ["FRI_CUDA_LIB"])
 L.fri_debug_trace.argtypes = [C.c_void_p, C.c_size_t]
 dev = torch.device("cuda", 0)
-W, H, Cc = 4096, 4096, 3
+W, H, Cc = (int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "4096x4096x3").split("x"))
 plan = capi.Plan(W, H, Cc)
 n = plan.launch_info()["n_groups"]
 px = torch.randint(0, 256, (H, W, Cc), device=dev, dtype=torch.int32).to(torch.uint8)
