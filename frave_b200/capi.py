@@ -54,6 +54,11 @@ _SYMBOLS = [
     ("fri_unemit_device16", C.c_int, [_P, _P, C.c_uint32, _P, _P]),
     ("fri_decode_tq_emit", C.c_int, [_P, _P, C.c_uint32, _P, C.c_int, _P]),
     ("fri_decode_tq_emit16", C.c_int, [_P, _P, C.c_uint32, _P, C.c_int, _P]),
+    ("fri_plan_emission_packed_bytes", C.c_uint64, [_P]),
+    ("fri_emit_device10", C.c_int, [_P, _P, C.c_uint32, _P, _P]),
+    ("fri_encode_tq_emit10", C.c_int, [_P, _P, C.c_uint32, _P, _P]),
+    ("fri_unemit_device10", C.c_int, [_P, _P, C.c_uint32, _P, _P]),
+    ("fri_decode_tq_emit10", C.c_int, [_P, _P, C.c_uint32, _P, C.c_int, _P]),
     ("fri_host_alloc", C.c_int, [C.POINTER(_P), C.c_size_t]),
     ("fri_host_free", None, [_P]),
     ("fri_plan_last_launches", C.c_uint32, [_P]),
@@ -111,6 +116,33 @@ def device_count() -> int:
 def quant_divide(value: int, q: int) -> int:
     """value / q with the kernels' multiply-high division routine (host evaluation, for tests)."""
     return int(lib().fri_quant_divide(int(value), int(q)))
+
+
+def pack10(values: np.ndarray) -> np.ndarray:
+    """Host restatement of the 10-bit packed transport for tests: int stream [..., n] -> uint8 [..., 80 * ceil(n / 64)]
+    (zig-zag pack_signed of utils.rs:34-40, 64 symbols per 80-byte block, little-endian bit order, zero padding)."""
+    v = np.asarray(values).astype(np.int64)
+    n = v.shape[-1]
+    pad = (-n) % 64
+    v = np.clip(v, -512, 511)
+    sym = np.where(v >= 0, 2 * v, -2 * v - 1).astype(np.uint64)
+    sym = np.concatenate([sym, np.zeros(v.shape[:-1] + (pad,), np.uint64)], axis=-1)
+    g = sym.reshape(v.shape[:-1] + (-1, 4))
+    word = g[..., 0] | g[..., 1] << np.uint64(10) | g[..., 2] << np.uint64(20) | g[..., 3] << np.uint64(30)
+    out = np.empty(word.shape + (5,), np.uint8)
+    for b in range(5):
+        out[..., b] = (word >> np.uint64(8 * b)) & np.uint64(0xff)
+    return out.reshape(v.shape[:-1] + (-1,))
+
+
+def unpack10(packed: np.ndarray, n: int) -> np.ndarray:
+    """Inverse of pack10: uint8 [..., 80 * ceil(n / 64)] -> int32 [..., n] (unpack_signed, utils.rs:42-48)."""
+    p = np.asarray(packed, dtype=np.uint8)
+    g = p.reshape(p.shape[:-1] + (-1, 5)).astype(np.uint64)
+    word = sum(g[..., b] << np.uint64(8 * b) for b in range(5))
+    sym = np.stack([(word >> np.uint64(10 * i)) & np.uint64(1023) for i in range(4)], axis=-1).reshape(p.shape[:-1] + (-1,))
+    sym = sym[..., :n].astype(np.int64)
+    return np.where(sym % 2 == 0, sym // 2, -((sym + 1) // 2)).astype(np.int32)
 
 
 def _q_array(q):
@@ -283,6 +315,46 @@ class Plan:
         if n == 0 and self.n_tiles:
             _check(lib().fri_plan_emission_order(self._h, np.empty(self.n_tiles << self.depth, np.uint32).ctypes.data))
         return n
+
+    def emission_packed_bytes(self) -> int:
+        """Bytes of one channel's stream in the 10-bit packed transport (80 bytes per 64 symbols)."""
+        self.emission_count()
+        return int(lib().fri_plan_emission_packed_bytes(self._h))
+
+    def encode_emit10(self, pixels: np.ndarray, q=None, out: np.ndarray | None = None) -> np.ndarray:
+        """HWC pixels [F, H, W, C] -> uint8 [F, C, emission_packed_bytes()]: emission-ordered streams in the
+        10-bit packed transport (fri_encode_tq_emit10); unpack10() gives the coefficients back."""
+        px, n = self._frames(pixels)
+        nb = self.emission_packed_bytes()
+        if out is None:
+            out = np.empty((n, self.channels, nb), np.uint8)
+        assert out.dtype == np.uint8 and out.flags.c_contiguous and out.shape == (n, self.channels, nb)
+        qa, qp = _q_array(q)
+        _check(lib().fri_encode_tq_emit10(self._h, px.ctypes.data, n, qp, out.ctypes.data))
+        return out
+
+    def decode_emit10(self, packed: np.ndarray, q=None, multiply: bool = False, out: np.ndarray | None = None) -> np.ndarray:
+        """uint8 [F, C, emission_packed_bytes()] packed streams -> HWC pixels [F, H, W, C] (fri_decode_tq_emit10)."""
+        pk = np.ascontiguousarray(packed, dtype=np.uint8)
+        nb = self.emission_packed_bytes()
+        if pk.shape == (self.channels, nb):
+            pk = pk[None]
+        if pk.ndim != 3 or pk.shape[1:] != (self.channels, nb):
+            raise ValueError(f"packed streams must have shape [F, {self.channels}, {nb}]")
+        n = pk.shape[0]
+        if out is None:
+            out = np.empty((n,) + self.frame_shape, self.pixel_dtype)
+        assert out.dtype == self.pixel_dtype and out.flags.c_contiguous and out.shape == (n,) + self.frame_shape
+        qa, qp = _q_array(q)
+        mode = FRI_DEQUANT_MULTIPLY if multiply else FRI_DEQUANT_DIVIDE
+        _check(lib().fri_decode_tq_emit10(self._h, pk.ctypes.data, n, qp, mode, out.ctypes.data))
+        return out
+
+    def emit_device10(self, d_coefs: int, n_frames: int, d_out: int, stream: int = 0) -> None:
+        _check(lib().fri_emit_device10(self._h, d_coefs, n_frames, d_out, stream))
+
+    def unemit_device10(self, d_packed: int, n_frames: int, d_coefs: int, stream: int = 0) -> None:
+        _check(lib().fri_unemit_device10(self._h, d_packed, n_frames, d_coefs, stream))
 
     def emit_device(self, d_coefs: int, n_frames: int, d_out: int, stream: int = 0, half: bool = False) -> None:
         """d_out: int32 (or, with half=True, int16) [n_frames, C, emission_count()] on the device."""

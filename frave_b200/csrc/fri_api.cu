@@ -51,6 +51,8 @@ struct Slot {
     int32_t *d_coefs = nullptr;
     int16_t *d_coefs16 = nullptr;  // 16-bit transport staging (fri_*_tq16), allocated on first use
     int32_t *d_dc = nullptr;
+    void *d_emit = nullptr;        // emission-ordered streams of the frame (fri_*_tq_emit*), sized for int32 streams
+    void *d_pack = nullptr;        // the same streams in the 10-bit packed transport (fri_*_tq_emit10)
     cudaEvent_t compute_done = nullptr;  // last kernel of the frame that used the slot
     cudaEvent_t out_done = nullptr;      // last device-to-host copy of that frame
     bool used = false;
@@ -76,8 +78,6 @@ struct fri_plan {
     Slot slots[kSlots];
     Pipeline pipe;
     bool slots_ready = false;
-    int32_t *d_dc_shared = nullptr;  // low-pass scratch for the *_device entry points (depth > 9)
-    size_t d_dc_frames = 0;
     uint32_t last_launches = 0;
     int bands = 0;  // fri_plan_set_bands: 0 = automatic
     bool async_mode = false;  // fri_plan_set_async
@@ -88,8 +88,7 @@ struct fri_plan {
     std::vector<uint32_t> emit_src;    // Some slots only
     void *d_emit_goff = nullptr, *d_emit_dst = nullptr, *d_emit_loc = nullptr;  // the Some slots partitioned by group
     EmitTables emit_tables;
-    void *d_emit_tmp = nullptr;         // device staging for fri_encode_tq_emit*
-    size_t d_emit_tmp_bytes = 0;
+    bool emit_device_ready = false;     // all three tables uploaded
 };
 
 namespace {
@@ -118,38 +117,59 @@ size_t dc_elems_per_frame(const Geometry &g)
     return g.sub_bits > 0 ? ((size_t)g.n_fractals * g.channels) << g.sub_bits : 0;
 }
 
-int ensure_dc(fri_plan *p, size_t frames)
-{
-    const Geometry &g = p->plan.geo;
-    if (g.sub_bits == 0 || frames <= p->d_dc_frames) return FRI_OK;
-    if (p->d_dc_shared) cudaFree(p->d_dc_shared);
-    p->d_dc_shared = nullptr;
-    p->d_dc_frames = 0;
-    FRI_CUDA(cudaMalloc(&p->d_dc_shared, frames * dc_elems_per_frame(g) * sizeof(int32_t)));
-    p->d_dc_frames = frames;
-    return FRI_OK;
-}
-
 int ensure_slots(fri_plan *p)
 {
     if (p->slots_ready) return FRI_OK;
+    // Every resource is created at most once, so a call that failed half-way (out of device memory) can be
+    // retried without leaking what the first attempt got.
     const Geometry &g = p->plan.geo;
     Pipeline &pl = p->pipe;
-    FRI_CUDA(cudaStreamCreateWithFlags(&pl.in, cudaStreamNonBlocking));
-    FRI_CUDA(cudaStreamCreateWithFlags(&pl.compute, cudaStreamNonBlocking));
-    FRI_CUDA(cudaStreamCreateWithFlags(&pl.out, cudaStreamNonBlocking));
+    for (cudaStream_t *st : {&pl.in, &pl.compute, &pl.out})
+        if (!*st) FRI_CUDA(cudaStreamCreateWithFlags(st, cudaStreamNonBlocking));
     for (int k = 0; k < kMaxBands; ++k) {
-        FRI_CUDA(cudaEventCreateWithFlags(&pl.in_ready[k], cudaEventDisableTiming));
-        FRI_CUDA(cudaEventCreateWithFlags(&pl.band_done[k], cudaEventDisableTiming));
+        if (!pl.in_ready[k]) FRI_CUDA(cudaEventCreateWithFlags(&pl.in_ready[k], cudaEventDisableTiming));
+        if (!pl.band_done[k]) FRI_CUDA(cudaEventCreateWithFlags(&pl.band_done[k], cudaEventDisableTiming));
     }
     for (auto &s : p->slots) {
-        FRI_CUDA(cudaMalloc(&s.d_pixels, (size_t)g.frame_bytes + 16));
-        FRI_CUDA(cudaMalloc(&s.d_coefs, (size_t)g.coefs_per_frame * sizeof(int32_t) + 16));
-        if (g.sub_bits > 0) FRI_CUDA(cudaMalloc(&s.d_dc, dc_elems_per_frame(g) * sizeof(int32_t)));
-        FRI_CUDA(cudaEventCreateWithFlags(&s.compute_done, cudaEventDisableTiming));
-        FRI_CUDA(cudaEventCreateWithFlags(&s.out_done, cudaEventDisableTiming));
+        if (!s.d_pixels) FRI_CUDA(cudaMalloc(&s.d_pixels, (size_t)g.frame_bytes + 16));
+        if (!s.d_coefs) FRI_CUDA(cudaMalloc(&s.d_coefs, (size_t)g.coefs_per_frame * sizeof(int32_t) + 16));
+        if (g.sub_bits > 0 && !s.d_dc) FRI_CUDA(cudaMalloc(&s.d_dc, dc_elems_per_frame(g) * sizeof(int32_t)));
+        if (!s.compute_done) FRI_CUDA(cudaEventCreateWithFlags(&s.compute_done, cudaEventDisableTiming));
+        if (!s.out_done) FRI_CUDA(cudaEventCreateWithFlags(&s.out_done, cudaEventDisableTiming));
     }
     p->slots_ready = true;
+    return FRI_OK;
+}
+
+// A slot is reused by the frame two calls later — possibly of the other direction or another element size
+// (an encode and a decode may alternate on one handle, also in asynchronous mode).  Its buffers are free once
+// the previous user's kernels AND device-to-host copies are done, and both the copy-in stream and the compute
+// stream touch them first, so both wait for both events.
+int acquire_slot(fri_plan *p, Slot &s)
+{
+    if (!s.used) return FRI_OK;
+    Pipeline &pl = p->pipe;
+    for (cudaStream_t st : {pl.in, pl.compute}) {
+        FRI_CUDA(cudaStreamWaitEvent(st, s.compute_done, 0));
+        FRI_CUDA(cudaStreamWaitEvent(st, s.out_done, 0));
+    }
+    return FRI_OK;
+}
+
+// Host buffers of the asynchronous mode must be page-locked: a pageable pointer would make cudaMemcpyAsync
+// synchronous at best and — once the call has returned — let the caller free memory a copy still reads.
+int check_pinned(const fri_plan *p, const void *ptr, const char *what)
+{
+    if (!p->async_mode) return FRI_OK;
+    cudaPointerAttributes attr{};
+    cudaError_t e = cudaPointerGetAttributes(&attr, ptr);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(FRI_E_INVALID, "%s: asynchronous mode needs page-locked host memory (fri_host_alloc)", what);
+    }
+    if (attr.type != cudaMemoryTypeHost && attr.type != cudaMemoryTypeManaged)
+        return fail(FRI_E_INVALID, "%s: asynchronous mode needs page-locked host memory (fri_host_alloc); the buffer is pageable",
+                    what);
     return FRI_OK;
 }
 
@@ -332,10 +352,11 @@ void fri_plan_destroy(fri_plan *p)
             if (s.d_coefs) cudaFree(s.d_coefs);
             if (s.d_coefs16) cudaFree(s.d_coefs16);
             if (s.d_dc) cudaFree(s.d_dc);
+            if (s.d_emit) cudaFree(s.d_emit);
+            if (s.d_pack) cudaFree(s.d_pack);
             if (s.compute_done) cudaEventDestroy(s.compute_done);
             if (s.out_done) cudaEventDestroy(s.out_done);
         }
-        if (p->d_dc_shared) cudaFree(p->d_dc_shared);
         if (p->d_groups) cudaFree(p->d_groups);
         if (p->d_groups_launch) cudaFree(p->d_groups_launch);
         if (p->d_tile_unit) cudaFree(p->d_tile_unit);
@@ -344,7 +365,6 @@ void fri_plan_destroy(fri_plan *p)
         if (p->d_emit_goff) cudaFree(p->d_emit_goff);
         if (p->d_emit_dst) cudaFree(p->d_emit_dst);
         if (p->d_emit_loc) cudaFree(p->d_emit_loc);
-        if (p->d_emit_tmp) cudaFree(p->d_emit_tmp);
         if (p->d_stage_list) cudaFree(p->d_stage_list);
     }
     delete p;
@@ -402,12 +422,19 @@ static int encode_device(const fri_plan *cp, const void *d_pixels, uint32_t n_fr
         return fail(FRI_E_UNSUPPORTED, "int16 coefficient arrays need 8-bit samples and depth 9");
     if ((uintptr_t)d_coefs & 15) return fail(FRI_E_INVALID, "d_coefs must be 16-byte aligned");
     if ((uintptr_t)d_pixels & (uintptr_t)(g.sample_bytes - 1)) return fail(FRI_E_INVALID, "d_pixels must be aligned to the sample size");
-    if ((rc = ensure_dc(p, n_frames))) return rc;
     QuantParams qp;
     make_quant_params(qp, q, 0);
-    p->last_launches = 0;
-    FRI_CUDA(launch_encode(g, p->tables, qp, d_pixels, n_frames, d_coefs, half, p->d_dc_shared, static_cast<cudaStream_t>(stream),
-                           &p->last_launches));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // depth > 9: the base tiles' low-pass roots go through a scratch array that lives for this call only —
+    // stream-ordered allocation, so calls on different streams (or an encode and a decode in flight together)
+    // never share it and the plan stays read-only
+    int32_t *d_dc = nullptr;
+    if (g.sub_bits > 0) FRI_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&d_dc), n_frames * dc_elems_per_frame(g) * sizeof(int32_t), st));
+    uint32_t launches = 0;
+    const cudaError_t e = launch_encode(g, p->tables, qp, d_pixels, n_frames, d_coefs, half, d_dc, st, &launches);
+    if (d_dc) cudaFreeAsync(d_dc, st);
+    p->last_launches = launches;
+    if (e != cudaSuccess) return cuda_fail(e, "launch_encode");
     return FRI_OK;
 }
 
@@ -427,16 +454,20 @@ static int decode_device(const fri_plan *cp, const void *d_coefs, bool half, uin
         return fail(FRI_E_UNSUPPORTED, "int16 coefficient arrays need 8-bit samples and depth 9");
     if ((uintptr_t)d_coefs & 15) return fail(FRI_E_INVALID, "d_coefs must be 16-byte aligned");
     if ((uintptr_t)d_pixels & (uintptr_t)(g.sample_bytes - 1)) return fail(FRI_E_INVALID, "d_pixels must be aligned to the sample size");
-    if ((rc = ensure_dc(p, n_frames))) return rc;
     QuantParams qp;
     make_quant_params(qp, q, dequant_mode == FRI_DEQUANT_MULTIPLY);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    p->last_launches = 0;
     // from_wavelet zero-initialises the raster (wavelet_transform.rs:309-317); only needed when
     // the retained fractals do not cover every pixel.
     if (p->plan.pixels_covered != (uint64_t)g.width * g.height)
         FRI_CUDA(cudaMemsetAsync(d_pixels, 0, (size_t)g.frame_bytes * n_frames, st));
-    FRI_CUDA(launch_decode(g, p->tables, qp, d_coefs, half, n_frames, d_pixels, p->d_dc_shared, st, &p->last_launches));
+    int32_t *d_dc = nullptr;  // per-call low-pass scratch (depth > 9), see encode_device
+    if (g.sub_bits > 0) FRI_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&d_dc), n_frames * dc_elems_per_frame(g) * sizeof(int32_t), st));
+    uint32_t launches = 0;
+    const cudaError_t e = launch_decode(g, p->tables, qp, d_coefs, half, n_frames, d_pixels, d_dc, st, &launches);
+    if (d_dc) cudaFreeAsync(d_dc, st);
+    p->last_launches = launches;
+    if (e != cudaSuccess) return cuda_fail(e, "launch_decode");
     return FRI_OK;
 }
 
@@ -471,6 +502,7 @@ static int encode_host(fri_plan *p, const void *pixels, uint32_t n_frames, const
     if ((rc = check_q(q))) return rc;
     if (n_frames == 0) return FRI_OK;
     if (!pixels || !coefs) return fail(FRI_E_INVALID, "NULL host buffer");
+    if ((rc = check_pinned(p, pixels, "pixels")) || (rc = check_pinned(p, coefs, "coefs"))) return rc;
     if ((rc = half ? ensure_slots16(p) : ensure_slots(p))) return rc;
     const Geometry &g = p->plan.geo;
     Pipeline &pl = p->pipe;
@@ -485,10 +517,7 @@ static int encode_host(fri_plan *p, const void *pixels, uint32_t n_frames, const
         const uint8_t *src = static_cast<const uint8_t *>(pixels) + (size_t)f * g.frame_bytes;
         const size_t esz = half ? sizeof(int16_t) : sizeof(int32_t);  // bytes per coefficient on the host side
         uint8_t *dst = static_cast<uint8_t *>(coefs) + (size_t)f * g.coefs_per_frame * esz;
-        if (s.used) {  // the frame that had this slot: its kernels have read the pixels, its copies the coefficients
-            FRI_CUDA(cudaStreamWaitEvent(pl.in, s.compute_done, 0));
-            FRI_CUDA(cudaStreamWaitEvent(pl.compute, s.out_done, 0));
-        }
+        if ((rc = acquire_slot(p, s))) return rc;
         int rows_up = 0;
         for (int k = 0; k < n_bands; ++k) {
             const Band &b = bands[k];
@@ -541,6 +570,7 @@ static int decode_host(fri_plan *p, const void *coefs, uint32_t n_frames, const 
         return fail(FRI_E_INVALID, "dequant_mode must be FRI_DEQUANT_DIVIDE or FRI_DEQUANT_MULTIPLY");
     if (n_frames == 0) return FRI_OK;
     if (!pixels || !coefs) return fail(FRI_E_INVALID, "NULL host buffer");
+    if ((rc = check_pinned(p, pixels, "pixels")) || (rc = check_pinned(p, coefs, "coefs"))) return rc;
     if ((rc = half ? ensure_slots16(p) : ensure_slots(p))) return rc;
     const Geometry &g = p->plan.geo;
     Pipeline &pl = p->pipe;
@@ -556,10 +586,7 @@ static int decode_host(fri_plan *p, const void *coefs, uint32_t n_frames, const 
         const size_t esz = half ? sizeof(int16_t) : sizeof(int32_t);
         const uint8_t *src = static_cast<const uint8_t *>(coefs) + (size_t)f * g.coefs_per_frame * esz;
         uint8_t *dst = static_cast<uint8_t *>(pixels) + (size_t)f * g.frame_bytes;
-        if (s.used) {  // previous user of the slot: kernels have read the coefficients, copies the pixels
-            FRI_CUDA(cudaStreamWaitEvent(pl.in, s.compute_done, 0));
-            FRI_CUDA(cudaStreamWaitEvent(pl.compute, s.out_done, 0));
-        }
+        if ((rc = acquire_slot(p, s))) return rc;
         if (need_zero) FRI_CUDA(cudaMemsetAsync(s.d_pixels, 0, (size_t)g.frame_bytes, pl.compute));
         int rows_out = 0;
         for (int k = 0; k < n_bands; ++k) {
@@ -642,7 +669,7 @@ static int ensure_emission_device(fri_plan *p)
 {
     int rc = ensure_emission(p);
     if (rc) return rc;
-    if (p->d_emit_goff || p->emit_src.empty()) return FRI_OK;
+    if (p->emit_device_ready || p->emit_src.empty()) return FRI_OK;
     // Partition the Some slots by the group that owns their tile (a group's tiles are consecutive in
     // plan order), keeping increasing emission index inside every group.
     const Plan &pl = p->plan;
@@ -672,9 +699,17 @@ static int ensure_emission_device(fri_plan *p)
         cudaError_t e = cudaMalloc(d, bytes);
         return e != cudaSuccess ? e : cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice);
     };
-    FRI_CUDA(upload(&p->d_emit_goff, goff.data(), goff.size() * sizeof(uint32_t)));
-    FRI_CUDA(upload(&p->d_emit_dst, dst.data(), count * sizeof(uint32_t)));
-    FRI_CUDA(upload(&p->d_emit_loc, loc.data(), count * sizeof(uint16_t)));
+    cudaError_t e = upload(&p->d_emit_goff, goff.data(), goff.size() * sizeof(uint32_t));
+    if (e == cudaSuccess) e = upload(&p->d_emit_dst, dst.data(), count * sizeof(uint32_t));
+    if (e == cudaSuccess) e = upload(&p->d_emit_loc, loc.data(), count * sizeof(uint16_t));
+    if (e != cudaSuccess) {  // all three or none: a later call starts over
+        for (void **d : {&p->d_emit_goff, &p->d_emit_dst, &p->d_emit_loc}) {
+            if (*d) cudaFree(*d);
+            *d = nullptr;
+        }
+        return cuda_fail(e, "uploading the emission tables");
+    }
+    p->emit_device_ready = true;
     p->emit_tables.goff = static_cast<const uint32_t *>(p->d_emit_goff);
     p->emit_tables.dst = static_cast<const uint32_t *>(p->d_emit_dst);
     p->emit_tables.loc = static_cast<const uint16_t *>(p->d_emit_loc);
@@ -696,7 +731,22 @@ int fri_plan_emission_order(fri_plan *p, uint32_t *order)
     return FRI_OK;
 }
 
-static int emit_device(fri_plan *p, const int32_t *d_coefs, uint32_t n_frames, void *d_out, bool half, void *stream)
+// Element type of an emission-ordered stream at the boundary.
+enum class StreamFmt { I32, I16, P10 };
+
+// Padded length of one channel's stream inside the device staging of the packed transport: a multiple of the
+// 64-symbol packing block.
+static size_t padded_count(size_t count) { return (count + kPackBlock - 1) / kPackBlock * kPackBlock; }
+static size_t packed_bytes(size_t count) { return padded_count(count) / kPackBlock * kPackBlockBytes; }
+
+static int check_stream_fmt(const fri_plan *p, StreamFmt fmt)
+{
+    if (fmt != StreamFmt::I32 && p->plan.geo.sample_bytes != 1)
+        return fail(FRI_E_UNSUPPORTED, "16-bit / 10-bit emission needs 8-bit samples (residues of 16-bit samples need 18 bits)");
+    return FRI_OK;
+}
+
+static int emit_device(fri_plan *p, const int32_t *d_coefs, uint32_t n_frames, void *d_out, StreamFmt fmt, void *stream)
 {
     int rc = enter_device(p);
     if (rc) return rc;
@@ -704,25 +754,67 @@ static int emit_device(fri_plan *p, const int32_t *d_coefs, uint32_t n_frames, v
     if (n_frames == 0) return FRI_OK;
     if (!d_coefs || !d_out) return fail(FRI_E_INVALID, "NULL device buffer");
     if ((uintptr_t)d_coefs & 15) return fail(FRI_E_INVALID, "d_coefs must be 16-byte aligned");
-    if (half && p->plan.geo.sample_bytes != 1)
-        return fail(FRI_E_UNSUPPORTED, "16-bit emission needs 8-bit samples (residues of 16-bit samples need 18 bits)");
-    p->last_launches = 0;
-    FRI_CUDA(launch_emit(p->plan.geo, p->tables, p->emit_tables, p->emit_src.size(), d_coefs, n_frames, d_out, half,
-                         static_cast<cudaStream_t>(stream), &p->last_launches));
+    if ((rc = check_stream_fmt(p, fmt))) return rc;
+    const Geometry &g = p->plan.geo;
+    const size_t count = p->emit_src.size();
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint32_t launches = 0;
+    cudaError_t e;
+    if (fmt == StreamFmt::P10) {
+        if ((uintptr_t)d_out & 15) return fail(FRI_E_INVALID, "packed streams must be 16-byte aligned");
+        // gather into int16 streams of padded stride (stream-ordered scratch), then pack
+        const size_t stride = padded_count(count), total = (size_t)n_frames * g.channels * stride;
+        int16_t *tmp = nullptr;
+        FRI_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&tmp), total * sizeof(int16_t), st));
+        e = cudaMemsetAsync(tmp, 0, total * sizeof(int16_t), st);  // the padding packs as symbol 0
+        if (e == cudaSuccess) e = launch_emit(g, p->tables, p->emit_tables, stride, d_coefs, n_frames, tmp, true, st, &launches);
+        if (e == cudaSuccess) e = launch_pack10(tmp, static_cast<uint8_t *>(d_out), total / kPackBlock, st, &launches);
+        cudaFreeAsync(tmp, st);
+    } else {
+        e = launch_emit(g, p->tables, p->emit_tables, count, d_coefs, n_frames, d_out, fmt == StreamFmt::I16, st, &launches);
+    }
+    p->last_launches = launches;
+    if (e != cudaSuccess) return cuda_fail(e, "emission gather");
     return FRI_OK;
 }
 
 int fri_emit_device(fri_plan *p, const int32_t *d_coefs, uint32_t n_frames, int32_t *d_out, void *stream)
 {
-    return emit_device(p, d_coefs, n_frames, d_out, false, stream);
+    return emit_device(p, d_coefs, n_frames, d_out, StreamFmt::I32, stream);
 }
 
 int fri_emit_device16(fri_plan *p, const int32_t *d_coefs, uint32_t n_frames, int16_t *d_out, void *stream)
 {
-    return emit_device(p, d_coefs, n_frames, d_out, true, stream);
+    return emit_device(p, d_coefs, n_frames, d_out, StreamFmt::I16, stream);
 }
 
-static int encode_emit_host(fri_plan *p, const void *pixels, uint32_t n_frames, const int32_t *q, void *out, bool half)
+int fri_emit_device10(fri_plan *p, const int32_t *d_coefs, uint32_t n_frames, uint8_t *d_out, void *stream)
+{
+    return emit_device(p, d_coefs, n_frames, d_out, StreamFmt::P10, stream);
+}
+
+uint64_t fri_plan_emission_packed_bytes(fri_plan *p)
+{
+    if (ensure_emission(p)) return 0;
+    return (uint64_t)packed_bytes(p->emit_src.size());
+}
+
+// Device staging of the emission-ordered streams of one frame per slot: sized for int32 streams of padded
+// stride (the largest of the three formats), plus the packed image of the same streams.
+static int ensure_emit_slots(fri_plan *p)
+{
+    int rc = ensure_slots(p);
+    if (rc) return rc;
+    const Geometry &g = p->plan.geo;
+    const size_t count = p->emit_src.size();
+    for (auto &s : p->slots) {
+        if (!s.d_emit) FRI_CUDA(cudaMalloc(&s.d_emit, (size_t)g.channels * padded_count(count) * sizeof(int32_t) + 16));
+        if (!s.d_pack && g.sample_bytes == 1) FRI_CUDA(cudaMalloc(&s.d_pack, (size_t)g.channels * packed_bytes(count) + 16));
+    }
+    return FRI_OK;
+}
+
+static int encode_emit_host(fri_plan *p, const void *pixels, uint32_t n_frames, const int32_t *q, void *out, StreamFmt fmt)
 {
     int rc = enter_device(p);
     if (rc) return rc;
@@ -730,43 +822,39 @@ static int encode_emit_host(fri_plan *p, const void *pixels, uint32_t n_frames, 
     if ((rc = ensure_emission_device(p))) return rc;
     if (n_frames == 0) return FRI_OK;
     if (!pixels || !out) return fail(FRI_E_INVALID, "NULL host buffer");
-    if ((rc = ensure_slots(p))) return rc;
+    if ((rc = check_stream_fmt(p, fmt))) return rc;
+    if ((rc = check_pinned(p, pixels, "pixels")) || (rc = check_pinned(p, out, "streams"))) return rc;
+    if ((rc = ensure_emit_slots(p))) return rc;
     const Geometry &g = p->plan.geo;
-    if (half && g.sample_bytes != 1)
-        return fail(FRI_E_UNSUPPORTED, "16-bit emission needs 8-bit samples (residues of 16-bit samples need 18 bits)");
     const size_t count = p->emit_src.size();
-    const size_t esz = half ? sizeof(int16_t) : sizeof(int32_t);
-    const size_t per_frame = (size_t)g.channels * count * esz;        // bytes
-    const size_t per_slot = (per_frame + 255) & ~(size_t)255;
-    if (p->d_emit_tmp_bytes < (size_t)kSlots * per_slot) {
-        if (p->d_emit_tmp) cudaFree(p->d_emit_tmp);
-        p->d_emit_tmp = nullptr;
-        p->d_emit_tmp_bytes = 0;
-        FRI_CUDA(cudaMalloc(&p->d_emit_tmp, (size_t)kSlots * per_slot));
-        p->d_emit_tmp_bytes = (size_t)kSlots * per_slot;
-    }
+    const bool packed = fmt == StreamFmt::P10;
+    const size_t stride = packed ? padded_count(count) : count;  // elements between two streams on the device
+    const size_t per_frame = packed ? (size_t)g.channels * packed_bytes(count)
+                                    : (size_t)g.channels * count * (fmt == StreamFmt::I16 ? sizeof(int16_t) : sizeof(int32_t));
     QuantParams qp;
     make_quant_params(qp, q, 0);
     p->last_launches = 0;
     Pipeline &pl = p->pipe;
     for (uint32_t f = 0; f < n_frames; ++f) {
         Slot &s = p->slots[f % kSlots];
-        uint8_t *d_emit = static_cast<uint8_t *>(p->d_emit_tmp) + (size_t)(f % kSlots) * per_slot;
-        if (s.used) {
-            FRI_CUDA(cudaStreamWaitEvent(pl.in, s.compute_done, 0));
-            FRI_CUDA(cudaStreamWaitEvent(pl.compute, s.out_done, 0));
-        }
+        if ((rc = acquire_slot(p, s))) return rc;
         FRI_CUDA(cudaMemcpyAsync(s.d_pixels, static_cast<const uint8_t *>(pixels) + (size_t)f * g.frame_bytes,
                                  (size_t)g.frame_bytes, cudaMemcpyHostToDevice, pl.in));
         FRI_CUDA(cudaEventRecord(pl.in_ready[0], pl.in));
         FRI_CUDA(cudaStreamWaitEvent(pl.compute, pl.in_ready[0], 0));
         FRI_CUDA(launch_encode(g, p->tables, qp, s.d_pixels, 1, s.d_coefs, false, s.d_dc, pl.compute, &p->last_launches));
-        FRI_CUDA(launch_emit(g, p->tables, p->emit_tables, count, s.d_coefs, 1, d_emit, half, pl.compute, &p->last_launches));
+        if (packed && stride != count)  // the padding of every stream packs as symbol 0
+            FRI_CUDA(cudaMemsetAsync(s.d_emit, 0, (size_t)g.channels * stride * sizeof(int16_t), pl.compute));
+        FRI_CUDA(launch_emit(g, p->tables, p->emit_tables, stride, s.d_coefs, 1, s.d_emit, fmt != StreamFmt::I32, pl.compute,
+                             &p->last_launches));
+        if (packed)
+            FRI_CUDA(launch_pack10(static_cast<const int16_t *>(s.d_emit), static_cast<uint8_t *>(s.d_pack),
+                                   (size_t)g.channels * stride / kPackBlock, pl.compute, &p->last_launches));
         FRI_CUDA(cudaEventRecord(pl.band_done[0], pl.compute));
         FRI_CUDA(cudaEventRecord(s.compute_done, pl.compute));
         FRI_CUDA(cudaStreamWaitEvent(pl.out, pl.band_done[0], 0));
-        FRI_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(out) + (size_t)f * per_frame, d_emit, per_frame, cudaMemcpyDeviceToHost,
-                                 pl.out));
+        FRI_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(out) + (size_t)f * per_frame, packed ? s.d_pack : s.d_emit, per_frame,
+                                 cudaMemcpyDeviceToHost, pl.out));
         FRI_CUDA(cudaEventRecord(s.out_done, pl.out));
         s.used = true;
     }
@@ -775,15 +863,20 @@ static int encode_emit_host(fri_plan *p, const void *pixels, uint32_t n_frames, 
 
 int fri_encode_tq_emit(fri_plan *p, const void *pixels, uint32_t n_frames, const int32_t *q, int32_t *out)
 {
-    return encode_emit_host(p, pixels, n_frames, q, out, false);
+    return encode_emit_host(p, pixels, n_frames, q, out, StreamFmt::I32);
 }
 
 int fri_encode_tq_emit16(fri_plan *p, const void *pixels, uint32_t n_frames, const int32_t *q, int16_t *out)
 {
-    return encode_emit_host(p, pixels, n_frames, q, out, true);
+    return encode_emit_host(p, pixels, n_frames, q, out, StreamFmt::I16);
 }
 
-static int unemit_device(fri_plan *p, const void *d_streams, bool half, uint32_t n_frames, int32_t *d_coefs, void *stream)
+int fri_encode_tq_emit10(fri_plan *p, const void *pixels, uint32_t n_frames, const int32_t *q, uint8_t *out)
+{
+    return encode_emit_host(p, pixels, n_frames, q, out, StreamFmt::P10);
+}
+
+static int unemit_device(fri_plan *p, const void *d_streams, StreamFmt fmt, uint32_t n_frames, int32_t *d_coefs, void *stream)
 {
     int rc = enter_device(p);
     if (rc) return rc;
@@ -791,23 +884,44 @@ static int unemit_device(fri_plan *p, const void *d_streams, bool half, uint32_t
     if (n_frames == 0) return FRI_OK;
     if (!d_coefs || !d_streams) return fail(FRI_E_INVALID, "NULL device buffer");
     if ((uintptr_t)d_coefs & 15) return fail(FRI_E_INVALID, "d_coefs must be 16-byte aligned");
-    p->last_launches = 0;
-    FRI_CUDA(launch_unemit(p->plan.geo, p->tables, p->emit_tables, p->emit_src.size(), d_streams, half, n_frames, d_coefs,
-                           static_cast<cudaStream_t>(stream), &p->last_launches));
+    if ((rc = check_stream_fmt(p, fmt))) return rc;
+    const Geometry &g = p->plan.geo;
+    const size_t count = p->emit_src.size();
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint32_t launches = 0;
+    cudaError_t e;
+    if (fmt == StreamFmt::P10) {
+        if ((uintptr_t)d_streams & 15) return fail(FRI_E_INVALID, "packed streams must be 16-byte aligned");
+        const size_t stride = padded_count(count), total = (size_t)n_frames * g.channels * stride;
+        int16_t *tmp = nullptr;
+        FRI_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&tmp), total * sizeof(int16_t), st));
+        e = launch_unpack10(static_cast<const uint8_t *>(d_streams), tmp, total / kPackBlock, st, &launches);
+        if (e == cudaSuccess) e = launch_unemit(g, p->tables, p->emit_tables, stride, tmp, true, n_frames, d_coefs, st, &launches);
+        cudaFreeAsync(tmp, st);
+    } else {
+        e = launch_unemit(g, p->tables, p->emit_tables, count, d_streams, fmt == StreamFmt::I16, n_frames, d_coefs, st, &launches);
+    }
+    p->last_launches = launches;
+    if (e != cudaSuccess) return cuda_fail(e, "emission un-gather");
     return FRI_OK;
 }
 
 int fri_unemit_device(fri_plan *p, const int32_t *d_streams, uint32_t n_frames, int32_t *d_coefs, void *stream)
 {
-    return unemit_device(p, d_streams, false, n_frames, d_coefs, stream);
+    return unemit_device(p, d_streams, StreamFmt::I32, n_frames, d_coefs, stream);
 }
 
 int fri_unemit_device16(fri_plan *p, const int16_t *d_streams, uint32_t n_frames, int32_t *d_coefs, void *stream)
 {
-    return unemit_device(p, d_streams, true, n_frames, d_coefs, stream);
+    return unemit_device(p, d_streams, StreamFmt::I16, n_frames, d_coefs, stream);
 }
 
-static int decode_emit_host(fri_plan *p, const void *streams, bool half, uint32_t n_frames, const int32_t *q, int dequant_mode,
+int fri_unemit_device10(fri_plan *p, const uint8_t *d_streams, uint32_t n_frames, int32_t *d_coefs, void *stream)
+{
+    return unemit_device(p, d_streams, StreamFmt::P10, n_frames, d_coefs, stream);
+}
+
+static int decode_emit_host(fri_plan *p, const void *streams, StreamFmt fmt, uint32_t n_frames, const int32_t *q, int dequant_mode,
                             void *pixels)
 {
     int rc = enter_device(p);
@@ -818,19 +932,15 @@ static int decode_emit_host(fri_plan *p, const void *streams, bool half, uint32_
     if ((rc = ensure_emission_device(p))) return rc;
     if (n_frames == 0) return FRI_OK;
     if (!pixels || !streams) return fail(FRI_E_INVALID, "NULL host buffer");
-    if ((rc = ensure_slots(p))) return rc;
+    if ((rc = check_stream_fmt(p, fmt))) return rc;
+    if ((rc = check_pinned(p, pixels, "pixels")) || (rc = check_pinned(p, streams, "streams"))) return rc;
+    if ((rc = ensure_emit_slots(p))) return rc;
     const Geometry &g = p->plan.geo;
     const size_t count = p->emit_src.size();
-    const size_t esz = half ? sizeof(int16_t) : sizeof(int32_t);
-    const size_t per_frame = (size_t)g.channels * count * esz;  // bytes
-    const size_t per_slot = (per_frame + 255) & ~(size_t)255;
-    if (p->d_emit_tmp_bytes < (size_t)kSlots * per_slot) {
-        if (p->d_emit_tmp) cudaFree(p->d_emit_tmp);
-        p->d_emit_tmp = nullptr;
-        p->d_emit_tmp_bytes = 0;
-        FRI_CUDA(cudaMalloc(&p->d_emit_tmp, (size_t)kSlots * per_slot));
-        p->d_emit_tmp_bytes = (size_t)kSlots * per_slot;
-    }
+    const bool packed = fmt == StreamFmt::P10;
+    const size_t stride = packed ? padded_count(count) : count;
+    const size_t per_frame = packed ? (size_t)g.channels * packed_bytes(count)
+                                    : (size_t)g.channels * count * (fmt == StreamFmt::I16 ? sizeof(int16_t) : sizeof(int32_t));
     QuantParams qp;
     make_quant_params(qp, q, dequant_mode == FRI_DEQUANT_MULTIPLY);
     p->last_launches = 0;
@@ -838,17 +948,17 @@ static int decode_emit_host(fri_plan *p, const void *streams, bool half, uint32_
     Pipeline &pl = p->pipe;
     for (uint32_t f = 0; f < n_frames; ++f) {
         Slot &s = p->slots[f % kSlots];
-        uint8_t *d_emit = static_cast<uint8_t *>(p->d_emit_tmp) + (size_t)(f % kSlots) * per_slot;
-        if (s.used) {
-            FRI_CUDA(cudaStreamWaitEvent(pl.in, s.compute_done, 0));
-            FRI_CUDA(cudaStreamWaitEvent(pl.compute, s.out_done, 0));
-        }
-        FRI_CUDA(cudaMemcpyAsync(d_emit, static_cast<const uint8_t *>(streams) + (size_t)f * per_frame, per_frame,
+        if ((rc = acquire_slot(p, s))) return rc;
+        FRI_CUDA(cudaMemcpyAsync(packed ? s.d_pack : s.d_emit, static_cast<const uint8_t *>(streams) + (size_t)f * per_frame, per_frame,
                                  cudaMemcpyHostToDevice, pl.in));
         FRI_CUDA(cudaEventRecord(pl.in_ready[0], pl.in));
         FRI_CUDA(cudaStreamWaitEvent(pl.compute, pl.in_ready[0], 0));
         if (need_zero) FRI_CUDA(cudaMemsetAsync(s.d_pixels, 0, (size_t)g.frame_bytes, pl.compute));
-        FRI_CUDA(launch_unemit(g, p->tables, p->emit_tables, count, d_emit, half, 1, s.d_coefs, pl.compute, &p->last_launches));
+        if (packed)
+            FRI_CUDA(launch_unpack10(static_cast<const uint8_t *>(s.d_pack), static_cast<int16_t *>(s.d_emit),
+                                     (size_t)g.channels * stride / kPackBlock, pl.compute, &p->last_launches));
+        FRI_CUDA(launch_unemit(g, p->tables, p->emit_tables, stride, s.d_emit, fmt != StreamFmt::I32, 1, s.d_coefs, pl.compute,
+                               &p->last_launches));
         FRI_CUDA(launch_decode(g, p->tables, qp, s.d_coefs, false, 1, s.d_pixels, s.d_dc, pl.compute, &p->last_launches));
         FRI_CUDA(cudaEventRecord(pl.band_done[0], pl.compute));
         FRI_CUDA(cudaEventRecord(s.compute_done, pl.compute));
@@ -863,12 +973,17 @@ static int decode_emit_host(fri_plan *p, const void *streams, bool half, uint32_
 
 int fri_decode_tq_emit(fri_plan *p, const int32_t *streams, uint32_t n_frames, const int32_t *q, int dequant_mode, void *pixels)
 {
-    return decode_emit_host(p, streams, false, n_frames, q, dequant_mode, pixels);
+    return decode_emit_host(p, streams, StreamFmt::I32, n_frames, q, dequant_mode, pixels);
 }
 
 int fri_decode_tq_emit16(fri_plan *p, const int16_t *streams, uint32_t n_frames, const int32_t *q, int dequant_mode, void *pixels)
 {
-    return decode_emit_host(p, streams, true, n_frames, q, dequant_mode, pixels);
+    return decode_emit_host(p, streams, StreamFmt::I16, n_frames, q, dequant_mode, pixels);
+}
+
+int fri_decode_tq_emit10(fri_plan *p, const uint8_t *streams, uint32_t n_frames, const int32_t *q, int dequant_mode, void *pixels)
+{
+    return decode_emit_host(p, streams, StreamFmt::P10, n_frames, q, dequant_mode, pixels);
 }
 
 int fri_host_alloc(void **out, size_t bytes)

@@ -727,8 +727,18 @@ __device__ __forceinline__ void prefetch_group_coefs(const Geometry &g, const Gr
         asm volatile("prefetch.global.L2 [%0];" ::"l"(first + (size_t)i * 128));
 }
 
+// Timing-only what-if switches (wrong results; variant builds for bounding what a change could buy)
 #ifndef FRI_WHATIF_NOWAIT
 #define FRI_WHATIF_NOWAIT 0
+#endif
+#ifndef FRI_WHATIF_SKIP_MIXED
+#define FRI_WHATIF_SKIP_MIXED 0   // decode: partially owned chunks are not written
+#endif
+#ifndef FRI_WHATIF_SKIP_FULL
+#define FRI_WHATIF_SKIP_FULL 0    // decode: fully owned chunks are not written
+#endif
+#ifndef FRI_WHATIF_SKIP_SCATTER
+#define FRI_WHATIF_SKIP_SCATTER 0 // decode: leaves are not stored to the staged region (one store per lane keeps them live)
 #endif
 // The coefficients of levels 6..8 a lane consumes for one (tile, channel): 2 x 128, 2 x 64, 2 x 32 bits.
 struct LaneCoefs {
@@ -900,6 +910,15 @@ __device__ __forceinline__ void dec_register_levels(const Geometry &g, const Qua
 
     // scatter into the staged region (clamp: images.rs:109)
     const uint32_t p1 = p0 + g.pitch, p2 = p1 + g.pitch;
+#if FRI_WHATIF_SKIP_SCATTER
+    {
+        int x = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x ^= v[i] ^ w[i];
+        store_clamped<S>(p0, x);
+        return;
+    }
+#endif
 #define FRI_ST(ptr, dx, val) store_clamped<S>((uint32_t)((int)(ptr) + (dx) * PB), (val))
     FRI_ST(p0, 0, v[0]);  FRI_ST(p1, 0, v[1]);
     FRI_ST(p1, -1, v[2]); FRI_ST(p2, -1, v[3]);
@@ -1016,6 +1035,10 @@ __device__ __forceinline__ void zero_region(const Geometry &g, uint8_t *region)
 // write_out_preload() *before* the CTA barrier that completes the region, so their latency hides
 // behind the barrier wait.
 constexpr int kWriteAhead = 6;
+// Fully owned chunks leave with a streaming (evict-first) store: decoded pixels are never re-read by the
+// kernel and should not push the prefetched coefficient runs out of L2 (+1.7 % on 16 x 4K frames per launch;
+// cache-global and write-through stores measured equal to the default).
+#define FRI_PIXEL_STORE(ptr, val) __stcs((ptr), (val))
 
 // Partially owned chunks are written one 32-bit word per thread and iteration (four neighbouring
 // lanes share a chunk): a word is skipped, stored whole, or — only the word the group's outline
@@ -1089,24 +1112,24 @@ __device__ __forceinline__ void write_out_group(const Geometry &g, const GroupDe
     const uint16_t *cmk = chunk_mask + (size_t)rv.phi0 * g.list_cap;
     const int n_full = g.list_full[rv.phi0], n_all = g.list_all[rv.phi0];
     if (rv.interior) {
-        const int rounds = (n_full + n_threads - 1) / n_threads;
+        const int rounds = FRI_WHATIF_SKIP_FULL ? 0 : (n_full + n_threads - 1) / n_threads;
 #pragma unroll
         for (int u = 0; u < kWriteAhead; ++u) {
             if (u < rounds) {  // CTA-uniform
                 const int r = (int)(ahead.e[u] >> 16), s = (int)(ahead.e[u] & 0xffffu) << 4;
-                *reinterpret_cast<int4 *>(rv.gaddr(r, s)) = *reinterpret_cast<const int4 *>(region + s);
+                FRI_PIXEL_STORE(reinterpret_cast<int4 *>(rv.gaddr(r, s)), *reinterpret_cast<const int4 *>(region + s));
             }
         }
 #if FRI_TRACE
         if ((threadIdx.x == 0 || threadIdx.x == 255) && blockIdx.x < 16384) g_trace2[4 * blockIdx.x + (threadIdx.x == 0 ? 0 : 1)] = gtime();
 #endif
 #pragma unroll 1
-        for (int k = threadIdx.x + kWriteAhead * n_threads; k < n_full; k += n_threads) {
+        for (int k = threadIdx.x + kWriteAhead * n_threads; k < (FRI_WHATIF_SKIP_FULL ? 0 : n_full); k += n_threads) {
             const uint32_t e = ld_table(cl + k, pol);
             const int r = (int)(e >> 16), s = (int)(e & 0xffffu) << 4;
-            *reinterpret_cast<int4 *>(rv.gaddr(r, s)) =
-                *reinterpret_cast<const int4 *>(region + s);
+            FRI_PIXEL_STORE(reinterpret_cast<int4 *>(rv.gaddr(r, s)), *reinterpret_cast<const int4 *>(region + s));
         }
+#if !FRI_WHATIF_SKIP_MIXED
         const int w = threadIdx.x & 3;
 #pragma unroll
         for (int u = 0; u < kMixedAhead; ++u)
@@ -1114,6 +1137,7 @@ __device__ __forceinline__ void write_out_group(const Geometry &g, const GroupDe
 #pragma unroll 1
         for (int k = n_full + ((threadIdx.x + kMixedAhead * n_threads) >> 2); k < n_all; k += n_threads >> 2)
             store_word_masked(rv, region, ld_table(cl + k, pol), ld_table(cmk + k, pol), w);
+#endif
 #if FRI_TRACE
         if ((threadIdx.x == 0 || threadIdx.x == 255) && blockIdx.x < 16384) g_trace2[4 * blockIdx.x + (threadIdx.x == 0 ? 2 : 3)] = gtime();
 #endif
@@ -1350,7 +1374,7 @@ fri_coarse_inverse_kernel(const __grid_constant__ QuantParams qp, int sub_bits, 
 template <typename T>
 __global__ void __launch_bounds__(256)
 fri_emit_kernel(const GroupDesc *__restrict__ groups, const uint32_t *__restrict__ goff, const uint32_t *__restrict__ dst,
-                const uint16_t *__restrict__ loc, unsigned long long count, int channels, int n_tiles,
+                const uint16_t *__restrict__ loc, unsigned long long stride, int channels, int n_tiles,
                 const int32_t *__restrict__ coefs, T *__restrict__ out)
 {
     extern __shared__ __align__(16) int32_t es[];
@@ -1365,7 +1389,7 @@ fri_emit_kernel(const GroupDesc *__restrict__ groups, const uint32_t *__restrict
             reinterpret_cast<int4 *>(es)[idx] = __ldcs(src + v);
         }
         __syncthreads();
-        T *o = out + ((size_t)frame * channels + ch) * count;
+        T *o = out + ((size_t)frame * channels + ch) * stride;  // stride: elements between the starts of two streams
         for (uint32_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) o[__ldg(dst + k)] = (T)es[__ldg(loc + k)];
         __syncthreads();
     }
@@ -1377,7 +1401,7 @@ fri_emit_kernel(const GroupDesc *__restrict__ groups, const uint32_t *__restrict
 template <typename T>
 __global__ void __launch_bounds__(256)
 fri_unemit_kernel(const GroupDesc *__restrict__ groups, const uint32_t *__restrict__ goff, const uint32_t *__restrict__ dst,
-                  const uint16_t *__restrict__ loc, unsigned long long count, int channels, int n_tiles,
+                  const uint16_t *__restrict__ loc, unsigned long long stride, int channels, int n_tiles,
                   const T *__restrict__ in, int32_t *__restrict__ coefs)
 {
     extern __shared__ __align__(16) int32_t es[];
@@ -1391,7 +1415,7 @@ fri_unemit_kernel(const GroupDesc *__restrict__ groups, const uint32_t *__restri
                 reinterpret_cast<int4 *>(es)[idx] = make_int4(0, 0, 0, 0);
             __syncthreads();
         }
-        const T *src = in + ((size_t)frame * channels + ch) * count;
+        const T *src = in + ((size_t)frame * channels + ch) * stride;
         uint32_t k = k0 + threadIdx.x;
         for (; k + 3 * blockDim.x < k1; k += 4 * blockDim.x) {  // four independent gathers in flight per thread
             uint32_t l[4];
@@ -1445,6 +1469,85 @@ fri_unpack16_kernel(const int4 *__restrict__ src, int4 *__restrict__ dst, size_t
         const int4 v = __ldcs(src + i);
         __stcs(dst + 2 * i, make_int4((int)(short)v.x, v.x >> 16, (int)(short)v.y, v.y >> 16));
         __stcs(dst + 2 * i + 1, make_int4((int)(short)v.z, v.z >> 16, (int)(short)v.w, v.w >> 16));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// 10-bit packed transport of the emission-ordered streams (host entry points fri_*_tq_emit10): a
+// coefficient travels as the symbol the reference's entropy coder would see, pack_signed(k) = 2k for
+// k >= 0, -2k - 1 for k < 0 (utils.rs:34-40), in the 1024-symbol alphabet (entropy_coding.rs:25) — every
+// coefficient of an 8-bit image fits (|k| <= 255) and so does every value a decodable container can hold.
+// Four symbols -> 40 bits -> 5 bytes, little-endian (symbol i of a group in bits [10 i, 10 i + 10)):
+// 1.25 bytes per coefficient over PCIe instead of 2.  One thread packs 64 symbols (128 B in, 80 B out);
+// streams are padded to a multiple of 64 symbols on both sides.  Encode saturates at +-511 / -512.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t zigzag10(int v)
+{
+    v = max(-512, min(511, v));
+    return (uint32_t)((v << 1) ^ (v >> 31));  // 2v for v >= 0, -2v - 1 for v < 0
+}
+__device__ __forceinline__ int unzigzag10(uint32_t s) { return (int)(s >> 1) ^ -(int)(s & 1u); }  // utils.rs:42-48
+
+__global__ void __launch_bounds__(256)
+fri_pack10_kernel(const int4 *__restrict__ src, int4 *__restrict__ dst, size_t n_blocks)
+{
+    for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_blocks; b += (size_t)gridDim.x * blockDim.x) {
+        uint32_t w[20];  // 16 groups of 40 bits
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {  // 8 symbols = 2 groups = 80 bits per 16-byte load
+            const int4 v = __ldcs(src + 8 * b + j);
+            const int x[4] = {v.x, v.y, v.z, v.w};
+            uint64_t g[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t s0 = zigzag10((int)(short)x[2 * h]), s1 = zigzag10(x[2 * h] >> 16);
+                const uint32_t s2 = zigzag10((int)(short)x[2 * h + 1]), s3 = zigzag10(x[2 * h + 1] >> 16);
+                g[h] = (uint64_t)s0 | (uint64_t)s1 << 10 | (uint64_t)s2 << 20 | (uint64_t)s3 << 30;
+            }
+            // 80 bits at bit offset 80 j of the 640-bit output block
+            const int bit = 80 * j, wi = bit >> 5, sh = bit & 31;  // sh is 0 or 16
+            const uint32_t lo0 = (uint32_t)g[0], hi0 = (uint32_t)(g[0] >> 32);  // 40 bits: lo0, hi0[7:0]
+            const uint64_t g1 = g[1];
+            // 80-bit value V = g0 | g1 << 40
+            const uint32_t v0 = lo0, v1 = hi0 | (uint32_t)(g1 << 8), v2 = (uint32_t)(g1 >> 24);  // v2: 16 bits
+            if (sh == 0) {
+                w[wi] = v0; w[wi + 1] = v1; w[wi + 2] = v2;             // low 16 bits of w[wi + 2]
+            } else {
+                w[wi] |= v0 << 16; w[wi + 1] = v0 >> 16 | v1 << 16; w[wi + 2] = v1 >> 16 | v2 << 16;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) __stcs(dst + 5 * b + k, make_int4((int)w[4 * k], (int)w[4 * k + 1], (int)w[4 * k + 2], (int)w[4 * k + 3]));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+fri_unpack10_kernel(const int4 *__restrict__ src, int4 *__restrict__ dst, size_t n_blocks)
+{
+    for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_blocks; b += (size_t)gridDim.x * blockDim.x) {
+        uint32_t w[21];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const int4 v = __ldcs(src + 5 * b + k);
+            w[4 * k] = (uint32_t)v.x; w[4 * k + 1] = (uint32_t)v.y; w[4 * k + 2] = (uint32_t)v.z; w[4 * k + 3] = (uint32_t)v.w;
+        }
+        w[20] = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int out[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {  // symbols 8 j + 2 h, 8 j + 2 h + 1
+                int v[2];
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const int bit = 10 * (8 * j + 2 * h + t), wi = bit >> 5, sh = bit & 31;
+                    const uint32_t sym = (uint32_t)(((uint64_t)w[wi] | (uint64_t)w[wi + 1] << 32) >> sh) & 1023u;
+                    v[t] = unzigzag10(sym);
+                }
+                out[h] = (v[0] & 0xffff) | (v[1] << 16);
+            }
+            __stcs(dst + 8 * b + j, make_int4(out[0], out[1], out[2], out[3]));
+        }
     }
 }
 
@@ -1669,7 +1772,7 @@ cudaError_t launch_decode(const Geometry &g, const DeviceTables &t, const QuantP
 
 cudaError_t launch_unemit(const Geometry &g, const DeviceTables &t, const EmitTables &et, uint64_t count, const void *d_in,
                           bool half, uint32_t n_frames, int32_t *d_coefs, cudaStream_t stream, uint32_t *launches)
-{
+{   // `count` here is the stream stride in elements (>= the number of Some slots)
     if (n_frames == 0 || g.n_groups == 0) return cudaSuccess;
     const size_t smem = (size_t)g.group_a * g.group_b * kTileLeaves * sizeof(int32_t);
     const size_t esz = half ? sizeof(int16_t) : sizeof(int32_t);
@@ -1686,6 +1789,24 @@ cudaError_t launch_unemit(const Geometry &g, const DeviceTables &t, const EmitTa
                                                                     g.n_fractals, reinterpret_cast<const int32_t *>(in), c);
         if (launches) ++*launches;
     }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack10(const int16_t *d_src, uint8_t *d_dst, size_t n_blocks, cudaStream_t stream, uint32_t *launches)
+{
+    if (n_blocks == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)std::min<size_t>((n_blocks + 255) / 256, (size_t)148 * 16);
+    fri_pack10_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const int4 *>(d_src), reinterpret_cast<int4 *>(d_dst), n_blocks);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unpack10(const uint8_t *d_src, int16_t *d_dst, size_t n_blocks, cudaStream_t stream, uint32_t *launches)
+{
+    if (n_blocks == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)std::min<size_t>((n_blocks + 255) / 256, (size_t)148 * 16);
+    fri_unpack10_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const int4 *>(d_src), reinterpret_cast<int4 *>(d_dst), n_blocks);
+    if (launches) ++*launches;
     return cudaGetLastError();
 }
 

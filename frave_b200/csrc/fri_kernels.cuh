@@ -131,13 +131,21 @@ struct EmitTables {
 };
 
 // Gathers coefficients into emission order: out[frame][ch][dst[k]] = coefficient loc[k] of the group, for every
-// group; out is int32 or (half) int16, [n_frames][C][count].
+// group; out is int32 or (half) int16, [n_frames][C][count].  `count` is the stride between two streams in
+// elements: the number of Some slots for dense streams, or a padded stride (the packed transport).
 cudaError_t launch_emit(const Geometry &g, const DeviceTables &t, const EmitTables &et, uint64_t count, const int32_t *d_coefs,
                         uint32_t n_frames, void *d_out, bool half, cudaStream_t stream, uint32_t *launches);
 
 // The inverse: coefs[frame][tile][ch][i] <- emitted streams (int32 or, half, int16), `None` slots 0.
 cudaError_t launch_unemit(const Geometry &g, const DeviceTables &t, const EmitTables &et, uint64_t count, const void *d_in,
                           bool half, uint32_t n_frames, int32_t *d_coefs, cudaStream_t stream, uint32_t *launches);
+
+// 10-bit packed transport of emission-ordered streams: int16 streams (stride a multiple of 64 elements, 16-byte
+// aligned) <-> blocks of 64 zig-zag symbols in 80 bytes; n_blocks = total elements / 64.
+constexpr int kPackBlock = 64;       // symbols per packed block
+constexpr int kPackBlockBytes = 80;  // 64 x 10 bits
+cudaError_t launch_pack10(const int16_t *d_src, uint8_t *d_dst, size_t n_blocks, cudaStream_t stream, uint32_t *launches);
+cudaError_t launch_unpack10(const uint8_t *d_src, int16_t *d_dst, size_t n_blocks, cudaStream_t stream, uint32_t *launches);
 
 // 16-bit transport of the host-buffer entry points: saturating i32 -> i16 repack and its inverse
 // (count is a multiple of 8; both pointers 16-byte aligned).

@@ -100,6 +100,11 @@ int fri_plan_masks(const fri_plan *plan, uint32_t *masks);
  *   pixels  n_frames consecutive HWC frames;  coefs  n_frames consecutive coefficient blocks.
  *   q       32-entry quantization matrix, host memory, every entry >= 1; q == NULL means
  *           all ones (get_quantization_matrix, quantization.rs:3-5).
+ * The plan is read-only here (the depth > 9 scratch is allocated per call, stream-ordered), so
+ * several calls may be in flight on different streams; only fri_plan_last_launches is last-writer-wins.
+ * The kernels use programmatic dependent launch: on one stream, a call's kernel may become resident
+ * while the previous kernel drains, but it waits for that kernel to complete (memory flushed) before
+ * it reads or writes frame data, so stream order is preserved as usual.
  */
 int fri_encode_tq_device(const fri_plan *plan, const void *d_pixels, uint32_t n_frames, const int32_t *q,
                          int32_t *d_coefs, void *stream);
@@ -120,9 +125,15 @@ int fri_decode_tq_device16(const fri_plan *plan, const int16_t *d_coefs, uint32_
 
 /*
  * Host-buffer entry points (what libfri's stage functions call): copy in, run, copy out,
- * synchronise.  Frames are pipelined over the plan's internal streams; buffers obtained from
- * fri_host_alloc are pinned and take the fast path, any other host memory is staged through
- * pinned bounce buffers.
+ * synchronise.  Frames are pipelined over the plan's internal streams.  Buffers obtained from
+ * fri_host_alloc are page-locked and take the fast path (truly asynchronous copies at the link's
+ * full rate — what the measured end-to-end numbers use, and what the libfri-cuda Rust crate's
+ * PinnedBuf wraps).  Any other host memory is accepted in the default, synchronous mode and goes
+ * through the CUDA driver's own pageable-copy staging (correct, roughly half the throughput, no
+ * overlap); there is no bounce ring inside this library.  In asynchronous mode (fri_plan_set_async)
+ * pageable buffers are rejected with FRI_E_INVALID.
+ * One handle may alternate encode and decode calls, also in asynchronous mode: a device slot is
+ * handed to the next frame only after the previous user's kernels and copies have finished.
  */
 int fri_encode_tq(fri_plan *plan, const void *pixels, uint32_t n_frames, const int32_t *q, int32_t *coefs);
 int fri_decode_tq(fri_plan *plan, const int32_t *coefs, uint32_t n_frames, const int32_t *q, int dequant_mode,
@@ -159,7 +170,25 @@ int fri_decode_tq16(fri_plan *plan, const int16_t *coefs, uint32_t n_frames, con
  * All of them fail with FRI_E_UNSUPPORTED (and say so in fri_last_error) for the image sizes on
  * which the reference's own scan fails its assertion at wavelet_transform.rs:701, e.g. 257x300.
  */
+/*
+ *   fri_*_emit10             the same streams in the 10-bit packed transport (8-bit samples only): a
+ *                            coefficient k travels as the symbol the reference's entropy coder works
+ *                            in, pack_signed(k) = 2k (k >= 0) / -2k - 1 (k < 0) (utils.rs:34-40), of the
+ *                            1024-symbol alphabet (entropy_coding.rs:25); 64 symbols -> 80 bytes,
+ *                            symbol i of a block in bits [10 i, 10 i + 10), little-endian.  One
+ *                            channel's stream is fri_plan_emission_packed_bytes() bytes (count rounded
+ *                            up to a multiple of 64 symbols, padding = symbol 0), layout
+ *                            [n_frames][C][packed_bytes].  1.25 bytes per coefficient over PCIe
+ *                            instead of 2; encode saturates at -512 / +511 (cannot happen for an
+ *                            8-bit image: |k| <= 255).
+ */
 uint64_t fri_plan_emission_count(fri_plan *plan);
+uint64_t fri_plan_emission_packed_bytes(fri_plan *plan);
+int fri_emit_device10(fri_plan *plan, const int32_t *d_coefs, uint32_t n_frames, uint8_t *d_out, void *stream);
+int fri_encode_tq_emit10(fri_plan *plan, const void *pixels, uint32_t n_frames, const int32_t *q, uint8_t *out);
+int fri_unemit_device10(fri_plan *plan, const uint8_t *d_streams, uint32_t n_frames, int32_t *d_coefs, void *stream);
+int fri_decode_tq_emit10(fri_plan *plan, const uint8_t *streams, uint32_t n_frames, const int32_t *q, int dequant_mode,
+                         void *pixels);
 int fri_plan_emission_order(fri_plan *plan, uint32_t *order);
 int fri_emit_device(fri_plan *plan, const int32_t *d_coefs, uint32_t n_frames, int32_t *d_out, void *stream);
 int fri_encode_tq_emit(fri_plan *plan, const void *pixels, uint32_t n_frames, const int32_t *q, int32_t *out);
@@ -195,8 +224,8 @@ int fri_plan_set_bands(fri_plan *plan, int bands);
  * Asynchronous mode of the host-buffer entry points ("async variants enqueue on
  * the handle's stream and expose sync()"): with fri_plan_set_async(plan, 1) the fri_encode_tq* /
  * fri_decode_tq* / *_emit* calls return once their copies and kernels are enqueued on the plan's
- * streams, and fri_plan_sync(plan) waits for them.  The host buffers must be pinned (fri_host_alloc)
- * and stay untouched until the sync.  One host thread can this way keep an encoder handle and a
+ * streams, and fri_plan_sync(plan) waits for them.  The host buffers must be pinned (fri_host_alloc;
+ * anything else is rejected with FRI_E_INVALID) and stay untouched until the sync.  One host thread can this way keep an encoder handle and a
  * decoder handle busy at once — the same full-duplex overlap two threads get.  Errors of the
  * enqueued work surface at the sync (or at the next call).
  */
