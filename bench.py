@@ -1,18 +1,26 @@
 #!/usr/bin/env python
 """bench.py — throughput of the fractal transform + quantization hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload frame|batch256]
 
-One step = one pass of the hot path over one frame per GPU: the fused forward transform +
+One step = one pass of the hot path over one batch of synthetic input: the fused forward transform +
 quantization (encode) followed by the fused dequantization + inverse transform (decode).
-Workload: BASELINE.json configs[1], a synthetic 4096x4096 8-bit RGB image (one per GPU; frames
-are independent, so N GPUs = N frames, weak scaling, no data-path collective).
 
-Prints ONE JSON line (rank 0).  `value` is device-resident MPix/s, `e2e` the same metric through
-the host-buffer C-ABI entry points (pinned host memory, copies inside the timed region; four driving
-patterns are timed, the headline one is named in `e2e.api`),
-`roofline` the dominant kernel against the measured HBM copy bandwidth, `cpu_baseline` the CPU
-oracle (single thread, like the reference) on the same image.
+Workloads
+  frame     (default) BASELINE.json configs[1]: one synthetic 4096x4096 8-bit RGB image per GPU and step
+            (frames are independent, so N GPUs = N frames, weak scaling, no data-path collective);
+  batch256  BASELINE.json configs[2]: a batch of 256 synthetic 3840x2160 RGB frames, sharded over the ranks with
+            frave_b200.sharding.shard_frames (256 / N frames per GPU and step, strong scaling).
+
+Prints ONE JSON line (rank 0).  `value` is device-resident MPix/s over exactly --steps steps, `e2e` the same
+metric through the host-buffer C-ABI entry points (pinned host memory, copies inside the timed region),
+`roofline` the dominant kernel against the measured HBM copy bandwidth, `cpu_baseline` the CPU oracle (single
+thread, like the reference) on the same image.
+
+Per-kernel durations do not depend on --steps: each kernel is launched `KERNEL_REPS` (>= 200) times back to
+back on the launching stream between two CUDA events (the average launch duration a stream of frames sees,
+programmatic dependent launch included), and the isolated, event-bracketed single-launch median is reported
+beside it.
 """
 from __future__ import annotations
 
@@ -23,6 +31,7 @@ import statistics
 import subprocess
 import sys
 import tempfile
+import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -35,7 +44,9 @@ METRIC = "MPix/s fractal transform+quant (enc/dec)"
 UNIT = "MPix/s"
 W, H, C = 4096, 4096, 3
 FRAMES = 1                  # frames per GPU per step (one batched launch per direction)
+BATCH_FRAMES = 256          # --workload batch256
 PREHEAT_S = 1.0
+KERNEL_REPS = 200           # back-to-back launches per kernel for the roofline numbers, whatever --steps is
 SMALLEST_LAYER_DIVISOR = 4  # q[8] = q[9] = 4: "dividing the smallest layer of fractals" (README.md:12)
 BYTES_PER_SAMPLE = 5        # u8 pixel + i32 coefficient, either direction
 N_SETS = int(os.environ.get("FRI_BENCH_SETS", "4"))  # rotating buffer sets: 4 x (50 + 201 + 50 MB) = 1.2 GB >> 126 MB of L2
@@ -47,7 +58,18 @@ def quant_matrix() -> np.ndarray:
     return q
 
 
-def workload_config(n_gpus: int) -> dict:
+def workload_config(n_gpus: int, workload: str) -> dict:
+    if workload == "batch256":
+        per = [len(_shard(BATCH_FRAMES, r, n_gpus)) for r in range(n_gpus)]
+        return {
+            "workload": f"batch of {BATCH_FRAMES} synthetic {W}x{H}x{C} u8 frames (BASELINE.json configs[2]) sharded over "
+                        f"{n_gpus} GPU(s) with sharding.shard_frames; step = fused transform+quant encode then fused "
+                        f"dequant+inverse decode of the whole batch, one batched launch per direction and GPU",
+            "frames_per_gpu": per, "global_frames": BATCH_FRAMES, "depth": 9,
+            "quant": f"q[8]=q[9]={SMALLEST_LAYER_DIVISOR}, other layers 1; decode divides again like quantization.rs:37",
+            "l2": f"{max(per) * W * H * C * 5 / 1e9:.1f} GB touched per launch and GPU, far beyond the 126 MB L2",
+            "parallelism": f"frames sharded over {n_gpus} GPU(s), no collective",
+        }
     return {
         "workload": f"{W}x{H}x{C} u8 synthetic image{' (BASELINE.json configs[1])' if (W, H, C, FRAMES) == (4096, 4096, 3, 1) else ''}"
                     f"; step = fused transform+quant encode then fused dequant+inverse decode of {FRAMES} frame(s) per GPU",
@@ -59,6 +81,11 @@ def workload_config(n_gpus: int) -> dict:
               f"launch reads cold HBM",
         "parallelism": f"frames sharded over {n_gpus} GPU(s), no collective",
     }
+
+
+def _shard(n_frames: int, rank: int, world: int) -> range:
+    from frave_b200 import sharding
+    return sharding.shard_frames(n_frames, rank, world)
 
 
 def measured_peak_gbs() -> tuple[float, str]:
@@ -145,19 +172,35 @@ def cpu_pass(O, img, centers, some, q, nthreads, tiles=None, coef_buf=None, out_
     return time.perf_counter() - t0
 
 
+def oracle_lattice(O) -> tuple[np.ndarray, float]:
+    """The reference's tile list from the ORACLE alone (no libfri_cuda involved): fractal_divide's BFS
+    (wavelet_transform.rs:450-484) and the retain rule (:415-416, a tile survives iff one of its 512 leaves is
+    inside the image).  Returns (retained centres, seconds the BFS took)."""
+    from oracle import fri_oracle_np as N
+    t0 = time.perf_counter()
+    built = O.fractal_divide(W, H)
+    t_bfs = time.perf_counter() - t0
+    off = N.leaf_offsets(9)
+    keep = np.zeros(len(built), bool)
+    for lo in range(0, len(built), 8192):
+        c = built[lo:lo + 8192]
+        x, y = c[:, 0:1] + off[None, :, 0], c[:, 1:2] + off[None, :, 1]
+        keep[lo:lo + 8192] = ((x >= 0) & (y >= 0) & (x < W) & (y < H)).any(axis=1)
+    return np.ascontiguousarray(built[keep]), t_bfs
+
+
 def run_reference(args, rank: int) -> None:
-    """--impl reference: the reference's CPU path.  The reference is pure Rust and cannot be built
-    here (no cargo/rustc), so this times the C oracle restating it, on all host threads."""
+    """--impl reference: the reference's CPU path.  The reference is pure Rust and cannot be built here (no
+    cargo/rustc), so this times the C oracle restating it (oracle/ only — nothing of frave_b200 is loaded), on
+    all host threads."""
     if rank != 0:
         return
-    from frave_b200 import capi
     from oracle import c_oracle as O
 
     threads = host_threads()
     q = quant_matrix()
     img = synthetic_image(2)
-    plan = capi.Plan(W, H, C, device=-1)  # host-only plan: tile list, no GPU involved
-    centers = plan.centers()
+    centers, t_bfs = oracle_lattice(O)
     n_tiles = len(centers)
     # calibrate, then bound the per-step sample so that the whole run stays within ~90 s
     probe = np.arange(min(2048, n_tiles))
@@ -179,14 +222,45 @@ def run_reference(args, rank: int) -> None:
     line = {
         "impl": "reference", "metric": METRIC, "value": mpix, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "i32", "data": "synthetic", "config": workload_config(args.gpus),
+        "vs_baseline": None, "dtype": "i32", "data": "synthetic", "config": workload_config(args.gpus, "frame"),
         "cpu_baseline": {"value": mpix, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
         "e2e": {"value": mpix, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "threads": threads,
+        "lattice_build_ms": 1e3 * t_bfs,
+        "lattice_note": "fractal_divide BFS of the C oracle for this image size, NOT inside the timed region; the real "
+                        "reference rebuilds the lattice (plus 511 HashMap inserts per tile) on every encode and every "
+                        "decode (wavelet_transform.rs:405-410, :392-403), so the timed arithmetic-only figure flatters it",
         "note": "reference is Rust and unbuildable here (no cargo); timed the C oracle port of its hot path, "
-                "tiles split over all host threads",
+                "tiles split over all host threads; tile list from the oracle's own BFS + retain (no libfri_cuda)",
     }
     print(json.dumps(line), flush=True)
+
+
+def b2b(fn, reps: int, torch) -> float:
+    """Average duration (ms) of `reps` back-to-back calls of fn(i) between two CUDA events on the current stream."""
+    for i in range(3):
+        fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def isolated(fn, reps: int, torch) -> float:
+    """Median duration (ms) of single launches, each bracketed by its own pair of CUDA events."""
+    evs = []
+    for i in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn(i)
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    return statistics.median(a.elapsed_time(b) for a, b in evs)
 
 
 def run_b200(args, rank: int, local_rank: int, world: int) -> None:
@@ -202,51 +276,64 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     q = quant_matrix()
+    batch = args.workload == "batch256"
+    frames = len(_shard(BATCH_FRAMES, rank, world)) if batch else FRAMES
+    n_sets = 1 if batch else N_SETS  # a 256-frame shard is tens of GB per launch: no rotation needed
+    t0 = time.perf_counter()
     plan = capi.Plan(W, H, C, device=local_rank)
+    plan_build_ms = 1e3 * (time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    emission_count = plan.emission_count()  # builds the emission order (the *_emit* entry points need it)
+    emission_build_ms = 1e3 * (time.perf_counter() - t0)
     stream = torch.cuda.current_stream().cuda_stream
 
-    # ---- buffers: N_SETS rotating sets, synthetic pixels generated per rank
+    # ---- buffers: rotating sets, synthetic pixels generated per rank
     img0 = synthetic_image(2 + rank)
     gen = torch.Generator(device=dev).manual_seed(1000 + rank)
     px = []
-    for _ in range(N_SETS):
-        t = torch.randint(0, 256, (FRAMES, H, W, C), generator=gen, device=dev, dtype=torch.int32).to(torch.uint8)
+    for _ in range(n_sets):
+        t = torch.empty((frames, H, W, C), dtype=torch.uint8, device=dev)
+        for f0 in range(0, frames, 8):  # generated in slices: randint works in int64
+            n = min(8, frames - f0)
+            t[f0:f0 + n] = torch.randint(0, 256, (n, H, W, C), generator=gen, device=dev, dtype=torch.int32).to(torch.uint8)
         px.append(t)
     px[0][0] = torch.from_numpy(img0).to(dev)
-    coefs = [torch.empty((FRAMES,) + plan.coef_shape, dtype=torch.int32, device=dev) for _ in range(N_SETS)]
-    outs = [torch.empty((FRAMES, H, W, C), dtype=torch.uint8, device=dev) for _ in range(N_SETS)]
+    coefs = [torch.empty((frames,) + plan.coef_shape, dtype=torch.int32, device=dev) for _ in range(n_sets)]
+    outs = [torch.empty((frames, H, W, C), dtype=torch.uint8, device=dev) for _ in range(n_sets)]
 
     # sanity (untimed): encode -> decode is the identity at q == 1
-    plan.encode_device(px[0].data_ptr(), FRAMES, coefs[0].data_ptr(), None, stream)
-    plan.decode_device(coefs[0].data_ptr(), FRAMES, outs[0].data_ptr(), None, False, stream)
+    plan.encode_device(px[0].data_ptr(), frames, coefs[0].data_ptr(), None, stream)
+    plan.decode_device(coefs[0].data_ptr(), frames, outs[0].data_ptr(), None, False, stream)
     torch.cuda.synchronize()
     if not torch.equal(px[0], outs[0]) and not os.environ.get("FRI_BENCH_NO_SANITY"):  # (timing-only hack builds)
         raise RuntimeError("sanity check failed: encode -> decode is not lossless at q == 1")
-    for s in range(N_SETS):
-        plan.encode_device(px[s].data_ptr(), FRAMES, coefs[s].data_ptr(), q, stream)
+    for s in range(n_sets):
+        plan.encode_device(px[s].data_ptr(), frames, coefs[s].data_ptr(), q, stream)
     torch.cuda.synchronize()
 
     launches = 0
 
-    def step(i: int, ev=None) -> None:
+    def enc(i: int) -> None:
         nonlocal launches
-        a, b = i % N_SETS, (i + N_SETS // 2) % N_SETS
-        if ev:
-            ev[0].record()
-        plan.encode_device(px[a].data_ptr(), FRAMES, coefs[a].data_ptr(), q, stream)
+        a = i % n_sets
+        plan.encode_device(px[a].data_ptr(), frames, coefs[a].data_ptr(), q, stream)
         launches += plan.last_launches
-        if ev:
-            ev[1].record()
-        plan.decode_device(coefs[b].data_ptr(), FRAMES, outs[b].data_ptr(), q, False, stream)
+
+    def dec(i: int) -> None:
+        nonlocal launches
+        b = (i + n_sets // 2) % n_sets
+        plan.decode_device(coefs[b].data_ptr(), frames, outs[b].data_ptr(), q, False, stream)
         launches += plan.last_launches
-        if ev:
-            ev[2].record()
+
+    def step(i: int) -> None:
+        enc(i)
+        dec(i)
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     t_end = time.perf_counter() + PREHEAT_S  # pre-heat so clocks are sampled under the same load
     i = 0
     while time.perf_counter() < t_end:
-        for _ in range(max(1, 50 // FRAMES)):
+        for _ in range(max(1, 50 // frames)):
             step(i)
             i += 1
         torch.cuda.synchronize()
@@ -257,210 +344,226 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
         dist.barrier()
     torch.cuda.synchronize()
 
-    events = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    # ---- the timed region: exactly --steps steps, device events on the launching stream, nothing in between
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches = 0
     start.record()
     for k in range(args.steps):
-        step(k, events[k])
+        step(k)
     end.record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    clocks = sampler.stop() if sampler else None
     elapsed_ms = start.elapsed_time(end)
-    enc_ms = statistics.fmean(e[0].elapsed_time(e[1]) for e in events)
-    dec_ms = statistics.fmean(e[1].elapsed_time(e[2]) for e in events)
     timed_launches = launches
+
+    # ---- per-kernel durations, independent of --steps: KERNEL_REPS back-to-back launches of one kernel between
+    # two events (what a stream of frames sees), and the isolated single-launch median
+    reps = max(8, KERNEL_REPS // frames) if not batch else 4
+    enc_ms, dec_ms = b2b(enc, reps, torch), b2b(dec, reps, torch)
+    enc_iso, dec_iso = isolated(enc, min(reps, 200), torch), isolated(dec, min(reps, 200), torch)
+    clocks = sampler.stop() if sampler else None
 
     # ---- the same step on int16 coefficient arrays (fri_*_tq_device16): 3 B per sample instead of 5,
     # reported as its own variant with its own byte count; the headline stays int32
-    c16 = [torch.empty((FRAMES,) + plan.coef_shape, dtype=torch.int16, device=dev) for _ in range(N_SETS)]
-    for s_ in range(N_SETS):
-        plan.encode_device(px[s_].data_ptr(), FRAMES, c16[s_].data_ptr(), q, stream, half=True)
-    v_steps = min(args.steps, 100)
-    vev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(v_steps)]
-    for k in range(-3, v_steps):
-        a, b = k % N_SETS, (k + N_SETS // 2) % N_SETS
-        if k >= 0:
-            vev[k][0].record()
-        plan.encode_device(px[a].data_ptr(), FRAMES, c16[a].data_ptr(), q, stream, half=True)
-        if k >= 0:
-            vev[k][1].record()
-        plan.decode_device(c16[b].data_ptr(), FRAMES, outs[b].data_ptr(), q, False, stream, half=True)
-        if k >= 0:
-            vev[k][2].record()
-    torch.cuda.synchronize()
-    v_enc = statistics.fmean(e[0].elapsed_time(e[1]) for e in vev)
-    v_dec = statistics.fmean(e[1].elapsed_time(e[2]) for e in vev)
-    del c16
+    v_enc = v_dec = 0.0
+    if not batch:
+        c16 = [torch.empty((frames,) + plan.coef_shape, dtype=torch.int16, device=dev) for _ in range(n_sets)]
+        for s_ in range(n_sets):
+            plan.encode_device(px[s_].data_ptr(), frames, c16[s_].data_ptr(), q, stream, half=True)
+        v_enc = b2b(lambda i: plan.encode_device(px[i % n_sets].data_ptr(), frames, c16[i % n_sets].data_ptr(), q, stream, half=True),
+                    reps, torch)
+        v_dec = b2b(lambda i: plan.decode_device(c16[i % n_sets].data_ptr(), frames, outs[i % n_sets].data_ptr(), q, False, stream,
+                                                 half=True), reps, torch)
+        del c16
 
     # ---- steady state: BASELINE.json configs[2] per-GPU share at 8 GPUs (32 batched 4K frames in one
     # launch per direction).  Reported beside the headline because a single 4096^2 frame is a ~50 us
     # launch whose ramp-up and last partial wave cost 15-25 %.
     batched = None
-    if not args.no_batched:
+    if not args.no_batched and not batch:
         bw, bh, bf = 3840, 2160, 32
         bplan = capi.Plan(bw, bh, C, device=local_rank)
         bpx = torch.randint(0, 256, (bf, bh, bw, C), generator=gen, device=dev, dtype=torch.int32).to(torch.uint8)
         bco = torch.empty((bf,) + bplan.coef_shape, dtype=torch.int32, device=dev)
         bout = torch.empty_like(bpx)
-        bsteps = 8
-        bev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(bsteps)]
-        for k in range(-2, bsteps):
-            if k >= 0:
-                bev[k][0].record()
-            bplan.encode_device(bpx.data_ptr(), bf, bco.data_ptr(), q, stream)
-            if k >= 0:
-                bev[k][1].record()
-            bplan.decode_device(bco.data_ptr(), bf, bout.data_ptr(), q, False, stream)
-            if k >= 0:
-                bev[k][2].record()
-        torch.cuda.synchronize()
-        b_enc = statistics.fmean(e[0].elapsed_time(e[1]) for e in bev)
-        b_dec = statistics.fmean(e[1].elapsed_time(e[2]) for e in bev)
+        b_enc = b2b(lambda i: bplan.encode_device(bpx.data_ptr(), bf, bco.data_ptr(), q, stream), 8, torch)
+        b_dec = b2b(lambda i: bplan.decode_device(bco.data_ptr(), bf, bout.data_ptr(), q, False, stream), 8, torch)
         batched = (bw, bh, bf, b_enc, b_dec)
         del bpx, bco, bout
         bplan.close()
 
     # ---- end to end through the host-buffer C ABI: pinned host memory, H2D and D2H in the timed region.
-    # Four ways to drive the same two stage calls; every step moves one frame through encode and one
-    # through decode, each with its own host->device and device->host copies:
+    # Every e2e step moves one frame through encode and one through decode, each with its own host->device and
+    # device->host copies.  Driving patterns:
     #   serial  = one host thread calls encode, then decode (the reference's single-threaded shape);
-    #   duplex  = an encoder thread and a decoder thread, one plan handle each (the ABI is re-entrant
-    #             across handles), so one call's device->host copy overlaps the other's host->device
-    #             copy on the full-duplex PCIe link;
-    #   i32/i16 = coefficient type on the host side of the copy (fri_*_tq / fri_*_tq16).
-    import threading
-
+    #   duplex  = an encoder thread and a decoder thread, one plan handle each (the ABI is re-entrant across
+    #             handles), so one call's device->host copy overlaps the other's host->device copy (PCIe is
+    #             full duplex);
+    #   async   = one thread, both handles in asynchronous mode, both synced every step;
+    # and host-side coefficient formats: i32 blocks (fri_*_tq), i16 blocks (fri_*_tq16), p10 = emission-ordered
+    # streams in the 10-bit packed transport (fri_*_tq_emit10: what the host entropy coder consumes, 1.25 B per
+    # coefficient).
     e2e_steps = max(4, min(args.steps, 12))
-    px_h = capi.PinnedBuffer((1, H, W, C), np.uint8)
-    out_h = capi.PinnedBuffer((1, H, W, C), np.uint8)
-    px_h.array[0] = img0
-    dplan = capi.Plan(W, H, C, device=local_rank)  # the decoder thread's handle
-    e2e = {}
-    h2d = d2h = 0
-    for cdt, tag in ((np.int32, "i32"), (np.int16, "i16")):
-        if args.no_e2e:
-            e2e.update({"serial_" + tag: float("inf"), "duplex_" + tag: float("inf"), "async_" + tag: float("inf")})
-            continue
-        cf_enc = capi.PinnedBuffer((1,) + plan.coef_shape, cdt)
-        cf_dec = capi.PinnedBuffer((1,) + plan.coef_shape, cdt)
-        plan.encode(px_h.array, q, out=cf_enc.array)  # warm-up (allocates the plans' device slots)
-        cf_dec.array[...] = cf_enc.array
-        dplan.decode(cf_dec.array, q, out=out_h.array)
-        plan.decode(cf_dec.array, q, out=out_h.array)
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            plan.encode(px_h.array, q, out=cf_enc.array)
-            plan.decode(cf_enc.array, q, out=out_h.array)
-        e2e["serial_" + tag] = time.perf_counter() - t0
+    e2e, e2e_bytes = {}, {}
+    if not args.no_e2e:
+        px_h = capi.PinnedBuffer((1, H, W, C), np.uint8)
+        out_h = capi.PinnedBuffer((1, H, W, C), np.uint8)
+        px_h.array[0] = img0
+        dplan = capi.Plan(W, H, C, device=local_rank)  # the decoder thread's handle
+        dplan.emission_count()
 
-        errors = []
+        def duplex(enc_call, dec_call) -> float:
+            errors = []
 
-        def enc_loop():
-            try:
-                for _ in range(e2e_steps):
-                    plan.encode(px_h.array, q, out=cf_enc.array)
-            except Exception as exc:  # surfaced after the join
-                errors.append(exc)
+            def loop(call):
+                try:
+                    for _ in range(e2e_steps):
+                        call()
+                except Exception as exc:  # surfaced after the join
+                    errors.append(exc)
 
-        def dec_loop():
-            try:
-                for _ in range(e2e_steps):
-                    dplan.decode(cf_dec.array, q, out=out_h.array)
-            except Exception as exc:
-                errors.append(exc)
+            if world > 1:
+                dist.barrier()
+            th = [threading.Thread(target=loop, args=(enc_call,)), threading.Thread(target=loop, args=(dec_call,))]
+            t0 = time.perf_counter()
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            dt = time.perf_counter() - t0
+            if errors:
+                raise errors[0]
+            return dt
 
-        if world > 1:
-            dist.barrier()
-        plan.set_bands(1)   # concurrent callers: the other thread's call supplies the overlap (fri_plan_set_bands)
-        dplan.set_bands(1)
-        th = [threading.Thread(target=enc_loop), threading.Thread(target=dec_loop)]
-        t0 = time.perf_counter()
-        for t in th:
-            t.start()
-        for t in th:
-            t.join()
-        e2e["duplex_" + tag] = time.perf_counter() - t0
-        if errors:
-            raise errors[0]
-        # the same overlap from ONE host thread: asynchronous mode, both handles enqueued, then both synced
-        plan.set_async(True)
-        dplan.set_async(True)
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            plan.encode(px_h.array, q, out=cf_enc.array)
+        for cdt, tag in ((np.int32, "i32"), (np.int16, "i16")):
+            cf_enc = capi.PinnedBuffer((1,) + plan.coef_shape, cdt)
+            cf_dec = capi.PinnedBuffer((1,) + plan.coef_shape, cdt)
+            plan.encode(px_h.array, q, out=cf_enc.array)  # warm-up (allocates the plans' device slots)
+            cf_dec.array[...] = cf_enc.array
             dplan.decode(cf_dec.array, q, out=out_h.array)
-            plan.sync()
-            dplan.sync()
-        e2e["async_" + tag] = time.perf_counter() - t0
-        plan.set_async(False)
-        dplan.set_async(False)
-        plan.set_bands(0)
-        dplan.set_bands(0)
-        h2d = px_h.array.nbytes + cf_dec.array.nbytes
-        d2h = cf_enc.array.nbytes + out_h.array.nbytes
-        cf_enc.free(); cf_dec.free()
-    dplan.close()
+            plan.decode(cf_dec.array, q, out=out_h.array)
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                plan.encode(px_h.array, q, out=cf_enc.array)
+                plan.decode(cf_enc.array, q, out=out_h.array)
+            e2e["serial_" + tag] = time.perf_counter() - t0
+            plan.set_bands(1)   # concurrent callers: the other thread's call supplies the overlap (fri_plan_set_bands)
+            dplan.set_bands(1)
+            e2e["duplex_" + tag] = duplex(lambda: plan.encode(px_h.array, q, out=cf_enc.array),
+                                          lambda: dplan.decode(cf_dec.array, q, out=out_h.array))
+            # the same overlap from ONE host thread: asynchronous mode, both handles enqueued, then both synced
+            plan.set_async(True)
+            dplan.set_async(True)
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                plan.encode(px_h.array, q, out=cf_enc.array)
+                dplan.decode(cf_dec.array, q, out=out_h.array)
+                plan.sync()
+                dplan.sync()
+            e2e["async_" + tag] = time.perf_counter() - t0
+            plan.set_async(False)
+            dplan.set_async(False)
+            plan.set_bands(0)
+            dplan.set_bands(0)
+            e2e_bytes[tag] = (px_h.array.nbytes + cf_dec.array.nbytes, cf_enc.array.nbytes + out_h.array.nbytes)
+            cf_enc.free(); cf_dec.free()
+        # 10-bit packed emission streams
+        nb = plan.emission_packed_bytes()
+        pk_enc = capi.PinnedBuffer((1, C, nb), np.uint8)
+        pk_dec = capi.PinnedBuffer((1, C, nb), np.uint8)
+        plan.encode_emit10(px_h.array, q, out=pk_enc.array)
+        pk_dec.array[...] = pk_enc.array
+        dplan.decode_emit10(pk_dec.array, q, out=out_h.array)
+        if not np.array_equal(out_h.array, plan.decode(plan.encode(px_h.array, q), q)):
+            raise RuntimeError("packed transport: decode of the packed streams differs from the block path")
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            plan.encode_emit10(px_h.array, q, out=pk_enc.array)
+            plan.decode_emit10(pk_enc.array, q, out=out_h.array)
+        e2e["serial_p10"] = time.perf_counter() - t0
+        e2e["duplex_p10"] = duplex(lambda: plan.encode_emit10(px_h.array, q, out=pk_enc.array),
+                                   lambda: dplan.decode_emit10(pk_dec.array, q, out=out_h.array))
+        e2e_bytes["p10"] = (px_h.array.nbytes + pk_dec.array.nbytes, pk_enc.array.nbytes + out_h.array.nbytes)
+        pk_enc.free(); pk_dec.free()
+        dplan.close()
+        px_h.free(); out_h.free()
     e2e_keys = sorted(e2e)
-    e2e_s = e2e["duplex_i16"]
 
+    vals = [elapsed_ms, enc_ms, dec_ms, enc_iso, dec_iso, v_enc, v_dec] + ([batched[3], batched[4]] if batched else [0.0, 0.0])
+    vals += [e2e[k] for k in e2e_keys]
     if world > 1:
-        vals = [elapsed_ms, e2e_s, enc_ms, dec_ms] + ([batched[3], batched[4]] if batched else [0.0, 0.0])
-        vals += [e2e[k] for k in e2e_keys] + [v_enc, v_dec]
         t = torch.tensor(vals, dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms, e2e_s, enc_ms, dec_ms, b0, b1 = (float(x) for x in t.tolist()[:6])
-        e2e = dict(zip(e2e_keys, (float(x) for x in t.tolist()[6:6 + len(e2e_keys)])))
-        v_enc, v_dec = (float(x) for x in t.tolist()[-2:])
-        if batched:
-            batched = batched[:3] + (b0, b1)
+        vals = [float(x) for x in t.tolist()]
         dist.barrier()
+    elapsed_ms, enc_ms, dec_ms, enc_iso, dec_iso, v_enc, v_dec, b0, b1 = vals[:9]
+    e2e = dict(zip(e2e_keys, vals[9:]))
+    if batched:
+        batched = batched[:3] + (b0, b1)
 
     if rank == 0:
-        pix_step = W * H * FRAMES * world  # pixels through encode+decode per step, all GPUs
+        total_frames = BATCH_FRAMES if batch else FRAMES * world
+        pix_step = W * H * total_frames  # pixels through encode+decode per step, all GPUs
         value = pix_step * args.steps / (elapsed_ms * 1e-3) / 1e6
-        e2e_value = W * H * world * e2e_steps / e2e_s / 1e6  # one frame per GPU per e2e step
         peak, peak_src = measured_peak_gbs()
-        alg_bytes = W * H * C * FRAMES * BYTES_PER_SAMPLE
+        alg_bytes = W * H * C * frames * BYTES_PER_SAMPLE  # per launch on one GPU (rank 0's shard)
 
-        def roof(ms: float, kernel: str) -> dict:
+        def roof(ms: float, iso_ms: float, kernel: str) -> dict:
             ach = alg_bytes / (ms * 1e-3) / 1e9
             return {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": ncu_traffic(kernel), "algorithmic_bytes": alg_bytes, "avg_launch_ms": ms,
-                    "peak_source": peak_src}
+                    "traffic": ncu_traffic(kernel) if not batch else None, "algorithmic_bytes": alg_bytes, "avg_launch_ms": ms,
+                    "timing": f"{reps} back-to-back launches between two CUDA events on the launching stream, inputs rotating "
+                              f"over {n_sets} buffer set(s); independent of --steps",
+                    "isolated_launch_ms": iso_ms, "isolated_frac": alg_bytes / (iso_ms * 1e-3) / 1e9 / peak,
+                    "frac_of_nominal_8TBs": ach / 8000.0, "peak_source": peak_src}
 
-        r_enc, r_dec = roof(enc_ms, f"fri_encode_kernel<{C},u8>"), roof(dec_ms, f"fri_decode_kernel<{C},u8>")
+        r_enc = roof(enc_ms, enc_iso, f"fri_encode_kernel<{C},u8>")
+        r_dec = roof(dec_ms, dec_iso, f"fri_decode_kernel<{C},u8>")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "i32", "data": "synthetic", "config": workload_config(world),
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "strong" if batch else "weak",
+            "vs_baseline": None, "dtype": "i32", "data": "synthetic", "config": workload_config(world, args.workload),
             "encode_mpix_s": pix_step / (enc_ms * 1e-3) / 1e6, "decode_mpix_s": pix_step / (dec_ms * 1e-3) / 1e6,
             "roofline": r_enc if enc_ms >= dec_ms else r_dec, "roofline_encode": r_enc, "roofline_decode": r_dec,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps,
-                    "api": "fri_encode_tq16 + fri_decode_tq16 (pinned host buffers, int16 coefficients on the host side), "
-                           "encoder thread and decoder thread with one plan handle each, one band per frame (fri_plan_set_bands(1))",
-                    "variants_mpix_s": {k: W * H * world * e2e_steps / v / 1e6 for k, v in e2e.items()},
-                    "variants": "serial = one thread, encode then decode; duplex = encoder and decoder threads; "
-                                "async = one thread, both handles in asynchronous mode (fri_plan_set_async / fri_plan_sync); "
-                                "i32 = fri_*_tq (4 B coefficients over PCIe: 255 MB each way per step), "
-                                "i16 = fri_*_tq16 (151 MB each way)"},
             "gpu_launches": timed_launches, "clocks": clocks, "launch": plan.launch_info(),
+            "plan_build_ms": plan_build_ms, "emission_order_build_ms": emission_build_ms,
+            "plan_note": "host work once per image size (lattice BFS, retain, chunk tables, upload; emission order = the "
+                         "reference's sort_lattice scan, needed by the *_emit* entry points only); outside the timed region",
         }
-        b16 = W * H * C * FRAMES * 3  # u8 pixel + i16 coefficient
-        line["int16_arrays"] = {
-            "note": "same step through fri_encode_tq_device16 / fri_decode_tq_device16 (int16 coefficient arrays, "
-                    "3 B per sample); a separate variant, not the headline",
-            "value": pix_step / ((v_enc + v_dec) * 1e-3) / 1e6, "unit": UNIT,
-            "encode": {"achieved": b16 / (v_enc * 1e-3) / 1e9, "frac": b16 / (v_enc * 1e-3) / 1e9 / peak, "avg_launch_ms": v_enc},
-            "decode": {"achieved": b16 / (v_dec * 1e-3) / 1e9, "frac": b16 / (v_dec * 1e-3) / 1e9 / peak, "avg_launch_ms": v_dec},
-            "algorithmic_bytes": b16, "unit_bw": "GB/s"}
+        if e2e:
+            best = min((k for k in e2e if k.startswith(("duplex", "async"))), key=lambda k: e2e[k])
+            fmt = best.split("_")[1]
+            api = {"i32": "fri_encode_tq + fri_decode_tq (int32 coefficient blocks on the host side)",
+                   "i16": "fri_encode_tq16 + fri_decode_tq16 (int16 coefficient blocks on the host side)",
+                   "p10": "fri_encode_tq_emit10 + fri_decode_tq_emit10 (emission-ordered streams, 10-bit packed symbols on the "
+                          "host side: what the reference's entropy coder consumes / produces)"}[fmt]
+            how = {"duplex": "encoder thread and decoder thread with one plan handle each",
+                   "async": "one thread, both handles in asynchronous mode", "serial": "one thread"}[best.split("_")[0]]
+            # one frame per GPU per e2e step
+            line["e2e"] = {
+                "value": W * H * world * e2e_steps / e2e[best] / 1e6, "unit": UNIT,
+                "h2d_bytes_per_step": e2e_bytes[fmt][0], "d2h_bytes_per_step": e2e_bytes[fmt][1], "steps": e2e_steps,
+                "api": f"{api}, pinned host buffers, {how}; one {W}x{H}x{C} frame per GPU and step",
+                "variant": best,
+                "variants_mpix_s": {k: W * H * world * e2e_steps / v / 1e6 for k, v in e2e.items()},
+                "variants": "serial = one thread, encode then decode; duplex = encoder and decoder threads; async = one thread, "
+                            "both handles asynchronous; i32 / i16 = coefficient blocks (4 / 2 B per coefficient over PCIe), "
+                            "p10 = emission-ordered 10-bit packed streams (1.25 B per coefficient)",
+                "limiter": "host<->device PCIe copies (both directions busy); kernels are a few percent of the step"}
+        if not batch:
+            b16 = W * H * C * frames * 3  # u8 pixel + i16 coefficient
+            line["int16_arrays"] = {
+                "note": "same step through fri_encode_tq_device16 / fri_decode_tq_device16 (int16 coefficient arrays, "
+                        "3 B per sample); a separate variant, not the headline",
+                "value": pix_step / ((v_enc + v_dec) * 1e-3) / 1e6, "unit": UNIT,
+                "encode": {"achieved": b16 / (v_enc * 1e-3) / 1e9, "frac": b16 / (v_enc * 1e-3) / 1e9 / peak, "avg_launch_ms": v_enc},
+                "decode": {"achieved": b16 / (v_dec * 1e-3) / 1e9, "frac": b16 / (v_dec * 1e-3) / 1e9 / peak, "avg_launch_ms": v_dec},
+                "algorithmic_bytes": b16, "unit_bw": "GB/s"}
         if batched:
             bw, bh, bf, b_enc, b_dec = batched
             bbytes = bw * bh * C * bf * BYTES_PER_SAMPLE
@@ -500,7 +603,6 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
                             "Fractal::new's per-tile containers (SipHash-1-3 HashMap inserts, Vec allocations; "
                             f"{n_sample} tiles sampled, {t_new:.2f} s per image and direction)"}}
         print(json.dumps(line), flush=True)
-    px_h.free(); out_h.free()
     plan.close()
     if world > 1:
         dist.destroy_process_group()
@@ -512,17 +614,25 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="frame", choices=["frame", "batch256"],
+                    help="frame = BASELINE.json configs[1] (default); batch256 = configs[2], 256 4K frames sharded over the ranks")
     ap.add_argument("--shape", default=None, help="WxHxC override for experiments (default: BASELINE.json configs[1])")
     ap.add_argument("--frames", type=int, default=1, help="frames per GPU per step (batched launch)")
+    ap.add_argument("--batch-frames", type=int, default=256, help="--workload batch256: total frames (experiments only)")
     ap.add_argument("--preheat", type=float, default=1.0, help="seconds of untimed load before the warm-up steps")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (experiments only)")
     ap.add_argument("--no-batched", action="store_true", help="skip the batched steady-state leg (experiments only)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (experiments only)")
     ap.add_argument("--divisor", type=int, default=None, help="smallest-layer divisor override (experiments only; default 4)")
     args = ap.parse_args()
-    global W, H, C, FRAMES, PREHEAT_S, SMALLEST_LAYER_DIVISOR
+    global W, H, C, FRAMES, PREHEAT_S, SMALLEST_LAYER_DIVISOR, BATCH_FRAMES
     if args.divisor is not None:
         SMALLEST_LAYER_DIVISOR = args.divisor
+    if args.workload == "batch256":
+        W, H, C = 3840, 2160, 3
+        BATCH_FRAMES = args.batch_frames
+        if args.steps == 500:
+            args.steps = 5  # a step is 256 frames (25 GB of traffic per direction)
     if args.shape:
         W, H, C = (int(v) for v in args.shape.lower().split("x"))
     FRAMES, PREHEAT_S = args.frames, args.preheat

@@ -1,6 +1,17 @@
-//! Safe wrapper over libfri_cuda's C ABI (include/fri_cuda.h).  Untested here: no cargo/rustc in
-//! the build image; every item maps 1:1 onto a prototype of the header.
+//! Wrapper over libfri_cuda's C ABI (include/fri_cuda.h).
+//!
+//! NEVER COMPILED IN THIS REPOSITORY'S ENVIRONMENT (no cargo/rustc in the image).  The `extern "C"` block
+//! below is checked mechanically against the header by tests/test_host.py::test_rust_extern_block_matches_header
+//! (every prototype bound, same argument count); the wrappers are meant to be reviewed by inspection.
+//!
+//! Soundness rules the wrappers enforce:
+//!   * every slice handed to the C side is length-checked against the plan's frame / coefficient sizes
+//!     BEFORE the call (a short slice is an `Err`, never an out-of-bounds access);
+//!   * host buffers of the fast path are `PinnedBuf`s (fri_host_alloc) — the path the measured end-to-end
+//!     numbers use; plain slices are accepted by the synchronous calls only;
+//!   * asynchronous mode is `unsafe`: the caller promises that the pinned buffers outlive `sync()`.
 use std::ffi::{c_char, c_int, c_void, CStr};
+use std::marker::PhantomData;
 
 #[repr(C)]
 pub struct FriPlan {
@@ -9,26 +20,54 @@ pub struct FriPlan {
 
 pub const FRI_DEQUANT_DIVIDE: c_int = 0; // quantization.rs:37 — the reference divides again
 pub const FRI_DEQUANT_MULTIPLY: c_int = 1;
+pub const FRI_BASE_DEPTH: u32 = 9; // BASE_FRAC_DEPTH, wavelet_transform.rs:39
 
 extern "C" {
+    fn fri_version() -> *const c_char;
     fn fri_last_error() -> *const c_char;
-    fn fri_plan_create(out: *mut *mut FriPlan, device: c_int, width: u32, height: u32, channels: u32, depth: u32,
-                       sample_bytes: u32) -> c_int;
+    fn fri_device_count() -> c_int;
+    fn fri_plan_create(out: *mut *mut FriPlan, device: c_int, width: u32, height: u32, channels: u32, depth: u32, sample_bytes: u32) -> c_int;
     fn fri_plan_destroy(plan: *mut FriPlan);
     fn fri_plan_num_tiles(plan: *const FriPlan) -> u32;
+    fn fri_plan_num_built(plan: *const FriPlan) -> u32;
+    fn fri_plan_num_full_tiles(plan: *const FriPlan) -> u32;
     fn fri_plan_coefs_per_frame(plan: *const FriPlan) -> u64;
+    fn fri_plan_pixels_covered(plan: *const FriPlan) -> u64;
+    fn fri_plan_launch_info(plan: *const FriPlan, info: *mut i32) -> c_int;
     fn fri_plan_centers(plan: *const FriPlan, centers: *mut i32) -> c_int;
     fn fri_plan_masks(plan: *const FriPlan, masks: *mut u32) -> c_int;
+    fn fri_encode_tq_device(plan: *const FriPlan, d_pixels: *const c_void, n_frames: u32, q: *const i32, d_coefs: *mut i32, stream: *mut c_void) -> c_int;
+    fn fri_decode_tq_device(plan: *const FriPlan, d_coefs: *const i32, n_frames: u32, q: *const i32, dequant_mode: c_int, d_pixels: *mut c_void, stream: *mut c_void) -> c_int;
+    fn fri_encode_tq_device16(plan: *const FriPlan, d_pixels: *const c_void, n_frames: u32, q: *const i32, d_coefs: *mut i16, stream: *mut c_void) -> c_int;
+    fn fri_decode_tq_device16(plan: *const FriPlan, d_coefs: *const i16, n_frames: u32, q: *const i32, dequant_mode: c_int, d_pixels: *mut c_void, stream: *mut c_void) -> c_int;
     fn fri_encode_tq(plan: *mut FriPlan, pixels: *const c_void, n_frames: u32, q: *const i32, coefs: *mut i32) -> c_int;
-    fn fri_decode_tq(plan: *mut FriPlan, coefs: *const i32, n_frames: u32, q: *const i32, dequant_mode: c_int,
-                     pixels: *mut c_void) -> c_int;
+    fn fri_decode_tq(plan: *mut FriPlan, coefs: *const i32, n_frames: u32, q: *const i32, dequant_mode: c_int, pixels: *mut c_void) -> c_int;
+    fn fri_encode_tq16(plan: *mut FriPlan, pixels: *const c_void, n_frames: u32, q: *const i32, coefs: *mut i16) -> c_int;
+    fn fri_decode_tq16(plan: *mut FriPlan, coefs: *const i16, n_frames: u32, q: *const i32, dequant_mode: c_int, pixels: *mut c_void) -> c_int;
+    fn fri_plan_emission_count(plan: *mut FriPlan) -> u64;
+    fn fri_plan_emission_packed_bytes(plan: *mut FriPlan) -> u64;
+    fn fri_plan_emission_order(plan: *mut FriPlan, order: *mut u32) -> c_int;
+    fn fri_emit_device(plan: *mut FriPlan, d_coefs: *const i32, n_frames: u32, d_out: *mut i32, stream: *mut c_void) -> c_int;
+    fn fri_emit_device16(plan: *mut FriPlan, d_coefs: *const i32, n_frames: u32, d_out: *mut i16, stream: *mut c_void) -> c_int;
+    fn fri_emit_device10(plan: *mut FriPlan, d_coefs: *const i32, n_frames: u32, d_out: *mut u8, stream: *mut c_void) -> c_int;
+    fn fri_encode_tq_emit(plan: *mut FriPlan, pixels: *const c_void, n_frames: u32, q: *const i32, out: *mut i32) -> c_int;
+    fn fri_encode_tq_emit16(plan: *mut FriPlan, pixels: *const c_void, n_frames: u32, q: *const i32, out: *mut i16) -> c_int;
+    fn fri_encode_tq_emit10(plan: *mut FriPlan, pixels: *const c_void, n_frames: u32, q: *const i32, out: *mut u8) -> c_int;
+    fn fri_unemit_device(plan: *mut FriPlan, d_streams: *const i32, n_frames: u32, d_coefs: *mut i32, stream: *mut c_void) -> c_int;
+    fn fri_unemit_device16(plan: *mut FriPlan, d_streams: *const i16, n_frames: u32, d_coefs: *mut i32, stream: *mut c_void) -> c_int;
+    fn fri_unemit_device10(plan: *mut FriPlan, d_streams: *const u8, n_frames: u32, d_coefs: *mut i32, stream: *mut c_void) -> c_int;
+    fn fri_decode_tq_emit(plan: *mut FriPlan, streams: *const i32, n_frames: u32, q: *const i32, dequant_mode: c_int, pixels: *mut c_void) -> c_int;
+    fn fri_decode_tq_emit16(plan: *mut FriPlan, streams: *const i16, n_frames: u32, q: *const i32, dequant_mode: c_int, pixels: *mut c_void) -> c_int;
+    fn fri_decode_tq_emit10(plan: *mut FriPlan, streams: *const u8, n_frames: u32, q: *const i32, dequant_mode: c_int, pixels: *mut c_void) -> c_int;
     fn fri_plan_set_bands(plan: *mut FriPlan, bands: c_int) -> c_int;
     fn fri_plan_set_async(plan: *mut FriPlan, on: c_int) -> c_int;
     fn fri_plan_sync(plan: *mut FriPlan) -> c_int;
-    // 16-bit transport of the same two calls (8-bit samples): half the bytes over PCIe
-    fn fri_encode_tq16(plan: *mut FriPlan, pixels: *const c_void, n_frames: u32, q: *const i32, coefs: *mut i16) -> c_int;
-    fn fri_decode_tq16(plan: *mut FriPlan, coefs: *const i16, n_frames: u32, q: *const i32, dequant_mode: c_int,
-                       pixels: *mut c_void) -> c_int;
+    fn fri_host_alloc(out: *mut *mut c_void, bytes: usize) -> c_int;
+    fn fri_host_free(p: *mut c_void);
+    fn fri_plan_last_launches(plan: *const FriPlan) -> u32;
+    fn fri_quant_divide(value: i32, q: i32) -> i32;
+    fn fri_quant_divide_magic(value: i32, q: i32) -> i32;
+    fn fri_quant_divide_small(value: i32, q: i32) -> i32;
 }
 
 fn check(rc: c_int) -> Result<(), String> {
@@ -40,58 +79,238 @@ fn check(rc: c_int) -> Result<(), String> {
     }
 }
 
+fn want_len(what: &str, got: usize, want: usize) -> Result<(), String> {
+    if got == want {
+        Ok(())
+    } else {
+        Err(format!("{what}: slice of {got} elements, the plan needs exactly {want}"))
+    }
+}
+
+pub fn version() -> String { unsafe { CStr::from_ptr(fri_version()) }.to_string_lossy().into_owned() }
+pub fn device_count() -> i32 { unsafe { fri_device_count() } }
+/// value / q exactly as the kernels compute it (truncation toward zero, quantization.rs:19).
+pub fn quant_divide(value: i32, q: i32) -> i32 { unsafe { fri_quant_divide(value, q) } }
+pub fn quant_divide_magic(value: i32, q: i32) -> i32 { unsafe { fri_quant_divide_magic(value, q) } }
+pub fn quant_divide_small(value: i32, q: i32) -> i32 { unsafe { fri_quant_divide_small(value, q) } }
+
+/// Page-locked host memory (fri_host_alloc): the buffers of the fast path — asynchronous copies at the
+/// link's full rate.  Owns its allocation; `T` is a plain integer type.
+pub struct PinnedBuf<T: Copy> {
+    ptr: *mut T,
+    len: usize,
+    _own: PhantomData<T>,
+}
+
+impl<T: Copy> PinnedBuf<T> {
+    pub fn new(len: usize) -> Result<Self, String> {
+        let mut p: *mut c_void = std::ptr::null_mut();
+        check(unsafe { fri_host_alloc(&mut p, len * std::mem::size_of::<T>()) })?;
+        unsafe { std::ptr::write_bytes(p as *mut u8, 0, len * std::mem::size_of::<T>()) };
+        Ok(PinnedBuf { ptr: p as *mut T, len, _own: PhantomData })
+    }
+    pub fn len(&self) -> usize { self.len }
+    pub fn is_empty(&self) -> bool { self.len == 0 }
+    pub fn as_slice(&self) -> &[T] { unsafe { std::slice::from_raw_parts(self.ptr, self.len) } }
+    pub fn as_mut_slice(&mut self) -> &mut [T] { unsafe { std::slice::from_raw_parts_mut(self.ptr, self.len) } }
+}
+
+impl<T: Copy> Drop for PinnedBuf<T> {
+    fn drop(&mut self) { unsafe { fri_host_free(self.ptr as *mut c_void) } }
+}
+unsafe impl<T: Copy + Send> Send for PinnedBuf<T> {}
+
 /// Lattice + launch geometry for one image size (replaces fractal_divide + Fractal::new + retain,
 /// wavelet_transform.rs:450-484, :42-69, :415-416, and from_metadata :392-403 on decode).
-pub struct Plan(*mut FriPlan);
+pub struct Plan {
+    raw: *mut FriPlan,
+    frame_bytes: usize,     // width * height * channels (8-bit samples)
+    coefs_per_frame: usize, // n_tiles * channels * 512
+    channels: usize,
+}
 
 impl Plan {
     pub fn new(device: i32, width: u32, height: u32, channels: u32) -> Result<Self, String> {
         let mut p = std::ptr::null_mut();
-        check(unsafe { fri_plan_create(&mut p, device, width, height, channels, 9, 1) })?;
-        Ok(Plan(p))
+        check(unsafe { fri_plan_create(&mut p, device, width, height, channels, FRI_BASE_DEPTH, 1) })?;
+        let coefs = unsafe { fri_plan_coefs_per_frame(p) } as usize;
+        Ok(Plan { raw: p, frame_bytes: width as usize * height as usize * channels as usize, coefs_per_frame: coefs, channels: channels as usize })
     }
-    pub fn num_tiles(&self) -> usize { unsafe { fri_plan_num_tiles(self.0) as usize } }
-    pub fn coefs_per_frame(&self) -> usize { unsafe { fri_plan_coefs_per_frame(self.0) as usize } }
+    pub fn num_tiles(&self) -> usize { unsafe { fri_plan_num_tiles(self.raw) as usize } }
+    pub fn num_built(&self) -> usize { unsafe { fri_plan_num_built(self.raw) as usize } }
+    pub fn num_full_tiles(&self) -> usize { unsafe { fri_plan_num_full_tiles(self.raw) as usize } }
+    pub fn coefs_per_frame(&self) -> usize { self.coefs_per_frame }
+    pub fn frame_bytes(&self) -> usize { self.frame_bytes }
+    pub fn pixels_covered(&self) -> u64 { unsafe { fri_plan_pixels_covered(self.raw) } }
+    pub fn last_launches(&self) -> u32 { unsafe { fri_plan_last_launches(self.raw) } }
+    pub fn launch_info(&self) -> Result<[i32; 16], String> {
+        let mut v = [0i32; 16];
+        check(unsafe { fri_plan_launch_info(self.raw, v.as_mut_ptr()) })?;
+        Ok(v)
+    }
     /// (re, im) of every retained tile, in the order of the coefficient blocks.
     pub fn centers(&self) -> Result<Vec<[i32; 2]>, String> {
         let mut v = vec![[0i32; 2]; self.num_tiles()];
-        check(unsafe { fri_plan_centers(self.0, v.as_mut_ptr() as *mut i32) })?;
+        check(unsafe { fri_plan_centers(self.raw, v.as_mut_ptr() as *mut i32) })?;
         Ok(v)
     }
     /// 512-bit Some/None mask per tile (bit i of word i/32 set <=> coefficient i is Some).
     pub fn masks(&self) -> Result<Vec<[u32; 16]>, String> {
         let mut v = vec![[0u32; 16]; self.num_tiles()];
-        check(unsafe { fri_plan_masks(self.0, v.as_mut_ptr() as *mut u32) })?;
+        check(unsafe { fri_plan_masks(self.raw, v.as_mut_ptr() as *mut u32) })?;
         Ok(v)
     }
+
+    // ---- the two stage calls, synchronous, any host memory (pageable slices take the driver's staging path)
     /// wavelet_transform::encode + quantization::encode (encoder.rs:26-33), fused.
-    pub fn encode_tq(&mut self, pixels: &[u8], q: &[i32; 32]) -> Result<Vec<i32>, String> {
-        let mut coefs = vec![0i32; self.coefs_per_frame()];
-        check(unsafe { fri_encode_tq(self.0, pixels.as_ptr() as *const c_void, 1, q.as_ptr(), coefs.as_mut_ptr()) })?;
-        Ok(coefs)
+    pub fn encode_tq(&mut self, pixels: &[u8], q: &[i32; 32], coefs: &mut [i32]) -> Result<(), String> {
+        want_len("pixels", pixels.len(), self.frame_bytes)?;
+        want_len("coefs", coefs.len(), self.coefs_per_frame)?;
+        check(unsafe { fri_encode_tq(self.raw, pixels.as_ptr() as *const c_void, 1, q.as_ptr(), coefs.as_mut_ptr()) })
     }
     /// quantization::decode + wavelet_transform::decode (decoder.rs:27-34), fused.
     pub fn decode_tq(&mut self, coefs: &[i32], q: &[i32; 32], pixels: &mut [u8]) -> Result<(), String> {
-        check(unsafe { fri_decode_tq(self.0, coefs.as_ptr(), 1, q.as_ptr(), FRI_DEQUANT_DIVIDE, pixels.as_mut_ptr() as *mut c_void) })
+        want_len("coefs", coefs.len(), self.coefs_per_frame)?;
+        want_len("pixels", pixels.len(), self.frame_bytes)?;
+        check(unsafe { fri_decode_tq(self.raw, coefs.as_ptr(), 1, q.as_ptr(), FRI_DEQUANT_DIVIDE, pixels.as_mut_ptr() as *mut c_void) })
     }
+    /// The same with int16 coefficients on the host side (every coefficient of an 8-bit image fits:
+    /// |residue| <= 255, wavelet_transform.rs:211-218); the glue widens while applying the mask.
+    pub fn encode_tq16(&mut self, pixels: &[u8], q: &[i32; 32], coefs: &mut [i16]) -> Result<(), String> {
+        want_len("pixels", pixels.len(), self.frame_bytes)?;
+        want_len("coefs", coefs.len(), self.coefs_per_frame)?;
+        check(unsafe { fri_encode_tq16(self.raw, pixels.as_ptr() as *const c_void, 1, q.as_ptr(), coefs.as_mut_ptr()) })
+    }
+    pub fn decode_tq16(&mut self, coefs: &[i16], q: &[i32; 32], pixels: &mut [u8]) -> Result<(), String> {
+        want_len("coefs", coefs.len(), self.coefs_per_frame)?;
+        want_len("pixels", pixels.len(), self.frame_bytes)?;
+        check(unsafe { fri_decode_tq16(self.raw, coefs.as_ptr(), 1, q.as_ptr(), FRI_DEQUANT_DIVIDE, pixels.as_mut_ptr() as *mut c_void) })
+    }
+
+    // ---- the fast path the end-to-end numbers measure: pinned buffers allocated once per image size
+    pub fn pinned_frame(&self) -> Result<PinnedBuf<u8>, String> { PinnedBuf::new(self.frame_bytes) }
+    pub fn pinned_coefs16(&self) -> Result<PinnedBuf<i16>, String> { PinnedBuf::new(self.coefs_per_frame) }
+    pub fn encode_tq16_pinned(&mut self, pixels: &PinnedBuf<u8>, q: &[i32; 32], coefs: &mut PinnedBuf<i16>) -> Result<(), String> {
+        let (p, c) = (pixels.as_slice().as_ptr(), coefs.as_mut_slice().as_mut_ptr());
+        want_len("pixels", pixels.len(), self.frame_bytes)?;
+        want_len("coefs", coefs.len(), self.coefs_per_frame)?;
+        check(unsafe { fri_encode_tq16(self.raw, p as *const c_void, 1, q.as_ptr(), c) })
+    }
+    pub fn decode_tq16_pinned(&mut self, coefs: &PinnedBuf<i16>, q: &[i32; 32], pixels: &mut PinnedBuf<u8>) -> Result<(), String> {
+        want_len("coefs", coefs.len(), self.coefs_per_frame)?;
+        want_len("pixels", pixels.len(), self.frame_bytes)?;
+        check(unsafe { fri_decode_tq16(self.raw, coefs.as_slice().as_ptr(), 1, q.as_ptr(), FRI_DEQUANT_DIVIDE, pixels.as_mut_slice().as_mut_ptr() as *mut c_void) })
+    }
+
+    // ---- emission order (entropy_coding.rs:283-329 over sort_lattice): flat streams for the host coder
+    pub fn emission_count(&mut self) -> usize { unsafe { fri_plan_emission_count(self.raw) as usize } }
+    pub fn emission_packed_bytes(&mut self) -> usize { unsafe { fri_plan_emission_packed_bytes(self.raw) as usize } }
+    pub fn emission_order(&mut self) -> Result<Vec<u32>, String> {
+        let mut v = vec![0u32; self.num_tiles() * 512];
+        check(unsafe { fri_plan_emission_order(self.raw, v.as_mut_ptr()) })?;
+        Ok(v)
+    }
+    /// pixels -> [C][emission_count] quantized Some coefficients in the order the entropy coder consumes them.
+    pub fn encode_tq_emit(&mut self, pixels: &[u8], q: &[i32; 32], out: &mut [i32]) -> Result<(), String> {
+        want_len("pixels", pixels.len(), self.frame_bytes)?;
+        let n = self.channels * self.emission_count();
+        want_len("streams", out.len(), n)?;
+        check(unsafe { fri_encode_tq_emit(self.raw, pixels.as_ptr() as *const c_void, 1, q.as_ptr(), out.as_mut_ptr()) })
+    }
+    pub fn encode_tq_emit16(&mut self, pixels: &[u8], q: &[i32; 32], out: &mut [i16]) -> Result<(), String> {
+        want_len("pixels", pixels.len(), self.frame_bytes)?;
+        let n = self.channels * self.emission_count();
+        want_len("streams", out.len(), n)?;
+        check(unsafe { fri_encode_tq_emit16(self.raw, pixels.as_ptr() as *const c_void, 1, q.as_ptr(), out.as_mut_ptr()) })
+    }
+    /// The same streams as 10-bit zig-zag symbols (utils.rs:34-40), 64 symbols per 80 bytes: [C][emission_packed_bytes].
+    pub fn encode_tq_emit10(&mut self, pixels: &[u8], q: &[i32; 32], out: &mut [u8]) -> Result<(), String> {
+        want_len("pixels", pixels.len(), self.frame_bytes)?;
+        let n = self.channels * self.emission_packed_bytes();
+        want_len("packed streams", out.len(), n)?;
+        check(unsafe { fri_encode_tq_emit10(self.raw, pixels.as_ptr() as *const c_void, 1, q.as_ptr(), out.as_mut_ptr()) })
+    }
+    pub fn decode_tq_emit(&mut self, streams: &[i32], q: &[i32; 32], pixels: &mut [u8]) -> Result<(), String> {
+        let n = self.channels * self.emission_count();
+        want_len("streams", streams.len(), n)?;
+        want_len("pixels", pixels.len(), self.frame_bytes)?;
+        check(unsafe { fri_decode_tq_emit(self.raw, streams.as_ptr(), 1, q.as_ptr(), FRI_DEQUANT_DIVIDE, pixels.as_mut_ptr() as *mut c_void) })
+    }
+    pub fn decode_tq_emit16(&mut self, streams: &[i16], q: &[i32; 32], pixels: &mut [u8]) -> Result<(), String> {
+        let n = self.channels * self.emission_count();
+        want_len("streams", streams.len(), n)?;
+        want_len("pixels", pixels.len(), self.frame_bytes)?;
+        check(unsafe { fri_decode_tq_emit16(self.raw, streams.as_ptr(), 1, q.as_ptr(), FRI_DEQUANT_DIVIDE, pixels.as_mut_ptr() as *mut c_void) })
+    }
+    pub fn decode_tq_emit10(&mut self, packed: &[u8], q: &[i32; 32], pixels: &mut [u8]) -> Result<(), String> {
+        let n = self.channels * self.emission_packed_bytes();
+        want_len("packed streams", packed.len(), n)?;
+        want_len("pixels", pixels.len(), self.frame_bytes)?;
+        check(unsafe { fri_decode_tq_emit10(self.raw, packed.as_ptr(), 1, q.as_ptr(), FRI_DEQUANT_DIVIDE, pixels.as_mut_ptr() as *mut c_void) })
+    }
+
     /// Bands per frame of the host-buffer calls: 0 = automatic (single caller), 1 when an encoder and a
     /// decoder thread drive one handle each.
-    pub fn set_bands(&mut self, bands: i32) -> Result<(), String> { check(unsafe { fri_plan_set_bands(self.0, bands) }) }
-    /// Asynchronous mode: encode_tq* / decode_tq* return once enqueued (the slices passed must then be
-    /// pinned memory from fri_host_alloc and must outlive the next `sync`).
-    pub fn set_async(&mut self, on: bool) -> Result<(), String> { check(unsafe { fri_plan_set_async(self.0, on as c_int) }) }
-    pub fn sync(&mut self) -> Result<(), String> { check(unsafe { fri_plan_sync(self.0) }) }
-    /// encode_tq with int16 coefficients on the host side (every coefficient of an 8-bit image fits:
-    /// |residue| <= 255, wavelet_transform.rs:211-218); widen while applying the mask.
-    pub fn encode_tq16(&mut self, pixels: &[u8], q: &[i32; 32]) -> Result<Vec<i16>, String> {
-        let mut coefs = vec![0i16; self.coefs_per_frame()];
-        check(unsafe { fri_encode_tq16(self.0, pixels.as_ptr() as *const c_void, 1, q.as_ptr(), coefs.as_mut_ptr()) })?;
-        Ok(coefs)
+    pub fn set_bands(&mut self, bands: i32) -> Result<(), String> { check(unsafe { fri_plan_set_bands(self.raw, bands) }) }
+
+    /// Asynchronous mode: the host-buffer calls return once enqueued.
+    /// # Safety
+    /// Every buffer passed to a call made in asynchronous mode must be a `PinnedBuf` (the library rejects
+    /// pageable memory with an error) that is neither dropped, read nor written until `sync()` has returned.
+    pub unsafe fn set_async(&mut self, on: bool) -> Result<(), String> { check(fri_plan_set_async(self.raw, on as c_int)) }
+    pub fn sync(&mut self) -> Result<(), String> { check(unsafe { fri_plan_sync(self.raw) }) }
+
+    // ---- device-resident entry points (raw device pointers from the caller's CUDA context)
+    /// # Safety
+    /// `d_pixels` / `d_coefs` must be device allocations of n_frames frames / coefficient blocks on the plan's
+    /// device, `stream` a cudaStream_t of that device (or null).
+    pub unsafe fn encode_tq_device(&self, d_pixels: *const c_void, n_frames: u32, q: &[i32; 32], d_coefs: *mut i32, stream: *mut c_void) -> Result<(), String> {
+        check(fri_encode_tq_device(self.raw, d_pixels, n_frames, q.as_ptr(), d_coefs, stream))
     }
-    /// decode_tq from int16 coefficients (a decodable container never holds more: 1024-symbol
-    /// alphabet, entropy_coding.rs:25).
-    pub fn decode_tq16(&mut self, coefs: &[i16], q: &[i32; 32], pixels: &mut [u8]) -> Result<(), String> {
-        check(unsafe { fri_decode_tq16(self.0, coefs.as_ptr(), 1, q.as_ptr(), FRI_DEQUANT_DIVIDE, pixels.as_mut_ptr() as *mut c_void) })
+    /// # Safety
+    /// See `encode_tq_device`.
+    pub unsafe fn decode_tq_device(&self, d_coefs: *const i32, n_frames: u32, q: &[i32; 32], d_pixels: *mut c_void, stream: *mut c_void) -> Result<(), String> {
+        check(fri_decode_tq_device(self.raw, d_coefs, n_frames, q.as_ptr(), FRI_DEQUANT_DIVIDE, d_pixels, stream))
+    }
+    /// # Safety
+    /// See `encode_tq_device`; int16 coefficient arrays.
+    pub unsafe fn encode_tq_device16(&self, d_pixels: *const c_void, n_frames: u32, q: &[i32; 32], d_coefs: *mut i16, stream: *mut c_void) -> Result<(), String> {
+        check(fri_encode_tq_device16(self.raw, d_pixels, n_frames, q.as_ptr(), d_coefs, stream))
+    }
+    /// # Safety
+    /// See `encode_tq_device`; int16 coefficient arrays.
+    pub unsafe fn decode_tq_device16(&self, d_coefs: *const i16, n_frames: u32, q: &[i32; 32], d_pixels: *mut c_void, stream: *mut c_void) -> Result<(), String> {
+        check(fri_decode_tq_device16(self.raw, d_coefs, n_frames, q.as_ptr(), FRI_DEQUANT_DIVIDE, d_pixels, stream))
+    }
+    /// # Safety
+    /// Device pointers: dense blocks in, [n_frames][C][emission_count] streams out.
+    pub unsafe fn emit_device(&mut self, d_coefs: *const i32, n_frames: u32, d_out: *mut i32, stream: *mut c_void) -> Result<(), String> {
+        check(fri_emit_device(self.raw, d_coefs, n_frames, d_out, stream))
+    }
+    /// # Safety
+    /// As `emit_device`, int16 streams.
+    pub unsafe fn emit_device16(&mut self, d_coefs: *const i32, n_frames: u32, d_out: *mut i16, stream: *mut c_void) -> Result<(), String> {
+        check(fri_emit_device16(self.raw, d_coefs, n_frames, d_out, stream))
+    }
+    /// # Safety
+    /// As `emit_device`, 10-bit packed streams ([n_frames][C][emission_packed_bytes], 16-byte aligned).
+    pub unsafe fn emit_device10(&mut self, d_coefs: *const i32, n_frames: u32, d_out: *mut u8, stream: *mut c_void) -> Result<(), String> {
+        check(fri_emit_device10(self.raw, d_coefs, n_frames, d_out, stream))
+    }
+    /// # Safety
+    /// Device pointers: streams in, dense blocks out (None slots zeroed).
+    pub unsafe fn unemit_device(&mut self, d_streams: *const i32, n_frames: u32, d_coefs: *mut i32, stream: *mut c_void) -> Result<(), String> {
+        check(fri_unemit_device(self.raw, d_streams, n_frames, d_coefs, stream))
+    }
+    /// # Safety
+    /// As `unemit_device`, int16 streams.
+    pub unsafe fn unemit_device16(&mut self, d_streams: *const i16, n_frames: u32, d_coefs: *mut i32, stream: *mut c_void) -> Result<(), String> {
+        check(fri_unemit_device16(self.raw, d_streams, n_frames, d_coefs, stream))
+    }
+    /// # Safety
+    /// As `unemit_device`, 10-bit packed streams.
+    pub unsafe fn unemit_device10(&mut self, d_streams: *const u8, n_frames: u32, d_coefs: *mut i32, stream: *mut c_void) -> Result<(), String> {
+        check(fri_unemit_device10(self.raw, d_streams, n_frames, d_coefs, stream))
     }
 }
 
@@ -100,5 +319,5 @@ impl Plan {
 unsafe impl Send for Plan {}
 
 impl Drop for Plan {
-    fn drop(&mut self) { unsafe { fri_plan_destroy(self.0) } }
+    fn drop(&mut self) { unsafe { fri_plan_destroy(self.raw) } }
 }

@@ -224,10 +224,30 @@ _WORKER = r"""
 import os, sys
 sys.path.insert(0, {root!r})
 import numpy as np, torch, torch.distributed as dist
-from frave_b200 import sharding
+from frave_b200 import capi, sharding
 from oracle import c_oracle as O
+import bench
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
 rank, world = dist.get_rank(), dist.get_world_size()
+# the product's host side of the N > 1 path: every rank builds the same plan (replicated, no exchange), takes its
+# contiguous block of the batch, and the per-rank frame counts bench.py reports add up to the batch
+with capi.Plan(3840, 2160, 3, device=-1) as plan:
+    meta = torch.tensor([plan.n_tiles, plan.coefs_per_frame, plan.n_built], dtype=torch.int64)
+gathered = [torch.zeros_like(meta) for _ in range(world)]
+dist.all_gather(gathered, meta)
+assert all(torch.equal(g, meta) for g in gathered) and meta[0].item() == 16541  # SURVEY.md §8(a)
+mine256 = sharding.shard_frames(256, rank, world)
+cnt = torch.tensor([len(mine256)], dtype=torch.int64)
+dist.all_reduce(cnt)
+assert cnt.item() == 256 and len(mine256) == 128
+bench.W, bench.H, bench.C = 3840, 2160, 3
+cfg = bench.workload_config(world, "batch256")
+assert cfg["frames_per_gpu"] == [128, 128] and cfg["global_frames"] == 256
+try:  # and there is no CPU path to fall back to on a rank without a device
+    capi.Plan(64, 64, 1, device=-1).encode(np.zeros((64, 64, 1), np.uint8))
+    raise SystemExit("compute call succeeded without a device")
+except capi.FriError as e:
+    assert e.code == capi.FRI_E_CUDA
 n_frames, h, w, c = 5, 40, 56, 3
 frames = [np.random.Generator(np.random.PCG64(100 + f)).integers(0, 256, (h, w, c), dtype=np.uint8) for f in range(n_frames)]
 mine = sharding.shard_frames(n_frames, rank, world)
@@ -264,3 +284,29 @@ def test_two_rank_sharding_over_gloo(tmp_path):
         out, _ = p.communicate(timeout=240)
         assert p.returncode == 0, out
         assert f"rank {r} ok" in out
+
+
+def _c_prototypes(text):
+    """name -> argument count of every fri_* prototype in a C header (comments stripped)."""
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(fri_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
+    return out
+
+
+def test_rust_extern_block_matches_header():
+    """rust/libfri-cuda/src/lib.rs cannot be compiled here (no cargo): its extern "C" block is diffed against
+    include/fri_cuda.h instead — every prototype bound, none invented, same argument counts."""
+    want = _c_prototypes(open(os.path.join(ROOT, "include", "fri_cuda.h")).read())
+    src = open(os.path.join(ROOT, "rust", "libfri-cuda", "src", "lib.rs")).read()
+    block = re.search(r'extern "C" \{(.*?)\n\}', src, flags=re.S).group(1)
+    got = {}
+    for m in re.finditer(r"\bfn (fri_[a-z0-9_]+)\s*\(([^)]*)\)", block):
+        args = m.group(2).strip()
+        got[m.group(1)] = 0 if not args else len([a for a in args.split(",") if a.strip()])
+    assert set(got) == set(want), set(got) ^ set(want)
+    assert got == want, {k: (got[k], want[k]) for k in want if got[k] != want[k]}
+    # the safe wrappers check slice lengths before crossing the boundary and keep async mode unsafe
+    assert "want_len(" in src and "pub unsafe fn set_async" in src and "struct PinnedBuf" in src
