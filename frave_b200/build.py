@@ -12,7 +12,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libfri_cuda.so")
-SOURCES = ["fri_api.cu", "fri_kernels.cu", "fri_plan.cpp", "fri_order.cpp"]
+SOURCES = ["fri_api.cu", "fri_kernels.cu", "fri_predict.cu", "fri_plan.cpp", "fri_order.cpp"]
 HEADERS = ["fri_geometry.h", "fri_plan.h", "fri_kernels.cuh", os.path.join("..", "..", "include", "fri_cuda.h")]
 
 NVCC_FLAGS = [

@@ -59,6 +59,7 @@ _SYMBOLS = [
     ("fri_encode_tq_emit10", C.c_int, [_P, _P, C.c_uint32, _P, _P]),
     ("fri_unemit_device10", C.c_int, [_P, _P, C.c_uint32, _P, _P]),
     ("fri_decode_tq_emit10", C.c_int, [_P, _P, C.c_uint32, _P, C.c_int, _P]),
+    ("fri_predict_device", C.c_int, [_P, _P, C.c_uint32, _P, _P, _P, _P, _P, _P, _P, _P]),
     ("fri_host_alloc", C.c_int, [C.POINTER(_P), C.c_size_t]),
     ("fri_host_free", None, [_P]),
     ("fri_plan_last_launches", C.c_uint32, [_P]),
@@ -355,6 +356,18 @@ class Plan:
 
     def unemit_device10(self, d_packed: int, n_frames: int, d_coefs: int, stream: int = 0) -> None:
         _check(lib().fri_unemit_device10(self._h, d_packed, n_frames, d_coefs, stream))
+
+    def predict_device(self, d_coefs: int, n_frames: int, value_params, width_params, d_bucket: int, d_pred: int, d_sym: int,
+                       d_hist: int, d_overflow: int = 0, stream: int = 0) -> None:
+        """Prediction + context bucketing of quantized dense blocks (fri_predict_device): value_params / width_params are
+        float32 [C, 3, 6]; outputs are device pointers (uint8 / int32 / uint16 [F, C, emission_count()], uint32
+        [F, C, 10, 1024], optional uint32 overflow counter)."""
+        vp = np.ascontiguousarray(value_params, dtype=np.float32)
+        wp = np.ascontiguousarray(width_params, dtype=np.float32)
+        if vp.shape != (self.channels, 3, 6) or wp.shape != (self.channels, 3, 6):
+            raise ValueError(f"predictor parameters must have shape ({self.channels}, 3, 6)")
+        _check(lib().fri_predict_device(self._h, d_coefs, n_frames, vp.ctypes.data, wp.ctypes.data, d_bucket, d_pred, d_sym,
+                                        d_hist, d_overflow or None, stream))
 
     def emit_device(self, d_coefs: int, n_frames: int, d_out: int, stream: int = 0, half: bool = False) -> None:
         """d_out: int32 (or, with half=True, int16) [n_frames, C, emission_count()] on the device."""

@@ -89,6 +89,10 @@ struct fri_plan {
     void *d_emit_goff = nullptr, *d_emit_dst = nullptr, *d_emit_loc = nullptr;  // the Some slots partitioned by group
     EmitTables emit_tables;
     bool emit_device_ready = false;     // all three tables uploaded
+    // prediction tables (computed on first use)
+    bool predict_ready = false;
+    void *d_pred_tile_at = nullptr, *d_pred_centers = nullptr, *d_pred_lut = nullptr, *d_pred_off = nullptr;
+    PredictTables predict_tables;
 };
 
 namespace {
@@ -366,6 +370,8 @@ void fri_plan_destroy(fri_plan *p)
         if (p->d_emit_dst) cudaFree(p->d_emit_dst);
         if (p->d_emit_loc) cudaFree(p->d_emit_loc);
         if (p->d_stage_list) cudaFree(p->d_stage_list);
+        for (void *d : {p->d_pred_tile_at, p->d_pred_centers, p->d_pred_lut, p->d_pred_off})
+            if (d) cudaFree(d);
     }
     delete p;
 }
@@ -984,6 +990,76 @@ int fri_decode_tq_emit16(fri_plan *p, const int16_t *streams, uint32_t n_frames,
 int fri_decode_tq_emit10(fri_plan *p, const uint8_t *streams, uint32_t n_frames, const int32_t *q, int dequant_mode, void *pixels)
 {
     return decode_emit_host(p, streams, StreamFmt::P10, n_frames, q, dequant_mode, pixels);
+}
+
+/* ---- prediction + context bucketing, encode side ------------------------ */
+static int ensure_predict_device(fri_plan *p)
+{
+    int rc = ensure_emission_device(p);
+    if (rc) return rc;
+    if (p->predict_ready) return FRI_OK;
+    LatticeIndex L;
+    std::vector<short2> off(kTileLeaves);
+    try {
+        build_lattice_index(p->plan, L);
+    } catch (const std::bad_alloc &) {
+        return fail(FRI_E_NOMEM, "out of host memory while building the lattice index");
+    }
+    for (int k = 0; k < kTileLeaves; ++k) off[k] = make_short2((short)L.off[k].x, (short)L.off[k].y);
+    auto upload = [&](void **d, const void *h, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc(d, bytes ? bytes : 4);
+        return e != cudaSuccess || bytes == 0 ? e : cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice);
+    };
+    cudaError_t e = upload(&p->d_pred_tile_at, L.tile_at.data(), L.tile_at.size() * sizeof(int32_t));
+    if (e == cudaSuccess) e = upload(&p->d_pred_centers, p->plan.centers.data(), p->plan.centers.size() * sizeof(int32_t));
+    if (e == cudaSuccess) e = upload(&p->d_pred_lut, L.lut, sizeof(L.lut));
+    if (e == cudaSuccess) e = upload(&p->d_pred_off, off.data(), off.size() * sizeof(short2));
+    if (e == cudaSuccess) e = configure_predict_kernel();
+    if (e != cudaSuccess) {
+        for (void **d : {&p->d_pred_tile_at, &p->d_pred_centers, &p->d_pred_lut, &p->d_pred_off}) {
+            if (*d) cudaFree(*d);
+            *d = nullptr;
+        }
+        return cuda_fail(e, "uploading the prediction tables");
+    }
+    PredictTables &t = p->predict_tables;
+    t.tile_at = static_cast<const int32_t *>(p->d_pred_tile_at);
+    t.centers = static_cast<const int32_t *>(p->d_pred_centers);
+    t.lut = static_cast<const uint16_t *>(p->d_pred_lut);
+    t.off = static_cast<const short2 *>(p->d_pred_off);
+    t.ax = L.ax; t.ay = L.ay; t.amin = L.amin; t.bmin = L.bmin; t.na = L.na; t.nb = L.nb;
+    for (int d = 0; d < 10; ++d) {
+        Vec2 nv[6] = {};
+        if (d >= 1) nearby_vectors(d, nv);
+        for (int j = 0; j < 6; ++j) t.nearby[d][j] = make_short2((short)nv[j].x, (short)nv[j].y);
+    }
+    p->predict_ready = true;
+    return FRI_OK;
+}
+
+int fri_predict_device(fri_plan *p, const int32_t *d_coefs, uint32_t n_frames, const float *value_params,
+                       const float *width_params, uint8_t *d_bucket, int32_t *d_pred, uint16_t *d_sym, uint32_t *d_hist,
+                       uint32_t *d_overflow, void *stream)
+{
+    int rc = enter_device(p);
+    if (rc) return rc;
+    if ((rc = ensure_predict_device(p))) return rc;
+    if (n_frames == 0) return FRI_OK;
+    if (!d_coefs || !d_bucket || !d_pred || !d_sym || !d_hist) return fail(FRI_E_INVALID, "NULL device buffer");
+    if (!value_params || !width_params) return fail(FRI_E_INVALID, "the predictor parameters are inputs: pass [C][3][6] floats each");
+    const Geometry &g = p->plan.geo;
+    PredictParams prm{};
+    std::memcpy(prm.value, value_params, sizeof(float) * 18 * g.channels);
+    std::memcpy(prm.width, width_params, sizeof(float) * 18 * g.channels);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FRI_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)n_frames * g.channels * 10 * 1024 * sizeof(uint32_t), st));
+    if (d_overflow) FRI_CUDA(cudaMemsetAsync(d_overflow, 0, sizeof(uint32_t), st));
+    uint32_t launches = 0;
+    const cudaError_t e = launch_predict(g, p->tables, p->emit_tables, p->predict_tables, prm, p->emit_src.size(), d_coefs, n_frames,
+                                         d_bucket, d_pred, d_sym, d_hist, d_overflow, st, &launches);
+    p->last_launches = launches;
+    if (e != cudaSuccess) return cuda_fail(e, "launch_predict");
+    return FRI_OK;
 }
 
 int fri_host_alloc(void **out, size_t bytes)

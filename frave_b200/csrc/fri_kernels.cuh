@@ -140,6 +140,29 @@ cudaError_t launch_emit(const Geometry &g, const DeviceTables &t, const EmitTabl
 cudaError_t launch_unemit(const Geometry &g, const DeviceTables &t, const EmitTables &et, uint64_t count, const void *d_in,
                           bool half, uint32_t n_frames, int32_t *d_coefs, cudaStream_t stream, uint32_t *launches);
 
+// Prediction + context bucketing (fri_predict.cu).  Device image of LatticeIndex plus
+// the neighbour vectors of every depth (get_nearby_vectors, wavelet_transform.rs:71-90).
+struct PredictTables {
+    const int32_t *tile_at = nullptr;  // [nb][na]
+    const int32_t *centers = nullptr;  // [n_tiles][2]
+    const uint16_t *lut = nullptr;     // [512]
+    const short2 *off = nullptr;       // [512]
+    int ax = 0, ay = 0, amin = 0, bmin = 0, na = 0, nb = 0;
+    short2 nearby[10][6];
+};
+struct PredictParams {  // value / width predictor parameters per channel and layer set (prediction.rs:164-178)
+    float value[3][3][6];
+    float width[3][3][6];
+};
+cudaError_t configure_predict_kernel();
+// For every frame and channel, in emission order (stride `count`): context bucket, prediction, zig-zag symbol of
+// (value - prediction) saturated to 16 bits, and the per-context histograms [n_frames][C][10][1024] (accumulated:
+// the caller zeroes them); *d_overflow counts symbols outside the 1024-symbol alphabet.
+cudaError_t launch_predict(const Geometry &g, const DeviceTables &t, const EmitTables &et, const PredictTables &pt,
+                           const PredictParams &prm, uint64_t count, const int32_t *d_coefs, uint32_t n_frames,
+                           uint8_t *d_bucket, int32_t *d_pred, uint16_t *d_sym, uint32_t *d_hist, uint32_t *d_overflow,
+                           cudaStream_t stream, uint32_t *launches);
+
 // 10-bit packed transport of emission-ordered streams: int16 streams (stride a multiple of 64 elements, 16-byte
 // aligned) <-> blocks of 64 zig-zag symbols in 80 bytes; n_blocks = total elements / 64.
 constexpr int kPackBlock = 64;       // symbols per packed block

@@ -24,10 +24,12 @@ struct P {
 };
 inline P operator+(P a, P b) { return P{a.x + b.x, a.y + b.y}; }
 
+}  // namespace
+
 // wavelet_transform.rs:71-90
-void nearby_vectors(int depth, P out[6])
+void nearby_vectors(int depth, Vec2 out[6])
 {
-    P zl, zmd;
+    Vec2 zl, zmd;
     if (depth == 1) { zl = {-1, 1}; zmd = {0, 2}; }
     else if (depth == 2) { zl = {-2, 0}; zmd = {0, -2}; }
     else if (depth == 3) { zl = {-3, -1}; zmd = {-1, -3}; }
@@ -43,46 +45,54 @@ void nearby_vectors(int depth, P out[6])
     out[5] = zmd;
 }
 
-struct Lattice {
-    int ax, ay;                      // anchor (w/2, h/2)
-    int amin, bmin, na, nb;          // extent of the retained tiles in lattice coordinates
-    std::vector<int32_t> tile_at;    // [nb][na] plan index of the tile at (a, b), -1 if none
-    uint16_t lut[kTileLeaves];       // residue -> leaf index
-    Vec2 off[kTileLeaves];           // leaf index -> offset from the tile centre
+int LatticeIndex::tile_of(int cx, int cy) const
+{
+    constexpr Vec2 l9 = kLiterals[kBaseDepth], l10 = kLiterals[kBaseDepth + 1];
+    const int64_t dx = cx - ax, dy = cy - ay;
+    const int64_t na_ = dx * l10.y - (int64_t)l10.x * dy, nb_ = (int64_t)l9.x * dy - dx * l9.y;
+    if (na_ % 512 != 0 || nb_ % 512 != 0) return -1;
+    const int64_t a = na_ / 512 - amin, b = nb_ / 512 - bmin;
+    if (a < 0 || b < 0 || a >= na || b >= nb) return -1;
+    return tile_at[(size_t)b * na + a];
+}
 
-    static int mod512(int v) { return ((v % 512) + 512) % 512; }
+bool LatticeIndex::node_at(int level, int x, int y, int &tile, int &heap) const
+{
+    const int k = lut[mod512((x - ax) + 181 * (y - ay))];
+    const int low = kBaseDepth - level;
+    if (k & ((1 << low) - 1)) return false;
+    tile = tile_of(x - off[k].x, y - off[k].y);
+    if (tile < 0) return false;
+    heap = (1 << level) + (k >> low);
+    return true;
+}
 
-    // plan index of the tile centred at c, or -1
-    int tile_of(P c) const
-    {
-        constexpr Vec2 l9 = kLiterals[kBaseDepth], l10 = kLiterals[kBaseDepth + 1];
-        const int64_t dx = c.x - ax, dy = c.y - ay;
-        const int64_t na_ = dx * l10.y - (int64_t)l10.x * dy, nb_ = (int64_t)l9.x * dy - dx * l9.y;
-        if (na_ % 512 != 0 || nb_ % 512 != 0) return -1;
-        const int64_t a = na_ / 512 - amin, b = nb_ / 512 - bmin;
-        if (a < 0 || b < 0 || a >= na || b >= nb) return -1;
-        return tile_at[(size_t)b * na + a];
+void build_lattice_index(const Plan &plan, LatticeIndex &L)
+{
+    const Geometry &g = plan.geo;
+    const int n_tiles = g.n_fractals;
+    L.ax = g.width / 2;
+    L.ay = g.height / 2;
+    for (unsigned k = 0; k < (unsigned)kTileLeaves; ++k) {
+        L.off[k] = digit_sum(k, 0, kBaseDepth);
+        L.lut[LatticeIndex::mod512(L.off[k].x + 181 * L.off[k].y)] = (uint16_t)k;
     }
-
-    // global_position_map[level].get(p): the owning tile and the node's heap index, or false
-    bool node_at(int level, P p, int &tile, int &heap) const
-    {
-        const int k = lut[mod512((p.x - ax) + 181 * (p.y - ay))];
-        const int low = kBaseDepth - level;
-        if (k & ((1 << low) - 1)) return false;
-        tile = tile_of(P{p.x - off[k].x, p.y - off[k].y});
-        if (tile < 0) return false;
-        heap = (1 << level) + (k >> low);
-        return true;
+    constexpr Vec2 l9 = kLiterals[kBaseDepth], l10 = kLiterals[kBaseDepth + 1];
+    std::vector<std::pair<int, int>> ab(n_tiles);
+    int amin = INT32_MAX, amax = INT32_MIN, bmin = INT32_MAX, bmax = INT32_MIN;
+    for (int t = 0; t < n_tiles; ++t) {
+        const int64_t dx = plan.centers[2 * t] - L.ax, dy = plan.centers[2 * t + 1] - L.ay;
+        const int a = (int)((dx * l10.y - (int64_t)l10.x * dy) / 512), b = (int)(((int64_t)l9.x * dy - dx * l9.y) / 512);
+        ab[t] = {a, b};
+        amin = std::min(amin, a); amax = std::max(amax, a);
+        bmin = std::min(bmin, b); bmax = std::max(bmax, b);
     }
-    bool contains(int level, P p) const
-    {
-        int t, h;
-        return node_at(level, p, t, h);
-    }
-};
-
-}  // namespace
+    if (n_tiles == 0) { amin = amax = bmin = bmax = 0; }
+    L.amin = amin; L.bmin = bmin;
+    L.na = amax - amin + 1; L.nb = bmax - bmin + 1;
+    L.tile_at.assign((size_t)L.na * L.nb, -1);
+    for (int t = 0; t < n_tiles; ++t) L.tile_at[(size_t)(ab[t].second - bmin) * L.na + (ab[t].first - amin)] = t;
+}
 
 std::string build_emission_order(const Plan &plan, std::vector<uint32_t> &order)
 {
@@ -92,29 +102,8 @@ std::string build_emission_order(const Plan &plan, std::vector<uint32_t> &order)
     order.clear();
     if (n_tiles == 0) return {};
 
-    Lattice L;
-    L.ax = g.width / 2;
-    L.ay = g.height / 2;
-    for (unsigned k = 0; k < (unsigned)kTileLeaves; ++k) {
-        L.off[k] = digit_sum(k, 0, kBaseDepth);
-        L.lut[Lattice::mod512(L.off[k].x + 181 * L.off[k].y)] = (uint16_t)k;
-    }
-    {
-        constexpr Vec2 l9 = kLiterals[kBaseDepth], l10 = kLiterals[kBaseDepth + 1];
-        std::vector<std::pair<int, int>> ab(n_tiles);
-        int amin = INT32_MAX, amax = INT32_MIN, bmin = INT32_MAX, bmax = INT32_MIN;
-        for (int t = 0; t < n_tiles; ++t) {
-            const int64_t dx = plan.centers[2 * t] - L.ax, dy = plan.centers[2 * t + 1] - L.ay;
-            const int a = (int)((dx * l10.y - (int64_t)l10.x * dy) / 512), b = (int)(((int64_t)l9.x * dy - dx * l9.y) / 512);
-            ab[t] = {a, b};
-            amin = std::min(amin, a); amax = std::max(amax, a);
-            bmin = std::min(bmin, b); bmax = std::max(bmax, b);
-        }
-        L.amin = amin; L.bmin = bmin;
-        L.na = amax - amin + 1; L.nb = bmax - bmin + 1;
-        L.tile_at.assign((size_t)L.na * L.nb, -1);
-        for (int t = 0; t < n_tiles; ++t) L.tile_at[(size_t)(ab[t].second - bmin) * L.na + (ab[t].first - amin)] = t;
-    }
+    LatticeIndex L;
+    build_lattice_index(plan, L);
 
     // :663-682 — bounds over the level-8 node positions (the even leaves of every retained tile)
     int min_real = INT32_MAX, max_real = INT32_MIN, min_imag = INT32_MAX, max_imag = INT32_MIN;
@@ -132,11 +121,13 @@ std::string build_emission_order(const Plan &plan, std::vector<uint32_t> &order)
     const P center{L.ax, L.ay};
     for (int level = 0; level < kBaseDepth; ++level) {
         // ---- scan_level (:505-654), statement for statement
+        Vec2 nv[6];
+        nearby_vectors(kBaseDepth - level, nv);
         P vec[6];
-        nearby_vectors(kBaseDepth - level, vec);
+        for (int i = 0; i < 6; ++i) vec[i] = P{nv[i].x, nv[i].y};
         const P row_dir = vec[3], rev_row_dir = vec[0], col_dir = vec[1], rev_col_dir = vec[4];
         const bool seven = kBaseDepth - level == 2;  // `depth - level != 2` is false: alternating steps
-        auto has = [&](P p) { return L.contains(level, p); };
+        auto has = [&](P p) { int t, h; return L.node_at(level, p.x, p.y, t, h); };
         int64_t steps = 0;
 
         P first = center;
@@ -184,7 +175,7 @@ std::string build_emission_order(const Plan &plan, std::vector<uint32_t> &order)
             P scan = first;
             for (;;) {
                 int t, h;
-                if (L.node_at(level, scan, t, h)) {
+                if (L.node_at(level, scan.x, scan.y, t, h)) {
                     if (count < expect) {
                         if (level == 0) {
                             order[count] = (uint32_t)t * kTileLeaves;                 // first scan: coefficient 0

@@ -93,6 +93,28 @@ std::string build_plan(Plan &plan, uint32_t width, uint32_t height, uint32_t cha
 // reference's own scan would fail its assertion (:701) for this image size.
 std::string build_emission_order(const Plan &plan, std::vector<uint32_t> &order);
 
+// O(1) answers to the questions the reference asks its per-level HashMaps (global_position_map,
+// wavelet_transform.rs:434-448, and Fractal::position_map, :49) for a depth-9 plan: position p holds leaf
+// k = lut[((p.x - ax) + 181 (p.y - ay)) mod 512] of the tile centred at p - off[k]; it is a level-L node
+// position iff the low 9 - L bits of k are zero and that tile is retained.  Used by the emission-order builder
+// (fri_order.cpp) and uploaded for the prediction kernel (fri_predict.cu).
+struct LatticeIndex {
+    int ax = 0, ay = 0;                     // anchor (w/2, h/2)
+    int amin = 0, bmin = 0, na = 0, nb = 0; // extent of the retained tiles in lattice coordinates
+    std::vector<int32_t> tile_at;           // [nb][na] plan index of the tile at (a, b), -1 if none
+    uint16_t lut[kTileLeaves];              // residue -> leaf index
+    Vec2 off[kTileLeaves];                  // leaf index -> offset from the tile centre
+
+    static int mod512(int v) { return ((v % 512) + 512) % 512; }
+    int tile_of(int cx, int cy) const;      // plan index of the tile centred at (cx, cy), or -1
+    // global_position_map[level].get(p): the owning tile and the node's heap index, or false
+    bool node_at(int level, int x, int y, int &tile, int &heap) const;
+};
+void build_lattice_index(const Plan &plan, LatticeIndex &out);
+
+// get_nearby_vectors (wavelet_transform.rs:71-90), hard-wired small depths included.
+void nearby_vectors(int depth, Vec2 out[6]);
+
 // 2^depth-bit Some/None mask of the fractal centred at (cx, cy): bit i <=> coefficient i is
 // Some.  out has 2^depth / 32 words.
 void fractal_mask(int depth, int32_t cx, int32_t cy, int32_t width, int32_t height, uint32_t *out);

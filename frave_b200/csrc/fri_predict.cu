@@ -1,0 +1,206 @@
+// fri_predict.cu — prediction + context bucketing of the quantized coefficients on the device, encode side
+// (SURVEY.md §8(f) next-2): what the reference computes, coefficient by coefficient on the host, between the
+// quantizer and the rANS coder.
+//
+// Reference (crates/libfri/src/...):
+//   stages/prediction.rs:86-149    get_lf_context_bucket: DC and root residue of every tile from the same
+//                                  coefficient of three lattice-neighbour tiles (MED-style predictor, width
+//                                  bucket from |left - up_right|);
+//   stages/prediction.rs:151-207   get_hf_context_bucket: levels 1..8 from six neighbours with a 6-tap f32
+//                                  predictor and a 6-term f32 width model (parameter set by level: < 7 / 7 / 8);
+//   context_modeling.rs:25-77      get_neighbour_values: left, up-left, up-right on the node's own level, and the
+//                                  PARENTS (heap / 2) of right, down-left, down-right;
+//   stages/wavelet_transform.rs:97-177  the six neighbour getters with their depth-2 special cases (which probe
+//                                  global_position_map[2], the LEVEL-2 map, for level-7 positions — kept);
+//   stages/prediction.rs:55-68     assign_bucket;  utils.rs:34-40 pack_signed;
+//   stages/prediction.rs:224-323   the per-context symbol histograms.
+// The 18 + 18 f32 parameters per channel are inputs (the reference fits them with an un-vendored f32 SVD).
+//
+// The reference answers "which tile holds a level-L node at position p, and at which heap index" with one
+// HashMap per level; here LatticeIndex answers it arithmetically (fri_plan.h).  One CTA per tile group (the
+// transform kernels' groups), one thread per emitted coefficient and channel; neighbour coefficients are
+// gathered from the dense [tile][channel][512] blocks, which for a group's neighbours sit in nearby HBM / L2.
+// f32 arithmetic uses explicit round-to-nearest multiplies and adds in the reference's order (no FMA
+// contraction), float -> int conversions saturate and map NaN to 0 like Rust's `as`.
+#include "fri_kernels.cuh"
+
+#include <algorithm>
+
+namespace fri {
+
+namespace {
+
+constexpr int kContexts = 10;     // CONTEXT_AMOUNT, prediction.rs:15
+constexpr int kAlphabet = 1024;   // ALPHABET_SIZE, entropy_coding.rs:25
+
+__device__ __forceinline__ int assign_bucket_u32(unsigned w)  // prediction.rs:55-68
+{
+    return w < 3 ? 0 : w < 5 ? 1 : w < 6 ? 2 : w < 8 ? 3 : w < 12 ? 4 : w < 16 ? 5 : w < 20 ? 6 : w < 25 ? 7 : w < 30 ? 8 : 9;
+}
+
+struct NodeRef {
+    int tile;  // -1: no such node
+    int heap;
+};
+
+struct Lookup {
+    const PredictTables &pt;
+    const uint16_t *lut;  // shared memory copies
+    const short2 *off;
+
+    __device__ __forceinline__ int tile_of(int cx, int cy) const
+    {
+        constexpr Vec2 l9 = kLiterals[kBaseDepth], l10 = kLiterals[kBaseDepth + 1];
+        const int dx = cx - pt.ax, dy = cy - pt.ay;
+        const int na_ = dx * l10.y - l10.x * dy, nb_ = l9.x * dy - dx * l9.y;
+        if ((na_ & 511) || (nb_ & 511)) return -1;
+        const int a = (na_ >> 9) - pt.amin, b = (nb_ >> 9) - pt.bmin;  // exact: multiples of 512
+        if (a < 0 || b < 0 || a >= pt.na || b >= pt.nb) return -1;
+        return __ldg(pt.tile_at + (size_t)b * pt.na + a);
+    }
+    __device__ __forceinline__ NodeRef node_at(int level, int x, int y) const
+    {
+        const int k = lut[((x - pt.ax) + 181 * (y - pt.ay)) & 511];
+        const int low = kBaseDepth - level;
+        if (k & ((1 << low) - 1)) return NodeRef{-1, 0};
+        const short2 o = off[k];
+        return NodeRef{tile_of(x - o.x, y - o.y), (1 << level) + (k >> low)};
+    }
+    __device__ __forceinline__ bool contains(int level, int x, int y) const { return node_at(level, x, y).tile >= 0; }
+};
+
+// One CTA per (group, frame); thread per emitted slot of the group; channels in an outer loop so that the
+// per-context histograms of one channel (10 x 1024 counters) fit in shared memory.
+__global__ void __launch_bounds__(256)
+fri_predict_kernel(const __grid_constant__ PredictTables pt, const __grid_constant__ PredictParams prm,
+                   const GroupDesc *__restrict__ groups,
+                   const uint32_t *__restrict__ goff, const uint32_t *__restrict__ dst, const uint16_t *__restrict__ loc,
+                   unsigned long long count, int channels, int n_tiles, const int32_t *__restrict__ coefs,
+                   uint8_t *__restrict__ bucket_out, int32_t *__restrict__ pred_out, uint16_t *__restrict__ sym_out,
+                   uint32_t *__restrict__ hist_out, uint32_t *__restrict__ overflow)
+{
+    __shared__ uint16_t s_lut[kTileLeaves];
+    __shared__ short2 s_off[kTileLeaves];
+    extern __shared__ __align__(16) uint32_t s_hist[];  // [10][1024]
+    for (int i = threadIdx.x; i < kTileLeaves; i += blockDim.x) {
+        s_lut[i] = pt.lut[i];
+        s_off[i] = pt.off[i];
+    }
+    const Lookup L{pt, s_lut, s_off};
+    const GroupDesc gd = groups[blockIdx.x];
+    const int frame = blockIdx.y;
+    const uint32_t k0 = goff[blockIdx.x], k1 = goff[blockIdx.x + 1];
+    const int32_t *fc = coefs + (size_t)frame * n_tiles * channels * kTileLeaves;
+    auto coef_at = [&](int tile, int ch, int heap) { return __ldg(fc + (((size_t)tile * channels + ch) << kBaseDepth) + heap); };
+
+    for (int ch = 0; ch < channels; ++ch) {
+        for (int i = threadIdx.x; i < kContexts * kAlphabet; i += blockDim.x) s_hist[i] = 0;
+        __syncthreads();
+        const float *vp_all = prm.value[ch][0], *wp_all = prm.width[ch][0];
+        const size_t out_base = ((size_t)frame * channels + ch) * count;
+        for (uint32_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
+            const uint32_t l = __ldg(loc + k);
+            const int tile = (int)gd.tile_base + (int)(l >> kBaseDepth), heap = (int)(l & (kTileLeaves - 1));
+            const int cx = __ldg(pt.centers + 2 * tile), cy = __ldg(pt.centers + 2 * tile + 1);
+            int bucket, prediction;
+            if (heap < 2) {
+                // ---- get_lf_context_bucket: the same coefficient of the tiles at centre + v9[4], v9[5], v9[0]
+                int v[3];
+                const int sel[3] = {4, 5, 0};
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const short2 d = pt.nearby[kBaseDepth][sel[j]];
+                    const int t = L.tile_of(cx + d.x, cy + d.y);
+                    v[j] = t >= 0 ? coef_at(t, ch, heap) : 0;
+                }
+                const unsigned width = (unsigned)abs(v[0] - v[2]);
+                bucket = assign_bucket_u32(__float2uint_rz((float)width));
+                const int hi = max(v[0], v[2]), lo = min(v[0], v[2]);
+                prediction = v[1] >= hi ? hi : (v[1] <= lo ? lo : v[0] + v[2] - v[1]);
+            } else {
+                // ---- get_hf_context_bucket
+                const int level = 31 - __clz(heap);
+                const int d = kBaseDepth - level;
+                const short2 o = s_off[(heap - (1 << level)) << d];  // the node sits at its first leaf
+                const int px = cx + o.x, py = cy + o.y;
+                const short2 *nv = pt.nearby[d];
+                bool alt_up = false, alt_down = false;
+                if (d == 2) {  // wavelet_transform.rs:115-177: probes of the level-`depth` (= 2) map, kept as written
+                    alt_down = !L.contains(2, px + nv[3].x, py + nv[3].y) && L.contains(2, px + 1, py + 1);
+                    alt_up = !L.contains(2, px + nv[0].x, py + nv[0].y) && L.contains(2, px - 1, py - 1);
+                }
+                int qx[6], qy[6];
+                qx[0] = px + nv[4].x; qy[0] = py + nv[4].y;                                     // left
+                if (alt_up) { qx[1] = px - 1 + nv[4].x; qy[1] = py - 1 + nv[4].y; qx[2] = px - 1; qy[2] = py - 1; }
+                else { qx[1] = px + nv[5].x; qy[1] = py + nv[5].y; qx[2] = px + nv[0].x; qy[2] = py + nv[0].y; }  // up-left, up-right
+                qx[3] = px + nv[1].x; qy[3] = py + nv[1].y;                                     // right
+                if (alt_down) { qx[4] = px + 1; qy[4] = py + 1; qx[5] = px + 1 + nv[1].x; qy[5] = py + 1 + nv[1].y; }
+                else { qx[4] = px + nv[3].x; qy[4] = py + nv[3].y; qx[5] = px + nv[2].x; qy[5] = py + nv[2].y; }  // down-left, down-right
+                int v[6];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    const NodeRef n = L.node_at(level, qx[j], qy[j]);
+                    v[j] = n.tile >= 0 ? coef_at(n.tile, ch, j < 3 ? n.heap : n.heap >> 1) : 0;
+                }
+                const int layer = level < kBaseDepth - 2 ? 2 : (level == kBaseDepth - 2 ? 1 : 0);
+                const float *vp = vp_all + 6 * layer, *wp = wp_all + 6 * layer;
+                float width = wp[0];
+                width = __fadd_rn(width, __fmul_rn(wp[1], (float)abs(v[0] - v[3])));
+                width = __fadd_rn(width, __fmul_rn(wp[2], (float)abs(v[1] - v[2])));
+                width = __fadd_rn(width, __fmul_rn(wp[3], (float)abs(v[4] - v[5])));
+                width = __fadd_rn(width, __fmul_rn(wp[4], (float)abs(v[1] - v[5])));
+                width = __fadd_rn(width, __fmul_rn(wp[5], (float)abs(v[2] - v[4])));
+                bucket = assign_bucket_u32(__float2uint_rz(width));  // `as u32`: saturating, NaN -> 0
+                float p = __fmul_rn((float)v[0], vp[0]);
+#pragma unroll
+                for (int j = 1; j < 6; ++j) p = __fadd_rn(p, __fmul_rn((float)v[j], vp[j]));
+                prediction = __float2int_rz(p);                      // `as i32`: saturating, NaN -> 0
+            }
+            const int value = coef_at(tile, ch, heap);
+            const int residual = (int)((unsigned)value - (unsigned)prediction);
+            const unsigned sym = residual >= 0 ? 2u * (unsigned)residual : (unsigned)(-2 * residual - 1);  // pack_signed
+            const size_t e = out_base + __ldg(dst + k);
+            bucket_out[e] = (uint8_t)bucket;
+            pred_out[e] = prediction;
+            sym_out[e] = (uint16_t)min(sym, 0xffffu);
+            if (sym < (unsigned)kAlphabet) atomicAdd(&s_hist[bucket * kAlphabet + sym], 1u);
+            else if (overflow) atomicAdd(overflow, 1u);  // the reference indexes freqs[sym] and panics (entropy_coding.rs:99)
+        }
+        __syncthreads();
+        uint32_t *h = hist_out + ((size_t)frame * channels + ch) * kContexts * kAlphabet;
+        for (int i = threadIdx.x; i < kContexts * kAlphabet; i += blockDim.x) {
+            const uint32_t c = s_hist[i];
+            if (c) atomicAdd(h + i, c);
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+cudaError_t configure_predict_kernel()
+{
+    return cudaFuncSetAttribute(fri_predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kContexts * kAlphabet * (int)sizeof(uint32_t));
+}
+
+cudaError_t launch_predict(const Geometry &g, const DeviceTables &t, const EmitTables &et, const PredictTables &pt,
+                           const PredictParams &prm, uint64_t count,
+                           const int32_t *d_coefs, uint32_t n_frames, uint8_t *d_bucket, int32_t *d_pred, uint16_t *d_sym,
+                           uint32_t *d_hist, uint32_t *d_overflow, cudaStream_t stream, uint32_t *launches)
+{
+    if (count == 0 || n_frames == 0 || g.n_groups == 0) return cudaSuccess;
+    const size_t smem = (size_t)kContexts * kAlphabet * sizeof(uint32_t);
+    for (uint32_t f0 = 0; f0 < n_frames; f0 += 65535u) {  // gridDim.y limit
+        const uint32_t nf = n_frames - f0 < 65535u ? n_frames - f0 : 65535u;
+        const dim3 grid((unsigned)g.n_groups, nf);
+        const size_t so = (size_t)f0 * g.channels * count;
+        fri_predict_kernel<<<grid, 256, smem, stream>>>(pt, prm, t.groups, et.goff, et.dst, et.loc, count, g.channels, g.n_fractals,
+                                                        d_coefs + (int64_t)f0 * g.coefs_per_frame, d_bucket + so, d_pred + so,
+                                                        d_sym + so, d_hist + (size_t)f0 * g.channels * kContexts * kAlphabet,
+                                                        d_overflow);
+        if (launches) ++*launches;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace fri

@@ -210,6 +210,31 @@ int fri_decode_tq_emit16(fri_plan *plan, const int16_t *streams, uint32_t n_fram
                          void *pixels);
 
 /*
+ * Prediction + context bucketing on the device, encode side (depth 9): what
+ * prediction::encode (stages/prediction.rs:224-323) computes per coefficient on the host before the rANS
+ * coder — get_lf_context_bucket (:86-149) for every DC and root residue, get_hf_context_bucket (:151-207)
+ * over ContextModeler::get_neighbour_values (context_modeling.rs:25-77) for levels 1..8, assign_bucket
+ * (:55-68) and pack_signed (utils.rs:34-40).
+ *   d_coefs        quantized dense blocks [n_frames][n_tiles][C][512] (`None` slots 0, as fri_encode_tq_device
+ *                  leaves them);
+ *   value_params,  host float [C][3][6] each: the value / width predictor parameters of the three layer sets
+ *   width_params   (index 0: level 8, 1: level 7, 2: levels 1..6; prediction.rs:164-178).  They are INPUTS: the
+ *                  reference fits them with an f32 SVD from crates that are not in its tree;
+ *   d_bucket       uint8  [n_frames][C][count]  context bucket 0..9 of every `Some` coefficient, emission order
+ *   d_pred         int32  [n_frames][C][count]  the prediction (`as i32` of the f32 predictor)
+ *   d_sym          uint16 [n_frames][C][count]  pack_signed(value - prediction), saturated to 16 bits
+ *   d_hist         uint32 [n_frames][C][10][1024]  symbol counts per context (AnsContext::bump_freq)
+ *   d_overflow     optional uint32: number of symbols >= 1024 — the reference would panic on the first one
+ *                  (entropy_coding.rs:99).
+ * f32 arithmetic is evaluated in the reference's order without fused multiply-adds, so (bucket, prediction)
+ * are bit-identical to a Rust evaluation of the same parameters.  The decoder side is inherently serial
+ * (every prediction reads already-decoded neighbours, entropy_coding.rs:205-264) and stays on the host.
+ */
+int fri_predict_device(fri_plan *plan, const int32_t *d_coefs, uint32_t n_frames, const float *value_params,
+                       const float *width_params, uint8_t *d_bucket, int32_t *d_pred, uint16_t *d_sym, uint32_t *d_hist,
+                       uint32_t *d_overflow, void *stream);
+
+/*
  * How the host-buffer entry points stream one frame through the device: in `bands` consecutive
  * bands of tile groups (1..8), each with its own copy in, kernels and copy out on three
  * event-chained streams, so that a single call overlaps its own host->device and device->host

@@ -14,6 +14,7 @@ fn main() {
         .arg(&lib)
         .arg(csrc.join("fri_api.cu"))
         .arg(csrc.join("fri_kernels.cu"))
+        .arg(csrc.join("fri_predict.cu"))
         .arg(csrc.join("fri_plan.cpp"))
         .arg(csrc.join("fri_order.cpp"))
         .status()
@@ -24,7 +25,7 @@ fn main() {
     println!("cargo:rustc-link-search=native=/usr/local/cuda/lib64");
     println!("cargo:rustc-link-lib=dylib=cudart");
     println!("cargo:rustc-link-lib=dylib=stdc++");
-    for f in ["fri_api.cu", "fri_kernels.cu", "fri_plan.cpp", "fri_order.cpp", "fri_kernels.cuh", "fri_plan.h", "fri_geometry.h"] {
+    for f in ["fri_api.cu", "fri_kernels.cu", "fri_predict.cu", "fri_plan.cpp", "fri_order.cpp", "fri_kernels.cuh", "fri_plan.h", "fri_geometry.h"] {
         println!("cargo:rerun-if-changed={}", csrc.join(f).display());
     }
 }

@@ -59,6 +59,7 @@ extern "C" {
     fn fri_decode_tq_emit(plan: *mut FriPlan, streams: *const i32, n_frames: u32, q: *const i32, dequant_mode: c_int, pixels: *mut c_void) -> c_int;
     fn fri_decode_tq_emit16(plan: *mut FriPlan, streams: *const i16, n_frames: u32, q: *const i32, dequant_mode: c_int, pixels: *mut c_void) -> c_int;
     fn fri_decode_tq_emit10(plan: *mut FriPlan, streams: *const u8, n_frames: u32, q: *const i32, dequant_mode: c_int, pixels: *mut c_void) -> c_int;
+    fn fri_predict_device(plan: *mut FriPlan, d_coefs: *const i32, n_frames: u32, value_params: *const f32, width_params: *const f32, d_bucket: *mut u8, d_pred: *mut i32, d_sym: *mut u16, d_hist: *mut u32, d_overflow: *mut u32, stream: *mut c_void) -> c_int;
     fn fri_plan_set_bands(plan: *mut FriPlan, bands: c_int) -> c_int;
     fn fri_plan_set_async(plan: *mut FriPlan, on: c_int) -> c_int;
     fn fri_plan_sync(plan: *mut FriPlan) -> c_int;
@@ -296,6 +297,18 @@ impl Plan {
     /// As `emit_device`, 10-bit packed streams ([n_frames][C][emission_packed_bytes], 16-byte aligned).
     pub unsafe fn emit_device10(&mut self, d_coefs: *const i32, n_frames: u32, d_out: *mut u8, stream: *mut c_void) -> Result<(), String> {
         check(fri_emit_device10(self.raw, d_coefs, n_frames, d_out, stream))
+    }
+    /// Prediction + context bucketing on the device (prediction.rs:224-323): per emitted coefficient the context
+    /// bucket, the prediction and the zig-zag symbol, plus the per-context histograms the rANS tables are built from.
+    /// # Safety
+    /// Device pointers sized as include/fri_cuda.h states; `params` are the [C][3][6] value / width predictors.
+    #[allow(clippy::too_many_arguments)]
+    pub unsafe fn predict_device(&mut self, d_coefs: *const i32, n_frames: u32, value_params: &[[[f32; 6]; 3]], width_params: &[[[f32; 6]; 3]],
+                                 d_bucket: *mut u8, d_pred: *mut i32, d_sym: *mut u16, d_hist: *mut u32, d_overflow: *mut u32, stream: *mut c_void) -> Result<(), String> {
+        want_len("value_params", value_params.len(), self.channels)?;
+        want_len("width_params", width_params.len(), self.channels)?;
+        check(fri_predict_device(self.raw, d_coefs, n_frames, value_params.as_ptr() as *const f32, width_params.as_ptr() as *const f32,
+                                 d_bucket, d_pred, d_sym, d_hist, d_overflow, stream))
     }
     /// # Safety
     /// Device pointers: streams in, dense blocks out (None slots zeroed).

@@ -284,3 +284,62 @@ def test_encoder_and_decoder_threads_packed_transport():
             t.join()
         assert np.array_equal(res["packed"], packed_want)
         assert np.array_equal(res["px"][0], px_want)
+
+
+# ------------------------------------------------------------------------------------------------
+# next-2: prediction + context bucketing on the device, against oracle/fri_predict_np.py
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,smooth", [((48, 64, 1), False), ((131, 77, 3), False), ((131, 77, 3), True), ((270, 480, 1), True),
+                                          ((37, 100, 3), False)],
+                         ids=["48x64x1", "131x77x3", "131x77x3-smooth", "270x480x1-smooth", "37x100x3"])
+def test_prediction_and_context_buckets(shape, smooth):
+    """fri_predict_device: (bucket, prediction as i32, zig-zag symbol) of every emitted coefficient and the
+    per-context histograms, bit for bit against the dict-based restatement of prediction.rs / context_modeling.rs,
+    for fixed predictor parameters (the lstsq fit stays on the host)."""
+    from oracle import fri_predict_np as PR
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda", 0)
+    h, w, c = shape
+    img = (smooth_image if smooth else uniform_image)(h, w, c, seed=h + w)
+    q = smallest_layer_q(3)
+    rng = np.random.Generator(np.random.PCG64(w))
+    for trial in range(2):
+        # trial 0: plausible parameters (a smoothing predictor); trial 1: arbitrary ones incl. negative widths
+        if trial == 0:
+            vp = np.tile(np.array([0.4, 0.1, 0.1, 0.2, 0.1, 0.1], np.float32), (c, 3, 1)) + rng.normal(0, 0.02, (c, 3, 6)).astype(np.float32)
+            wp = np.abs(rng.normal(0.5, 0.3, (c, 3, 6))).astype(np.float32)
+        else:
+            vp = rng.normal(0, 1.5, (c, 3, 6)).astype(np.float32)
+            wp = rng.normal(0, 2.0, (c, 3, 6)).astype(np.float32)
+        with capi.Plan(w, h, c) as plan:
+            coefs = plan.encode(img, q)[0]
+            some = plan.masks()
+            order = plan.emission_order().astype(np.int64)
+            src = order[some.reshape(-1)[order]]
+            cnt = plan.emission_count()
+            assert len(src) == cnt
+            want_b, want_p, want_s, want_h, want_o = PR.predict(plan.centers(), coefs, some, src, vp, wp)
+            d_coefs = torch.from_numpy(coefs).to(dev)
+            d_b = torch.full((1, c, cnt), 255, dtype=torch.uint8, device=dev)
+            d_p = torch.zeros((1, c, cnt), dtype=torch.int32, device=dev)
+            d_s = torch.zeros((1, c, cnt), dtype=torch.int16, device=dev)
+            d_h = torch.full((1, c, 10, 1024), 7, dtype=torch.int32, device=dev)  # the call zeroes it
+            d_o = torch.full((1,), 99, dtype=torch.int32, device=dev)
+            plan.predict_device(d_coefs.data_ptr(), 1, vp, wp, d_b.data_ptr(), d_p.data_ptr(), d_s.data_ptr(), d_h.data_ptr(),
+                                d_o.data_ptr())
+            torch.cuda.synchronize()
+            assert np.array_equal(d_b.cpu().numpy()[0], want_b)
+            assert np.array_equal(d_p.cpu().numpy()[0], want_p)
+            assert np.array_equal(d_s.cpu().numpy()[0].view(np.uint16), np.minimum(want_s, 0xffff).astype(np.uint16))
+            assert np.array_equal(d_h.cpu().numpy()[0].view(np.uint32), want_h)
+            assert int(d_o.item()) == want_o
+            if trial == 0 and smooth:
+                assert want_o == 0  # a sane predictor on a smooth image stays inside the 1024-symbol alphabet
+            # the symbols + predictions give the coefficients back: value = unpack_signed(symbol) + prediction
+            if want_o == 0:
+                back = capi.unpack10(capi.pack10(np.zeros(1, np.int32)), 1)  # (format helper sanity)
+                assert back[0] == 0
+                sym = want_s.astype(np.int64)
+                res = np.where(sym % 2 == 0, sym // 2, -((sym + 1) // 2))
+                streams = plan.encode_emit(img, q)[0]
+                assert np.array_equal(res + want_p, streams)
