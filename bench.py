@@ -404,7 +404,7 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
     # and host-side coefficient formats: i32 blocks (fri_*_tq), i16 blocks (fri_*_tq16), p10 = emission-ordered
     # streams in the 10-bit packed transport (fri_*_tq_emit10: what the host entropy coder consumes, 1.25 B per
     # coefficient).
-    e2e_steps = max(4, min(args.steps, 12))
+    e2e_steps = 24  # per variant and repetition, whatever --steps is (a step is ~3 ms: short runs are noisy)
     e2e, e2e_bytes = {}, {}
     if not args.no_e2e:
         px_h = capi.PinnedBuffer((1, H, W, C), np.uint8)
@@ -414,6 +414,9 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
         dplan.emission_count()
 
         def duplex(enc_call, dec_call) -> float:
+            return statistics.median(duplex_once(enc_call, dec_call) for _ in range(3))
+
+        def duplex_once(enc_call, dec_call) -> float:
             errors = []
 
             def loop(call):
@@ -489,6 +492,50 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
         e2e["duplex_p10"] = duplex(lambda: plan.encode_emit10(px_h.array, q, out=pk_enc.array),
                                    lambda: dplan.decode_emit10(pk_dec.array, q, out=out_h.array))
         e2e_bytes["p10"] = (px_h.array.nbytes + pk_dec.array.nbytes, pk_enc.array.nbytes + out_h.array.nbytes)
+        # quad: TWO encoder threads and TWO decoder threads, one handle and one set of pinned buffers each — while one
+        # call of a direction runs its kernels, the other's copies keep the link busy.  Half the steps per thread:
+        # the same number of frames as the duplex run.
+        plan2, dplan2 = capi.Plan(W, H, C, device=local_rank), capi.Plan(W, H, C, device=local_rank)
+        px_h2, out_h2 = capi.PinnedBuffer((1, H, W, C), np.uint8), capi.PinnedBuffer((1, H, W, C), np.uint8)
+        pk_enc2, pk_dec2 = capi.PinnedBuffer((1, C, nb), np.uint8), capi.PinnedBuffer((1, C, nb), np.uint8)
+        px_h2.array[...] = px_h.array
+        pk_dec2.array[...] = pk_dec.array
+        plan2.encode_emit10(px_h2.array, q, out=pk_enc2.array)
+        dplan2.decode_emit10(pk_dec2.array, q, out=out_h2.array)
+
+        def quad_once() -> float:
+            errors = []
+
+            def loop(call):
+                try:
+                    for _ in range(e2e_steps // 2):
+                        call()
+                except Exception as exc:
+                    errors.append(exc)
+
+            calls = [lambda: plan.encode_emit10(px_h.array, q, out=pk_enc.array),
+                     lambda: plan2.encode_emit10(px_h2.array, q, out=pk_enc2.array),
+                     lambda: dplan.decode_emit10(pk_dec.array, q, out=out_h.array),
+                     lambda: dplan2.decode_emit10(pk_dec2.array, q, out=out_h2.array)]
+            if world > 1:
+                dist.barrier()
+            th = [threading.Thread(target=loop, args=(c,)) for c in calls]
+            t0 = time.perf_counter()
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            dt = time.perf_counter() - t0
+            if errors:
+                raise errors[0]
+            return dt
+
+        e2e["quad_p10"] = statistics.median(quad_once() for _ in range(3))
+        if not np.array_equal(pk_enc2.array, pk_enc.array) or not np.array_equal(out_h2.array, out_h.array):
+            raise RuntimeError("quad e2e: the two handles of a direction disagree")
+        for b in (px_h2, out_h2, pk_enc2, pk_dec2):
+            b.free()
+        plan2.close(); dplan2.close()
         pk_enc.free(); pk_dec.free()
         dplan.close()
         px_h.free(); out_h.free()
@@ -536,13 +583,14 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
                          "reference's sort_lattice scan, needed by the *_emit* entry points only); outside the timed region",
         }
         if e2e:
-            best = min((k for k in e2e if k.startswith(("duplex", "async"))), key=lambda k: e2e[k])
+            best = min((k for k in e2e if k.startswith(("duplex", "async", "quad"))), key=lambda k: e2e[k])
             fmt = best.split("_")[1]
             api = {"i32": "fri_encode_tq + fri_decode_tq (int32 coefficient blocks on the host side)",
                    "i16": "fri_encode_tq16 + fri_decode_tq16 (int16 coefficient blocks on the host side)",
                    "p10": "fri_encode_tq_emit10 + fri_decode_tq_emit10 (emission-ordered streams, 10-bit packed symbols on the "
                           "host side: what the reference's entropy coder consumes / produces)"}[fmt]
-            how = {"duplex": "encoder thread and decoder thread with one plan handle each",
+            how = {"quad": "two encoder threads and two decoder threads with one plan handle each",
+                   "duplex": "encoder thread and decoder thread with one plan handle each",
                    "async": "one thread, both handles in asynchronous mode", "serial": "one thread"}[best.split("_")[0]]
             # one frame per GPU per e2e step
             line["e2e"] = {
@@ -551,7 +599,7 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
                 "api": f"{api}, pinned host buffers, {how}; one {W}x{H}x{C} frame per GPU and step",
                 "variant": best,
                 "variants_mpix_s": {k: W * H * world * e2e_steps / v / 1e6 for k, v in e2e.items()},
-                "variants": "serial = one thread, encode then decode; duplex = encoder and decoder threads; async = one thread, "
+                "variants": "serial = one thread, encode then decode; duplex = encoder and decoder threads; quad = two of each; async = one thread, "
                             "both handles asynchronous; i32 / i16 = coefficient blocks (4 / 2 B per coefficient over PCIe), "
                             "p10 = emission-ordered 10-bit packed streams (1.25 B per coefficient)",
                 "limiter": "host<->device PCIe copies (both directions busy); kernels are a few percent of the step"}
