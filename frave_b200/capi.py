@@ -66,6 +66,7 @@ _SYMBOLS = [
     ("fri_plan_set_bands", C.c_int, [_P, C.c_int]),
     ("fri_plan_set_async", C.c_int, [_P, C.c_int]),
     ("fri_plan_sync", C.c_int, [_P]),
+    ("fri_plan_set_independent_calls", C.c_int, [_P, C.c_int]),
     ("fri_quant_divide", C.c_int32, [C.c_int32, C.c_int32]),
     ("fri_quant_divide_small", C.c_int32, [C.c_int32, C.c_int32]),
     ("fri_quant_divide_magic", C.c_int32, [C.c_int32, C.c_int32]),
@@ -255,6 +256,10 @@ class Plan:
 
     def sync(self) -> None:
         _check(lib().fri_plan_sync(self._h))
+
+    def set_independent_calls(self, on: bool) -> None:
+        """Promise that consecutive *_device calls on one stream touch disjoint buffers (fri_plan_set_independent_calls)."""
+        _check(lib().fri_plan_set_independent_calls(self._h, 1 if on else 0))
 
     @property
     def last_launches(self) -> int:

@@ -83,6 +83,7 @@ struct fri_plan {
     std::mutex pool_mutex;
     int bands = 0;  // fri_plan_set_bands: 0 = automatic
     bool async_mode = false;  // fri_plan_set_async
+    bool independent_calls = false;  // fri_plan_set_independent_calls
     // emission order (computed on first use)
     int emit_state = 0;  // 0 = not computed, 1 = ready, -1 = failed (emit_error)
     std::string emit_error;
@@ -465,7 +466,9 @@ static int encode_device(const fri_plan *cp, const void *d_pixels, uint32_t n_fr
     if (g.sub_bits > 0 && (rc = pool_alloc(p, reinterpret_cast<void **>(&d_dc), n_frames * dc_elems_per_frame(g) * sizeof(int32_t), st)))
         return rc;
     uint32_t launches = 0;
-    const cudaError_t e = launch_encode(g, p->tables, qp, d_pixels, n_frames, d_coefs, half, d_dc, st, &launches);
+    Geometry gl = g;
+    gl.independent_calls = p->independent_calls ? 1 : 0;
+    const cudaError_t e = launch_encode(gl, p->tables, qp, d_pixels, n_frames, d_coefs, half, d_dc, st, &launches);
     if (d_dc) cudaFreeAsync(d_dc, st);
     p->last_launches = launches;
     if (e != cudaSuccess) return cuda_fail(e, "launch_encode");
@@ -499,7 +502,9 @@ static int decode_device(const fri_plan *cp, const void *d_coefs, bool half, uin
     if (g.sub_bits > 0 && (rc = pool_alloc(p, reinterpret_cast<void **>(&d_dc), n_frames * dc_elems_per_frame(g) * sizeof(int32_t), st)))
         return rc;
     uint32_t launches = 0;
-    const cudaError_t e = launch_decode(g, p->tables, qp, d_coefs, half, n_frames, d_pixels, d_dc, st, &launches);
+    Geometry gl = g;
+    gl.independent_calls = p->independent_calls && p->plan.pixels_covered == (uint64_t)g.width * g.height ? 1 : 0;  // (the memset orders itself)
+    const cudaError_t e = launch_decode(gl, p->tables, qp, d_coefs, half, n_frames, d_pixels, d_dc, st, &launches);
     if (d_dc) cudaFreeAsync(d_dc, st);
     p->last_launches = launches;
     if (e != cudaSuccess) return cuda_fail(e, "launch_decode");
@@ -1117,6 +1122,13 @@ int fri_plan_set_async(fri_plan *p, int on)
 {
     if (!p) return fail(FRI_E_INVALID, "plan is NULL");
     p->async_mode = on != 0;
+    return FRI_OK;
+}
+
+int fri_plan_set_independent_calls(fri_plan *p, int on)
+{
+    if (!p) return fail(FRI_E_INVALID, "plan is NULL");
+    p->independent_calls = on != 0;
     return FRI_OK;
 }
 

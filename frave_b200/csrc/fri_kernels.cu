@@ -728,9 +728,6 @@ __device__ __forceinline__ void prefetch_group_coefs(const Geometry &g, const Gr
 }
 
 // Timing-only what-if switches (wrong results; variant builds for bounding what a change could buy)
-#ifndef FRI_WHATIF_NOWAIT
-#define FRI_WHATIF_NOWAIT 0
-#endif
 #ifndef FRI_WHATIF_SKIP_MIXED
 #define FRI_WHATIF_SKIP_MIXED 0   // decode: partially owned chunks are not written
 #endif
@@ -1203,9 +1200,9 @@ fri_encode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
         mbar_init(&bars[1], max(1, g.region_h - g.n_rows_first));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-#if !FRI_WHATIF_NOWAIT
-    pdl_wait();  // the previous kernel of the stream may have written these pixels (or still read the coefficients)
-#endif
+    // the previous kernel of the stream may have written these pixels (or still read the coefficients) — unless
+    // the caller has promised that consecutive calls are independent (fri_plan_set_independent_calls)
+    if (DEEP || !g.independent_calls) pdl_wait();
     if (bulk) {
         // only the warps that issue copies (thread r copies row r) wait for the barrier initialisation; the
         // others go straight on to the look-ahead and meet them at the CTA barrier before the wait
@@ -1281,9 +1278,8 @@ fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
     FRI_TRACE_MARK(0);
     const bool sparse = __popc(gd.tile_mask) != g.group_a * g.group_b;
     if (sparse) zero_region(g, region);
-#if !FRI_WHATIF_NOWAIT
-    pdl_wait();  // the previous kernel of the stream may have produced these coefficients (or still read the pixels)
-#endif
+    // the previous kernel of the stream may have produced these coefficients (or still read the pixels)
+    if (DEEP || !g.independent_calls) pdl_wait();
     if ((int64_t)blockIdx.y * gridDim.x + blockIdx.x >= no_prefetch_ctas) prefetch_group_coefs<C, DEEP, CT>(g, gd, frame, coefs);
     if (sparse) __syncthreads();
     decode_tiles<C, S, DEEP, QS, CT>(g, qp, gd, rv, tile_unit, frame, region, scratch, coefs, dc_in);

@@ -41,7 +41,7 @@ struct Geometry {
     int32_t n_fractals;          // retained fractals per frame (== n_base_tiles at depth 9)
     int32_t list_cap;            // entries per phase in the chunk list
     int32_t tiles_per_warp;      // base tiles each warp of a CTA processes (full group)
-    int32_t pad_;
+    int32_t independent_calls;   // per launch: the kernel does not wait for the previous kernel of its stream (fri_plan_set_independent_calls)
     int64_t row_stride;          // width * channels * sample_bytes
     int64_t frame_bytes;         // height * row_stride
     int64_t coefs_per_frame;     // n_fractals * channels * 2^depth

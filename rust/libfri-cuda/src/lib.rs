@@ -62,6 +62,7 @@ extern "C" {
     fn fri_predict_device(plan: *mut FriPlan, d_coefs: *const i32, n_frames: u32, value_params: *const f32, width_params: *const f32, d_bucket: *mut u8, d_pred: *mut i32, d_sym: *mut u16, d_hist: *mut u32, d_overflow: *mut u32, stream: *mut c_void) -> c_int;
     fn fri_plan_set_bands(plan: *mut FriPlan, bands: c_int) -> c_int;
     fn fri_plan_set_async(plan: *mut FriPlan, on: c_int) -> c_int;
+    fn fri_plan_set_independent_calls(plan: *mut FriPlan, on: c_int) -> c_int;
     fn fri_plan_sync(plan: *mut FriPlan) -> c_int;
     fn fri_host_alloc(out: *mut *mut c_void, bytes: usize) -> c_int;
     fn fri_host_free(p: *mut c_void);
@@ -260,6 +261,10 @@ impl Plan {
     /// pageable memory with an error) that is neither dropped, read nor written until `sync()` has returned.
     pub unsafe fn set_async(&mut self, on: bool) -> Result<(), String> { check(fri_plan_set_async(self.raw, on as c_int)) }
     pub fn sync(&mut self) -> Result<(), String> { check(unsafe { fri_plan_sync(self.raw) }) }
+    /// Hint: consecutive *_device calls on one stream are independent (their kernels may overlap).
+    /// # Safety
+    /// Dependent calls (e.g. encode then decode of the same coefficient buffer) with the hint set are a data race.
+    pub unsafe fn set_independent_calls(&mut self, on: bool) -> Result<(), String> { check(fri_plan_set_independent_calls(self.raw, on as c_int)) }
 
     // ---- device-resident entry points (raw device pointers from the caller's CUDA context)
     /// # Safety

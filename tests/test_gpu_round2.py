@@ -343,3 +343,35 @@ def test_prediction_and_context_buckets(shape, smooth):
                 res = np.where(sym % 2 == 0, sym // 2, -((sym + 1) // 2))
                 streams = plan.encode_emit(img, q)[0]
                 assert np.array_equal(res + want_p, streams)
+
+
+def test_independent_calls_hint_overlaps_kernels_without_changing_results():
+    """fri_plan_set_independent_calls: a stream of frames in disjoint buffers, no dependency wait between the
+    launches — every frame still equals the oracle; with the hint off again, dependent chains work as before."""
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda", 0)
+    h, w, c, n = 1080, 1920, 3, 6
+    q = smallest_layer_q(4)
+    imgs = [uniform_image(h, w, c, seed=500 + i) for i in range(n)]
+    with capi.Plan(w, h, c) as plan:
+        some = some_of(plan)
+        want = [oracle_encode(plan, im, q)[0] for im in imgs]
+        d_px = [torch.from_numpy(im).to(dev) for im in imgs]
+        d_co = [torch.zeros(plan.coef_shape, dtype=torch.int32, device=dev) for _ in range(n)]
+        d_in = [torch.from_numpy(x).to(dev) for x in want]
+        d_out = [torch.zeros((h, w, c), dtype=torch.uint8, device=dev) for _ in range(n)]
+        torch.cuda.synchronize()
+        plan.set_independent_calls(True)
+        for rep in range(3):
+            for i in range(n):  # encode frame i and decode frame i's reference coefficients: all buffers distinct
+                plan.encode_device(d_px[i].data_ptr(), 1, d_co[i].data_ptr(), q)
+                plan.decode_device(d_in[i].data_ptr(), 1, d_out[i].data_ptr(), q)
+        torch.cuda.synchronize()
+        plan.set_independent_calls(False)
+        for i in range(n):
+            assert np.array_equal(d_co[i].cpu().numpy(), want[i])
+            assert np.array_equal(d_out[i].cpu().numpy(), oracle_decode(plan, want[i], some, q))
+        plan.encode_device(d_px[0].data_ptr(), 1, d_co[1].data_ptr(), None)   # dependent chain, hint off
+        plan.decode_device(d_co[1].data_ptr(), 1, d_out[1].data_ptr(), None)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_out[1].cpu().numpy(), imgs[0])
