@@ -492,6 +492,8 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
         dplan.decode_emit10(pk_dec.array, q, out=out_h.array)
         if not np.array_equal(out_h.array, plan.decode(plan.encode(px_h.array, q), q)):
             raise RuntimeError("packed transport: decode of the packed streams differs from the block path")
+        if world > 1:
+            dist.barrier()  # every rank copies at the same time: the host's aggregate PCIe rate is the shared resource
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             plan.encode_emit10(px_h.array, q, out=pk_enc.array)

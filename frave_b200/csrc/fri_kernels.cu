@@ -1059,15 +1059,14 @@ __device__ __forceinline__ WriteAhead write_out_preload(const Geometry &g, const
     WriteAhead w;
     const uint32_t *cl = chunk_list + (size_t)rv.phi0 * g.list_cap;
     const int n_full = g.list_full[rv.phi0];
-    // Slots past the end of the list inside the last used round repeat its last chunk (a redundant store of
-    // the same bytes) instead of being skipped: the unrolled stores then need no per-chunk test and branch.
-    // Whole rounds past the end (a 1-byte-per-pixel group has 883 full chunks for 6 x 256 slots) are skipped
-    // by a CTA-uniform test — they would all hit the same 16 bytes.
-    const int rounds = (n_full + (int)blockDim.x - 1) / (int)blockDim.x;
+    // Slots past the end of the list repeat its last chunk (a redundant store of the same bytes)
+    // instead of being skipped: the unrolled stores then need no per-chunk test and branch.
+    // (Skipping whole unused rounds with a CTA-uniform test — a 1-byte-per-pixel group has 883 full chunks
+    // for 6 x 256 slots — measured equal for 1-channel images and cost the RGB kernel a spill.)
 #pragma unroll
     for (int u = 0; u < kWriteAhead; ++u) {
         const int k = min((int)(threadIdx.x + u * blockDim.x), n_full - 1);
-        w.e[u] = (rv.interior && u < rounds) ? ld_table(cl + k, pol) : kNoChunk;
+        w.e[u] = (rv.interior && n_full > 0) ? ld_table(cl + k, pol) : kNoChunk;
     }
     const uint16_t *cmk = chunk_mask + (size_t)rv.phi0 * g.list_cap;
     const int n_all = g.list_all[rv.phi0];
@@ -1109,10 +1108,9 @@ __device__ __forceinline__ void write_out_group(const Geometry &g, const GroupDe
     const uint16_t *cmk = chunk_mask + (size_t)rv.phi0 * g.list_cap;
     const int n_full = g.list_full[rv.phi0], n_all = g.list_all[rv.phi0];
     if (rv.interior) {
-        const int rounds = FRI_WHATIF_SKIP_FULL ? 0 : (n_full + n_threads - 1) / n_threads;
+        if (n_full > 0 && !FRI_WHATIF_SKIP_FULL) {
 #pragma unroll
-        for (int u = 0; u < kWriteAhead; ++u) {
-            if (u < rounds) {  // CTA-uniform
+            for (int u = 0; u < kWriteAhead; ++u) {
                 const int r = (int)(ahead.e[u] >> 16), s = (int)(ahead.e[u] & 0xffffu) << 4;
                 FRI_PIXEL_STORE(reinterpret_cast<int4 *>(rv.gaddr(r, s)), *reinterpret_cast<const int4 *>(region + s));
             }
