@@ -12,14 +12,14 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libfri_cuda.so")
-SOURCES = ["fri_api.cu", "fri_kernels.cu", "fri_predict.cu", "fri_plan.cpp", "fri_order.cpp"]
-HEADERS = ["fri_geometry.h", "fri_plan.h", "fri_kernels.cuh", os.path.join("..", "..", "include", "fri_cuda.h")]
+SOURCES = ["fri_api.cu", "fri_kernels.cu", "fri_predict.cu", "fri_plan.cpp", "fri_order.cpp", "fri_codec.cpp"]
+HEADERS = ["fri_geometry.h", "fri_plan.h", "fri_kernels.cuh", "fri_codec.h", os.path.join("..", "..", "include", "fri_cuda.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo",
-    "-Xcompiler", "-fPIC,-O3,-Wall",
+    "-Xcompiler", "-fPIC,-O3,-Wall,-ffp-contract=off",  # no FMA contraction in host f32 code (bit parity with Rust)
     "--shared",
     "-cudart", "static",
 ]

@@ -60,6 +60,14 @@ _SYMBOLS = [
     ("fri_unemit_device10", C.c_int, [_P, _P, C.c_uint32, _P, _P]),
     ("fri_decode_tq_emit10", C.c_int, [_P, _P, C.c_uint32, _P, C.c_int, _P]),
     ("fri_predict_device", C.c_int, [_P, _P, C.c_uint32, _P, _P, _P, _P, _P, _P, _P, _P]),
+    ("fri_fit_parameters", C.c_int, [_P, _P, _P, _P]),
+    ("fri_predict_host", C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    ("fri_frv_pack", C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, C.POINTER(_P), C.POINTER(C.c_size_t)]),
+    ("fri_frv_unpack", C.c_int, [_P, _P, C.c_size_t, _P]),
+    ("fri_frv_info", C.c_int, [_P, C.c_size_t, _P, _P, _P]),
+    ("fri_frv_encode", C.c_int, [_P, _P, _P, C.c_int, C.POINTER(_P), C.POINTER(C.c_size_t)]),
+    ("fri_frv_decode", C.c_int, [_P, _P, C.c_size_t, _P, C.c_int, _P]),
+    ("fri_frv_free", None, [_P]),
     ("fri_host_alloc", C.c_int, [C.POINTER(_P), C.c_size_t]),
     ("fri_host_free", None, [_P]),
     ("fri_plan_last_launches", C.c_uint32, [_P]),
@@ -118,6 +126,14 @@ def device_count() -> int:
 def quant_divide(value: int, q: int) -> int:
     """value / q with the kernels' multiply-high division routine (host evaluation, for tests)."""
     return int(lib().fri_quant_divide(int(value), int(q)))
+
+
+def frv_info(data: bytes) -> tuple[int, int, int]:
+    """(width, height, channels) of a `frif` container."""
+    buf = np.frombuffer(data, dtype=np.uint8)
+    w, h, c = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+    _check(lib().fri_frv_info(buf.ctypes.data, len(data), C.addressof(w), C.addressof(h), C.addressof(c)))
+    return int(w.value), int(h.value), int(c.value)
 
 
 def pack10(values: np.ndarray) -> np.ndarray:
@@ -415,6 +431,84 @@ class Plan:
         mode = FRI_DEQUANT_MULTIPLY if multiply else FRI_DEQUANT_DIVIDE
         fn = lib().fri_decode_tq_emit16 if half else lib().fri_decode_tq_emit
         _check(fn(self._h, st.ctypes.data, n, qp, mode, out.ctypes.data))
+        return out
+
+    # ---- host codec behind the transform: parameter fit, context model, rANS, frif container -----------
+    def _dense(self, coefs: np.ndarray) -> np.ndarray:
+        cf = np.ascontiguousarray(coefs, dtype=np.int32)
+        if cf.shape != self.coef_shape:
+            raise ValueError(f"coefs must have shape {self.coef_shape} (one frame)")
+        return cf
+
+    def fit_parameters(self, coefs: np.ndarray):
+        """Quantized dense blocks of one frame -> (value_params, width_params), float32 [C, 3, 6] each."""
+        cf = self._dense(coefs)
+        vp = np.zeros((self.channels, 3, 6), np.float32)
+        wp = np.zeros((self.channels, 3, 6), np.float32)
+        _check(lib().fri_fit_parameters(self._h, cf.ctypes.data, vp.ctypes.data, wp.ctypes.data))
+        return vp, wp
+
+    def predict_host(self, coefs: np.ndarray, value_params, width_params):
+        """Host form of predict_device for one frame: (bucket u8 [C, n], prediction i32 [C, n], symbol u16 [C, n],
+        histograms u32 [C, 10, 1024], overflow count)."""
+        cf = self._dense(coefs)
+        vp = np.ascontiguousarray(value_params, dtype=np.float32)
+        wp = np.ascontiguousarray(width_params, dtype=np.float32)
+        n = self.emission_count()
+        b = np.zeros((self.channels, n), np.uint8)
+        p = np.zeros((self.channels, n), np.int32)
+        s = np.zeros((self.channels, n), np.uint16)
+        h = np.zeros((self.channels, 10, 1024), np.uint32)
+        o = C.c_uint32(0)
+        _check(lib().fri_predict_host(self._h, cf.ctypes.data, vp.ctypes.data, wp.ctypes.data, b.ctypes.data, p.ctypes.data,
+                                      s.ctypes.data, h.ctypes.data, C.addressof(o)))
+        return b, p, s, h, int(o.value)
+
+    @staticmethod
+    def _take_bytes(ptr, n) -> bytes:
+        try:
+            return C.string_at(ptr.value, n.value)
+        finally:
+            lib().fri_frv_free(ptr)
+
+    def frv_pack(self, value_params, width_params, bucket, sym, hist, colorspace: int = 0) -> bytes:
+        """Symbols + buckets + histograms of one frame -> `frif` container bytes (rANS on the host)."""
+        vp = np.ascontiguousarray(value_params, dtype=np.float32)
+        wp = np.ascontiguousarray(width_params, dtype=np.float32)
+        b = np.ascontiguousarray(bucket, dtype=np.uint8)
+        s = np.ascontiguousarray(sym, dtype=np.uint16)
+        h = np.ascontiguousarray(hist, dtype=np.uint32)
+        n = self.emission_count()
+        assert b.shape == (self.channels, n) and s.shape == (self.channels, n) and h.shape == (self.channels, 10, 1024)
+        out, ln = _P(), C.c_size_t(0)
+        _check(lib().fri_frv_pack(self._h, colorspace, vp.ctypes.data, wp.ctypes.data, b.ctypes.data, s.ctypes.data, h.ctypes.data,
+                                  C.byref(out), C.byref(ln)))
+        return self._take_bytes(out, ln)
+
+    def frv_unpack(self, data: bytes) -> np.ndarray:
+        """Container bytes -> quantized dense blocks [n_tiles, C, 512] (serial entropy decode on the host)."""
+        buf = np.frombuffer(data, dtype=np.uint8)
+        out = np.empty(self.coef_shape, np.int32)
+        _check(lib().fri_frv_unpack(self._h, buf.ctypes.data, len(data), out.ctypes.data))
+        return out
+
+    def frv_encode(self, pixels: np.ndarray, q=None, colorspace: int = 0) -> bytes:
+        """HWC pixels of one frame -> container bytes (FRIEncoder::encode with the transform, quantizer and
+        prediction on the device)."""
+        px, n = self._frames(pixels)
+        assert n == 1
+        qa, qp = _q_array(q)
+        out, ln = _P(), C.c_size_t(0)
+        _check(lib().fri_frv_encode(self._h, px.ctypes.data, qp, colorspace, C.byref(out), C.byref(ln)))
+        return self._take_bytes(out, ln)
+
+    def frv_decode(self, data: bytes, q=None, multiply: bool = False) -> np.ndarray:
+        """Container bytes -> HWC pixels [H, W, C] (FRIDecoder::decode)."""
+        buf = np.frombuffer(data, dtype=np.uint8)
+        out = np.empty(self.frame_shape, self.pixel_dtype)
+        qa, qp = _q_array(q)
+        mode = FRI_DEQUANT_MULTIPLY if multiply else FRI_DEQUANT_DIVIDE
+        _check(lib().fri_frv_decode(self._h, buf.ctypes.data, len(data), qp, mode, out.ctypes.data))
         return out
 
     # ---- device-resident entry points (raw device pointers, e.g. torch.Tensor.data_ptr()) -----

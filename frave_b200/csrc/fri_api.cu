@@ -6,11 +6,14 @@
 #include <algorithm>
 #include <cstring>
 #include <mutex>
+#include <thread>
+#include <cstdlib>
 #include <new>
 #include <string>
 #include <vector>
 
 #include "../../include/fri_cuda.h"
+#include "fri_codec.h"
 #include "fri_kernels.cuh"
 #include "fri_plan.h"
 
@@ -96,6 +99,10 @@ struct fri_plan {
     bool predict_ready = false;
     void *d_pred_tile_at = nullptr, *d_pred_centers = nullptr, *d_pred_lut = nullptr, *d_pred_off = nullptr;
     PredictTables predict_tables;
+    // host lattice index for the host predictor / entropy decoder (computed on first use)
+    bool lattice_ready = false;
+    LatticeIndex lattice;
+    std::vector<uint8_t> some_flat;  // [n_tiles * 512] Some / None
 };
 
 namespace {
@@ -1101,6 +1108,264 @@ int fri_predict_device(fri_plan *p, const int32_t *d_coefs, uint32_t n_frames, c
     p->last_launches = launches;
     if (e != cudaSuccess) return cuda_fail(e, "launch_predict");
     return FRI_OK;
+}
+
+/* ---- host codec behind the transform: parameter fit, context model, rANS, `frif` container
+ *      (fri_codec.cpp) ------------------------------------------- */
+static int ensure_lattice(fri_plan *p)
+{
+    int rc = ensure_emission(p);
+    if (rc) return rc;
+    if (p->lattice_ready) return FRI_OK;
+    try {
+        build_lattice_index(p->plan, p->lattice);
+        const Geometry &g = p->plan.geo;
+        p->some_flat.assign((size_t)g.n_fractals * kTileLeaves, 1);
+        std::vector<uint32_t> mask(kTileLeaves / 32);
+        for (int32_t t = 0; t < g.n_fractals; ++t) {
+            if (p->plan.full[t]) continue;
+            fractal_mask(g.depth, p->plan.centers[2 * t], p->plan.centers[2 * t + 1], g.width, g.height, mask.data());
+            for (int i = 0; i < kTileLeaves; ++i) p->some_flat[(size_t)t * kTileLeaves + i] = (mask[i >> 5] >> (i & 31)) & 1u;
+        }
+    } catch (const std::bad_alloc &) {
+        return fail(FRI_E_NOMEM, "out of host memory while building the lattice index");
+    }
+    p->lattice_ready = true;
+    return FRI_OK;
+}
+
+static int host_threads_hint()
+{
+    const unsigned n = std::thread::hardware_concurrency();
+    return (int)std::max(1u, std::min(n, 16u));
+}
+
+int fri_fit_parameters(fri_plan *p, const int32_t *coefs, float *value_params, float *width_params)
+{
+    if (!p || !coefs || !value_params || !width_params) return fail(FRI_E_INVALID, "NULL argument");
+    int rc = ensure_lattice(p);
+    if (rc) return rc;
+    try {
+        codec::fit_parameters(p->plan, p->lattice, p->some_flat, coefs, value_params, width_params, host_threads_hint());
+    } catch (const std::bad_alloc &) {
+        return fail(FRI_E_NOMEM, "out of host memory");
+    }
+    return FRI_OK;
+}
+
+int fri_predict_host(fri_plan *p, const int32_t *coefs, const float *value_params, const float *width_params, uint8_t *bucket,
+                     int32_t *pred, uint16_t *sym, uint32_t *hist, uint32_t *overflow)
+{
+    if (!p || !coefs || !value_params || !width_params || !bucket || !pred || !sym || !hist) return fail(FRI_E_INVALID, "NULL argument");
+    int rc = ensure_lattice(p);
+    if (rc) return rc;
+    const Geometry &g = p->plan.geo;
+    const int C = g.channels;
+    const size_t count = p->emit_src.size();
+    const codec::Predictor pr(p->lattice, p->plan.centers.data(), C);
+    std::memset(hist, 0, sizeof(uint32_t) * (size_t)C * codec::kContexts * codec::kAlphabet);
+    uint32_t over = 0;
+    for (int ch = 0; ch < C; ++ch) {
+        float vp[3][6], wp[3][6];
+        std::memcpy(vp, value_params + (size_t)ch * 18, sizeof(vp));
+        std::memcpy(wp, width_params + (size_t)ch * 18, sizeof(wp));
+        for (size_t k = 0; k < count; ++k) {
+            const uint32_t src = p->emit_src[k];
+            const int tile = (int)(src >> kBaseDepth), heap = (int)(src & (kTileLeaves - 1));
+            int b;
+            int32_t pv;
+            if (heap < 2) pr.lf(coefs, tile, heap, ch, b, pv);
+            else pr.hf(coefs, tile, heap, ch, vp, wp, b, pv);
+            const int32_t value = coefs[(((size_t)tile * C + ch) << kBaseDepth) + heap];
+            const uint32_t s = codec::pack_signed((int32_t)((uint32_t)value - (uint32_t)pv));
+            bucket[ch * count + k] = (uint8_t)b;
+            pred[ch * count + k] = pv;
+            sym[ch * count + k] = (uint16_t)std::min<uint32_t>(s, 0xffffu);
+            if (s < (uint32_t)codec::kAlphabet) ++hist[((size_t)ch * codec::kContexts + b) * codec::kAlphabet + s];
+            else ++over;
+        }
+    }
+    if (overflow) *overflow = over;
+    return FRI_OK;
+}
+
+static int colorspace_code(const Geometry &g, int colorspace)
+{
+    if (colorspace == 0) return g.channels == 1 ? 1 : 2;  // Luma / RGB (images.rs:23-29)
+    return colorspace;
+}
+
+int fri_frv_pack(fri_plan *p, int colorspace, const float *value_params, const float *width_params, const uint8_t *bucket,
+                 const uint16_t *sym, const uint32_t *hist, uint8_t **out, size_t *out_len)
+{
+    if (!p || !value_params || !width_params || !bucket || !sym || !hist || !out || !out_len) return fail(FRI_E_INVALID, "NULL argument");
+    *out = nullptr;
+    *out_len = 0;
+    int rc = ensure_emission(p);
+    if (rc) return rc;
+    const Geometry &g = p->plan.geo;
+    if (g.sample_bytes != 1) return fail(FRI_E_UNSUPPORTED, "the frif container holds 8-bit images (images.rs:84)");
+    colorspace = colorspace_code(g, colorspace);
+    if (colorspace < 1 || colorspace > 3 || (colorspace == 1) != (g.channels == 1))
+        return fail(FRI_E_INVALID, "colorspace must be 1 (Luma, 1 channel), 2 (RGB) or 3 (YCbCr), or 0 for the default");
+    const int C = g.channels;
+    const size_t count = p->emit_src.size();
+    try {
+        std::vector<codec::ChannelPayload> payload((size_t)C);
+        std::vector<std::string> err((size_t)C);
+        std::vector<std::thread> th;
+        for (int ch = 0; ch < C; ++ch)
+            th.emplace_back([&, ch] {
+                std::memcpy(payload[ch].value_params, value_params + (size_t)ch * 18, sizeof(float) * 18);
+                std::memcpy(payload[ch].width_params, width_params + (size_t)ch * 18, sizeof(float) * 18);
+                err[ch] = codec::entropy_encode_channel(sym + (size_t)ch * count, bucket + (size_t)ch * count, count,
+                                                        hist + (size_t)ch * codec::kContexts * codec::kAlphabet, payload[ch]);
+            });
+        for (auto &t : th) t.join();
+        for (int ch = 0; ch < C; ++ch)
+            if (!err[ch].empty()) return fail(FRI_E_UNSUPPORTED, "channel %d: %s", ch, err[ch].c_str());
+        const std::vector<uint8_t> bytes = codec::serialize((uint32_t)g.height, (uint32_t)g.width, colorspace, payload);
+        uint8_t *buf = static_cast<uint8_t *>(std::malloc(bytes.size() ? bytes.size() : 1));
+        if (!buf) return fail(FRI_E_NOMEM, "out of host memory");
+        std::memcpy(buf, bytes.data(), bytes.size());
+        *out = buf;
+        *out_len = bytes.size();
+    } catch (const std::bad_alloc &) {
+        return fail(FRI_E_NOMEM, "out of host memory");
+    }
+    return FRI_OK;
+}
+
+void fri_frv_free(uint8_t *bytes) { std::free(bytes); }
+
+int fri_frv_info(const uint8_t *bytes, size_t len, uint32_t *width, uint32_t *height, uint32_t *channels)
+{
+    if (!bytes || len < 16 || std::memcmp(bytes, "frif", 4) != 0) return fail(FRI_E_INVALID, "Invalid signature for FRIF image.");
+    auto u32 = [&](size_t o) { return (uint32_t)bytes[o] | (uint32_t)bytes[o + 1] << 8 | (uint32_t)bytes[o + 2] << 16 | (uint32_t)bytes[o + 3] << 24; };
+    const uint32_t cs = u32(12) >> 30 & 3;
+    if (cs == 0) return fail(FRI_E_INVALID, "Invalid metadata");
+    if (height) *height = u32(4);
+    if (width) *width = u32(8);
+    if (channels) *channels = cs == 1 ? 1 : 3;
+    return FRI_OK;
+}
+
+int fri_frv_unpack(fri_plan *p, const uint8_t *bytes, size_t len, int32_t *coefs)
+{
+    if (!p || !bytes || !coefs) return fail(FRI_E_INVALID, "NULL argument");
+    int rc = ensure_lattice(p);
+    if (rc) return rc;
+    const Geometry &g = p->plan.geo;
+    try {
+        uint32_t h = 0, w = 0;
+        int cs = 0;
+        std::vector<codec::ChannelPayload> payload;
+        const std::string perr = codec::deserialize(bytes, len, h, w, cs, payload);
+        if (!perr.empty()) return fail(FRI_E_INVALID, "%s", perr.c_str());
+        const int C = cs == 1 ? 1 : 3;
+        if ((int32_t)h != g.height || (int32_t)w != g.width || C != g.channels)
+            return fail(FRI_E_INVALID, "container holds a %ux%ux%d image, the plan is for %dx%dx%d", w, h, C, g.width, g.height, g.channels);
+        if ((int)payload.size() != C) return fail(FRI_E_INVALID, "container holds %zu channel(s), expected %d", payload.size(), C);
+        std::memset(coefs, 0, sizeof(int32_t) * (size_t)g.coefs_per_frame);  // from_metadata: every covered coefficient Some(0)
+        const codec::Predictor pr(p->lattice, p->plan.centers.data(), C);
+        std::vector<std::string> err((size_t)C);
+        std::vector<std::thread> th;  // channels are independent: a channel's predictor reads its own channel only
+        for (int ch = 0; ch < C; ++ch)
+            th.emplace_back([&, ch] { err[ch] = codec::entropy_decode_channel(payload[ch], pr, p->emit_src, ch, coefs); });
+        for (auto &t : th) t.join();
+        for (int ch = 0; ch < C; ++ch)
+            if (!err[ch].empty()) return fail(FRI_E_INVALID, "channel %d: %s", ch, err[ch].c_str());
+    } catch (const std::bad_alloc &) {
+        return fail(FRI_E_NOMEM, "out of host memory");
+    }
+    return FRI_OK;
+}
+
+int fri_frv_encode(fri_plan *p, const void *pixels, const int32_t *q, int colorspace, uint8_t **out, size_t *out_len)
+{
+    if (!out || !out_len) return fail(FRI_E_INVALID, "NULL argument");
+    *out = nullptr;
+    *out_len = 0;
+    int rc = enter_device(p);
+    if (rc) return rc;
+    if (!pixels) return fail(FRI_E_INVALID, "NULL host buffer");
+    if ((rc = check_q(q))) return rc;
+    if ((rc = ensure_predict_device(p))) return rc;
+    if ((rc = ensure_lattice(p))) return rc;
+    if ((rc = ensure_slots(p))) return rc;
+    const Geometry &g = p->plan.geo;
+    if (g.sample_bytes != 1) return fail(FRI_E_UNSUPPORTED, "the frif container holds 8-bit images (images.rs:84)");
+    const int C = g.channels;
+    const size_t count = p->emit_src.size(), n_hist = (size_t)C * codec::kContexts * codec::kAlphabet;
+    QuantParams qp;
+    make_quant_params(qp, q, 0);
+    Pipeline &pl = p->pipe;
+    Slot &s = p->slots[0];
+    cudaStream_t st = pl.compute;
+    if ((rc = acquire_slot(p, s))) return rc;
+    p->last_launches = 0;
+    try {
+        // 1. transform + quantization on the device; the dense blocks come back for the parameter fit
+        std::vector<int32_t> coefs((size_t)g.coefs_per_frame);
+        FRI_CUDA(cudaMemcpyAsync(s.d_pixels, pixels, (size_t)g.frame_bytes, cudaMemcpyHostToDevice, st));
+        FRI_CUDA(launch_encode(g, p->tables, qp, s.d_pixels, 1, s.d_coefs, false, s.d_dc, st, &p->last_launches));
+        FRI_CUDA(cudaMemcpyAsync(coefs.data(), s.d_coefs, coefs.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        FRI_CUDA(cudaStreamSynchronize(st));
+        // 2. predictor parameters (host least squares; context_modeling.rs:204-214)
+        std::vector<float> vp((size_t)C * 18), wp((size_t)C * 18);
+        codec::fit_parameters(p->plan, p->lattice, p->some_flat, coefs.data(), vp.data(), wp.data(), host_threads_hint());
+        // 3. prediction + context buckets + histograms on the device
+        PredictParams prm{};
+        std::memcpy(prm.value, vp.data(), sizeof(float) * 18 * C);
+        std::memcpy(prm.width, wp.data(), sizeof(float) * 18 * C);
+        uint8_t *d_bucket = nullptr;
+        int32_t *d_pred = nullptr;
+        uint16_t *d_sym = nullptr;
+        uint32_t *d_hist = nullptr;
+        if ((rc = pool_alloc(p, reinterpret_cast<void **>(&d_bucket), (size_t)C * count, st))) return rc;
+        if ((rc = pool_alloc(p, reinterpret_cast<void **>(&d_pred), (size_t)C * count * sizeof(int32_t), st))) return rc;
+        if ((rc = pool_alloc(p, reinterpret_cast<void **>(&d_sym), (size_t)C * count * sizeof(uint16_t), st))) return rc;
+        if ((rc = pool_alloc(p, reinterpret_cast<void **>(&d_hist), (n_hist + 1) * sizeof(uint32_t), st))) return rc;
+        std::vector<uint8_t> bucket((size_t)C * count);
+        std::vector<uint16_t> sym((size_t)C * count);
+        std::vector<uint32_t> hist(n_hist + 1);
+        FRI_CUDA(cudaMemsetAsync(d_hist, 0, (n_hist + 1) * sizeof(uint32_t), st));
+        FRI_CUDA(launch_predict(g, p->tables, p->emit_tables, p->predict_tables, prm, count, s.d_coefs, 1, d_bucket, d_pred, d_sym,
+                                d_hist, d_hist + n_hist, st, &p->last_launches));
+        FRI_CUDA(cudaMemcpyAsync(bucket.data(), d_bucket, bucket.size(), cudaMemcpyDeviceToHost, st));
+        FRI_CUDA(cudaMemcpyAsync(sym.data(), d_sym, sym.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+        FRI_CUDA(cudaMemcpyAsync(hist.data(), d_hist, hist.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        for (void *d : {(void *)d_bucket, (void *)d_pred, (void *)d_sym, (void *)d_hist}) cudaFreeAsync(d, st);
+        FRI_CUDA(cudaEventRecord(s.compute_done, st));
+        FRI_CUDA(cudaEventRecord(s.out_done, st));
+        s.used = true;
+        FRI_CUDA(cudaStreamSynchronize(st));
+        if (hist[n_hist] != 0)
+            return fail(FRI_E_UNSUPPORTED, "%u residual(s) fall outside the 1024-symbol alphabet (the reference panics at entropy_coding.rs:99)",
+                        hist[n_hist]);
+        // 4. rANS + container on the host
+        return fri_frv_pack(p, colorspace, vp.data(), wp.data(), bucket.data(), sym.data(), hist.data(), out, out_len);
+    } catch (const std::bad_alloc &) {
+        return fail(FRI_E_NOMEM, "out of host memory");
+    }
+}
+
+int fri_frv_decode(fri_plan *p, const uint8_t *bytes, size_t len, const int32_t *q, int dequant_mode, void *pixels)
+{
+    int rc = enter_device(p);
+    if (rc) return rc;
+    if (!bytes || !pixels) return fail(FRI_E_INVALID, "NULL argument");
+    try {
+        std::vector<int32_t> coefs((size_t)p->plan.geo.coefs_per_frame);
+        if ((rc = fri_frv_unpack(p, bytes, len, coefs.data()))) return rc;  // entropy decoding: serial, host (entropy_coding.rs:354-449)
+        const bool was_async = p->async_mode;
+        p->async_mode = false;  // `coefs` is a local: the copies must have finished before it goes away
+        rc = fri_decode_tq(p, coefs.data(), 1, q, dequant_mode, pixels);
+        p->async_mode = was_async;
+        return rc;
+    } catch (const std::bad_alloc &) {
+        return fail(FRI_E_NOMEM, "out of host memory");
+    }
 }
 
 int fri_host_alloc(void **out, size_t bytes)

@@ -235,6 +235,43 @@ int fri_predict_device(fri_plan *plan, const int32_t *d_coefs, uint32_t n_frames
                        uint32_t *d_overflow, void *stream);
 
 /*
+ * The host side of the codec behind the transform (depth 9, 8-bit samples):
+ * the reference keeps context modelling, rANS and the `frif` container on the host, and so does this
+ * library — in C++ (frave_b200/csrc/fri_codec.cpp), restating stages/entropy_coding.rs:32-176, :205-449,
+ * stages/serialize.rs:40-268, context_modeling.rs:79-214 and the published rans64 algorithm behind the
+ * un-vendored `rans 0.2.1` crate.  PARITY UNPINNED (no reference build exists here): containers written here
+ * decode here bit-exactly; byte identity with the reference's `.frv` files is not claimed.
+ *   fri_fit_parameters  host coefs [n_tiles][C][512] -> value / width predictor parameters float [C][3][6]
+ *                       (least squares; the solver is NOT lstsq / nalgebra's f32 SVD)
+ *   fri_predict_host    the host form of fri_predict_device (same outputs, host arrays, one frame): what the
+ *                       serial entropy decoder evaluates per coefficient
+ *   fri_frv_pack        symbols + buckets + histograms (from fri_predict_device / _host) -> container bytes:
+ *                       AnsContext tables from the Laplace model, 10 interleaved 64-bit rANS streams fed in
+ *                       reverse emission order, serialize.rs layout.  *out is malloc'd: fri_frv_free.
+ *                       colorspace: 0 = default (Luma for 1 channel, RGB for 3), 1 Luma, 2 RGB, 3 YCbCr.
+ *   fri_frv_unpack      container bytes -> dense coefficient blocks (serial: every prediction reads already
+ *                       decoded neighbours, entropy_coding.rs:205-264; channels run on separate host threads)
+ *   fri_frv_info        width / height / channels of a container
+ *   fri_frv_encode      host pixels -> container bytes: transform + quantization on the device, parameter fit
+ *                       on the host, prediction + buckets + histograms on the device, rANS + container on the
+ *                       host (FRIEncoder::encode, encoder.rs:87-109)
+ *   fri_frv_decode      container bytes -> host pixels: fri_frv_unpack, then dequantization + inverse
+ *                       transform on the device (FRIDecoder::decode, decoder.rs:48-59)
+ * FRI_E_UNSUPPORTED where the reference itself panics: a residual outside the 1024-symbol alphabet
+ * (entropy_coding.rs:99), or an image size whose sort_lattice scan asserts (wavelet_transform.rs:701).
+ */
+int fri_fit_parameters(fri_plan *plan, const int32_t *coefs, float *value_params, float *width_params);
+int fri_predict_host(fri_plan *plan, const int32_t *coefs, const float *value_params, const float *width_params,
+                     uint8_t *bucket, int32_t *pred, uint16_t *sym, uint32_t *hist, uint32_t *overflow);
+int fri_frv_pack(fri_plan *plan, int colorspace, const float *value_params, const float *width_params,
+                 const uint8_t *bucket, const uint16_t *sym, const uint32_t *hist, uint8_t **out, size_t *out_len);
+int fri_frv_unpack(fri_plan *plan, const uint8_t *bytes, size_t len, int32_t *coefs);
+int fri_frv_info(const uint8_t *bytes, size_t len, uint32_t *width, uint32_t *height, uint32_t *channels);
+int fri_frv_encode(fri_plan *plan, const void *pixels, const int32_t *q, int colorspace, uint8_t **out, size_t *out_len);
+int fri_frv_decode(fri_plan *plan, const uint8_t *bytes, size_t len, const int32_t *q, int dequant_mode, void *pixels);
+void fri_frv_free(uint8_t *bytes);
+
+/*
  * How the host-buffer entry points stream one frame through the device: in `bands` consecutive
  * bands of tile groups (1..8), each with its own copy in, kernels and copy out on three
  * event-chained streams, so that a single call overlaps its own host->device and device->host

@@ -10,13 +10,14 @@ fn main() {
     let lib = out.join("libfri_cuda.a");
     let status = Command::new(&nvcc)
         .args(["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo"])
-        .args(["-Xcompiler", "-fPIC", "--lib", "-o"])
+        .args(["-Xcompiler", "-fPIC,-ffp-contract=off", "--lib", "-o"])
         .arg(&lib)
         .arg(csrc.join("fri_api.cu"))
         .arg(csrc.join("fri_kernels.cu"))
         .arg(csrc.join("fri_predict.cu"))
         .arg(csrc.join("fri_plan.cpp"))
         .arg(csrc.join("fri_order.cpp"))
+        .arg(csrc.join("fri_codec.cpp"))
         .status()
         .expect("nvcc not found: libfri-cuda has no CPU fallback");
     assert!(status.success(), "nvcc failed");
@@ -25,7 +26,7 @@ fn main() {
     println!("cargo:rustc-link-search=native=/usr/local/cuda/lib64");
     println!("cargo:rustc-link-lib=dylib=cudart");
     println!("cargo:rustc-link-lib=dylib=stdc++");
-    for f in ["fri_api.cu", "fri_kernels.cu", "fri_predict.cu", "fri_plan.cpp", "fri_order.cpp", "fri_kernels.cuh", "fri_plan.h", "fri_geometry.h"] {
+    for f in ["fri_api.cu", "fri_kernels.cu", "fri_predict.cu", "fri_plan.cpp", "fri_order.cpp", "fri_codec.cpp", "fri_codec.h", "fri_kernels.cuh", "fri_plan.h", "fri_geometry.h"] {
         println!("cargo:rerun-if-changed={}", csrc.join(f).display());
     }
 }

@@ -60,6 +60,14 @@ extern "C" {
     fn fri_decode_tq_emit16(plan: *mut FriPlan, streams: *const i16, n_frames: u32, q: *const i32, dequant_mode: c_int, pixels: *mut c_void) -> c_int;
     fn fri_decode_tq_emit10(plan: *mut FriPlan, streams: *const u8, n_frames: u32, q: *const i32, dequant_mode: c_int, pixels: *mut c_void) -> c_int;
     fn fri_predict_device(plan: *mut FriPlan, d_coefs: *const i32, n_frames: u32, value_params: *const f32, width_params: *const f32, d_bucket: *mut u8, d_pred: *mut i32, d_sym: *mut u16, d_hist: *mut u32, d_overflow: *mut u32, stream: *mut c_void) -> c_int;
+    fn fri_fit_parameters(plan: *mut FriPlan, coefs: *const i32, value_params: *mut f32, width_params: *mut f32) -> c_int;
+    fn fri_predict_host(plan: *mut FriPlan, coefs: *const i32, value_params: *const f32, width_params: *const f32, bucket: *mut u8, pred: *mut i32, sym: *mut u16, hist: *mut u32, overflow: *mut u32) -> c_int;
+    fn fri_frv_pack(plan: *mut FriPlan, colorspace: c_int, value_params: *const f32, width_params: *const f32, bucket: *const u8, sym: *const u16, hist: *const u32, out: *mut *mut u8, out_len: *mut usize) -> c_int;
+    fn fri_frv_unpack(plan: *mut FriPlan, bytes: *const u8, len: usize, coefs: *mut i32) -> c_int;
+    fn fri_frv_info(bytes: *const u8, len: usize, width: *mut u32, height: *mut u32, channels: *mut u32) -> c_int;
+    fn fri_frv_encode(plan: *mut FriPlan, pixels: *const c_void, q: *const i32, colorspace: c_int, out: *mut *mut u8, out_len: *mut usize) -> c_int;
+    fn fri_frv_decode(plan: *mut FriPlan, bytes: *const u8, len: usize, q: *const i32, dequant_mode: c_int, pixels: *mut c_void) -> c_int;
+    fn fri_frv_free(bytes: *mut u8);
     fn fri_plan_set_bands(plan: *mut FriPlan, bands: c_int) -> c_int;
     fn fri_plan_set_async(plan: *mut FriPlan, on: c_int) -> c_int;
     fn fri_plan_set_independent_calls(plan: *mut FriPlan, on: c_int) -> c_int;
@@ -91,6 +99,12 @@ fn want_len(what: &str, got: usize, want: usize) -> Result<(), String> {
 
 pub fn version() -> String { unsafe { CStr::from_ptr(fri_version()) }.to_string_lossy().into_owned() }
 pub fn device_count() -> i32 { unsafe { fri_device_count() } }
+/// (width, height, channels) of a `frif` container.
+pub fn frv_info(bytes: &[u8]) -> Result<(u32, u32, u32), String> {
+    let (mut w, mut h, mut c) = (0u32, 0u32, 0u32);
+    check(unsafe { fri_frv_info(bytes.as_ptr(), bytes.len(), &mut w, &mut h, &mut c) })?;
+    Ok((w, h, c))
+}
 /// value / q exactly as the kernels compute it (truncation toward zero, quantization.rs:19).
 pub fn quant_divide(value: i32, q: i32) -> i32 { unsafe { fri_quant_divide(value, q) } }
 pub fn quant_divide_magic(value: i32, q: i32) -> i32 { unsafe { fri_quant_divide_magic(value, q) } }
@@ -249,6 +263,66 @@ impl Plan {
         want_len("packed streams", packed.len(), n)?;
         want_len("pixels", pixels.len(), self.frame_bytes)?;
         check(unsafe { fri_decode_tq_emit10(self.raw, packed.as_ptr(), 1, q.as_ptr(), FRI_DEQUANT_DIVIDE, pixels.as_mut_ptr() as *mut c_void) })
+    }
+
+    // ---- the whole codec (this library's own host entropy coder + container; parity with the reference's bytes unpinned)
+    /// FRIEncoder::encode (encoder.rs:87-109): pixels -> `frif` container bytes.
+    pub fn frv_encode(&mut self, pixels: &[u8], q: &[i32; 32]) -> Result<Vec<u8>, String> {
+        want_len("pixels", pixels.len(), self.frame_bytes)?;
+        let (mut out, mut len) = (std::ptr::null_mut::<u8>(), 0usize);
+        check(unsafe { fri_frv_encode(self.raw, pixels.as_ptr() as *const c_void, q.as_ptr(), 0, &mut out, &mut len) })?;
+        let v = unsafe { std::slice::from_raw_parts(out, len) }.to_vec();
+        unsafe { fri_frv_free(out) };
+        Ok(v)
+    }
+    /// FRIDecoder::decode (decoder.rs:48-59): container bytes -> pixels.
+    pub fn frv_decode(&mut self, bytes: &[u8], q: &[i32; 32], pixels: &mut [u8]) -> Result<(), String> {
+        want_len("pixels", pixels.len(), self.frame_bytes)?;
+        check(unsafe { fri_frv_decode(self.raw, bytes.as_ptr(), bytes.len(), q.as_ptr(), FRI_DEQUANT_DIVIDE, pixels.as_mut_ptr() as *mut c_void) })
+    }
+    /// Entropy decoding only: container bytes -> quantized dense blocks (for a caller that keeps its own lattice).
+    pub fn frv_unpack(&mut self, bytes: &[u8], coefs: &mut [i32]) -> Result<(), String> {
+        want_len("coefs", coefs.len(), self.coefs_per_frame)?;
+        check(unsafe { fri_frv_unpack(self.raw, bytes.as_ptr(), bytes.len(), coefs.as_mut_ptr()) })
+    }
+    /// Predictor parameter fit on the host (context_modeling.rs:204-214): ([C][3][6] value, [C][3][6] width).
+    pub fn fit_parameters(&mut self, coefs: &[i32]) -> Result<(Vec<[[f32; 6]; 3]>, Vec<[[f32; 6]; 3]>), String> {
+        want_len("coefs", coefs.len(), self.coefs_per_frame)?;
+        let (mut v, mut w) = (vec![[[0f32; 6]; 3]; self.channels], vec![[[0f32; 6]; 3]; self.channels]);
+        check(unsafe { fri_fit_parameters(self.raw, coefs.as_ptr(), v.as_mut_ptr() as *mut f32, w.as_mut_ptr() as *mut f32) })?;
+        Ok((v, w))
+    }
+    /// Host predictor (what the serial entropy decoder evaluates): see include/fri_cuda.h for the array shapes.
+    #[allow(clippy::too_many_arguments)]
+    pub fn predict_host(&mut self, coefs: &[i32], value_params: &[[[f32; 6]; 3]], width_params: &[[[f32; 6]; 3]], bucket: &mut [u8], pred: &mut [i32],
+                        sym: &mut [u16], hist: &mut [u32]) -> Result<u32, String> {
+        let n = self.channels * self.emission_count();
+        want_len("coefs", coefs.len(), self.coefs_per_frame)?;
+        want_len("value_params", value_params.len(), self.channels)?;
+        want_len("width_params", width_params.len(), self.channels)?;
+        want_len("bucket", bucket.len(), n)?;
+        want_len("pred", pred.len(), n)?;
+        want_len("sym", sym.len(), n)?;
+        want_len("hist", hist.len(), self.channels * 10 * 1024)?;
+        let mut over = 0u32;
+        check(unsafe { fri_predict_host(self.raw, coefs.as_ptr(), value_params.as_ptr() as *const f32, width_params.as_ptr() as *const f32,
+                                        bucket.as_mut_ptr(), pred.as_mut_ptr(), sym.as_mut_ptr(), hist.as_mut_ptr(), &mut over) })?;
+        Ok(over)
+    }
+    /// Symbols + buckets + histograms -> container bytes (rANS + serialize on the host).
+    pub fn frv_pack(&mut self, value_params: &[[[f32; 6]; 3]], width_params: &[[[f32; 6]; 3]], bucket: &[u8], sym: &[u16], hist: &[u32]) -> Result<Vec<u8>, String> {
+        let n = self.channels * self.emission_count();
+        want_len("value_params", value_params.len(), self.channels)?;
+        want_len("width_params", width_params.len(), self.channels)?;
+        want_len("bucket", bucket.len(), n)?;
+        want_len("sym", sym.len(), n)?;
+        want_len("hist", hist.len(), self.channels * 10 * 1024)?;
+        let (mut out, mut len) = (std::ptr::null_mut::<u8>(), 0usize);
+        check(unsafe { fri_frv_pack(self.raw, 0, value_params.as_ptr() as *const f32, width_params.as_ptr() as *const f32, bucket.as_ptr(), sym.as_ptr(),
+                                    hist.as_ptr(), &mut out, &mut len) })?;
+        let v = unsafe { std::slice::from_raw_parts(out, len) }.to_vec();
+        unsafe { fri_frv_free(out) };
+        Ok(v)
     }
 
     /// Bands per frame of the host-buffer calls: 0 = automatic (single caller), 1 when an encoder and a
