@@ -77,7 +77,7 @@ struct fri_plan {
     int device = -1;
     DeviceTables tables;
     void *d_groups_launch = nullptr;
-    void *d_groups = nullptr, *d_tile_unit = nullptr, *d_chunk_mask = nullptr, *d_chunk_list = nullptr, *d_stage_list = nullptr;
+    void *d_groups = nullptr, *d_tile_unit = nullptr, *d_chunk_mask = nullptr, *d_chunk_list = nullptr, *d_stage_list = nullptr, *d_edge_list = nullptr;
     Slot slots[kSlots];
     Pipeline pipe;
     bool slots_ready = false;
@@ -359,6 +359,7 @@ int fri_plan_create(fri_plan **out, int device, uint32_t width, uint32_t height,
         if (e == cudaSuccess) e = upload(&p->d_chunk_mask, pl.chunk_mask.data(), pl.chunk_mask.size() * sizeof(uint16_t));
         if (e == cudaSuccess) e = upload(&p->d_stage_list, pl.stage_list.data(), pl.stage_list.size() * sizeof(uint32_t));
         if (e == cudaSuccess) e = upload(&p->d_chunk_list, pl.chunk_list.data(), pl.chunk_list.size() * sizeof(uint32_t));
+        if (e == cudaSuccess) e = upload(&p->d_edge_list, pl.edge_list.data(), pl.edge_list.size() * sizeof(uint32_t));
         if (e != cudaSuccess) {
             fri_plan_destroy(p);
             return cuda_fail(e, "uploading the plan tables");
@@ -368,6 +369,7 @@ int fri_plan_create(fri_plan **out, int device, uint32_t width, uint32_t height,
         p->tables.tile_unit = static_cast<const uint32_t *>(p->d_tile_unit);
         p->tables.chunk_mask = static_cast<const uint16_t *>(p->d_chunk_mask);
         p->tables.chunk_list = static_cast<const uint32_t *>(p->d_chunk_list);
+        p->tables.edge_list = static_cast<const uint32_t *>(p->d_edge_list);
         p->tables.stage_list = static_cast<const uint32_t *>(p->d_stage_list);
     }
     *out = p;
@@ -401,6 +403,7 @@ void fri_plan_destroy(fri_plan *p)
         if (p->d_tile_unit) cudaFree(p->d_tile_unit);
         if (p->d_chunk_mask) cudaFree(p->d_chunk_mask);
         if (p->d_chunk_list) cudaFree(p->d_chunk_list);
+        if (p->d_edge_list) cudaFree(p->d_edge_list);
         if (p->d_emit_goff) cudaFree(p->d_emit_goff);
         if (p->d_emit_dst) cudaFree(p->d_emit_dst);
         if (p->d_emit_loc) cudaFree(p->d_emit_loc);

@@ -1037,24 +1037,24 @@ constexpr int kWriteAhead = 6;
 // cache-global and write-through stores measured equal to the default).
 #define FRI_PIXEL_STORE(ptr, val) __stcs((ptr), (val))
 
-// Partially owned chunks are written one 32-bit word per thread and iteration (four neighbouring
-// lanes share a chunk): a word is skipped, stored whole, or — only the word the group's outline
-// passes through — stored bytewise.  One chunk per thread would make every warp walk through all
-// four words' byte paths.
-#ifndef FRI_MIXED_AHEAD
-#define FRI_MIXED_AHEAD 5
-#endif
-constexpr int kMixedAhead = FRI_MIXED_AHEAD;  // word-loop iterations whose table entries are fetched before the barrier
+// Partially owned chunks (the group's fractal outline; 289 of a 4 x 4 RGB group's 1 682 chunks): an interior
+// group writes them from the plan's edge list — first the fully owned 32-bit words (one LDS.32 + STG.32 each),
+// then the owned samples of the words the outline passes through (one sample-sized load and store each) — so the
+// loop has no per-word mask test and no divergence; the round's earlier form walked chunk masks word by word
+// (skip / whole word / bytewise) and cost three times the instructions.  Groups that touch the image border keep
+// the masked chunk form, which also clips.
+constexpr int kWordAhead = 2;  // edge-list entries per thread fetched before the barrier: words ...
+constexpr int kSampAhead = 4;  // ... and samples
 
 struct WriteAhead {
-    uint32_t e[kWriteAhead];      // fully owned chunks
-    uint32_t me[kMixedAhead];     // partially owned chunks ...
-    uint32_t mm[kMixedAhead];     // ... and their byte masks
+    uint32_t e[kWriteAhead];   // fully owned chunks
+    uint32_t w[kWordAhead];    // fully owned words of the partially owned chunks
+    uint32_t s[kSampAhead];    // owned samples of the remaining words
 };
 
 __device__ __forceinline__ WriteAhead write_out_preload(const Geometry &g, const RegionView &rv,
                                                         const uint32_t *__restrict__ chunk_list,
-                                                        const uint16_t *__restrict__ chunk_mask, uint64_t pol)
+                                                        const uint32_t *__restrict__ edge_list, uint64_t pol)
 {
     WriteAhead w;
     const uint32_t *cl = chunk_list + (size_t)rv.phi0 * g.list_cap;
@@ -1068,44 +1068,38 @@ __device__ __forceinline__ WriteAhead write_out_preload(const Geometry &g, const
         const int k = min((int)(threadIdx.x + u * blockDim.x), n_full - 1);
         w.e[u] = (rv.interior && n_full > 0) ? ld_table(cl + k, pol) : kNoChunk;
     }
-    const uint16_t *cmk = chunk_mask + (size_t)rv.phi0 * g.list_cap;
-    const int n_all = g.list_all[rv.phi0];
+    const uint32_t *el = edge_list + (size_t)rv.phi0 * g.edge_cap;
+    const int n_words = g.edge_words[rv.phi0], n_samples = g.edge_samples[rv.phi0];
 #pragma unroll
-    for (int u = 0; u < kMixedAhead; ++u) {
-        const int k = n_full + ((threadIdx.x + u * blockDim.x) >> 2);
-        const bool on = rv.interior && k < n_all;
-        w.me[u] = on ? ld_table(cl + k, pol) : kNoChunk;
-        w.mm[u] = on ? ld_table(cmk + k, pol) : 0u;
+    for (int u = 0; u < kWordAhead; ++u) {
+        const int k = (int)(threadIdx.x + u * blockDim.x);
+        w.w[u] = (rv.interior && k < n_words) ? ld_table(el + k, pol) : kNoChunk;
+    }
+#pragma unroll
+    for (int u = 0; u < kSampAhead; ++u) {
+        const int k = (int)(threadIdx.x + u * blockDim.x);
+        w.s[u] = (rv.interior && k < n_samples) ? ld_table(el + n_words + k, pol) : kNoChunk;
     }
     return w;
 }
 
-// Word `w` (0..3) of the partially owned chunk `e` with byte mask `m`.
-__device__ __forceinline__ void store_word_masked(const RegionView &rv, const uint8_t *region, uint32_t e, uint32_t m, int w)
+// One entry of the edge list: row << 20 | shared-memory byte offset.
+template <typename T>
+__device__ __forceinline__ void store_edge(const RegionView &rv, const uint8_t *region, uint32_t e)
 {
-    const uint32_t nib = (m >> (4 * w)) & 15u;
-    if (nib == 0) return;
-    const int r = (int)(e >> 16), s = ((int)(e & 0xffffu) << 4) + 4 * w;
-    uint8_t *gp = rv.gaddr(r, s);
-    const uint32_t v = *reinterpret_cast<const uint32_t *>(region + s);
-    if (nib == 15u) {
-        *reinterpret_cast<uint32_t *>(gp) = v;
-    } else {
-        if (nib & 1u) gp[0] = (uint8_t)v;
-        if (nib & 2u) gp[1] = (uint8_t)(v >> 8);
-        if (nib & 4u) gp[2] = (uint8_t)(v >> 16);
-        if (nib & 8u) gp[3] = (uint8_t)(v >> 24);
-    }
+    const int r = (int)(e >> 20), s = (int)(e & 0xfffffu);
+    *reinterpret_cast<T *>(rv.gaddr(r, s)) = *reinterpret_cast<const T *>(region + s);
 }
 
+template <typename S>
 __device__ __forceinline__ void write_out_group(const Geometry &g, const GroupDesc &gd, const RegionView &rv,
                                                 const uint32_t *__restrict__ chunk_list,
-                                                const uint16_t *__restrict__ chunk_mask, const uint8_t *region,
+                                                const uint16_t *__restrict__ chunk_mask,
+                                                const uint32_t *__restrict__ edge_list, const uint8_t *region,
                                                 const WriteAhead &ahead, uint64_t pol)
 {
     const int n_threads = blockDim.x;
     const uint32_t *cl = chunk_list + (size_t)rv.phi0 * g.list_cap;
-    const uint16_t *cmk = chunk_mask + (size_t)rv.phi0 * g.list_cap;
     const int n_full = g.list_full[rv.phi0], n_all = g.list_all[rv.phi0];
     if (rv.interior) {
         if (n_full > 0 && !FRI_WHATIF_SKIP_FULL) {
@@ -1125,18 +1119,25 @@ __device__ __forceinline__ void write_out_group(const Geometry &g, const GroupDe
             FRI_PIXEL_STORE(reinterpret_cast<int4 *>(rv.gaddr(r, s)), *reinterpret_cast<const int4 *>(region + s));
         }
 #if !FRI_WHATIF_SKIP_MIXED
-        const int w = threadIdx.x & 3;
+        const uint32_t *el = edge_list + (size_t)rv.phi0 * g.edge_cap;
+        const int n_words = g.edge_words[rv.phi0], n_samples = g.edge_samples[rv.phi0];
 #pragma unroll
-        for (int u = 0; u < kMixedAhead; ++u)
-            if (ahead.me[u] != kNoChunk) store_word_masked(rv, region, ahead.me[u], ahead.mm[u], w);
+        for (int u = 0; u < kWordAhead; ++u)
+            if (ahead.w[u] != kNoChunk) store_edge<uint32_t>(rv, region, ahead.w[u]);
 #pragma unroll 1
-        for (int k = n_full + ((threadIdx.x + kMixedAhead * n_threads) >> 2); k < n_all; k += n_threads >> 2)
-            store_word_masked(rv, region, ld_table(cl + k, pol), ld_table(cmk + k, pol), w);
+        for (int k = threadIdx.x + kWordAhead * n_threads; k < n_words; k += n_threads) store_edge<uint32_t>(rv, region, ld_table(el + k, pol));
+#pragma unroll
+        for (int u = 0; u < kSampAhead; ++u)
+            if (ahead.s[u] != kNoChunk) store_edge<S>(rv, region, ahead.s[u]);
+#pragma unroll 1
+        for (int k = threadIdx.x + kSampAhead * n_threads; k < n_samples; k += n_threads)
+            store_edge<S>(rv, region, ld_table(el + n_words + k, pol));
 #endif
 #if FRI_TRACE
         if ((threadIdx.x == 0 || threadIdx.x == 255) && blockIdx.x < 16384) g_trace2[4 * blockIdx.x + (threadIdx.x == 0 ? 2 : 3)] = gtime();
 #endif
     } else {
+        const uint16_t *cmk = chunk_mask + (size_t)rv.phi0 * g.list_cap;
         const int stride32 = (int)g.row_stride;
 #pragma unroll 1
         for (int k = threadIdx.x; k < n_all; k += n_threads) {
@@ -1262,6 +1263,7 @@ __global__ void __launch_bounds__(kThreads, FRI_DEC_MINB)
 fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ QuantParams qp,
                   const GroupDesc *__restrict__ groups, const uint32_t *__restrict__ tile_unit,
                   const uint32_t *__restrict__ chunk_list, const uint16_t *__restrict__ chunk_mask,
+                  const uint32_t *__restrict__ edge_list,
                   const CT *__restrict__ coefs, const int32_t *__restrict__ dc_in, uint8_t *__restrict__ pixels,
                   int group_offset, int no_prefetch_ctas)
 {
@@ -1281,10 +1283,10 @@ fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
     if ((int64_t)blockIdx.y * gridDim.x + blockIdx.x >= no_prefetch_ctas) prefetch_group_coefs<C, DEEP, CT>(g, gd, frame, coefs);
     if (sparse) __syncthreads();
     decode_tiles<C, S, DEEP, QS, CT>(g, qp, gd, rv, tile_unit, frame, region, scratch, coefs, dc_in);
-    const WriteAhead ahead = write_out_preload(g, rv, chunk_list, chunk_mask, pol);
+    const WriteAhead ahead = write_out_preload(g, rv, chunk_list, edge_list, pol);
     __syncthreads();
     FRI_TRACE_MARK(1);
-    write_out_group(g, gd, rv, chunk_list, chunk_mask, region, ahead, pol);
+    write_out_group<S>(g, gd, rv, chunk_list, chunk_mask, edge_list, region, ahead, pol);
 #if FRI_TRACE
     __syncthreads();
 #endif
@@ -1737,7 +1739,7 @@ cudaError_t launch_decode(const Geometry &g, const DeviceTables &t, const QuantP
         int32_t *dc = d_dc ? d_dc + (((int64_t)f0 * g.n_fractals * g.channels) << g.sub_bits) : nullptr;
         cudaError_t launch_err = cudaSuccess;
 #define FRI_LAUNCH_Q(CC, SS, DD, QQ, TT, PTR) \
-    launch_err = launch_pdl(fri_decode_kernel<CC, SS, DD, QQ, TT>, grid, cta_threads(g), smem, stream, g, qp, gtab, t.tile_unit, t.chunk_list, t.chunk_mask, PTR, dc, p, group_begin, no_prefetch_ctas)
+    launch_err = launch_pdl(fri_decode_kernel<CC, SS, DD, QQ, TT>, grid, cta_threads(g), smem, stream, g, qp, gtab, t.tile_unit, t.chunk_list, t.chunk_mask, t.edge_list, PTR, dc, p, group_begin, no_prefetch_ctas)
 #define FRI_LAUNCH(CC, SS, TT, PTR)                                                           \
         do {                                                                                  \
             if (qclass == kQuantNone) FRI_LAUNCH_Q(CC, SS, false, kQuantNone, TT, PTR);       \

@@ -103,6 +103,7 @@ struct DeviceTables {
     const uint32_t *tile_unit = nullptr;   // nullptr at depth 9
     const uint32_t *chunk_list = nullptr;  // [16][list_cap]
     const uint16_t *chunk_mask = nullptr;  // [16][list_cap]
+    const uint32_t *edge_list = nullptr;   // [16][edge_cap]
     const uint32_t *stage_list = nullptr;  // [16][list_cap]
 };
 

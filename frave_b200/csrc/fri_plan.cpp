@@ -368,7 +368,36 @@ std::string build_plan(Plan &plan, uint32_t width, uint32_t height, uint32_t cha
         stage[phase] = std::move(st_first);
         stage[phase].insert(stage[phase].end(), st_rest.begin(), st_rest.end());
     }
-    if ((size_t)g.region_h * g.pitch > ((size_t)1 << 20) || g.region_h > 0xffff) return "group region too large";
+    if ((size_t)g.region_h * g.pitch > ((size_t)1 << 20) || g.region_h >= 4096) return "group region too large";
+    // edge lists: words and samples of the partially owned chunks
+    {
+        std::vector<std::vector<uint32_t>> edges(16);
+        g.edge_cap = 0;
+        for (int phase = 0; phase < 16; ++phase) {
+            std::vector<uint32_t> words, samples;
+            for (size_t k = (size_t)g.list_full[phase]; k < lists[phase].size(); ++k) {
+                const uint32_t entry = lists[phase][k].first, m = lists[phase][k].second;
+                const uint32_t r = entry >> 16, sb = (entry & 0xffffu) << 4;
+                for (uint32_t w = 0; w < 4; ++w) {
+                    const uint32_t nib = (m >> (4 * w)) & 15u;
+                    if (nib == 15u) {
+                        words.push_back(r << 20 | (sb + 4 * w));
+                    } else {
+                        for (uint32_t j = 0; j < 4; j += sample_bytes)
+                            if ((nib >> j) & 1u) samples.push_back(r << 20 | (sb + 4 * w + j));
+                    }
+                }
+            }
+            g.edge_words[phase] = (int32_t)words.size();
+            g.edge_samples[phase] = (int32_t)samples.size();
+            edges[phase] = std::move(words);
+            edges[phase].insert(edges[phase].end(), samples.begin(), samples.end());
+            g.edge_cap = std::max(g.edge_cap, (int32_t)edges[phase].size());
+        }
+        plan.edge_list.assign((size_t)16 * std::max(g.edge_cap, 1), 0u);
+        for (int phase = 0; phase < 16; ++phase)
+            std::copy(edges[phase].begin(), edges[phase].end(), plan.edge_list.begin() + (size_t)phase * g.edge_cap);
+    }
     plan.chunk_list.assign((size_t)16 * g.list_cap, 0u);
     plan.chunk_mask.assign((size_t)16 * g.list_cap, 0);
     plan.stage_list.assign((size_t)16 * g.list_cap, 0u);

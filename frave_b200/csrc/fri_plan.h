@@ -51,6 +51,9 @@ struct Geometry {
     int32_t list_full[16];               // per phase: fully owned 16-byte chunks (listed first)
     int32_t list_all[16];                // per phase: all chunks that hold at least one owned byte
     int32_t stage_first[16];             // per phase: leading stage_list entries needed by the first tile of every warp
+    int32_t edge_cap;                    // entries per phase in the edge list
+    int32_t edge_words[16];              // per phase: fully owned 32-bit words of the partially owned chunks (listed first)
+    int32_t edge_samples[16];            // per phase: owned samples of their remaining, partially owned words
     // Row spans of a full group's footprint, for the encoder's bulk-copy staging of interior groups (one
     // cp.async.bulk per staged row): owned bytes of region row r lie in [row_lo[r], row_hi[r]) (holes
     // inside a span belong to neighbouring groups and are fetched along); row_order lists the rows that
@@ -76,6 +79,10 @@ struct Plan {
     // bytes, fully owned chunks first; chunk_mask[phase][k]: bit j <=> byte j of that chunk is owned.
     std::vector<uint32_t> chunk_list;  // [16][list_cap]
     std::vector<uint16_t> chunk_mask;  // [16][list_cap]
+    // The partially owned chunks (the group's fractal outline) resolved to what the decoder's write-out of an
+    // interior group actually stores: edge_list[phase][k] = row << 20 | shared-memory byte offset of, first, every
+    // fully owned 32-bit word, then every owned sample of the words the outline passes through.
+    std::vector<uint32_t> edge_list;   // [16][edge_cap]
     // the same chunks in the order the encoder stages them: first those that hold a pixel of tile
     // slots 0 .. warps-1 (every warp's first tile), then the rest
     std::vector<uint32_t> stage_list;  // [16][list_cap]
