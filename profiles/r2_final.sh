@@ -24,6 +24,7 @@ python profiles/exp_b2b.py --shape 512x512x1 --frames 256 --divisor 1 --reps 50 
 python profiles/exp_b2b.py --shape 512x512x1 --frames 1 --divisor 1 --reps 200 --tag "configs[0] single 512^2 x 1"
 } > gpurun_out/other_$T.jsonl 2>&1
 python profiles/emit_prof.py > gpurun_out/emit_$T.txt 2>&1
+python profiles/codec_timing.py > gpurun_out/codec_$T.jsonl 2>&1
 python profiles/pcie.py > gpurun_out/pcie_$T.txt 2>&1
 python -m frave_b200.build --variant trace -DFRI_TRACE=1 > /dev/null 2>&1; python profiles/trace.py > gpurun_out/timeline_$T.txt 2>&1; python profiles/trace.py 4096x4096x1 >> gpurun_out/timeline_$T.txt 2>&1
 CMD="python bench.py --steps 3 --warmup 3 --preheat 0 --no-cpu --no-batched --no-e2e"
