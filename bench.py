@@ -483,6 +483,19 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
             dplan.set_bands(0)
             e2e_bytes[tag] = (px_h.array.nbytes + cf_dec.array.nbytes, cf_enc.array.nbytes + out_h.array.nbytes)
             cf_enc.free(); cf_dec.free()
+        # 9-bit packed emission streams (everything an 8-bit image produces fits: |k| <= 255), duplex and quad
+        nb9 = plan.emission_packed_size(9)
+        p9 = [capi.PinnedBuffer((1, C, nb9), np.uint8) for _ in range(2)]
+        plan.encode_emit_packed(px_h.array, q, 9, out=p9[0].array)
+        p9[1].array[...] = p9[0].array
+        dplan.decode_emit_packed(p9[1].array, q, 9, out=out_h.array)
+        if not np.array_equal(out_h.array, plan.decode(plan.encode(px_h.array, q), q)):
+            raise RuntimeError("9-bit packed transport: decode of the packed streams differs from the block path")
+        e2e["duplex_p9"] = duplex(lambda: plan.encode_emit_packed(px_h.array, q, 9, out=p9[0].array),
+                                  lambda: dplan.decode_emit_packed(p9[1].array, q, 9, out=out_h.array))
+        e2e_bytes["p9"] = (px_h.array.nbytes + p9[1].array.nbytes, p9[0].array.nbytes + out_h.array.nbytes)
+        for b_ in p9:
+            b_.free()
         # 10-bit packed emission streams
         nb = plan.emission_packed_bytes()
         pk_enc = capi.PinnedBuffer((1, C, nb), np.uint8)
@@ -512,8 +525,12 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
         pk_dec2.array[...] = pk_dec.array
         plan2.encode_emit10(px_h2.array, q, out=pk_enc2.array)
         dplan2.decode_emit10(pk_dec2.array, q, out=out_h2.array)
+        q9 = [capi.PinnedBuffer((1, C, nb9), np.uint8) for _ in range(4)]  # enc, enc2, dec, dec2
+        plan.encode_emit_packed(px_h.array, q, 9, out=q9[0].array)
+        q9[2].array[...] = q9[0].array
+        q9[3].array[...] = q9[0].array
 
-        def quad_once() -> float:
+        def quad_once(bits: int = 10) -> float:
             errors = []
 
             def loop(call):
@@ -523,10 +540,16 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
                 except Exception as exc:
                     errors.append(exc)
 
-            calls = [lambda: plan.encode_emit10(px_h.array, q, out=pk_enc.array),
-                     lambda: plan2.encode_emit10(px_h2.array, q, out=pk_enc2.array),
-                     lambda: dplan.decode_emit10(pk_dec.array, q, out=out_h.array),
-                     lambda: dplan2.decode_emit10(pk_dec2.array, q, out=out_h2.array)]
+            if bits == 10:
+                calls = [lambda: plan.encode_emit10(px_h.array, q, out=pk_enc.array),
+                         lambda: plan2.encode_emit10(px_h2.array, q, out=pk_enc2.array),
+                         lambda: dplan.decode_emit10(pk_dec.array, q, out=out_h.array),
+                         lambda: dplan2.decode_emit10(pk_dec2.array, q, out=out_h2.array)]
+            else:
+                calls = [lambda: plan.encode_emit_packed(px_h.array, q, 9, out=q9[0].array),
+                         lambda: plan2.encode_emit_packed(px_h2.array, q, 9, out=q9[1].array),
+                         lambda: dplan.decode_emit_packed(q9[2].array, q, 9, out=out_h.array),
+                         lambda: dplan2.decode_emit_packed(q9[3].array, q, 9, out=out_h2.array)]
             if world > 1:
                 dist.barrier()
             th = [threading.Thread(target=loop, args=(c,)) for c in calls]
@@ -541,6 +564,11 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
             return dt
 
         e2e["quad_p10"] = statistics.median(quad_once() for _ in range(3))
+        e2e["quad_p9"] = statistics.median(quad_once(9) for _ in range(3))
+        if not np.array_equal(q9[1].array, q9[0].array):
+            raise RuntimeError("quad e2e: the two encoder handles disagree (9-bit streams)")
+        for b_ in q9:
+            b_.free()
         if not np.array_equal(pk_enc2.array, pk_enc.array) or not np.array_equal(out_h2.array, out_h.array):
             raise RuntimeError("quad e2e: the two handles of a direction disagree")
         for b in (px_h2, out_h2, pk_enc2, pk_dec2):
@@ -598,6 +626,8 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
             fmt = best.split("_")[1]
             api = {"i32": "fri_encode_tq + fri_decode_tq (int32 coefficient blocks on the host side)",
                    "i16": "fri_encode_tq16 + fri_decode_tq16 (int16 coefficient blocks on the host side)",
+                   "p9": "fri_encode_tq_emit_packed + fri_decode_tq_emit_packed at 9 bits per symbol (emission-ordered streams; every "
+                         "coefficient of an 8-bit image fits: |k| <= 255)",
                    "p10": "fri_encode_tq_emit10 + fri_decode_tq_emit10 (emission-ordered streams, 10-bit packed symbols on the "
                           "host side: what the reference's entropy coder consumes / produces)"}[fmt]
             how = {"quad": "two encoder threads and two decoder threads with one plan handle each",
@@ -612,7 +642,7 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
                 "variants_mpix_s": {k: W * H * world * e2e_steps / v / 1e6 for k, v in e2e.items()},
                 "variants": "serial = one thread, encode then decode; duplex = encoder and decoder threads; quad = two of each; async = one thread, "
                             "both handles asynchronous; i32 / i16 = coefficient blocks (4 / 2 B per coefficient over PCIe), "
-                            "p10 = emission-ordered 10-bit packed streams (1.25 B per coefficient)",
+                            "p10 / p9 = emission-ordered streams packed at 10 / 9 bits per symbol (1.25 / 1.125 B per coefficient)",
                 "limiter": "host<->device PCIe copies (both directions busy); kernels are a few percent of the step"}
         if o_pair > 0:
             line["stream_overlap"] = {

@@ -55,6 +55,11 @@ _SYMBOLS = [
     ("fri_decode_tq_emit", C.c_int, [_P, _P, C.c_uint32, _P, C.c_int, _P]),
     ("fri_decode_tq_emit16", C.c_int, [_P, _P, C.c_uint32, _P, C.c_int, _P]),
     ("fri_plan_emission_packed_bytes", C.c_uint64, [_P]),
+    ("fri_plan_emission_packed_size", C.c_uint64, [_P, C.c_int]),
+    ("fri_emit_device_packed", C.c_int, [_P, _P, C.c_uint32, C.c_int, _P, _P]),
+    ("fri_encode_tq_emit_packed", C.c_int, [_P, _P, C.c_uint32, _P, C.c_int, _P]),
+    ("fri_unemit_device_packed", C.c_int, [_P, _P, C.c_uint32, C.c_int, _P, _P]),
+    ("fri_decode_tq_emit_packed", C.c_int, [_P, _P, C.c_uint32, C.c_int, _P, C.c_int, _P]),
     ("fri_emit_device10", C.c_int, [_P, _P, C.c_uint32, _P, _P]),
     ("fri_encode_tq_emit10", C.c_int, [_P, _P, C.c_uint32, _P, _P]),
     ("fri_unemit_device10", C.c_int, [_P, _P, C.c_uint32, _P, _P]),
@@ -136,31 +141,36 @@ def frv_info(data: bytes) -> tuple[int, int, int]:
     return int(w.value), int(h.value), int(c.value)
 
 
-def pack10(values: np.ndarray) -> np.ndarray:
-    """Host restatement of the 10-bit packed transport for tests: int stream [..., n] -> uint8 [..., 80 * ceil(n / 64)]
-    (zig-zag pack_signed of utils.rs:34-40, 64 symbols per 80-byte block, little-endian bit order, zero padding)."""
+def pack_bits(values: np.ndarray, bits: int = 10) -> np.ndarray:
+    """Host restatement of the packed transport for tests: int stream [..., n] -> uint8 [..., 8 * bits * ceil(n / 64)]
+    (zig-zag pack_signed of utils.rs:34-40 saturated to `bits` bits, 64 symbols per block, little-endian bit order,
+    zero padding)."""
     v = np.asarray(values).astype(np.int64)
     n = v.shape[-1]
     pad = (-n) % 64
-    v = np.clip(v, -512, 511)
-    sym = np.where(v >= 0, 2 * v, -2 * v - 1).astype(np.uint64)
+    v = np.clip(v, -(1 << (bits - 1)), (1 << (bits - 1)) - 1)
+    sym = np.where(v >= 0, 2 * v, -2 * v - 1).astype(np.uint8 if False else np.uint64)
     sym = np.concatenate([sym, np.zeros(v.shape[:-1] + (pad,), np.uint64)], axis=-1)
-    g = sym.reshape(v.shape[:-1] + (-1, 4))
-    word = g[..., 0] | g[..., 1] << np.uint64(10) | g[..., 2] << np.uint64(20) | g[..., 3] << np.uint64(30)
-    out = np.empty(word.shape + (5,), np.uint8)
-    for b in range(5):
-        out[..., b] = (word >> np.uint64(8 * b)) & np.uint64(0xff)
-    return out.reshape(v.shape[:-1] + (-1,))
+    # symbol i of a 64-symbol block occupies bits [bits * i, bits * i + bits) of the block's 8 * bits bytes
+    b = ((sym[..., None] >> np.arange(bits, dtype=np.uint64)) & np.uint64(1)).astype(np.uint8)  # [..., n_pad, bits], LSB first
+    b = b.reshape(v.shape[:-1] + (-1,))
+    return np.packbits(b, axis=-1, bitorder="little")
+
+
+def unpack_bits(packed: np.ndarray, n: int, bits: int = 10) -> np.ndarray:
+    """Inverse of pack_bits: uint8 [..., 8 * bits * ceil(n / 64)] -> int32 [..., n] (unpack_signed, utils.rs:42-48)."""
+    p = np.asarray(packed, dtype=np.uint8)
+    b = np.unpackbits(p, axis=-1, bitorder="little").reshape(p.shape[:-1] + (-1, bits)).astype(np.int64)
+    sym = (b << np.arange(bits, dtype=np.int64)).sum(axis=-1)[..., :n]
+    return np.where(sym % 2 == 0, sym // 2, -((sym + 1) // 2)).astype(np.int32)
+
+
+def pack10(values: np.ndarray) -> np.ndarray:
+    return pack_bits(values, 10)
 
 
 def unpack10(packed: np.ndarray, n: int) -> np.ndarray:
-    """Inverse of pack10: uint8 [..., 80 * ceil(n / 64)] -> int32 [..., n] (unpack_signed, utils.rs:42-48)."""
-    p = np.asarray(packed, dtype=np.uint8)
-    g = p.reshape(p.shape[:-1] + (-1, 5)).astype(np.uint64)
-    word = sum(g[..., b] << np.uint64(8 * b) for b in range(5))
-    sym = np.stack([(word >> np.uint64(10 * i)) & np.uint64(1023) for i in range(4)], axis=-1).reshape(p.shape[:-1] + (-1,))
-    sym = sym[..., :n].astype(np.int64)
-    return np.where(sym % 2 == 0, sym // 2, -((sym + 1) // 2)).astype(np.int32)
+    return unpack_bits(packed, n, 10)
 
 
 def _q_array(q):
@@ -342,6 +352,49 @@ class Plan:
         """Bytes of one channel's stream in the 10-bit packed transport (80 bytes per 64 symbols)."""
         self.emission_count()
         return int(lib().fri_plan_emission_packed_bytes(self._h))
+
+    def emission_packed_size(self, bits: int) -> int:
+        """Bytes of one channel's stream packed at `bits` (9 or 10) bits per symbol."""
+        self.emission_count()
+        n = int(lib().fri_plan_emission_packed_size(self._h, int(bits)))
+        if n == 0 and self.n_tiles:
+            raise FriError(FRI_E_INVALID, lib().fri_last_error().decode("utf-8", "replace"))
+        return n
+
+    def encode_emit_packed(self, pixels: np.ndarray, q=None, bits: int = 10, out: np.ndarray | None = None) -> np.ndarray:
+        """HWC pixels [F, H, W, C] -> uint8 [F, C, emission_packed_size(bits)] (fri_encode_tq_emit_packed)."""
+        px, n = self._frames(pixels)
+        nb = self.emission_packed_size(bits)
+        if out is None:
+            out = np.empty((n, self.channels, nb), np.uint8)
+        assert out.dtype == np.uint8 and out.flags.c_contiguous and out.shape == (n, self.channels, nb)
+        qa, qp = _q_array(q)
+        _check(lib().fri_encode_tq_emit_packed(self._h, px.ctypes.data, n, qp, int(bits), out.ctypes.data))
+        return out
+
+    def decode_emit_packed(self, packed: np.ndarray, q=None, bits: int = 10, multiply: bool = False,
+                           out: np.ndarray | None = None) -> np.ndarray:
+        """uint8 [F, C, emission_packed_size(bits)] -> HWC pixels [F, H, W, C] (fri_decode_tq_emit_packed)."""
+        pk = np.ascontiguousarray(packed, dtype=np.uint8)
+        nb = self.emission_packed_size(bits)
+        if pk.shape == (self.channels, nb):
+            pk = pk[None]
+        if pk.ndim != 3 or pk.shape[1:] != (self.channels, nb):
+            raise ValueError(f"packed streams must have shape [F, {self.channels}, {nb}]")
+        n = pk.shape[0]
+        if out is None:
+            out = np.empty((n,) + self.frame_shape, self.pixel_dtype)
+        assert out.dtype == self.pixel_dtype and out.flags.c_contiguous and out.shape == (n,) + self.frame_shape
+        qa, qp = _q_array(q)
+        mode = FRI_DEQUANT_MULTIPLY if multiply else FRI_DEQUANT_DIVIDE
+        _check(lib().fri_decode_tq_emit_packed(self._h, pk.ctypes.data, n, int(bits), qp, mode, out.ctypes.data))
+        return out
+
+    def emit_device_packed(self, d_coefs: int, n_frames: int, bits: int, d_out: int, stream: int = 0) -> None:
+        _check(lib().fri_emit_device_packed(self._h, d_coefs, n_frames, int(bits), d_out, stream))
+
+    def unemit_device_packed(self, d_packed: int, n_frames: int, bits: int, d_coefs: int, stream: int = 0) -> None:
+        _check(lib().fri_unemit_device_packed(self._h, d_packed, n_frames, int(bits), d_coefs, stream))
 
     def encode_emit10(self, pixels: np.ndarray, q=None, out: np.ndarray | None = None) -> np.ndarray:
         """HWC pixels [F, H, W, C] -> uint8 [F, C, emission_packed_bytes()]: emission-ordered streams in the

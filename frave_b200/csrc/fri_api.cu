@@ -781,13 +781,21 @@ int fri_plan_emission_order(fri_plan *p, uint32_t *order)
     return FRI_OK;
 }
 
-// Element type of an emission-ordered stream at the boundary.
-enum class StreamFmt { I32, I16, P10 };
+// Element type of an emission-ordered stream at the boundary: int32, int16, or zig-zag symbols packed at
+// `bits` (10 or 9) bits each.
+struct StreamFmt {
+    int elem_bytes;  // 4 or 2 (dense streams); 0 = packed
+    int bits;        // packed only
+    bool packed() const { return elem_bytes == 0; }
+    bool half() const { return elem_bytes != 4; }  // the device-side staging of this format is int16
+};
+static const StreamFmt kFmtI32{4, 0}, kFmtI16{2, 0};
+static StreamFmt fmt_packed(int bits) { return StreamFmt{0, bits}; }
 
 // Padded length of one channel's stream inside the device staging of the packed transport: a multiple of the
 // 64-symbol packing block.
 static size_t padded_count(size_t count) { return (count + kPackBlock - 1) / kPackBlock * kPackBlock; }
-static size_t packed_bytes(size_t count) { return padded_count(count) / kPackBlock * kPackBlockBytes; }
+static size_t packed_bytes(size_t count, int bits) { return padded_count(count) / kPackBlock * (size_t)pack_block_bytes(bits); }
 
 // Zeroes elements [count, stride) of every one of n_streams int16 streams of padded stride.
 static cudaError_t zero_stream_padding(int16_t *streams, size_t count, size_t stride, size_t n_streams, cudaStream_t st)
@@ -798,8 +806,10 @@ static cudaError_t zero_stream_padding(int16_t *streams, size_t count, size_t st
 
 static int check_stream_fmt(const fri_plan *p, StreamFmt fmt)
 {
-    if (fmt != StreamFmt::I32 && p->plan.geo.sample_bytes != 1)
-        return fail(FRI_E_UNSUPPORTED, "16-bit / 10-bit emission needs 8-bit samples (residues of 16-bit samples need 18 bits)");
+    if (fmt.packed() && fmt.bits != 9 && fmt.bits != 10)
+        return fail(FRI_E_INVALID, "packed streams carry 9 or 10 bits per symbol, not %d", fmt.bits);
+    if (fmt.half() && p->plan.geo.sample_bytes != 1)
+        return fail(FRI_E_UNSUPPORTED, "16-bit / packed emission needs 8-bit samples (residues of 16-bit samples need 18 bits)");
     return FRI_OK;
 }
 
@@ -807,17 +817,17 @@ static int emit_device(fri_plan *p, const int32_t *d_coefs, uint32_t n_frames, v
 {
     int rc = enter_device(p);
     if (rc) return rc;
+    if ((rc = check_stream_fmt(p, fmt))) return rc;
     if ((rc = ensure_emission_device(p))) return rc;
     if (n_frames == 0) return FRI_OK;
     if (!d_coefs || !d_out) return fail(FRI_E_INVALID, "NULL device buffer");
     if ((uintptr_t)d_coefs & 15) return fail(FRI_E_INVALID, "d_coefs must be 16-byte aligned");
-    if ((rc = check_stream_fmt(p, fmt))) return rc;
     const Geometry &g = p->plan.geo;
     const size_t count = p->emit_src.size();
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     uint32_t launches = 0;
     cudaError_t e;
-    if (fmt == StreamFmt::P10) {
+    if (fmt.packed()) {
         if ((uintptr_t)d_out & 15) return fail(FRI_E_INVALID, "packed streams must be 16-byte aligned");
         // gather into int16 streams of padded stride (stream-ordered scratch), then pack
         const size_t stride = padded_count(count), total = (size_t)n_frames * g.channels * stride;
@@ -825,10 +835,10 @@ static int emit_device(fri_plan *p, const int32_t *d_coefs, uint32_t n_frames, v
         if ((rc = pool_alloc(p, reinterpret_cast<void **>(&tmp), total * sizeof(int16_t), st))) return rc;
         e = zero_stream_padding(tmp, count, stride, (size_t)n_frames * g.channels, st);  // the padding packs as symbol 0
         if (e == cudaSuccess) e = launch_emit(g, p->tables, p->emit_tables, stride, d_coefs, n_frames, tmp, true, st, &launches);
-        if (e == cudaSuccess) e = launch_pack10(tmp, static_cast<uint8_t *>(d_out), total / kPackBlock, st, &launches);
+        if (e == cudaSuccess) e = launch_pack_bits(fmt.bits, tmp, static_cast<uint8_t *>(d_out), total / kPackBlock, st, &launches);
         cudaFreeAsync(tmp, st);
     } else {
-        e = launch_emit(g, p->tables, p->emit_tables, count, d_coefs, n_frames, d_out, fmt == StreamFmt::I16, st, &launches);
+        e = launch_emit(g, p->tables, p->emit_tables, count, d_coefs, n_frames, d_out, fmt.half(), st, &launches);
     }
     p->last_launches = launches;
     if (e != cudaSuccess) return cuda_fail(e, "emission gather");
@@ -837,27 +847,42 @@ static int emit_device(fri_plan *p, const int32_t *d_coefs, uint32_t n_frames, v
 
 int fri_emit_device(fri_plan *p, const int32_t *d_coefs, uint32_t n_frames, int32_t *d_out, void *stream)
 {
-    return emit_device(p, d_coefs, n_frames, d_out, StreamFmt::I32, stream);
+    return emit_device(p, d_coefs, n_frames, d_out, kFmtI32, stream);
 }
 
 int fri_emit_device16(fri_plan *p, const int32_t *d_coefs, uint32_t n_frames, int16_t *d_out, void *stream)
 {
-    return emit_device(p, d_coefs, n_frames, d_out, StreamFmt::I16, stream);
+    return emit_device(p, d_coefs, n_frames, d_out, kFmtI16, stream);
 }
 
 int fri_emit_device10(fri_plan *p, const int32_t *d_coefs, uint32_t n_frames, uint8_t *d_out, void *stream)
 {
-    return emit_device(p, d_coefs, n_frames, d_out, StreamFmt::P10, stream);
+    return emit_device(p, d_coefs, n_frames, d_out, fmt_packed(10), stream);
+}
+
+int fri_emit_device_packed(fri_plan *p, const int32_t *d_coefs, uint32_t n_frames, int bits, uint8_t *d_out, void *stream)
+{
+    return emit_device(p, d_coefs, n_frames, d_out, fmt_packed(bits), stream);
 }
 
 uint64_t fri_plan_emission_packed_bytes(fri_plan *p)
 {
     if (ensure_emission(p)) return 0;
-    return (uint64_t)packed_bytes(p->emit_src.size());
+    return (uint64_t)packed_bytes(p->emit_src.size(), 10);
+}
+
+uint64_t fri_plan_emission_packed_size(fri_plan *p, int bits)
+{
+    if (bits != 9 && bits != 10) {
+        fail(FRI_E_INVALID, "packed streams carry 9 or 10 bits per symbol, not %d", bits);
+        return 0;
+    }
+    if (ensure_emission(p)) return 0;
+    return (uint64_t)packed_bytes(p->emit_src.size(), bits);
 }
 
 // Device staging of the emission-ordered streams of one frame per slot: sized for int32 streams of padded
-// stride (the largest of the three formats), plus the packed image of the same streams.
+// stride (the largest of the formats), plus the packed image of the same streams.
 static int ensure_emit_slots(fri_plan *p)
 {
     int rc = ensure_slots(p);
@@ -866,9 +891,14 @@ static int ensure_emit_slots(fri_plan *p)
     const size_t count = p->emit_src.size();
     for (auto &s : p->slots) {
         if (!s.d_emit) FRI_CUDA(cudaMalloc(&s.d_emit, (size_t)g.channels * padded_count(count) * sizeof(int32_t) + 16));
-        if (!s.d_pack && g.sample_bytes == 1) FRI_CUDA(cudaMalloc(&s.d_pack, (size_t)g.channels * packed_bytes(count) + 16));
+        if (!s.d_pack && g.sample_bytes == 1) FRI_CUDA(cudaMalloc(&s.d_pack, (size_t)g.channels * packed_bytes(count, 10) + 16));
     }
     return FRI_OK;
+}
+
+static size_t stream_frame_bytes(const Geometry &g, size_t count, StreamFmt fmt)
+{
+    return fmt.packed() ? (size_t)g.channels * packed_bytes(count, fmt.bits) : (size_t)g.channels * count * (size_t)fmt.elem_bytes;
 }
 
 static int encode_emit_host(fri_plan *p, const void *pixels, uint32_t n_frames, const int32_t *q, void *out, StreamFmt fmt)
@@ -876,18 +906,16 @@ static int encode_emit_host(fri_plan *p, const void *pixels, uint32_t n_frames, 
     int rc = enter_device(p);
     if (rc) return rc;
     if ((rc = check_q(q))) return rc;
+    if ((rc = check_stream_fmt(p, fmt))) return rc;
     if ((rc = ensure_emission_device(p))) return rc;
     if (n_frames == 0) return FRI_OK;
     if (!pixels || !out) return fail(FRI_E_INVALID, "NULL host buffer");
-    if ((rc = check_stream_fmt(p, fmt))) return rc;
     if ((rc = check_pinned(p, pixels, "pixels")) || (rc = check_pinned(p, out, "streams"))) return rc;
     if ((rc = ensure_emit_slots(p))) return rc;
     const Geometry &g = p->plan.geo;
     const size_t count = p->emit_src.size();
-    const bool packed = fmt == StreamFmt::P10;
-    const size_t stride = packed ? padded_count(count) : count;  // elements between two streams on the device
-    const size_t per_frame = packed ? (size_t)g.channels * packed_bytes(count)
-                                    : (size_t)g.channels * count * (fmt == StreamFmt::I16 ? sizeof(int16_t) : sizeof(int32_t));
+    const size_t stride = fmt.packed() ? padded_count(count) : count;  // elements between two streams on the device
+    const size_t per_frame = stream_frame_bytes(g, count, fmt);
     QuantParams qp;
     make_quant_params(qp, q, 0);
     p->last_launches = 0;
@@ -900,17 +928,17 @@ static int encode_emit_host(fri_plan *p, const void *pixels, uint32_t n_frames, 
         FRI_CUDA(cudaEventRecord(pl.in_ready[0], pl.in));
         FRI_CUDA(cudaStreamWaitEvent(pl.compute, pl.in_ready[0], 0));
         FRI_CUDA(launch_encode(g, p->tables, qp, s.d_pixels, 1, s.d_coefs, false, s.d_dc, pl.compute, &p->last_launches));
-        if (packed)  // the padding of every stream packs as symbol 0
+        if (fmt.packed())  // the padding of every stream packs as symbol 0
             FRI_CUDA(zero_stream_padding(static_cast<int16_t *>(s.d_emit), count, stride, (size_t)g.channels, pl.compute));
-        FRI_CUDA(launch_emit(g, p->tables, p->emit_tables, stride, s.d_coefs, 1, s.d_emit, fmt != StreamFmt::I32, pl.compute,
+        FRI_CUDA(launch_emit(g, p->tables, p->emit_tables, stride, s.d_coefs, 1, s.d_emit, fmt.half(), pl.compute,
                              &p->last_launches));
-        if (packed)
-            FRI_CUDA(launch_pack10(static_cast<const int16_t *>(s.d_emit), static_cast<uint8_t *>(s.d_pack),
-                                   (size_t)g.channels * stride / kPackBlock, pl.compute, &p->last_launches));
+        if (fmt.packed())
+            FRI_CUDA(launch_pack_bits(fmt.bits, static_cast<const int16_t *>(s.d_emit), static_cast<uint8_t *>(s.d_pack),
+                                      (size_t)g.channels * stride / kPackBlock, pl.compute, &p->last_launches));
         FRI_CUDA(cudaEventRecord(pl.band_done[0], pl.compute));
         FRI_CUDA(cudaEventRecord(s.compute_done, pl.compute));
         FRI_CUDA(cudaStreamWaitEvent(pl.out, pl.band_done[0], 0));
-        FRI_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(out) + (size_t)f * per_frame, packed ? s.d_pack : s.d_emit, per_frame,
+        FRI_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(out) + (size_t)f * per_frame, fmt.packed() ? s.d_pack : s.d_emit, per_frame,
                                  cudaMemcpyDeviceToHost, pl.out));
         FRI_CUDA(cudaEventRecord(s.out_done, pl.out));
         s.used = true;
@@ -920,43 +948,48 @@ static int encode_emit_host(fri_plan *p, const void *pixels, uint32_t n_frames, 
 
 int fri_encode_tq_emit(fri_plan *p, const void *pixels, uint32_t n_frames, const int32_t *q, int32_t *out)
 {
-    return encode_emit_host(p, pixels, n_frames, q, out, StreamFmt::I32);
+    return encode_emit_host(p, pixels, n_frames, q, out, kFmtI32);
 }
 
 int fri_encode_tq_emit16(fri_plan *p, const void *pixels, uint32_t n_frames, const int32_t *q, int16_t *out)
 {
-    return encode_emit_host(p, pixels, n_frames, q, out, StreamFmt::I16);
+    return encode_emit_host(p, pixels, n_frames, q, out, kFmtI16);
 }
 
 int fri_encode_tq_emit10(fri_plan *p, const void *pixels, uint32_t n_frames, const int32_t *q, uint8_t *out)
 {
-    return encode_emit_host(p, pixels, n_frames, q, out, StreamFmt::P10);
+    return encode_emit_host(p, pixels, n_frames, q, out, fmt_packed(10));
+}
+
+int fri_encode_tq_emit_packed(fri_plan *p, const void *pixels, uint32_t n_frames, const int32_t *q, int bits, uint8_t *out)
+{
+    return encode_emit_host(p, pixels, n_frames, q, out, fmt_packed(bits));
 }
 
 static int unemit_device(fri_plan *p, const void *d_streams, StreamFmt fmt, uint32_t n_frames, int32_t *d_coefs, void *stream)
 {
     int rc = enter_device(p);
     if (rc) return rc;
+    if ((rc = check_stream_fmt(p, fmt))) return rc;
     if ((rc = ensure_emission_device(p))) return rc;
     if (n_frames == 0) return FRI_OK;
     if (!d_coefs || !d_streams) return fail(FRI_E_INVALID, "NULL device buffer");
     if ((uintptr_t)d_coefs & 15) return fail(FRI_E_INVALID, "d_coefs must be 16-byte aligned");
-    if ((rc = check_stream_fmt(p, fmt))) return rc;
     const Geometry &g = p->plan.geo;
     const size_t count = p->emit_src.size();
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     uint32_t launches = 0;
     cudaError_t e;
-    if (fmt == StreamFmt::P10) {
+    if (fmt.packed()) {
         if ((uintptr_t)d_streams & 15) return fail(FRI_E_INVALID, "packed streams must be 16-byte aligned");
         const size_t stride = padded_count(count), total = (size_t)n_frames * g.channels * stride;
         int16_t *tmp = nullptr;
         if ((rc = pool_alloc(p, reinterpret_cast<void **>(&tmp), total * sizeof(int16_t), st))) return rc;
-        e = launch_unpack10(static_cast<const uint8_t *>(d_streams), tmp, total / kPackBlock, st, &launches);
+        e = launch_unpack_bits(fmt.bits, static_cast<const uint8_t *>(d_streams), tmp, total / kPackBlock, st, &launches);
         if (e == cudaSuccess) e = launch_unemit(g, p->tables, p->emit_tables, stride, tmp, true, n_frames, d_coefs, st, &launches);
         cudaFreeAsync(tmp, st);
     } else {
-        e = launch_unemit(g, p->tables, p->emit_tables, count, d_streams, fmt == StreamFmt::I16, n_frames, d_coefs, st, &launches);
+        e = launch_unemit(g, p->tables, p->emit_tables, count, d_streams, fmt.half(), n_frames, d_coefs, st, &launches);
     }
     p->last_launches = launches;
     if (e != cudaSuccess) return cuda_fail(e, "emission un-gather");
@@ -965,17 +998,22 @@ static int unemit_device(fri_plan *p, const void *d_streams, StreamFmt fmt, uint
 
 int fri_unemit_device(fri_plan *p, const int32_t *d_streams, uint32_t n_frames, int32_t *d_coefs, void *stream)
 {
-    return unemit_device(p, d_streams, StreamFmt::I32, n_frames, d_coefs, stream);
+    return unemit_device(p, d_streams, kFmtI32, n_frames, d_coefs, stream);
 }
 
 int fri_unemit_device16(fri_plan *p, const int16_t *d_streams, uint32_t n_frames, int32_t *d_coefs, void *stream)
 {
-    return unemit_device(p, d_streams, StreamFmt::I16, n_frames, d_coefs, stream);
+    return unemit_device(p, d_streams, kFmtI16, n_frames, d_coefs, stream);
 }
 
 int fri_unemit_device10(fri_plan *p, const uint8_t *d_streams, uint32_t n_frames, int32_t *d_coefs, void *stream)
 {
-    return unemit_device(p, d_streams, StreamFmt::P10, n_frames, d_coefs, stream);
+    return unemit_device(p, d_streams, fmt_packed(10), n_frames, d_coefs, stream);
+}
+
+int fri_unemit_device_packed(fri_plan *p, const uint8_t *d_streams, uint32_t n_frames, int bits, int32_t *d_coefs, void *stream)
+{
+    return unemit_device(p, d_streams, fmt_packed(bits), n_frames, d_coefs, stream);
 }
 
 static int decode_emit_host(fri_plan *p, const void *streams, StreamFmt fmt, uint32_t n_frames, const int32_t *q, int dequant_mode,
@@ -986,18 +1024,16 @@ static int decode_emit_host(fri_plan *p, const void *streams, StreamFmt fmt, uin
     if ((rc = check_q(q))) return rc;
     if (dequant_mode != FRI_DEQUANT_DIVIDE && dequant_mode != FRI_DEQUANT_MULTIPLY)
         return fail(FRI_E_INVALID, "dequant_mode must be FRI_DEQUANT_DIVIDE or FRI_DEQUANT_MULTIPLY");
+    if ((rc = check_stream_fmt(p, fmt))) return rc;
     if ((rc = ensure_emission_device(p))) return rc;
     if (n_frames == 0) return FRI_OK;
     if (!pixels || !streams) return fail(FRI_E_INVALID, "NULL host buffer");
-    if ((rc = check_stream_fmt(p, fmt))) return rc;
     if ((rc = check_pinned(p, pixels, "pixels")) || (rc = check_pinned(p, streams, "streams"))) return rc;
     if ((rc = ensure_emit_slots(p))) return rc;
     const Geometry &g = p->plan.geo;
     const size_t count = p->emit_src.size();
-    const bool packed = fmt == StreamFmt::P10;
-    const size_t stride = packed ? padded_count(count) : count;
-    const size_t per_frame = packed ? (size_t)g.channels * packed_bytes(count)
-                                    : (size_t)g.channels * count * (fmt == StreamFmt::I16 ? sizeof(int16_t) : sizeof(int32_t));
+    const size_t stride = fmt.packed() ? padded_count(count) : count;
+    const size_t per_frame = stream_frame_bytes(g, count, fmt);
     QuantParams qp;
     make_quant_params(qp, q, dequant_mode == FRI_DEQUANT_MULTIPLY);
     p->last_launches = 0;
@@ -1006,15 +1042,15 @@ static int decode_emit_host(fri_plan *p, const void *streams, StreamFmt fmt, uin
     for (uint32_t f = 0; f < n_frames; ++f) {
         Slot &s = p->slots[f % kSlots];
         if ((rc = acquire_slot(p, s))) return rc;
-        FRI_CUDA(cudaMemcpyAsync(packed ? s.d_pack : s.d_emit, static_cast<const uint8_t *>(streams) + (size_t)f * per_frame, per_frame,
-                                 cudaMemcpyHostToDevice, pl.in));
+        FRI_CUDA(cudaMemcpyAsync(fmt.packed() ? s.d_pack : s.d_emit, static_cast<const uint8_t *>(streams) + (size_t)f * per_frame,
+                                 per_frame, cudaMemcpyHostToDevice, pl.in));
         FRI_CUDA(cudaEventRecord(pl.in_ready[0], pl.in));
         FRI_CUDA(cudaStreamWaitEvent(pl.compute, pl.in_ready[0], 0));
         if (need_zero) FRI_CUDA(cudaMemsetAsync(s.d_pixels, 0, (size_t)g.frame_bytes, pl.compute));
-        if (packed)
-            FRI_CUDA(launch_unpack10(static_cast<const uint8_t *>(s.d_pack), static_cast<int16_t *>(s.d_emit),
-                                     (size_t)g.channels * stride / kPackBlock, pl.compute, &p->last_launches));
-        FRI_CUDA(launch_unemit(g, p->tables, p->emit_tables, stride, s.d_emit, fmt != StreamFmt::I32, 1, s.d_coefs, pl.compute,
+        if (fmt.packed())
+            FRI_CUDA(launch_unpack_bits(fmt.bits, static_cast<const uint8_t *>(s.d_pack), static_cast<int16_t *>(s.d_emit),
+                                        (size_t)g.channels * stride / kPackBlock, pl.compute, &p->last_launches));
+        FRI_CUDA(launch_unemit(g, p->tables, p->emit_tables, stride, s.d_emit, fmt.half(), 1, s.d_coefs, pl.compute,
                                &p->last_launches));
         FRI_CUDA(launch_decode(g, p->tables, qp, s.d_coefs, false, 1, s.d_pixels, s.d_dc, pl.compute, &p->last_launches));
         FRI_CUDA(cudaEventRecord(pl.band_done[0], pl.compute));
@@ -1030,17 +1066,23 @@ static int decode_emit_host(fri_plan *p, const void *streams, StreamFmt fmt, uin
 
 int fri_decode_tq_emit(fri_plan *p, const int32_t *streams, uint32_t n_frames, const int32_t *q, int dequant_mode, void *pixels)
 {
-    return decode_emit_host(p, streams, StreamFmt::I32, n_frames, q, dequant_mode, pixels);
+    return decode_emit_host(p, streams, kFmtI32, n_frames, q, dequant_mode, pixels);
 }
 
 int fri_decode_tq_emit16(fri_plan *p, const int16_t *streams, uint32_t n_frames, const int32_t *q, int dequant_mode, void *pixels)
 {
-    return decode_emit_host(p, streams, StreamFmt::I16, n_frames, q, dequant_mode, pixels);
+    return decode_emit_host(p, streams, kFmtI16, n_frames, q, dequant_mode, pixels);
 }
 
 int fri_decode_tq_emit10(fri_plan *p, const uint8_t *streams, uint32_t n_frames, const int32_t *q, int dequant_mode, void *pixels)
 {
-    return decode_emit_host(p, streams, StreamFmt::P10, n_frames, q, dequant_mode, pixels);
+    return decode_emit_host(p, streams, fmt_packed(10), n_frames, q, dequant_mode, pixels);
+}
+
+int fri_decode_tq_emit_packed(fri_plan *p, const uint8_t *streams, uint32_t n_frames, int bits, const int32_t *q, int dequant_mode,
+                              void *pixels)
+{
+    return decode_emit_host(p, streams, fmt_packed(bits), n_frames, q, dequant_mode, pixels);
 }
 
 /* ---- prediction + context bucketing, encode side ------------------------ */

@@ -1473,61 +1473,64 @@ fri_unpack16_kernel(const int4 *__restrict__ src, int4 *__restrict__ dst, size_t
 // coefficient travels as the symbol the reference's entropy coder would see, pack_signed(k) = 2k for
 // k >= 0, -2k - 1 for k < 0 (utils.rs:34-40), in the 1024-symbol alphabet (entropy_coding.rs:25) — every
 // coefficient of an 8-bit image fits (|k| <= 255) and so does every value a decodable container can hold.
-// Four symbols -> 40 bits -> 5 bytes, little-endian (symbol i of a group in bits [10 i, 10 i + 10)):
+// Four symbols -> 40 bits -> 5 bytes, little-endian (symbol i of a block in bits [10 i, 10 i + 10)):
 // 1.25 bytes per coefficient over PCIe instead of 2.  One thread packs 64 symbols (128 B in, 80 B out);
 // streams are padded to a multiple of 64 symbols on both sides.  Encode saturates at +-511 / -512.
+// A 9-bit form of the same layout (72 B per 64 symbols, saturating at -256 / +255) carries everything the
+// transform of an 8-bit image can produce (|k| <= 255) in 1.125 bytes per coefficient.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t zigzag10(int v)
+template <int BITS>
+__device__ __forceinline__ uint32_t zigzag_sat(int v)
 {
-    v = max(-512, min(511, v));
+    v = max(-(1 << (BITS - 1)), min((1 << (BITS - 1)) - 1, v));
     return (uint32_t)((v << 1) ^ (v >> 31));  // 2v for v >= 0, -2v - 1 for v < 0
 }
-__device__ __forceinline__ int unzigzag10(uint32_t s) { return (int)(s >> 1) ^ -(int)(s & 1u); }  // utils.rs:42-48
+__device__ __forceinline__ int unzigzag(uint32_t s) { return (int)(s >> 1) ^ -(int)(s & 1u); }  // utils.rs:42-48
 
+// One thread packs 64 symbols of BITS bits (128 B in) into 8 * BITS bytes (symbol i of a block in bits
+// [BITS i, BITS i + BITS), little-endian); all shifts are compile-time after unrolling.
+template <int BITS>
 __global__ void __launch_bounds__(256)
-fri_pack10_kernel(const int4 *__restrict__ src, int4 *__restrict__ dst, size_t n_blocks)
+fri_pack_kernel(const int4 *__restrict__ src, int2 *__restrict__ dst, size_t n_blocks)
 {
     for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_blocks; b += (size_t)gridDim.x * blockDim.x) {
-        uint32_t w[20];  // 16 groups of 40 bits
+        uint32_t w[2 * BITS];
+        uint64_t acc = 0;
+        int nb = 0, wi = 0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {  // 8 symbols = 2 groups = 80 bits per 16-byte load
+        for (int j = 0; j < 8; ++j) {
             const int4 v = __ldcs(src + 8 * b + j);
             const int x[4] = {v.x, v.y, v.z, v.w};
-            uint64_t g[2];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const uint32_t s0 = zigzag10((int)(short)x[2 * h]), s1 = zigzag10(x[2 * h] >> 16);
-                const uint32_t s2 = zigzag10((int)(short)x[2 * h + 1]), s3 = zigzag10(x[2 * h + 1] >> 16);
-                g[h] = (uint64_t)s0 | (uint64_t)s1 << 10 | (uint64_t)s2 << 20 | (uint64_t)s3 << 30;
-            }
-            // 80 bits at bit offset 80 j of the 640-bit output block
-            const int bit = 80 * j, wi = bit >> 5, sh = bit & 31;  // sh is 0 or 16
-            const uint32_t lo0 = (uint32_t)g[0], hi0 = (uint32_t)(g[0] >> 32);  // 40 bits: lo0, hi0[7:0]
-            const uint64_t g1 = g[1];
-            // 80-bit value V = g0 | g1 << 40
-            const uint32_t v0 = lo0, v1 = hi0 | (uint32_t)(g1 << 8), v2 = (uint32_t)(g1 >> 24);  // v2: 16 bits
-            if (sh == 0) {
-                w[wi] = v0; w[wi + 1] = v1; w[wi + 2] = v2;             // low 16 bits of w[wi + 2]
-            } else {
-                w[wi] |= v0 << 16; w[wi + 1] = v0 >> 16 | v1 << 16; w[wi + 2] = v1 >> 16 | v2 << 16;
+            for (int t = 0; t < 8; ++t) {
+                const int e = (t & 1) ? (x[t >> 1] >> 16) : (int)(short)x[t >> 1];
+                acc |= (uint64_t)zigzag_sat<BITS>(e) << nb;
+                nb += BITS;
+                if (nb >= 32) {
+                    w[wi++] = (uint32_t)acc;
+                    acc >>= 32;
+                    nb -= 32;
+                }
             }
         }
 #pragma unroll
-        for (int k = 0; k < 5; ++k) __stcs(dst + 5 * b + k, make_int4((int)w[4 * k], (int)w[4 * k + 1], (int)w[4 * k + 2], (int)w[4 * k + 3]));
+        for (int k = 0; k < BITS; ++k) __stcs(dst + (size_t)BITS * b + k, make_int2((int)w[2 * k], (int)w[2 * k + 1]));
     }
 }
 
+template <int BITS>
 __global__ void __launch_bounds__(256)
-fri_unpack10_kernel(const int4 *__restrict__ src, int4 *__restrict__ dst, size_t n_blocks)
+fri_unpack_kernel(const int2 *__restrict__ src, int4 *__restrict__ dst, size_t n_blocks)
 {
     for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_blocks; b += (size_t)gridDim.x * blockDim.x) {
-        uint32_t w[21];
+        uint32_t w[2 * BITS + 1];
 #pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            const int4 v = __ldcs(src + 5 * b + k);
-            w[4 * k] = (uint32_t)v.x; w[4 * k + 1] = (uint32_t)v.y; w[4 * k + 2] = (uint32_t)v.z; w[4 * k + 3] = (uint32_t)v.w;
+        for (int k = 0; k < BITS; ++k) {
+            const int2 v = __ldcs(src + (size_t)BITS * b + k);
+            w[2 * k] = (uint32_t)v.x;
+            w[2 * k + 1] = (uint32_t)v.y;
         }
-        w[20] = 0;
+        w[2 * BITS] = 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             int out[4];
@@ -1536,9 +1539,9 @@ fri_unpack10_kernel(const int4 *__restrict__ src, int4 *__restrict__ dst, size_t
                 int v[2];
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
-                    const int bit = 10 * (8 * j + 2 * h + t), wi = bit >> 5, sh = bit & 31;
-                    const uint32_t sym = (uint32_t)(((uint64_t)w[wi] | (uint64_t)w[wi + 1] << 32) >> sh) & 1023u;
-                    v[t] = unzigzag10(sym);
+                    const int bit = BITS * (8 * j + 2 * h + t), wi = bit >> 5, sh = bit & 31;
+                    const uint32_t sym = (uint32_t)(((uint64_t)w[wi] | (uint64_t)w[wi + 1] << 32) >> sh) & ((1u << BITS) - 1u);
+                    v[t] = unzigzag(sym);
                 }
                 out[h] = (v[0] & 0xffff) | (v[1] << 16);
             }
@@ -1788,20 +1791,30 @@ cudaError_t launch_unemit(const Geometry &g, const DeviceTables &t, const EmitTa
     return cudaGetLastError();
 }
 
-cudaError_t launch_pack10(const int16_t *d_src, uint8_t *d_dst, size_t n_blocks, cudaStream_t stream, uint32_t *launches)
+cudaError_t launch_pack_bits(int bits, const int16_t *d_src, uint8_t *d_dst, size_t n_blocks, cudaStream_t stream, uint32_t *launches)
 {
     if (n_blocks == 0) return cudaSuccess;
     const unsigned blocks = (unsigned)std::min<size_t>((n_blocks + 255) / 256, (size_t)148 * 16);
-    fri_pack10_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const int4 *>(d_src), reinterpret_cast<int4 *>(d_dst), n_blocks);
+    if (bits == 10)
+        fri_pack_kernel<10><<<blocks, 256, 0, stream>>>(reinterpret_cast<const int4 *>(d_src), reinterpret_cast<int2 *>(d_dst), n_blocks);
+    else if (bits == 9)
+        fri_pack_kernel<9><<<blocks, 256, 0, stream>>>(reinterpret_cast<const int4 *>(d_src), reinterpret_cast<int2 *>(d_dst), n_blocks);
+    else
+        return cudaErrorInvalidValue;
     if (launches) ++*launches;
     return cudaGetLastError();
 }
 
-cudaError_t launch_unpack10(const uint8_t *d_src, int16_t *d_dst, size_t n_blocks, cudaStream_t stream, uint32_t *launches)
+cudaError_t launch_unpack_bits(int bits, const uint8_t *d_src, int16_t *d_dst, size_t n_blocks, cudaStream_t stream, uint32_t *launches)
 {
     if (n_blocks == 0) return cudaSuccess;
     const unsigned blocks = (unsigned)std::min<size_t>((n_blocks + 255) / 256, (size_t)148 * 16);
-    fri_unpack10_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const int4 *>(d_src), reinterpret_cast<int4 *>(d_dst), n_blocks);
+    if (bits == 10)
+        fri_unpack_kernel<10><<<blocks, 256, 0, stream>>>(reinterpret_cast<const int2 *>(d_src), reinterpret_cast<int4 *>(d_dst), n_blocks);
+    else if (bits == 9)
+        fri_unpack_kernel<9><<<blocks, 256, 0, stream>>>(reinterpret_cast<const int2 *>(d_src), reinterpret_cast<int4 *>(d_dst), n_blocks);
+    else
+        return cudaErrorInvalidValue;
     if (launches) ++*launches;
     return cudaGetLastError();
 }

@@ -164,12 +164,12 @@ cudaError_t launch_predict(const Geometry &g, const DeviceTables &t, const EmitT
                            uint8_t *d_bucket, int32_t *d_pred, uint16_t *d_sym, uint32_t *d_hist, uint32_t *d_overflow,
                            cudaStream_t stream, uint32_t *launches);
 
-// 10-bit packed transport of emission-ordered streams: int16 streams (stride a multiple of 64 elements, 16-byte
-// aligned) <-> blocks of 64 zig-zag symbols in 80 bytes; n_blocks = total elements / 64.
-constexpr int kPackBlock = 64;       // symbols per packed block
-constexpr int kPackBlockBytes = 80;  // 64 x 10 bits
-cudaError_t launch_pack10(const int16_t *d_src, uint8_t *d_dst, size_t n_blocks, cudaStream_t stream, uint32_t *launches);
-cudaError_t launch_unpack10(const uint8_t *d_src, int16_t *d_dst, size_t n_blocks, cudaStream_t stream, uint32_t *launches);
+// Packed transport of emission-ordered streams (bits = 10 or 9): int16 streams (stride a multiple of 64
+// elements, 16-byte aligned) <-> blocks of 64 zig-zag symbols in 8 * bits bytes; n_blocks = total elements / 64.
+constexpr int kPackBlock = 64;  // symbols per packed block
+constexpr int pack_block_bytes(int bits) { return 8 * bits; }
+cudaError_t launch_pack_bits(int bits, const int16_t *d_src, uint8_t *d_dst, size_t n_blocks, cudaStream_t stream, uint32_t *launches);
+cudaError_t launch_unpack_bits(int bits, const uint8_t *d_src, int16_t *d_dst, size_t n_blocks, cudaStream_t stream, uint32_t *launches);
 
 // 16-bit transport of the host-buffer entry points: saturating i32 -> i16 repack and its inverse
 // (count is a multiple of 8; both pointers 16-byte aligned).

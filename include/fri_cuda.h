@@ -182,8 +182,23 @@ int fri_decode_tq16(fri_plan *plan, const int16_t *coefs, uint32_t n_frames, con
  *                            instead of 2; encode saturates at -512 / +511 (cannot happen for an
  *                            8-bit image: |k| <= 255).
  */
+/*
+ *   fri_*_packed             the same layout at `bits` = 10 or 9 bits per symbol (8 * bits bytes per 64
+ *                            symbols; fri_plan_emission_packed_size(plan, bits) bytes per channel).  9 bits
+ *                            carry everything the transform of an 8-bit image produces (|k| <= 255, symbols
+ *                            < 512) in 1.125 bytes per coefficient, saturating at -256 / +255; use 10 where
+ *                            the streams may hold anything a container can (1024-symbol alphabet).
+ *                            FRI_E_INVALID for any other width.
+ */
 uint64_t fri_plan_emission_count(fri_plan *plan);
 uint64_t fri_plan_emission_packed_bytes(fri_plan *plan);
+uint64_t fri_plan_emission_packed_size(fri_plan *plan, int bits);
+int fri_emit_device_packed(fri_plan *plan, const int32_t *d_coefs, uint32_t n_frames, int bits, uint8_t *d_out, void *stream);
+int fri_encode_tq_emit_packed(fri_plan *plan, const void *pixels, uint32_t n_frames, const int32_t *q, int bits, uint8_t *out);
+int fri_unemit_device_packed(fri_plan *plan, const uint8_t *d_streams, uint32_t n_frames, int bits, int32_t *d_coefs,
+                             void *stream);
+int fri_decode_tq_emit_packed(fri_plan *plan, const uint8_t *streams, uint32_t n_frames, int bits, const int32_t *q,
+                              int dequant_mode, void *pixels);
 int fri_emit_device10(fri_plan *plan, const int32_t *d_coefs, uint32_t n_frames, uint8_t *d_out, void *stream);
 int fri_encode_tq_emit10(fri_plan *plan, const void *pixels, uint32_t n_frames, const int32_t *q, uint8_t *out);
 int fri_unemit_device10(fri_plan *plan, const uint8_t *d_streams, uint32_t n_frames, int32_t *d_coefs, void *stream);

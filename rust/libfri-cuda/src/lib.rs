@@ -46,6 +46,11 @@ extern "C" {
     fn fri_decode_tq16(plan: *mut FriPlan, coefs: *const i16, n_frames: u32, q: *const i32, dequant_mode: c_int, pixels: *mut c_void) -> c_int;
     fn fri_plan_emission_count(plan: *mut FriPlan) -> u64;
     fn fri_plan_emission_packed_bytes(plan: *mut FriPlan) -> u64;
+    fn fri_plan_emission_packed_size(plan: *mut FriPlan, bits: c_int) -> u64;
+    fn fri_emit_device_packed(plan: *mut FriPlan, d_coefs: *const i32, n_frames: u32, bits: c_int, d_out: *mut u8, stream: *mut c_void) -> c_int;
+    fn fri_encode_tq_emit_packed(plan: *mut FriPlan, pixels: *const c_void, n_frames: u32, q: *const i32, bits: c_int, out: *mut u8) -> c_int;
+    fn fri_unemit_device_packed(plan: *mut FriPlan, d_streams: *const u8, n_frames: u32, bits: c_int, d_coefs: *mut i32, stream: *mut c_void) -> c_int;
+    fn fri_decode_tq_emit_packed(plan: *mut FriPlan, streams: *const u8, n_frames: u32, bits: c_int, q: *const i32, dequant_mode: c_int, pixels: *mut c_void) -> c_int;
     fn fri_plan_emission_order(plan: *mut FriPlan, order: *mut u32) -> c_int;
     fn fri_emit_device(plan: *mut FriPlan, d_coefs: *const i32, n_frames: u32, d_out: *mut i32, stream: *mut c_void) -> c_int;
     fn fri_emit_device16(plan: *mut FriPlan, d_coefs: *const i32, n_frames: u32, d_out: *mut i16, stream: *mut c_void) -> c_int;
@@ -245,6 +250,30 @@ impl Plan {
         let n = self.channels * self.emission_packed_bytes();
         want_len("packed streams", out.len(), n)?;
         check(unsafe { fri_encode_tq_emit10(self.raw, pixels.as_ptr() as *const c_void, 1, q.as_ptr(), out.as_mut_ptr()) })
+    }
+    /// The packed streams at `bits` = 9 or 10 bits per symbol: [C][emission_packed_size(bits)] bytes.
+    pub fn emission_packed_size(&mut self, bits: i32) -> usize { unsafe { fri_plan_emission_packed_size(self.raw, bits) as usize } }
+    pub fn encode_tq_emit_packed(&mut self, pixels: &[u8], q: &[i32; 32], bits: i32, out: &mut [u8]) -> Result<(), String> {
+        want_len("pixels", pixels.len(), self.frame_bytes)?;
+        let n = self.channels * self.emission_packed_size(bits);
+        want_len("packed streams", out.len(), n)?;
+        check(unsafe { fri_encode_tq_emit_packed(self.raw, pixels.as_ptr() as *const c_void, 1, q.as_ptr(), bits, out.as_mut_ptr()) })
+    }
+    pub fn decode_tq_emit_packed(&mut self, packed: &[u8], bits: i32, q: &[i32; 32], pixels: &mut [u8]) -> Result<(), String> {
+        let n = self.channels * self.emission_packed_size(bits);
+        want_len("packed streams", packed.len(), n)?;
+        want_len("pixels", pixels.len(), self.frame_bytes)?;
+        check(unsafe { fri_decode_tq_emit_packed(self.raw, packed.as_ptr(), 1, bits, q.as_ptr(), FRI_DEQUANT_DIVIDE, pixels.as_mut_ptr() as *mut c_void) })
+    }
+    /// # Safety
+    /// Device pointers; packed output [n_frames][C][emission_packed_size(bits)], 16-byte aligned.
+    pub unsafe fn emit_device_packed(&mut self, d_coefs: *const i32, n_frames: u32, bits: i32, d_out: *mut u8, stream: *mut c_void) -> Result<(), String> {
+        check(fri_emit_device_packed(self.raw, d_coefs, n_frames, bits, d_out, stream))
+    }
+    /// # Safety
+    /// Device pointers; see `emit_device_packed`.
+    pub unsafe fn unemit_device_packed(&mut self, d_streams: *const u8, n_frames: u32, bits: i32, d_coefs: *mut i32, stream: *mut c_void) -> Result<(), String> {
+        check(fri_unemit_device_packed(self.raw, d_streams, n_frames, bits, d_coefs, stream))
     }
     pub fn decode_tq_emit(&mut self, streams: &[i32], q: &[i32; 32], pixels: &mut [u8]) -> Result<(), String> {
         let n = self.channels * self.emission_count();

@@ -375,3 +375,35 @@ def test_independent_calls_hint_overlaps_kernels_without_changing_results():
         plan.decode_device(d_co[1].data_ptr(), 1, d_out[1].data_ptr(), None)
         torch.cuda.synchronize()
         assert np.array_equal(d_out[1].cpu().numpy(), imgs[0])
+
+
+@pytest.mark.parametrize("bits", [9, 10])
+@pytest.mark.parametrize("shape", [(131, 77, 3), (512, 512, 1), (1080, 1920, 3)], ids=lambda s: "x".join(map(str, s)))
+def test_packed_transport_at_9_and_10_bits(shape, bits):
+    """fri_*_packed: the packed layout at 9 bits (everything an 8-bit image produces: |k| <= 255) and 10 bits."""
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda", 0)
+    h, w, c = shape
+    frames = np.stack([uniform_image(h, w, c, seed=700 + i) for i in range(2)])
+    q = smallest_layer_q(2)
+    with capi.Plan(w, h, c) as plan:
+        cnt, nb = plan.emission_count(), plan.emission_packed_size(bits)
+        assert nb == 8 * bits * ((cnt + 63) // 64)
+        streams = plan.encode_emit(frames, None)  # q == 1: residues span the whole +-255 range
+        assert np.abs(streams).max() <= 255
+        packed = plan.encode_emit_packed(frames, None, bits)
+        assert np.array_equal(packed, capi.pack_bits(streams, bits))
+        assert np.array_equal(capi.unpack_bits(packed, cnt, bits), streams)  # nothing saturates
+        assert np.array_equal(plan.decode_emit_packed(packed, None, bits), frames if plan.pixels_covered == w * h else plan.decode_emit(streams))
+        sq = plan.encode_emit(frames, q)
+        assert np.array_equal(plan.decode_emit_packed(plan.encode_emit_packed(frames, q, bits), q, bits), plan.decode_emit(sq, q))
+        d_coefs = torch.from_numpy(plan.encode(frames)).to(dev)
+        d_p = torch.zeros((2, c, nb), dtype=torch.uint8, device=dev)
+        plan.emit_device_packed(d_coefs.data_ptr(), 2, bits, d_p.data_ptr())
+        back = torch.full_like(d_coefs, 3)
+        plan.unemit_device_packed(d_p.data_ptr(), 2, bits, back.data_ptr())
+        torch.cuda.synchronize()
+        assert np.array_equal(d_p.cpu().numpy(), packed) and torch.equal(back, d_coefs)
+        with pytest.raises(capi.FriError) as ei:
+            plan.encode_emit_packed(frames, None, 8)
+        assert ei.value.code == capi.FRI_E_INVALID
