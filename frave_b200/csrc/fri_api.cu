@@ -77,7 +77,7 @@ struct fri_plan {
     int device = -1;
     DeviceTables tables;
     void *d_groups_launch = nullptr;
-    void *d_groups = nullptr, *d_tile_unit = nullptr, *d_chunk_mask = nullptr, *d_chunk_list = nullptr, *d_stage_list = nullptr, *d_edge_list = nullptr;
+    void *d_groups = nullptr, *d_tile_unit = nullptr, *d_chunk_mask = nullptr, *d_chunk_list = nullptr, *d_stage_list = nullptr, *d_edge_list = nullptr, *d_absent_unit = nullptr;
     Slot slots[kSlots];
     Pipeline pipe;
     bool slots_ready = false;
@@ -356,6 +356,8 @@ int fri_plan_create(fri_plan **out, int device, uint32_t width, uint32_t height,
         }
         if (e == cudaSuccess && pl.geo.sub_bits > 0)
             e = upload(&p->d_tile_unit, pl.tile_unit.data(), pl.tile_unit.size() * sizeof(uint32_t));
+        if (e == cudaSuccess && !pl.absent_unit.empty())
+            e = upload(&p->d_absent_unit, pl.absent_unit.data(), pl.absent_unit.size() * sizeof(uint32_t));
         if (e == cudaSuccess) e = upload(&p->d_chunk_mask, pl.chunk_mask.data(), pl.chunk_mask.size() * sizeof(uint16_t));
         if (e == cudaSuccess) e = upload(&p->d_stage_list, pl.stage_list.data(), pl.stage_list.size() * sizeof(uint32_t));
         if (e == cudaSuccess) e = upload(&p->d_chunk_list, pl.chunk_list.data(), pl.chunk_list.size() * sizeof(uint32_t));
@@ -367,6 +369,8 @@ int fri_plan_create(fri_plan **out, int device, uint32_t width, uint32_t height,
         p->tables.groups = static_cast<const GroupDesc *>(p->d_groups);
         p->tables.groups_launch = static_cast<const GroupDesc *>(p->d_groups_launch);
         p->tables.tile_unit = static_cast<const uint32_t *>(p->d_tile_unit);
+        p->tables.absent_unit = static_cast<const uint32_t *>(p->d_absent_unit);
+        p->tables.n_absent = (uint32_t)pl.absent_unit.size();
         p->tables.chunk_mask = static_cast<const uint16_t *>(p->d_chunk_mask);
         p->tables.chunk_list = static_cast<const uint32_t *>(p->d_chunk_list);
         p->tables.edge_list = static_cast<const uint32_t *>(p->d_edge_list);
@@ -401,6 +405,7 @@ void fri_plan_destroy(fri_plan *p)
         if (p->d_groups) cudaFree(p->d_groups);
         if (p->d_groups_launch) cudaFree(p->d_groups_launch);
         if (p->d_tile_unit) cudaFree(p->d_tile_unit);
+        if (p->d_absent_unit) cudaFree(p->d_absent_unit);
         if (p->d_chunk_mask) cudaFree(p->d_chunk_mask);
         if (p->d_chunk_list) cudaFree(p->d_chunk_list);
         if (p->d_edge_list) cudaFree(p->d_edge_list);

@@ -1294,6 +1294,35 @@ fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
 }
 
 // ------------------------------------------------------------------------------------------
+// depth > 9: base tiles of a retained fractal that lie entirely outside the image hold only `None`
+// coefficients.  The transform kernels skip them (they are not in any group); the encoder writes the zeros the
+// dense array holds for `None` with this pure store kernel: one warp per (absent base tile, channel), the nine
+// level runs of the tile inside the fractal's heap.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+fri_zero_absent_kernel(const uint32_t *__restrict__ absent_unit, uint32_t n_absent, int channels, int n_fractals, int sub_bits,
+                       int depth, int32_t *__restrict__ coefs)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t task = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (task >= (size_t)n_absent * channels) return;
+    const uint32_t u = __ldg(absent_unit + task / channels);
+    const int ch = (int)(task % channels), frame = blockIdx.y;
+    const uint32_t f = u >> sub_bits, node = (1u << sub_bits) + (u & ((1u << sub_bits) - 1u));
+    int32_t *out = coefs + ((((int64_t)frame * n_fractals + f) * channels + ch) << depth);
+    const int4 z4 = make_int4(0, 0, 0, 0);
+    int4 *o8 = reinterpret_cast<int4 *>(out + ((size_t)node << 8));
+    __stcs(o8 + lane, z4);
+    __stcs(o8 + 32 + lane, z4);
+    __stcs(reinterpret_cast<int4 *>(out + ((size_t)node << 7)) + lane, z4);
+    __stcs(reinterpret_cast<int2 *>(out + ((size_t)node << 6)) + lane, make_int2(0, 0));
+    __stcs(out + ((size_t)node << 5) + lane, 0);
+#pragma unroll
+    for (int L = 4; L >= 0; --L)
+        if (lane < (1 << L)) __stcs(out + ((size_t)node << L) + lane, 0);
+}
+
+// ------------------------------------------------------------------------------------------
 // coarse levels (depth > 9): the top depth-9 levels over the base tiles' low-pass roots
 // ------------------------------------------------------------------------------------------
 constexpr int kCoarseThreads = 256;
@@ -1665,6 +1694,20 @@ cudaError_t launch_encode(const Geometry &g, const DeviceTables &t, const QuantP
     int bulk_staging = 1;
     if (const char *env = std::getenv("FRI_STAGE_BULK")) bulk_staging = std::atoi(env) != 0;  // tuning knob
     const GroupDesc *gtab = whole && t.groups_launch ? t.groups_launch : t.groups;  // launch order (whole frames only)
+    if (g.sub_bits > 0 && t.n_absent > 0 && group_begin == 0) {
+        // base tiles outside the image: their low-pass roots are `None` (0 for the coarse kernel), their slots 0
+        const size_t dc_bytes = (((size_t)n_frames * g.n_fractals * g.channels) << g.sub_bits) * sizeof(int32_t);
+        cudaError_t e = cudaMemsetAsync(d_dc, 0, dc_bytes, stream);
+        if (e != cudaSuccess) return e;
+        const unsigned tasks = t.n_absent * (unsigned)g.channels;
+        for (uint32_t f0 = 0; f0 < n_frames; f0 += 65535u) {
+            const uint32_t nf = n_frames - f0 < 65535u ? n_frames - f0 : 65535u;
+            fri_zero_absent_kernel<<<dim3((tasks + 7) / 8, nf), 256, 0, stream>>>(t.absent_unit, t.n_absent, g.channels, g.n_fractals,
+                                                                                 g.sub_bits, g.depth,
+                                                                                 d_coefs + (int64_t)f0 * g.coefs_per_frame);
+            if (launches) ++*launches;
+        }
+    }
     const uint8_t *px = static_cast<const uint8_t *>(d_pixels);
     for (uint32_t f0 = 0; f0 < n_frames; f0 += 65535u) {  // gridDim.y limit
         const uint32_t nf = n_frames - f0 < 65535u ? n_frames - f0 : 65535u;

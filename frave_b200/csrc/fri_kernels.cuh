@@ -101,6 +101,8 @@ struct DeviceTables {
     const GroupDesc *groups = nullptr;         // plan order (top to bottom): banded launches, emission kernels
     const GroupDesc *groups_launch = nullptr;  // whole-frame launch order (nullptr = plan order)
     const uint32_t *tile_unit = nullptr;   // nullptr at depth 9
+    const uint32_t *absent_unit = nullptr; // depth > 9: base tiles entirely outside the image (encoder zero fill)
+    uint32_t n_absent = 0;
     const uint32_t *chunk_list = nullptr;  // [16][list_cap]
     const uint16_t *chunk_mask = nullptr;  // [16][list_cap]
     const uint32_t *edge_list = nullptr;   // [16][edge_cap]

@@ -196,6 +196,7 @@ std::string build_plan(Plan &plan, uint32_t width, uint32_t height, uint32_t cha
         });
     std::vector<BaseTile> tiles;
     tiles.reserve(kept.size() << sub_bits);
+    plan.absent_unit.clear();
     for (size_t f = 0; f < kept.size(); ++f)
         for (uint32_t s = 0; s < (1u << sub_bits); ++s) {
             Vec2 o = digit_sum(s, kBaseDepth, sub_bits);
@@ -209,6 +210,10 @@ std::string build_plan(Plan &plan, uint32_t width, uint32_t height, uint32_t cha
             bt.a = (int32_t)(na / det);
             bt.b = (int32_t)(nbn / det);
             bt.unit = (uint32_t)((f << sub_bits) | s);
+            if (sub_bits > 0 && base_tile_inside(bt.cx, bt.cy, W, H) == 0) {
+                plan.absent_unit.push_back(bt.unit);  // nothing of this base tile is inside the image
+                continue;
+            }
             tiles.push_back(bt);
         }
 

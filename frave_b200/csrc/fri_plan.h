@@ -37,7 +37,7 @@ struct Geometry {
     int32_t chunks_per_row;      // upper bound on 16-byte chunks covering one staged row
     int32_t own_words;           // 32-bit words per row of the ownership bitmap
     int32_t n_groups;
-    int32_t n_base_tiles;        // base tiles processed per frame (n_fractals << sub_bits)
+    int32_t n_base_tiles;        // base tiles processed per frame: those of the retained fractals with a pixel inside the image
     int32_t n_fractals;          // retained fractals per frame (== n_base_tiles at depth 9)
     int32_t list_cap;            // entries per phase in the chunk list
     int32_t tiles_per_warp;      // base tiles each warp of a CTA processes (full group)
@@ -72,6 +72,9 @@ struct Plan {
     std::vector<uint8_t> full;        // [n_fractals]
     std::vector<GroupDesc> groups;    // [n_groups]
     std::vector<uint32_t> tile_unit;  // [n_base_tiles] fractal_index << sub_bits | sub_tile (empty at depth 9)
+    // depth > 9: base tiles of retained fractals that lie entirely outside the image.  All their coefficients are
+    // `None`; the transform kernels skip them, the encoder zero-fills their slots of the dense array.
+    std::vector<uint32_t> absent_unit;
     std::vector<uint32_t> ownership;  // [region_h][own_words]: bit x set <=> region pixel belongs to the group
     // Byte-ownership of the staged region cut into the 16-byte chunks the kernels move, for each
     // of the 16 possible phases (global address of the region's first byte mod 16):

@@ -124,7 +124,7 @@ def test_deep_tree_extension(depth, dtype, c):
         got = plan.encode(img, q)[0]
         want, some = oracle_encode(plan, img, q)
         assert np.array_equal(got, want)
-        assert plan.last_launches == 2  # base kernel + coarse levels
+        assert plan.last_launches in (2, 3)  # [zero fill of base tiles outside the image +] base kernel + coarse levels
         assert np.array_equal(plan.decode(got, q)[0], oracle_decode(plan, got, some, q))
         lossless = plan.encode(img)[0]
         rec = plan.decode(lossless)[0]

@@ -66,7 +66,7 @@ def test_deep_tree_16384_every_fractal(depth):
     with capi.Plan(w, h, 1, depth=depth, sample_bytes=2) as plan:
         centers = plan.centers()
         got = plan.encode(img, q)[0]
-        assert plan.last_launches == 2  # base kernel + coarse levels
+        assert plan.last_launches in (2, 3)  # [zero fill of base tiles outside the image +] base kernel + coarse levels
         want, some = O.extract_tiles(img, centers, depth=depth, nthreads=8)
         want = O.quantize(want, some, q, depth=depth)
         assert np.array_equal(got, want)
