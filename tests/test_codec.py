@@ -139,3 +139,43 @@ def test_frv_encode_decode_on_the_device(shape, smooth):
         some = np.broadcast_to(plan.masks()[:, None, :], plan.coef_shape)
         want = O.extract_values(plan.centers(), O.quantize(cq, some, q), some, h, w)
         assert np.array_equal(plan.frv_decode(dq, q), want)
+
+
+def test_stage_mirror_of_the_entropy_stages_on_cpu():
+    """stages.prediction / entropy_coding / serialize keep the reference's names and hand-offs; on a host-only plan
+    (device = -1) everything behind the quantizer runs, fed with oracle coefficients."""
+    from frave_b200 import stages
+    h, w, c = 96, 120, 3
+    img = smooth_image(h, w, c, seed=4)
+    with capi.Plan(w, h, c, device=-1) as plan:
+        coefs = _coefs(plan, img)
+        wi = stages.WaveletImage(stages.ImageMetadata(h, w, stages.ColorSpace.YCbCr), plan.centers(), coefs, plan.masks(), 9,
+                                 np.ones(32, np.int32), 1, -1, quantized=True)
+    ctx = stages.prediction.encode(wi)
+    ci = stages.entropy_coding.encode(wi, ctx)
+    data = stages.serialize.encode(ci)
+    back = stages.serialize.decode(data)
+    assert (back.metadata.height, back.metadata.width, back.metadata.colorspace) == (h, w, stages.ColorSpace.YCbCr)
+    wi2 = stages.entropy_coding.decode(back, device=-1)
+    assert np.array_equal(wi2.coefficients, coefs) and np.array_equal(wi2.centers, wi.centers)
+    with pytest.raises(stages.StageError):
+        stages.serialize.decode(b"not a frif file")
+
+
+@pytest.mark.gpu
+def test_fri_encoder_and_decoder_drivers():
+    """The reference's two public entry points (encoder.rs:87-109, decoder.rs:48-59) on the device."""
+    from frave_b200 import stages
+    h, w = 270, 480
+    rgb = smooth_image(h, w, 3, seed=8)
+    data = stages.FRIEncoder().encode(rgb.tobytes(), h, w, stages.ColorSpace.RGB)
+    out = stages.FRIDecoder().decode(data)
+    assert out.metadata.colorspace is stages.ColorSpace.RGB and out.data.shape == (h, w, 3)
+    with capi.Plan(w, h, 3) as plan:  # 480x270: the reference's BFS leaves five pixels uncovered, they decode to 0
+        assert int((out.data != rgb).any(axis=2).sum()) == w * h - plan.pixels_covered
+    luma = smooth_image(64, 96, 1, seed=9)
+    back = stages.FRIDecoder().decode(stages.FRIEncoder().encode(luma, 64, 96, stages.ColorSpace.Luma))
+    assert np.array_equal(back.data, luma) and back.metadata.colorspace is stages.ColorSpace.Luma
+    with pytest.raises(stages.StageError) as ei:
+        stages.FRIDecoder().decode(data[:100])
+    assert "Failed to decode" in str(ei.value)
