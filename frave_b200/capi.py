@@ -66,6 +66,7 @@ _SYMBOLS = [
     ("fri_decode_tq_emit10", C.c_int, [_P, _P, C.c_uint32, _P, C.c_int, _P]),
     ("fri_predict_device", C.c_int, [_P, _P, C.c_uint32, _P, _P, _P, _P, _P, _P, _P, _P]),
     ("fri_fit_parameters", C.c_int, [_P, _P, _P, _P]),
+    ("fri_fit_device", C.c_int, [_P, _P, _P, _P, _P]),
     ("fri_predict_host", C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),
     ("fri_frv_pack", C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, C.POINTER(_P), C.POINTER(C.c_size_t)]),
     ("fri_frv_unpack", C.c_int, [_P, _P, C.c_size_t, _P]),
@@ -499,6 +500,14 @@ class Plan:
         vp = np.zeros((self.channels, 3, 6), np.float32)
         wp = np.zeros((self.channels, 3, 6), np.float32)
         _check(lib().fri_fit_parameters(self._h, cf.ctypes.data, vp.ctypes.data, wp.ctypes.data))
+        return vp, wp
+
+    def fit_device(self, d_coefs: int, stream: int = 0):
+        """The same fit for one device-resident frame (sums on the device, solve on the host): bit-identical
+        parameters to fit_parameters on the same coefficients."""
+        vp = np.zeros((self.channels, 3, 6), np.float32)
+        wp = np.zeros((self.channels, 3, 6), np.float32)
+        _check(lib().fri_fit_device(self._h, C.c_void_p(d_coefs), vp.ctypes.data, wp.ctypes.data, C.c_void_p(stream)))
         return vp, wp
 
     def predict_host(self, coefs: np.ndarray, value_params, width_params):

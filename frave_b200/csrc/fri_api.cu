@@ -103,6 +103,7 @@ struct fri_plan {
     bool lattice_ready = false;
     LatticeIndex lattice;
     std::vector<uint8_t> some_flat;  // [n_tiles * 512] Some / None
+    uint64_t fit_zero_rows[3] = {0, 0, 0};  // codec::fit_zero_rows of this plan
 };
 
 namespace {
@@ -1177,6 +1178,7 @@ static int ensure_lattice(fri_plan *p)
             fractal_mask(g.depth, p->plan.centers[2 * t], p->plan.centers[2 * t + 1], g.width, g.height, mask.data());
             for (int i = 0; i < kTileLeaves; ++i) p->some_flat[(size_t)t * kTileLeaves + i] = (mask[i >> 5] >> (i & 31)) & 1u;
         }
+        codec::fit_zero_rows(p->plan, p->some_flat, p->fit_zero_rows);
     } catch (const std::bad_alloc &) {
         return fail(FRI_E_NOMEM, "out of host memory while building the lattice index");
     }
@@ -1188,6 +1190,57 @@ static int host_threads_hint()
 {
     const unsigned n = std::thread::hardware_concurrency();
     return (int)std::max(1u, std::min(n, 16u));
+}
+
+/* Predictor parameters of one device-resident frame: the normal equations are summed on the device (two passes
+ * of fri_fit_kernel, exact integers), the 6 x 6 systems solved on the host between and after them. */
+static int fit_on_device(fri_plan *p, const int32_t *d_coefs, float *value_params, float *width_params, cudaStream_t st)
+{
+    const Geometry &g = p->plan.geo;
+    const int C = g.channels;
+    constexpr int kTerms = 27;
+    const size_t n = (size_t)C * 3 * kTerms;
+    unsigned long long *d_sums = nullptr;
+    int rc = pool_alloc(p, reinterpret_cast<void **>(&d_sums), n * sizeof(unsigned long long), st);
+    if (rc) return rc;
+    std::vector<unsigned long long> sums(n);
+    PredictParams prm{};
+    auto pass = [&](bool width) -> int {
+        FRI_CUDA(cudaMemsetAsync(d_sums, 0, n * sizeof(unsigned long long), st));
+        FRI_CUDA(launch_fit(g, p->tables, p->emit_tables, p->predict_tables, prm, width, d_coefs, d_sums, st, &p->last_launches));
+        FRI_CUDA(cudaMemcpyAsync(sums.data(), d_sums, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        FRI_CUDA(cudaStreamSynchronize(st));
+        return FRI_OK;
+    };
+    auto solve = [&](bool width, float *out) {
+        for (int cs = 0; cs < C * 3; ++cs) {
+            codec::FitSums f;
+            for (int i = 0; i < 21; ++i) f.a[i] = sums[(size_t)cs * kTerms + i];
+            for (int i = 0; i < 6; ++i) f.b[i] = sums[(size_t)cs * kTerms + 21 + i];
+            if (width) f.a[0] += p->fit_zero_rows[cs % 3];
+            codec::solve_fit(f, width ? (double)codec::kFitScale : 1.0, out + (size_t)cs * 6);
+        }
+    };
+    rc = pass(false);
+    if (!rc) {
+        solve(false, value_params);
+        std::memcpy(prm.value, value_params, sizeof(float) * 18 * C);
+        rc = pass(true);
+    }
+    if (!rc) solve(true, width_params);
+    cudaFreeAsync(d_sums, st);
+    return rc;
+}
+
+int fri_fit_device(fri_plan *p, const int32_t *d_coefs, float *value_params, float *width_params, void *stream)
+{
+    int rc = enter_device(p);
+    if (rc) return rc;
+    if (!d_coefs || !value_params || !width_params) return fail(FRI_E_INVALID, "NULL argument");
+    if ((rc = ensure_predict_device(p))) return rc;
+    if ((rc = ensure_lattice(p))) return rc;
+    p->last_launches = 0;
+    return fit_on_device(p, d_coefs, value_params, width_params, static_cast<cudaStream_t>(stream));
 }
 
 int fri_fit_parameters(fri_plan *p, const int32_t *coefs, float *value_params, float *width_params)
@@ -1355,15 +1408,13 @@ int fri_frv_encode(fri_plan *p, const void *pixels, const int32_t *q, int colors
     if ((rc = acquire_slot(p, s))) return rc;
     p->last_launches = 0;
     try {
-        // 1. transform + quantization on the device; the dense blocks come back for the parameter fit
-        std::vector<int32_t> coefs((size_t)g.coefs_per_frame);
+        // 1. transform + quantization on the device
         FRI_CUDA(cudaMemcpyAsync(s.d_pixels, pixels, (size_t)g.frame_bytes, cudaMemcpyHostToDevice, st));
         FRI_CUDA(launch_encode(g, p->tables, qp, s.d_pixels, 1, s.d_coefs, false, s.d_dc, st, &p->last_launches));
-        FRI_CUDA(cudaMemcpyAsync(coefs.data(), s.d_coefs, coefs.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        FRI_CUDA(cudaStreamSynchronize(st));
-        // 2. predictor parameters (host least squares; context_modeling.rs:204-214)
+        // 2. predictor parameters: normal equations summed on the device, solved on the host
+        //    (context_modeling.rs:204-214; bit-identical to fri_fit_parameters on the same coefficients)
         std::vector<float> vp((size_t)C * 18), wp((size_t)C * 18);
-        codec::fit_parameters(p->plan, p->lattice, p->some_flat, coefs.data(), vp.data(), wp.data(), host_threads_hint());
+        if ((rc = fit_on_device(p, s.d_coefs, vp.data(), wp.data(), st))) return rc;
         // 3. prediction + context buckets + histograms on the device
         PredictParams prm{};
         std::memcpy(prm.value, vp.data(), sizeof(float) * 18 * C);

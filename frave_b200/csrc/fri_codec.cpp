@@ -321,39 +321,40 @@ void Predictor::hf(const int32_t *coefs, int tile, int heap, int ch, const float
 }
 
 // ---------------------------------------------------------------------------------------------
-// parameter fit (context_modeling.rs:79-214) — normal equations, see the header
+// parameter fit (context_modeling.rs:79-214) — integer normal equations, see the header
 // ---------------------------------------------------------------------------------------------
-namespace {
+void FitSums::add(const int64_t w[6], int64_t y)
+{
+    int k = 0;
+    for (int i = 0; i < 6; ++i) {
+        b[i] += (uint64_t)w[i] * (uint64_t)y;
+        for (int j = i; j < 6; ++j) a[k++] += (uint64_t)w[i] * (uint64_t)w[j];
+    }
+}
 
-struct Normal {
-    double a[6][6] = {};
-    double b[6] = {};
-    void add(const double w[6], double y)
-    {
-        for (int i = 0; i < 6; ++i) {
-            b[i] += w[i] * y;
-            for (int j = i; j < 6; ++j) a[i][j] += w[i] * w[j];
-        }
-    }
-    void merge(const Normal &o)
-    {
-        for (int i = 0; i < 6; ++i) {
-            b[i] += o.b[i];
-            for (int j = 0; j < 6; ++j) a[i][j] += o.a[i][j];
-        }
-    }
-};
+void FitSums::merge(const FitSums &o)
+{
+    for (int i = 0; i < 21; ++i) a[i] += o.a[i];
+    for (int i = 0; i < 6; ++i) b[i] += o.b[i];
+}
+
+int64_t width_target(float coef, float prediction)
+{
+    const float r = std::fabs(coef - prediction) * (float)kFitScale;
+    return r < 1.0e12f ? (int64_t)r : (int64_t)1 << 40;  // NaN / overflow: the same cap as the kernel's
+}
 
 // Minimum-norm least-squares solution of the symmetric system through a Jacobi eigen-decomposition
 // (what an SVD-based lstsq returns, up to rounding).
-void solve_min_norm(const Normal &n, float out[6])
+void solve_fit(const FitSums &n, double b_scale, float out[6])
 {
-    double a[6][6], v[6][6];
+    double a[6][6], v[6][6], rhs[6];
+    for (int i = 0, k = 0; i < 6; ++i) {
+        rhs[i] = (double)(int64_t)n.b[i] / b_scale;
+        for (int j = i; j < 6; ++j, ++k) a[i][j] = a[j][i] = (double)(int64_t)n.a[k];
+    }
     for (int i = 0; i < 6; ++i)
-        for (int j = 0; j < 6; ++j) {
-            a[i][j] = j >= i ? n.a[i][j] : n.a[j][i];
-            v[i][j] = i == j;
-        }
+        for (int j = 0; j < 6; ++j) v[i][j] = i == j;
     for (int sweep = 0; sweep < 60; ++sweep) {
         double off = 0;
         for (int i = 0; i < 6; ++i)
@@ -389,15 +390,22 @@ void solve_min_norm(const Normal &n, float out[6])
         const double lam = a[k][k];
         if (lmax == 0 || lam <= 1e-12 * lmax) continue;  // rank-deficient direction: contributes nothing (minimum norm)
         double proj = 0;
-        for (int i = 0; i < 6; ++i) proj += v[i][k] * n.b[i];
+        for (int i = 0; i < 6; ++i) proj += v[i][k] * rhs[i];
         for (int i = 0; i < 6; ++i) x[i] += v[i][k] * proj / lam;
     }
     for (int i = 0; i < 6; ++i) out[i] = (float)x[i];
 }
 
-inline int layer_set(int level) { return level < kBaseDepth - 2 ? 2 : (level == kBaseDepth - 2 ? 1 : 0); }
-
-}  // namespace
+void fit_zero_rows(const Plan &plan, const std::vector<uint8_t> &some, uint64_t rows[3])
+{
+    rows[0] = rows[1] = rows[2] = 0;
+    const int n_tiles = plan.geo.n_fractals;
+    for (int tile = 0; tile < n_tiles; ++tile) {
+        for (int heap = 2; heap < kTileLeaves; ++heap)
+            if (!some[(size_t)tile * kTileLeaves + heap]) ++rows[fit_layer_set(31 - __builtin_clz((unsigned)heap))];
+        rows[2] += 2;
+    }
+}
 
 void fit_parameters(const Plan &plan, const LatticeIndex &lat, const std::vector<uint8_t> &some, const int32_t *coefs,
                     float *value_params, float *width_params, int n_threads)
@@ -411,56 +419,53 @@ void fit_parameters(const Plan &plan, const LatticeIndex &lat, const std::vector
         for (int t = 0; t < n_threads; ++t) th.emplace_back([&, t] { body(t, (int)((int64_t)n_tiles * t / n_threads), (int)((int64_t)n_tiles * (t + 1) / n_threads)); });
         for (auto &x : th) x.join();
     };
+    uint64_t zero_rows[3];
+    fit_zero_rows(plan, some, zero_rows);
     for (int ch = 0; ch < C; ++ch) {
         // ---- value predictors: y ~ v . p per layer set
-        std::vector<Normal> acc((size_t)n_threads * 3);
+        std::vector<FitSums> acc((size_t)n_threads * 3);
         parallel([&](int t, int lo, int hi) {
             for (int tile = lo; tile < hi; ++tile)
                 for (int heap = 2; heap < kTileLeaves; ++heap) {
                     if (!some[(size_t)tile * kTileLeaves + heap]) continue;
                     int32_t v[6];
                     pred.neighbour_values(coefs, tile, heap, ch, v);
-                    const double w[6] = {(double)v[0], (double)v[1], (double)v[2], (double)v[3], (double)v[4], (double)v[5]};
-                    acc[(size_t)t * 3 + layer_set(31 - __builtin_clz((unsigned)heap))].add(
-                        w, (double)coefs[(((size_t)tile * C + ch) << kBaseDepth) + heap]);
+                    const int64_t w[6] = {v[0], v[1], v[2], v[3], v[4], v[5]};
+                    acc[(size_t)t * 3 + fit_layer_set(31 - __builtin_clz((unsigned)heap))].add(
+                        w, coefs[(((size_t)tile * C + ch) << kBaseDepth) + heap]);
                 }
         });
         float vp[3][6];
         for (int s = 0; s < 3; ++s) {
-            Normal n;
+            FitSums n;
             for (int t = 0; t < n_threads; ++t) n.merge(acc[(size_t)t * 3 + s]);
-            solve_min_norm(n, vp[s]);
+            solve_fit(n, 1.0, vp[s]);
             std::memcpy(value_params + ((size_t)ch * 3 + s) * 6, vp[s], sizeof(float) * 6);
         }
         // ---- width predictors: |y - v . p| ~ w . [1, |v0-v3|, |v1-v2|, |v4-v5|, |v1-v5|, |v2-v4|]; rows the
         // reference's matrices keep at zero (None coefficients, two spare rows per tile in the last set) count as
-        // [1, 0, 0, 0, 0, 0] -> 0
-        std::vector<Normal> wacc((size_t)n_threads * 3);
+        // [1, 0, 0, 0, 0, 0] -> 0 (fit_zero_rows)
+        std::vector<FitSums> wacc((size_t)n_threads * 3);
         parallel([&](int t, int lo, int hi) {
-            for (int tile = lo; tile < hi; ++tile) {
+            for (int tile = lo; tile < hi; ++tile)
                 for (int heap = 2; heap < kTileLeaves; ++heap) {
-                    const int s = layer_set(31 - __builtin_clz((unsigned)heap));
-                    if (!some[(size_t)tile * kTileLeaves + heap]) {
-                        wacc[(size_t)t * 3 + s].a[0][0] += 1.0;
-                        continue;
-                    }
+                    if (!some[(size_t)tile * kTileLeaves + heap]) continue;
+                    const int s = fit_layer_set(31 - __builtin_clz((unsigned)heap));
                     int32_t v[6];
                     pred.neighbour_values(coefs, tile, heap, ch, v);
                     float p = (float)v[0] * vp[s][0];
                     for (int j = 1; j < 6; ++j) p = p + (float)v[j] * vp[s][j];
-                    const double r = std::fabs((double)((float)coefs[(((size_t)tile * C + ch) << kBaseDepth) + heap] - p));
-                    const double w[6] = {1.0, std::fabs((double)v[0] - v[3]), std::fabs((double)v[1] - v[2]), std::fabs((double)v[4] - v[5]),
-                                         std::fabs((double)v[1] - v[5]), std::fabs((double)v[2] - v[4])};
-                    wacc[(size_t)t * 3 + s].add(w, r);
+                    auto ad = [](int32_t x, int32_t y) { return std::abs((int64_t)x - (int64_t)y); };
+                    const int64_t w[6] = {1, ad(v[0], v[3]), ad(v[1], v[2]), ad(v[4], v[5]), ad(v[1], v[5]), ad(v[2], v[4])};
+                    wacc[(size_t)t * 3 + s].add(w, width_target((float)coefs[(((size_t)tile * C + ch) << kBaseDepth) + heap], p));
                 }
-                wacc[(size_t)t * 3 + 2].a[0][0] += 2.0;
-            }
         });
         for (int s = 0; s < 3; ++s) {
-            Normal n;
+            FitSums n;
             for (int t = 0; t < n_threads; ++t) n.merge(wacc[(size_t)t * 3 + s]);
+            n.a[0] += zero_rows[s];
             float wp[6];
-            solve_min_norm(n, wp);
+            solve_fit(n, (double)kFitScale, wp);
             std::memcpy(width_params + ((size_t)ch * 3 + s) * 6, wp, sizeof(float) * 6);
         }
     }

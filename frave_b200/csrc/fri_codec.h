@@ -93,8 +93,26 @@ struct Predictor {
 
 // Predictor parameters of every channel: value[C][3][6], width[C][3][6] (layer set 0: level 8, 1: level 7,
 // 2: levels 1..6).  Least squares like context_modeling.rs:144-214, but solved through the 6 x 6 normal
-// equations in f64 with a pseudo-inverse for rank-deficient cases — NOT lstsq 0.6 / nalgebra's f32 SVD,
-// which are not in the reference tree; the parameters are stored in the container, so any fit decodes.
+// equations with a pseudo-inverse for rank-deficient cases — NOT lstsq 0.6 / nalgebra's f32 SVD, which are not
+// in the reference tree; the parameters are stored in the container, so any fit decodes.
+//
+// The normal equations are accumulated in EXACT integer arithmetic (every regressor is an integer; the width
+// fit's target |coefficient - prediction| is taken in 1/kFitScale fixed point), so that the host fit below and
+// the device fit (fri_fit_kernel: per-thread sums, shuffles, atomics — any order) produce the same sums and,
+// through the same host solve, bit-identical parameters.  Sums wrap modulo 2^64 on both sides.
+constexpr int kFitScale = 256;
+struct FitSums {
+    uint64_t a[21] = {};  // upper triangle of sum w w^T, row-major
+    uint64_t b[6] = {};   // sum w * y
+    void add(const int64_t w[6], int64_t y);
+    void merge(const FitSums &o);
+};
+inline int fit_layer_set(int level) { return level < kBaseDepth - 2 ? 2 : (level == kBaseDepth - 2 ? 1 : 0); }
+int64_t width_target(float coef, float prediction);                    // |coef - prediction| * kFitScale, truncated
+void solve_fit(const FitSums &n, double b_scale, float out[6]);        // minimum-norm solution of a x = b / b_scale
+// Rows of the reference's width matrices that stay [1, 0, 0, 0, 0, 0] -> 0 (None coefficients, two spare rows per
+// tile in set 2): a plan constant per layer set, added to a[0][0].
+void fit_zero_rows(const Plan &plan, const std::vector<uint8_t> &some, uint64_t rows[3]);
 void fit_parameters(const Plan &plan, const LatticeIndex &lat, const std::vector<uint8_t> &some, const int32_t *coefs,
                     float *value_params, float *width_params, int n_threads);
 

@@ -165,6 +165,12 @@ cudaError_t launch_predict(const Geometry &g, const DeviceTables &t, const EmitT
                            const PredictParams &prm, uint64_t count, const int32_t *d_coefs, uint32_t n_frames,
                            uint8_t *d_bucket, int32_t *d_pred, uint16_t *d_sym, uint32_t *d_hist, uint32_t *d_overflow,
                            cudaStream_t stream, uint32_t *launches);
+// One pass of the predictor parameter fit over one frame: adds the integer normal-equation sums of every
+// (channel, layer set) to d_sums[C][3][27] (21 upper-triangle terms + 6 right-hand sides; the caller zeroes
+// them).  width_pass = false: value fit; true: width fit with prm.value already solved.
+cudaError_t launch_fit(const Geometry &g, const DeviceTables &t, const EmitTables &et, const PredictTables &pt,
+                       const PredictParams &prm, bool width_pass, const int32_t *d_coefs, unsigned long long *d_sums,
+                       cudaStream_t stream, uint32_t *launches);
 
 // Packed transport of emission-ordered streams (bits = 10 or 9): int16 streams (stride a multiple of 64
 // elements, 16-byte aligned) <-> blocks of 64 zig-zag symbols in 8 * bits bytes; n_blocks = total elements / 64.

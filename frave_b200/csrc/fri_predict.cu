@@ -69,6 +69,35 @@ struct Lookup {
     __device__ __forceinline__ bool contains(int level, int x, int y) const { return node_at(level, x, y).tile >= 0; }
 };
 
+// get_neighbour_values (context_modeling.rs:25-77) of the level-`level` node `heap` of the tile centred at
+// (cx, cy): left, up-left, up-right on the node's own level, the parents of right, down-left, down-right.
+template <typename CoefAt>
+__device__ __forceinline__ void hf_neighbour_values(const Lookup &L, int cx, int cy, int heap, int level, CoefAt coef_at, int v[6])
+{
+    const PredictTables &pt = L.pt;
+    const int d = kBaseDepth - level;
+    const short2 o = L.off[(heap - (1 << level)) << d];  // the node sits at its first leaf
+    const int px = cx + o.x, py = cy + o.y;
+    const short2 *nv = pt.nearby[d];
+    bool alt_up = false, alt_down = false;
+    if (d == 2) {  // wavelet_transform.rs:115-177: probes of the level-`depth` (= 2) map, kept as written
+        alt_down = !L.contains(2, px + nv[3].x, py + nv[3].y) && L.contains(2, px + 1, py + 1);
+        alt_up = !L.contains(2, px + nv[0].x, py + nv[0].y) && L.contains(2, px - 1, py - 1);
+    }
+    int qx[6], qy[6];
+    qx[0] = px + nv[4].x; qy[0] = py + nv[4].y;                                     // left
+    if (alt_up) { qx[1] = px - 1 + nv[4].x; qy[1] = py - 1 + nv[4].y; qx[2] = px - 1; qy[2] = py - 1; }
+    else { qx[1] = px + nv[5].x; qy[1] = py + nv[5].y; qx[2] = px + nv[0].x; qy[2] = py + nv[0].y; }  // up-left, up-right
+    qx[3] = px + nv[1].x; qy[3] = py + nv[1].y;                                     // right
+    if (alt_down) { qx[4] = px + 1; qy[4] = py + 1; qx[5] = px + 1 + nv[1].x; qy[5] = py + 1 + nv[1].y; }
+    else { qx[4] = px + nv[3].x; qy[4] = py + nv[3].y; qx[5] = px + nv[2].x; qy[5] = py + nv[2].y; }  // down-left, down-right
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        const NodeRef n = L.node_at(level, qx[j], qy[j]);
+        v[j] = n.tile >= 0 ? coef_at(n.tile, j < 3 ? n.heap : n.heap >> 1) : 0;
+    }
+}
+
 // One CTA per (group, frame); thread per emitted slot of the group; channels in an outer loop so that the
 // per-context histograms of one channel (10 x 1024 counters) fit in shared memory.
 __global__ void __launch_bounds__(256)
@@ -120,28 +149,8 @@ fri_predict_kernel(const __grid_constant__ PredictTables pt, const __grid_consta
             } else {
                 // ---- get_hf_context_bucket
                 const int level = 31 - __clz(heap);
-                const int d = kBaseDepth - level;
-                const short2 o = s_off[(heap - (1 << level)) << d];  // the node sits at its first leaf
-                const int px = cx + o.x, py = cy + o.y;
-                const short2 *nv = pt.nearby[d];
-                bool alt_up = false, alt_down = false;
-                if (d == 2) {  // wavelet_transform.rs:115-177: probes of the level-`depth` (= 2) map, kept as written
-                    alt_down = !L.contains(2, px + nv[3].x, py + nv[3].y) && L.contains(2, px + 1, py + 1);
-                    alt_up = !L.contains(2, px + nv[0].x, py + nv[0].y) && L.contains(2, px - 1, py - 1);
-                }
-                int qx[6], qy[6];
-                qx[0] = px + nv[4].x; qy[0] = py + nv[4].y;                                     // left
-                if (alt_up) { qx[1] = px - 1 + nv[4].x; qy[1] = py - 1 + nv[4].y; qx[2] = px - 1; qy[2] = py - 1; }
-                else { qx[1] = px + nv[5].x; qy[1] = py + nv[5].y; qx[2] = px + nv[0].x; qy[2] = py + nv[0].y; }  // up-left, up-right
-                qx[3] = px + nv[1].x; qy[3] = py + nv[1].y;                                     // right
-                if (alt_down) { qx[4] = px + 1; qy[4] = py + 1; qx[5] = px + 1 + nv[1].x; qy[5] = py + 1 + nv[1].y; }
-                else { qx[4] = px + nv[3].x; qy[4] = py + nv[3].y; qx[5] = px + nv[2].x; qy[5] = py + nv[2].y; }  // down-left, down-right
                 int v[6];
-#pragma unroll
-                for (int j = 0; j < 6; ++j) {
-                    const NodeRef n = L.node_at(level, qx[j], qy[j]);
-                    v[j] = n.tile >= 0 ? coef_at(n.tile, ch, j < 3 ? n.heap : n.heap >> 1) : 0;
-                }
+                hf_neighbour_values(L, cx, cy, heap, level, [&](int t, int h) { return coef_at(t, ch, h); }, v);
                 const int layer = level < kBaseDepth - 2 ? 2 : (level == kBaseDepth - 2 ? 1 : 0);
                 const float *vp = vp_all + 6 * layer, *wp = wp_all + 6 * layer;
                 float width = wp[0];
@@ -176,6 +185,96 @@ fri_predict_kernel(const __grid_constant__ PredictTables pt, const __grid_consta
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Predictor parameter fit (context_modeling.rs:144-214), accumulation side: the 6 x 6 normal equations of
+// every (channel, layer set) as exact 64-bit integer sums (fri_codec.h, FitSums) — pass VALUE: regressors the
+// six neighbour values, target the coefficient; pass WIDTH: regressors [1, |v0-v3|, |v1-v2|, |v4-v5|, |v1-v5|,
+// |v2-v4|], target |coefficient - prediction| in 1/256 fixed point with the value parameters of pass one.  One
+// CTA per group; a thread keeps the 27 sums of one layer set in registers while it walks the group's slots of
+// that set, then shuffles + shared memory + one atomic per CTA and sum.  Integer sums are order-independent,
+// so the parameters the host solves from them are bit-identical to the host fit's.
+// ------------------------------------------------------------------------------------------
+constexpr int kFitTerms = 27;  // 21 (upper triangle) + 6
+
+template <bool WIDTH>
+__global__ void __launch_bounds__(256)
+fri_fit_kernel(const __grid_constant__ PredictTables pt, const __grid_constant__ PredictParams prm,
+               const GroupDesc *__restrict__ groups, const uint32_t *__restrict__ goff, const uint16_t *__restrict__ loc,
+               int channels, const int32_t *__restrict__ coefs, unsigned long long *__restrict__ sums)
+{
+    __shared__ uint16_t s_lut[kTileLeaves];
+    __shared__ short2 s_off[kTileLeaves];
+    __shared__ unsigned long long s_part[8][kFitTerms];
+    for (int i = threadIdx.x; i < kTileLeaves; i += blockDim.x) {
+        s_lut[i] = pt.lut[i];
+        s_off[i] = pt.off[i];
+    }
+    __syncthreads();
+    const Lookup L{pt, s_lut, s_off};
+    const GroupDesc gd = groups[blockIdx.x];
+    const uint32_t k0 = goff[blockIdx.x], k1 = goff[blockIdx.x + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int ch = 0; ch < channels; ++ch) {
+        auto coef_at = [&](int tile, int heap) { return __ldg(coefs + (((size_t)tile * channels + ch) << kBaseDepth) + heap); };
+#pragma unroll 1
+        for (int set = 0; set < 3; ++set) {
+            const float *vp = prm.value[ch][set];
+            unsigned long long acc[kFitTerms];
+#pragma unroll
+            for (int i = 0; i < kFitTerms; ++i) acc[i] = 0;
+            for (uint32_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
+                const uint32_t l = __ldg(loc + k);
+                const int heap = (int)(l & (kTileLeaves - 1));
+                if (heap < 2) continue;
+                const int level = 31 - __clz(heap);
+                if ((level < kBaseDepth - 2 ? 2 : (level == kBaseDepth - 2 ? 1 : 0)) != set) continue;
+                const int tile = (int)gd.tile_base + (int)(l >> kBaseDepth);
+                const int cx = __ldg(pt.centers + 2 * tile), cy = __ldg(pt.centers + 2 * tile + 1);
+                int v[6];
+                hf_neighbour_values(L, cx, cy, heap, level, coef_at, v);
+                const int value = coef_at(tile, heap);
+                long long w[6], y;
+                if (!WIDTH) {
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) w[j] = v[j];
+                    y = value;
+                } else {
+                    float p = __fmul_rn((float)v[0], vp[0]);
+#pragma unroll
+                    for (int j = 1; j < 6; ++j) p = __fadd_rn(p, __fmul_rn((float)v[j], vp[j]));
+                    const float r = __fmul_rn(fabsf(__fsub_rn((float)value, p)), 256.0f);
+                    y = r < 1.0e12f ? __float2ll_rz(r) : 1ll << 40;
+                    auto ad = [](int a, int b) { return llabs((long long)a - (long long)b); };
+                    w[0] = 1; w[1] = ad(v[0], v[3]); w[2] = ad(v[1], v[2]); w[3] = ad(v[4], v[5]);
+                    w[4] = ad(v[1], v[5]); w[5] = ad(v[2], v[4]);
+                }
+                int t = 0;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    acc[21 + i] += (unsigned long long)w[i] * (unsigned long long)y;
+#pragma unroll
+                    for (int j = i; j < 6; ++j) acc[t++] += (unsigned long long)w[i] * (unsigned long long)w[j];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < kFitTerms; ++i) {
+                unsigned long long x = acc[i];
+#pragma unroll
+                for (int sh = 16; sh > 0; sh >>= 1) x += __shfl_xor_sync(0xffffffffu, x, sh);
+                if (lane == 0) s_part[warp][i] = x;
+            }
+            __syncthreads();
+            if (threadIdx.x < kFitTerms) {
+                unsigned long long x = 0;
+                for (int wp = 0; wp < (int)(blockDim.x >> 5); ++wp) x += s_part[wp][threadIdx.x];
+                if (x) atomicAdd(sums + ((size_t)ch * 3 + set) * kFitTerms + threadIdx.x, x);
+            }
+            __syncthreads();
+        }
+    }
+}
+
 }  // namespace
 
 cudaError_t configure_predict_kernel()
@@ -203,4 +302,18 @@ cudaError_t launch_predict(const Geometry &g, const DeviceTables &t, const EmitT
     return cudaGetLastError();
 }
 
+cudaError_t launch_fit(const Geometry &g, const DeviceTables &t, const EmitTables &et, const PredictTables &pt,
+                       const PredictParams &prm, bool width_pass, const int32_t *d_coefs, unsigned long long *d_sums,
+                       cudaStream_t stream, uint32_t *launches)
+{
+    if (g.n_groups == 0) return cudaSuccess;
+    if (width_pass)
+        fri_fit_kernel<true><<<(unsigned)g.n_groups, 256, 0, stream>>>(pt, prm, t.groups, et.goff, et.loc, g.channels, d_coefs, d_sums);
+    else
+        fri_fit_kernel<false><<<(unsigned)g.n_groups, 256, 0, stream>>>(pt, prm, t.groups, et.goff, et.loc, g.channels, d_coefs, d_sums);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
 }  // namespace fri
+

@@ -257,7 +257,12 @@ int fri_predict_device(fri_plan *plan, const int32_t *d_coefs, uint32_t n_frames
  * un-vendored `rans 0.2.1` crate.  PARITY UNPINNED (no reference build exists here): containers written here
  * decode here bit-exactly; byte identity with the reference's `.frv` files is not claimed.
  *   fri_fit_parameters  host coefs [n_tiles][C][512] -> value / width predictor parameters float [C][3][6]
- *                       (least squares; the solver is NOT lstsq / nalgebra's f32 SVD)
+ *                       (least squares; the solver is NOT lstsq / nalgebra's f32 SVD).  The normal equations
+ *                       are exact integer sums (the width fit's targets in 1/256 fixed point).
+ *   fri_fit_device      the same fit for one device-resident frame: the sums are accumulated by a kernel (two
+ *                       passes over the coefficients), the 6 x 6 systems solved on the host; synchronizes
+ *                       `stream`.  Integer sums are order-independent: the parameters are bit-identical to
+ *                       fri_fit_parameters on the same coefficients.
  *   fri_predict_host    the host form of fri_predict_device (same outputs, host arrays, one frame): what the
  *                       serial entropy decoder evaluates per coefficient
  *   fri_frv_pack        symbols + buckets + histograms (from fri_predict_device / _host) -> container bytes:
@@ -267,15 +272,16 @@ int fri_predict_device(fri_plan *plan, const int32_t *d_coefs, uint32_t n_frames
  *   fri_frv_unpack      container bytes -> dense coefficient blocks (serial: every prediction reads already
  *                       decoded neighbours, entropy_coding.rs:205-264; channels run on separate host threads)
  *   fri_frv_info        width / height / channels of a container
- *   fri_frv_encode      host pixels -> container bytes: transform + quantization on the device, parameter fit
- *                       on the host, prediction + buckets + histograms on the device, rANS + container on the
- *                       host (FRIEncoder::encode, encoder.rs:87-109)
+ *   fri_frv_encode      host pixels -> container bytes: transform + quantization, parameter fit (fri_fit_device),
+ *                       prediction + buckets + histograms on the device, rANS + container on the host
+ *                       (FRIEncoder::encode, encoder.rs:87-109)
  *   fri_frv_decode      container bytes -> host pixels: fri_frv_unpack, then dequantization + inverse
  *                       transform on the device (FRIDecoder::decode, decoder.rs:48-59)
  * FRI_E_UNSUPPORTED where the reference itself panics: a residual outside the 1024-symbol alphabet
  * (entropy_coding.rs:99), or an image size whose sort_lattice scan asserts (wavelet_transform.rs:701).
  */
 int fri_fit_parameters(fri_plan *plan, const int32_t *coefs, float *value_params, float *width_params);
+int fri_fit_device(fri_plan *plan, const int32_t *d_coefs, float *value_params, float *width_params, void *stream);
 int fri_predict_host(fri_plan *plan, const int32_t *coefs, const float *value_params, const float *width_params,
                      uint8_t *bucket, int32_t *pred, uint16_t *sym, uint32_t *hist, uint32_t *overflow);
 int fri_frv_pack(fri_plan *plan, int colorspace, const float *value_params, const float *width_params,

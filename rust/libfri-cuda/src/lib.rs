@@ -66,6 +66,7 @@ extern "C" {
     fn fri_decode_tq_emit10(plan: *mut FriPlan, streams: *const u8, n_frames: u32, q: *const i32, dequant_mode: c_int, pixels: *mut c_void) -> c_int;
     fn fri_predict_device(plan: *mut FriPlan, d_coefs: *const i32, n_frames: u32, value_params: *const f32, width_params: *const f32, d_bucket: *mut u8, d_pred: *mut i32, d_sym: *mut u16, d_hist: *mut u32, d_overflow: *mut u32, stream: *mut c_void) -> c_int;
     fn fri_fit_parameters(plan: *mut FriPlan, coefs: *const i32, value_params: *mut f32, width_params: *mut f32) -> c_int;
+    fn fri_fit_device(plan: *mut FriPlan, d_coefs: *const i32, value_params: *mut f32, width_params: *mut f32, stream: *mut c_void) -> c_int;
     fn fri_predict_host(plan: *mut FriPlan, coefs: *const i32, value_params: *const f32, width_params: *const f32, bucket: *mut u8, pred: *mut i32, sym: *mut u16, hist: *mut u32, overflow: *mut u32) -> c_int;
     fn fri_frv_pack(plan: *mut FriPlan, colorspace: c_int, value_params: *const f32, width_params: *const f32, bucket: *const u8, sym: *const u16, hist: *const u32, out: *mut *mut u8, out_len: *mut usize) -> c_int;
     fn fri_frv_unpack(plan: *mut FriPlan, bytes: *const u8, len: usize, coefs: *mut i32) -> c_int;
@@ -319,6 +320,14 @@ impl Plan {
         want_len("coefs", coefs.len(), self.coefs_per_frame)?;
         let (mut v, mut w) = (vec![[[0f32; 6]; 3]; self.channels], vec![[[0f32; 6]; 3]; self.channels]);
         check(unsafe { fri_fit_parameters(self.raw, coefs.as_ptr(), v.as_mut_ptr() as *mut f32, w.as_mut_ptr() as *mut f32) })?;
+        Ok((v, w))
+    }
+    /// The same fit for one frame resident on the device (sums by a kernel, solve on the host; synchronizes `stream`).
+    /// # Safety
+    /// `d_coefs` must be a device pointer to one frame of dense blocks on this plan's device.
+    pub unsafe fn fit_device(&mut self, d_coefs: *const i32, stream: *mut c_void) -> Result<(Vec<[[f32; 6]; 3]>, Vec<[[f32; 6]; 3]>), String> {
+        let (mut v, mut w) = (vec![[[0f32; 6]; 3]; self.channels], vec![[[0f32; 6]; 3]; self.channels]);
+        check(fri_fit_device(self.raw, d_coefs, v.as_mut_ptr() as *mut f32, w.as_mut_ptr() as *mut f32, stream))?;
         Ok((v, w))
     }
     /// Host predictor (what the serial entropy decoder evaluates): see include/fri_cuda.h for the array shapes.

@@ -141,6 +141,27 @@ def test_frv_encode_decode_on_the_device(shape, smooth):
         assert np.array_equal(plan.frv_decode(dq, q), want)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,smooth", [((270, 480, 3), True), ((512, 512, 1), True), ((300, 700, 3), False), ((1080, 1920, 3), True)],
+                         ids=["270x480x3", "512x512x1", "700x300x3-noise", "1080p"])
+def test_device_fit_is_bit_identical_to_the_host_fit(shape, smooth):
+    """fri_fit_device sums the normal equations on the device in exact integers (any order), the host fit sums
+    the same integers: the solved parameters must agree bit for bit, with and without a quantizer."""
+    import torch
+    h, w, c = shape
+    img = (smooth_image if smooth else uniform_image)(h, w, c, seed=h + 1)
+    with capi.Plan(w, h, c) as plan:
+        for q in (ONES, smallest_layer_q(3)):
+            coefs = plan.encode(img, q)[0]
+            d = torch.from_numpy(coefs).cuda()
+            vp, wp = plan.fit_device(d.data_ptr())
+            assert plan.last_launches == 2
+            hv, hw = plan.fit_parameters(coefs)
+            assert np.array_equal(vp.view(np.uint32), hv.view(np.uint32))
+            assert np.array_equal(wp.view(np.uint32), hw.view(np.uint32))
+            assert np.isfinite(vp).all() and np.isfinite(wp).all() and np.abs(vp).max() > 0
+
+
 def test_stage_mirror_of_the_entropy_stages_on_cpu():
     """stages.prediction / entropy_coding / serialize keep the reference's names and hand-offs; on a host-only plan
     (device = -1) everything behind the quantizer runs, fed with oracle coefficients."""
