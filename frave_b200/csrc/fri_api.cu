@@ -98,6 +98,8 @@ struct fri_plan {
     // prediction tables (computed on first use)
     bool predict_ready = false;
     void *d_pred_tile_at = nullptr, *d_pred_centers = nullptr, *d_pred_lut = nullptr, *d_pred_off = nullptr;
+    void *h_dense = nullptr;    // pinned staging of fri_frv_decode: one frame of dense blocks
+    void *h_symbols = nullptr;  // pinned staging of fri_frv_encode: [C][count] u16 symbols, then [C][count] u8 buckets
     PredictTables predict_tables;
     // host lattice index for the host predictor / entropy decoder (computed on first use)
     bool lattice_ready = false;
@@ -416,6 +418,8 @@ void fri_plan_destroy(fri_plan *p)
         if (p->d_stage_list) cudaFree(p->d_stage_list);
         for (void *d : {p->d_pred_tile_at, p->d_pred_centers, p->d_pred_lut, p->d_pred_off})
             if (d) cudaFree(d);
+        if (p->h_symbols) cudaFreeHost(p->h_symbols);
+        if (p->h_dense) cudaFreeHost(p->h_dense);
     }
     delete p;
 }
@@ -1420,23 +1424,25 @@ int fri_frv_encode(fri_plan *p, const void *pixels, const int32_t *q, int colors
         std::memcpy(prm.value, vp.data(), sizeof(float) * 18 * C);
         std::memcpy(prm.width, wp.data(), sizeof(float) * 18 * C);
         uint8_t *d_bucket = nullptr;
-        int32_t *d_pred = nullptr;
+        int32_t *d_pred = nullptr;  // the predictions themselves are not needed: the symbols carry the residuals
         uint16_t *d_sym = nullptr;
         uint32_t *d_hist = nullptr;
         if ((rc = pool_alloc(p, reinterpret_cast<void **>(&d_bucket), (size_t)C * count, st))) return rc;
-        if ((rc = pool_alloc(p, reinterpret_cast<void **>(&d_pred), (size_t)C * count * sizeof(int32_t), st))) return rc;
         if ((rc = pool_alloc(p, reinterpret_cast<void **>(&d_sym), (size_t)C * count * sizeof(uint16_t), st))) return rc;
         if ((rc = pool_alloc(p, reinterpret_cast<void **>(&d_hist), (n_hist + 1) * sizeof(uint32_t), st))) return rc;
-        std::vector<uint8_t> bucket((size_t)C * count);
-        std::vector<uint16_t> sym((size_t)C * count);
+        // buckets + symbols come back through pinned memory kept with the plan (150 MB for 4096 x 4096 x 3:
+        // pageable destinations cost 20x the copy time)
+        if (!p->h_symbols) FRI_CUDA(cudaHostAlloc(&p->h_symbols, (size_t)C * count * 3 + 16, cudaHostAllocDefault));
+        uint16_t *sym = static_cast<uint16_t *>(p->h_symbols);
+        uint8_t *bucket = reinterpret_cast<uint8_t *>(sym + (size_t)C * count);
         std::vector<uint32_t> hist(n_hist + 1);
         FRI_CUDA(cudaMemsetAsync(d_hist, 0, (n_hist + 1) * sizeof(uint32_t), st));
         FRI_CUDA(launch_predict(g, p->tables, p->emit_tables, p->predict_tables, prm, count, s.d_coefs, 1, d_bucket, d_pred, d_sym,
                                 d_hist, d_hist + n_hist, st, &p->last_launches));
-        FRI_CUDA(cudaMemcpyAsync(bucket.data(), d_bucket, bucket.size(), cudaMemcpyDeviceToHost, st));
-        FRI_CUDA(cudaMemcpyAsync(sym.data(), d_sym, sym.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+        FRI_CUDA(cudaMemcpyAsync(bucket, d_bucket, (size_t)C * count, cudaMemcpyDeviceToHost, st));
+        FRI_CUDA(cudaMemcpyAsync(sym, d_sym, (size_t)C * count * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
         FRI_CUDA(cudaMemcpyAsync(hist.data(), d_hist, hist.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        for (void *d : {(void *)d_bucket, (void *)d_pred, (void *)d_sym, (void *)d_hist}) cudaFreeAsync(d, st);
+        for (void *d : {(void *)d_bucket, (void *)d_sym, (void *)d_hist}) cudaFreeAsync(d, st);
         FRI_CUDA(cudaEventRecord(s.compute_done, st));
         FRI_CUDA(cudaEventRecord(s.out_done, st));
         s.used = true;
@@ -1445,7 +1451,7 @@ int fri_frv_encode(fri_plan *p, const void *pixels, const int32_t *q, int colors
             return fail(FRI_E_UNSUPPORTED, "%u residual(s) fall outside the 1024-symbol alphabet (the reference panics at entropy_coding.rs:99)",
                         hist[n_hist]);
         // 4. rANS + container on the host
-        return fri_frv_pack(p, colorspace, vp.data(), wp.data(), bucket.data(), sym.data(), hist.data(), out, out_len);
+        return fri_frv_pack(p, colorspace, vp.data(), wp.data(), bucket, sym, hist.data(), out, out_len);
     } catch (const std::bad_alloc &) {
         return fail(FRI_E_NOMEM, "out of host memory");
     }
@@ -1456,17 +1462,15 @@ int fri_frv_decode(fri_plan *p, const uint8_t *bytes, size_t len, const int32_t 
     int rc = enter_device(p);
     if (rc) return rc;
     if (!bytes || !pixels) return fail(FRI_E_INVALID, "NULL argument");
-    try {
-        std::vector<int32_t> coefs((size_t)p->plan.geo.coefs_per_frame);
-        if ((rc = fri_frv_unpack(p, bytes, len, coefs.data()))) return rc;  // entropy decoding: serial, host (entropy_coding.rs:354-449)
-        const bool was_async = p->async_mode;
-        p->async_mode = false;  // `coefs` is a local: the copies must have finished before it goes away
-        rc = fri_decode_tq(p, coefs.data(), 1, q, dequant_mode, pixels);
-        p->async_mode = was_async;
-        return rc;
-    } catch (const std::bad_alloc &) {
-        return fail(FRI_E_NOMEM, "out of host memory");
-    }
+    // the entropy decoder writes into pinned memory kept with the plan: the upload then runs at link speed
+    if (!p->h_dense) FRI_CUDA(cudaHostAlloc(&p->h_dense, (size_t)p->plan.geo.coefs_per_frame * sizeof(int32_t) + 16, cudaHostAllocDefault));
+    int32_t *coefs = static_cast<int32_t *>(p->h_dense);
+    if ((rc = fri_frv_unpack(p, bytes, len, coefs))) return rc;  // entropy decoding: serial, host (entropy_coding.rs:354-449)
+    const bool was_async = p->async_mode;
+    p->async_mode = false;  // the staging buffer is reused by the next call: the copies must have finished on return
+    rc = fri_decode_tq(p, coefs, 1, q, dequant_mode, pixels);
+    p->async_mode = was_async;
+    return rc;
 }
 
 int fri_host_alloc(void **out, size_t bytes)

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <stdexcept>
 #include <thread>
 
 namespace fri {
@@ -37,8 +38,11 @@ static int32_t f32_as_i32(float x)  // Rust `as i32`
 
 int assign_bucket(float width)  // prediction.rs:55-68
 {
+    // thresholds 3, 5, 6, 8, 12, 16, 20, 25, 30 — as a table: the serial entropy decoder calls this per symbol and
+    // a compare chain mispredicts on every other one
+    static const uint8_t kBucket[31] = {0, 0, 0, 1, 1, 2, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 6, 6, 6, 6, 7, 7, 7, 7, 7, 8, 8, 8, 8, 8, 9};
     const uint32_t w = f32_as_u32(width);
-    return w < 3 ? 0 : w < 5 ? 1 : w < 6 ? 2 : w < 8 ? 3 : w < 12 ? 4 : w < 16 ? 5 : w < 20 ? 6 : w < 25 ? 7 : w < 30 ? 8 : 9;
+    return kBucket[w < 30 ? w : 30];
 }
 
 float width_from_bucket(int bucket)  // prediction.rs:70-84
@@ -184,6 +188,39 @@ void RansEncoderMulti::put_at(int index, uint32_t start, uint32_t freq, uint32_t
     state_[index] = ((x / freq) << scale_bits) + (x % freq) + start;
 }
 
+RansEncSymbol::RansEncSymbol(uint32_t start, uint32_t freq, uint32_t scale_bits)
+{
+    x_max = ((kRansL >> scale_bits) << 32) * freq;
+    codable = 1;
+    cmpl_freq = (1ull << scale_bits) - freq;  // modulo 2^64: the reference's wrapped last frequency may exceed 2^scale_bits
+    if (freq < 2) {  // x / 1: mul_hi(x, 2^64 - 1) = x - 1, the bias makes up for it
+        rcp_freq = ~0ull;
+        rcp_shift = 0;
+        bias = (uint64_t)start + (1ull << scale_bits) - 1;
+    } else {
+        uint32_t shift = 0;
+        while (freq > (1ull << shift)) ++shift;
+        rcp_freq = (uint64_t)((((unsigned __int128)1 << (shift + 63)) + freq - 1) / freq);
+        rcp_shift = shift - 1;
+        bias = start;
+    }
+}
+
+void RansEncoderMulti::put_at(int index, const RansEncSymbol &s)
+{
+    uint64_t x = state_[index];
+    if (x >= s.x_max) {
+        words_.push_back((uint32_t)x);
+        x >>= 32;
+    }
+    // x < 2^63 and rcp_freq = ceil(2^(63 + shift) / freq): the quotient is exact (Alverson), so this is
+    // ((x / freq) << scale_bits) + x % freq + start without the division
+    const uint64_t q = (uint64_t)(((unsigned __int128)x * s.rcp_freq) >> 64) >> s.rcp_shift;
+    state_[index] = x + s.bias + q * s.cmpl_freq;
+}
+
+void RansEncoderMulti::reserve_words(size_t n) { words_.reserve(n); }
+
 void RansEncoderMulti::flush_all()
 {
     for (uint64_t x : state_) {  // index order; each flush lands in front of the previous one
@@ -243,43 +280,89 @@ void RansDecoderMulti::advance_at(int index, uint32_t start, uint32_t freq, uint
 // ---------------------------------------------------------------------------------------------
 // host predictor (prediction.rs:86-207, context_modeling.rs:25-77, wavelet_transform.rs:97-177)
 // ---------------------------------------------------------------------------------------------
+// The neighbour of a node is a fixed (tile step, heap index) pair per heap index: positions are tile centre +
+// leaf offset + neighbour vector, and the residue map / leaf offsets do not depend on the tile.  The table is
+// built by running the lattice queries the reference makes (global_position_map[level].get) for a virtual tile
+// at the anchor; per query only "does that tile exist" is left for run time.
 Predictor::Predictor(const LatticeIndex &l, const int32_t *c, int ch) : lat(l), centers(c), channels(ch)
 {
     for (int d = 0; d < 10; ++d) {
         for (int j = 0; j < 6; ++j) nearby[d][j] = Vec2{0, 0};
         if (d >= 1) nearby_vectors(d, nearby[d]);
     }
+    int max_t = -1;
+    for (int32_t t : lat.tile_at) max_t = std::max(max_t, (int)t);
+    adjacent.assign(((size_t)max_t + 1) * 9, -1);
+    for (int b = 0; b < lat.nb; ++b)
+        for (int a = 0; a < lat.na; ++a) {
+            const int32_t t = lat.tile_at[(size_t)b * lat.na + a];
+            if (t < 0) continue;
+            for (int db = -1; db <= 1; ++db)
+                for (int da = -1; da <= 1; ++da) {
+                    const int aa = a + da, bb = b + db;
+                    if (aa >= 0 && bb >= 0 && aa < lat.na && bb < lat.nb)
+                        adjacent[(size_t)t * 9 + (db + 1) * 3 + (da + 1)] = lat.tile_at[(size_t)bb * lat.na + aa];
+                }
+        }
+    constexpr Vec2 l9 = kLiterals[kBaseDepth], l10 = kLiterals[kBaseDepth + 1];
+    auto ref_at = [&](int level, int x, int y) {  // LatticeIndex::node_at for a tile centred at the anchor
+        NodeStep r{-1, 4};
+        const int k = lat.lut[LatticeIndex::mod512((x - lat.ax) + 181 * (y - lat.ay))];
+        const int low = kBaseDepth - level;
+        if (k & ((1 << low) - 1)) return r;
+        const int64_t dx = x - lat.off[k].x - lat.ax, dy = y - lat.off[k].y - lat.ay;
+        const int64_t na_ = dx * l10.y - (int64_t)l10.x * dy, nb_ = (int64_t)l9.x * dy - dx * l9.y;
+        if (na_ % 512 != 0 || nb_ % 512 != 0) return r;
+        const int64_t da = na_ / 512, db = nb_ / 512;
+        if (da < -1 || da > 1 || db < -1 || db > 1) throw std::logic_error("a neighbour node lies beyond the adjacent tiles");
+        r.heap = (int16_t)((1 << level) + (k >> low));
+        r.cell = (int8_t)((db + 1) * 3 + (da + 1));
+        return r;
+    };
+    for (int heap = 0; heap < kTileLeaves; ++heap) {
+        HeapSteps &hs = steps[heap];
+        for (NodeStep &n : hs.regular) n = NodeStep{-1, 4};
+        for (NodeStep &n : hs.alt) n = NodeStep{-1, 4};
+        for (NodeStep &n : hs.probe) n = NodeStep{-1, 4};
+        if (heap < 2) continue;
+        const int level = 31 - __builtin_clz((unsigned)heap), d = kBaseDepth - level;
+        const Vec2 o = lat.off[(heap - (1 << level)) << d];
+        const int px = lat.ax + o.x, py = lat.ay + o.y;
+        const Vec2 *nv = nearby[d];
+        const Vec2 q[6] = {{px + nv[4].x, py + nv[4].y}, {px + nv[5].x, py + nv[5].y}, {px + nv[0].x, py + nv[0].y},
+                           {px + nv[1].x, py + nv[1].y}, {px + nv[3].x, py + nv[3].y}, {px + nv[2].x, py + nv[2].y}};
+        for (int j = 0; j < 6; ++j) hs.regular[j] = ref_at(level, q[j].x, q[j].y);
+        if (d == 2) {
+            hs.alt[0] = ref_at(level, px - 1 + nv[4].x, py - 1 + nv[4].y);  // up-left
+            hs.alt[1] = ref_at(level, px - 1, py - 1);                      // up-right
+            hs.alt[2] = ref_at(level, px + 1, py + 1);                      // down-left
+            hs.alt[3] = ref_at(level, px + 1 + nv[1].x, py + 1 + nv[1].y);  // down-right
+            hs.probe[0] = ref_at(2, px + nv[3].x, py + nv[3].y);            // the level-2 map, as written in the reference
+            hs.probe[1] = ref_at(2, px + 1, py + 1);
+            hs.probe[2] = ref_at(2, px + nv[0].x, py + nv[0].y);
+            hs.probe[3] = ref_at(2, px - 1, py - 1);
+        }
+    }
+}
+
+inline int Predictor::step_tile(int tile, const NodeStep &n) const
+{
+    return n.heap < 0 ? -1 : adjacent[(size_t)tile * 9 + n.cell];
 }
 
 void Predictor::neighbour_values(const int32_t *coefs, int tile, int heap, int ch, int32_t v[6]) const
 {
-    const int level = 31 - __builtin_clz((unsigned)heap);
-    const int d = kBaseDepth - level;
-    const Vec2 o = lat.off[(heap - (1 << level)) << d];
-    const int px = centers[2 * tile] + o.x, py = centers[2 * tile + 1] + o.y;
-    const Vec2 *nv = nearby[d];
-    auto contains2 = [&](int x, int y) {
-        int t, h;
-        return lat.node_at(2, x, y, t, h);  // the level-`depth` (= 2) map, as written in the reference
-    };
-    bool alt_up = false, alt_down = false;
-    if (d == 2) {
-        alt_down = !contains2(px + nv[3].x, py + nv[3].y) && contains2(px + 1, py + 1);
-        alt_up = !contains2(px + nv[0].x, py + nv[0].y) && contains2(px - 1, py - 1);
+    const HeapSteps &hs = steps[heap];
+    const NodeStep *sel[6] = {&hs.regular[0], &hs.regular[1], &hs.regular[2], &hs.regular[3], &hs.regular[4], &hs.regular[5]};
+    if (heap >= 128 && heap < 256) {  // level 7 (depth 2): wavelet_transform.rs:115-177
+        const bool alt_down = step_tile(tile, hs.probe[0]) < 0 && step_tile(tile, hs.probe[1]) >= 0;
+        const bool alt_up = step_tile(tile, hs.probe[2]) < 0 && step_tile(tile, hs.probe[3]) >= 0;
+        if (alt_up) { sel[1] = &hs.alt[0]; sel[2] = &hs.alt[1]; }
+        if (alt_down) { sel[4] = &hs.alt[2]; sel[5] = &hs.alt[3]; }
     }
-    int qx[6], qy[6];
-    qx[0] = px + nv[4].x; qy[0] = py + nv[4].y;
-    if (alt_up) { qx[1] = px - 1 + nv[4].x; qy[1] = py - 1 + nv[4].y; qx[2] = px - 1; qy[2] = py - 1; }
-    else { qx[1] = px + nv[5].x; qy[1] = py + nv[5].y; qx[2] = px + nv[0].x; qy[2] = py + nv[0].y; }
-    qx[3] = px + nv[1].x; qy[3] = py + nv[1].y;
-    if (alt_down) { qx[4] = px + 1; qy[4] = py + 1; qx[5] = px + 1 + nv[1].x; qy[5] = py + 1 + nv[1].y; }
-    else { qx[4] = px + nv[3].x; qy[4] = py + nv[3].y; qx[5] = px + nv[2].x; qy[5] = py + nv[2].y; }
     for (int j = 0; j < 6; ++j) {
-        int t, h;
-        if (lat.node_at(level, qx[j], qy[j], t, h))
-            v[j] = coefs[(((size_t)t * channels + ch) << kBaseDepth) + (j < 3 ? h : h >> 1)];
-        else
-            v[j] = 0;
+        const int t = step_tile(tile, *sel[j]);
+        v[j] = t >= 0 ? coefs[(((size_t)t * channels + ch) << kBaseDepth) + (j < 3 ? sel[j]->heap : sel[j]->heap >> 1)] : 0;
     }
 }
 
@@ -479,16 +562,24 @@ std::string entropy_encode_channel(const uint16_t *sym, const uint8_t *bucket, s
 {
     out.contexts.clear();
     for (int b = 0; b < kContexts; ++b) out.contexts.push_back(context_from_counts(hist + (size_t)b * kAlphabet, b));
+    // per (context, symbol): the division-free form of the coding step
+    std::vector<RansEncSymbol> table((size_t)kContexts * kAlphabet);
+    for (int b = 0; b < kContexts; ++b) {
+        const AnsContext &c = out.contexts[b];
+        for (int s = 0; s < kAlphabet; ++s)
+            if (c.freqs[s] != 0 && c.max_freq_bits <= 31) table[(size_t)b * kAlphabet + s] = RansEncSymbol(c.cdf[s], c.freqs[s], c.max_freq_bits);
+    }
     RansEncoderMulti enc(kContexts);
+    enc.reserve_words(count / 2 + 64);
     for (size_t k = count; k-- > 0;) {  // entropy_coding.rs:332-334: pushed in reverse
         const uint32_t s = sym[k];
         const int b = bucket[k];
         if (s >= (uint32_t)kAlphabet)
             return "a residual falls outside the 1024-symbol alphabet (the reference panics at entropy_coding.rs:99)";
         if (b >= kContexts) return "context bucket out of range";
-        const AnsContext &c = out.contexts[b];
-        if (c.freqs[s] == 0 || c.max_freq_bits > 31) return "symbol with zero model frequency (cannot be coded)";
-        enc.put_at(b, c.cdf[s], c.freqs[s], c.max_freq_bits);
+        const RansEncSymbol &e = table[(size_t)b * kAlphabet + s];
+        if (!e.codable) return "symbol with zero model frequency (cannot be coded)";
+        enc.put_at(b, e);
     }
     enc.flush_all();
     out.data = enc.data();
@@ -503,6 +594,25 @@ std::string entropy_decode_channel(const ChannelPayload &in, const Predictor &pr
         if (c.max_freq_bits > 31) return "context with an impossible max_freq_bits";
     RansDecoderMulti dec(kContexts, in.data.data(), in.data.size());
     const int C = pred.channels;
+    // slot -> symbol: a coarse table over the top kCoarseBits bits of the slot bounds the search in the cdf
+    constexpr int kCoarseBits = 12;
+    struct Coarse {
+        int shift;
+        std::vector<uint16_t> first;  // symbol owning the first slot of every cell, plus a sentinel
+    };
+    std::vector<Coarse> coarse(kContexts);
+    for (int b = 0; b < kContexts; ++b) {
+        const AnsContext &c = in.contexts[b];
+        const int bits = (int)c.max_freq_bits, cells_bits = std::min(bits, kCoarseBits);
+        coarse[b].shift = bits - cells_bits;
+        coarse[b].first.resize(((size_t)1 << cells_bits) + 1);
+        for (size_t i = 0; i < ((size_t)1 << cells_bits); ++i) {
+            const uint32_t slot = (uint32_t)(i << coarse[b].shift);
+            const int sym = (int)(std::upper_bound(c.cdf.begin(), c.cdf.end(), slot) - c.cdf.begin()) - 1;
+            coarse[b].first[i] = (uint16_t)std::max(sym, 0);
+        }
+        coarse[b].first.back() = kAlphabet - 1;
+    }
     for (uint32_t src : emit_src) {
         const int tile = (int)(src >> kBaseDepth), heap = (int)(src & (kTileLeaves - 1));
         int bucket;
@@ -512,8 +622,13 @@ std::string entropy_decode_channel(const ChannelPayload &in, const Predictor &pr
         const AnsContext &c = in.contexts[bucket];
         const int pos = kContexts - bucket - 1;  // entropy_coding.rs:239
         const uint32_t got = dec.get_at(pos, c.max_freq_bits);
-        // find_nearest_or_equal + the "last index with that cdf" walk (:244-255): the symbol owning `got`
-        int symbol = (int)(std::upper_bound(c.cdf.begin(), c.cdf.end(), got) - c.cdf.begin()) - 1;
+        // find_nearest_or_equal + the "last index with that cdf" walk (:244-255): the symbol owning `got`,
+        // i.e. the last index whose cdf is <= got; it lies between the owners of the cell's first slot and of
+        // the next cell's
+        const Coarse &cs = coarse[bucket];
+        const uint32_t cell = got >> cs.shift;
+        const uint32_t *lo = c.cdf.data() + cs.first[cell], *hi = c.cdf.data() + cs.first[cell + 1] + 1;
+        int symbol = (int)(std::upper_bound(lo, hi, got) - c.cdf.data()) - 1;
         if (symbol < 0) symbol = 0;
         if (c.freqs[symbol] == 0) return "corrupt stream: decoded a symbol with zero frequency";
         dec.advance_at(pos, c.cdf[symbol], c.freqs[symbol], c.max_freq_bits);

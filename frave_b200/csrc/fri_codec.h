@@ -52,10 +52,19 @@ AnsContext context_from_counts(const uint32_t *counts, int bucket);
 AnsContext context_from_header(uint32_t max_freq_bits, std::vector<uint16_t> off_distribution_values, int bucket);
 
 // N interleaved 64-bit rANS coders sharing one word stream (rans::B64RansEncoderMulti / DecoderMulti).
+// One (start, freq) of a context prepared for coding without a division (ryg_rans' Rans64EncSymbol).
+struct RansEncSymbol {
+    uint64_t rcp_freq = 0, bias = 0, cmpl_freq = 0, x_max = 0;
+    uint32_t rcp_shift = 0, codable = 0;  // codable == 0: zero frequency
+    RansEncSymbol() = default;
+    RansEncSymbol(uint32_t start, uint32_t freq, uint32_t scale_bits);
+};
 class RansEncoderMulti {
 public:
     explicit RansEncoderMulti(int n);
     void put_at(int index, uint32_t start, uint32_t freq, uint32_t scale_bits);
+    void put_at(int index, const RansEncSymbol &s);  // the same step, division-free
+    void reserve_words(size_t n);
     void flush_all();
     std::vector<uint8_t> data() const;  // the bytes in decoding order
 private:
@@ -83,7 +92,12 @@ struct Predictor {
     const int32_t *centers;  // [n_tiles][2]
     int channels;
     Vec2 nearby[10][6];
+    struct NodeStep { int16_t heap; int8_t cell; };  // heap < 0: no node there in any tile; cell: (db + 1) * 3 + (da + 1)
+    struct HeapSteps { NodeStep regular[6], alt[4], probe[4]; };
+    HeapSteps steps[kTileLeaves];       // per heap index: where its neighbours sit, relative to the tile
+    std::vector<int32_t> adjacent;      // [n_tiles][9] plan index of the tile one lattice step away, -1 if none
     Predictor(const LatticeIndex &l, const int32_t *c, int ch);
+    int step_tile(int tile, const NodeStep &n) const;
     // neighbour values of the level-`level` node `heap` of `tile` (context_modeling.rs:25-77), levels 1..8
     void neighbour_values(const int32_t *coefs, int tile, int heap, int ch, int32_t v[6]) const;
     void lf(const int32_t *coefs, int tile, int heap, int ch, int &bucket, int32_t &prediction) const;

@@ -170,7 +170,7 @@ fri_predict_kernel(const __grid_constant__ PredictTables pt, const __grid_consta
             const unsigned sym = residual >= 0 ? 2u * (unsigned)residual : (unsigned)(-2 * residual - 1);  // pack_signed
             const size_t e = out_base + __ldg(dst + k);
             bucket_out[e] = (uint8_t)bucket;
-            pred_out[e] = prediction;
+            if (pred_out) pred_out[e] = prediction;
             sym_out[e] = (uint16_t)min(sym, 0xffffu);
             if (sym < (unsigned)kAlphabet) atomicAdd(&s_hist[bucket * kAlphabet + sym], 1u);
             else if (overflow) atomicAdd(overflow, 1u);  // the reference indexes freqs[sym] and panics (entropy_coding.rs:99)

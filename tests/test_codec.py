@@ -66,6 +66,28 @@ def test_context_tables_are_rebuilt_identically_from_the_header():
         assert len(ctx.off_distribution_values) > 0 and sum(ctx.freqs) == 1 << ctx.max_freq_bits
 
 
+@pytest.mark.parametrize("seed", [0, 1])
+def test_rans_bytes_for_arbitrary_symbol_streams(seed):
+    """The division-free coding step and the decoder's coarse slot table against the Python restatement's plain
+    integer arithmetic, on symbol / bucket streams that do not come from an image: wide range of frequencies
+    (2^17 symbols per context at most), rare symbols far in the tail."""
+    h, w, c = 300, 420, 1
+    rng = np.random.default_rng(seed)
+    with capi.Plan(w, h, c, device=-1) as plan:
+        n = plan.emission_count()
+        b = rng.integers(0, 10, size=(c, n)).astype(np.uint8)
+        scale = np.array([0.7, 1.5, 3, 5, 8, 12, 20, 40, 80, 160])[b]
+        s = np.minimum(np.abs(rng.laplace(0, scale)).astype(np.int64), 1023).astype(np.uint16)
+        if seed:
+            b[:] = 3  # one context only: the other nine stay at their unused default
+        hist = np.zeros((c, 10, 1024), np.uint32)
+        np.add.at(hist[0], (b[0], s[0]), 1)
+        vp = rng.normal(size=(c, 3, 6)).astype(np.float32)
+        wp = rng.normal(size=(c, 3, 6)).astype(np.float32)
+        data = plan.frv_pack(vp, wp, b, s, hist)
+        assert data == EN.encode(h, w, 1, vp, wp, b, s, hist)
+
+
 def test_symbols_outside_the_alphabet_are_refused():
     h, w, c = 48, 64, 1
     with capi.Plan(w, h, c, device=-1) as plan:
