@@ -277,6 +277,9 @@ int fri_predict_device(fri_plan *plan, const int32_t *d_coefs, uint32_t n_frames
  *                       (FRIEncoder::encode, encoder.rs:87-109)
  *   fri_frv_decode      container bytes -> host pixels: fri_frv_unpack, then dequantization + inverse
  *                       transform on the device (FRIDecoder::decode, decoder.rs:48-59)
+ * fri_frv_encode / fri_frv_decode keep pinned staging memory with the plan from their first call on (3 bytes per
+ * emitted coefficient for the encoder, one frame of dense blocks for the decoder; released by fri_plan_destroy),
+ * and — like every host-buffer entry point — serve one caller per plan handle at a time.
  * FRI_E_UNSUPPORTED where the reference itself panics: a residual outside the 1024-symbol alphabet
  * (entropy_coding.rs:99), or an image size whose sort_lattice scan asserts (wavelet_transform.rs:701).
  */
