@@ -731,14 +731,148 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
         dist.destroy_process_group()
 
 
+def run_image_split(args, rank: int, local_rank: int, world: int) -> None:
+    """--workload image16k: ONE 16384x16384 16-bit single-channel image (BASELINE.json configs[3], depth 9) split over
+    the GPUs by contiguous ranges of tile groups.  Strong scaling.  A step on every rank: transform the
+    rank's tiles from its band of pixel rows, invert them into a band that starts from zero in the rows shared with
+    a neighbour, then the path's one exchange step: the overlap rows (tiles straddle the cut) go to the neighbour
+    and are merged by addition (NCCL send / recv).  Device-resident; the max over ranks is the step time."""
+    import torch
+    import torch.distributed as dist
+
+    from frave_b200 import capi, sharding
+
+    if capi.device_count() < 1:
+        raise RuntimeError("bench.py needs a CUDA device: libfri_cuda has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    iw, ih = (16384, 16384) if not args.shape else tuple(int(v) for v in args.shape.lower().split("x")[:2])
+    q = np.ones(32, np.int32)  # 16-bit extension: transform only (no container), the reference's all-ones matrix
+    t0 = time.perf_counter()
+    plan = capi.Plan(iw, ih, 1, sample_bytes=2, device=local_rank)
+    plan_build_ms = 1e3 * (time.perf_counter() - t0)
+    part = sharding.shard_image(plan, rank, world)
+    shared = sharding.overlaps(plan, rank, world)
+    t_lo, t_hi, r0, r1 = part["tile_begin"], part["tile_end"], part["row_begin"], part["row_end"]
+    stream = torch.cuda.current_stream().cuda_stream
+    # every rank generates the same image row by row block (seeded per block of rows) and keeps only its band
+    n_sets = 2
+    block_rows = 1024
+    bands = []
+    for s_ in range(n_sets):
+        band = torch.empty((r1 - r0, iw), dtype=torch.int16, device=dev)
+        for b0 in range(r0 // block_rows * block_rows, r1, block_rows):
+            g_ = torch.Generator(device=dev).manual_seed(77 + 1000 * s_ + b0)
+            rows = torch.randint(0, 65536, (block_rows, iw), generator=g_, device=dev, dtype=torch.int32).to(torch.int16)
+            lo, hi = max(b0, r0), min(b0 + block_rows, r1)
+            band[lo - r0:hi - r0] = rows[lo - b0:hi - b0]
+        bands.append(band)
+    coefs = [torch.empty((t_hi - t_lo, 1, 512), dtype=torch.int32, device=dev) for _ in range(n_sets)]
+    outs = [torch.empty((r1 - r0, iw), dtype=torch.int16, device=dev) for _ in range(n_sets)]
+    recv = {peer: torch.empty((hi - lo, iw), dtype=torch.int16, device=dev) for peer, lo, hi in shared}
+    launches = 0
+
+    def step(i: int) -> None:
+        nonlocal launches
+        a = i % n_sets
+        plan.encode_device_part(bands[a].data_ptr(), coefs[a].data_ptr(), rank, world, q, stream)
+        launches += plan.last_launches
+        for _, lo, hi in shared:  # the rows a neighbour also writes into start from zero
+            outs[a][lo - r0:hi - r0].zero_()
+        plan.decode_device_part(coefs[a].data_ptr(), outs[a].data_ptr(), rank, world, q, False, stream)
+        launches += plan.last_launches
+        if shared:
+            ops = []
+            for peer, lo, hi in shared:
+                ops.append(dist.P2POp(dist.isend, outs[a][lo - r0:hi - r0].view(torch.uint8), peer))  # (NCCL has no int16)
+                ops.append(dist.P2POp(dist.irecv, recv[peer].view(torch.uint8), peer))
+            for w_ in dist.batch_isend_irecv(ops):
+                w_.wait()
+            for peer, lo, hi in shared:
+                outs[a][lo - r0:hi - r0] += recv[peer]  # a pixel has one owner: the other side holds zero there
+
+    # sanity (untimed): the assembled band equals the input (lossless at the all-ones matrix)
+    step(0)
+    torch.cuda.synchronize()
+    if plan.pixels_covered == iw * ih and not torch.equal(outs[0], bands[0]):
+        raise RuntimeError("sanity check failed: the split encode -> decode -> exchange is not lossless")
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    for k in range(max(args.warmup, 3)):
+        step(k)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    start.record()
+    for k in range(args.steps):
+        step(k)
+    end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    elapsed_ms = start.elapsed_time(end)
+    timed_launches = launches
+
+    def enc_only(i: int) -> None:
+        plan.encode_device_part(bands[i % n_sets].data_ptr(), coefs[i % n_sets].data_ptr(), rank, world, q, stream)
+
+    def dec_only(i: int) -> None:
+        plan.decode_device_part(coefs[i % n_sets].data_ptr(), outs[i % n_sets].data_ptr(), rank, world, q, False, stream)
+
+    reps = 40
+    enc_ms, dec_ms = b2b(enc_only, reps, torch), b2b(dec_only, reps, torch)
+    clocks = sampler.stop() if sampler else None
+    vals = torch.tensor([elapsed_ms, enc_ms, dec_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    elapsed_ms, enc_ms, dec_ms = vals.tolist()
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        alg = (t_hi - t_lo) * 512 * 6  # this rank's samples x (2 B pixel + 4 B coefficient)
+
+        def roof(ms: float, kernel: str) -> dict:
+            ach = alg / (ms * 1e-3) / 1e9
+            return {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "algorithmic_bytes": alg, "avg_launch_ms": ms, "peak_source": peak_src,
+                    "timing": f"{reps} back-to-back launches of rank 0's part between two CUDA events (max over ranks)"}
+
+        r_enc, r_dec = roof(enc_ms, "fri_encode_kernel<1,u16>"), roof(dec_ms, "fri_decode_kernel<1,u16>")
+        halo = sum(hi - lo for _, lo, hi in shared)
+        line = {
+            "metric": METRIC, "value": iw * ih * args.steps / (elapsed_ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
+            "config": {"workload": f"one {iw}x{ih}x1 u16 synthetic image (BASELINE.json configs[3], depth 9) split over {world} GPU(s) by "
+                                   "contiguous ranges of tile groups; step = encode + decode of every rank's tiles + exchange of the "
+                                   "overlap rows between neighbours (NCCL send/recv, merged by addition)",
+                       "parts": world, "tiles_rank0": t_hi - t_lo, "rows_rank0": [r0, r1], "halo_rows_rank0": halo,
+                       "quant": "all ones (16-bit extension: transform only)",
+                       "l2": f"{n_sets} rotating buffer sets; rank 0's set is {(r1 - r0) * iw * 2 * 2 + (t_hi - t_lo) * 2048 >> 20} MB",
+                       "parallelism": f"tile groups of one image sharded over {world} GPU(s); one point-to-point exchange of "
+                                      f"{halo} overlap rows per rank and step"},
+            "roofline": r_enc if enc_ms >= dec_ms else r_dec, "roofline_encode": r_enc, "roofline_decode": r_dec,
+            "gpu_launches": timed_launches, "clocks": clocks, "launch": plan.launch_info(), "plan_build_ms": plan_build_ms,
+            "e2e": None, "cpu_baseline": None,
+            "note": "secondary workload (the driver's line is the default one): e2e / cpu_baseline are reported there"}
+        print(json.dumps(line), flush=True)
+    plan.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="frame", choices=["frame", "batch256"],
-                    help="frame = BASELINE.json configs[1] (default); batch256 = configs[2], 256 4K frames sharded over the ranks")
+    ap.add_argument("--workload", default="frame", choices=["frame", "batch256", "image16k"],
+                    help="frame = BASELINE.json configs[1] (default); batch256 = configs[2], 256 4K frames sharded over the ranks; "
+                         "image16k = configs[3] at depth 9, ONE 16384x16384 u16 image split over the ranks by tile-group ranges")
     ap.add_argument("--shape", default=None, help="WxHxC override for experiments (default: BASELINE.json configs[1])")
     ap.add_argument("--frames", type=int, default=1, help="frames per GPU per step (batched launch)")
     ap.add_argument("--batch-frames", type=int, default=256, help="--workload batch256: total frames (experiments only)")
@@ -771,6 +905,9 @@ def main() -> None:
         return
     if world != args.gpus and world == 1 and args.gpus > 1:
         raise SystemExit("launch N > 1 with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...")
+    if args.workload == "image16k":
+        run_image_split(args, rank, local_rank, world)
+        return
     run_b200(args, rank, local_rank, world)
 
 

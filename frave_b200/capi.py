@@ -67,6 +67,9 @@ _SYMBOLS = [
     ("fri_predict_device", C.c_int, [_P, _P, C.c_uint32, _P, _P, _P, _P, _P, _P, _P, _P]),
     ("fri_fit_parameters", C.c_int, [_P, _P, _P, _P]),
     ("fri_fit_device", C.c_int, [_P, _P, _P, _P, _P]),
+    ("fri_plan_part", C.c_int, [_P, C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, _P]),
+    ("fri_encode_tq_device_part", C.c_int, [_P, _P, _P, _P, C.c_uint32, C.c_uint32, _P]),
+    ("fri_decode_tq_device_part", C.c_int, [_P, _P, _P, C.c_int, _P, C.c_uint32, C.c_uint32, _P]),
     ("fri_predict_host", C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),
     ("fri_frv_pack", C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, C.POINTER(_P), C.POINTER(C.c_size_t)]),
     ("fri_frv_unpack", C.c_int, [_P, _P, C.c_size_t, _P]),
@@ -572,6 +575,26 @@ class Plan:
         mode = FRI_DEQUANT_MULTIPLY if multiply else FRI_DEQUANT_DIVIDE
         _check(lib().fri_frv_decode(self._h, buf.ctypes.data, len(data), qp, mode, out.ctypes.data))
         return out
+
+    # ---- one image split over several GPUs by ranges of tile groups -----------
+    def part(self, part: int, n_parts: int) -> dict:
+        """Groups, tiles (plan order) and pixel rows of part `part` of `n_parts` (fri_plan_part)."""
+        v = [C.c_uint32() for _ in range(6)]
+        _check(lib().fri_plan_part(self._h, part, n_parts, *[C.byref(x) for x in v]))
+        keys = ("group_begin", "group_end", "tile_begin", "tile_end", "row_begin", "row_end")
+        return {k: int(x.value) for k, x in zip(keys, v)}
+
+    def encode_device_part(self, d_pixel_rows: int, d_coef_tiles: int, part: int, n_parts: int, q=None, stream: int = 0) -> None:
+        """d_pixel_rows: the band of pixel rows [row_begin, row_end) of the part; d_coef_tiles: int32 blocks of its tiles."""
+        qa, qp = _q_array(q)
+        _check(lib().fri_encode_tq_device_part(self._h, d_pixel_rows, qp, d_coef_tiles, part, n_parts, stream))
+
+    def decode_device_part(self, d_coef_tiles: int, d_pixel_rows: int, part: int, n_parts: int, q=None, multiply: bool = False,
+                           stream: int = 0) -> None:
+        """Writes only the pixels the part's tiles own into the band (rows [row_begin, row_end))."""
+        qa, qp = _q_array(q)
+        mode = FRI_DEQUANT_MULTIPLY if multiply else FRI_DEQUANT_DIVIDE
+        _check(lib().fri_decode_tq_device_part(self._h, d_coef_tiles, qp, mode, d_pixel_rows, part, n_parts, stream))
 
     # ---- device-resident entry points (raw device pointers, e.g. torch.Tensor.data_ptr()) -----
     def encode_device(self, d_pixels: int, n_frames: int, d_coefs: int, q=None, stream: int = 0, half: bool = False) -> None:

@@ -531,6 +531,98 @@ static int decode_device(const fri_plan *cp, const void *d_coefs, bool half, uin
     return FRI_OK;
 }
 
+/* ---- one image split over several GPUs by ranges of tile groups -------------------------- */
+struct Part {
+    int g0, g1;         // groups [g0, g1)
+    int64_t t0, t1;     // tiles [t0, t1) in plan order: the coefficient blocks the part produces / consumes
+    int row0, row1;     // pixel rows [row0, row1) the part's groups read (encode) or write into (decode)
+};
+
+static int plan_part(const fri_plan *p, uint32_t part, uint32_t n_parts, Part &out)
+{
+    if (!p) return fail(FRI_E_INVALID, "plan is NULL");
+    const Plan &pl = p->plan;
+    const Geometry &g = pl.geo;
+    if (g.sub_bits != 0) return fail(FRI_E_UNSUPPORTED, "an image is split by tile groups at depth 9 only (deeper trees fold every base tile's root in one pass)");
+    if (n_parts == 0 || part >= n_parts || n_parts > (uint32_t)std::max(1, g.n_groups))
+        return fail(FRI_E_INVALID, "part %u of %u: need part < n_parts <= %d groups", part, n_parts, g.n_groups);
+    out.g0 = (int)((int64_t)g.n_groups * part / n_parts);
+    out.g1 = (int)((int64_t)g.n_groups * (part + 1) / n_parts);
+    out.t0 = pl.groups[out.g0].tile_base;
+    out.t1 = out.g1 < g.n_groups ? (int64_t)pl.groups[out.g1].tile_base : (int64_t)g.n_base_tiles;
+    int lo = g.height, hi = 0;
+    for (int i = out.g0; i < out.g1; ++i) {
+        lo = std::min(lo, pl.groups[i].y0);
+        hi = std::max(hi, pl.groups[i].y0 + g.region_h);
+    }
+    out.row0 = std::max(0, std::min(lo, g.height));
+    out.row1 = std::max(out.row0, std::min(hi, g.height));
+    return FRI_OK;
+}
+
+int fri_plan_part(const fri_plan *p, uint32_t part, uint32_t n_parts, uint32_t *group_begin, uint32_t *group_end,
+                  uint32_t *tile_begin, uint32_t *tile_end, uint32_t *row_begin, uint32_t *row_end)
+{
+    Part pt;
+    int rc = plan_part(p, part, n_parts, pt);
+    if (rc) return rc;
+    if (group_begin) *group_begin = (uint32_t)pt.g0;
+    if (group_end) *group_end = (uint32_t)pt.g1;
+    if (tile_begin) *tile_begin = (uint32_t)pt.t0;
+    if (tile_end) *tile_end = (uint32_t)pt.t1;
+    if (row_begin) *row_begin = (uint32_t)pt.row0;
+    if (row_end) *row_end = (uint32_t)pt.row1;
+    return FRI_OK;
+}
+
+// The kernels address a whole frame; a part touches rows [row0, row1) and tiles [t0, t1) only, so the caller's
+// band buffers are handed over as frame bases shifted back by the part's first row / first tile.
+static int part_call(const fri_plan *cp, bool encode, const void *d_in, void *d_out, const int32_t *q, int dequant_mode,
+                     uint32_t part, uint32_t n_parts, void *stream)
+{
+    fri_plan *p = const_cast<fri_plan *>(cp);
+    int rc = enter_device(p);
+    if (rc) return rc;
+    if ((rc = check_q(q))) return rc;
+    if (!encode && dequant_mode != FRI_DEQUANT_DIVIDE && dequant_mode != FRI_DEQUANT_MULTIPLY)
+        return fail(FRI_E_INVALID, "dequant_mode must be FRI_DEQUANT_DIVIDE or FRI_DEQUANT_MULTIPLY");
+    Part pt;
+    if ((rc = plan_part(p, part, n_parts, pt))) return rc;
+    if (!d_in || !d_out) return fail(FRI_E_INVALID, "NULL device buffer");
+    const Geometry &g = p->plan.geo;
+    const void *d_pixels_rows = encode ? d_in : d_out;
+    const void *d_coefs_tiles = encode ? d_out : d_in;
+    if ((uintptr_t)d_coefs_tiles & 15) return fail(FRI_E_INVALID, "the coefficient buffer must be 16-byte aligned");
+    if ((uintptr_t)d_pixels_rows & (uintptr_t)(g.sample_bytes - 1)) return fail(FRI_E_INVALID, "the pixel band must be aligned to the sample size");
+    const size_t block = (size_t)g.channels << g.depth;
+    const uintptr_t px_base = (uintptr_t)d_pixels_rows - (uintptr_t)pt.row0 * (uintptr_t)g.row_stride;
+    const uintptr_t co_base = (uintptr_t)d_coefs_tiles - (uintptr_t)pt.t0 * block * sizeof(int32_t);
+    QuantParams qp;
+    make_quant_params(qp, q, !encode && dequant_mode == FRI_DEQUANT_MULTIPLY);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint32_t launches = 0;
+    const cudaError_t e = encode
+        ? launch_encode(g, p->tables, qp, reinterpret_cast<const void *>(px_base), 1, reinterpret_cast<void *>(co_base), false, nullptr, st,
+                        &launches, pt.g0, pt.g1)
+        : launch_decode(g, p->tables, qp, reinterpret_cast<const void *>(co_base), false, 1, reinterpret_cast<void *>(px_base), nullptr, st,
+                        &launches, pt.g0, pt.g1);
+    p->last_launches = launches;
+    if (e != cudaSuccess) return cuda_fail(e, encode ? "launch_encode (part)" : "launch_decode (part)");
+    return FRI_OK;
+}
+
+int fri_encode_tq_device_part(const fri_plan *p, const void *d_pixel_rows, const int32_t *q, int32_t *d_coef_tiles, uint32_t part,
+                              uint32_t n_parts, void *stream)
+{
+    return part_call(p, true, d_pixel_rows, d_coef_tiles, q, FRI_DEQUANT_DIVIDE, part, n_parts, stream);
+}
+
+int fri_decode_tq_device_part(const fri_plan *p, const int32_t *d_coef_tiles, const int32_t *q, int dequant_mode, void *d_pixel_rows,
+                              uint32_t part, uint32_t n_parts, void *stream)
+{
+    return part_call(p, false, d_coef_tiles, d_pixel_rows, q, dequant_mode, part, n_parts, stream);
+}
+
 int fri_encode_tq_device(const fri_plan *p, const void *d_pixels, uint32_t n_frames, const int32_t *q, int32_t *d_coefs,
                          void *stream)
 {

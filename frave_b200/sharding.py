@@ -1,9 +1,15 @@
-"""Frame sharding across the GPUs of one node.
+"""Sharding across the GPUs of one node.
 
 Fractals, channels and frames are independent (wavelet_transform.rs:412-414, :191), so a batch
 is split by frame with no exchange step: rank r of `world` takes one contiguous block.  There is
 no collective on the data path; torch.distributed is used by the callers only for the timing
 barrier and the max-over-ranks reduction.
+
+A single huge image is split by contiguous ranges of tile groups instead
+(`shard_image`): rank r transforms the tiles of its groups from the band of pixel rows they touch.
+Tiles straddle the cut, so the row bands of neighbouring ranks overlap by a halo; on decode every rank
+writes only the pixels its own tiles own, and the overlap rows are the one exchange step of the path —
+bands that start from zero merge by addition (`overlaps` lists who shares which rows with whom).
 """
 from __future__ import annotations
 
@@ -24,3 +30,25 @@ def frame_owner(frame: int, n_frames: int, world: int) -> int:
     if frame < cut:
         return frame // (base + 1)
     return extra + (frame - cut) // base
+
+
+def shard_image(plan, rank: int, world: int) -> dict:
+    """Part `rank` of `world` of one image (capi.Plan.part): group / tile / pixel-row ranges, half open."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError("bad rank/world")
+    return plan.part(rank, world)
+
+
+def overlaps(plan, rank: int, world: int) -> list[tuple[int, int, int]]:
+    """(peer, row_lo, row_hi) for every other rank whose pixel-row band intersects this rank's: the rows both
+    write into on decode (each its own pixels) and both read on encode."""
+    mine = shard_image(plan, rank, world)
+    out = []
+    for peer in range(world):
+        if peer == rank:
+            continue
+        other = shard_image(plan, peer, world)
+        lo, hi = max(mine["row_begin"], other["row_begin"]), min(mine["row_end"], other["row_end"])
+        if lo < hi:
+            out.append((peer, lo, hi))
+    return out

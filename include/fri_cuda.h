@@ -250,6 +250,28 @@ int fri_predict_device(fri_plan *plan, const int32_t *d_coefs, uint32_t n_frames
                        uint32_t *d_overflow, void *stream);
 
 /*
+ * One image split over several GPUs ("a single huge image may additionally be split by tile-index
+ * ranges across GPUs"; depth 9).  Part `part` of `n_parts` is a contiguous range of the plan's tile groups:
+ *   fri_plan_part   groups [group_begin, group_end), the tiles [tile_begin, tile_end) (plan order) whose coefficient
+ *                   blocks the part produces / consumes, and the pixel rows [row_begin, row_end) its groups read
+ *                   (encode) or write into (decode).  Tile ranges of the parts are disjoint and cover the plan; row
+ *                   ranges of neighbouring parts overlap by the halo of the tiles that straddle the cut.
+ *   fri_encode_tq_device_part   d_pixel_rows points at pixel row `row_begin` (a band of row_end - row_begin rows,
+ *                   frame row stride), d_coef_tiles at the block of tile `tile_begin`; only those are touched.
+ *   fri_decode_tq_device_part   the inverse.  Only pixels OWNED by the part's tiles are written: in the rows two
+ *                   parts share each writes its own pixels and leaves the others alone, so bands that start from
+ *                   zero merge by addition (the one exchange step of the split: the overlap rows between
+ *                   neighbours; see frave_b200/sharding.py and bench.py --workload image16k).
+ * No collective inside the library; one frame per call; FRI_E_UNSUPPORTED at depth > 9.
+ */
+int fri_plan_part(const fri_plan *plan, uint32_t part, uint32_t n_parts, uint32_t *group_begin, uint32_t *group_end,
+                  uint32_t *tile_begin, uint32_t *tile_end, uint32_t *row_begin, uint32_t *row_end);
+int fri_encode_tq_device_part(const fri_plan *plan, const void *d_pixel_rows, const int32_t *q, int32_t *d_coef_tiles,
+                              uint32_t part, uint32_t n_parts, void *stream);
+int fri_decode_tq_device_part(const fri_plan *plan, const int32_t *d_coef_tiles, const int32_t *q, int dequant_mode,
+                              void *d_pixel_rows, uint32_t part, uint32_t n_parts, void *stream);
+
+/*
  * The host side of the codec behind the transform (depth 9, 8-bit samples):
  * the reference keeps context modelling, rANS and the `frif` container on the host, and so does this
  * library — in C++ (frave_b200/csrc/fri_codec.cpp), restating stages/entropy_coding.rs:32-176, :205-449,

@@ -67,6 +67,9 @@ extern "C" {
     fn fri_predict_device(plan: *mut FriPlan, d_coefs: *const i32, n_frames: u32, value_params: *const f32, width_params: *const f32, d_bucket: *mut u8, d_pred: *mut i32, d_sym: *mut u16, d_hist: *mut u32, d_overflow: *mut u32, stream: *mut c_void) -> c_int;
     fn fri_fit_parameters(plan: *mut FriPlan, coefs: *const i32, value_params: *mut f32, width_params: *mut f32) -> c_int;
     fn fri_fit_device(plan: *mut FriPlan, d_coefs: *const i32, value_params: *mut f32, width_params: *mut f32, stream: *mut c_void) -> c_int;
+    fn fri_plan_part(plan: *const FriPlan, part: u32, n_parts: u32, group_begin: *mut u32, group_end: *mut u32, tile_begin: *mut u32, tile_end: *mut u32, row_begin: *mut u32, row_end: *mut u32) -> c_int;
+    fn fri_encode_tq_device_part(plan: *const FriPlan, d_pixel_rows: *const c_void, q: *const i32, d_coef_tiles: *mut i32, part: u32, n_parts: u32, stream: *mut c_void) -> c_int;
+    fn fri_decode_tq_device_part(plan: *const FriPlan, d_coef_tiles: *const i32, q: *const i32, dequant_mode: c_int, d_pixel_rows: *mut c_void, part: u32, n_parts: u32, stream: *mut c_void) -> c_int;
     fn fri_predict_host(plan: *mut FriPlan, coefs: *const i32, value_params: *const f32, width_params: *const f32, bucket: *mut u8, pred: *mut i32, sym: *mut u16, hist: *mut u32, overflow: *mut u32) -> c_int;
     fn fri_frv_pack(plan: *mut FriPlan, colorspace: c_int, value_params: *const f32, width_params: *const f32, bucket: *const u8, sym: *const u16, hist: *const u32, out: *mut *mut u8, out_len: *mut usize) -> c_int;
     fn fri_frv_unpack(plan: *mut FriPlan, bytes: *const u8, len: usize, coefs: *mut i32) -> c_int;
@@ -329,6 +332,25 @@ impl Plan {
         let (mut v, mut w) = (vec![[[0f32; 6]; 3]; self.channels], vec![[[0f32; 6]; 3]; self.channels]);
         check(fri_fit_device(self.raw, d_coefs, v.as_mut_ptr() as *mut f32, w.as_mut_ptr() as *mut f32, stream))?;
         Ok((v, w))
+    }
+    /// Part `part` of `n_parts` of one image split over several GPUs: (groups, tiles, pixel rows) as half-open ranges.
+    pub fn part(&self, part: u32, n_parts: u32) -> Result<[(u32, u32); 3], String> {
+        let mut v = [0u32; 6];
+        let p = v.as_mut_ptr();
+        check(unsafe { fri_plan_part(self.raw, part, n_parts, p, p.add(1), p.add(2), p.add(3), p.add(4), p.add(5)) })?;
+        Ok([(v[0], v[1]), (v[2], v[3]), (v[4], v[5])])
+    }
+    /// # Safety
+    /// `d_pixel_rows` / `d_coef_tiles` must be device buffers on this plan's device covering the part's rows / tiles.
+    pub unsafe fn encode_device_part(&self, d_pixel_rows: *const c_void, q: &[i32; 32], d_coef_tiles: *mut i32, part: u32, n_parts: u32,
+                                     stream: *mut c_void) -> Result<(), String> {
+        check(fri_encode_tq_device_part(self.raw, d_pixel_rows, q.as_ptr(), d_coef_tiles, part, n_parts, stream))
+    }
+    /// # Safety
+    /// As `encode_device_part`; writes only the pixels the part's tiles own.
+    pub unsafe fn decode_device_part(&self, d_coef_tiles: *const i32, q: &[i32; 32], d_pixel_rows: *mut c_void, part: u32, n_parts: u32,
+                                     stream: *mut c_void) -> Result<(), String> {
+        check(fri_decode_tq_device_part(self.raw, d_coef_tiles, q.as_ptr(), FRI_DEQUANT_DIVIDE, d_pixel_rows, part, n_parts, stream))
     }
     /// Host predictor (what the serial entropy decoder evaluates): see include/fri_cuda.h for the array shapes.
     #[allow(clippy::too_many_arguments)]

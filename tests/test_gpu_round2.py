@@ -407,3 +407,43 @@ def test_packed_transport_at_9_and_10_bits(shape, bits):
         with pytest.raises(capi.FriError) as ei:
             plan.encode_emit_packed(frames, None, 8)
         assert ei.value.code == capi.FRI_E_INVALID
+
+
+# ------------------------------------------------------------------------------------------------
+# one image split over several GPUs by ranges of tile groups (here: the parts run one after the
+# other on one GPU, each with its own band buffers, exactly as N ranks would hold them)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,dtype,n_parts", [((1080, 1920, 3), np.uint8, 2), ((1080, 1920, 3), np.uint8, 8), ((517, 333, 3), np.uint8, 3),
+                                                 ((700, 500, 1), np.uint16, 4), ((2048, 2048, 1), np.uint8, 5)],
+                         ids=["1080p/2", "1080p/8", "333x517x3/3", "500x700 u16/4", "2048x2048x1/5"])
+def test_image_split_by_tile_group_ranges(shape, dtype, n_parts):
+    import torch
+    from frave_b200 import sharding
+    h, w, c = shape
+    sb = np.dtype(dtype).itemsize
+    img = uniform_image(h, w, c, seed=h + n_parts, dtype=dtype)
+    q = smallest_layer_q(3)
+    tdt = torch.uint8 if sb == 1 else torch.int16
+    with capi.Plan(w, h, c, sample_bytes=sb) as plan:
+        want = plan.encode(img, q)[0]
+        full = plan.decode(want, q)[0]
+        merged = torch.zeros((h, w, c), dtype=torch.int32, device="cuda")
+        seen_tiles = 0
+        for r in range(n_parts):
+            p = sharding.shard_image(plan, r, n_parts)
+            t0, t1, r0, r1 = p["tile_begin"], p["tile_end"], p["row_begin"], p["row_end"]
+            band = torch.from_numpy(img[r0:r1].view(np.uint8 if sb == 1 else np.int16).copy()).cuda()  # only the rows the part touches
+            coefs = torch.full((t1 - t0, c, 512), 123456, dtype=torch.int32, device="cuda")
+            plan.encode_device_part(band.data_ptr(), coefs.data_ptr(), r, n_parts, q)
+            assert plan.last_launches == 1
+            assert np.array_equal(coefs.cpu().numpy(), want[t0:t1]), f"part {r}: coefficients differ from the whole-frame call"
+            out = torch.zeros((r1 - r0, w, c), dtype=tdt, device="cuda")
+            plan.decode_device_part(coefs.data_ptr(), out.data_ptr(), r, n_parts, q)
+            o32 = out.to(torch.int32) & (0xFFFF if sb == 2 else 0xFF)
+            assert not ((merged[r0:r1] != 0) & (o32 != 0)).any(), "two parts wrote the same pixel"
+            merged[r0:r1] += o32  # the exchange step: overlap rows merge by addition
+            seen_tiles += t1 - t0
+        assert seen_tiles == plan.n_tiles
+        assert np.array_equal(merged.cpu().numpy().astype(dtype), full)
+        with pytest.raises(capi.FriError):
+            plan.encode_device_part(band.data_ptr(), coefs.data_ptr(), n_parts, n_parts, q)

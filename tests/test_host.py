@@ -227,6 +227,39 @@ def test_shard_frames_partitions_the_batch():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_image_parts_partition_the_plan():
+    """fri_plan_part: tile ranges of the parts are disjoint and cover the plan, group ranges likewise, every pixel a
+    part's tiles own lies inside the part's band of rows; depth > 9 and bad arguments are refused."""
+    for (w, h, c), worlds in (((320, 240, 3), (1, 2, 3, 5)), ((1920, 1080, 1), (2, 8)), ((77, 131, 3), (1, 2))):
+        img = np.full((h, w, c), 255, np.uint8)
+        with capi.Plan(w, h, c, device=-1) as plan:
+            centers = plan.centers()
+            n_groups = plan.launch_info()["n_groups"]
+            for world in worlds:
+                if world > n_groups:
+                    continue
+                parts = [sharding.shard_image(plan, r, world) for r in range(world)]
+                assert parts[0]["tile_begin"] == 0 and parts[-1]["tile_end"] == plan.n_tiles
+                assert parts[0]["group_begin"] == 0 and parts[-1]["group_end"] == n_groups
+                for a, b in zip(parts, parts[1:]):
+                    assert a["tile_end"] == b["tile_begin"] and a["group_end"] == b["group_begin"]
+                for r, p in enumerate(parts):
+                    assert 0 <= p["row_begin"] <= p["row_end"] <= h
+                    coef, some = O.extract_tiles(img, centers[p["tile_begin"]:p["tile_end"]])
+                    own = O.extract_values(centers[p["tile_begin"]:p["tile_end"]], coef, some, h, w)
+                    assert not own[:p["row_begin"]].any() and not own[p["row_end"]:].any()
+                    for peer, lo, hi in sharding.overlaps(plan, r, world):
+                        assert peer != r and p["row_begin"] <= lo < hi <= p["row_end"]
+            with pytest.raises(capi.FriError):
+                plan.part(2, 2)
+            with pytest.raises(capi.FriError):
+                plan.part(0, 0)
+    with capi.Plan(300, 200, 1, depth=12, device=-1) as deep:
+        with pytest.raises(capi.FriError) as ei:
+            deep.part(0, 2)
+        assert ei.value.code == capi.FRI_E_UNSUPPORTED
+
+
 _WORKER = r"""
 import os, sys
 sys.path.insert(0, {root!r})
@@ -268,6 +301,34 @@ t = torch.tensor([local, len(mine)], dtype=torch.int64)
 dist.all_reduce(t)
 want = sum(int(O.from_raster(frames[f])[1].astype(np.int64).sum()) * (f + 1) for f in range(n_frames))
 assert t[0].item() == want and t[1].item() == n_frames, (t, want)
+# ---- one image split by tile-group ranges (SURVEY.md §8(e)): every rank transforms its own tiles, decodes only the
+# pixels they own, and the overlap rows are exchanged and merged by addition — the host logic of
+# bench.py --workload image16k, with the oracle standing in for the kernels
+ih, iw, ic = 240, 320, 3
+img = np.random.Generator(np.random.PCG64(7)).integers(1, 256, (ih, iw, ic), dtype=np.uint8)  # no zero pixel: ownership is visible
+with capi.Plan(iw, ih, ic, device=-1) as plan:
+    part = sharding.shard_image(plan, rank, world)
+    shared = sharding.overlaps(plan, rank, world)
+    centers = plan.centers()
+    covered = plan.pixels_covered == iw * ih
+t0, t1, r0, r1 = part["tile_begin"], part["tile_end"], part["row_begin"], part["row_end"]
+coef, some = O.extract_tiles(img, centers[t0:t1])
+mine_px = O.extract_values(centers[t0:t1], coef, some, ih, iw)      # only the pixels my tiles own, zeros elsewhere
+assert not mine_px[:r0].any() and not mine_px[r1:].any()            # ... all inside my band of rows
+band = torch.from_numpy(mine_px[r0:r1].astype(np.int32))
+assert shared == [(1 - rank, max(r0, shared[0][1]), min(r1, shared[0][2]))] and len(shared) == 1
+peer, lo, hi = shared[0]
+theirs = torch.zeros((hi - lo, iw, ic), dtype=torch.int32)
+ops = [dist.P2POp(dist.isend, band[lo - r0:hi - r0].contiguous(), peer), dist.P2POp(dist.irecv, theirs, peer)]
+for w_ in dist.batch_isend_irecv(ops):
+    w_.wait()
+assert not ((band[lo - r0:hi - r0] != 0) & (theirs != 0)).any()     # a pixel has exactly one owner
+band[lo - r0:hi - r0] += theirs
+if covered:
+    assert np.array_equal(band.numpy().astype(np.uint8), img[r0:r1])
+tiles = torch.tensor([t1 - t0], dtype=torch.int64)
+dist.all_reduce(tiles)
+assert tiles.item() == len(centers)
 el = torch.tensor([1.0 + rank])
 dist.all_reduce(el, op=dist.ReduceOp.MAX)
 assert el.item() == 2.0
