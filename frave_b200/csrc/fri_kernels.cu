@@ -129,15 +129,15 @@ namespace {
 //   kQuantNone      layers 6..9 all have divisor 1 — the reference's matrix (quantization.rs:3-5);
 //   kQuantSmallest  only layers 8 and 9 are active, with one divisor — "dividing the smallest layer
 //                   of fractals" (README.md:12; BASELINE.json's divisor sweep);
-//   kQuantGeneric   anything else (and every deep-tree launch).
+//   kQuantGeneric   anything else (deep trees: everything but kQuantNone).
 // Layers 0..5 are handled by the run-time tests in every class (once per tile, not per channel).
 constexpr int kQuantGeneric = 0, kQuantNone = 1, kQuantSmallest = 2;
 
 int quant_class(const QuantParams &qp, const Geometry &g)
 {
-    if (g.sub_bits != 0) return kQuantGeneric;
-    const uint32_t hi = (qp.active >> 6) & 0xfu;
+    const uint32_t hi = (qp.active >> (g.sub_bits + 6)) & 0xfu;  // the register levels' layers sit sub_bits deeper in a deep tree
     if (hi == 0) return kQuantNone;
+    if (g.sub_bits != 0) return kQuantGeneric;
     if (hi == 0xcu && qp.q[8] == qp.q[9]) return kQuantSmallest;
     return kQuantGeneric;
 }
@@ -1627,6 +1627,10 @@ cudaError_t configure_kernels()
     FRI_CFG((name<3, uint8_t, false, kQuantSmallest, int32_t>));     \
     FRI_CFG((name<1, uint16_t, false, kQuantSmallest, int32_t>));    \
     FRI_CFG((name<3, uint16_t, false, kQuantSmallest, int32_t>));    \
+    FRI_CFG((name<1, uint8_t, true, kQuantNone, int32_t>));          \
+    FRI_CFG((name<3, uint8_t, true, kQuantNone, int32_t>));          \
+    FRI_CFG((name<1, uint16_t, true, kQuantNone, int32_t>));         \
+    FRI_CFG((name<3, uint16_t, true, kQuantNone, int32_t>));         \
     FRI_CFG((name<1, uint8_t, true, kQuantGeneric, int32_t>));       \
     FRI_CFG((name<3, uint8_t, true, kQuantGeneric, int32_t>));       \
     FRI_CFG((name<1, uint16_t, true, kQuantGeneric, int32_t>));      \
@@ -1729,10 +1733,16 @@ cudaError_t launch_encode(const Geometry &g, const DeviceTables &t, const QuantP
             if (g.channels == 1) FRI_LAUNCH(1, uint8_t, int16_t, c16);
             else FRI_LAUNCH(3, uint8_t, int16_t, c16);
         } else if (g.sub_bits != 0) {
-            if (g.channels == 1 && g.sample_bytes == 1) FRI_LAUNCH_Q(1, uint8_t, true, kQuantGeneric, int32_t, c);
-            else if (g.channels == 3 && g.sample_bytes == 1) FRI_LAUNCH_Q(3, uint8_t, true, kQuantGeneric, int32_t, c);
-            else if (g.channels == 1 && g.sample_bytes == 2) FRI_LAUNCH_Q(1, uint16_t, true, kQuantGeneric, int32_t, c);
-            else FRI_LAUNCH_Q(3, uint16_t, true, kQuantGeneric, int32_t, c);
+#define FRI_LAUNCH_DEEP(CC, SS)                                                               \
+            do {                                                                              \
+                if (qclass == kQuantNone) FRI_LAUNCH_Q(CC, SS, true, kQuantNone, int32_t, c); \
+                else FRI_LAUNCH_Q(CC, SS, true, kQuantGeneric, int32_t, c);                   \
+            } while (0)
+            if (g.channels == 1 && g.sample_bytes == 1) FRI_LAUNCH_DEEP(1, uint8_t);
+            else if (g.channels == 3 && g.sample_bytes == 1) FRI_LAUNCH_DEEP(3, uint8_t);
+            else if (g.channels == 1 && g.sample_bytes == 2) FRI_LAUNCH_DEEP(1, uint16_t);
+            else FRI_LAUNCH_DEEP(3, uint16_t);
+#undef FRI_LAUNCH_DEEP
         } else if (g.channels == 1 && g.sample_bytes == 1) FRI_LAUNCH(1, uint8_t, int32_t, c);
         else if (g.channels == 3 && g.sample_bytes == 1) FRI_LAUNCH(3, uint8_t, int32_t, c);
         else if (g.channels == 1 && g.sample_bytes == 2) FRI_LAUNCH(1, uint16_t, int32_t, c);
@@ -1796,10 +1806,16 @@ cudaError_t launch_decode(const Geometry &g, const DeviceTables &t, const QuantP
             if (g.channels == 1) FRI_LAUNCH(1, uint8_t, int16_t, c16);
             else FRI_LAUNCH(3, uint8_t, int16_t, c16);
         } else if (g.sub_bits != 0) {
-            if (g.channels == 1 && g.sample_bytes == 1) FRI_LAUNCH_Q(1, uint8_t, true, kQuantGeneric, int32_t, c);
-            else if (g.channels == 3 && g.sample_bytes == 1) FRI_LAUNCH_Q(3, uint8_t, true, kQuantGeneric, int32_t, c);
-            else if (g.channels == 1 && g.sample_bytes == 2) FRI_LAUNCH_Q(1, uint16_t, true, kQuantGeneric, int32_t, c);
-            else FRI_LAUNCH_Q(3, uint16_t, true, kQuantGeneric, int32_t, c);
+#define FRI_LAUNCH_DEEP(CC, SS)                                                               \
+            do {                                                                              \
+                if (qclass == kQuantNone) FRI_LAUNCH_Q(CC, SS, true, kQuantNone, int32_t, c); \
+                else FRI_LAUNCH_Q(CC, SS, true, kQuantGeneric, int32_t, c);                   \
+            } while (0)
+            if (g.channels == 1 && g.sample_bytes == 1) FRI_LAUNCH_DEEP(1, uint8_t);
+            else if (g.channels == 3 && g.sample_bytes == 1) FRI_LAUNCH_DEEP(3, uint8_t);
+            else if (g.channels == 1 && g.sample_bytes == 2) FRI_LAUNCH_DEEP(1, uint16_t);
+            else FRI_LAUNCH_DEEP(3, uint16_t);
+#undef FRI_LAUNCH_DEEP
         } else if (g.channels == 1 && g.sample_bytes == 1) FRI_LAUNCH(1, uint8_t, int32_t, c);
         else if (g.channels == 3 && g.sample_bytes == 1) FRI_LAUNCH(3, uint8_t, int32_t, c);
         else if (g.channels == 1 && g.sample_bytes == 2) FRI_LAUNCH(1, uint16_t, int32_t, c);
