@@ -717,9 +717,24 @@ __device__ __forceinline__ void encode_tiles(const Geometry &g, const QuantParam
 // (plan order is group-major), n_present * C * 2 KB in one run.
 template <int C, bool DEEP, typename CT>
 __device__ __forceinline__ void prefetch_group_coefs(const Geometry &g, const GroupDesc &gd, int frame,
-                                                     const CT *__restrict__ coefs)
+                                                     const CT *__restrict__ coefs, const uint32_t *__restrict__ tile_unit)
 {
-    if (DEEP) return;
+    if (DEEP) {
+        // depth > 9: a base tile's coefficients are nine runs inside its fractal's heap (node << level):
+        // 8 + 4 + 2 lines for levels 8, 7, 6 and one line for each level below, per tile and channel
+        constexpr int kLines = 8 + 4 + 2 + 6;
+        const int total = __popc(gd.tile_mask) * C * kLines;
+#pragma unroll 1
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+            const int task = i / kLines, s = i - task * kLines;
+            const TaskAddr ta = task_addr<C, true>(g, tile_unit, frame, (int)gd.tile_base + task / C, task % C);
+            const int level = s < 8 ? 8 : s < 12 ? 7 : s < 14 ? 6 : 19 - s;
+            const int line = s < 8 ? s : s < 12 ? s - 8 : s < 14 ? s - 12 : 0;
+            const char *p = reinterpret_cast<const char *>(coefs + ta.block + ((int64_t)ta.node << level)) + line * 128;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+        }
+        return;
+    }
     const char *first = reinterpret_cast<const char *>(coefs + ((((int64_t)frame * g.n_fractals + gd.tile_base) * C) << kBaseDepth));
     const int lines = __popc(gd.tile_mask) * C * (4 * (int)sizeof(CT));  // 128-byte lines: 512 coefficients per (tile, channel)
 #pragma unroll 1
@@ -1280,7 +1295,7 @@ fri_decode_kernel(const __grid_constant__ Geometry g, const __grid_constant__ Qu
     if (sparse) zero_region(g, region);
     // the previous kernel of the stream may have produced these coefficients (or still read the pixels)
     if (DEEP || !g.independent_calls) pdl_wait();
-    if ((int64_t)blockIdx.y * gridDim.x + blockIdx.x >= no_prefetch_ctas) prefetch_group_coefs<C, DEEP, CT>(g, gd, frame, coefs);
+    if ((int64_t)blockIdx.y * gridDim.x + blockIdx.x >= no_prefetch_ctas) prefetch_group_coefs<C, DEEP, CT>(g, gd, frame, coefs, tile_unit);
     if (sparse) __syncthreads();
     decode_tiles<C, S, DEEP, QS, CT>(g, qp, gd, rv, tile_unit, frame, region, scratch, coefs, dc_in);
     const WriteAhead ahead = write_out_preload(g, rv, chunk_list, edge_list, pol);
