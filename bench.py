@@ -774,7 +774,8 @@ def run_image_split(args, rank: int, local_rank: int, world: int) -> None:
     recv = {peer: torch.empty((hi - lo, iw), dtype=torch.int16, device=dev) for peer, lo, hi in shared}
     launches = 0
 
-    def step(i: int) -> None:
+    def step_nccl(i: int) -> None:
+        """exchange by NCCL: shared rows start from zero, point-to-point send / receive, merge by addition"""
         nonlocal launches
         a = i % n_sets
         plan.encode_device_part(bands[a].data_ptr(), coefs[a].data_ptr(), rank, world, q, stream)
@@ -793,29 +794,99 @@ def run_image_split(args, rank: int, local_rank: int, world: int) -> None:
             for peer, lo, hi in shared:
                 outs[a][lo - r0:hi - r0] += recv[peer]  # a pixel has one owner: the other side holds zero there
 
+    # ---- exchange by the transform kernel's own stores over peer memory: the bands live in symmetric memory (every
+    # rank maps every other rank's band over NVLink); a rank re-runs its groups along each cut with the NEIGHBOUR's
+    # band as the target (fri_decode_tq_device_groups), so the neighbour's shared rows are completed by P2P stores
+    # of the kernel that computed them; no zeroing, no merge pass, one device-side barrier per step
+    peer_err, step_peer, p_outs = None, None, None
+    if world > 1 and args.exchange in ("auto", "peer"):
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            margin = plan.launch_info()["region_h"]
+            parts = [sharding.shard_image(plan, r, world) for r in range(world)]
+            pushes = sharding.halo_pushes(plan, rank, world)
+            for ps in pushes:
+                pp = parts[ps["peer"]]
+                if not (pp["row_begin"] - margin <= ps["span_begin"] and ps["span_end"] <= pp["row_end"] + margin):
+                    raise RuntimeError("margin too small for the groups along the cut")
+            rows_max = max(p_["row_end"] - p_["row_begin"] for p_ in parts) + 2 * margin
+            sym = symm_mem.empty((n_sets, rows_max, iw), dtype=torch.int16, device=dev)
+            hdl = symm_mem.rendezvous(sym, dist.group.WORLD)
+            set_bytes = rows_max * iw * 2
+            stride = iw * 2
+            p_outs = [sym[a_][margin:margin + r1 - r0] for a_ in range(n_sets)]
+
+            def step_peer(i: int) -> None:
+                nonlocal launches
+                a = i % n_sets
+                plan.encode_device_part(bands[a].data_ptr(), coefs[a].data_ptr(), rank, world, q, stream)
+                launches += plan.last_launches
+                plan.decode_device_part(coefs[a].data_ptr(), p_outs[a].data_ptr(), rank, world, q, False, stream)
+                launches += plan.last_launches
+                for ps in pushes:
+                    target = int(hdl.buffer_ptrs[ps["peer"]]) + a * set_bytes  # the peer's band incl. its margin
+                    plan.decode_device_groups(coefs[a].data_ptr(), t_lo, target, parts[ps["peer"]]["row_begin"] - margin,
+                                              ps["first"], ps["last"], q, False, stream)
+                    launches += plan.last_launches
+                hdl.barrier(channel=0)  # every rank's pushes have landed
+
+            for a_ in range(n_sets):
+                sym[a_].fill_(12345)  # no zeroing in this variant: stale data must be overwritten by an owner
+            torch.cuda.synchronize()
+            dist.barrier()  # (a neighbour's first push must not land before this fill)
+            step_peer(0)
+            torch.cuda.synchronize()
+            if plan.pixels_covered == iw * ih and not torch.equal(p_outs[0], bands[0]):
+                raise RuntimeError("peer exchange: assembled band differs from the input")
+        except Exception as e:  # noqa: BLE001 — symmetric memory may be unavailable on a box; the NCCL variant stands
+            peer_err, step_peer = f"{type(e).__name__}: {e}"[:300], None
+            if args.exchange == "peer":
+                raise
+    ok = torch.tensor([1 if step_peer is not None else 0], device=dev)
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # all ranks or none
+    if ok.item() == 0:
+        step_peer = None
+
     # sanity (untimed): the assembled band equals the input (lossless at the all-ones matrix)
-    step(0)
+    step_nccl(0)
     torch.cuda.synchronize()
     if plan.pixels_covered == iw * ih and not torch.equal(outs[0], bands[0]):
         raise RuntimeError("sanity check failed: the split encode -> decode -> exchange is not lossless")
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    for k in range(max(args.warmup, 3)):
-        step(k)
-    torch.cuda.synchronize()
+
+    def timed(step) -> tuple[float, int]:
+        nonlocal launches
+        for k in range(max(args.warmup, 3)):
+            step(k)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches = 0
+        start.record()
+        for k in range(args.steps):
+            step(k)
+        end.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        return start.elapsed_time(end), launches
+
+    variants = {}
+    if args.exchange != "peer" or step_peer is None:
+        variants["nccl"] = timed(step_nccl)
+    if step_peer is not None:
+        variants["peer"] = timed(step_peer)
+    tv = torch.tensor([variants.get(k, (0.0, 0))[0] for k in ("nccl", "peer")], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches = 0
-    start.record()
-    for k in range(args.steps):
-        step(k)
-    end.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    elapsed_ms = start.elapsed_time(end)
-    timed_launches = launches
+        dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+    for k, v in zip(("nccl", "peer"), tv.tolist()):
+        if k in variants:
+            variants[k] = (v, variants[k][1])
+    best = min(variants, key=lambda k: variants[k][0])
+    elapsed_ms, timed_launches = variants[best]
 
     def enc_only(i: int) -> None:
         plan.encode_device_part(bands[i % n_sets].data_ptr(), coefs[i % n_sets].data_ptr(), rank, world, q, stream)
@@ -826,10 +897,10 @@ def run_image_split(args, rank: int, local_rank: int, world: int) -> None:
     reps = 40
     enc_ms, dec_ms = b2b(enc_only, reps, torch), b2b(dec_only, reps, torch)
     clocks = sampler.stop() if sampler else None
-    vals = torch.tensor([elapsed_ms, enc_ms, dec_ms], dtype=torch.float64, device=dev)
+    vals = torch.tensor([enc_ms, dec_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
-    elapsed_ms, enc_ms, dec_ms = vals.tolist()
+    enc_ms, dec_ms = vals.tolist()
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         alg = (t_hi - t_lo) * 512 * 6  # this rank's samples x (2 B pixel + 4 B coefficient)
@@ -850,12 +921,17 @@ def run_image_split(args, rank: int, local_rank: int, world: int) -> None:
                                    "contiguous ranges of tile groups; step = encode + decode of every rank's tiles + exchange of the "
                                    "overlap rows between neighbours (NCCL send/recv, merged by addition)",
                        "parts": world, "tiles_rank0": t_hi - t_lo, "rows_rank0": [r0, r1], "halo_rows_rank0": halo,
+                       "exchange": {"nccl": "shared rows zeroed, NCCL send/recv, merged by addition",
+                                    "peer": "bands in symmetric memory; every rank re-runs its groups along the cut with the neighbour's "
+                                            "band as the target of the decode kernel (P2P stores over NVLink), one device-side "
+                                            "barrier per step; no zeroing, no merge"}[best],
                        "quant": "all ones (16-bit extension: transform only)",
                        "l2": f"{n_sets} rotating buffer sets; rank 0's set is {(r1 - r0) * iw * 2 * 2 + (t_hi - t_lo) * 2048 >> 20} MB",
                        "parallelism": f"tile groups of one image sharded over {world} GPU(s); one point-to-point exchange of "
                                       f"{halo} overlap rows per rank and step"},
             "roofline": r_enc if enc_ms >= dec_ms else r_dec, "roofline_encode": r_enc, "roofline_decode": r_dec,
             "gpu_launches": timed_launches, "clocks": clocks, "launch": plan.launch_info(), "plan_build_ms": plan_build_ms,
+            "exchanges_ms_per_step": {k: v[0] / args.steps for k, v in variants.items()}, "peer_exchange_error": peer_err,
             "e2e": None, "cpu_baseline": None,
             "note": "secondary workload (the driver's line is the default one): e2e / cpu_baseline are reported there"}
         print(json.dumps(line), flush=True)
@@ -880,6 +956,8 @@ def main() -> None:
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (experiments only)")
     ap.add_argument("--no-batched", action="store_true", help="skip the batched steady-state leg (experiments only)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (experiments only)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "peer"],
+                    help="--workload image16k: how the overlap rows reach the neighbour (auto = time both, report the faster)")
     ap.add_argument("--no-codec", action="store_true", help="skip the whole-codec (frif container) leg (experiments only)")
     ap.add_argument("--divisor", type=int, default=None, help="smallest-layer divisor override (experiments only; default 4)")
     args = ap.parse_args()

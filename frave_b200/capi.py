@@ -70,6 +70,8 @@ _SYMBOLS = [
     ("fri_plan_part", C.c_int, [_P, C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, _P]),
     ("fri_encode_tq_device_part", C.c_int, [_P, _P, _P, _P, C.c_uint32, C.c_uint32, _P]),
     ("fri_decode_tq_device_part", C.c_int, [_P, _P, _P, C.c_int, _P, C.c_uint32, C.c_uint32, _P]),
+    ("fri_plan_groups_in_rows", C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _P, _P, _P, _P]),
+    ("fri_decode_tq_device_groups", C.c_int, [_P, _P, C.c_uint32, _P, C.c_int, _P, C.c_int32, C.c_uint32, C.c_uint32, _P]),
     ("fri_predict_host", C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),
     ("fri_frv_pack", C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, C.POINTER(_P), C.POINTER(C.c_size_t)]),
     ("fri_frv_unpack", C.c_int, [_P, _P, C.c_size_t, _P]),
@@ -595,6 +597,22 @@ class Plan:
         qa, qp = _q_array(q)
         mode = FRI_DEQUANT_MULTIPLY if multiply else FRI_DEQUANT_DIVIDE
         _check(lib().fri_decode_tq_device_part(self._h, d_coef_tiles, qp, mode, d_pixel_rows, part, n_parts, stream))
+
+    def groups_in_rows(self, group_begin: int, group_end: int, row_begin: int, row_end: int) -> dict:
+        """Smallest contiguous sub-range of groups [group_begin, group_end) holding every group that touches pixel rows
+        [row_begin, row_end), and the rows that sub-range touches in all (fri_plan_groups_in_rows)."""
+        v = [C.c_uint32() for _ in range(4)]
+        _check(lib().fri_plan_groups_in_rows(self._h, group_begin, group_end, row_begin, row_end, *[C.byref(x) for x in v]))
+        return {k: int(x.value) for k, x in zip(("first", "last", "span_begin", "span_end"), v)}
+
+    def decode_device_groups(self, d_coef_tiles: int, tile_first: int, d_pixel_rows: int, row_first: int, group_begin: int,
+                             group_end: int, q=None, multiply: bool = False, stream: int = 0) -> None:
+        """Inverse transform of groups [group_begin, group_end): d_coef_tiles points at tile `tile_first`'s block,
+        d_pixel_rows at frame row `row_first` (may be negative); only the pixels those groups' tiles own are written."""
+        qa, qp = _q_array(q)
+        mode = FRI_DEQUANT_MULTIPLY if multiply else FRI_DEQUANT_DIVIDE
+        _check(lib().fri_decode_tq_device_groups(self._h, d_coef_tiles, tile_first, qp, mode, d_pixel_rows, row_first, group_begin,
+                                                 group_end, stream))
 
     # ---- device-resident entry points (raw device pointers, e.g. torch.Tensor.data_ptr()) -----
     def encode_device(self, d_pixels: int, n_frames: int, d_coefs: int, q=None, stream: int = 0, half: bool = False) -> None:

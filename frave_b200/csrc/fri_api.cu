@@ -575,10 +575,10 @@ int fri_plan_part(const fri_plan *p, uint32_t part, uint32_t n_parts, uint32_t *
     return FRI_OK;
 }
 
-// The kernels address a whole frame; a part touches rows [row0, row1) and tiles [t0, t1) only, so the caller's
-// band buffers are handed over as frame bases shifted back by the part's first row / first tile.
-static int part_call(const fri_plan *cp, bool encode, const void *d_in, void *d_out, const int32_t *q, int dequant_mode,
-                     uint32_t part, uint32_t n_parts, void *stream)
+// The kernels address a whole frame; a range of groups touches some rows and tiles only, so the caller's band
+// buffers are handed over as frame bases shifted back by the band's first row / first tile.
+static int range_call(const fri_plan *cp, bool encode, const void *d_in, void *d_out, const int32_t *q, int dequant_mode,
+                      int g0, int g1, int64_t tile_first, int row_first, void *stream)
 {
     fri_plan *p = const_cast<fri_plan *>(cp);
     int rc = enter_device(p);
@@ -586,8 +586,6 @@ static int part_call(const fri_plan *cp, bool encode, const void *d_in, void *d_
     if ((rc = check_q(q))) return rc;
     if (!encode && dequant_mode != FRI_DEQUANT_DIVIDE && dequant_mode != FRI_DEQUANT_MULTIPLY)
         return fail(FRI_E_INVALID, "dequant_mode must be FRI_DEQUANT_DIVIDE or FRI_DEQUANT_MULTIPLY");
-    Part pt;
-    if ((rc = plan_part(p, part, n_parts, pt))) return rc;
     if (!d_in || !d_out) return fail(FRI_E_INVALID, "NULL device buffer");
     const Geometry &g = p->plan.geo;
     const void *d_pixels_rows = encode ? d_in : d_out;
@@ -595,32 +593,80 @@ static int part_call(const fri_plan *cp, bool encode, const void *d_in, void *d_
     if ((uintptr_t)d_coefs_tiles & 15) return fail(FRI_E_INVALID, "the coefficient buffer must be 16-byte aligned");
     if ((uintptr_t)d_pixels_rows & (uintptr_t)(g.sample_bytes - 1)) return fail(FRI_E_INVALID, "the pixel band must be aligned to the sample size");
     const size_t block = (size_t)g.channels << g.depth;
-    const uintptr_t px_base = (uintptr_t)d_pixels_rows - (uintptr_t)pt.row0 * (uintptr_t)g.row_stride;
-    const uintptr_t co_base = (uintptr_t)d_coefs_tiles - (uintptr_t)pt.t0 * block * sizeof(int32_t);
+    const uintptr_t px_base = (uintptr_t)d_pixels_rows - (uintptr_t)row_first * (uintptr_t)g.row_stride;
+    const uintptr_t co_base = (uintptr_t)d_coefs_tiles - (uintptr_t)tile_first * block * sizeof(int32_t);
     QuantParams qp;
     make_quant_params(qp, q, !encode && dequant_mode == FRI_DEQUANT_MULTIPLY);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     uint32_t launches = 0;
     const cudaError_t e = encode
         ? launch_encode(g, p->tables, qp, reinterpret_cast<const void *>(px_base), 1, reinterpret_cast<void *>(co_base), false, nullptr, st,
-                        &launches, pt.g0, pt.g1)
+                        &launches, g0, g1)
         : launch_decode(g, p->tables, qp, reinterpret_cast<const void *>(co_base), false, 1, reinterpret_cast<void *>(px_base), nullptr, st,
-                        &launches, pt.g0, pt.g1);
+                        &launches, g0, g1);
     p->last_launches = launches;
-    if (e != cudaSuccess) return cuda_fail(e, encode ? "launch_encode (part)" : "launch_decode (part)");
+    if (e != cudaSuccess) return cuda_fail(e, encode ? "launch_encode (group range)" : "launch_decode (group range)");
     return FRI_OK;
 }
 
 int fri_encode_tq_device_part(const fri_plan *p, const void *d_pixel_rows, const int32_t *q, int32_t *d_coef_tiles, uint32_t part,
                               uint32_t n_parts, void *stream)
 {
-    return part_call(p, true, d_pixel_rows, d_coef_tiles, q, FRI_DEQUANT_DIVIDE, part, n_parts, stream);
+    Part pt;
+    int rc = plan_part(p, part, n_parts, pt);
+    if (rc) return rc;
+    return range_call(p, true, d_pixel_rows, d_coef_tiles, q, FRI_DEQUANT_DIVIDE, pt.g0, pt.g1, pt.t0, pt.row0, stream);
 }
 
 int fri_decode_tq_device_part(const fri_plan *p, const int32_t *d_coef_tiles, const int32_t *q, int dequant_mode, void *d_pixel_rows,
                               uint32_t part, uint32_t n_parts, void *stream)
 {
-    return part_call(p, false, d_coef_tiles, d_pixel_rows, q, dequant_mode, part, n_parts, stream);
+    Part pt;
+    int rc = plan_part(p, part, n_parts, pt);
+    if (rc) return rc;
+    return range_call(p, false, d_coef_tiles, d_pixel_rows, q, dequant_mode, pt.g0, pt.g1, pt.t0, pt.row0, stream);
+}
+
+int fri_plan_groups_in_rows(const fri_plan *p, uint32_t group_begin, uint32_t group_end, uint32_t row_begin, uint32_t row_end,
+                            uint32_t *first, uint32_t *last, uint32_t *span_begin, uint32_t *span_end)
+{
+    if (!p) return fail(FRI_E_INVALID, "plan is NULL");
+    const Plan &pl = p->plan;
+    const Geometry &g = pl.geo;
+    if (g.sub_bits != 0) return fail(FRI_E_UNSUPPORTED, "group ranges exist at depth 9 only");
+    if (group_begin > group_end || group_end > (uint32_t)g.n_groups) return fail(FRI_E_INVALID, "bad group range");
+    int lo = -1, hi = -1;
+    for (int i = (int)group_begin; i < (int)group_end; ++i) {
+        const int y0 = std::max(0, pl.groups[i].y0), y1 = std::min(g.height, pl.groups[i].y0 + g.region_h);
+        if (y0 < (int)row_end && y1 > (int)row_begin) {
+            if (lo < 0) lo = i;
+            hi = i + 1;
+        }
+    }
+    if (lo < 0) lo = hi = (int)group_begin;
+    int s0 = g.height, s1 = 0;
+    for (int i = lo; i < hi; ++i) {
+        s0 = std::min(s0, std::max(0, pl.groups[i].y0));
+        s1 = std::max(s1, std::min(g.height, pl.groups[i].y0 + g.region_h));
+    }
+    if (lo == hi) s0 = s1 = 0;
+    if (first) *first = (uint32_t)lo;
+    if (last) *last = (uint32_t)hi;
+    if (span_begin) *span_begin = (uint32_t)s0;
+    if (span_end) *span_end = (uint32_t)s1;
+    return FRI_OK;
+}
+
+int fri_decode_tq_device_groups(const fri_plan *p, const int32_t *d_coef_tiles, uint32_t tile_first, const int32_t *q, int dequant_mode,
+                                void *d_pixel_rows, int32_t row_first, uint32_t group_begin, uint32_t group_end, void *stream)
+{
+    if (!p) return fail(FRI_E_INVALID, "plan is NULL");
+    const Geometry &g = p->plan.geo;
+    if (g.sub_bits != 0) return fail(FRI_E_UNSUPPORTED, "group ranges exist at depth 9 only");
+    if (group_begin > group_end || group_end > (uint32_t)g.n_groups) return fail(FRI_E_INVALID, "bad group range");
+    if (group_begin == group_end) return FRI_OK;
+    if ((int64_t)tile_first > (int64_t)p->plan.groups[group_begin].tile_base) return fail(FRI_E_INVALID, "tile_first lies behind the first group's tiles");
+    return range_call(p, false, d_coef_tiles, d_pixel_rows, q, dequant_mode, (int)group_begin, (int)group_end, tile_first, row_first, stream);
 }
 
 int fri_encode_tq_device(const fri_plan *p, const void *d_pixels, uint32_t n_frames, const int32_t *q, int32_t *d_coefs,

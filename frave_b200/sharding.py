@@ -52,3 +52,18 @@ def overlaps(plan, rank: int, world: int) -> list[tuple[int, int, int]]:
         if lo < hi:
             out.append((peer, lo, hi))
     return out
+
+
+def halo_pushes(plan, rank: int, world: int) -> list[dict]:
+    """The exchange step of the image split done by the transform kernel's own stores: for every peer sharing pixel
+    rows with `rank`, the sub-range of `rank`'s groups that touch the shared rows (`first`, `last`) and the rows that
+    sub-range touches in all (`span_begin`, `span_end`) — decoding those groups a second time into the PEER's band
+    (fri_decode_tq_device_groups on a peer-mapped pointer) completes the peer's rows without a merge pass.  The peer's
+    band needs a margin so that `span` fits: the groups along the cut also own pixels outside the shared rows."""
+    mine = shard_image(plan, rank, world)
+    out = []
+    for peer, lo, hi in overlaps(plan, rank, world):
+        g = plan.groups_in_rows(mine["group_begin"], mine["group_end"], lo, hi)
+        if g["first"] < g["last"]:
+            out.append({"peer": peer, "row_lo": lo, "row_hi": hi, **g})
+    return out

@@ -262,6 +262,15 @@ int fri_predict_device(fri_plan *plan, const int32_t *d_coefs, uint32_t n_frames
  *                   parts share each writes its own pixels and leaves the others alone, so bands that start from
  *                   zero merge by addition (the one exchange step of the split: the overlap rows between
  *                   neighbours; see frave_b200/sharding.py and bench.py --workload image16k).
+ *   fri_plan_groups_in_rows     the smallest contiguous sub-range [first, last) of groups [group_begin, group_end)
+ *                   that contains every group touching pixel rows [row_begin, row_end), and the rows
+ *                   [span_begin, span_end) that sub-range touches in all.
+ *   fri_decode_tq_device_groups  the inverse transform of an arbitrary range of groups: d_coef_tiles points at the
+ *                   block of tile `tile_first`, d_pixel_rows at frame row `row_first` (may be negative: a band with
+ *                   a margin above row 0).  With a PEER-MAPPED band as the target this is the halo exchange done by
+ *                   the transform kernel's own stores: a rank re-runs its groups along the cut into the neighbour's
+ *                   band (which needs a margin of span rows around the shared ones), no zeroing, no merge pass —
+ *                   only a barrier afterwards (bench.py --workload image16k, exchange "peer").
  * No collective inside the library; one frame per call; FRI_E_UNSUPPORTED at depth > 9.
  */
 int fri_plan_part(const fri_plan *plan, uint32_t part, uint32_t n_parts, uint32_t *group_begin, uint32_t *group_end,
@@ -270,6 +279,11 @@ int fri_encode_tq_device_part(const fri_plan *plan, const void *d_pixel_rows, co
                               uint32_t part, uint32_t n_parts, void *stream);
 int fri_decode_tq_device_part(const fri_plan *plan, const int32_t *d_coef_tiles, const int32_t *q, int dequant_mode,
                               void *d_pixel_rows, uint32_t part, uint32_t n_parts, void *stream);
+int fri_plan_groups_in_rows(const fri_plan *plan, uint32_t group_begin, uint32_t group_end, uint32_t row_begin, uint32_t row_end,
+                            uint32_t *first, uint32_t *last, uint32_t *span_begin, uint32_t *span_end);
+int fri_decode_tq_device_groups(const fri_plan *plan, const int32_t *d_coef_tiles, uint32_t tile_first, const int32_t *q,
+                                int dequant_mode, void *d_pixel_rows, int32_t row_first, uint32_t group_begin, uint32_t group_end,
+                                void *stream);
 
 /*
  * The host side of the codec behind the transform (depth 9, 8-bit samples):

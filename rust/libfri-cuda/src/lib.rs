@@ -70,6 +70,8 @@ extern "C" {
     fn fri_plan_part(plan: *const FriPlan, part: u32, n_parts: u32, group_begin: *mut u32, group_end: *mut u32, tile_begin: *mut u32, tile_end: *mut u32, row_begin: *mut u32, row_end: *mut u32) -> c_int;
     fn fri_encode_tq_device_part(plan: *const FriPlan, d_pixel_rows: *const c_void, q: *const i32, d_coef_tiles: *mut i32, part: u32, n_parts: u32, stream: *mut c_void) -> c_int;
     fn fri_decode_tq_device_part(plan: *const FriPlan, d_coef_tiles: *const i32, q: *const i32, dequant_mode: c_int, d_pixel_rows: *mut c_void, part: u32, n_parts: u32, stream: *mut c_void) -> c_int;
+    fn fri_plan_groups_in_rows(plan: *const FriPlan, group_begin: u32, group_end: u32, row_begin: u32, row_end: u32, first: *mut u32, last: *mut u32, span_begin: *mut u32, span_end: *mut u32) -> c_int;
+    fn fri_decode_tq_device_groups(plan: *const FriPlan, d_coef_tiles: *const i32, tile_first: u32, q: *const i32, dequant_mode: c_int, d_pixel_rows: *mut c_void, row_first: i32, group_begin: u32, group_end: u32, stream: *mut c_void) -> c_int;
     fn fri_predict_host(plan: *mut FriPlan, coefs: *const i32, value_params: *const f32, width_params: *const f32, bucket: *mut u8, pred: *mut i32, sym: *mut u16, hist: *mut u32, overflow: *mut u32) -> c_int;
     fn fri_frv_pack(plan: *mut FriPlan, colorspace: c_int, value_params: *const f32, width_params: *const f32, bucket: *const u8, sym: *const u16, hist: *const u32, out: *mut *mut u8, out_len: *mut usize) -> c_int;
     fn fri_frv_unpack(plan: *mut FriPlan, bytes: *const u8, len: usize, coefs: *mut i32) -> c_int;
@@ -351,6 +353,21 @@ impl Plan {
     pub unsafe fn decode_device_part(&self, d_coef_tiles: *const i32, q: &[i32; 32], d_pixel_rows: *mut c_void, part: u32, n_parts: u32,
                                      stream: *mut c_void) -> Result<(), String> {
         check(fri_decode_tq_device_part(self.raw, d_coef_tiles, q.as_ptr(), FRI_DEQUANT_DIVIDE, d_pixel_rows, part, n_parts, stream))
+    }
+    /// Groups of `[group_begin, group_end)` touching pixel rows `[row_begin, row_end)`: ((first, last), (span_begin, span_end)).
+    pub fn groups_in_rows(&self, group_begin: u32, group_end: u32, row_begin: u32, row_end: u32) -> Result<[(u32, u32); 2], String> {
+        let mut v = [0u32; 4];
+        let p = v.as_mut_ptr();
+        check(unsafe { fri_plan_groups_in_rows(self.raw, group_begin, group_end, row_begin, row_end, p, p.add(1), p.add(2), p.add(3)) })?;
+        Ok([(v[0], v[1]), (v[2], v[3])])
+    }
+    /// # Safety
+    /// `d_coef_tiles` points at tile `tile_first`'s block, `d_pixel_rows` at frame row `row_first`; both must cover what the
+    /// groups touch (the target may be a peer-mapped band of another GPU).
+    #[allow(clippy::too_many_arguments)]
+    pub unsafe fn decode_device_groups(&self, d_coef_tiles: *const i32, tile_first: u32, q: &[i32; 32], d_pixel_rows: *mut c_void, row_first: i32,
+                                       group_begin: u32, group_end: u32, stream: *mut c_void) -> Result<(), String> {
+        check(fri_decode_tq_device_groups(self.raw, d_coef_tiles, tile_first, q.as_ptr(), FRI_DEQUANT_DIVIDE, d_pixel_rows, row_first, group_begin, group_end, stream))
     }
     /// Host predictor (what the serial entropy decoder evaluates): see include/fri_cuda.h for the array shapes.
     #[allow(clippy::too_many_arguments)]

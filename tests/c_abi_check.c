@@ -22,7 +22,7 @@ int main(void)
         (fn)fri_emit_device16, (fn)fri_encode_tq_emit16, (fn)fri_unemit_device, (fn)fri_unemit_device16,
         (fn)fri_decode_tq_emit, (fn)fri_decode_tq_emit16, (fn)fri_plan_emission_packed_bytes, (fn)fri_plan_emission_packed_size, (fn)fri_emit_device_packed,
         (fn)fri_encode_tq_emit_packed, (fn)fri_unemit_device_packed, (fn)fri_decode_tq_emit_packed, (fn)fri_emit_device10,
-        (fn)fri_encode_tq_emit10, (fn)fri_unemit_device10, (fn)fri_decode_tq_emit10, (fn)fri_predict_device, (fn)fri_fit_parameters, (fn)fri_fit_device, (fn)fri_plan_part, (fn)fri_encode_tq_device_part, (fn)fri_decode_tq_device_part, (fn)fri_predict_host, (fn)fri_frv_pack, (fn)fri_frv_unpack,
+        (fn)fri_encode_tq_emit10, (fn)fri_unemit_device10, (fn)fri_decode_tq_emit10, (fn)fri_predict_device, (fn)fri_fit_parameters, (fn)fri_fit_device, (fn)fri_plan_part, (fn)fri_encode_tq_device_part, (fn)fri_decode_tq_device_part, (fn)fri_plan_groups_in_rows, (fn)fri_decode_tq_device_groups, (fn)fri_predict_host, (fn)fri_frv_pack, (fn)fri_frv_unpack,
         (fn)fri_frv_info, (fn)fri_frv_encode, (fn)fri_frv_decode, (fn)fri_frv_free, (fn)fri_plan_set_bands, (fn)fri_plan_set_async, (fn)fri_plan_set_independent_calls, (fn)fri_plan_sync, (fn)fri_host_alloc, (fn)fri_host_free,
         (fn)fri_plan_last_launches, (fn)fri_quant_divide, (fn)fri_quant_divide_magic, (fn)fri_quant_divide_small,
     };

@@ -445,5 +445,25 @@ def test_image_split_by_tile_group_ranges(shape, dtype, n_parts):
             seen_tiles += t1 - t0
         assert seen_tiles == plan.n_tiles
         assert np.array_equal(merged.cpu().numpy().astype(dtype), full)
+        # the same exchange done by the kernel's own stores (what N ranks do over peer-mapped bands): every part
+        # decodes its tiles into its own band, then re-runs its groups along each cut into the neighbour's band;
+        # no zeroing, no merge — bands start as garbage and must end up complete
+        if plan.pixels_covered == w * h:
+            margin = plan.launch_info()["region_h"]
+            parts = [sharding.shard_image(plan, r, n_parts) for r in range(n_parts)]
+            dcoefs = torch.from_numpy(want).cuda()
+            bands = [torch.full((p["row_end"] - p["row_begin"] + 2 * margin, w, c), 77, dtype=tdt, device="cuda") for p in parts]
+            stride = w * c * sb
+            for r, p in enumerate(parts):
+                own = bands[r].data_ptr() + margin * stride
+                plan.decode_device_part(dcoefs[p["tile_begin"]:].data_ptr(), own, r, n_parts, q)
+                for push in sharding.halo_pushes(plan, r, n_parts):
+                    peer = parts[push["peer"]]
+                    assert peer["row_begin"] - margin <= push["span_begin"] and push["span_end"] <= peer["row_end"] + margin
+                    plan.decode_device_groups(dcoefs[p["tile_begin"]:].data_ptr(), p["tile_begin"], bands[push["peer"]].data_ptr(),
+                                              peer["row_begin"] - margin, push["first"], push["last"], q)
+            for r, p in enumerate(parts):
+                got = bands[r][margin:margin + p["row_end"] - p["row_begin"]].cpu().numpy().view(dtype)
+                assert np.array_equal(got, full[p["row_begin"]:p["row_end"]]), f"band {r} is incomplete after the pushes"
         with pytest.raises(capi.FriError):
             plan.encode_device_part(band.data_ptr(), coefs.data_ptr(), n_parts, n_parts, q)

@@ -250,6 +250,13 @@ def test_image_parts_partition_the_plan():
                     assert not own[:p["row_begin"]].any() and not own[p["row_end"]:].any()
                     for peer, lo, hi in sharding.overlaps(plan, r, world):
                         assert peer != r and p["row_begin"] <= lo < hi <= p["row_end"]
+                    margin = plan.launch_info()["region_h"]
+                    for push in sharding.halo_pushes(plan, r, world):  # the groups along the cut, for the peer-memory exchange
+                        assert p["group_begin"] <= push["first"] < push["last"] <= p["group_end"]
+                        assert push["span_begin"] < push["row_hi"] and push["span_end"] > push["row_lo"]
+                        if abs(push["peer"] - r) == 1 and world <= 3:  # neighbours: the span fits the peer's band plus one region height
+                            assert parts[push["peer"]]["row_begin"] - margin <= push["span_begin"]
+                            assert push["span_end"] <= parts[push["peer"]]["row_end"] + margin
             with pytest.raises(capi.FriError):
                 plan.part(2, 2)
             with pytest.raises(capi.FriError):
