@@ -821,13 +821,13 @@ def run_image_split(args, rank: int, local_rank: int, world: int) -> None:
                 a = i % n_sets
                 plan.encode_device_part(bands[a].data_ptr(), coefs[a].data_ptr(), rank, world, q, stream)
                 launches += plan.last_launches
-                plan.decode_device_part(coefs[a].data_ptr(), p_outs[a].data_ptr(), rank, world, q, False, stream)
-                launches += plan.last_launches
-                for ps in pushes:
+                for ps in pushes:  # first, so that the remote stores are in flight while the own tiles are decoded
                     target = int(hdl.buffer_ptrs[ps["peer"]]) + a * set_bytes  # the peer's band incl. its margin
                     plan.decode_device_groups(coefs[a].data_ptr(), t_lo, target, parts[ps["peer"]]["row_begin"] - margin,
                                               ps["first"], ps["last"], q, False, stream)
                     launches += plan.last_launches
+                plan.decode_device_part(coefs[a].data_ptr(), p_outs[a].data_ptr(), rank, world, q, False, stream)
+                launches += plan.last_launches
                 hdl.barrier(channel=0)  # every rank's pushes have landed
 
             for a_ in range(n_sets):
