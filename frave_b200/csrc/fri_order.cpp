@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "fri_plan.h"
@@ -116,10 +117,10 @@ std::string build_emission_order(const Plan &plan, std::vector<uint32_t> &order)
     auto in_box = [&](P p) { return p.y <= max_imag && p.y >= min_imag && p.x <= max_real && p.x >= min_real; };
     const int64_t guard = 64ll * ((int64_t)(max_real - min_real + 64) * (max_imag - min_imag + 64)) + 1024;  // runaway stop
 
-    order.resize((size_t)n_tiles * kTileLeaves);
-    size_t w = 0;  // write cursor: DCs, roots, then levels 1..8
+    order.resize((size_t)n_tiles * kTileLeaves);  // DCs, roots, then levels 1..8: every level owns its segment
     const P center{L.ax, L.ay};
-    for (int level = 0; level < kBaseDepth; ++level) {
+    // The levels are scanned independently of one another (one host thread each: level 8 is half of the work).
+    auto scan_one_level = [&](int level) -> std::string {
         // ---- scan_level (:505-654), statement for statement
         Vec2 nv[6];
         nearby_vectors(kBaseDepth - level, nv);
@@ -214,9 +215,23 @@ std::string build_emission_order(const Plan &plan, std::vector<uint32_t> &order)
         if (count != expect)  // the reference's assert_eq! at :701 — it would panic for this image size
             return "the reference's sort_lattice assertion (wavelet_transform.rs:701) fails for this image size: level " +
                    std::to_string(level) + " scan visits " + std::to_string(count) + " of " + std::to_string(expect) + " nodes";
-        w += expect;
+        return {};
+    };
+    std::string level_err[kBaseDepth];
+    {
+        std::vector<std::thread> workers;
+        for (int level = 0; level < kBaseDepth; ++level)
+            workers.emplace_back([&, level] {
+                try {
+                    level_err[level] = scan_one_level(level);
+                } catch (const std::exception &e) {
+                    level_err[level] = std::string("emission order: ") + e.what();
+                }
+            });
+        for (auto &t : workers) t.join();
     }
-    (void)w;
+    for (int level = 0; level < kBaseDepth; ++level)
+        if (!level_err[level].empty()) return level_err[level];
     // every (tile, coefficient) must appear exactly once
     std::vector<uint8_t> seen(order.size(), 0);
     for (uint32_t v : order) {
