@@ -265,6 +265,25 @@ def test_image_parts_partition_the_plan():
         with pytest.raises(capi.FriError) as ei:
             deep.part(0, 2)
         assert ei.value.code == capi.FRI_E_UNSUPPORTED
+        with pytest.raises(capi.FriError) as ei:
+            deep.groups_in_rows(0, 1, 0, 10)
+        assert ei.value.code == capi.FRI_E_UNSUPPORTED
+    with capi.Plan(320, 240, 3, device=-1) as plan:
+        n_groups = plan.launch_info()["n_groups"]
+        whole = plan.groups_in_rows(0, n_groups, 0, 240)
+        assert (whole["first"], whole["last"], whole["span_begin"], whole["span_end"]) == (0, n_groups, 0, 240)
+        none = plan.groups_in_rows(0, n_groups, 240, 240)
+        assert none["first"] == none["last"]
+        for bad in ((5, 2), (0, n_groups + 1)):
+            with pytest.raises(capi.FriError) as ei:
+                plan.groups_in_rows(bad[0], bad[1], 0, 10)
+            assert ei.value.code == capi.FRI_E_INVALID
+            with pytest.raises(capi.FriError) as ei:
+                plan.decode_device_groups(16, 0, 16, 0, bad[0], bad[1])
+            assert ei.value.code == capi.FRI_E_INVALID
+        with pytest.raises(capi.FriError) as ei:  # a valid range still needs a device: no CPU fallback
+            plan.decode_device_groups(16, 0, 16, 0, 0, 1)
+        assert ei.value.code == capi.FRI_E_CUDA
 
 
 _WORKER = r"""
