@@ -1561,16 +1561,25 @@ int fri_frv_encode(fri_plan *p, const void *pixels, const int32_t *q, int colors
         PredictParams prm{};
         std::memcpy(prm.value, vp.data(), sizeof(float) * 18 * C);
         std::memcpy(prm.width, wp.data(), sizeof(float) * 18 * C);
+        // buckets + symbols come back through pinned memory kept with the plan (150 MB for 4096 x 4096 x 3:
+        // pageable destinations cost 20x the copy time)
+        if (!p->h_symbols) FRI_CUDA(cudaHostAlloc(&p->h_symbols, (size_t)C * count * 3 + 16, cudaHostAllocDefault));
         uint8_t *d_bucket = nullptr;
         int32_t *d_pred = nullptr;  // the predictions themselves are not needed: the symbols carry the residuals
         uint16_t *d_sym = nullptr;
         uint32_t *d_hist = nullptr;
+        struct Scratch {  // stream-ordered frees on every way out of this scope
+            void **slots[3];
+            cudaStream_t st;
+            ~Scratch()
+            {
+                for (void **d : slots)
+                    if (*d) cudaFreeAsync(*d, st);
+            }
+        } scratch{{reinterpret_cast<void **>(&d_bucket), reinterpret_cast<void **>(&d_sym), reinterpret_cast<void **>(&d_hist)}, st};
         if ((rc = pool_alloc(p, reinterpret_cast<void **>(&d_bucket), (size_t)C * count, st))) return rc;
         if ((rc = pool_alloc(p, reinterpret_cast<void **>(&d_sym), (size_t)C * count * sizeof(uint16_t), st))) return rc;
         if ((rc = pool_alloc(p, reinterpret_cast<void **>(&d_hist), (n_hist + 1) * sizeof(uint32_t), st))) return rc;
-        // buckets + symbols come back through pinned memory kept with the plan (150 MB for 4096 x 4096 x 3:
-        // pageable destinations cost 20x the copy time)
-        if (!p->h_symbols) FRI_CUDA(cudaHostAlloc(&p->h_symbols, (size_t)C * count * 3 + 16, cudaHostAllocDefault));
         uint16_t *sym = static_cast<uint16_t *>(p->h_symbols);
         uint8_t *bucket = reinterpret_cast<uint8_t *>(sym + (size_t)C * count);
         std::vector<uint32_t> hist(n_hist + 1);
@@ -1580,7 +1589,6 @@ int fri_frv_encode(fri_plan *p, const void *pixels, const int32_t *q, int colors
         FRI_CUDA(cudaMemcpyAsync(bucket, d_bucket, (size_t)C * count, cudaMemcpyDeviceToHost, st));
         FRI_CUDA(cudaMemcpyAsync(sym, d_sym, (size_t)C * count * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
         FRI_CUDA(cudaMemcpyAsync(hist.data(), d_hist, hist.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        for (void *d : {(void *)d_bucket, (void *)d_sym, (void *)d_hist}) cudaFreeAsync(d, st);
         FRI_CUDA(cudaEventRecord(s.compute_done, st));
         FRI_CUDA(cudaEventRecord(s.out_done, st));
         s.used = true;
