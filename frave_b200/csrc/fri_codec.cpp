@@ -353,8 +353,18 @@ inline int Predictor::step_tile(int tile, const NodeStep &n) const
 void Predictor::neighbour_values(const int32_t *coefs, int tile, int heap, int ch, int32_t v[6]) const
 {
     const HeapSteps &hs = steps[heap];
+    const int32_t *adj = adjacent.data() + (size_t)tile * 9;
+    if (heap < 128 || heap >= 256) {  // every level but 7: the six regular positions
+#pragma GCC unroll 6
+        for (int j = 0; j < 6; ++j) {
+            const NodeStep n = hs.regular[j];
+            const int t = n.heap < 0 ? -1 : adj[n.cell];
+            v[j] = t >= 0 ? coefs[(((size_t)t * channels + ch) << kBaseDepth) + (j < 3 ? n.heap : n.heap >> 1)] : 0;
+        }
+        return;
+    }
     const NodeStep *sel[6] = {&hs.regular[0], &hs.regular[1], &hs.regular[2], &hs.regular[3], &hs.regular[4], &hs.regular[5]};
-    if (heap >= 128 && heap < 256) {  // level 7 (depth 2): wavelet_transform.rs:115-177
+    {  // level 7 (depth 2): wavelet_transform.rs:115-177
         const bool alt_down = step_tile(tile, hs.probe[0]) < 0 && step_tile(tile, hs.probe[1]) >= 0;
         const bool alt_up = step_tile(tile, hs.probe[2]) < 0 && step_tile(tile, hs.probe[3]) >= 0;
         if (alt_up) { sel[1] = &hs.alt[0]; sel[2] = &hs.alt[1]; }
@@ -627,9 +637,18 @@ std::string entropy_decode_channel(const ChannelPayload &in, const Predictor &pr
         // the next cell's
         const Coarse &cs = coarse[bucket];
         const uint32_t cell = got >> cs.shift;
-        const uint32_t *lo = c.cdf.data() + cs.first[cell], *hi = c.cdf.data() + cs.first[cell + 1] + 1;
-        int symbol = (int)(std::upper_bound(lo, hi, got) - c.cdf.data()) - 1;
-        if (symbol < 0) symbol = 0;
+        int symbol = cs.first[cell];
+        const int sym_hi = cs.first[cell + 1];
+        if (symbol != sym_hi) {  // several symbols share the cell: the last one whose cdf is <= got (branch-free count)
+            const uint32_t *cdf = c.cdf.data();
+            if (sym_hi - symbol <= 8) {
+                int n = 0;
+                for (int i = symbol + 1; i <= sym_hi; ++i) n += cdf[i] <= got;
+                symbol += n;  // cdf is non-decreasing: the qualifying entries are a prefix
+            } else {
+                symbol = (int)(std::upper_bound(cdf + symbol, cdf + sym_hi + 1, got) - cdf) - 1;
+            }
+        }
         if (c.freqs[symbol] == 0) return "corrupt stream: decoded a symbol with zero frequency";
         dec.advance_at(pos, c.cdf[symbol], c.freqs[symbol], c.max_freq_bits);
         if (dec.overrun()) return "corrupt stream: entropy-coded data ends early";
