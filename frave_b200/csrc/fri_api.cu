@@ -9,6 +9,7 @@
 #include <thread>
 #include <cstdlib>
 #include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -97,7 +98,7 @@ struct fri_plan {
     bool emit_device_ready = false;     // all three tables uploaded
     // prediction tables (computed on first use)
     bool predict_ready = false;
-    void *d_pred_tile_at = nullptr, *d_pred_centers = nullptr, *d_pred_lut = nullptr, *d_pred_off = nullptr;
+    void *d_pred_adjacent = nullptr, *d_pred_steps = nullptr;
     void *h_dense = nullptr;    // pinned staging of fri_frv_decode: one frame of dense blocks
     void *h_symbols = nullptr;  // pinned staging of fri_frv_encode: [C][count] u16 symbols, then [C][count] u8 buckets
     PredictTables predict_tables;
@@ -416,7 +417,7 @@ void fri_plan_destroy(fri_plan *p)
         if (p->d_emit_dst) cudaFree(p->d_emit_dst);
         if (p->d_emit_loc) cudaFree(p->d_emit_loc);
         if (p->d_stage_list) cudaFree(p->d_stage_list);
-        for (void *d : {p->d_pred_tile_at, p->d_pred_centers, p->d_pred_lut, p->d_pred_off})
+        for (void *d : {p->d_pred_adjacent, p->d_pred_steps})
             if (d) cudaFree(d);
         if (p->h_symbols) cudaFreeHost(p->h_symbols);
         if (p->h_dense) cudaFreeHost(p->h_dense);
@@ -1234,46 +1235,52 @@ int fri_decode_tq_emit_packed(fri_plan *p, const uint8_t *streams, uint32_t n_fr
 }
 
 /* ---- prediction + context bucketing, encode side ------------------------ */
+static int ensure_lattice(fri_plan *p);
+
 static int ensure_predict_device(fri_plan *p)
 {
     int rc = ensure_emission_device(p);
     if (rc) return rc;
     if (p->predict_ready) return FRI_OK;
-    LatticeIndex L;
-    std::vector<short2> off(kTileLeaves);
+    if ((rc = ensure_lattice(p))) return rc;
+    // the device image of the host predictor's neighbour tables (codec::Predictor, fri_codec.cpp)
+    std::vector<uint32_t> steps((size_t)kTileLeaves * 14);
+    PredictTables &t = p->predict_tables;
+    std::vector<int32_t> adjacent;
     try {
-        build_lattice_index(p->plan, L);
+        const codec::Predictor pr(p->lattice, p->plan.centers.data(), p->plan.geo.channels);
+        auto pack = [](const codec::Predictor::NodeStep &n) { return n.heap < 0 ? 0xffffu : ((uint32_t)n.heap | (uint32_t)n.cell << 16); };
+        for (int h = 0; h < kTileLeaves; ++h) {
+            const codec::Predictor::HeapSteps &hs = pr.steps[h];
+            uint32_t *o = steps.data() + (size_t)h * 14;
+            for (int j = 0; j < 6; ++j) o[j] = pack(hs.regular[j]);
+            for (int j = 0; j < 4; ++j) o[6 + j] = pack(hs.alt[j]);
+            for (int j = 0; j < 4; ++j) o[10 + j] = pack(hs.probe[j]);
+        }
+        adjacent = pr.adjacent;
+        adjacent.resize((size_t)p->plan.geo.n_fractals * 9, -1);
+        for (int j = 0; j < 3; ++j) t.lf_cell[j] = pr.lf_cell[j];
     } catch (const std::bad_alloc &) {
-        return fail(FRI_E_NOMEM, "out of host memory while building the lattice index");
+        return fail(FRI_E_NOMEM, "out of host memory while building the prediction tables");
+    } catch (const std::logic_error &e) {
+        return fail(FRI_E_UNSUPPORTED, "%s", e.what());
     }
-    for (int k = 0; k < kTileLeaves; ++k) off[k] = make_short2((short)L.off[k].x, (short)L.off[k].y);
     auto upload = [&](void **d, const void *h, size_t bytes) -> cudaError_t {
         cudaError_t e = cudaMalloc(d, bytes ? bytes : 4);
         return e != cudaSuccess || bytes == 0 ? e : cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice);
     };
-    cudaError_t e = upload(&p->d_pred_tile_at, L.tile_at.data(), L.tile_at.size() * sizeof(int32_t));
-    if (e == cudaSuccess) e = upload(&p->d_pred_centers, p->plan.centers.data(), p->plan.centers.size() * sizeof(int32_t));
-    if (e == cudaSuccess) e = upload(&p->d_pred_lut, L.lut, sizeof(L.lut));
-    if (e == cudaSuccess) e = upload(&p->d_pred_off, off.data(), off.size() * sizeof(short2));
+    cudaError_t e = upload(&p->d_pred_adjacent, adjacent.data(), adjacent.size() * sizeof(int32_t));
+    if (e == cudaSuccess) e = upload(&p->d_pred_steps, steps.data(), steps.size() * sizeof(uint32_t));
     if (e == cudaSuccess) e = configure_predict_kernel();
     if (e != cudaSuccess) {
-        for (void **d : {&p->d_pred_tile_at, &p->d_pred_centers, &p->d_pred_lut, &p->d_pred_off}) {
+        for (void **d : {&p->d_pred_adjacent, &p->d_pred_steps}) {
             if (*d) cudaFree(*d);
             *d = nullptr;
         }
         return cuda_fail(e, "uploading the prediction tables");
     }
-    PredictTables &t = p->predict_tables;
-    t.tile_at = static_cast<const int32_t *>(p->d_pred_tile_at);
-    t.centers = static_cast<const int32_t *>(p->d_pred_centers);
-    t.lut = static_cast<const uint16_t *>(p->d_pred_lut);
-    t.off = static_cast<const short2 *>(p->d_pred_off);
-    t.ax = L.ax; t.ay = L.ay; t.amin = L.amin; t.bmin = L.bmin; t.na = L.na; t.nb = L.nb;
-    for (int d = 0; d < 10; ++d) {
-        Vec2 nv[6] = {};
-        if (d >= 1) nearby_vectors(d, nv);
-        for (int j = 0; j < 6; ++j) t.nearby[d][j] = make_short2((short)nv[j].x, (short)nv[j].y);
-    }
+    t.adjacent = static_cast<const int32_t *>(p->d_pred_adjacent);
+    t.steps = static_cast<const uint32_t *>(p->d_pred_steps);
     p->predict_ready = true;
     return FRI_OK;
 }

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <thread>
@@ -319,6 +320,16 @@ Predictor::Predictor(const LatticeIndex &l, const int32_t *c, int ch) : lat(l), 
         r.cell = (int8_t)((db + 1) * 3 + (da + 1));
         return r;
     };
+    {
+        const int sel[3] = {4, 5, 0};
+        for (int j = 0; j < 3; ++j) {  // whole-tile steps: the level-9 neighbour vectors are lattice vectors
+            const Vec2 d = nearby[kBaseDepth][sel[j]];
+            const int64_t na_ = (int64_t)d.x * l10.y - (int64_t)l10.x * d.y, nb_ = (int64_t)l9.x * d.y - (int64_t)d.x * l9.y;
+            if (na_ % 512 != 0 || nb_ % 512 != 0 || std::llabs(na_ / 512) > 1 || std::llabs(nb_ / 512) > 1)
+                throw std::logic_error("a level-9 neighbour vector is not a step to an adjacent tile");
+            lf_cell[j] = (int)((nb_ / 512 + 1) * 3 + (na_ / 512 + 1));
+        }
+    }
     for (int heap = 0; heap < kTileLeaves; ++heap) {
         HeapSteps &hs = steps[heap];
         for (NodeStep &n : hs.regular) n = NodeStep{-1, 4};
@@ -378,12 +389,9 @@ void Predictor::neighbour_values(const int32_t *coefs, int tile, int heap, int c
 
 void Predictor::lf(const int32_t *coefs, int tile, int heap, int ch, int &bucket, int32_t &prediction) const
 {
-    const int cx = centers[2 * tile], cy = centers[2 * tile + 1];
-    const int sel[3] = {4, 5, 0};
     int32_t v[3];
     for (int j = 0; j < 3; ++j) {
-        const Vec2 d = nearby[kBaseDepth][sel[j]];
-        const int t = lat.tile_of(cx + d.x, cy + d.y);
+        const int t = adjacent[(size_t)tile * 9 + lf_cell[j]];
         v[j] = t >= 0 ? coefs[(((size_t)t * channels + ch) << kBaseDepth) + heap] : 0;
     }
     const uint32_t width = (uint32_t)std::abs((int64_t)v[0] - v[2]);

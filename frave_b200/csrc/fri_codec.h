@@ -96,6 +96,7 @@ struct Predictor {
     struct HeapSteps { NodeStep regular[6], alt[4], probe[4]; };
     HeapSteps steps[kTileLeaves];       // per heap index: where its neighbours sit, relative to the tile
     std::vector<int32_t> adjacent;      // [n_tiles][9] plan index of the tile one lattice step away, -1 if none
+    int lf_cell[3];                     // adjacency cells of the tiles at centre + v9[4], v9[5], v9[0] (prediction.rs:86-149)
     Predictor(const LatticeIndex &l, const int32_t *c, int ch);
     int step_tile(int tile, const NodeStep &n) const;
     // neighbour values of the level-`level` node `heap` of `tile` (context_modeling.rs:25-77), levels 1..8

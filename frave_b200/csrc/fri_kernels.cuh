@@ -143,15 +143,12 @@ cudaError_t launch_emit(const Geometry &g, const DeviceTables &t, const EmitTabl
 cudaError_t launch_unemit(const Geometry &g, const DeviceTables &t, const EmitTables &et, uint64_t count, const void *d_in,
                           bool half, uint32_t n_frames, int32_t *d_coefs, cudaStream_t stream, uint32_t *launches);
 
-// Prediction + context bucketing (fri_predict.cu).  Device image of LatticeIndex plus
-// the neighbour vectors of every depth (get_nearby_vectors, wavelet_transform.rs:71-90).
+// Prediction + context bucketing (fri_predict.cu).  Device image of codec::Predictor's
+// neighbour tables (fri_codec.h): where a coefficient's neighbours sit, per heap index, and every tile's adjacent tiles.
 struct PredictTables {
-    const int32_t *tile_at = nullptr;  // [nb][na]
-    const int32_t *centers = nullptr;  // [n_tiles][2]
-    const uint16_t *lut = nullptr;     // [512]
-    const short2 *off = nullptr;       // [512]
-    int ax = 0, ay = 0, amin = 0, bmin = 0, na = 0, nb = 0;
-    short2 nearby[10][6];
+    const int32_t *adjacent = nullptr;  // [n_tiles][9] plan index of the tile one lattice step away ((db+1)*3 + da+1), -1 if none
+    const uint32_t *steps = nullptr;    // [512][14] per heap index: regular[6], alt[4], probe[4] as heap | cell << 16 (0xffff: none)
+    int lf_cell[3] = {4, 4, 4};         // adjacency cells of the tiles at centre + v9[4], v9[5], v9[0]
 };
 struct PredictParams {  // value / width predictor parameters per channel and layer set (prediction.rs:164-178)
     float value[3][3][6];

@@ -38,121 +38,99 @@ __device__ __forceinline__ int assign_bucket_u32(unsigned w)  // prediction.rs:5
     return w < 3 ? 0 : w < 5 ? 1 : w < 6 ? 2 : w < 8 ? 3 : w < 12 ? 4 : w < 16 ? 5 : w < 20 ? 6 : w < 25 ? 7 : w < 30 ? 8 : 9;
 }
 
-struct NodeRef {
-    int tile;  // -1: no such node
-    int heap;
-};
+// Where the six neighbours of a coefficient sit does not depend on the tile: per heap index the plan holds
+// (heap index, step to an adjacent tile) pairs — built on the host by running the reference's lattice queries once
+// for a virtual tile (codec::Predictor, fri_codec.cpp) — and per tile the plan indices of its eight neighbours.
+// A step is packed as heap | cell << 16, heap == 0xffff: no node at that position in any tile.
+constexpr int kStepsPerHeap = 14;  // regular[6], alt[4], probe[4]
 
-struct Lookup {
-    const PredictTables &pt;
-    const uint16_t *lut;  // shared memory copies
-    const short2 *off;
-
-    __device__ __forceinline__ int tile_of(int cx, int cy) const
-    {
-        constexpr Vec2 l9 = kLiterals[kBaseDepth], l10 = kLiterals[kBaseDepth + 1];
-        const int dx = cx - pt.ax, dy = cy - pt.ay;
-        const int na_ = dx * l10.y - l10.x * dy, nb_ = l9.x * dy - dx * l9.y;
-        if ((na_ & 511) || (nb_ & 511)) return -1;
-        const int a = (na_ >> 9) - pt.amin, b = (nb_ >> 9) - pt.bmin;  // exact: multiples of 512
-        if (a < 0 || b < 0 || a >= pt.na || b >= pt.nb) return -1;
-        return __ldg(pt.tile_at + (size_t)b * pt.na + a);
-    }
-    __device__ __forceinline__ NodeRef node_at(int level, int x, int y) const
-    {
-        const int k = lut[((x - pt.ax) + 181 * (y - pt.ay)) & 511];
-        const int low = kBaseDepth - level;
-        if (k & ((1 << low) - 1)) return NodeRef{-1, 0};
-        const short2 o = off[k];
-        return NodeRef{tile_of(x - o.x, y - o.y), (1 << level) + (k >> low)};
-    }
-    __device__ __forceinline__ bool contains(int level, int x, int y) const { return node_at(level, x, y).tile >= 0; }
-};
-
-// get_neighbour_values (context_modeling.rs:25-77) of the level-`level` node `heap` of the tile centred at
-// (cx, cy): left, up-left, up-right on the node's own level, the parents of right, down-left, down-right.
-template <typename CoefAt>
-__device__ __forceinline__ void hf_neighbour_values(const Lookup &L, int cx, int cy, int heap, int level, CoefAt coef_at, int v[6])
+__device__ __forceinline__ int step_tile(const int32_t *__restrict__ adj_row, uint32_t st)
 {
-    const PredictTables &pt = L.pt;
-    const int d = kBaseDepth - level;
-    const short2 o = L.off[(heap - (1 << level)) << d];  // the node sits at its first leaf
-    const int px = cx + o.x, py = cy + o.y;
-    const short2 *nv = pt.nearby[d];
-    bool alt_up = false, alt_down = false;
-    if (d == 2) {  // wavelet_transform.rs:115-177: probes of the level-`depth` (= 2) map, kept as written
-        alt_down = !L.contains(2, px + nv[3].x, py + nv[3].y) && L.contains(2, px + 1, py + 1);
-        alt_up = !L.contains(2, px + nv[0].x, py + nv[0].y) && L.contains(2, px - 1, py - 1);
+    return (st & 0xffffu) == 0xffffu ? -1 : __ldg(adj_row + (st >> 16));
+}
+
+// Element offsets (channel 0) of the neighbour values of coefficient `heap` of `tile`, -1 where the neighbour does not
+// exist: get_lf_context_bucket's three (heap < 2) or get_neighbour_values' six (context_modeling.rs:25-77, with the
+// level-7 alternatives of wavelet_transform.rs:115-177).
+template <int C>
+__device__ __forceinline__ void neighbour_offsets(const PredictTables &pt, int tile, int heap, int off[6])
+{
+    const int32_t *adj = pt.adjacent + (size_t)tile * 9;
+    if (heap < 2) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int t = __ldg(adj + pt.lf_cell[j]);
+            off[j] = t >= 0 ? ((t * C) << kBaseDepth) + heap : -1;
+        }
+        off[3] = off[4] = off[5] = -1;
+        return;
     }
-    int qx[6], qy[6];
-    qx[0] = px + nv[4].x; qy[0] = py + nv[4].y;                                     // left
-    if (alt_up) { qx[1] = px - 1 + nv[4].x; qy[1] = py - 1 + nv[4].y; qx[2] = px - 1; qy[2] = py - 1; }
-    else { qx[1] = px + nv[5].x; qy[1] = py + nv[5].y; qx[2] = px + nv[0].x; qy[2] = py + nv[0].y; }  // up-left, up-right
-    qx[3] = px + nv[1].x; qy[3] = py + nv[1].y;                                     // right
-    if (alt_down) { qx[4] = px + 1; qy[4] = py + 1; qx[5] = px + 1 + nv[1].x; qy[5] = py + 1 + nv[1].y; }
-    else { qx[4] = px + nv[3].x; qy[4] = py + nv[3].y; qx[5] = px + nv[2].x; qy[5] = py + nv[2].y; }  // down-left, down-right
+    const uint32_t *hs = pt.steps + heap * kStepsPerHeap;
+    uint32_t st[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) st[j] = __ldg(hs + j);
+    if (heap >= 128 && heap < 256) {  // level 7: probes of the level-2 map, kept as written in the reference
+        const bool alt_down = step_tile(adj, __ldg(hs + 10)) < 0 && step_tile(adj, __ldg(hs + 11)) >= 0;
+        const bool alt_up = step_tile(adj, __ldg(hs + 12)) < 0 && step_tile(adj, __ldg(hs + 13)) >= 0;
+        if (alt_up) { st[1] = __ldg(hs + 6); st[2] = __ldg(hs + 7); }
+        if (alt_down) { st[4] = __ldg(hs + 8); st[5] = __ldg(hs + 9); }
+    }
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
-        const NodeRef n = L.node_at(level, qx[j], qy[j]);
-        v[j] = n.tile >= 0 ? coef_at(n.tile, j < 3 ? n.heap : n.heap >> 1) : 0;
+        const int t = step_tile(adj, st[j]);
+        const int h = (int)(st[j] & 0xffffu);
+        off[j] = t >= 0 ? ((t * C) << kBaseDepth) + (j < 3 ? h : h >> 1) : -1;
     }
 }
 
-// One CTA per (group, frame); thread per emitted slot of the group; channels in an outer loop so that the
-// per-context histograms of one channel (10 x 1024 counters) fit in shared memory.
-__global__ void __launch_bounds__(256)
+// One CTA per (group, frame), 1024 threads, one thread per emitted slot of the group and iteration: the neighbour
+// offsets are looked up once per slot, then every channel gathers its six values, predicts, and counts its symbol in
+// the channel's own 10 x 1024 histogram in shared memory (C x 40 KB); the histograms reach global memory as one atomic
+// per non-zero bin.
+constexpr int kPredictThreads = 1024;
+
+template <int C>
+__global__ void __launch_bounds__(kPredictThreads, 1)
 fri_predict_kernel(const __grid_constant__ PredictTables pt, const __grid_constant__ PredictParams prm,
                    const GroupDesc *__restrict__ groups,
                    const uint32_t *__restrict__ goff, const uint32_t *__restrict__ dst, const uint16_t *__restrict__ loc,
-                   unsigned long long count, int channels, int n_tiles, const int32_t *__restrict__ coefs,
+                   unsigned long long count, int n_tiles, const int32_t *__restrict__ coefs,
                    uint8_t *__restrict__ bucket_out, int32_t *__restrict__ pred_out, uint16_t *__restrict__ sym_out,
                    uint32_t *__restrict__ hist_out, uint32_t *__restrict__ overflow)
 {
-    __shared__ uint16_t s_lut[kTileLeaves];
-    __shared__ short2 s_off[kTileLeaves];
-    extern __shared__ __align__(16) uint32_t s_hist[];  // [10][1024]
-    for (int i = threadIdx.x; i < kTileLeaves; i += blockDim.x) {
-        s_lut[i] = pt.lut[i];
-        s_off[i] = pt.off[i];
-    }
-    const Lookup L{pt, s_lut, s_off};
+    extern __shared__ __align__(16) uint32_t s_hist[];  // [C][10][1024]
+    for (int i = threadIdx.x; i < C * kContexts * kAlphabet; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
     const GroupDesc gd = groups[blockIdx.x];
     const int frame = blockIdx.y;
     const uint32_t k0 = goff[blockIdx.x], k1 = goff[blockIdx.x + 1];
-    const int32_t *fc = coefs + (size_t)frame * n_tiles * channels * kTileLeaves;
-    auto coef_at = [&](int tile, int ch, int heap) { return __ldg(fc + (((size_t)tile * channels + ch) << kBaseDepth) + heap); };
+    const int32_t *fc = coefs + (size_t)frame * n_tiles * C * kTileLeaves;
 
-    for (int ch = 0; ch < channels; ++ch) {
-        for (int i = threadIdx.x; i < kContexts * kAlphabet; i += blockDim.x) s_hist[i] = 0;
-        __syncthreads();
-        const float *vp_all = prm.value[ch][0], *wp_all = prm.width[ch][0];
-        const size_t out_base = ((size_t)frame * channels + ch) * count;
-        for (uint32_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
-            const uint32_t l = __ldg(loc + k);
-            const int tile = (int)gd.tile_base + (int)(l >> kBaseDepth), heap = (int)(l & (kTileLeaves - 1));
-            const int cx = __ldg(pt.centers + 2 * tile), cy = __ldg(pt.centers + 2 * tile + 1);
+    for (uint32_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
+        const uint32_t l = __ldg(loc + k);
+        const int tile = (int)gd.tile_base + (int)(l >> kBaseDepth), heap = (int)(l & (kTileLeaves - 1));
+        int off[6];
+        neighbour_offsets<C>(pt, tile, heap, off);
+        const int self = ((tile * C) << kBaseDepth) + heap;
+        const size_t e0 = (size_t)frame * C * count + __ldg(dst + k);
+        const int level = 31 - __clz(max(heap, 1));
+        const int layer = level < kBaseDepth - 2 ? 2 : (level == kBaseDepth - 2 ? 1 : 0);
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) {
+            const int32_t *cc = fc + (ch << kBaseDepth);
+            int v[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) v[j] = off[j] >= 0 ? __ldg(cc + off[j]) : 0;
             int bucket, prediction;
             if (heap < 2) {
                 // ---- get_lf_context_bucket: the same coefficient of the tiles at centre + v9[4], v9[5], v9[0]
-                int v[3];
-                const int sel[3] = {4, 5, 0};
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    const short2 d = pt.nearby[kBaseDepth][sel[j]];
-                    const int t = L.tile_of(cx + d.x, cy + d.y);
-                    v[j] = t >= 0 ? coef_at(t, ch, heap) : 0;
-                }
                 const unsigned width = (unsigned)abs(v[0] - v[2]);
                 bucket = assign_bucket_u32(__float2uint_rz((float)width));
                 const int hi = max(v[0], v[2]), lo = min(v[0], v[2]);
                 prediction = v[1] >= hi ? hi : (v[1] <= lo ? lo : v[0] + v[2] - v[1]);
             } else {
                 // ---- get_hf_context_bucket
-                const int level = 31 - __clz(heap);
-                int v[6];
-                hf_neighbour_values(L, cx, cy, heap, level, [&](int t, int h) { return coef_at(t, ch, h); }, v);
-                const int layer = level < kBaseDepth - 2 ? 2 : (level == kBaseDepth - 2 ? 1 : 0);
-                const float *vp = vp_all + 6 * layer, *wp = wp_all + 6 * layer;
+                const float *vp = prm.value[ch][layer], *wp = prm.width[ch][layer];
                 float width = wp[0];
                 width = __fadd_rn(width, __fmul_rn(wp[1], (float)abs(v[0] - v[3])));
                 width = __fadd_rn(width, __fmul_rn(wp[2], (float)abs(v[1] - v[2])));
@@ -165,26 +143,24 @@ fri_predict_kernel(const __grid_constant__ PredictTables pt, const __grid_consta
                 for (int j = 1; j < 6; ++j) p = __fadd_rn(p, __fmul_rn((float)v[j], vp[j]));
                 prediction = __float2int_rz(p);                      // `as i32`: saturating, NaN -> 0
             }
-            const int value = coef_at(tile, ch, heap);
+            const int value = __ldg(cc + self);
             const int residual = (int)((unsigned)value - (unsigned)prediction);
             const unsigned sym = residual >= 0 ? 2u * (unsigned)residual : (unsigned)(-2 * residual - 1);  // pack_signed
-            const size_t e = out_base + __ldg(dst + k);
+            const size_t e = e0 + (size_t)ch * count;
             bucket_out[e] = (uint8_t)bucket;
             if (pred_out) pred_out[e] = prediction;
             sym_out[e] = (uint16_t)min(sym, 0xffffu);
-            if (sym < (unsigned)kAlphabet) atomicAdd(&s_hist[bucket * kAlphabet + sym], 1u);
+            if (sym < (unsigned)kAlphabet) atomicAdd(&s_hist[(ch * kContexts + bucket) * kAlphabet + sym], 1u);
             else if (overflow) atomicAdd(overflow, 1u);  // the reference indexes freqs[sym] and panics (entropy_coding.rs:99)
         }
-        __syncthreads();
-        uint32_t *h = hist_out + ((size_t)frame * channels + ch) * kContexts * kAlphabet;
-        for (int i = threadIdx.x; i < kContexts * kAlphabet; i += blockDim.x) {
-            const uint32_t c = s_hist[i];
-            if (c) atomicAdd(h + i, c);
-        }
-        __syncthreads();
+    }
+    __syncthreads();
+    uint32_t *h = hist_out + (size_t)frame * C * kContexts * kAlphabet;
+    for (int i = threadIdx.x; i < C * kContexts * kAlphabet; i += blockDim.x) {
+        const uint32_t c = s_hist[i];
+        if (c) atomicAdd(h + i, c);
     }
 }
-
 
 // ------------------------------------------------------------------------------------------
 // Predictor parameter fit (context_modeling.rs:144-214), accumulation side: the 6 x 6 normal equations of
@@ -203,20 +179,12 @@ fri_fit_kernel(const __grid_constant__ PredictTables pt, const __grid_constant__
                const GroupDesc *__restrict__ groups, const uint32_t *__restrict__ goff, const uint16_t *__restrict__ loc,
                int channels, const int32_t *__restrict__ coefs, unsigned long long *__restrict__ sums)
 {
-    __shared__ uint16_t s_lut[kTileLeaves];
-    __shared__ short2 s_off[kTileLeaves];
     __shared__ unsigned long long s_part[8][kFitTerms];
-    for (int i = threadIdx.x; i < kTileLeaves; i += blockDim.x) {
-        s_lut[i] = pt.lut[i];
-        s_off[i] = pt.off[i];
-    }
-    __syncthreads();
-    const Lookup L{pt, s_lut, s_off};
     const GroupDesc gd = groups[blockIdx.x];
     const uint32_t k0 = goff[blockIdx.x], k1 = goff[blockIdx.x + 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int ch = 0; ch < channels; ++ch) {
-        auto coef_at = [&](int tile, int heap) { return __ldg(coefs + (((size_t)tile * channels + ch) << kBaseDepth) + heap); };
+        const int32_t *cc = coefs + (ch << kBaseDepth);
 #pragma unroll 1
         for (int set = 0; set < 3; ++set) {
             const float *vp = prm.value[ch][set];
@@ -230,10 +198,12 @@ fri_fit_kernel(const __grid_constant__ PredictTables pt, const __grid_constant__
                 const int level = 31 - __clz(heap);
                 if ((level < kBaseDepth - 2 ? 2 : (level == kBaseDepth - 2 ? 1 : 0)) != set) continue;
                 const int tile = (int)gd.tile_base + (int)(l >> kBaseDepth);
-                const int cx = __ldg(pt.centers + 2 * tile), cy = __ldg(pt.centers + 2 * tile + 1);
-                int v[6];
-                hf_neighbour_values(L, cx, cy, heap, level, coef_at, v);
-                const int value = coef_at(tile, heap);
+                int off[6], v[6];
+                if (channels == 3) neighbour_offsets<3>(pt, tile, heap, off);
+                else neighbour_offsets<1>(pt, tile, heap, off);
+#pragma unroll
+                for (int j = 0; j < 6; ++j) v[j] = off[j] >= 0 ? __ldg(cc + off[j]) : 0;
+                const int value = __ldg(cc + ((tile * channels) << kBaseDepth) + heap);
                 long long w[6], y;
                 if (!WIDTH) {
 #pragma unroll
@@ -279,7 +249,9 @@ fri_fit_kernel(const __grid_constant__ PredictTables pt, const __grid_constant__
 
 cudaError_t configure_predict_kernel()
 {
-    return cudaFuncSetAttribute(fri_predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kContexts * kAlphabet * (int)sizeof(uint32_t));
+    cudaError_t e = cudaFuncSetAttribute(fri_predict_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kContexts * kAlphabet * (int)sizeof(uint32_t));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(fri_predict_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * kContexts * kAlphabet * (int)sizeof(uint32_t));
 }
 
 cudaError_t launch_predict(const Geometry &g, const DeviceTables &t, const EmitTables &et, const PredictTables &pt,
@@ -288,15 +260,20 @@ cudaError_t launch_predict(const Geometry &g, const DeviceTables &t, const EmitT
                            uint32_t *d_hist, uint32_t *d_overflow, cudaStream_t stream, uint32_t *launches)
 {
     if (count == 0 || n_frames == 0 || g.n_groups == 0) return cudaSuccess;
-    const size_t smem = (size_t)kContexts * kAlphabet * sizeof(uint32_t);
+    if (g.channels != 1 && g.channels != 3) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)g.channels * kContexts * kAlphabet * sizeof(uint32_t);
     for (uint32_t f0 = 0; f0 < n_frames; f0 += 65535u) {  // gridDim.y limit
         const uint32_t nf = n_frames - f0 < 65535u ? n_frames - f0 : 65535u;
         const dim3 grid((unsigned)g.n_groups, nf);
         const size_t so = (size_t)f0 * g.channels * count;
-        fri_predict_kernel<<<grid, 256, smem, stream>>>(pt, prm, t.groups, et.goff, et.dst, et.loc, count, g.channels, g.n_fractals,
-                                                        d_coefs + (int64_t)f0 * g.coefs_per_frame, d_bucket + so, d_pred + so,
-                                                        d_sym + so, d_hist + (size_t)f0 * g.channels * kContexts * kAlphabet,
-                                                        d_overflow);
+        const int32_t *fc = d_coefs + (int64_t)f0 * g.coefs_per_frame;
+        uint32_t *fh = d_hist + (size_t)f0 * g.channels * kContexts * kAlphabet;
+        if (g.channels == 1)
+            fri_predict_kernel<1><<<grid, kPredictThreads, smem, stream>>>(pt, prm, t.groups, et.goff, et.dst, et.loc, count, g.n_fractals, fc,
+                                                                         d_bucket + so, d_pred ? d_pred + so : nullptr, d_sym + so, fh, d_overflow);
+        else
+            fri_predict_kernel<3><<<grid, kPredictThreads, smem, stream>>>(pt, prm, t.groups, et.goff, et.dst, et.loc, count, g.n_fractals, fc,
+                                                                         d_bucket + so, d_pred ? d_pred + so : nullptr, d_sym + so, fh, d_overflow);
         if (launches) ++*launches;
     }
     return cudaGetLastError();
