@@ -534,9 +534,9 @@ static int decode_device(const fri_plan *cp, const void *d_coefs, bool half, uin
 
 /* ---- one image split over several GPUs by ranges of tile groups -------------------------- */
 struct Part {
-    int g0, g1;         // groups [g0, g1)
-    int64_t t0, t1;     // tiles [t0, t1) in plan order: the coefficient blocks the part produces / consumes
-    int row0, row1;     // pixel rows [row0, row1) the part's groups read (encode) or write into (decode)
+    int g0 = 0, g1 = 0;       // groups [g0, g1)
+    int64_t t0 = 0, t1 = 0;   // tiles [t0, t1) in plan order: the coefficient blocks the part produces / consumes
+    int row0 = 0, row1 = 0;   // pixel rows [row0, row1) the part's groups read (encode) or write into (decode)
 };
 
 static int plan_part(const fri_plan *p, uint32_t part, uint32_t n_parts, Part &out)
